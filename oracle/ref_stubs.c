@@ -1,0 +1,5 @@
+/* TEST INFRASTRUCTURE ONLY.  libbwaref.so leaves out the reference's main.c (a shared
+ * library should not define main); this supplies the one other symbol main.c owns
+ * (main.c:43-46) so the library has no undefined references. */
+#include <stdio.h>
+void bwa_print_sam_PG(void) { printf("@PG\tID:bwa\tPN:bwa\tVN:oracle-ref\n"); }

@@ -1,0 +1,217 @@
+/* bwa_gpu.h -- C-ABI of the B200-native `bwa aln` hot path (libbwagpu.so).
+ *
+ * The reference (mpieva/network-aware-bwa) has no plugin/FFI interface: the seam is the
+ * set of plain C calls bam2bam.c's phase functions make into the alignment layer, one
+ * record at a time.  Each entry point below is the BATCH form of one of those calls and
+ * cites the call it replaces.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Conventions:
+ *   - return 0 on success, non-zero on error (bwa_gpu_last_error() has the text); the
+ *     reference itself never returns errors on this path (xassert -> abort, utils.c:68-83),
+ *     so a reference-style caller should abort() on non-zero;
+ *   - there is NO CPU fallback: every entry point fails if no sm_100 device is usable;
+ *   - arrays handed back inside reference structs (bwa_seq_t.aln) are libc calloc()'d,
+ *     because bwa_free_read_seq1 (bwaseqio.c:253-261) free()s them.
+ *
+ * Including this header AFTER the reference's bwtaln.h re-uses the reference's own
+ * types; stand-alone it declares layout-identical mirrors (sizes checked at compile
+ * time below and against the real headers in tests/test_abi.py).
+ */
+#ifndef BWA_GPU_H
+#define BWA_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if !defined(BWTALN_H)
+/* ---- mirrors of the reference's types (only when its headers are not in scope) ---- */
+#ifndef BWA_UBYTE
+#define BWA_UBYTE
+typedef unsigned char ubyte_t;
+#endif
+#ifndef BWA_BWT_H
+typedef uint32_t bwtint_t; /* bwt.h:41 */
+
+/* bwt.h:43-59 (non-mmap build, the Makefile default) */
+typedef struct {
+	bwtint_t primary;
+	bwtint_t L2[5];
+	bwtint_t seq_len;
+	bwtint_t bwt_size;
+	uint32_t *bwt;
+	uint32_t cnt_table[256];
+	int sa_intv;
+	bwtint_t n_sa;
+	bwtint_t *sa;
+} bwt_t;
+#endif
+
+/* bwtaln.h:43-47 -- also the .sai record and a 0MQ wire format (bam2bam.c:1001) */
+typedef struct {
+	uint32_t n_mm : 8, n_gapo : 8, n_gape : 8, a : 1;
+	bwtint_t k, l;
+	int score;
+} bwt_aln1_t;
+
+typedef uint16_t bwa_cigar_t; /* bwtaln.h:49 */
+
+/* bwtaln.h:58-62 */
+typedef struct {
+	uint32_t pos;
+	uint32_t n_cigar : 15, gap : 8, mm : 8, strand : 1;
+	bwa_cigar_t *cigar;
+} bwt_multi1_t;
+
+/* bwtaln.h:64-90 */
+typedef struct {
+	char *name;
+	ubyte_t *seq, *rseq, *qual;
+	uint32_t len : 20, strand : 1, type : 2, dummy : 1, extra_flag : 8;
+	uint32_t n_mm : 8, n_gapo : 8, n_gape : 8, mapQ : 8;
+	int score;
+	int clip_len;
+	int n_aln;
+	bwt_aln1_t *aln;
+	int n_multi;
+	bwt_multi1_t *multi;
+	bwtint_t sa, pos;
+	uint64_t c1 : 28, c2 : 28, seQ : 8;
+	int n_cigar;
+	bwa_cigar_t *cigar;
+	int tid;
+	char bc[64];
+	uint32_t full_len : 20, nm : 12;
+	char *md;
+	int max_entries;
+} bwa_seq_t;
+
+/* bwtaln.h:143-153; defaults gap_init_opt bwtaln.c:19-35 */
+typedef struct {
+	int s_mm, s_gapo, s_gape;
+	int mode;
+	int indel_end_skip, max_del_occ, max_entries;
+	float fnr;
+	int max_diff, max_gapo, max_gape;
+	int max_seed_diff, seed_len;
+	int n_threads;
+	int max_top2;
+	int trim_qual;
+} gap_opt_t;
+
+#define BWA_MODE_GAPE 0x01
+#define BWA_MODE_COMPREAD 0x02
+#define BWA_MODE_LOGGAP 0x04
+#define BWA_MODE_NONSTOP 0x10
+#endif /* !BWTALN_H */
+
+#if defined(__cplusplus) && __cplusplus >= 201103L
+static_assert(sizeof(bwt_aln1_t) == 16, "bwt_aln1_t ABI");
+static_assert(sizeof(bwt_multi1_t) == 16, "bwt_multi1_t ABI");
+static_assert(sizeof(bwa_seq_t) == 200, "bwa_seq_t ABI");
+static_assert(sizeof(gap_opt_t) == 64, "gap_opt_t ABI");
+#endif
+
+/* ------------------------------------------------------------------ lifetime */
+
+/* One context (stream set, scratch arenas) per listed CUDA device.  n_devices <= 0 or
+ * device_ids == NULL means "device 0 only".  Replaces nothing in the reference (it has
+ * no device); sits where init_genome_index (bam2bam.c:844-868) is called. */
+int bwa_gpu_init(int n_devices, const int *device_ids);
+
+/* Upload both strands' FM-index and re-lay it out for HBM (32-byte blocks of 4 counts +
+ * 64 bases as two bit planes), replicated on every device of the context.
+ * bwt[0] = forward (.bwt/.sa), bwt[1] = reverse (.rbwt/.rsa), exactly the globals of
+ * bam2bam.c:88-91 after bwt_restore_bwt/bwt_restore_sa (bam2bam.c:848-861).  sa may be
+ * NULL (then bwa_gpu_cal_pac_pos fails); pac may be NULL (then bwa_gpu_mate_sw fails).
+ * The host arrays are not referenced after the call returns. */
+int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64_t l_pac);
+
+void bwa_gpu_destroy(void);
+
+const char *bwa_gpu_last_error(void);
+
+/* ------------------------------------------------------------------ K2 + K3: gapped search
+ * Batch form of   bwa_cal_sa_reg_gap(bwt, 1, &seqs[i], opt)   for i in [0, n_seqs)
+ * (bwtaln.c:93-142 as called from bam2bam.c:616 and 676: PER-READ semantics -- max_diff,
+ * the max_gapo clamp and the seed switch are derived from each read's own length).
+ * Reads  seqs[i].{seq, rseq, len};  writes {n_aln, aln (calloc'd), max_entries} and resets
+ * sa/type/c1/c2 like bwtaln.c:113.  The aln list is byte-identical to the reference's,
+ * order included. */
+int bwa_gpu_cal_sa_reads_gap(int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt);
+
+/* Flat form of the same call for batch drivers that do not keep bwa_seq_t around.
+ * bases[offs[i] .. offs[i+1]) is read i in sequencing orientation, codes 0..3 = ACGT,
+ * 4 = N (bwaseqio.c:10); the library derives seq (reversed) and rseq (reverse complement)
+ * as bam1_to_seq does (bwaseqio.c:294-297).  Outputs (caller-allocated): n_aln[n],
+ * max_entries[n] (0 when the search never started: len == 0 or too many N), aln_off[n+1]
+ * (prefix sums of n_aln).  *aln_pool receives a library-owned pinned host array of
+ * aln_off[n] records in read order, valid until the next call on this context. */
+int bwa_gpu_aln_flat(int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt,
+                     int32_t *n_aln, int32_t *max_entries, int64_t *aln_off,
+                     const bwt_aln1_t **aln_pool);
+
+/* ------------------------------------------------------------------ K4: SA -> coordinate
+ * Batch form of the raw bwt_sa() calls (bwt.c:72-81) at bwase.c:145,152 and
+ * bam2bam.c:635-636, 752, 761, 786.  which[i] != 0 selects the forward index (bwt[0]),
+ * 0 the reverse index (bwt[1]).  out[i] = bwt_sa(bwt[which ? 0 : 1], sa_idx[i]), the raw
+ * u32 value; the caller applies  pos = strand ? out : seq_len - (out + len)  (bwase.c:144-153). */
+int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint8_t *which, bwtint_t *out_sa);
+
+/* ------------------------------------------------------------------ K5: mate-rescue SW
+ * Batch form of the aln_local_core(ref, l, seq, len, &aln_param_bwa, path, &path_len, 1, 0)
+ * call inside bwa_sw_core (bwape.c:456; stdaln.c:529-761): local affine-gap alignment of
+ * seq[0..len) against the pac window [beg, beg+reglen).  score/end_* are the forward
+ * pass's first arg-max in (read row, ref column) scan order (stdaln.c:623-625); start_*
+ * come from the reverse pass (stdaln.c:651-696).  Coordinates are 1-based like path_t. */
+typedef struct {
+	int64_t beg;        /* first reference base of the window (pac coordinate) */
+	int32_t reglen;     /* window length (l in bwape.c:447-456) */
+	int32_t len;        /* read length */
+	const ubyte_t *seq; /* read bases 0..4, orientation as bwa_sw_core receives it */
+} bwa_gpu_sw_job_t;
+
+typedef struct {
+	int32_t score;
+	int32_t start_i, start_j; /* ref, read: 1-based start of the local alignment */
+	int32_t end_i, end_j;     /* ref, read: 1-based end */
+} bwa_gpu_sw_res_t;
+
+int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_res_t *res);
+
+/* ------------------------------------------------------------------ measurement hooks
+ * Device-side timing (CUDA events on the library's own streams) and work counters of the
+ * most recent batch call, summed over its chunks.  occ_fetches counts occurrence-block
+ * fetches the way the REFERENCE layout needs them (1 when both ends fall in one 128-base
+ * block, else 2: bwt.c:127,189) -- the algorithmic-bytes unit of SURVEY.md §8(d). */
+typedef struct {
+	double ms_h2d, ms_width, ms_search, ms_compact, ms_d2h, ms_total_device;
+	double ms_host_marshal;
+	int64_t n_reads, n_aln, n_overflow_t2, n_overflow_t3;
+	int64_t occ_fetches_width, occ_fetches_search; /* filled only when stats are enabled */
+	int64_t own_fetches_width, own_fetches_search; /* 32-byte blocks this layout touched */
+	int64_t n_pops, n_pushes;
+	int32_t launches; /* kernels launched by the call */
+	int32_t n_devices;
+} bwa_gpu_stats_t;
+
+int bwa_gpu_get_stats(bwa_gpu_stats_t *out);
+/* 0 = off (default, the timed configuration), 1 = count fetches/pops/pushes in-kernel */
+int bwa_gpu_set_stats(int enabled);
+
+/* Device-resident variant used for kernel-only throughput: stage a flat batch in HBM
+ * once, then run K2+K3 over it repeatedly without host traffic.  run returns the device
+ * time of that pass in *ms (CUDA events).  Results stay on the device; fetch copies the
+ * last pass's results out in bwa_gpu_aln_flat's output format. */
+int bwa_gpu_resident_stage(int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt);
+int bwa_gpu_resident_run(double *ms);
+int bwa_gpu_resident_fetch(int32_t *n_aln, int32_t *max_entries, int64_t *aln_off,
+                           const bwt_aln1_t **aln_pool);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BWA_GPU_H */

@@ -1,0 +1,160 @@
+"""Python binding of the C-ABI (include/bwa_gpu.h) -- ctypes over libbwagpu.so.
+
+This is the stub a host in another language would write (INTEGRATION.md shows the C
+version for bam2bam.c).  It adds nothing: every call goes straight to the library, and
+there is no fallback of any kind -- if the library is missing, cannot be loaded or finds no
+sm_100 device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .build import LIB
+
+
+class BwaGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise BwaGpuError(f"{LIB} is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB)
+        L.bwa_gpu_last_error.restype = C.c_char_p
+        L.bwa_gpu_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.bwa_gpu_load_index.argtypes = [C.POINTER(C.POINTER(abi.bwt_t)), C.c_void_p, C.c_int64]
+        L.bwa_gpu_destroy.restype = None
+        L.bwa_gpu_cal_sa_reads_gap.argtypes = [C.c_int, C.POINTER(abi.bwa_seq_t), C.POINTER(abi.gap_opt_t)]
+        L.bwa_gpu_aln_flat.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t), C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bwa_gpu_cal_pac_pos.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bwa_gpu_mate_sw.argtypes = [C.c_int, C.POINTER(abi.sw_job_t), C.POINTER(abi.sw_res_t)]
+        L.bwa_gpu_get_stats.argtypes = [C.POINTER(abi.stats_t)]
+        L.bwa_gpu_set_stats.argtypes = [C.c_int]
+        L.bwa_gpu_resident_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t)]
+        L.bwa_gpu_resident_run.argtypes = [C.POINTER(C.c_double)]
+        L.bwa_gpu_resident_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib = L
+    return _lib
+
+
+EXPORTS = [
+    "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_destroy", "bwa_gpu_last_error",
+    "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw",
+    "bwa_gpu_get_stats", "bwa_gpu_set_stats",
+    "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
+]
+
+
+def _ck(rc: int) -> None:
+    if rc != 0:
+        raise BwaGpuError(lib().bwa_gpu_last_error().decode())
+
+
+def init(device_ids=None) -> None:
+    if device_ids is None:
+        _ck(lib().bwa_gpu_init(0, None))
+    else:
+        arr = (C.c_int * len(device_ids))(*device_ids)
+        _ck(lib().bwa_gpu_init(len(device_ids), arr))
+
+
+def destroy() -> None:
+    lib().bwa_gpu_destroy()
+
+
+def load_index(idx) -> None:
+    """idx: index.FMIndex (host arrays in the reference's layout)."""
+    t0, t1 = abi.make_bwt_t(idx.bwt[0]), abi.make_bwt_t(idx.bwt[1])
+    arr = (C.POINTER(abi.bwt_t) * 2)(C.pointer(t0), C.pointer(t1))
+    pac = np.ascontiguousarray(idx.pac)
+    _ck(lib().bwa_gpu_load_index(arr, pac.ctypes.data, idx.l_pac))
+
+
+def cal_sa_reads_gap(seqs, opt) -> None:
+    """seqs: ctypes array of abi.bwa_seq_t; filled in place like bwa_cal_sa_reg_gap."""
+    _ck(lib().bwa_gpu_cal_sa_reads_gap(len(seqs), seqs, C.byref(opt)))
+
+
+def _wrap_pool(ptr, n):
+    if n == 0:
+        return np.empty(0, dtype=abi.ALN_DTYPE)
+    buf = (C.c_char * (16 * n)).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=abi.ALN_DTYPE, count=n).copy()
+
+
+def aln_flat(bases: np.ndarray, offs: np.ndarray, opt):
+    """-> (n_aln int32[n], max_entries int32[n], aln_off int64[n+1], aln structured[n_total])"""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    n = offs.size - 1
+    n_aln = np.empty(n, dtype=np.int32)
+    max_entries = np.empty(n, dtype=np.int32)
+    aln_off = np.empty(n + 1, dtype=np.int64)
+    pool = C.c_void_p()
+    _ck(lib().bwa_gpu_aln_flat(n, bases.ctypes.data, offs.ctypes.data, C.byref(opt), n_aln.ctypes.data,
+                               max_entries.ctypes.data, aln_off.ctypes.data, C.byref(pool)))
+    return n_aln, max_entries, aln_off, _wrap_pool(pool, int(aln_off[n]))
+
+
+def cal_pac_pos(sa_idx: np.ndarray, which: np.ndarray) -> np.ndarray:
+    sa_idx = np.ascontiguousarray(sa_idx, dtype=np.uint32)
+    which = np.ascontiguousarray(which, dtype=np.uint8)
+    out = np.empty(sa_idx.size, dtype=np.uint32)
+    _ck(lib().bwa_gpu_cal_pac_pos(sa_idx.size, sa_idx.ctypes.data, which.ctypes.data, out.ctypes.data))
+    return out
+
+
+def mate_sw(jobs):
+    """jobs: list of (beg, reglen, seq uint8 array) -> list of (score, start_i, start_j, end_i, end_j)"""
+    n = len(jobs)
+    arr = (abi.sw_job_t * n)()
+    keep = []
+    for i, (beg, reglen, seq) in enumerate(jobs):
+        s = np.ascontiguousarray(seq, dtype=np.uint8)
+        keep.append(s)
+        arr[i].beg, arr[i].reglen, arr[i].len = beg, reglen, s.size
+        arr[i].seq = s.ctypes.data_as(C.POINTER(C.c_ubyte))
+    res = (abi.sw_res_t * n)()
+    _ck(lib().bwa_gpu_mate_sw(n, arr, res))
+    return [(r.score, r.start_i, r.start_j, r.end_i, r.end_j) for r in res]
+
+
+def set_stats(enabled: bool) -> None:
+    _ck(lib().bwa_gpu_set_stats(1 if enabled else 0))
+
+
+def get_stats() -> dict:
+    s = abi.stats_t()
+    _ck(lib().bwa_gpu_get_stats(C.byref(s)))
+    return s.asdict()
+
+
+def resident_stage(bases: np.ndarray, offs: np.ndarray, opt) -> None:
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    _ck(lib().bwa_gpu_resident_stage(offs.size - 1, bases.ctypes.data, offs.ctypes.data, C.byref(opt)))
+
+
+def resident_run() -> float:
+    ms = C.c_double()
+    _ck(lib().bwa_gpu_resident_run(C.byref(ms)))
+    return ms.value
+
+
+def resident_fetch(n: int):
+    n_aln = np.empty(n, dtype=np.int32)
+    max_entries = np.empty(n, dtype=np.int32)
+    aln_off = np.empty(n + 1, dtype=np.int64)
+    pool = C.c_void_p()
+    _ck(lib().bwa_gpu_resident_fetch(n_aln.ctypes.data, max_entries.ctypes.data, aln_off.ctypes.data, C.byref(pool)))
+    return n_aln, max_entries, aln_off, _wrap_pool(pool, int(aln_off[n]))

@@ -1,0 +1,748 @@
+// bwagpu.cu -- host side of libbwagpu.so: the C-ABI of include/bwa_gpu.h.
+//
+// One Ctx per CUDA device (its own stream, scratch arenas, pinned staging).  A batch call
+// splits the reads into contiguous per-device ranges (index replicated, no collective:
+// SURVEY.md §8e), each range into chunks, and runs per chunk
+//     H2D -> K2 width -> K3 search (tier 1 [-> tier 2 -> tier 3] for reads whose stack or
+//     hit list outgrew the tier) -> scan + gather (read-ordered aln pool) -> D2H.
+// There is no CPU fallback: without a usable device every entry point returns an error.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bwa_gpu.h"
+#include "kernels.cuh"
+#include "sw.cuh"
+#include "hostprep.h"
+
+using namespace bwagpu;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string t_err;
+static std::string g_err;
+static std::mutex g_err_mu;
+
+static int fail(const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	t_err = buf;
+	std::lock_guard<std::mutex> g(g_err_mu);
+	g_err = buf;
+	return 1;
+}
+
+#define CK(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+namespace bwagpu {
+int hostprep_fail(const char *fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	return fail("%s", buf);
+}
+}
+
+extern "C" const char *bwa_gpu_last_error(void)
+{
+	std::lock_guard<std::mutex> g(g_err_mu);
+	return g_err.c_str();
+}
+
+// ------------------------------------------------------------------ buffers
+template <typename T> struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t n)
+	{
+		if (n <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+		if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T> struct PinBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t n, bool keep = false)
+	{
+		if (n <= cap) return 0;
+		size_t want = n + n / 4 + 256;
+		T *q = nullptr;
+		cudaError_t e = cudaMallocHost((void **)&q, want * sizeof(T));
+		if (e != cudaSuccess) return fail("cudaMallocHost(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+		if (p) { if (keep) memcpy(q, p, cap * sizeof(T)); cudaFreeHost(p); }
+		p = q; cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Tier {
+	uint32_t cap, aln_cap, slots_blocks; // slots = blocks * 128
+	DevBuf<uint4> ent;
+	DevBuf<uint32_t> nxt, heads;
+	DevBuf<uint4> alnbuf;
+};
+
+struct Ctx {
+	int dev = 0;
+	int n_sm = 0;
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev[8] = {};
+	// index
+	DevIndex ix[2] = {};
+	DevBuf<uint4> blk[2];
+	DevBuf<uint32_t> sa[2];
+	DevBuf<uint8_t> pac;
+	int64_t l_pac = 0;
+	bool has_index = false, has_sa = false, has_pac = false;
+	// chunk inputs / outputs on device
+	DevBuf<uint8_t> d_seq;
+	DevBuf<ReadMeta> d_meta;
+	DevBuf<uint32_t> d_w;
+	DevBuf<uint16_t> d_bid;
+	DevBuf<int32_t> d_naln, d_maxent, d_jobs_a, d_jobs_b;
+	DevBuf<uint32_t> d_pooloff, d_outoff;
+	DevBuf<uint4> d_pool, d_out;
+	DevBuf<int> d_counters;            // [0] work [1] overflow [2] pool_count(u32)
+	DevBuf<unsigned long long> d_stats; // 4
+	DevBuf<uint8_t> d_cubtmp;
+	Tier tier[3];
+	// pinned staging
+	PinBuf<uint8_t> h_seq;
+	PinBuf<ReadMeta> h_meta;
+	PinBuf<int32_t> h_naln, h_maxent;
+	PinBuf<uint4> h_out;
+	PinBuf<int> h_counters;
+	// K4 / K5 staging
+	DevBuf<uint32_t> d_q, d_qo;
+	DevBuf<uint8_t> d_which;
+	// resident batch
+	int res_n = 0;
+	size_t res_w_entries = 0;
+	GapOpt res_opt = {};
+	uint32_t res_nstacks = 0;
+	bool res_valid = false;
+	int64_t res_total_aln = 0;
+	// per-call stats
+	bwa_gpu_stats_t stats = {};
+};
+
+static std::vector<Ctx *> g_ctx;
+static bool g_stats_enabled = false;
+static std::mutex g_mu;
+static std::vector<uint4> g_flat_pool; // result pool of the last flat call (multi-device concat)
+
+// ------------------------------------------------------------------ lifetime
+extern "C" void bwa_gpu_destroy(void)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	for (Ctx *c : g_ctx) {
+		cudaSetDevice(c->dev);
+		cudaDeviceSynchronize();
+		for (int s = 0; s < 2; ++s) { c->blk[s].release(); c->sa[s].release(); }
+		c->pac.release();
+		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release();
+		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release();
+		c->d_pooloff.release(); c->d_outoff.release(); c->d_pool.release(); c->d_out.release();
+		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
+		for (Tier &t : c->tier) { t.ent.release(); t.nxt.release(); t.heads.release(); t.alnbuf.release(); }
+		c->h_seq.release(); c->h_meta.release(); c->h_naln.release(); c->h_maxent.release(); c->h_out.release();
+		c->h_counters.release();
+		c->d_q.release(); c->d_qo.release(); c->d_which.release();
+		for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+		if (c->st) cudaStreamDestroy(c->st);
+		delete c;
+	}
+	g_ctx.clear();
+	std::vector<uint4>().swap(g_flat_pool);
+}
+
+extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
+{
+	bwa_gpu_destroy();
+	std::lock_guard<std::mutex> g(g_mu);
+	int have = 0;
+	cudaError_t e = cudaGetDeviceCount(&have);
+	if (e != cudaSuccess || have == 0)
+		return fail("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+	std::vector<int> ids;
+	if (n_devices <= 0 || !device_ids) ids.push_back(0);
+	else ids.assign(device_ids, device_ids + n_devices);
+	for (int id : ids) {
+		if (id < 0 || id >= have) return fail("device id %d out of range (have %d)", id, have);
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, id));
+		if (prop.major < 10) return fail("device %d is sm_%d%d; libbwagpu is built for sm_100a only", id, prop.major, prop.minor);
+		CK(cudaSetDevice(id));
+		Ctx *c = new Ctx();
+		c->dev = id;
+		c->n_sm = prop.multiProcessorCount;
+		CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+		for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+		g_ctx.push_back(c);
+	}
+	return 0;
+}
+
+static int upload_index_one(Ctx *c, bwt_t *const bwt[2], const ubyte_t *pac, int64_t l_pac)
+{
+	CK(cudaSetDevice(c->dev));
+	c->has_sa = true;
+	for (int s = 0; s < 2; ++s) {
+		const bwt_t *b = bwt[s];
+		if (!b || !b->bwt) return fail("bwa_gpu_load_index: bwt[%d] is not loaded", s);
+		const uint32_t n_blk = (b->seq_len >> 6) + 1;
+		DevBuf<uint32_t> raw;
+		if (raw.reserve(b->bwt_size)) return 1;
+		CK(cudaMemcpyAsync(raw.p, b->bwt, (size_t)b->bwt_size * 4, cudaMemcpyHostToDevice, c->st));
+		if (c->blk[s].reserve(2 * (size_t)n_blk)) return 1;
+		k_relayout<<<(n_blk + 255) / 256, 256, 0, c->st>>>(raw.p, b->seq_len, n_blk, c->blk[s].p, b->L2[1] - b->L2[0],
+		                                                   b->L2[2] - b->L2[1], b->L2[3] - b->L2[2], b->L2[4] - b->L2[3]);
+		CK(cudaGetLastError());
+		DevIndex &ix = c->ix[s];
+		ix.blk = c->blk[s].p;
+		ix.primary = b->primary; ix.seq_len = b->seq_len; ix.n_blk = n_blk;
+		for (int j = 0; j < 5; ++j) ix.L2[j] = b->L2[j];
+		ix.sa = nullptr; ix.n_sa = 0; ix.sa_intv = 32;
+		if (b->sa) {
+			if (b->sa_intv <= 0) return fail("bwt[%d].sa_intv = %d", s, b->sa_intv);
+			if (c->sa[s].reserve(b->n_sa)) return 1;
+			CK(cudaMemcpyAsync(c->sa[s].p, b->sa, (size_t)b->n_sa * 4, cudaMemcpyHostToDevice, c->st));
+			// sa[0] is never read on the host path either (bwt.c:80); make it well defined
+			const uint32_t m1 = 0xffffffffu;
+			CK(cudaMemcpyAsync(c->sa[s].p, &m1, 4, cudaMemcpyHostToDevice, c->st));
+			ix.sa = c->sa[s].p; ix.n_sa = b->n_sa; ix.sa_intv = (uint32_t)b->sa_intv;
+		} else c->has_sa = false;
+		CK(cudaStreamSynchronize(c->st));
+		raw.release();
+	}
+	c->has_pac = false;
+	if (pac && l_pac > 0) {
+		const size_t nb = (size_t)(l_pac / 4 + 1);
+		if (c->pac.reserve(nb)) return 1;
+		CK(cudaMemcpyAsync(c->pac.p, pac, nb, cudaMemcpyHostToDevice, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		c->l_pac = l_pac;
+		c->has_pac = true;
+	}
+	c->has_index = true;
+	c->res_valid = false;
+	return 0;
+}
+
+extern "C" int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64_t l_pac)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_load_index: call bwa_gpu_init first");
+	if (bwt[0]->seq_len != bwt[1]->seq_len) return fail("forward and reverse index differ in seq_len");
+	for (Ctx *c : g_ctx)
+		if (upload_index_one(c, bwt, pac, l_pac)) return 1;
+	return 0;
+}
+
+extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
+
+// ------------------------------------------------------------------ device pipeline for one resident chunk
+static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt)
+{
+	Tier &T = c->tier[t];
+	if (t == 0) {
+		int bps = 0;
+		if (g_stats_enabled) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true>, 128, 0));
+		else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false>, 128, 0));
+		if (bps < 1) bps = 1;
+		const char *env = getenv("BWAGPU_T1_BLOCKS_PER_SM");
+		if (env && atoi(env) > 0) bps = std::min(bps, atoi(env));
+		T.slots_blocks = (uint32_t)(bps * c->n_sm);
+		env = getenv("BWAGPU_T1_CAP");
+		T.cap = env && atoi(env) > 0 ? (uint32_t)atoi(env) : 1024;
+		T.aln_cap = 64;
+	} else if (t == 1) {
+		T.slots_blocks = 64; // 8192 slots
+		T.cap = 65536; T.aln_cap = 4096;
+	} else {
+		T.slots_blocks = 2; // 256 slots
+		T.cap = max_entries_opt + 16; T.aln_cap = 1u << 18;
+	}
+	const size_t slots = (size_t)T.slots_blocks * 128;
+	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap) || T.heads.reserve(slots * n_stacks) ||
+	    T.alnbuf.reserve(slots * T.aln_cap))
+		return 1;
+	return 0;
+}
+
+// Runs K2 + K3(+tiers) + ordered compaction on a chunk whose seq/meta are on the device.
+// On return (stream synchronised): d_naln, d_maxent, d_outoff (exclusive scan), d_out
+// hold the results, *total_aln the pool size.
+static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, uint32_t n_stacks, int64_t *total_aln)
+{
+	const bool stats = g_stats_enabled;
+	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1)) return 1;
+	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
+		return 1;
+	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
+	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(4)) return 1;
+	size_t pool_cap = std::max<size_t>((size_t)n * 8, 1u << 20);
+	if (pool_cap > 0xfffffff0ull) pool_cap = 0xfffffff0ull;
+	if (c->d_pool.reserve(pool_cap)) return 1;
+
+	Batch B;
+	B.ix[0] = c->ix[0]; B.ix[1] = c->ix[1];
+	B.opt = opt;
+	B.n_reads = n;
+	B.seq = c->d_seq.p; B.meta = c->d_meta.p;
+	B.w = c->d_w.p; B.bid = c->d_bid.p;
+	B.n_aln = c->d_naln.p; B.max_entries = c->d_maxent.p; B.pool_off = c->d_pooloff.p;
+	B.pool = c->d_pool.p; B.pool_cap = (uint32_t)pool_cap;
+	B.pool_count = (unsigned int *)(c->d_counters.p + 2);
+	B.work_counter = c->d_counters.p; B.overflow_count = c->d_counters.p + 1;
+	B.stats = c->d_stats.p;
+	B.n_stacks = n_stacks;
+
+	CK(cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(int), c->st));
+	if (stats) CK(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st));
+
+	// K2
+	CK(cudaEventRecord(c->ev[1], c->st));
+	{
+		const long long threads = 4ll * n;
+		const int blocks = (int)((threads + 127) / 128);
+		if (blocks > 0) {
+			if (stats) k_width<true><<<blocks, 128, 0, c->st>>>(B);
+			else k_width<false><<<blocks, 128, 0, c->st>>>(B);
+			CK(cudaGetLastError());
+			c->stats.launches++;
+		}
+	}
+	CK(cudaEventRecord(c->ev[2], c->st));
+	if (stats) {
+		unsigned long long hs[4];
+		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		c->stats.occ_fetches_width += (int64_t)hs[0];
+		c->stats.own_fetches_width += (int64_t)hs[1];
+		CK(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st));
+	}
+
+	// K3, tier by tier
+	int n_jobs = n;
+	const int32_t *jobs = nullptr;
+	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
+		if (tier_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
+		Tier &T = c->tier[t];
+		B.ent = T.ent.p; B.nxt = T.nxt.p; B.heads = T.heads.p; B.alnbuf = T.alnbuf.p;
+		B.cap = T.cap; B.aln_cap = T.aln_cap;
+		B.jobs = jobs; B.n_jobs = n_jobs;
+		int32_t *ovf = (t & 1) ? c->d_jobs_b.p : c->d_jobs_a.p;
+		B.overflow_ids = ovf;
+		CK(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(int), c->st)); // work + overflow counters
+		uint32_t blocks = T.slots_blocks;
+		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
+		if (blocks > need) blocks = need;
+		if (stats) k_search<true><<<blocks, 128, 0, c->st>>>(B);
+		else k_search<false><<<blocks, 128, 0, c->st>>>(B);
+		CK(cudaGetLastError());
+		c->stats.launches++;
+		CK(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		const int n_over = c->h_counters.p[1];
+		const unsigned int pool_used = (unsigned int)c->h_counters.p[2];
+		if (pool_used > pool_cap) { // the shared pool ran out: grow it and rerun the flagged reads at this tier
+			return fail("aln pool overflow (%u > %zu records in one chunk); lower BWAGPU_CHUNK", pool_used, pool_cap);
+		}
+		if (t == 0) c->stats.n_overflow_t2 += n_over;
+		if (t == 1) c->stats.n_overflow_t3 += n_over;
+		if (n_over > 0 && t == 2)
+			return fail("%d reads exceeded the largest search tier (stack > max_entries+16 or > %u hits)", n_over, T.aln_cap);
+		jobs = ovf;
+		n_jobs = n_over;
+	}
+	CK(cudaEventRecord(c->ev[3], c->st));
+	if (stats) {
+		unsigned long long hs[4];
+		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaStreamSynchronize(c->st));
+		c->stats.occ_fetches_search += (int64_t)hs[0];
+		c->stats.own_fetches_search += (int64_t)hs[1];
+		c->stats.n_pops += (int64_t)hs[2];
+		c->stats.n_pushes += (int64_t)hs[3];
+	}
+
+	// ordered compaction: exclusive scan of n_aln (n+1 items so that out_off[n] = total)
+	CK(cudaMemsetAsync(c->d_naln.p + n, 0, sizeof(int32_t), c->st));
+	size_t tmp_bytes = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->d_naln.p, (int32_t *)c->d_outoff.p, n + 1, c->st));
+	if (c->d_cubtmp.reserve(tmp_bytes + 16)) return 1;
+	CK(cub::DeviceScan::ExclusiveSum(c->d_cubtmp.p, tmp_bytes, c->d_naln.p, (int32_t *)c->d_outoff.p, n + 1, c->st));
+	c->stats.launches += 2;
+	uint32_t tot = 0;
+	CK(cudaMemcpyAsync(&tot, c->d_outoff.p + n, 4, cudaMemcpyDeviceToHost, c->st));
+	CK(cudaStreamSynchronize(c->st));
+	if (c->d_out.reserve((size_t)tot + 1)) return 1;
+	if (n > 0) {
+		k_gather_aln<<<(n + 255) / 256, 256, 0, c->st>>>(n, c->d_naln.p, c->d_pooloff.p, c->d_outoff.p, c->d_pool.p, c->d_out.p);
+		CK(cudaGetLastError());
+		c->stats.launches++;
+	}
+	CK(cudaEventRecord(c->ev[4], c->st));
+	CK(cudaStreamSynchronize(c->st));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.ms_width += ms;
+	CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats.ms_search += ms;
+	CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats.ms_compact += ms;
+	*total_aln = tot;
+	return 0;
+}
+
+// ------------------------------------------------------------------ flat batch on one device
+struct FlatJob {
+	int n = 0;
+	const uint8_t *bases = nullptr;      // flat API: sequencing orientation
+	const int64_t *offs = nullptr;
+	bwa_seq_t *seqs = nullptr;           // struct API instead
+	const gap_opt_t *opt = nullptr;
+	int32_t *n_aln = nullptr, *max_entries = nullptr;
+	std::vector<uint4> pool;             // read-ordered alns of this range
+	int rc = 0;
+	std::string err;
+};
+
+static size_t chunk_reads()
+{
+	const char *env = getenv("BWAGPU_CHUNK");
+	size_t c = env ? (size_t)atoll(env) : 0;
+	return c > 0 ? c : (size_t)1 << 20;
+}
+
+static int run_range(Ctx *c, FlatJob &J)
+{
+	CK(cudaSetDevice(c->dev));
+	if (!c->has_index) return fail("no index loaded (bwa_gpu_load_index)");
+	const gap_opt_t *opt = J.opt;
+	const GapOpt gopt = to_gapopt(opt);
+	MaxDiffTable mdt;
+	const size_t CH = chunk_reads();
+	J.pool.clear();
+	for (size_t r0 = 0; r0 < (size_t)J.n; r0 += CH) {
+		const int n = (int)std::min(CH, (size_t)J.n - r0);
+		auto t0 = std::chrono::steady_clock::now();
+		// ---- marshal: pack bases, per-read meta
+		uint64_t n_bases = 0;
+		for (int i = 0; i < n; ++i)
+			n_bases += J.seqs ? J.seqs[r0 + i].len : (uint64_t)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
+		if (n_bases >= 0xffffffffull) return fail("chunk holds %llu bases; lower BWAGPU_CHUNK", (unsigned long long)n_bases);
+		if (c->h_seq.reserve(n_bases + 1) || c->h_meta.reserve(n)) return 1;
+		uint64_t so = 0, wo = 0;
+		uint32_t n_stacks = 1;
+		for (int i = 0; i < n; ++i) {
+			int len;
+			uint8_t *dst = c->h_seq.p + so;
+			if (J.seqs) {
+				const bwa_seq_t *p = J.seqs + r0 + i;
+				len = (int)p->len;
+				pack_seq_pair(dst, p->seq, p->rseq, len);
+			} else {
+				const uint8_t *src = J.bases + J.offs[r0 + i];
+				len = (int)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
+				pack_read(dst, src, len);
+			}
+			uint64_t we = 0;
+			if (fill_meta(len, so, wo, opt, mdt, c->h_meta.p[i], we, n_stacks)) return 1;
+			so += (uint64_t)len;
+			wo += we;
+			if (wo >= 0xffffffffull) return fail("width arena exceeds 2^32 entries; lower BWAGPU_CHUNK");
+		}
+		auto t1 = std::chrono::steady_clock::now();
+		c->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t1 - t0).count();
+		// ---- H2D
+		if (c->d_seq.reserve(n_bases + 1) || c->d_meta.reserve(n)) return 1;
+		CK(cudaEventRecord(c->ev[0], c->st));
+		CK(cudaMemcpyAsync(c->d_seq.p, c->h_seq.p, n_bases, cudaMemcpyHostToDevice, c->st));
+		CK(cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, (size_t)n * sizeof(ReadMeta), cudaMemcpyHostToDevice, c->st));
+		int64_t tot = 0;
+		if (run_chunk_device(c, n, (size_t)wo, gopt, n_stacks, &tot)) return 1;
+		// ---- D2H
+		if (c->h_naln.reserve(n) || c->h_maxent.reserve(n) || c->h_out.reserve((size_t)tot + 1)) return 1;
+		CK(cudaEventRecord(c->ev[5], c->st));
+		CK(cudaMemcpyAsync(c->h_naln.p, c->d_naln.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaMemcpyAsync(c->h_maxent.p, c->d_maxent.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+		if (tot) CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaEventRecord(c->ev[6], c->st));
+		CK(cudaStreamSynchronize(c->st));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.ms_h2d += ms;
+		CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->stats.ms_d2h += ms;
+		CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6])); c->stats.ms_total_device += ms;
+		auto t2 = std::chrono::steady_clock::now();
+		memcpy(J.n_aln + r0, c->h_naln.p, (size_t)n * 4);
+		memcpy(J.max_entries + r0, c->h_maxent.p, (size_t)n * 4);
+		const size_t base = J.pool.size();
+		J.pool.resize(base + (size_t)tot);
+		if (tot) memcpy(J.pool.data() + base, c->h_out.p, (size_t)tot * 16);
+		auto t3 = std::chrono::steady_clock::now();
+		c->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t3 - t2).count();
+		c->stats.n_reads += n;
+		c->stats.n_aln += tot;
+	}
+	return 0;
+}
+
+// splits [0,n) over the devices, one host thread per device
+static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *seqs, const gap_opt_t *opt,
+                   int32_t *n_aln, int32_t *max_entries, std::vector<FlatJob> &jobs)
+{
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
+	const int nd = (int)g_ctx.size();
+	jobs.assign(nd, FlatJob());
+	for (Ctx *c : g_ctx) { c->stats = bwa_gpu_stats_t(); c->stats.n_devices = nd; }
+	std::vector<std::thread> th;
+	for (int d = 0; d < nd; ++d) {
+		const int64_t lo = (int64_t)n * d / nd, hi = (int64_t)n * (d + 1) / nd;
+		FlatJob &J = jobs[d];
+		J.n = (int)(hi - lo);
+		J.opt = opt;
+		J.n_aln = n_aln + lo; J.max_entries = max_entries + lo;
+		if (seqs) J.seqs = seqs + lo;
+		else { J.bases = bases; J.offs = offs + lo; }
+		if (nd == 1) { J.rc = run_range(g_ctx[d], J); if (J.rc) J.err = t_err; }
+		else th.emplace_back([d, &jobs]() { FlatJob &Jd = jobs[d]; Jd.rc = run_range(g_ctx[d], Jd); if (Jd.rc) Jd.err = t_err; });
+	}
+	for (auto &t : th) t.join();
+	for (int d = 0; d < nd; ++d)
+		if (jobs[d].rc) return fail("device %d: %s", g_ctx[d]->dev, jobs[d].err.c_str());
+	return 0;
+}
+
+extern "C" int bwa_gpu_aln_flat(int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt, int32_t *n_aln,
+                                int32_t *max_entries, int64_t *aln_off, const bwt_aln1_t **aln_pool)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (n < 0 || !opt || !n_aln || !max_entries || !aln_off || !aln_pool) return fail("bwa_gpu_aln_flat: bad argument");
+	std::vector<FlatJob> jobs;
+	if (run_all(n, bases, offs, nullptr, opt, n_aln, max_entries, jobs)) return 1;
+	int64_t acc = 0;
+	for (int i = 0; i < n; ++i) { aln_off[i] = acc; acc += n_aln[i]; }
+	aln_off[n] = acc;
+	if (jobs.size() == 1) g_flat_pool.swap(jobs[0].pool);
+	else {
+		g_flat_pool.clear();
+		g_flat_pool.reserve((size_t)acc);
+		for (auto &J : jobs) g_flat_pool.insert(g_flat_pool.end(), J.pool.begin(), J.pool.end());
+	}
+	if ((int64_t)g_flat_pool.size() != acc) return fail("internal: pool size %zu != %lld", g_flat_pool.size(), (long long)acc);
+	*aln_pool = (const bwt_aln1_t *)g_flat_pool.data();
+	return 0;
+}
+
+extern "C" int bwa_gpu_cal_sa_reads_gap(int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (n_seqs < 0 || !opt || (n_seqs && !seqs)) return fail("bwa_gpu_cal_sa_reads_gap: bad argument");
+	std::vector<int32_t> n_aln(n_seqs), max_entries(n_seqs);
+	std::vector<FlatJob> jobs;
+	if (run_all(n_seqs, nullptr, nullptr, seqs, opt, n_aln.data(), max_entries.data(), jobs)) return 1;
+	auto t0 = std::chrono::steady_clock::now();
+	const int nd = (int)jobs.size();
+	for (int d = 0; d < nd; ++d) {
+		const int64_t lo = (int64_t)n_seqs * d / nd;
+		const uint4 *src = jobs[d].pool.data();
+		for (int i = 0; i < jobs[d].n; ++i) {
+			bwa_seq_t *p = seqs + lo + i;
+			const int na = n_aln[lo + i];
+			// bwtaln.c:113 resets these before the search
+			p->sa = 0; p->type = 0 /* BWA_TYPE_NO_MATCH */; p->c1 = p->c2 = 0;
+			p->n_aln = na;
+			if (p->len == 0) { p->aln = 0; continue; } // bwtaln.c:134
+			// bwt_match_gap always returns a calloc'd array of m_aln >= 4 records, grown by
+			// doubling (bwtgap.c:114-115,188-191); consumers free() it.
+			int m_aln = 4;
+			while (m_aln < na) m_aln <<= 1;
+			p->aln = (bwt_aln1_t *)calloc((size_t)m_aln, sizeof(bwt_aln1_t));
+			if (!p->aln) return fail("calloc failed");
+			if (na) memcpy(p->aln, src, (size_t)na * 16);
+			src += na;
+			if (max_entries[lo + i] > 0) p->max_entries = max_entries[lo + i]; // untouched when the search never ran (bwtgap.c:120-123)
+		}
+	}
+	auto t1 = std::chrono::steady_clock::now();
+	g_ctx[0]->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t1 - t0).count();
+	return 0;
+}
+
+extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
+{
+	if (!out) return fail("bwa_gpu_get_stats: null");
+	bwa_gpu_stats_t s = bwa_gpu_stats_t();
+	for (Ctx *c : g_ctx) {
+		const bwa_gpu_stats_t &t = c->stats;
+		// devices run concurrently: times are the max over devices, counters the sum
+		s.ms_h2d = std::max(s.ms_h2d, t.ms_h2d); s.ms_width = std::max(s.ms_width, t.ms_width);
+		s.ms_search = std::max(s.ms_search, t.ms_search); s.ms_compact = std::max(s.ms_compact, t.ms_compact);
+		s.ms_d2h = std::max(s.ms_d2h, t.ms_d2h); s.ms_total_device = std::max(s.ms_total_device, t.ms_total_device);
+		s.ms_host_marshal = std::max(s.ms_host_marshal, t.ms_host_marshal);
+		s.n_reads += t.n_reads; s.n_aln += t.n_aln; s.n_overflow_t2 += t.n_overflow_t2; s.n_overflow_t3 += t.n_overflow_t3;
+		s.occ_fetches_width += t.occ_fetches_width; s.occ_fetches_search += t.occ_fetches_search;
+		s.own_fetches_width += t.own_fetches_width; s.own_fetches_search += t.own_fetches_search;
+		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.launches += t.launches;
+	}
+	s.n_devices = (int32_t)g_ctx.size();
+	*out = s;
+	return 0;
+}
+
+// ------------------------------------------------------------------ resident batch (kernel-only timing)
+extern "C" int bwa_gpu_resident_stage(int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
+	Ctx *c = g_ctx[0];
+	CK(cudaSetDevice(c->dev));
+	if (!c->has_index) return fail("no index loaded");
+	MaxDiffTable mdt;
+	const uint64_t n_bases = (uint64_t)(offs[n] - offs[0]);
+	if (n_bases >= 0xffffffffull) return fail("resident batch too large (%llu bases)", (unsigned long long)n_bases);
+	if (c->h_seq.reserve(n_bases + 1) || c->h_meta.reserve(n)) return 1;
+	uint64_t so = 0, wo = 0;
+	uint32_t n_stacks = 1;
+	for (int i = 0; i < n; ++i) {
+		const uint8_t *src = bases + offs[i];
+		const int len = (int)(offs[i + 1] - offs[i]);
+		uint8_t *dst = c->h_seq.p + so;
+		pack_read(dst, src, len);
+		uint64_t we = 0;
+		if (fill_meta(len, so, wo, opt, mdt, c->h_meta.p[i], we, n_stacks)) return 1;
+		so += (uint64_t)len; wo += we;
+		if (wo >= 0xffffffffull) return fail("resident batch too large (width arena)");
+	}
+	if (c->d_seq.reserve(n_bases + 1) || c->d_meta.reserve(n)) return 1;
+	CK(cudaMemcpyAsync(c->d_seq.p, c->h_seq.p, n_bases, cudaMemcpyHostToDevice, c->st));
+	CK(cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, (size_t)n * sizeof(ReadMeta), cudaMemcpyHostToDevice, c->st));
+	CK(cudaStreamSynchronize(c->st));
+	c->res_n = n; c->res_w_entries = (size_t)wo; c->res_opt = to_gapopt(opt); c->res_nstacks = n_stacks;
+	c->res_valid = true;
+	return 0;
+}
+
+extern "C" int bwa_gpu_resident_run(double *ms)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called");
+	Ctx *c = g_ctx[0];
+	if (!c->res_valid) return fail("bwa_gpu_resident_run: nothing staged");
+	CK(cudaSetDevice(c->dev));
+	c->stats = bwa_gpu_stats_t();
+	c->stats.n_devices = 1;
+	CK(cudaEventRecord(c->ev[0], c->st));
+	int64_t tot = 0;
+	if (run_chunk_device(c, c->res_n, c->res_w_entries, c->res_opt, c->res_nstacks, &tot)) return 1;
+	CK(cudaEventRecord(c->ev[7], c->st));
+	CK(cudaStreamSynchronize(c->st));
+	float t = 0;
+	CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[7]));
+	c->stats.ms_total_device = t;
+	c->stats.n_reads = c->res_n;
+	c->stats.n_aln = tot;
+	c->res_total_aln = tot;
+	if (ms) *ms = t;
+	return 0;
+}
+
+extern "C" int bwa_gpu_resident_fetch(int32_t *n_aln, int32_t *max_entries, int64_t *aln_off, const bwt_aln1_t **aln_pool)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called");
+	Ctx *c = g_ctx[0];
+	if (!c->res_valid) return fail("bwa_gpu_resident_fetch: nothing staged");
+	CK(cudaSetDevice(c->dev));
+	const int n = c->res_n;
+	const int64_t tot = c->res_total_aln;
+	g_flat_pool.resize((size_t)tot);
+	CK(cudaMemcpy(n_aln, c->d_naln.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(max_entries, c->d_maxent.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	if (tot) CK(cudaMemcpy(g_flat_pool.data(), c->d_out.p, (size_t)tot * 16, cudaMemcpyDeviceToHost));
+	int64_t acc = 0;
+	for (int i = 0; i < n; ++i) { aln_off[i] = acc; acc += n_aln[i]; }
+	aln_off[n] = acc;
+	*aln_pool = (const bwt_aln1_t *)g_flat_pool.data();
+	return 0;
+}
+
+// ------------------------------------------------------------------ K4
+extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint8_t *which, bwtint_t *out_sa)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
+	if (n < 0 || (n && (!sa_idx || !which || !out_sa))) return fail("bwa_gpu_cal_pac_pos: bad argument");
+	const int nd = (int)g_ctx.size();
+	std::vector<int> rc(nd, 0);
+	std::vector<std::string> errs(nd);
+	auto work = [&](int d) -> int {
+		Ctx *c = g_ctx[d];
+		CK(cudaSetDevice(c->dev));
+		if (!c->has_index || !c->has_sa) return fail("no suffix array loaded (bwt->sa was NULL in bwa_gpu_load_index)");
+		const int64_t lo = n * d / nd, hi = n * (d + 1) / nd;
+		const int64_t CH = 1ll << 26;
+		for (int64_t r0 = lo; r0 < hi; r0 += CH) {
+			const int64_t m = std::min(CH, hi - r0);
+			if (c->d_q.reserve(m) || c->d_qo.reserve(m) || c->d_which.reserve(m)) return 1;
+			for (int64_t i = 0; i < m; ++i) {
+				const DevIndex &ix = c->ix[which[r0 + i] ? 0 : 1];
+				if (sa_idx[r0 + i] > ix.seq_len) return fail("sa_idx[%lld] = %u out of range", (long long)(r0 + i), sa_idx[r0 + i]);
+			}
+			CK(cudaMemcpyAsync(c->d_q.p, sa_idx + r0, (size_t)m * 4, cudaMemcpyHostToDevice, c->st));
+			CK(cudaMemcpyAsync(c->d_which.p, which + r0, (size_t)m, cudaMemcpyHostToDevice, c->st));
+			IndexPair P; P.ix[0] = c->ix[0]; P.ix[1] = c->ix[1];
+			k_sa<<<(unsigned)((m + 255) / 256), 256, 0, c->st>>>(P, m, c->d_q.p, c->d_which.p, c->d_qo.p);
+			CK(cudaGetLastError());
+			CK(cudaMemcpyAsync(out_sa + r0, c->d_qo.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->st));
+			CK(cudaStreamSynchronize(c->st));
+		}
+		return 0;
+	};
+	if (nd == 1) { if (work(0)) return 1; return 0; }
+	std::vector<std::thread> th;
+	for (int d = 0; d < nd; ++d) th.emplace_back([&, d]() { rc[d] = work(d); if (rc[d]) errs[d] = t_err; });
+	for (auto &t : th) t.join();
+	for (int d = 0; d < nd; ++d) if (rc[d]) return fail("device %d: %s", g_ctx[d]->dev, errs[d].c_str());
+	return 0;
+}
+
+// ------------------------------------------------------------------ K5
+extern "C" int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_res_t *res)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
+	if (n < 0 || (n && (!jobs || !res))) return fail("bwa_gpu_mate_sw: bad argument");
+	Ctx *c = g_ctx[0];
+	CK(cudaSetDevice(c->dev));
+	if (!c->has_pac) return fail("no packed reference loaded (pac was NULL in bwa_gpu_load_index)");
+	return sw_batch(c->st, c->pac.p, c->l_pac, n, jobs, res, fail);
+}

@@ -1,0 +1,94 @@
+// hostprep.h -- host-side preparation shared by the library (bwagpu.cu) and the CPU
+// kernel-logic emulation used by the tests (tests/host_emu/): the integer decisions the
+// reference takes in floating point, and the packing of a read into the device format.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include "../../include/bwa_gpu.h"
+#include "kernels.cuh"
+
+namespace bwagpu {
+
+int hostprep_fail(const char *fmt, ...); // provided by the including translation unit
+
+// ------------------------------------------------------------------ host-side integer decisions
+// bwa_cal_maxdiff (bwtaln.c:37-49): smallest k whose Poisson(l*err) tail drops below
+// thres.  Double arithmetic + libm exp on the HOST, as in the reference; the device only
+// ever sees the resulting integer.
+static inline int cal_maxdiff(int l, double err, double thres)
+{
+	double elambda = exp(-l * err);
+	double sum = elambda, y = 1.0;
+	int x = 1;
+	for (int k = 1; k < 1000; ++k) {
+		y *= l * err;
+		x *= k; // int, overflows for large k exactly like the reference's `int x`
+		sum += elambda * y / x;
+		if (1.0 - sum < thres) return k;
+	}
+	return 2;
+}
+
+struct MaxDiffTable {
+	float fnr = -1.f;
+	std::vector<int> tab;
+	int get(int len, const gap_opt_t *opt)
+	{
+		if (!(opt->fnr > 0.0)) return opt->max_diff;
+		if (fnr != opt->fnr) { fnr = opt->fnr; tab.assign(65536, -1); }
+		if (tab[len] < 0) tab[len] = cal_maxdiff(len, 0.02 /* BWA_AVG_ERR bwtaln.h:27 */, opt->fnr);
+		return tab[len];
+	}
+};
+
+static inline GapOpt to_gapopt(const gap_opt_t *o)
+{
+	GapOpt g;
+	g.s_mm = o->s_mm; g.s_gapo = o->s_gapo; g.s_gape = o->s_gape; g.mode = o->mode;
+	g.indel_end_skip = o->indel_end_skip; g.max_del_occ = o->max_del_occ; g.max_entries = o->max_entries;
+	g.max_gape = o->max_gape; g.max_seed_diff = o->max_seed_diff; g.seed_len = o->seed_len; g.max_top2 = o->max_top2;
+	return g;
+}
+
+// per-read meta (max_diff, clamped max_gapo: bwtaln.c:102-103 with n_seqs = 1) + offsets
+static inline int fill_meta(int len, uint64_t seq_off, uint64_t w_off, const gap_opt_t *opt, MaxDiffTable &mdt, ReadMeta &m,
+                     uint64_t &w_entries, uint32_t &n_stacks)
+{
+	if (len < 0 || len > 65534) return hostprep_fail("read length %d not supported (max 65534)", len);
+	int md = len > 0 ? mdt.get(len, opt) : 0;
+	int go = opt->max_gapo;
+	if (md < go) go = md;
+	if (md < 0 || md > 254 || go < 0 || go > 255 || opt->max_gape < 0 || opt->max_gape > 255)
+		return hostprep_fail("option range not supported on device: max_diff=%d max_gapo=%d max_gape=%d", md, go, opt->max_gape);
+	uint32_t ns = (uint32_t)((md + 1) * opt->s_mm + (go + 1) * opt->s_gapo + (opt->max_gape + 1) * opt->s_gape);
+	if (ns > 256) return hostprep_fail("score range %u exceeds 256 buckets (s_mm/s_gapo/s_gape/max_diff too large)", ns);
+	if (ns > n_stacks) n_stacks = ns;
+	m.seq_off = (uint32_t)seq_off;
+	m.w_off = (uint32_t)w_off;
+	m.len = (uint16_t)len;
+	m.max_diff = (uint8_t)md;
+	m.max_gapo = (uint8_t)go;
+	m.pad = 0;
+	w_entries = len > 0 ? 2 * (uint64_t)(len + 1) + (len > opt->seed_len ? 2 * (uint64_t)(opt->seed_len + 1) : 0) : 0;
+	return 0;
+}
+
+
+// byte j of a packed read = seq[0][j] | seq[1][j] << 4 (values 0..4)
+static inline void pack_seq_pair(uint8_t *dst, const uint8_t *seq, const uint8_t *rseq, int len)
+{
+	for (int j = 0; j < len; ++j) dst[j] = (uint8_t)((seq[j] > 3 ? 4 : seq[j]) | (rseq[j] > 3 ? 4 : rseq[j]) << 4);
+}
+
+// read in sequencing orientation -> seq = reversed read, rseq = reverse complement, i.e.
+// rseq[j] = complement(seq[j])  (bam1_to_seq, bwaseqio.c:294-297 with is_comp = 1)
+static inline void pack_read(uint8_t *dst, const uint8_t *read, int len)
+{
+	for (int j = 0; j < len; ++j) {
+		const uint8_t b = read[len - 1 - j];
+		dst[j] = (uint8_t)((b > 3 ? 4 : b) | (b > 3 ? 4 : 3 - b) << 4);
+	}
+}
+
+} // namespace bwagpu

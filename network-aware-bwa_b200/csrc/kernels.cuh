@@ -1,0 +1,537 @@
+// kernels.cuh -- K0 (index re-layout), K2 (width), K3 (gapped search), K4 (SA gather).
+// Hand-written for sm_100a; integer-only (every floating-point decision of the reference
+// -- bwa_cal_maxdiff, bwtaln.c:37-49 -- is taken on the host and shipped as an integer).
+#pragma once
+#include "fmindex.cuh"
+
+namespace bwagpu {
+
+#define STATE_M 0u
+#define STATE_I 1u
+#define STATE_D 2u
+#define NIL 0xffffffffu
+
+// ------------------------------------------------------------------ K0: re-layout
+// raw = the reference's bwt_t::bwt (12-word blocks, bwtmisc.c:125-152) on the device.
+__global__ void k_relayout(const uint32_t *__restrict__ raw, uint32_t seq_len, uint32_t n_blk, uint4 *__restrict__ blk,
+                           uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3)
+{
+	const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_blk) return;
+	const uint64_t p0 = (uint64_t)b << 6;
+	uint32_t c[4] = {t0, t1, t2, t3}; // totals: used by the terminal block when seq_len % 64 == 0
+	uint64_t lo = 0, hi = 0;
+	if (p0 < seq_len) {
+		const uint32_t rb = b >> 1, half = b & 1u;
+		const uint32_t *q = raw + (size_t)rb * 12;
+		c[0] = q[0]; c[1] = q[1]; c[2] = q[2]; c[3] = q[3];
+		const uint32_t n_words = (seq_len + 15) >> 4; // words the reference emitted in total
+		for (uint32_t w = 0; w < 8; ++w) {
+			const uint32_t gw = rb * 8 + w; // global word index
+			const uint32_t x = gw < n_words ? q[4 + w] : 0u;
+			if (half == 1 && w < 4) { // second half: fold the first 64 bases into the counts
+				for (int t = 0; t < 16; ++t) {
+					const uint64_t pos = (uint64_t)gw * 16 + t;
+					if (pos < seq_len) ++c[(x >> ((15 - t) << 1)) & 3u];
+				}
+			} else if ((w >> 2) == half) {
+				for (int t = 0; t < 16; ++t) {
+					const uint32_t base = (x >> ((15 - t) << 1)) & 3u;
+					const int j = (int)(w & 3u) * 16 + t;
+					lo |= (uint64_t)(base & 1u) << j;
+					hi |= (uint64_t)(base >> 1) << j;
+				}
+			}
+		}
+	}
+	blk[2 * (size_t)b] = make_uint4(c[0], c[1], c[2], c[3]);
+	blk[2 * (size_t)b + 1] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
+// ------------------------------------------------------------------ batch description
+struct GapOpt { // integer subset of gap_opt_t (bwtaln.h:143-153)
+	int s_mm, s_gapo, s_gape, mode;
+	int indel_end_skip, max_del_occ, max_entries;
+	int max_gape, max_seed_diff, seed_len, max_top2;
+};
+
+struct ReadMeta {        // 16 B per read, filled by the host
+	uint32_t seq_off;    // into the packed base array (chunk-local)
+	uint32_t w_off;      // into the width arena (entries)
+	uint16_t len;
+	uint8_t max_diff;    // local_opt.max_diff for this read (bwtaln.c:102,126)
+	uint8_t max_gapo;    // after the clamp of bwtaln.c:103
+	uint32_t pad;
+};
+
+struct Batch {
+	DevIndex ix[2];
+	GapOpt opt;
+	int n_reads;
+	const uint8_t *__restrict__ seq; // byte j of a read: seq[0][j] | seq[1][j] << 4
+	const ReadMeta *__restrict__ meta;
+	uint32_t *w;       // width arena: w values
+	uint16_t *bid;     // width arena: bid values
+	// results, per read
+	int32_t *n_aln;       // -1 = not done (overflow -> next tier)
+	int32_t *max_entries;
+	uint32_t *pool_off;   // offset of the read's alns in the unordered pool
+	uint4 *pool;
+	uint32_t pool_cap;
+	unsigned int *pool_count;
+	// work list
+	const int32_t *jobs; // NULL = identity
+	int n_jobs;
+	int *work_counter;
+	int32_t *overflow_ids;
+	int *overflow_count;
+	// per-slot scratch
+	uint4 *ent;
+	uint32_t *nxt;
+	uint32_t *heads;
+	uint4 *alnbuf;
+	uint32_t cap, aln_cap, n_stacks;
+	// stats (STATS builds only)
+	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes
+};
+
+__device__ __forceinline__ uint32_t sel4(uint32_t c, const uint32_t v[4])
+{
+	return c == 0 ? v[0] : c == 1 ? v[1] : c == 2 ? v[2] : v[3];
+}
+
+// ------------------------------------------------------------------ K2: width
+// bwt_cal_width (bwtaln.c:52-76) for the 4 strings of each read: thread = (read, a, seed).
+// w[a] is computed on index a with seq[a] (bwtaln.c:123-124), the seed widths on the last
+// seed_len bases (128-129).  4 independent dependent chains per read.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_width(const Batch B)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int r = t >> 2;
+	uint32_t f_ref = 0, f_own = 0;
+	if (r < B.n_reads) {
+		const ReadMeta m = B.meta[r];
+		const int a = t & 1, seed = (t >> 1) & 1;
+		const int len = m.len;
+		const bool has_seed = len > B.opt.seed_len;
+		if (len > 0 && (!seed || has_seed)) {
+			const int n = seed ? B.opt.seed_len : len;
+			const uint8_t *s = B.seq + m.seq_off + (seed ? len - n : 0);
+			const size_t wo = (size_t)m.w_off + (seed ? 2 * (size_t)(len + 1) + (size_t)a * (n + 1) : (size_t)a * (len + 1));
+			uint32_t *w = B.w + wo;
+			uint16_t *bd = B.bid + wo;
+			const DevIndex &ix = B.ix[a];
+			uint32_t k = 0, l = ix.seq_len;
+			uint32_t bid = 0;
+			for (int i = 0; i < n; ++i) {
+				const uint32_t c = (s[i] >> (a << 2)) & 15u;
+				if (c < 4) {
+					uint32_t ok, ol;
+					occ1_pair<STATS>(ix, k - 1, l, c, ok, ol, f_ref, f_own);
+					k = ix.L2[c] + ok + 1;
+					l = ix.L2[c] + ol;
+				}
+				if (k > l || c > 3) { // restart
+					k = 0; l = ix.seq_len; ++bid;
+				}
+				w[i] = l - k + 1;
+				bd[i] = (uint16_t)bid;
+			}
+			w[n] = 0;
+			bd[n] = (uint16_t)(bid + 1);
+		}
+	}
+	if (STATS) {
+		atomicAdd(B.stats + 0, (unsigned long long)f_ref);
+		atomicAdd(B.stats + 1, (unsigned long long)f_own);
+	}
+}
+
+// ------------------------------------------------------------------ K3: gapped search
+// bwt_match_gap (bwtgap.c:104-266) with its gap_stack (bwtgap.c:13-79), one read per
+// thread, persistent threads pulling reads from a global counter.
+//
+// Exactness: the traversal order is the reference's -- lowest non-empty score bucket
+// first, LIFO inside a bucket, pushes in the order insertion / deletions c=0..3 /
+// mismatches c=(str[i]+j)&3 j=1..4.  Buckets are singly linked lists threaded through a
+// per-thread entry arena (the reference uses realloc-doubling arrays; only the order is
+// observable).  Two things never reach memory:
+//   * the match continuation (pushed last, same score as the entry just popped, hence
+//     always the very next pop) is carried in registers (`held`);
+//   * the arena slot freed by the latest pop is kept in a register for the next push.
+// n_entries still counts held entries, so max_entries and the `> opt->max_entries` stop
+// (bwtgap.c:139-140) are unchanged.
+//
+// The per-thread control flow is a small state machine so that the lanes of a warp meet
+// at ONE occurrence lookup per trip whatever each lane is doing (expanding a node or
+// walking the exact-match tail of bwtgap.c:163-164 / bwt.c:237-252).
+struct Entry {
+	uint32_t k, l;
+	uint32_t pos;  // i | last_diff_pos << 16
+	uint32_t tag;  // n_mm | n_gapo << 8 | n_gape << 16 | state << 24 | a << 26
+};
+
+#define E_I(e) ((int)((e).pos & 0xffffu))
+#define E_LDP(e) ((int)((e).pos >> 16))
+#define E_MM(e) ((int)((e).tag & 0xffu))
+#define E_GO(e) ((int)(((e).tag >> 8) & 0xffu))
+#define E_GE(e) ((int)(((e).tag >> 16) & 0xffu))
+#define E_ST(e) (((e).tag >> 24) & 3u)
+#define E_A(e) (((e).tag >> 26) & 1u)
+
+enum { MODE_NEW = 0, MODE_POP = 1, MODE_EXACT = 2, MODE_EXPAND = 3 };
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_search(const Batch B)
+{
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	uint4 *const ent = B.ent + (size_t)slot * B.cap;
+	uint32_t *const nxt = B.nxt + (size_t)slot * B.cap;
+	uint32_t *const heads = B.heads + (size_t)slot * B.n_stacks;
+	uint4 *const alnbuf = B.alnbuf + (size_t)slot * B.aln_cap;
+	const GapOpt &O = B.opt;
+	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
+
+	// heads start empty for this launch
+	for (uint32_t s = 0; s < B.n_stacks; ++s) heads[s] = NIL;
+
+	int mode = MODE_NEW;
+	// per-read state
+	int rid = -1, len = 0, max_diff = 0, opt_max_diff = 0, max_gapo = 0;
+	int best_score = 0, best_cnt = 0, n_aln = 0, n_entries = 0, max_entries = 0;
+	bool has_seed = false, overflow = false;
+	const uint8_t *seq = nullptr;
+	uint32_t *w_base = nullptr;
+	uint16_t *bid_base = nullptr;
+	uint64_t mask0 = 0, mask1 = 0, mask2 = 0, mask3 = 0; // non-empty buckets
+	uint32_t bump = 0, free_head = NIL, spare = NIL;
+	Entry held; bool held_valid = false;
+	Entry e = {0, 0, 0, 0}; // entry being processed
+	int ii = 0; // exact-tail cursor
+	int m = 0, m_seed = 0, i = 0;
+	uint32_t k = 0, l = 0;
+	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0;
+
+	auto score_of = [&](int mm, int go, int ge) { return mm * O.s_mm + go * O.s_gapo + ge * O.s_gape; };
+
+	auto mask_set = [&](int s) {
+		const uint64_t bit = 1ull << (s & 63);
+		if (s < 64) mask0 |= bit; else if (s < 128) mask1 |= bit; else if (s < 192) mask2 |= bit; else mask3 |= bit;
+	};
+	auto mask_clear = [&](int s) {
+		const uint64_t bit = ~(1ull << (s & 63));
+		if (s < 64) mask0 &= bit; else if (s < 128) mask1 &= bit; else if (s < 192) mask2 &= bit; else mask3 &= bit;
+	};
+	auto mask_lowest = [&]() -> int {
+		if (mask0) return __ffsll((long long)mask0) - 1;
+		if (mask1) return 64 + __ffsll((long long)mask1) - 1;
+		if (mask2) return 128 + __ffsll((long long)mask2) - 1;
+		return 192 + __ffsll((long long)mask3) - 1;
+	};
+
+	// gap_push (bwtgap.c:45-64) to the in-memory bucket lists
+	auto push_mem = [&](const Entry &x, int s) {
+		uint32_t idx;
+		if (spare != NIL) { idx = spare; spare = NIL; }
+		else if (free_head != NIL) { idx = free_head; free_head = nxt[idx]; }
+		else if (bump < B.cap) idx = bump++;
+		else { overflow = true; return; }
+		ent[idx] = make_uint4(x.k, x.l, x.pos, x.tag);
+		nxt[idx] = heads[s];
+		heads[s] = idx;
+		mask_set(s);
+	};
+	auto push = [&](uint32_t a, int pi, uint32_t pk, uint32_t pl, int mm, int go, int ge, uint32_t st, bool is_diff,
+	                bool hold) {
+		Entry x;
+		x.k = pk; x.l = pl;
+		x.pos = (uint32_t)pi | (is_diff ? (uint32_t)pi << 16 : 0u);
+		x.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
+		++n_entries;
+		if (STATS) ++n_pushes;
+		if (hold) { held = x; held_valid = true; }
+		else push_mem(x, score_of(mm, go, ge));
+	};
+
+	// copies the finished read's results out and resets the per-slot stack
+	auto finish_read = [&]() {
+		if (overflow || (uint32_t)n_aln > B.aln_cap) overflow = true;
+		uint32_t off = 0;
+		if (!overflow && n_aln > 0) {
+			off = atomicAdd(B.pool_count, (unsigned int)n_aln);
+			if (off + (uint32_t)n_aln > B.pool_cap) overflow = true;
+		}
+		if (overflow) {
+			B.n_aln[rid] = -1;
+			const int o = atomicAdd(B.overflow_count, 1);
+			B.overflow_ids[o] = rid;
+		} else {
+			for (int j = 0; j < n_aln; ++j) B.pool[off + j] = alnbuf[j];
+			B.n_aln[rid] = n_aln;
+			B.pool_off[rid] = off;
+			B.max_entries[rid] = max_entries;
+		}
+		// reset: only non-empty buckets have a live head
+		while (mask0 | mask1 | mask2 | mask3) { const int s = mask_lowest(); heads[s] = NIL; mask_clear(s); }
+		bump = 0; free_head = NIL; spare = NIL; held_valid = false; n_entries = 0;
+	};
+
+	// action for found hits (bwtgap.c:167-200).  Returns false when the search must stop.
+	auto process_hit = [&](uint32_t hk, uint32_t hl) -> bool {
+		const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+		const int score = score_of(mm, go, ge);
+		bool do_add = true;
+		if (n_aln == 0) {
+			best_score = score;
+			int best_diff = mm + go;
+			if (gape_mode) best_diff += ge;
+			if (!nonstop) max_diff = (best_diff + 1 > opt_max_diff) ? opt_max_diff : best_diff + 1; // top2 behaviour
+		}
+		if (score == best_score) best_cnt += (int)(hl - hk + 1);
+		else if (best_cnt > O.max_top2) return false; // top2b behaviour
+		if (go) { // the hit may have been found already (gap in a tandem repeat)
+			for (int j = 0; j < n_aln && j < (int)B.aln_cap; ++j) {
+				const uint4 q = alnbuf[j];
+				if (q.y == hk && q.z == hl) { do_add = false; break; }
+			}
+		}
+		if (do_add) {
+			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array
+			const uint32_t a = E_A(e);
+			uint32_t *w = w_base + (size_t)a * (len + 1);
+			uint16_t *bd = bid_base + (size_t)a * (len + 1);
+			const uint32_t x = hl - hk + 1, mx = B.ix[1 - a].seq_len;
+			const int ldp = E_LDP(e);
+			uint32_t j = 0;
+			for (int t = 0; t < ldp; ++t) {
+				const uint32_t wv = w[t];
+				if (wv > x) w[t] = wv - x;
+				else if (wv == x) { bd[t] = 1; w[t] = mx - (++j); }
+			}
+			if ((uint32_t)n_aln < B.aln_cap)
+				alnbuf[n_aln] = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl,
+				                           (uint32_t)score);
+			++n_aln; // beyond aln_cap: counted, flagged as overflow at finish
+		}
+		return true;
+	};
+
+	for (;;) {
+		if (mode == MODE_NEW) {
+			const int job = atomicAdd(B.work_counter, 1);
+			if (job >= B.n_jobs) break;
+			rid = B.jobs ? B.jobs[job] : job;
+			const ReadMeta md = B.meta[rid];
+			len = md.len;
+			overflow = false;
+			n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
+			if (len == 0) { // bwtaln.c:134: aln = 0, n_aln = 0
+				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
+				continue;
+			}
+			opt_max_diff = max_diff = md.max_diff;
+			max_gapo = md.max_gapo;
+			has_seed = len > O.seed_len;
+			seq = B.seq + md.seq_off;
+			w_base = B.w + md.w_off;
+			bid_base = B.bid + md.w_off;
+			best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
+			// too many N? (bwtgap.c:118-123) -- *pmax_entries is left untouched there
+			int n_amb = 0;
+			for (int j = 0; j < len; ++j) n_amb += (seq[j] & 15u) > 3u;
+			if (n_amb > max_diff) {
+				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
+				continue;
+			}
+			push(0u, len, 0u, B.ix[0].seq_len, 0, 0, 0, STATE_M, false, false);
+			push(1u, len, 0u, B.ix[0].seq_len, 0, 0, 0, STATE_M, false, true);
+			if (overflow) { finish_read(); continue; }
+			mode = MODE_POP;
+		}
+
+		if (mode == MODE_POP) {
+			if (overflow || n_entries == 0) { finish_read(); mode = MODE_NEW; continue; }
+			if (max_entries < n_entries) max_entries = n_entries;
+			if (n_entries > O.max_entries) { finish_read(); mode = MODE_NEW; continue; }
+			// gap_pop (bwtgap.c:66-79)
+			if (held_valid) { e = held; held_valid = false; }
+			else {
+				const int s = mask_lowest();
+				const uint32_t idx = heads[s];
+				const uint4 q = ent[idx];
+				const uint32_t nx = nxt[idx];
+				heads[s] = nx;
+				if (nx == NIL) mask_clear(s);
+				if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
+				spare = idx;
+				e.k = q.x; e.l = q.y; e.pos = q.z; e.tag = q.w;
+			}
+			--n_entries;
+			if (STATS) ++n_pops;
+			k = e.k; l = e.l; i = E_I(e);
+			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+			if (!nonstop && score_of(mm, go, ge) > best_score + O.s_mm) { finish_read(); mode = MODE_NEW; continue; }
+			m = max_diff - (mm + go);
+			if (gape_mode) m -= ge;
+			if (m < 0) continue;
+			if (has_seed) {
+				m_seed = O.max_seed_diff - (mm + go);
+				if (gape_mode) m_seed -= ge;
+			}
+			const uint32_t a = E_A(e);
+			if (i > 0 && m < (int)bid_base[(size_t)a * (len + 1) + i - 1]) continue;
+			if (i == 0) {
+				if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
+				continue;
+			}
+			if (m == 0 && (E_ST(e) == STATE_M || gape_mode || ge == O.max_gape)) { // no diff allowed
+				ii = i;
+				if (((seq[ii - 1] >> (a << 2)) & 15u) > 3u) continue; // N in the tail: no match
+				mode = MODE_EXACT;
+			} else {
+				--i;
+				mode = MODE_EXPAND;
+			}
+		}
+
+		// ---- the one occurrence lookup per trip (bwt_2occ4 at bwtgap.c:202 / bwt_2occ at bwt.c:245)
+		const uint32_t a = E_A(e);
+		const DevIndex &ix = B.ix[1 - a];
+		uint32_t cnt_k[4], cnt_l[4];
+		occ4_pair<STATS>(ix, k - 1, l, cnt_k, cnt_l, f_ref, f_own);
+
+		if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
+			const uint32_t c = (seq[ii - 1] >> (a << 2)) & 15u;
+			k = ix.L2[c] + sel4(c, cnt_k) + 1;
+			l = ix.L2[c] + sel4(c, cnt_l);
+			--ii;
+			if (k > l) { mode = MODE_POP; continue; }
+			if (ii == 0) {
+				mode = MODE_POP;
+				if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
+				continue;
+			}
+			if (((seq[ii - 1] >> (a << 2)) & 15u) > 3u) mode = MODE_POP;
+			continue;
+		}
+
+		// ---- MODE_EXPAND (bwtgap.c:201-259); i was already decremented
+		{
+			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+			const uint32_t st = E_ST(e);
+			const uint32_t occ = l - k + 1;
+			const uint32_t *w = w_base + (size_t)a * (len + 1);
+			const uint16_t *bd = bid_base + (size_t)a * (len + 1);
+			bool allow_diff = true, allow_M = true;
+			if (i > 0) {
+				const int b1 = bd[i - 1];
+				if (b1 > m - 1) allow_diff = false;
+				else if (b1 == m - 1 && (int)bd[i] == m - 1 && w[i - 1] == w[i]) allow_M = false;
+				if (has_seed) {
+					const int si = i - (len - O.seed_len);
+					if (si > 0) {
+						const size_t so = 2 * (size_t)(len + 1) + (size_t)a * (O.seed_len + 1);
+						const uint32_t *sw = w_base + so;
+						const uint16_t *sb = bid_base + so;
+						const int s1 = sb[si - 1];
+						if (s1 > m_seed - 1) allow_diff = false;
+						else if (s1 == m_seed - 1 && (int)sb[si] == m_seed - 1 && sw[si - 1] == sw[si]) allow_M = false;
+					}
+				}
+			}
+			const uint32_t ci = (seq[i] >> (a << 2)) & 15u;
+			// the match continuation is the last push and the next pop: carried in registers
+			// indels
+			int tmp;
+			if (loggap) {
+				uint32_t v = (uint32_t)(ge + go);
+				tmp = (v ? 31 - __clz(v) : 0) / 2 + 1; // int_log2 (bwtgap.c:93-102)
+			} else tmp = go + ge;
+			if (allow_diff && i >= O.indel_end_skip + tmp && len - i >= O.indel_end_skip + tmp) {
+				if (st == STATE_M) { // gap open
+					if (go < max_gapo) {
+						push(a, i, k, l, mm, go + 1, ge, STATE_I, true, false); // insertion
+						for (uint32_t c = 0; c < 4; ++c) { // deletion
+							const uint32_t nk = ix.L2[c] + cnt_k[c] + 1, nl = ix.L2[c] + cnt_l[c];
+							if (nk <= nl) push(a, i + 1, nk, nl, mm, go + 1, ge, STATE_D, true, false);
+						}
+					}
+				} else if (st == STATE_I) { // extension of an insertion
+					if (ge < O.max_gape) push(a, i, k, l, mm, go, ge + 1, STATE_I, true, false);
+				} else { // extension of a deletion
+					if (ge < O.max_gape && (ge + go < max_diff || occ < (uint32_t)O.max_del_occ)) {
+						for (uint32_t c = 0; c < 4; ++c) {
+							const uint32_t nk = ix.L2[c] + cnt_k[c] + 1, nl = ix.L2[c] + cnt_l[c];
+							if (nk <= nl) push(a, i + 1, nk, nl, mm, go, ge + 1, STATE_D, true, false);
+						}
+					}
+				}
+			}
+			// mismatches, the match last
+			if (allow_diff && allow_M) {
+#pragma unroll
+				for (uint32_t j = 1; j <= 4; ++j) {
+					const uint32_t c = (ci + j) & 3u;
+					const bool is_mm = (j != 4 || ci > 3);
+					const uint32_t nk = ix.L2[c] + sel4(c, cnt_k) + 1, nl = ix.L2[c] + sel4(c, cnt_l);
+					if (nk <= nl) push(a, i, nk, nl, mm + (is_mm ? 1 : 0), go, ge, STATE_M, is_mm, !is_mm);
+				}
+			} else if (ci < 4) { // exact match only
+				const uint32_t nk = ix.L2[ci] + sel4(ci, cnt_k) + 1, nl = ix.L2[ci] + sel4(ci, cnt_l);
+				if (nk <= nl) push(a, i, nk, nl, mm, go, ge, STATE_M, false, true);
+			}
+			mode = MODE_POP;
+		}
+	}
+
+	if (STATS) {
+		atomicAdd(B.stats + 0, (unsigned long long)f_ref);
+		atomicAdd(B.stats + 1, (unsigned long long)f_own);
+		atomicAdd(B.stats + 2, (unsigned long long)n_pops);
+		atomicAdd(B.stats + 3, (unsigned long long)n_pushes);
+	}
+}
+
+// ------------------------------------------------------------------ ordered compaction of the aln pool
+// gather: pool (completion order) -> out (read order, offsets = exclusive scan of n_aln)
+__global__ void k_gather_aln(int n_reads, const int32_t *__restrict__ n_aln, const uint32_t *__restrict__ pool_off,
+                             const uint32_t *__restrict__ out_off, const uint4 *__restrict__ pool, uint4 *__restrict__ out)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int n = n_aln[r];
+	const uint32_t src = pool_off[r], dst = out_off[r];
+	for (int j = 0; j < n; ++j) out[dst + j] = pool[src + j];
+}
+
+// ------------------------------------------------------------------ K4: SA -> coordinate
+// bwt_sa (bwt.c:72-81): walk LF to the next sampled row; one 32-byte block per step.
+struct IndexPair { DevIndex ix[2]; }; // [0] forward, [1] reverse
+
+__global__ void __launch_bounds__(256) k_sa(const IndexPair P, long long n,
+                                            const uint32_t *__restrict__ q, const uint8_t *__restrict__ which,
+                                            uint32_t *__restrict__ out)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const bool fw = which[t] != 0;
+	DevIndex ix; // field-wise select keeps the struct in registers (no local copy of the param)
+	ix.blk = fw ? P.ix[0].blk : P.ix[1].blk;
+	ix.sa = fw ? P.ix[0].sa : P.ix[1].sa;
+	ix.primary = fw ? P.ix[0].primary : P.ix[1].primary;
+	ix.seq_len = fw ? P.ix[0].seq_len : P.ix[1].seq_len;
+	ix.sa_intv = fw ? P.ix[0].sa_intv : P.ix[1].sa_intv;
+#pragma unroll
+	for (int j = 0; j < 5; ++j) ix.L2[j] = fw ? P.ix[0].L2[j] : P.ix[1].L2[j];
+	uint32_t k = q[t], steps = 0;
+	const uint32_t intv = ix.sa_intv;
+	while (k % intv != 0) {
+		++steps;
+		k = inv_psi(ix, k);
+	}
+	k /= intv;
+	out[t] = steps + (k ? ix.sa[k] : 0xffffffffu);
+}
+
+} // namespace bwagpu

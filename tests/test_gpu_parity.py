@@ -1,0 +1,166 @@
+"""GPU parity tests proper: every call goes through the C-ABI of libbwagpu.so (ctypes), and
+is compared bit-for-bit with (a) the committed golden vectors the reference produced and
+(b) the reference itself (oracle/_ref, prebuilt, travels with the snapshot) on fresh seeded
+inputs.  Integer/byte work: the bar is bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import refload as R
+from test_kernel_logic import CONFIGS, golden_case
+
+pytestmark = pytest.mark.gpu
+abi, api = R.abi, R.bwa.api
+
+
+@pytest.fixture(scope="module")
+def gpu_index(small_index):
+    T, idx = small_index
+    api.init()
+    api.load_index(idx)
+    yield T, idx
+    api.destroy()
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_aln_flat_matches_golden(golden, gpu_index, name):
+    reads, opt, want = golden_case(golden, name)
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    assert R.compare_aln(want, got, name) == []
+
+
+def test_struct_api_matches_golden(golden, gpu_index):
+    """bwa_gpu_cal_sa_reads_gap on bwa_seq_t[]: same fields the reference call fills
+    (bwtaln.c:113,132), aln arrays libc-owned."""
+    reads, opt, want = golden_case(golden, "ragged")
+    seqs, keep = abi.make_seqs(reads)
+    for s in seqs:  # poison the fields the call must reset
+        s.sa, s.type, s.c1, s.c2, s.n_aln, s.max_entries = 77, 3, 5, 6, 99, -5
+    api.cal_sa_reads_gap(seqs, opt)
+    n_aln, max_entries, off, aln = want
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for i, s in enumerate(seqs):
+        assert s.n_aln == n_aln[i]
+        assert (s.sa, s.type, s.c1, s.c2) == (0, 0, 0, 0)
+        if s.len == 0:
+            assert not s.aln
+            continue
+        assert bool(s.aln)  # bwt_match_gap always hands back a calloc'd array (bwtgap.c:115)
+        if max_entries[i] != 0:
+            assert s.max_entries == max_entries[i]
+        else:
+            assert s.max_entries == -5  # too many N: the reference leaves it untouched (bwtgap.c:120-123)
+        if s.n_aln:
+            buf = (C.c_char * (16 * s.n_aln)).from_address(C.addressof(s.aln.contents))
+            assert bytes(buf) == aln[off[i]:off[i + 1]].tobytes()
+        libc.free(C.cast(s.aln, C.c_void_p))
+
+
+def test_cal_pac_pos_matches_golden(golden, gpu_index):
+    out = api.cal_pac_pos(golden["sa_k"], golden["sa_which"])
+    assert np.array_equal(out, golden["sa_out"])
+
+
+def test_chunking_and_tiers_are_invisible(golden, gpu_index, monkeypatch):
+    """Tiny chunks + a tiny tier-1 arena must not change a single byte."""
+    reads, opt, want = golden_case(golden, "pe100")
+    monkeypatch.setenv("BWAGPU_CHUNK", "97")
+    monkeypatch.setenv("BWAGPU_T1_CAP", "48")
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    st = api.get_stats()
+    assert st["n_overflow_t2"] > 0
+    assert R.compare_aln(want, got, "chunked") == []
+
+
+def test_stats_counters(golden, gpu_index):
+    reads, opt, want = golden_case(golden, "se76")
+    api.set_stats(True)
+    try:
+        got = api.aln_flat(reads.bases, reads.offs, opt)
+        st = api.get_stats()
+    finally:
+        api.set_stats(False)
+    assert R.compare_aln(want, got, "stats build") == []
+    assert st["n_reads"] == reads.n and st["n_aln"] == want[3].size
+    assert st["n_pops"] > reads.n and st["n_pushes"] >= st["n_pops"]
+    assert st["occ_fetches_search"] > 0 and st["own_fetches_search"] > 0
+
+
+def test_resident_path_matches_flat(golden, gpu_index):
+    reads, opt, want = golden_case(golden, "se36")
+    api.resident_stage(reads.bases, reads.offs, opt)
+    ms1 = api.resident_run()
+    ms2 = api.resident_run()  # idempotent: widths are recomputed, nothing carries over
+    assert ms1 > 0 and ms2 > 0
+    got = api.resident_fetch(reads.n)
+    assert R.compare_aln(want, got, "resident") == []
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("length,optkw,simkw", [
+    (36, {}, {}),
+    (76, {}, {}),
+    (100, {}, {}),
+    ((30, 50), dict(seed_len=1024, fnr=0.01, max_gapo=2), dict(adna=True, sub_rate=0.01)),
+    ((15, 250), dict(max_gapo=2, max_gape=10), dict(n_rate=0.005)),
+])
+def test_aln_matches_reference_live(gpu_index, length, optkw, simkw):
+    T, idx = gpu_index
+    ridx = R.RefIndex(idx)
+    reads = R.bwa.simulate.simulate_reads(T, 20000, length, seed=4242, **simkw)
+    opt = abi.default_gap_opt(**optkw)
+    want = R.ref_aln(ridx, reads, opt, threads=8)
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    assert R.compare_aln(want, got, f"live {length}") == []
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+def test_cal_pac_pos_matches_reference_live(gpu_index):
+    T, idx = gpu_index
+    ridx = R.RefIndex(idx)
+    rng = np.random.default_rng(8)
+    k = rng.integers(0, idx.bwt[0].seq_len + 1, size=300000, dtype=np.uint32)
+    which = rng.integers(0, 2, size=k.size, dtype=np.uint8)
+    assert np.array_equal(api.cal_pac_pos(k, which), R.ref_sa(ridx, k, which))
+
+
+def test_sa_of_every_row_is_a_permutation(gpu_index):
+    """Size-independent property: bwt_sa over all rows 1..n of one strand is a permutation
+    of 0..n-1 (row 0 is the sentinel row and yields -1 + steps, bwt.c:79-80)."""
+    T, idx = gpu_index
+    n = idx.bwt[0].seq_len
+    k = np.arange(1, n + 1, dtype=np.uint32)
+    for which in (1, 0):
+        out = api.cal_pac_pos(k, np.full(k.size, which, dtype=np.uint8))
+        assert np.array_equal(np.sort(out), np.arange(n, dtype=np.uint32))
+
+
+def test_exact_reads_are_found_at_their_origin(gpu_index):
+    """Size-independent property used at full size in bench.py --check: an error-free read
+    cut from the genome gets a 0-difference hit whose SA interval contains its origin."""
+    T, idx = gpu_index
+    reads = R.bwa.simulate.simulate_reads(T, 5000, 50, seed=77, sub_rate=0.0, indel_frac=0.0, n_rate=0.0, junk_frac=0.0)
+    opt = abi.default_gap_opt()
+    n_aln, _, off, aln = api.aln_flat(reads.bases, reads.offs, opt)
+    assert (n_aln >= 1).all()
+    first = aln[off[:-1]]
+    assert (first["score"] == 0).all()
+    # expand the first hit of each read to coordinates and look for the simulated origin
+    ks, which, owner = [], [], []
+    for i in range(reads.n):
+        a = first[i]
+        strand = (a["info"] >> 24) & 1
+        w = min(int(a["l"] - a["k"] + 1), 64)
+        ks.append(np.arange(a["k"], a["k"] + w, dtype=np.uint32))
+        which.append(np.full(w, strand, dtype=np.uint8))
+        owner.append(np.full(w, i))
+    ks, which, owner = np.concatenate(ks), np.concatenate(which), np.concatenate(owner)
+    sa = api.cal_pac_pos(ks, which)
+    n = idx.bwt[0].seq_len
+    pos = np.where(which == 1, sa, n - (sa + 50)).astype(np.int64)  # bwase.c:144-153
+    hit = np.zeros(reads.n, dtype=bool)
+    np.logical_or.at(hit, owner, pos == reads.pos[owner])
+    full = (first["l"] - first["k"] + 1) <= 64
+    assert hit[full].all()

@@ -1,0 +1,74 @@
+"""CPU checks of the kernels' LOGIC: the bodies of csrc/kernels.cuh compiled for the host
+(tests/host_emu) against (a) the committed golden vectors made by the reference and (b) the
+reference itself when oracle/_ref is present.  These do not replace the GPU parity tests;
+they catch traversal-order and layout mistakes without a device."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import refload as R
+
+abi = R.abi
+CONFIGS = ["se36", "se76", "pe100", "adna", "ragged", "fixed_n3", "nonstop_loggap", "nogape"]
+
+
+def opt_from_words(words):
+    o = abi.gap_opt_t()
+    C.memmove(C.addressof(o), words.tobytes(), 64)
+    return o
+
+
+def golden_case(golden, name):
+    reads = R.bwa.simulate.Reads(golden[f"{name}_bases"], golden[f"{name}_offs"], None, None)
+    opt = opt_from_words(golden[f"{name}_opt"])
+    n_aln = golden[f"{name}_n_aln"]
+    off = np.zeros(n_aln.size + 1, dtype=np.int64)
+    off[1:] = np.cumsum(n_aln)
+    aln = np.ascontiguousarray(golden[f"{name}_aln"]).view(abi.ALN_DTYPE).reshape(-1)
+    return reads, opt, (n_aln, golden[f"{name}_max_entries"], off, aln)
+
+
+@pytest.fixture(scope="module")
+def emu_index(small_index):
+    T, idx = small_index
+    ridx = R.RefIndex(idx)
+    h = R.emu().emu_load_index(ridx.arr)
+    yield h, ridx
+    R.emu().emu_free_index(h)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_search_logic_matches_golden(golden, emu_index, name):
+    h, _ = emu_index
+    reads, opt, want = golden_case(golden, name)
+    got = R.emu_aln(h, reads, opt)
+    assert R.compare_aln(want, got, name) == []
+
+
+def test_search_logic_tiny_tiers(golden, emu_index):
+    """Force most reads through the overflow tiers (tiny tier-1 arena and hit list)."""
+    h, _ = emu_index
+    reads, opt, want = golden_case(golden, "se76")
+    got = R.emu_aln(h, reads, opt, cap1=64, aln_cap1=1, n_slots=2)
+    assert got[4][4] > 100  # reads that overflowed tier 1
+    assert R.compare_aln(want, got, "tiers") == []
+
+
+def test_sa_logic_matches_golden(golden, emu_index):
+    h, _ = emu_index
+    k, which = golden["sa_k"], golden["sa_which"]
+    out = np.empty(k.size, dtype=np.uint32)
+    R.emu().emu_sa(h, k.size, k.ctypes.data, which.ctypes.data, out.ctypes.data)
+    assert np.array_equal(out, golden["sa_out"])
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not built")
+def test_search_logic_matches_reference_live(small_index, emu_index):
+    T, _ = small_index
+    h, ridx = emu_index
+    reads = R.bwa.simulate.simulate_reads(T, 800, (20, 120), seed=123, n_rate=0.01)
+    opt = abi.default_gap_opt(max_gapo=2, max_gape=8)
+    want = R.ref_aln(ridx, reads, opt, threads=4)
+    got = R.emu_aln(h, reads, opt)
+    assert R.compare_aln(want, got, "live") == []

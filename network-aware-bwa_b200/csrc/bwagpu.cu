@@ -331,6 +331,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	if (stats) CK(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st));
 
 	// K2
+	B.jobs = nullptr; B.n_jobs = n;
 	CK(cudaEventRecord(c->ev[1], c->st));
 	{
 		const long long threads = 4ll * n;
@@ -364,6 +365,13 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		int32_t *ovf = (t & 1) ? c->d_jobs_b.p : c->d_jobs_a.p;
 		B.overflow_ids = ovf;
 		CK(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(int), c->st)); // work + overflow counters
+		if (t > 0) { // pristine widths for the reads being retried
+			const int wb = (int)((4ll * n_jobs + 127) / 128);
+			if (stats) k_width<true><<<wb, 128, 0, c->st>>>(B);
+			else k_width<false><<<wb, 128, 0, c->st>>>(B);
+			CK(cudaGetLastError());
+			c->stats.launches++;
+		}
 		uint32_t blocks = T.slots_blocks;
 		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
 		if (blocks > need) blocks = need;

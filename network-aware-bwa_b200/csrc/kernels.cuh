@@ -108,9 +108,12 @@ template <bool STATS>
 __global__ void __launch_bounds__(128) k_width(const Batch B)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int r = t >> 2;
+	const int job = t >> 2;
 	uint32_t f_ref = 0, f_own = 0;
-	if (r < B.n_reads) {
+	if (job < B.n_jobs) {
+		// later tiers recompute the widths of their reads: gap_shadow (bwtgap.c:81-91) edited
+		// them in place during the attempt that overflowed
+		const int r = B.jobs ? B.jobs[job] : job;
 		const ReadMeta m = B.meta[r];
 		const int a = t & 1, seed = (t >> 1) & 1;
 		const int len = m.len;

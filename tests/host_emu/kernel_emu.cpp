@@ -104,6 +104,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	B.n_stacks = n_stacks;
 	// K2
 	blockDim.x = 1; threadIdx.x = 0;
+	B.jobs = nullptr; B.n_jobs = n;
 	for (long long t = 0; t < 4ll * n; ++t) { blockIdx.x = (unsigned)t; k_width<true>(B); }
 	if (stats8) { stats8[0] = stats[0]; stats8[1] = stats[1]; }
 	stats[0] = stats[1] = 0;
@@ -122,6 +123,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		int32_t *ovf = (t & 1) ? jobs_b.data() : jobs_a.data();
 		B.overflow_ids = ovf;
 		counters[0] = counters[1] = 0;
+		if (t > 0) for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
 		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; k_search<true>(B); }
 		if (stats8) stats8[4 + t] = (unsigned long long)counters[1];
 		if (counters[1] > 0 && t == 2) { g_err = "reads exceeded the largest tier"; return 1; }

@@ -55,6 +55,16 @@ def test_search_logic_tiny_tiers(golden, emu_index):
     assert R.compare_aln(want, got, "tiers") == []
 
 
+def test_search_logic_retry_after_hits(golden, emu_index):
+    """A read that overflows AFTER its first hit has had its widths edited by gap_shadow;
+    the retry in the next tier must start from pristine widths."""
+    h, _ = emu_index
+    reads, opt, want = golden_case(golden, "adna")
+    got = R.emu_aln(h, reads, opt, cap1=300, aln_cap1=64, n_slots=2)
+    assert got[4][4] > 20
+    assert R.compare_aln(want, got, "retry") == []
+
+
 def test_sa_logic_matches_golden(golden, emu_index):
     h, _ = emu_index
     k, which = golden["sa_k"], golden["sa_which"]

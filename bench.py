@@ -246,10 +246,12 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     dev_ms, search_ms, width_ms, launches = 0.0, 0.0, 0.0, 0
+    tier_ms = [0.0] * 4
     for _ in range(args.steps):
         dev_ms += api.resident_run()
         st = api.get_stats()
         search_ms += st["ms_search"]; width_ms += st["ms_width"]; launches += st["launches"]
+        tier_ms = [a + b for a, b in zip(tier_ms, st["ms_tier"])]
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -356,7 +358,10 @@ def main():
                      "traffic": traffic, "kernel": "k_search (all tiers)", "peak_source": peak_src,
                      "algorithmic_bytes": "64 B x occ-block fetches of the reference layout (SURVEY.md §8d)",
                      "fetches_per_read": fetches / n_reads, "own_32B_blocks_per_read": st_counts["own_fetches_search"] / n_reads,
-                     "kernel_ms_per_step": search_ms / args.steps, "width_ms_per_step": width_ms / args.steps},
+                     "kernel_ms_per_step": search_ms / args.steps, "width_ms_per_step": width_ms / args.steps,
+                     "tier_ms_per_step": [t / args.steps for t in tier_ms],
+                     "pops_per_read": st_counts["n_pops"] / n_reads, "pushes_per_read": st_counts["n_pushes"] / n_reads,
+                     "stored_pushes_per_read": st_counts["n_stored"] / n_reads},
         "cpu_baseline": cpu_baseline,
         "parity_sample": parity,
         "wall_s_timed_region": wall_s,

@@ -196,6 +196,8 @@ typedef struct {
 	int64_t n_pops, n_pushes;
 	int32_t launches; /* kernels launched by the call */
 	int32_t n_devices;
+	double ms_tier[4]; /* k_search (+ its width refresh) per tier */
+	int64_t n_stored;  /* pushes that reached the in-memory stack (stats builds) */
 } bwa_gpu_stats_t;
 
 int bwa_gpu_get_stats(bwa_gpu_stats_t *out);

@@ -130,10 +130,14 @@ class stats_t(C.Structure):
         ("own_fetches_width", C.c_int64), ("own_fetches_search", C.c_int64),
         ("n_pops", C.c_int64), ("n_pushes", C.c_int64),
         ("launches", C.c_int32), ("n_devices", C.c_int32),
+        ("ms_tier", C.c_double * 4),
+        ("n_stored", C.c_int64),
     ]
 
     def asdict(self) -> dict:
-        return {f[0]: getattr(self, f[0]) for f in self._fields_}
+        d = {f[0]: getattr(self, f[0]) for f in self._fields_}
+        d["ms_tier"] = list(self.ms_tier)
+        return d
 
 
 def make_bwt_t(b) -> bwt_t:

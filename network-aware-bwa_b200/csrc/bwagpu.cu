@@ -115,10 +115,10 @@ struct Ctx {
 	int dev = 0;
 	int n_sm = 0;
 	cudaStream_t st = nullptr;
-	cudaEvent_t ev[8] = {};
+	cudaEvent_t ev[16] = {};
 	// index
 	DevIndex ix[2] = {};
-	DevBuf<uint4> blk[2];
+	DevBuf<uint4> blk_all; // both strands' occ blocks in ONE allocation (one L2 persistence window)
 	DevBuf<uint32_t> sa[2];
 	DevBuf<uint8_t> pac;
 	int64_t l_pac = 0;
@@ -134,7 +134,7 @@ struct Ctx {
 	DevBuf<int> d_counters;            // [0] work [1] overflow [2] pool_count(u32)
 	DevBuf<unsigned long long> d_stats; // 4
 	DevBuf<uint8_t> d_cubtmp;
-	Tier tier[3];
+	Tier tier[4];
 	// pinned staging
 	PinBuf<uint8_t> h_seq;
 	PinBuf<ReadMeta> h_meta;
@@ -167,7 +167,8 @@ extern "C" void bwa_gpu_destroy(void)
 	for (Ctx *c : g_ctx) {
 		cudaSetDevice(c->dev);
 		cudaDeviceSynchronize();
-		for (int s = 0; s < 2; ++s) { c->blk[s].release(); c->sa[s].release(); }
+		c->blk_all.release();
+		for (int s = 0; s < 2; ++s) c->sa[s].release();
 		c->pac.release();
 		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release();
 		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release();
@@ -216,19 +217,25 @@ static int upload_index_one(Ctx *c, bwt_t *const bwt[2], const ubyte_t *pac, int
 {
 	CK(cudaSetDevice(c->dev));
 	c->has_sa = true;
+	size_t blk_off[2] = {0, 0}, blk_total = 0;
+	for (int s = 0; s < 2; ++s) {
+		if (!bwt[s] || !bwt[s]->bwt) return fail("bwa_gpu_load_index: bwt[%d] is not loaded", s);
+		blk_off[s] = blk_total;
+		blk_total += 2 * ((size_t)(bwt[s]->seq_len >> 6) + 1);
+		blk_total = (blk_total + 7) & ~(size_t)7; // keep each strand 128-byte aligned
+	}
+	if (c->blk_all.reserve(blk_total)) return 1;
 	for (int s = 0; s < 2; ++s) {
 		const bwt_t *b = bwt[s];
-		if (!b || !b->bwt) return fail("bwa_gpu_load_index: bwt[%d] is not loaded", s);
 		const uint32_t n_blk = (b->seq_len >> 6) + 1;
 		DevBuf<uint32_t> raw;
 		if (raw.reserve(b->bwt_size)) return 1;
 		CK(cudaMemcpyAsync(raw.p, b->bwt, (size_t)b->bwt_size * 4, cudaMemcpyHostToDevice, c->st));
-		if (c->blk[s].reserve(2 * (size_t)n_blk)) return 1;
-		k_relayout<<<(n_blk + 255) / 256, 256, 0, c->st>>>(raw.p, b->seq_len, n_blk, c->blk[s].p, b->L2[1] - b->L2[0],
+		k_relayout<<<(n_blk + 255) / 256, 256, 0, c->st>>>(raw.p, b->seq_len, n_blk, c->blk_all.p + blk_off[s], b->L2[1] - b->L2[0],
 		                                                   b->L2[2] - b->L2[1], b->L2[3] - b->L2[2], b->L2[4] - b->L2[3]);
 		CK(cudaGetLastError());
 		DevIndex &ix = c->ix[s];
-		ix.blk = c->blk[s].p;
+		ix.blk = c->blk_all.p + blk_off[s];
 		ix.primary = b->primary; ix.seq_len = b->seq_len; ix.n_blk = n_blk;
 		for (int j = 0; j < 5; ++j) ix.L2[j] = b->L2[j];
 		ix.sa = nullptr; ix.n_sa = 0; ix.sa_intv = 32;
@@ -253,6 +260,31 @@ static int upload_index_one(Ctx *c, bwt_t *const bwt[2], const ubyte_t *pac, int
 		c->l_pac = l_pac;
 		c->has_pac = true;
 	}
+	// L2 persistence for the occ blocks (B200: 126 MB L2).  The window covers both strands;
+	// when the index is larger than the persisting carve-out, hitRatio keeps a random
+	// subset resident instead of thrashing.  Stack/width traffic is marked streaming.
+	{
+		int max_persist = 0, max_window = 0;
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->dev);
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->dev);
+		const char *env = getenv("BWAGPU_L2_PERSIST");
+		const bool on = env && atoi(env) != 0; // measured slower on B200 for a 100 MB index (profiles/): opt-in
+		const size_t bytes = blk_total * sizeof(uint4);
+		if (on && max_persist > 0 && max_window > 0) {
+			const size_t carve = std::min((size_t)max_persist, bytes);
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+				cudaStreamAttrValue av;
+				memset(&av, 0, sizeof av);
+				av.accessPolicyWindow.base_ptr = c->blk_all.p;
+				av.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+				av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				cudaStreamSetAttribute(c->st, cudaStreamAttributeAccessPolicyWindow, &av);
+			}
+			cudaGetLastError(); // persistence is a hint: never fatal
+		}
+	}
 	c->has_index = true;
 	c->res_valid = false;
 	return 0;
@@ -271,6 +303,18 @@ extern "C" int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64
 extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
 
 // ------------------------------------------------------------------ device pipeline for one resident chunk
+static const int N_TIERS = 4;
+
+static uint32_t env_u32(const char *name, uint32_t dflt)
+{
+	const char *e = getenv(name);
+	return e && atoll(e) > 0 ? (uint32_t)atoll(e) : dflt;
+}
+
+// Tier t = (stack arena entries per thread, hit-list capacity, resident threads).  Every read
+// starts in tier 0; a read whose stack or hit list outgrows its tier is retried from scratch
+// in the next one (fewer threads, bigger arenas).  The last tier holds opt->max_entries + 16
+// entries, which the search can never exceed (bwtgap.c:140 stops it first).
 static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt)
 {
 	Tier &T = c->tier[t];
@@ -279,19 +323,21 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 		if (g_stats_enabled) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true>, 128, 0));
 		else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false>, 128, 0));
 		if (bps < 1) bps = 1;
-		const char *env = getenv("BWAGPU_T1_BLOCKS_PER_SM");
-		if (env && atoi(env) > 0) bps = std::min(bps, atoi(env));
+		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_T1_BLOCKS_PER_SM", 64));
 		T.slots_blocks = (uint32_t)(bps * c->n_sm);
-		env = getenv("BWAGPU_T1_CAP");
-		T.cap = env && atoi(env) > 0 ? (uint32_t)atoi(env) : 1024;
+		T.cap = env_u32("BWAGPU_T1_CAP", 2048);
 		T.aln_cap = 64;
 	} else if (t == 1) {
-		T.slots_blocks = 64; // 8192 slots
-		T.cap = 65536; T.aln_cap = 4096;
+		T.slots_blocks = env_u32("BWAGPU_T2_BLOCKS", 256); // 32768 threads
+		T.cap = env_u32("BWAGPU_T2_CAP", 8192); T.aln_cap = 512;
+	} else if (t == 2) {
+		T.slots_blocks = 16; // 2048 threads
+		T.cap = 131072; T.aln_cap = 8192;
 	} else {
-		T.slots_blocks = 2; // 256 slots
+		T.slots_blocks = 1; // 128 threads
 		T.cap = max_entries_opt + 16; T.aln_cap = 1u << 18;
 	}
+	if (T.cap > max_entries_opt + 16) T.cap = max_entries_opt + 16;
 	const size_t slots = (size_t)T.slots_blocks * 128;
 	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap) || T.heads.reserve(slots * n_stacks) ||
 	    T.alnbuf.reserve(slots * T.aln_cap))
@@ -309,7 +355,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
-	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(4)) return 1;
+	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(8)) return 1;
 	size_t pool_cap = std::max<size_t>((size_t)n * 8, 1u << 20);
 	if (pool_cap > 0xfffffff0ull) pool_cap = 0xfffffff0ull;
 	if (c->d_pool.reserve(pool_cap)) return 1;
@@ -328,7 +374,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	B.n_stacks = n_stacks;
 
 	CK(cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(int), c->st));
-	if (stats) CK(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st));
+	if (stats) CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), c->st));
 
 	// K2
 	B.jobs = nullptr; B.n_jobs = n;
@@ -345,18 +391,18 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	}
 	CK(cudaEventRecord(c->ev[2], c->st));
 	if (stats) {
-		unsigned long long hs[4];
+		unsigned long long hs[8];
 		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaStreamSynchronize(c->st));
 		c->stats.occ_fetches_width += (int64_t)hs[0];
 		c->stats.own_fetches_width += (int64_t)hs[1];
-		CK(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st));
+		CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), c->st));
 	}
 
 	// K3, tier by tier
 	int n_jobs = n;
 	const int32_t *jobs = nullptr;
-	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
+	for (int t = 0; t < N_TIERS && n_jobs > 0; ++t) {
 		if (tier_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
 		Tier &T = c->tier[t];
 		B.ent = T.ent.p; B.nxt = T.nxt.p; B.heads = T.heads.p; B.alnbuf = T.alnbuf.p;
@@ -365,6 +411,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		int32_t *ovf = (t & 1) ? c->d_jobs_b.p : c->d_jobs_a.p;
 		B.overflow_ids = ovf;
 		CK(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(int), c->st)); // work + overflow counters
+		CK(cudaEventRecord(c->ev[8 + 2 * t], c->st));
 		if (t > 0) { // pristine widths for the reads being retried
 			const int wb = (int)((4ll * n_jobs + 127) / 128);
 			if (stats) k_width<true><<<wb, 128, 0, c->st>>>(B);
@@ -379,8 +426,14 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		else k_search<false><<<blocks, 128, 0, c->st>>>(B);
 		CK(cudaGetLastError());
 		c->stats.launches++;
+		CK(cudaEventRecord(c->ev[9 + 2 * t], c->st));
 		CK(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
 		CK(cudaStreamSynchronize(c->st));
+		{
+			float tms = 0;
+			CK(cudaEventElapsedTime(&tms, c->ev[8 + 2 * t], c->ev[9 + 2 * t]));
+			c->stats.ms_tier[t] += tms;
+		}
 		const int n_over = c->h_counters.p[1];
 		const unsigned int pool_used = (unsigned int)c->h_counters.p[2];
 		if (pool_used > pool_cap) { // the shared pool ran out: grow it and rerun the flagged reads at this tier
@@ -388,20 +441,21 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		}
 		if (t == 0) c->stats.n_overflow_t2 += n_over;
 		if (t == 1) c->stats.n_overflow_t3 += n_over;
-		if (n_over > 0 && t == 2)
+		if (n_over > 0 && t == N_TIERS - 1)
 			return fail("%d reads exceeded the largest search tier (stack > max_entries+16 or > %u hits)", n_over, T.aln_cap);
 		jobs = ovf;
 		n_jobs = n_over;
 	}
 	CK(cudaEventRecord(c->ev[3], c->st));
 	if (stats) {
-		unsigned long long hs[4];
+		unsigned long long hs[8];
 		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaStreamSynchronize(c->st));
 		c->stats.occ_fetches_search += (int64_t)hs[0];
 		c->stats.own_fetches_search += (int64_t)hs[1];
 		c->stats.n_pops += (int64_t)hs[2];
 		c->stats.n_pushes += (int64_t)hs[3];
+		c->stats.n_stored += (int64_t)hs[4];
 	}
 
 	// ordered compaction: exclusive scan of n_aln (n+1 items so that out_off[n] = total)
@@ -472,18 +526,20 @@ static int run_range(Ctx *c, FlatJob &J)
 		uint32_t n_stacks = 1;
 		for (int i = 0; i < n; ++i) {
 			int len;
+			uint32_t n_amb = 0;
 			uint8_t *dst = c->h_seq.p + so;
 			if (J.seqs) {
 				const bwa_seq_t *p = J.seqs + r0 + i;
 				len = (int)p->len;
-				pack_seq_pair(dst, p->seq, p->rseq, len);
+				n_amb = pack_seq_pair(dst, p->seq, p->rseq, len);
 			} else {
 				const uint8_t *src = J.bases + J.offs[r0 + i];
 				len = (int)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
-				pack_read(dst, src, len);
+				n_amb = pack_read(dst, src, len);
 			}
 			uint64_t we = 0;
 			if (fill_meta(len, so, wo, opt, mdt, c->h_meta.p[i], we, n_stacks)) return 1;
+			c->h_meta.p[i].n_amb = n_amb;
 			so += (uint64_t)len;
 			wo += we;
 			if (wo >= 0xffffffffull) return fail("width arena exceeds 2^32 entries; lower BWAGPU_CHUNK");
@@ -619,7 +675,8 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 		s.n_reads += t.n_reads; s.n_aln += t.n_aln; s.n_overflow_t2 += t.n_overflow_t2; s.n_overflow_t3 += t.n_overflow_t3;
 		s.occ_fetches_width += t.occ_fetches_width; s.occ_fetches_search += t.occ_fetches_search;
 		s.own_fetches_width += t.own_fetches_width; s.own_fetches_search += t.own_fetches_search;
-		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.launches += t.launches;
+		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.launches += t.launches;
+		for (int q = 0; q < 4; ++q) s.ms_tier[q] = std::max(s.ms_tier[q], t.ms_tier[q]);
 	}
 	s.n_devices = (int32_t)g_ctx.size();
 	*out = s;
@@ -644,9 +701,10 @@ extern "C" int bwa_gpu_resident_stage(int n, const uint8_t *bases, const int64_t
 		const uint8_t *src = bases + offs[i];
 		const int len = (int)(offs[i + 1] - offs[i]);
 		uint8_t *dst = c->h_seq.p + so;
-		pack_read(dst, src, len);
+		const uint32_t n_amb = pack_read(dst, src, len);
 		uint64_t we = 0;
 		if (fill_meta(len, so, wo, opt, mdt, c->h_meta.p[i], we, n_stacks)) return 1;
+		c->h_meta.p[i].n_amb = n_amb;
 		so += (uint64_t)len; wo += we;
 		if (wo >= 0xffffffffull) return fail("resident batch too large (width arena)");
 	}

@@ -69,26 +69,35 @@ static inline int fill_meta(int len, uint64_t seq_off, uint64_t w_off, const gap
 	m.len = (uint16_t)len;
 	m.max_diff = (uint8_t)md;
 	m.max_gapo = (uint8_t)go;
-	m.pad = 0;
+	m.n_amb = 0; // filled by pack_*
 	w_entries = len > 0 ? 2 * (uint64_t)(len + 1) + (len > opt->seed_len ? 2 * (uint64_t)(opt->seed_len + 1) : 0) : 0;
 	return 0;
 }
 
 
 // byte j of a packed read = seq[0][j] | seq[1][j] << 4 (values 0..4)
-static inline void pack_seq_pair(uint8_t *dst, const uint8_t *seq, const uint8_t *rseq, int len)
+// Both return the number of ambiguous bases in seq[0] (bwtgap.c:118-119 counts seq[0]).
+static inline uint32_t pack_seq_pair(uint8_t *dst, const uint8_t *seq, const uint8_t *rseq, int len)
 {
-	for (int j = 0; j < len; ++j) dst[j] = (uint8_t)((seq[j] > 3 ? 4 : seq[j]) | (rseq[j] > 3 ? 4 : rseq[j]) << 4);
+	uint32_t n_amb = 0;
+	for (int j = 0; j < len; ++j) {
+		dst[j] = (uint8_t)((seq[j] > 3 ? 4 : seq[j]) | (rseq[j] > 3 ? 4 : rseq[j]) << 4);
+		n_amb += seq[j] > 3;
+	}
+	return n_amb;
 }
 
 // read in sequencing orientation -> seq = reversed read, rseq = reverse complement, i.e.
 // rseq[j] = complement(seq[j])  (bam1_to_seq, bwaseqio.c:294-297 with is_comp = 1)
-static inline void pack_read(uint8_t *dst, const uint8_t *read, int len)
+static inline uint32_t pack_read(uint8_t *dst, const uint8_t *read, int len)
 {
+	uint32_t n_amb = 0;
 	for (int j = 0; j < len; ++j) {
 		const uint8_t b = read[len - 1 - j];
 		dst[j] = (uint8_t)((b > 3 ? 4 : b) | (b > 3 ? 4 : 3 - b) << 4);
+		n_amb += b > 3;
 	}
+	return n_amb;
 }
 
 } // namespace bwagpu

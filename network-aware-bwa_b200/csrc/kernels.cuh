@@ -61,7 +61,7 @@ struct ReadMeta {        // 16 B per read, filled by the host
 	uint16_t len;
 	uint8_t max_diff;    // local_opt.max_diff for this read (bwtaln.c:102,126)
 	uint8_t max_gapo;    // after the clamp of bwtaln.c:103
-	uint32_t pad;
+	uint32_t n_amb;      // bases > 3 in the read (the "too many N" test of bwtgap.c:118-123)
 };
 
 struct Batch {
@@ -92,7 +92,7 @@ struct Batch {
 	uint4 *alnbuf;
 	uint32_t cap, aln_cap, n_stacks;
 	// stats (STATS builds only)
-	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes
+	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes [4] pushes stored in memory
 };
 
 __device__ __forceinline__ uint32_t sel4(uint32_t c, const uint32_t v[4])
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	// per-read state
 	int rid = -1, len = 0, max_diff = 0, opt_max_diff = 0, max_gapo = 0;
 	int best_score = 0, best_cnt = 0, n_aln = 0, n_entries = 0, max_entries = 0;
-	bool has_seed = false, overflow = false;
+	bool has_seed = false, overflow = false, have_best = false;
 	const uint8_t *seq = nullptr;
 	uint32_t *w_base = nullptr;
 	uint16_t *bid_base = nullptr;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	int ii = 0; // exact-tail cursor
 	int m = 0, m_seed = 0, i = 0;
 	uint32_t k = 0, l = 0;
-	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0;
+	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0;
 
 	auto score_of = [&](int mm, int go, int ge) { return mm * O.s_mm + go * O.s_gapo + ge * O.s_gape; };
 
@@ -253,8 +253,15 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		x.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
 		++n_entries;
 		if (STATS) ++n_pushes;
-		if (hold) { held = x; held_valid = true; }
-		else push_mem(x, score_of(mm, go, ge));
+		if (hold) { held = x; held_valid = true; return; }
+		const int s = score_of(mm, go, ge);
+		// Once the first hit fixed best_score, an entry scoring above best_score + s_mm can
+		// never be expanded: popping it ends the search (bwtgap.c:144).  It stays a PHANTOM:
+		// counted in n_entries (max_entries and the max_entries stop are unchanged) but never
+		// stored.  Phantoms outscore every stored entry, so pop order is unaffected.
+		if (have_best && !nonstop && s > best_score + O.s_mm) return;
+		if (STATS) ++n_stored;
+		push_mem(x, s);
 	};
 
 	// copies the finished read's results out and resets the per-slot stack
@@ -286,6 +293,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		const int score = score_of(mm, go, ge);
 		bool do_add = true;
 		if (n_aln == 0) {
+			have_best = true;
 			best_score = score;
 			int best_diff = mm + go;
 			if (gape_mode) best_diff += ge;
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			rid = B.jobs ? B.jobs[job] : job;
 			const ReadMeta md = B.meta[rid];
 			len = md.len;
-			overflow = false;
+			overflow = false; have_best = false;
 			n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
 			if (len == 0) { // bwtaln.c:134: aln = 0, n_aln = 0
 				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
@@ -341,9 +349,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			bid_base = B.bid + md.w_off;
 			best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
 			// too many N? (bwtgap.c:118-123) -- *pmax_entries is left untouched there
-			int n_amb = 0;
-			for (int j = 0; j < len; ++j) n_amb += (seq[j] & 15u) > 3u;
-			if (n_amb > max_diff) {
+			if ((int)md.n_amb > max_diff) {
 				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
 				continue;
 			}
@@ -359,7 +365,9 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			if (n_entries > O.max_entries) { finish_read(); mode = MODE_NEW; continue; }
 			// gap_pop (bwtgap.c:66-79)
 			if (held_valid) { e = held; held_valid = false; }
-			else {
+			else if (!(mask0 | mask1 | mask2 | mask3)) { // only phantoms left: the reference pops one and stops
+				finish_read(); mode = MODE_NEW; continue;
+			} else {
 				const int s = mask_lowest();
 				const uint32_t idx = heads[s];
 				const uint4 q = ent[idx];
@@ -493,6 +501,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		atomicAdd(B.stats + 1, (unsigned long long)f_own);
 		atomicAdd(B.stats + 2, (unsigned long long)n_pops);
 		atomicAdd(B.stats + 3, (unsigned long long)n_pushes);
+		atomicAdd(B.stats + 4, (unsigned long long)n_stored);
 	}
 }
 

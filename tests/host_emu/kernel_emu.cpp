@@ -78,9 +78,10 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	uint32_t n_stacks = 1;
 	for (int i = 0; i < n; ++i) {
 		const int len = (int)(offs[i + 1] - offs[i]);
-		pack_read(seq.data() + so, bases + offs[i], len);
+		const uint32_t n_amb = pack_read(seq.data() + so, bases + offs[i], len);
 		uint64_t we = 0;
 		if (fill_meta(len, so, wo, opt, mdt, meta[i], we, n_stacks)) return 1;
+		meta[i].n_amb = n_amb;
 		so += len; wo += we;
 	}
 	std::vector<uint32_t> w(wo + 1);
@@ -89,7 +90,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	std::vector<uint4> pool((size_t)n * 64 + (1 << 16));
 	std::vector<int32_t> jobs_a(n), jobs_b(n);
 	int counters[4] = {0, 0, 0, 0};
-	unsigned long long stats[4] = {0, 0, 0, 0};
+	unsigned long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	Batch B;
 	B.ix[0] = E->ix[0]; B.ix[1] = E->ix[1];
 	B.opt = to_gapopt(opt);
@@ -109,8 +110,8 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	if (stats8) { stats8[0] = stats[0]; stats8[1] = stats[1]; }
 	stats[0] = stats[1] = 0;
 	// K3 tiers
-	const uint32_t caps[3] = {cap1, 65536u, (uint32_t)opt->max_entries + 16u};
-	const uint32_t acaps[3] = {aln_cap1, 4096u, 1u << 18};
+	const uint32_t caps[3] = {cap1, 8192u, (uint32_t)opt->max_entries + 16u};
+	const uint32_t acaps[3] = {aln_cap1, 512u, 1u << 18};
 	int n_jobs = n;
 	const int32_t *jobs = nullptr;
 	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
@@ -129,7 +130,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		if (counters[1] > 0 && t == 2) { g_err = "reads exceeded the largest tier"; return 1; }
 		jobs = ovf; n_jobs = counters[1];
 	}
-	if (stats8) { stats8[2] = stats[0]; stats8[3] = stats[1]; stats8[7] = stats[2]; }
+	if (stats8) { stats8[2] = stats[0]; stats8[3] = stats[1]; stats8[7] = stats[2]; stats8[6] = stats[4]; }
 	int64_t acc = 0;
 	for (int i = 0; i < n; ++i) { aln_off[i] = acc; acc += n_aln[i]; }
 	aln_off[n] = acc;

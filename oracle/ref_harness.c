@@ -109,6 +109,56 @@ int refh_sw1(const uint8_t *ref, int l_ref, const uint8_t *query, int l_query,
 	return score;
 }
 
+/* Forward score + start/end cells of aln_local_core without the path-filling third pass:
+ * path_len == NULL makes it store (start_i,start_j),(end_i,end_j) in path[0..1]
+ * (stdaln.c:708-712); _thres = 0 keeps the NULL path_len from being dereferenced at
+ * stdaln.c:634.  Passes 1 and 2 do not depend on _thres. */
+int refh_sw_ends(const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int32_t out[4])
+{
+	path_t path[2];
+	int score;
+	memset(path, 0, sizeof path);
+	score = aln_local_core((unsigned char *)ref, l_ref, (unsigned char *)query, l_query, &aln_param_bwa, path, 0, 0, 0);
+	out[0] = path[0].i; out[1] = path[0].j; out[2] = path[1].i; out[3] = path[1].j;
+	return score;
+}
+
+typedef struct {
+	int n, tid, nthreads;
+	const uint8_t *refs, *queries;
+	const int64_t *ref_off, *q_off;
+	int32_t *out; /* 5 per job: score, start_i, start_j, end_i, end_j */
+} sw_job_t;
+
+static void *sw_worker(void *p)
+{
+	sw_job_t *j = (sw_job_t *)p;
+	int i;
+	for (i = j->tid; i < j->n; i += j->nthreads)
+		j->out[5 * i] = refh_sw_ends(j->refs + j->ref_off[i], (int)(j->ref_off[i + 1] - j->ref_off[i]),
+		                             j->queries + j->q_off[i], (int)(j->q_off[i + 1] - j->q_off[i]), j->out + 5 * i + 1);
+	return 0;
+}
+
+int refh_sw_batch(int n, const uint8_t *refs, const int64_t *ref_off, const uint8_t *queries, const int64_t *q_off,
+                  int32_t *out, int nthreads)
+{
+	int t;
+	pthread_t *th;
+	sw_job_t *jobs;
+	if (nthreads < 1) nthreads = 1;
+	th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+	jobs = (sw_job_t *)calloc(nthreads, sizeof(sw_job_t));
+	for (t = 0; t < nthreads; ++t) {
+		jobs[t].n = n; jobs[t].tid = t; jobs[t].nthreads = nthreads;
+		jobs[t].refs = refs; jobs[t].queries = queries; jobs[t].ref_off = ref_off; jobs[t].q_off = q_off; jobs[t].out = out;
+		pthread_create(&th[t], 0, sw_worker, &jobs[t]);
+	}
+	for (t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+	free(th); free(jobs);
+	return 0;
+}
+
 #ifndef REFH_SHARED
 int main(void)
 {

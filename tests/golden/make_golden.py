@@ -8,7 +8,8 @@ oracle/_ref to pin parity.
 Contents: genome (uint8 0..3); per config c in CONFIGS: c_bases, c_offs (reads), c_opt (the 16
 gap_opt_t words), c_n_aln, c_max_entries, c_aln (bwt_aln1_t bytes as u32[n,4]) from
 bwa_cal_sa_reg_gap(bwt, 1, &seq, opt) (bwtaln.c:93), plus sa_k, sa_which, sa_out from bwt_sa
-(bwt.c:72) and maxdiff tables from bwa_cal_maxdiff (bwtaln.c:37).
+(bwt.c:72), maxdiff tables from bwa_cal_maxdiff (bwtaln.c:37), and sw_* = Smith-Waterman jobs with
+(score, start_i, start_j, end_i, end_j) from aln_local_core (stdaln.c:529).
 """
 import ctypes as C
 import os
@@ -80,6 +81,10 @@ def main():
     L, _ = R.ref()
     out["maxdiff_004"] = np.array([L.bwa_cal_maxdiff(l, 0.02, float(np.float32(0.04))) for l in range(0, 400)], dtype=np.int32)
     out["maxdiff_001"] = np.array([L.bwa_cal_maxdiff(l, 0.02, float(np.float32(0.01))) for l in range(0, 400)], dtype=np.int32)
+    # aln_local_core forward score + start/end cells (stdaln.c:529-712) on mate-rescue-like jobs
+    refs, ro, qs, qo = R.make_sw_jobs(T, 2000, seed=17)
+    out["sw_refs"], out["sw_ref_off"], out["sw_queries"], out["sw_q_off"] = refs, ro, qs, qo
+    out["sw_out"] = R.ref_sw_batch(refs, ro, qs, qo)
     np.savez_compressed(os.path.join(HERE, "aln_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "aln_golden.npz"), os.path.getsize(os.path.join(HERE, "aln_golden.npz")))
 

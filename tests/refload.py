@@ -158,3 +158,145 @@ def compare_aln(a, b, label=""):
                          (aa["score"] != ab["score"]))[0]
         errs.append(f"{label} aln records differ at {neq.size} positions, first {neq[:5]}: {aa[neq[:3]]} vs {ab[neq[:3]]}")
     return errs
+
+
+# ---------------------------------------------------------------- this repo's C restatement (oracle/liboracle.so)
+class orc_index_t(C.Structure):
+    _fields_ = [("primary", C.c_uint32), ("seq_len", C.c_uint32), ("L2", C.c_uint32 * 5),
+                ("bwt", C.POINTER(C.c_uint32)), ("sa", C.POINTER(C.c_uint32)), ("sa_intv", C.c_int)]
+
+
+class orc_opt_t(C.Structure):
+    _fields_ = [("s_mm", C.c_int), ("s_gapo", C.c_int), ("s_gape", C.c_int), ("mode", C.c_int),
+                ("indel_end_skip", C.c_int), ("max_del_occ", C.c_int), ("max_entries", C.c_int),
+                ("fnr", C.c_double),
+                ("max_diff", C.c_int), ("max_gapo", C.c_int), ("max_gape", C.c_int), ("max_seed_diff", C.c_int),
+                ("seed_len", C.c_int), ("max_top2", C.c_int)]
+
+
+_orc = None
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        so = os.path.join(ROOT, "oracle", "liboracle.so")
+        src = [os.path.join(ROOT, "oracle", f) for f in ("bwa_oracle.c", "bwa_oracle.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+            subprocess.run(["gcc", "-O2", "-Wall", "-fPIC", "-shared", "-o", so, src[0], "-lm"], check=True)
+        O = C.CDLL(so)
+        O.orc_occ.argtypes = [C.POINTER(orc_index_t), C.c_uint32, C.c_int]
+        O.orc_occ.restype = C.c_uint32
+        O.orc_sa.argtypes = [C.POINTER(orc_index_t), C.c_uint32]
+        O.orc_sa.restype = C.c_uint32
+        O.orc_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
+        O.orc_aln_flat.argtypes = [C.POINTER(orc_index_t), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(orc_opt_t),
+                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        O.orc_free.argtypes = [C.c_void_p]
+        O.orc_sw_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        _orc = O
+    return _orc
+
+
+def orc_index(idx):
+    arr = (orc_index_t * 2)()
+    for s in range(2):
+        b = idx.bwt[s]
+        arr[s].primary, arr[s].seq_len, arr[s].sa_intv = b.primary, b.seq_len, b.sa_intv
+        for i in range(5):
+            arr[s].L2[i] = int(b.L2[i])
+        arr[s].bwt = b.bwt.ctypes.data_as(C.POINTER(C.c_uint32))
+        arr[s].sa = b.sa.ctypes.data_as(C.POINTER(C.c_uint32))
+    return arr
+
+
+def orc_opt(opt) -> orc_opt_t:
+    o = orc_opt_t()
+    for f, _ in orc_opt_t._fields_:
+        setattr(o, f, getattr(opt, f))
+    return o
+
+
+def orc_aln(oidx, reads, opt):
+    O = orc()
+    n = reads.n
+    bases = np.ascontiguousarray(reads.bases, dtype=np.uint8)
+    offs = np.ascontiguousarray(reads.offs, dtype=np.int64)
+    n_aln = np.empty(n, dtype=np.int32)
+    max_entries = np.zeros(n, dtype=np.int32)
+    pool = C.c_void_p()
+    oo = orc_opt(opt)
+    O.orc_aln_flat(oidx, n, bases.ctypes.data, offs.ctypes.data, C.byref(oo), n_aln.ctypes.data, max_entries.ctypes.data,
+                   C.byref(pool))
+    aln_off = np.zeros(n + 1, dtype=np.int64)
+    aln_off[1:] = np.cumsum(n_aln)
+    tot = int(aln_off[n])
+    aln = np.empty(tot, dtype=abi.ALN_DTYPE)
+    if tot:
+        buf = (C.c_char * (16 * tot)).from_address(pool.value)
+        aln[:] = np.frombuffer(buf, dtype=abi.ALN_DTYPE, count=tot)
+    O.orc_free(pool)
+    return n_aln, max_entries, aln_off, aln
+
+
+def orc_sw_batch(refs, ref_off, queries, q_off) -> np.ndarray:
+    """-> int32[n,5]: score, start_i, start_j, end_i, end_j"""
+    O = orc()
+    n = ref_off.size - 1
+    out = np.zeros((n, 5), dtype=np.int32)
+    res = (C.c_int * 4)()
+    for i in range(n):
+        r = np.ascontiguousarray(refs[ref_off[i]:ref_off[i + 1]])
+        q = np.ascontiguousarray(queries[q_off[i]:q_off[i + 1]])
+        out[i, 0] = O.orc_sw_local(r.ctypes.data, r.size, q.ctypes.data, q.size, res)
+        out[i, 1:] = list(res)
+    return out
+
+
+def ref_sw_batch(refs, ref_off, queries, q_off, threads: int = 8) -> np.ndarray:
+    _, H = ref()
+    H.refh_sw_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    refs = np.ascontiguousarray(refs, dtype=np.uint8)
+    queries = np.ascontiguousarray(queries, dtype=np.uint8)
+    ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+    q_off = np.ascontiguousarray(q_off, dtype=np.int64)
+    n = ref_off.size - 1
+    out = np.zeros((n, 5), dtype=np.int32)
+    H.refh_sw_batch(n, refs.ctypes.data, ref_off.ctypes.data, queries.ctypes.data, q_off.ctypes.data, out.ctypes.data, threads)
+    return out
+
+
+def make_sw_jobs(T, n_jobs: int, seed: int, read_len=(30, 120), win=(60, 420)):
+    """Mate-rescue-like SW jobs: a reference window and a read that (mostly) comes from it,
+    with substitutions, an indel, N, or nothing in common.  -> refs, ref_off, queries, q_off"""
+    rng = np.random.default_rng(seed)
+    refs, queries, ro, qo = [], [], [0], [0]
+    n = T.size
+    for j in range(n_jobs):
+        L = int(rng.integers(read_len[0], read_len[1] + 1))
+        W = int(rng.integers(max(win[0], 20), win[1] + 1))
+        beg = int(rng.integers(0, n - W - 1))
+        window = T[beg:beg + W].copy()
+        kind = j % 8
+        if kind == 7:  # unrelated read
+            q = rng.integers(0, 4, size=L, dtype=np.uint8)
+        else:
+            L = min(L, W)
+            s = int(rng.integers(0, W - L + 1))
+            q = window[s:s + L].copy()
+            sub = rng.random(L) < (0.02 if kind < 4 else 0.10)
+            q[sub] = (q[sub] + rng.integers(1, 4, size=int(sub.sum()), dtype=np.uint8)) & 3
+            if kind in (2, 5) and L > 20:  # deletion from the read
+                p, d = int(rng.integers(5, L - 10)), int(rng.integers(1, 6))
+                q = np.concatenate([q[:p], q[p + d:]])
+            if kind in (3, 6) and L > 20:  # insertion into the read
+                p, d = int(rng.integers(5, L - 10)), int(rng.integers(1, 6))
+                q = np.concatenate([q[:p], rng.integers(0, 4, size=d, dtype=np.uint8), q[p:]])
+            if kind == 4:
+                q[rng.random(q.size) < 0.03] = 4
+        if j % 11 == 0:
+            window[rng.random(W) < 0.02] = 4
+        refs.append(window); queries.append(q.astype(np.uint8))
+        ro.append(ro[-1] + window.size); qo.append(qo[-1] + q.size)
+    return (np.concatenate(refs).astype(np.uint8), np.array(ro, dtype=np.int64),
+            np.concatenate(queries).astype(np.uint8), np.array(qo, dtype=np.int64))

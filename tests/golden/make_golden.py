@@ -85,6 +85,10 @@ def main():
     refs, ro, qs, qo = R.make_sw_jobs(T, 2000, seed=17)
     out["sw_refs"], out["sw_ref_off"], out["sw_queries"], out["sw_q_off"] = refs, ro, qs, qo
     out["sw_out"] = R.ref_sw_batch(refs, ro, qs, qo)
+    # the same on windows of the packed genome (what bwa_sw_core feeds it, bwape.c:447-456): K5's input
+    refs, ro, qs, qo, begs = R.make_sw_jobs(T, 3000, seed=23, ref_n=False, with_beg=True, read_len=(25, 150), win=(30, 700))
+    out["swp_beg"], out["swp_reglen"], out["swp_queries"], out["swp_q_off"] = begs, np.diff(ro).astype(np.int32), qs, qo
+    out["swp_out"] = R.ref_sw_batch(refs, ro, qs, qo)
     np.savez_compressed(os.path.join(HERE, "aln_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "aln_golden.npz"), os.path.getsize(os.path.join(HERE, "aln_golden.npz")))
 

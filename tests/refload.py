@@ -266,11 +266,11 @@ def ref_sw_batch(refs, ref_off, queries, q_off, threads: int = 8) -> np.ndarray:
     return out
 
 
-def make_sw_jobs(T, n_jobs: int, seed: int, read_len=(30, 120), win=(60, 420)):
+def make_sw_jobs(T, n_jobs: int, seed: int, read_len=(30, 120), win=(60, 420), ref_n=True, with_beg=False):
     """Mate-rescue-like SW jobs: a reference window and a read that (mostly) comes from it,
     with substitutions, an indel, N, or nothing in common.  -> refs, ref_off, queries, q_off"""
     rng = np.random.default_rng(seed)
-    refs, queries, ro, qo = [], [], [0], [0]
+    refs, queries, ro, qo, begs = [], [], [0], [0], []
     n = T.size
     for j in range(n_jobs):
         L = int(rng.integers(read_len[0], read_len[1] + 1))
@@ -294,9 +294,11 @@ def make_sw_jobs(T, n_jobs: int, seed: int, read_len=(30, 120), win=(60, 420)):
                 q = np.concatenate([q[:p], rng.integers(0, 4, size=d, dtype=np.uint8), q[p:]])
             if kind == 4:
                 q[rng.random(q.size) < 0.03] = 4
-        if j % 11 == 0:
+        if ref_n and j % 11 == 0:
             window[rng.random(W) < 0.02] = 4
+        begs.append(beg)
         refs.append(window); queries.append(q.astype(np.uint8))
         ro.append(ro[-1] + window.size); qo.append(qo[-1] + q.size)
-    return (np.concatenate(refs).astype(np.uint8), np.array(ro, dtype=np.int64),
-            np.concatenate(queries).astype(np.uint8), np.array(qo, dtype=np.int64))
+    out = (np.concatenate(refs).astype(np.uint8), np.array(ro, dtype=np.int64),
+           np.concatenate(queries).astype(np.uint8), np.array(qo, dtype=np.int64))
+    return out + (np.array(begs, dtype=np.int64),) if with_beg else out

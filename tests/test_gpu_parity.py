@@ -164,3 +164,42 @@ def test_exact_reads_are_found_at_their_origin(gpu_index):
     np.logical_or.at(hit, owner, pos == reads.pos[owner])
     full = (first["l"] - first["k"] + 1) <= 64
     assert hit[full].all()
+
+
+def sw_jobs_from(begs, reglens, queries, q_off):
+    return [(int(begs[i]), int(reglens[i]), queries[q_off[i]:q_off[i + 1]]) for i in range(len(begs))]
+
+
+def test_mate_sw_matches_golden(golden, gpu_index):
+    """K5: score, start and end cells of aln_local_core on pac windows (bwape.c:447-456)."""
+    jobs = sw_jobs_from(golden["swp_beg"], golden["swp_reglen"], golden["swp_queries"], golden["swp_q_off"])
+    got = np.array(api.mate_sw(jobs), dtype=np.int32)
+    want = golden["swp_out"]
+    bad = np.nonzero((got != want).any(1))[0]
+    assert bad.size == 0, (bad[:5], got[bad[:5]], want[bad[:5]])
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+def test_mate_sw_matches_reference_live(gpu_index):
+    T, idx = gpu_index
+    # wide windows (several 512-column sweeps), long and short reads, window clipped at the genome end
+    refs, ro, qs, qo, begs = R.make_sw_jobs(T, 6000, seed=1234, ref_n=False, with_beg=True, read_len=(20, 260), win=(20, 1400))
+    reglens = np.diff(ro).astype(np.int32)
+    want = R.ref_sw_batch(refs, ro, qs, qo)
+    got = np.array(api.mate_sw(sw_jobs_from(begs, reglens, qs, qo)), dtype=np.int32)
+    bad = np.nonzero((got != want).any(1))[0]
+    assert bad.size == 0, (bad[:5], got[bad[:5]], want[bad[:5]])
+    # a window running past l_pac is clipped like bwa_sw_core's copy loop
+    n = idx.l_pac
+    q = T[n - 60:n - 10].copy()
+    got = api.mate_sw([(n - 100, 400, q)])
+    win = T[n - 100:n]
+    want = R.ref_sw_batch(win, np.array([0, win.size]), q, np.array([0, q.size]))
+    assert list(got[0]) == list(want[0])
+
+
+def test_mate_sw_empty_inputs(gpu_index):
+    T, idx = gpu_index
+    assert api.mate_sw([]) == []
+    got = api.mate_sw([(10, 0, T[:30]), (10, 50, T[:0])])
+    assert got[0][0] == -1 and got[1][0] == -1  # stdaln.c:559

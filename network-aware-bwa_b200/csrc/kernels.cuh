@@ -156,23 +156,34 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 // thread, persistent threads pulling reads from a global counter.
 //
 // Exactness: the traversal order is the reference's -- lowest non-empty score bucket
-// first, LIFO inside a bucket, pushes in the order insertion / deletions c=0..3 /
+// first, LIFO inside a bucket, children in the order insertion / deletions c=0..3 /
 // mismatches c=(str[i]+j)&3 j=1..4.  Buckets are singly linked lists threaded through a
-// per-thread entry arena (the reference uses realloc-doubling arrays; only the order is
-// observable).  Two things never reach memory:
+// per-thread arena (the reference uses realloc-doubling arrays; only the order is
+// observable).  What is stored differs from the reference, what is popped does not:
 //   * the match continuation (pushed last, same score as the entry just popped, hence
-//     always the very next pop) is carried in registers (`held`);
+//     always the very next pop) is carried in registers (`held`) and never stored;
+//   * GROUP RECORDS: the children one expansion sends to the same bucket (the gap children:
+//     insertion + deletions; the mismatch children) are consecutive in that bucket's LIFO,
+//     so they are stored as ONE 16-byte record = the parent node + a bit mask of the
+//     children still to come.  Popping takes the highest set bit (the child pushed last),
+//     rewrites the mask in place (the record stays on top) and re-derives the child's
+//     SA interval from the parent's with one extra occurrence lookup -- and only if the
+//     child survives the cheap pruning tests.  An expansion therefore stores at most two
+//     records instead of up to nine entries;
+//   * PHANTOMS: once the first hit fixed best_score, children scoring above best_score +
+//     s_mm can only ever end the search when popped (bwtgap.c:144); they are counted but
+//     not stored;
 //   * the arena slot freed by the latest pop is kept in a register for the next push.
-// n_entries still counts held entries, so max_entries and the `> opt->max_entries` stop
-// (bwtgap.c:139-140) are unchanged.
+// n_entries counts every child individually, stored or not, so max_entries and the
+// `> opt->max_entries` stop (bwtgap.c:139-140) are the reference's.
 //
 // The per-thread control flow is a small state machine so that the lanes of a warp meet
-// at ONE occurrence lookup per trip whatever each lane is doing (expanding a node or
-// walking the exact-match tail of bwtgap.c:163-164 / bwt.c:237-252).
+// at ONE occurrence lookup per trip whatever each lane is doing (expanding a node,
+// deriving a group child, or walking the exact-match tail of bwt.c:237-252).
 struct Entry {
 	uint32_t k, l;
-	uint32_t pos;  // i | last_diff_pos << 16
-	uint32_t tag;  // n_mm | n_gapo << 8 | n_gape << 16 | state << 24 | a << 26
+	uint32_t pos;  // plain: i | last_diff_pos << 16      group: parent i (after --i) | child mask << 16
+	uint32_t tag;  // n_mm | n_gapo << 8 | n_gape << 16 | state << 24 | a << 26 | kind << 27
 };
 
 #define E_I(e) ((int)((e).pos & 0xffffu))
@@ -182,8 +193,11 @@ struct Entry {
 #define E_GE(e) ((int)(((e).tag >> 16) & 0xffu))
 #define E_ST(e) (((e).tag >> 24) & 3u)
 #define E_A(e) (((e).tag >> 26) & 1u)
+#define KIND_PLAIN 0u
+#define KIND_GAP 1u // bit 0 = insertion (child i = parent i), bit 1+c = deletion of c (child i = parent i + 1)
+#define KIND_MM 2u  // bit j-1 = mismatch child c = (str[i] + j) & 3
 
-enum { MODE_NEW = 0, MODE_POP = 1, MODE_EXACT = 2, MODE_EXPAND = 3 };
+enum { MODE_NEW = 0, MODE_POP = 1, MODE_DECIDE = 2, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND = 5 };
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) k_search(const Batch B)
@@ -196,8 +210,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	const GapOpt &O = B.opt;
 	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
 
-	// heads start empty for this launch
-	for (uint32_t s = 0; s < B.n_stacks; ++s) heads[s] = NIL;
+	for (uint32_t s = 0; s < B.n_stacks; ++s) heads[s] = NIL; // heads start empty for this launch
 
 	int mode = MODE_NEW;
 	// per-read state
@@ -209,9 +222,10 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	uint16_t *bid_base = nullptr;
 	uint64_t mask0 = 0, mask1 = 0, mask2 = 0, mask3 = 0; // non-empty buckets
 	uint32_t bump = 0, free_head = NIL, spare = NIL;
-	Entry held; bool held_valid = false;
-	Entry e = {0, 0, 0, 0}; // entry being processed
-	int ii = 0; // exact-tail cursor
+	Entry held = {0, 0, 0, 0}; bool held_valid = false;
+	Entry e = {0, 0, 0, 0}; // node being processed (always a plain node)
+	uint32_t derive_c = 0;  // MODE_DERIVE: which child interval of e.{k,l} to take
+	int ii = 0;             // exact-tail cursor
 	int m = 0, m_seed = 0, i = 0;
 	uint32_t k = 0, l = 0;
 	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0;
@@ -233,35 +247,21 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		return 192 + __ffsll((long long)mask3) - 1;
 	};
 
-	// gap_push (bwtgap.c:45-64) to the in-memory bucket lists
-	auto push_mem = [&](const Entry &x, int s) {
+	// gap_push (bwtgap.c:45-64): one record holding n_children nodes of score s
+	auto push_rec = [&](uint32_t rk, uint32_t rl, uint32_t pos, uint32_t tag, int s, int n_children) {
+		n_entries += n_children;
+		if (STATS) n_pushes += n_children;
+		if (have_best && !nonstop && s > best_score + O.s_mm) return; // phantoms: counted, never stored
+		if (STATS) ++n_stored;
 		uint32_t idx;
 		if (spare != NIL) { idx = spare; spare = NIL; }
 		else if (free_head != NIL) { idx = free_head; free_head = nxt[idx]; }
 		else if (bump < B.cap) idx = bump++;
 		else { overflow = true; return; }
-		ent[idx] = make_uint4(x.k, x.l, x.pos, x.tag);
+		ent[idx] = make_uint4(rk, rl, pos, tag);
 		nxt[idx] = heads[s];
 		heads[s] = idx;
 		mask_set(s);
-	};
-	auto push = [&](uint32_t a, int pi, uint32_t pk, uint32_t pl, int mm, int go, int ge, uint32_t st, bool is_diff,
-	                bool hold) {
-		Entry x;
-		x.k = pk; x.l = pl;
-		x.pos = (uint32_t)pi | (is_diff ? (uint32_t)pi << 16 : 0u);
-		x.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
-		++n_entries;
-		if (STATS) ++n_pushes;
-		if (hold) { held = x; held_valid = true; return; }
-		const int s = score_of(mm, go, ge);
-		// Once the first hit fixed best_score, an entry scoring above best_score + s_mm can
-		// never be expanded: popping it ends the search (bwtgap.c:144).  It stays a PHANTOM:
-		// counted in n_entries (max_entries and the max_entries stop are unchanged) but never
-		// stored.  Phantoms outscore every stored entry, so pop order is unaffected.
-		if (have_best && !nonstop && s > best_score + O.s_mm) return;
-		if (STATS) ++n_stored;
-		push_mem(x, s);
 	};
 
 	// copies the finished read's results out and resets the per-slot stack
@@ -353,9 +353,11 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
 				continue;
 			}
-			push(0u, len, 0u, B.ix[0].seq_len, 0, 0, 0, STATE_M, false, false);
-			push(1u, len, 0u, B.ix[0].seq_len, 0, 0, 0, STATE_M, false, true);
-			if (overflow) { finish_read(); continue; }
+			// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
+			push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
+			held.k = 0u; held.l = B.ix[0].seq_len; held.pos = (uint32_t)len; held.tag = 1u << 26;
+			held_valid = true; ++n_entries;
+			if (STATS) ++n_pushes;
 			mode = MODE_POP;
 		}
 
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			if (overflow || n_entries == 0) { finish_read(); mode = MODE_NEW; continue; }
 			if (max_entries < n_entries) max_entries = n_entries;
 			if (n_entries > O.max_entries) { finish_read(); mode = MODE_NEW; continue; }
+			bool need_derive = false;
 			// gap_pop (bwtgap.c:66-79)
 			if (held_valid) { e = held; held_valid = false; }
 			else if (!(mask0 | mask1 | mask2 | mask3)) { // only phantoms left: the reference pops one and stops
@@ -371,12 +374,38 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				const int s = mask_lowest();
 				const uint32_t idx = heads[s];
 				const uint4 q = ent[idx];
-				const uint32_t nx = nxt[idx];
-				heads[s] = nx;
-				if (nx == NIL) mask_clear(s);
-				if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
-				spare = idx;
-				e.k = q.x; e.l = q.y; e.pos = q.z; e.tag = q.w;
+				const uint32_t kind = (q.w >> 27) & 3u;
+				uint32_t gm = 0, b = 0;
+				if (kind != KIND_PLAIN) {
+					gm = (q.z >> 16) & 31u;
+					b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
+					gm &= ~(1u << b);
+				}
+				if (gm) ent[idx].z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
+				else { // unlink
+					const uint32_t nx = nxt[idx];
+					heads[s] = nx;
+					if (nx == NIL) mask_clear(s);
+					if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
+					spare = idx;
+				}
+				e.k = q.x; e.l = q.y;
+				if (kind == KIND_PLAIN) { e.pos = q.z; e.tag = q.w; }
+				else {
+					const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
+					uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
+					if (kind == KIND_MM) {
+						const uint32_t cb = (seq[pi] >> (a << 2)) & 15u;
+						derive_c = (cb + b + 1u) & 3u;
+						++mm; ci = pi; st = STATE_M; need_derive = true;
+					} else {
+						if (pst == STATE_M) ++go; else ++ge;
+						if (b == 0) { ci = pi; st = STATE_I; }
+						else { ci = pi + 1u; st = STATE_D; derive_c = b - 1u; need_derive = true; }
+					}
+					e.pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
+					e.tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
+				}
 			}
 			--n_entries;
 			if (STATS) ++n_pops;
@@ -390,15 +419,20 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				m_seed = O.max_seed_diff - (mm + go);
 				if (gape_mode) m_seed -= ge;
 			}
+			if (i > 0 && m < (int)bid_base[(size_t)E_A(e) * (len + 1) + i - 1]) continue;
+			mode = need_derive ? MODE_DERIVE : MODE_DECIDE;
+		}
+
+		if (mode == MODE_DECIDE) { // hit / exact tail / expansion (bwtgap.c:160-165, 201)
 			const uint32_t a = E_A(e);
-			if (i > 0 && m < (int)bid_base[(size_t)a * (len + 1) + i - 1]) continue;
 			if (i == 0) {
+				mode = MODE_POP;
 				if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
 				continue;
 			}
-			if (m == 0 && (E_ST(e) == STATE_M || gape_mode || ge == O.max_gape)) { // no diff allowed
+			if (m == 0 && (E_ST(e) == STATE_M || gape_mode || E_GE(e) == O.max_gape)) { // no diff allowed
 				ii = i;
-				if (((seq[ii - 1] >> (a << 2)) & 15u) > 3u) continue; // N in the tail: no match
+				if (((seq[ii - 1] >> (a << 2)) & 15u) > 3u) { mode = MODE_POP; continue; } // N in the tail: no match
 				mode = MODE_EXACT;
 			} else {
 				--i;
@@ -411,6 +445,14 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		const DevIndex &ix = B.ix[1 - a];
 		uint32_t cnt_k[4], cnt_l[4];
 		occ4_pair<STATS>(ix, k - 1, l, cnt_k, cnt_l, f_ref, f_own);
+
+		if (mode == MODE_DERIVE) { // k,l were the parent's: take child derive_c's interval
+			k = ix.L2[derive_c] + sel4(derive_c, cnt_k) + 1;
+			l = ix.L2[derive_c] + sel4(derive_c, cnt_l);
+			e.k = k; e.l = l;
+			mode = MODE_DECIDE;
+			continue;
+		}
 
 		if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
 			const uint32_t c = (seq[ii - 1] >> (a << 2)) & 15u;
@@ -452,45 +494,57 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				}
 			}
 			const uint32_t ci = (seq[i] >> (a << 2)) & 15u;
-			// the match continuation is the last push and the next pop: carried in registers
-			// indels
-			int tmp;
-			if (loggap) {
-				uint32_t v = (uint32_t)(ge + go);
-				tmp = (v ? 31 - __clz(v) : 0) / 2 + 1; // int_log2 (bwtgap.c:93-102)
-			} else tmp = go + ge;
-			if (allow_diff && i >= O.indel_end_skip + tmp && len - i >= O.indel_end_skip + tmp) {
-				if (st == STATE_M) { // gap open
-					if (go < max_gapo) {
-						push(a, i, k, l, mm, go + 1, ge, STATE_I, true, false); // insertion
-						for (uint32_t c = 0; c < 4; ++c) { // deletion
-							const uint32_t nk = ix.L2[c] + cnt_k[c] + 1, nl = ix.L2[c] + cnt_l[c];
-							if (nk <= nl) push(a, i + 1, nk, nl, mm, go + 1, ge, STATE_D, true, false);
+			// which of the four one-symbol extensions are non-empty (k' <= l')
+			const uint32_t V = (cnt_k[0] < cnt_l[0] ? 1u : 0u) | (cnt_k[1] < cnt_l[1] ? 2u : 0u) |
+			                   (cnt_k[2] < cnt_l[2] ? 4u : 0u) | (cnt_k[3] < cnt_l[3] ? 8u : 0u);
+			const int score = score_of(mm, go, ge);
+			const uint32_t ptag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
+			if (allow_diff) {
+				// indels (bwtgap.c:218-247): one KIND_GAP record
+				int tmp;
+				if (loggap) {
+					const uint32_t v = (uint32_t)(ge + go);
+					tmp = (v ? 31 - __clz((int)v) : 0) / 2 + 1; // int_log2 (bwtgap.c:93-102)
+				} else tmp = go + ge;
+				if (i >= O.indel_end_skip + tmp && len - i >= O.indel_end_skip + tmp) {
+					uint32_t gm = 0;
+					int gs = score + O.s_gape;
+					if (st == STATE_M) { if (go < max_gapo) { gm = 1u | V << 1; gs = score + O.s_gapo; } }
+					else if (st == STATE_I) { if (ge < O.max_gape) gm = 1u; }
+					else if (ge < O.max_gape && (ge + go < max_diff || occ < (uint32_t)O.max_del_occ)) gm = V << 1;
+					if (gm & (gm - 1)) push_rec(k, l, (uint32_t)i | gm << 16, ptag | KIND_GAP << 27, gs, __popc(gm));
+					else if (gm) { // a single child is stored as the plain node it is (no derive trip later)
+						const uint32_t ngo = st == STATE_M ? go + 1 : go, nge = st == STATE_M ? ge : ge + 1;
+						const uint32_t tg = (uint32_t)mm | ngo << 8 | nge << 16 | a << 26;
+						if (gm == 1u) push_rec(k, l, (uint32_t)i | (uint32_t)i << 16, tg | STATE_I << 24, gs, 1);
+						else {
+							const uint32_t c = 30u - (uint32_t)__clz((int)gm); // bit 1 + c
+							push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l),
+							         (uint32_t)(i + 1) | (uint32_t)(i + 1) << 16, tg | STATE_D << 24, gs, 1);
 						}
 					}
-				} else if (st == STATE_I) { // extension of an insertion
-					if (ge < O.max_gape) push(a, i, k, l, mm, go, ge + 1, STATE_I, true, false);
-				} else { // extension of a deletion
-					if (ge < O.max_gape && (ge + go < max_diff || occ < (uint32_t)O.max_del_occ)) {
-						for (uint32_t c = 0; c < 4; ++c) {
-							const uint32_t nk = ix.L2[c] + cnt_k[c] + 1, nl = ix.L2[c] + cnt_l[c];
-							if (nk <= nl) push(a, i + 1, nk, nl, mm, go, ge + 1, STATE_D, true, false);
-						}
+				}
+				if (allow_M) { // mismatches (bwtgap.c:248-257): one KIND_MM record; the match is held
+					uint32_t mmask = 0;
+#pragma unroll
+					for (uint32_t j = 1; j <= 3; ++j) mmask |= ((V >> ((ci + j) & 3u)) & 1u) << (j - 1);
+					if (ci > 3) mmask |= (V & 1u) << 3; // N: j = 4 is a mismatch too, c = (4 + 4) & 3 = 0
+					if (mmask & (mmask - 1)) push_rec(k, l, (uint32_t)i | mmask << 16, ptag | KIND_MM << 27, score + O.s_mm, __popc(mmask));
+					else if (mmask) {
+						const uint32_t c = (ci + (32u - (uint32_t)__clz((int)mmask))) & 3u; // bit j-1 -> c = (ci + j) & 3
+						push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l), (uint32_t)i | (uint32_t)i << 16,
+						         (uint32_t)(mm + 1) | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26,
+						         score + O.s_mm, 1);
 					}
 				}
 			}
-			// mismatches, the match last
-			if (allow_diff && allow_M) {
-#pragma unroll
-				for (uint32_t j = 1; j <= 4; ++j) {
-					const uint32_t c = (ci + j) & 3u;
-					const bool is_mm = (j != 4 || ci > 3);
-					const uint32_t nk = ix.L2[c] + sel4(c, cnt_k) + 1, nl = ix.L2[c] + sel4(c, cnt_l);
-					if (nk <= nl) push(a, i, nk, nl, mm + (is_mm ? 1 : 0), go, ge, STATE_M, is_mm, !is_mm);
-				}
-			} else if (ci < 4) { // exact match only
-				const uint32_t nk = ix.L2[ci] + sel4(ci, cnt_k) + 1, nl = ix.L2[ci] + sel4(ci, cnt_l);
-				if (nk <= nl) push(a, i, nk, nl, mm, go, ge, STATE_M, false, true);
+			if (ci < 4 && ((V >> ci) & 1u)) { // the match: last push, next pop -> registers
+				held.k = ix.L2[ci] + sel4(ci, cnt_k) + 1;
+				held.l = ix.L2[ci] + sel4(ci, cnt_l);
+				held.pos = (uint32_t)i;
+				held.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
+				held_valid = true; ++n_entries;
+				if (STATS) ++n_pushes;
 			}
 			mode = MODE_POP;
 		}

@@ -26,9 +26,10 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            raise BwaGpuError(f"{LIB} is not built (run __graft_entry__.build()); there is no CPU fallback")
-        L = C.CDLL(LIB)
+        path = os.environ.get("BWAGPU_LIB", LIB)  # experiment builds (build.build_variant)
+        if not os.path.exists(path):
+            raise BwaGpuError(f"{path} is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(path)
         L.bwa_gpu_last_error.restype = C.c_char_p
         L.bwa_gpu_init.argtypes = [C.c_int, C.POINTER(C.c_int)]
         L.bwa_gpu_load_index.argtypes = [C.POINTER(C.POINTER(abi.bwt_t)), C.c_void_p, C.c_int64]

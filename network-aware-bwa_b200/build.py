@@ -22,6 +22,20 @@ def _stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+def build_variant(name: str, defines: list) -> str:
+    """Experiment builds (scripts/ab.sh): same sources with -D switches -> variants/libbwagpu_<name>.so,
+    selected at run time with BWAGPU_LIB=<path>."""
+    out_dir = os.path.join(HERE, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libbwagpu_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile if sources are newer than the library (or no nvcc: use the prebuilt one)."""
     if not force and not _stale():

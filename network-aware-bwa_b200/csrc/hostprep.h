@@ -55,7 +55,7 @@ static inline GapOpt to_gapopt(const gap_opt_t *o)
 static inline int fill_meta(int len, uint64_t seq_off, uint64_t w_off, const gap_opt_t *opt, MaxDiffTable &mdt, ReadMeta &m,
                      uint64_t &w_entries, uint32_t &n_stacks)
 {
-	if (len < 0 || len > 65534) return hostprep_fail("read length %d not supported (max 65534)", len);
+	if (len < 0 || len > 32766) return hostprep_fail("read length %d not supported (max 32766)", len);
 	int md = len > 0 ? mdt.get(len, opt) : 0;
 	int go = opt->max_gapo;
 	if (md < go) go = md;

@@ -10,6 +10,8 @@ namespace bwagpu {
 #define STATE_I 1u
 #define STATE_D 2u
 #define NIL 0xffffffffu
+#define WB_EQ 0x8000u
+#define WB_BID 0x7fffu
 
 // ------------------------------------------------------------------ K0: re-layout
 // raw = the reference's bwt_t::bwt (12-word blocks, bwtmisc.c:125-152) on the device.
@@ -70,8 +72,8 @@ struct Batch {
 	int n_reads;
 	const uint8_t *__restrict__ seq; // byte j of a read: seq[0][j] | seq[1][j] << 4
 	const ReadMeta *__restrict__ meta;
-	uint32_t *w;       // width arena: w values
-	uint16_t *bid;     // width arena: bid values
+	uint32_t *w;       // width arena: w values (only gap_shadow reads them back)
+	uint16_t *bid;     // width arena: bid | (w[i-1] == w[i]) << 15 -- all the pruning tests need
 	// results, per read
 	int32_t *n_aln;       // -1 = not done (overflow -> next tier)
 	int32_t *max_entries;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 			uint16_t *bd = B.bid + wo;
 			const DevIndex &ix = B.ix[a];
 			uint32_t k = 0, l = ix.seq_len;
-			uint32_t bid = 0;
+			uint32_t bid = 0, prev_w = 0;
 			for (int i = 0; i < n; ++i) {
 				const uint32_t c = (s[i] >> (a << 2)) & 15u;
 				if (c < 4) {
@@ -138,11 +140,13 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 				if (k > l || c > 3) { // restart
 					k = 0; l = ix.seq_len; ++bid;
 				}
-				w[i] = l - k + 1;
-				bd[i] = (uint16_t)bid;
+				const uint32_t wi = l - k + 1;
+				w[i] = wi;
+				bd[i] = (uint16_t)(bid | ((i > 0 && wi == prev_w) ? WB_EQ : 0u)); // bid | (w[i-1] == w[i]) << 15
+				prev_w = wi;
 			}
 			w[n] = 0;
-			bd[n] = (uint16_t)(bid + 1);
+			bd[n] = (uint16_t)((bid + 1) | (prev_w == 0 ? WB_EQ : 0u));
 		}
 	}
 	if (STATS) {
@@ -197,10 +201,17 @@ struct Entry {
 #define KIND_GAP 1u // bit 0 = insertion (child i = parent i), bit 1+c = deletion of c (child i = parent i + 1)
 #define KIND_MM 2u  // bit j-1 = mismatch child c = (str[i] + j) & 3
 
-enum { MODE_NEW = 0, MODE_POP = 1, MODE_DECIDE = 2, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND = 5 };
+enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND = 5, MODE_DONE = 6 };
+
+#ifndef BWAGPU_MINBLOCKS
+#define BWAGPU_MINBLOCKS 1 // __launch_bounds__ second argument: blocks/SM the register allocator must allow
+#endif
+#ifndef BWAGPU_CONVERGE
+#define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
+#endif
 
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_search(const Batch B)
+__global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	uint4 *const ent = B.ent + (size_t)slot * B.cap;
@@ -210,8 +221,6 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	const GapOpt &O = B.opt;
 	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
 
-	for (uint32_t s = 0; s < B.n_stacks; ++s) heads[s] = NIL; // heads start empty for this launch
-
 	int mode = MODE_NEW;
 	// per-read state
 	int rid = -1, len = 0, max_diff = 0, opt_max_diff = 0, max_gapo = 0;
@@ -219,15 +228,24 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	bool has_seed = false, overflow = false, have_best = false;
 	const uint8_t *seq = nullptr;
 	uint32_t *w_base = nullptr;
-	uint16_t *bid_base = nullptr;
+	uint16_t *wb_base = nullptr;
+	// Bucket lists.  heads[s] in memory is only meaningful while bit s of the mask is set, and
+	// the head of the bucket popped last lives in a register (cur_s / cur_head), so neither a
+	// reset pass nor a head load per pop is needed.
 	uint64_t mask0 = 0, mask1 = 0, mask2 = 0, mask3 = 0; // non-empty buckets
+	int cur_s = -1;
+	uint32_t cur_head = NIL;
 	uint32_t bump = 0, free_head = NIL, spare = NIL;
 	Entry held = {0, 0, 0, 0}; bool held_valid = false;
 	Entry e = {0, 0, 0, 0}; // node being processed (always a plain node)
 	uint32_t derive_c = 0;  // MODE_DERIVE: which child interval of e.{k,l} to take
 	int ii = 0;             // exact-tail cursor
+	uint32_t ce = 0;        // exact tail: base at ii-1
 	int m = 0, m_seed = 0, i = 0;
 	uint32_t k = 0, l = 0;
+	// context of the current node, loaded together with its occurrence blocks:
+	// wb1 = wb[i-1], wb2 = wb[i-2], sw1 = seed_wb[si], sw2 = seed_wb[si-1], c1 = str[i-1]   (i = the node's i)
+	uint32_t wb1 = 0, wb2 = 0, sw1 = 0, sw2 = 0, c1 = 0;
 	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0;
 
 	auto score_of = [&](int mm, int go, int ge) { return mm * O.s_mm + go * O.s_gapo + ge * O.s_gape; };
@@ -239,6 +257,10 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 	auto mask_clear = [&](int s) {
 		const uint64_t bit = ~(1ull << (s & 63));
 		if (s < 64) mask0 &= bit; else if (s < 128) mask1 &= bit; else if (s < 192) mask2 &= bit; else mask3 &= bit;
+	};
+	auto mask_test = [&](int s) -> bool {
+		const uint64_t w = s < 64 ? mask0 : s < 128 ? mask1 : s < 192 ? mask2 : mask3;
+		return (w >> (s & 63)) & 1ull;
 	};
 	auto mask_lowest = [&]() -> int {
 		if (mask0) return __ffsll((long long)mask0) - 1;
@@ -259,8 +281,8 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		else if (bump < B.cap) idx = bump++;
 		else { overflow = true; return; }
 		ent[idx] = make_uint4(rk, rl, pos, tag);
-		nxt[idx] = heads[s];
-		heads[s] = idx;
+		if (s == cur_s) { nxt[idx] = cur_head; cur_head = idx; }
+		else { nxt[idx] = mask_test(s) ? heads[s] : NIL; heads[s] = idx; }
 		mask_set(s);
 	};
 
@@ -282,8 +304,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			B.pool_off[rid] = off;
 			B.max_entries[rid] = max_entries;
 		}
-		// reset: only non-empty buckets have a live head
-		while (mask0 | mask1 | mask2 | mask3) { const int s = mask_lowest(); heads[s] = NIL; mask_clear(s); }
+		mask0 = mask1 = mask2 = mask3 = 0; cur_s = -1; cur_head = NIL;
 		bump = 0; free_head = NIL; spare = NIL; held_valid = false; n_entries = 0;
 	};
 
@@ -308,17 +329,22 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			}
 		}
 		if (do_add) {
-			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array
+			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array, then refresh
+			// the packed (bid, w[t-1]==w[t]) view of the positions it may have changed
 			const uint32_t a = E_A(e);
 			uint32_t *w = w_base + (size_t)a * (len + 1);
-			uint16_t *bd = bid_base + (size_t)a * (len + 1);
+			uint16_t *wb = wb_base + (size_t)a * (len + 1);
 			const uint32_t x = hl - hk + 1, mx = B.ix[1 - a].seq_len;
 			const int ldp = E_LDP(e);
-			uint32_t j = 0;
-			for (int t = 0; t < ldp; ++t) {
-				const uint32_t wv = w[t];
-				if (wv > x) w[t] = wv - x;
-				else if (wv == x) { bd[t] = 1; w[t] = mx - (++j); }
+			uint32_t j = 0, prev = 0;
+			for (int t = 0; t <= ldp && t <= len; ++t) {
+				uint32_t wv = w[t], bid = wb[t] & WB_BID;
+				if (t < ldp) {
+					if (wv > x) { wv -= x; w[t] = wv; }
+					else if (wv == x) { bid = 1; wv = mx - (++j); w[t] = wv; }
+				}
+				wb[t] = (uint16_t)(bid | ((t > 0 && wv == prev) ? WB_EQ : 0u));
+				prev = wv;
 			}
 			if ((uint32_t)n_aln < B.aln_cap)
 				alnbuf[n_aln] = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl,
@@ -328,10 +354,39 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 		return true;
 	};
 
+	// hit / exact tail / expansion for the node in e with interval (k, l) (bwtgap.c:160-165, 201).
+	// Returns true when the trip goes on to an occurrence lookup.
+	auto decide = [&]() -> bool {
+		if (i == 0) {
+			mode = MODE_POP;
+			if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
+			return false;
+		}
+		if (m == 0 && (E_ST(e) == STATE_M || gape_mode || E_GE(e) == O.max_gape)) { // no diff allowed
+			if (c1 > 3u) { mode = MODE_POP; return false; } // N in the tail: no match
+			ii = i; ce = c1;
+			mode = MODE_EXACT;
+		} else {
+			--i;
+			mode = MODE_EXPAND;
+		}
+		return true;
+	};
+
 	for (;;) {
+#if BWAGPU_CONVERGE
+		__syncwarp();
+		if (__all_sync(0xffffffffu, mode == MODE_DONE)) break;
+		if (mode == MODE_DONE) continue;
+#endif
+		bool fresh = false, need_derive = false;
 		if (mode == MODE_NEW) {
 			const int job = atomicAdd(B.work_counter, 1);
+#if BWAGPU_CONVERGE
+			if (job >= B.n_jobs) { mode = MODE_DONE; continue; }
+#else
 			if (job >= B.n_jobs) break;
+#endif
 			rid = B.jobs ? B.jobs[job] : job;
 			const ReadMeta md = B.meta[rid];
 			len = md.len;
@@ -346,7 +401,7 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			has_seed = len > O.seed_len;
 			seq = B.seq + md.seq_off;
 			w_base = B.w + md.w_off;
-			bid_base = B.bid + md.w_off;
+			wb_base = B.bid + md.w_off;
 			best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
 			// too many N? (bwtgap.c:118-123) -- *pmax_entries is left untouched there
 			if ((int)md.n_amb > max_diff) {
@@ -365,14 +420,17 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			if (overflow || n_entries == 0) { finish_read(); mode = MODE_NEW; continue; }
 			if (max_entries < n_entries) max_entries = n_entries;
 			if (n_entries > O.max_entries) { finish_read(); mode = MODE_NEW; continue; }
-			bool need_derive = false;
 			// gap_pop (bwtgap.c:66-79)
 			if (held_valid) { e = held; held_valid = false; }
 			else if (!(mask0 | mask1 | mask2 | mask3)) { // only phantoms left: the reference pops one and stops
 				finish_read(); mode = MODE_NEW; continue;
 			} else {
 				const int s = mask_lowest();
-				const uint32_t idx = heads[s];
+				if (s != cur_s) {
+					if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s] = cur_head;
+					cur_s = s; cur_head = heads[s];
+				}
+				const uint32_t idx = cur_head;
 				const uint4 q = ent[idx];
 				const uint32_t kind = (q.w >> 27) & 3u;
 				uint32_t gm = 0, b = 0;
@@ -383,9 +441,8 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				}
 				if (gm) ent[idx].z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
 				else { // unlink
-					const uint32_t nx = nxt[idx];
-					heads[s] = nx;
-					if (nx == NIL) mask_clear(s);
+					cur_head = nxt[idx];
+					if (cur_head == NIL) mask_clear(s);
 					if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
 					spare = idx;
 				}
@@ -410,6 +467,45 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			--n_entries;
 			if (STATS) ++n_pops;
 			k = e.k; l = e.l; i = E_I(e);
+			fresh = true;
+		}
+
+		// ---- issue every load this trip depends on before using any of them: the two
+		// occurrence blocks (bwt_2occ4 at bwtgap.c:202 / bwt_2occ at bwt.c:245) and, for a
+		// node just popped, its pruning context.  One memory round trip per trip.
+		const uint32_t a = E_A(e);
+		const DevIndex &ix = B.ix[1 - a];
+		const uint32_t jk = occ_arg(ix, k - 1), jl = occ_arg(ix, l);
+		const OccBlock ob_l = load_block(ix, jl >> 6);
+		const OccBlock ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
+		uint32_t cn = 0;
+		if (fresh) {
+			const uint16_t *wb = wb_base + (size_t)a * (len + 1);
+			wb1 = i >= 1 ? wb[i - 1] : 0u;
+			wb2 = i >= 2 ? wb[i - 2] : 0u;
+			c1 = i >= 1 ? (uint32_t)(seq[i - 1] >> (a << 2)) & 15u : 0u;
+			cn = i >= 2 ? (uint32_t)(seq[i - 2] >> (a << 2)) & 15u : 0u; // second base of an exact tail starting here
+			if (has_seed) {
+				const int si = (i - 1) - (len - O.seed_len);
+				if (si >= 1) {
+					const uint16_t *swb = wb_base + 2 * (size_t)(len + 1) + (size_t)a * (O.seed_len + 1);
+					sw1 = swb[si]; sw2 = swb[si - 1];
+				}
+			}
+		} else if (mode == MODE_EXACT) {
+			cn = ii >= 2 ? (uint32_t)(seq[ii - 2] >> (a << 2)) & 15u : 0u;
+		}
+		if (STATS) {
+			f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
+			if (k == 0) f_ref += 1u;
+			else {
+				const uint32_t km1 = k - 1;
+				const uint32_t pk = km1 >= ix.primary ? km1 - 1 : km1, pl = l >= ix.primary ? l - 1 : l;
+				f_ref += (pk >> 7) == (pl >> 7) ? 1u : 2u;
+			}
+		}
+
+		if (fresh) { // pruning tests of bwtgap.c:144-157
 			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
 			if (!nonstop && score_of(mm, go, ge) > best_score + O.s_mm) { finish_read(); mode = MODE_NEW; continue; }
 			m = max_diff - (mm + go);
@@ -419,45 +515,26 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				m_seed = O.max_seed_diff - (mm + go);
 				if (gape_mode) m_seed -= ge;
 			}
-			if (i > 0 && m < (int)bid_base[(size_t)E_A(e) * (len + 1) + i - 1]) continue;
-			mode = need_derive ? MODE_DERIVE : MODE_DECIDE;
+			if (i > 0 && m < (int)(wb1 & WB_BID)) continue;
+			if (need_derive) mode = MODE_DERIVE;
+			else if (!decide()) continue;
 		}
 
-		if (mode == MODE_DECIDE) { // hit / exact tail / expansion (bwtgap.c:160-165, 201)
-			const uint32_t a = E_A(e);
-			if (i == 0) {
-				mode = MODE_POP;
-				if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
-				continue;
-			}
-			if (m == 0 && (E_ST(e) == STATE_M || gape_mode || E_GE(e) == O.max_gape)) { // no diff allowed
-				ii = i;
-				if (((seq[ii - 1] >> (a << 2)) & 15u) > 3u) { mode = MODE_POP; continue; } // N in the tail: no match
-				mode = MODE_EXACT;
-			} else {
-				--i;
-				mode = MODE_EXPAND;
-			}
-		}
-
-		// ---- the one occurrence lookup per trip (bwt_2occ4 at bwtgap.c:202 / bwt_2occ at bwt.c:245)
-		const uint32_t a = E_A(e);
-		const DevIndex &ix = B.ix[1 - a];
 		uint32_t cnt_k[4], cnt_l[4];
-		occ4_pair<STATS>(ix, k - 1, l, cnt_k, cnt_l, f_ref, f_own);
+		occ4_in_block(ob_k, jk, cnt_k);
+		occ4_in_block(ob_l, jl, cnt_l);
 
 		if (mode == MODE_DERIVE) { // k,l were the parent's: take child derive_c's interval
 			k = ix.L2[derive_c] + sel4(derive_c, cnt_k) + 1;
 			l = ix.L2[derive_c] + sel4(derive_c, cnt_l);
 			e.k = k; e.l = l;
-			mode = MODE_DECIDE;
+			decide(); // next trip looks the child's own interval up
 			continue;
 		}
 
 		if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
-			const uint32_t c = (seq[ii - 1] >> (a << 2)) & 15u;
-			k = ix.L2[c] + sel4(c, cnt_k) + 1;
-			l = ix.L2[c] + sel4(c, cnt_l);
+			k = ix.L2[ce] + sel4(ce, cnt_k) + 1;
+			l = ix.L2[ce] + sel4(ce, cnt_l);
 			--ii;
 			if (k > l) { mode = MODE_POP; continue; }
 			if (ii == 0) {
@@ -465,7 +542,8 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 				if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
 				continue;
 			}
-			if (((seq[ii - 1] >> (a << 2)) & 15u) > 3u) mode = MODE_POP;
+			ce = cn;
+			if (ce > 3u) mode = MODE_POP;
 			continue;
 		}
 
@@ -474,26 +552,21 @@ __global__ void __launch_bounds__(128) k_search(const Batch B)
 			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
 			const uint32_t st = E_ST(e);
 			const uint32_t occ = l - k + 1;
-			const uint32_t *w = w_base + (size_t)a * (len + 1);
-			const uint16_t *bd = bid_base + (size_t)a * (len + 1);
 			bool allow_diff = true, allow_M = true;
 			if (i > 0) {
-				const int b1 = bd[i - 1];
+				const int b1 = (int)(wb2 & WB_BID); // width[i-1].bid
 				if (b1 > m - 1) allow_diff = false;
-				else if (b1 == m - 1 && (int)bd[i] == m - 1 && w[i - 1] == w[i]) allow_M = false;
+				else if (b1 == m - 1 && (int)(wb1 & WB_BID) == m - 1 && (wb1 & WB_EQ)) allow_M = false;
 				if (has_seed) {
 					const int si = i - (len - O.seed_len);
 					if (si > 0) {
-						const size_t so = 2 * (size_t)(len + 1) + (size_t)a * (O.seed_len + 1);
-						const uint32_t *sw = w_base + so;
-						const uint16_t *sb = bid_base + so;
-						const int s1 = sb[si - 1];
+						const int s1 = (int)(sw2 & WB_BID); // seed_width[si-1].bid
 						if (s1 > m_seed - 1) allow_diff = false;
-						else if (s1 == m_seed - 1 && (int)sb[si] == m_seed - 1 && sw[si - 1] == sw[si]) allow_M = false;
+						else if (s1 == m_seed - 1 && (int)(sw1 & WB_BID) == m_seed - 1 && (sw1 & WB_EQ)) allow_M = false;
 					}
 				}
 			}
-			const uint32_t ci = (seq[i] >> (a << 2)) & 15u;
+			const uint32_t ci = c1;
 			// which of the four one-symbol extensions are non-empty (k' <= l')
 			const uint32_t V = (cnt_k[0] < cnt_l[0] ? 1u : 0u) | (cnt_k[1] < cnt_l[1] ? 2u : 0u) |
 			                   (cnt_k[2] < cnt_l[2] ? 4u : 0u) | (cnt_k[3] < cnt_l[3] ? 8u : 0u);

@@ -36,6 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 GENOME_BP = 100_000_000
 READ_LEN = 76
 READS_TOTAL = 10_000_000  # the configuration the metric is quoted on
+METRIC = "reads/sec (aln: bwa_cal_sa_reg_gap per read = width bounds + gapped FM-index search)"
 WORKLOAD = "SE 10M x 76bp, -n 0.04 -o 1, synthetic 100 Mb genome (BASELINE.json configs[1])"
 
 
@@ -124,17 +125,6 @@ def seq_struct_array(abi, reads):
     return ptr, (rec, seq, rseq)
 
 
-def free_alns(rec: np.ndarray):
-    """free() the aln arrays a batch call calloc'd (what bwa_free_read_seq1 does, bwaseqio.c:259)."""
-    libc = C.CDLL(None)
-    libc.free.argtypes = [C.c_void_p]
-    ptrs = rec.view(np.uint64).reshape(-1, 25)[:, 7]
-    for p in ptrs.tolist():
-        if p:
-            libc.free(p)
-    ptrs[:] = 0
-
-
 # ------------------------------------------------------------------ reference arm / cpu baseline
 def time_reference(R, idx, reads, opt, target_s: float, threads: int):
     """Times the reference's own bwa_cal_sa_reg_gap (n_seqs = 1 per read, as bam2bam calls it)
@@ -150,7 +140,8 @@ def time_reference(R, idx, reads, opt, target_s: float, threads: int):
         t = time.perf_counter()
         H.refh_aln_batch(ridx.arr, hi - lo, ptr, C.byref(opt), threads)
         dt = time.perf_counter() - t
-        free_alns(keep[0])
+        H.refh_free_alns.argtypes = [C.c_int, C.POINTER(abi.bwa_seq_t)]
+        H.refh_free_alns(hi - lo, ptr)
         return dt
 
     dt = run(0, probe)
@@ -166,7 +157,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (default: 2M; reference arm: bounded sample)")
+    ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (default: the full 10M-read workload; reference arm: bounded sample)")
     ap.add_argument("--genome-bp", type=int, default=GENOME_BP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -202,7 +193,7 @@ def main():
                 rates.append(rate); ns.append(n); total_t += dt
         value = sum(ns) / total_t
         line = {
-            "impl": "reference", "metric": "reads/sec (aln: bwa_cal_sa_reg_gap per read)", "value": value, "unit": "reads/s",
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{ns[0]} reads per step", "threads": host_cores},
@@ -221,7 +212,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_reads = args.reads or 2_000_000
+    n_reads = args.reads or READS_TOTAL
     T, idx, reads = make_workload(bwa, n_reads, f"cuda:{local_rank}", seed=1000 + rank, genome_bp=args.genome_bp)
     torch.cuda.empty_cache()
     api.init([local_rank])
@@ -287,7 +278,7 @@ def main():
         lib = api.lib()
         for _ in range(min(args.warmup, 1)):
             assert lib.bwa_gpu_cal_sa_reads_gap(reads.n, ptr, C.byref(opt)) == 0, lib.bwa_gpu_last_error()
-            free_alns(keep[0])
+            lib.bwa_gpu_free_alns(reads.n, ptr)
         barrier()
         e2e_s = 0.0
         n_aln_tot = 0
@@ -297,8 +288,7 @@ def main():
             e2e_s += time.perf_counter() - t0
             assert rc == 0, lib.bwa_gpu_last_error()
             n_aln_tot = int(api.get_stats()["n_aln"])
-            launches_e2e = api.get_stats()["launches"]
-            free_alns(keep[0])
+            lib.bwa_gpu_free_alns(reads.n, ptr)  # untimed: the caller's bwa_free_read_seq1
         barrier()
         if dist is not None:
             t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
@@ -342,13 +332,13 @@ def main():
     except Exception:
         pass
     line = {
-        "metric": "reads/sec (aln: K2 width + K3 gapped search, bwa_cal_sa_reg_gap per read)",
+        "metric": METRIC,
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": n_reads, "read_len": READ_LEN, "genome_bp": args.genome_bp,
                    "parallelism": f"replica x{world}, reads sharded, no collective",
-                   "l2": "inputs larger than L2 (width arena + search stacks are GBs per step); same batch every step",
+                   "l2": "inputs larger than L2 (index 100 MB + width arena and search stacks of several GB per step); same batch every step",
                    "timed": "CUDA events on the library stream around K2+K3(+tiers)+compaction",
                    "tier2_reads": int(n_over2), "tier3_reads": int(n_over3)},
         "e2e": e2e,
@@ -361,7 +351,9 @@ def main():
                      "kernel_ms_per_step": search_ms / args.steps, "width_ms_per_step": width_ms / args.steps,
                      "tier_ms_per_step": [t / args.steps for t in tier_ms],
                      "pops_per_read": st_counts["n_pops"] / n_reads, "pushes_per_read": st_counts["n_pushes"] / n_reads,
-                     "stored_pushes_per_read": st_counts["n_stored"] / n_reads},
+                     "stored_pushes_per_read": st_counts["n_stored"] / n_reads,
+                     "per_read": {k: st_counts["n_" + k] / n_reads for k in ("pruned", "expand", "exact", "derive", "trips")},
+                     "stats_pass_ms": {"queue_empty": st_counts["ns_queue_empty"] / 1e6, "kernel": st_counts["ns_kernel"] / 1e6}},
         "cpu_baseline": cpu_baseline,
         "parity_sample": parity,
         "wall_s_timed_region": wall_s,

@@ -143,6 +143,10 @@ const char *bwa_gpu_last_error(void);
  * order included. */
 int bwa_gpu_cal_sa_reads_gap(int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt);
 
+/* Convenience for batch drivers: free() every seqs[i].aln and zero the field -- the part of
+ * bwa_free_read_seq1 (bwaseqio.c:253-261) that concerns what the call above allocated. */
+void bwa_gpu_free_alns(int n_seqs, bwa_seq_t *seqs);
+
 /* Flat form of the same call for batch drivers that do not keep bwa_seq_t around.
  * bases[offs[i] .. offs[i+1]) is read i in sequencing orientation, codes 0..3 = ACGT,
  * 4 = N (bwaseqio.c:10); the library derives seq (reversed) and rseq (reverse complement)
@@ -197,7 +201,11 @@ typedef struct {
 	int32_t launches; /* kernels launched by the call */
 	int32_t n_devices;
 	double ms_tier[4]; /* k_search (+ its width refresh) per tier */
-	int64_t n_stored;  /* pushes that reached the in-memory stack (stats builds) */
+	int64_t n_stored;  /* records that reached the in-memory stack (stats builds) */
+	int64_t n_pruned, n_expand, n_exact, n_derive; /* pops pruned / nodes expanded / exact-tail steps / group-child derivations */
+	int64_t n_trips;          /* loop trips summed over threads (stats builds) */
+	int64_t ns_queue_empty;   /* last k_search launch: time from start until the work queue ran dry */
+	int64_t ns_kernel;        /* last k_search launch: start to last thread exit (globaltimer) */
 } bwa_gpu_stats_t;
 
 int bwa_gpu_get_stats(bwa_gpu_stats_t *out);

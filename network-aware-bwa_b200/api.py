@@ -35,6 +35,8 @@ def lib() -> C.CDLL:
         L.bwa_gpu_load_index.argtypes = [C.POINTER(C.POINTER(abi.bwt_t)), C.c_void_p, C.c_int64]
         L.bwa_gpu_destroy.restype = None
         L.bwa_gpu_cal_sa_reads_gap.argtypes = [C.c_int, C.POINTER(abi.bwa_seq_t), C.POINTER(abi.gap_opt_t)]
+        L.bwa_gpu_free_alns.argtypes = [C.c_int, C.POINTER(abi.bwa_seq_t)]
+        L.bwa_gpu_free_alns.restype = None
         L.bwa_gpu_aln_flat.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.bwa_gpu_cal_pac_pos.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -50,7 +52,7 @@ def lib() -> C.CDLL:
 
 EXPORTS = [
     "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_destroy", "bwa_gpu_last_error",
-    "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw",
+    "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw",
     "bwa_gpu_get_stats", "bwa_gpu_set_stats",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
 ]

@@ -8,6 +8,7 @@
 // There is no CPU fallback: without a usable device every entry point returns an error.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -111,8 +112,15 @@ struct Tier {
 	DevBuf<uint4> alnbuf;
 };
 
+// One Ctx = one LANE: a host thread's worth of state on one device (stream, scratch arenas,
+// pinned staging).  A device gets BWAGPU_LANES lanes (default 4) that share its index; a
+// batch call gives every lane a contiguous range of reads, so host-side packing/unpacking of
+// one lane overlaps the kernels of another and a kernel's straggler tail overlaps the next
+// kernel's start.
 struct Ctx {
 	int dev = 0;
+	int lane = 0;
+	Ctx *owner = nullptr; // lane 0 of the same device owns the index allocations
 	int n_sm = 0;
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev[16] = {};
@@ -128,7 +136,8 @@ struct Ctx {
 	DevBuf<ReadMeta> d_meta;
 	DevBuf<uint32_t> d_w;
 	DevBuf<uint16_t> d_bid;
-	DevBuf<int32_t> d_naln, d_maxent, d_jobs_a, d_jobs_b;
+	DevBuf<int32_t> d_naln, d_maxent, d_jobs_a, d_jobs_b, d_ids, d_order;
+	DevBuf<uint8_t> d_keys, d_keys2;
 	DevBuf<uint32_t> d_pooloff, d_outoff;
 	DevBuf<uint4> d_pool, d_out;
 	DevBuf<int> d_counters;            // [0] work [1] overflow [2] pool_count(u32)
@@ -160,6 +169,12 @@ static bool g_stats_enabled = false;
 static std::mutex g_mu;
 static std::vector<uint4> g_flat_pool; // result pool of the last flat call (multi-device concat)
 
+static uint32_t env_u32(const char *name, uint32_t dflt)
+{
+	const char *e = getenv(name);
+	return e && atoll(e) > 0 ? (uint32_t)atoll(e) : dflt;
+}
+
 // ------------------------------------------------------------------ lifetime
 extern "C" void bwa_gpu_destroy(void)
 {
@@ -167,11 +182,13 @@ extern "C" void bwa_gpu_destroy(void)
 	for (Ctx *c : g_ctx) {
 		cudaSetDevice(c->dev);
 		cudaDeviceSynchronize();
-		c->blk_all.release();
-		for (int s = 0; s < 2; ++s) c->sa[s].release();
-		c->pac.release();
+		if (!c->owner) {
+			c->blk_all.release();
+			for (int s = 0; s < 2; ++s) c->sa[s].release();
+			c->pac.release();
+		}
 		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release();
-		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release();
+		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release(); c->d_ids.release(); c->d_order.release(); c->d_keys.release(); c->d_keys2.release();
 		c->d_pooloff.release(); c->d_outoff.release(); c->d_pool.release(); c->d_out.release();
 		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
 		for (Tier &t : c->tier) { t.ent.release(); t.nxt.release(); t.heads.release(); t.alnbuf.release(); }
@@ -203,12 +220,19 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 		CK(cudaGetDeviceProperties(&prop, id));
 		if (prop.major < 10) return fail("device %d is sm_%d%d; libbwagpu is built for sm_100a only", id, prop.major, prop.minor);
 		CK(cudaSetDevice(id));
-		Ctx *c = new Ctx();
-		c->dev = id;
-		c->n_sm = prop.multiProcessorCount;
-		CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-		for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-		g_ctx.push_back(c);
+		const int lanes = (int)env_u32("BWAGPU_LANES", 4);
+		Ctx *first = nullptr;
+		for (int ln = 0; ln < lanes; ++ln) {
+			Ctx *c = new Ctx();
+			c->dev = id;
+			c->lane = ln;
+			c->owner = first;
+			if (!first) first = c;
+			c->n_sm = prop.multiProcessorCount;
+			CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+			for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+			g_ctx.push_back(c);
+		}
 	}
 	return 0;
 }
@@ -295,8 +319,16 @@ extern "C" int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64
 	std::lock_guard<std::mutex> g(g_mu);
 	if (g_ctx.empty()) return fail("bwa_gpu_load_index: call bwa_gpu_init first");
 	if (bwt[0]->seq_len != bwt[1]->seq_len) return fail("forward and reverse index differ in seq_len");
-	for (Ctx *c : g_ctx)
-		if (upload_index_one(c, bwt, pac, l_pac)) return 1;
+	for (Ctx *c : g_ctx) {
+		if (!c->owner) { if (upload_index_one(c, bwt, pac, l_pac)) return 1; }
+		else { // sibling lane: same device, same index arrays
+			const Ctx *o = c->owner;
+			c->ix[0] = o->ix[0]; c->ix[1] = o->ix[1];
+			c->pac.p = o->pac.p; c->pac.cap = 0; c->l_pac = o->l_pac;
+			c->has_index = o->has_index; c->has_sa = o->has_sa; c->has_pac = o->has_pac;
+			c->res_valid = false;
+		}
+	}
 	return 0;
 }
 
@@ -304,12 +336,6 @@ extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; 
 
 // ------------------------------------------------------------------ device pipeline for one resident chunk
 static const int N_TIERS = 4;
-
-static uint32_t env_u32(const char *name, uint32_t dflt)
-{
-	const char *e = getenv(name);
-	return e && atoll(e) > 0 ? (uint32_t)atoll(e) : dflt;
-}
 
 // Tier t = (stack arena entries per thread, hit-list capacity, resident threads).  Every read
 // starts in tier 0; a read whose stack or hit list outgrows its tier is retried from scratch
@@ -355,7 +381,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
-	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(8)) return 1;
+	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(16)) return 1;
 	size_t pool_cap = std::max<size_t>((size_t)n * 8, 1u << 20);
 	if (pool_cap > 0xfffffff0ull) pool_cap = 0xfffffff0ull;
 	if (c->d_pool.reserve(pool_cap)) return 1;
@@ -374,7 +400,12 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	B.n_stacks = n_stacks;
 
 	CK(cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(int), c->st));
-	if (stats) CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), c->st));
+	if (stats) {
+		unsigned long long init[16] = {0};
+		init[11] = init[12] = ~0ull;
+		CK(cudaMemcpyAsync(c->d_stats.p, init, sizeof init, cudaMemcpyHostToDevice, c->st));
+		CK(cudaStreamSynchronize(c->st));
+	}
 
 	// K2
 	B.jobs = nullptr; B.n_jobs = n;
@@ -389,19 +420,38 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			c->stats.launches++;
 		}
 	}
-	CK(cudaEventRecord(c->ev[2], c->st));
 	if (stats) {
-		unsigned long long hs[8];
+		unsigned long long hs[16];
 		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaStreamSynchronize(c->st));
 		c->stats.occ_fetches_width += (int64_t)hs[0];
 		c->stats.own_fetches_width += (int64_t)hs[1];
-		CK(cudaMemsetAsync(c->d_stats.p, 0, 8 * sizeof(unsigned long long), c->st));
+		unsigned long long init[16] = {0};
+		init[11] = init[12] = ~0ull;
+		CK(cudaMemcpyAsync(c->d_stats.p, init, sizeof init, cudaMemcpyHostToDevice, c->st));
+		CK(cudaStreamSynchronize(c->st));
 	}
+
+	// job order for tier 0: longest-looking searches first (k_job_keys)
+	const int32_t *jobs = nullptr;
+	{
+		const char *env = getenv("BWAGPU_SORT_JOBS");
+		if (!(env && atoi(env) == 0) && n > 1) {
+			if (c->d_keys.reserve(n) || c->d_keys2.reserve(n) || c->d_ids.reserve(n) || c->d_order.reserve(n)) return 1;
+			k_job_keys<<<(n + 255) / 256, 256, 0, c->st>>>(B, c->d_keys.p, c->d_ids.p);
+			CK(cudaGetLastError());
+			size_t tb = 0;
+			CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_keys.p, c->d_keys2.p, c->d_ids.p, c->d_order.p, n, 0, 8, c->st));
+			if (c->d_cubtmp.reserve(tb + 16)) return 1;
+			CK(cub::DeviceRadixSort::SortPairs(c->d_cubtmp.p, tb, c->d_keys.p, c->d_keys2.p, c->d_ids.p, c->d_order.p, n, 0, 8, c->st));
+			c->stats.launches += 3;
+			jobs = c->d_order.p;
+		}
+	}
+	CK(cudaEventRecord(c->ev[2], c->st)); // the sort is accounted to the width phase
 
 	// K3, tier by tier
 	int n_jobs = n;
-	const int32_t *jobs = nullptr;
 	for (int t = 0; t < N_TIERS && n_jobs > 0; ++t) {
 		if (tier_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
 		Tier &T = c->tier[t];
@@ -448,7 +498,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	}
 	CK(cudaEventRecord(c->ev[3], c->st));
 	if (stats) {
-		unsigned long long hs[8];
+		unsigned long long hs[16];
 		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaStreamSynchronize(c->st));
 		c->stats.occ_fetches_search += (int64_t)hs[0];
@@ -456,6 +506,13 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		c->stats.n_pops += (int64_t)hs[2];
 		c->stats.n_pushes += (int64_t)hs[3];
 		c->stats.n_stored += (int64_t)hs[4];
+		c->stats.n_pruned += (int64_t)hs[5];
+		c->stats.n_expand += (int64_t)hs[6];
+		c->stats.n_exact += (int64_t)hs[7];
+		c->stats.n_derive += (int64_t)hs[8];
+		c->stats.n_trips += (int64_t)hs[9];
+		c->stats.ns_queue_empty = (int64_t)(hs[11] - hs[12]);
+		c->stats.ns_kernel = (int64_t)(hs[13] - hs[12]);
 	}
 
 	// ordered compaction: exclusive scan of n_aln (n+1 items so that out_off[n] = total)
@@ -501,7 +558,7 @@ static size_t chunk_reads()
 {
 	const char *env = getenv("BWAGPU_CHUNK");
 	size_t c = env ? (size_t)atoll(env) : 0;
-	return c > 0 ? c : (size_t)1 << 20;
+	return c > 0 ? c : (size_t)1 << 19; // 512 K reads: several chunks per lane so packing, copies and kernels of different lanes overlap
 }
 
 static int run_range(Ctx *c, FlatJob &J)
@@ -568,9 +625,31 @@ static int run_range(Ctx *c, FlatJob &J)
 		auto t2 = std::chrono::steady_clock::now();
 		memcpy(J.n_aln + r0, c->h_naln.p, (size_t)n * 4);
 		memcpy(J.max_entries + r0, c->h_maxent.p, (size_t)n * 4);
-		const size_t base = J.pool.size();
-		J.pool.resize(base + (size_t)tot);
-		if (tot) memcpy(J.pool.data() + base, c->h_out.p, (size_t)tot * 16);
+		if (J.seqs) { // struct API: hand the hits back the way bwa_cal_sa_reg_gap does
+			const uint4 *src = c->h_out.p;
+			for (int i = 0; i < n; ++i) {
+				bwa_seq_t *p = J.seqs + r0 + i;
+				const int na = c->h_naln.p[i];
+				// bwtaln.c:113 resets these before the search
+				p->sa = 0; p->type = 0 /* BWA_TYPE_NO_MATCH */; p->c1 = p->c2 = 0;
+				p->n_aln = na;
+				if (p->len == 0) { p->aln = 0; continue; } // bwtaln.c:134
+				// bwt_match_gap always returns a calloc'd array of m_aln >= 4 records, grown by
+				// doubling (bwtgap.c:114-115,188-191); consumers free() it.
+				int m_aln = 4;
+				while (m_aln < na) m_aln <<= 1;
+				p->aln = (bwt_aln1_t *)calloc((size_t)m_aln, sizeof(bwt_aln1_t));
+				if (!p->aln) return fail("calloc failed");
+				if (na) memcpy(p->aln, src, (size_t)na * 16);
+				src += na;
+				// untouched when the search never ran (bwtgap.c:120-123)
+				if (c->h_maxent.p[i] > 0) p->max_entries = c->h_maxent.p[i];
+			}
+		} else {
+			const size_t base = J.pool.size();
+			J.pool.resize(base + (size_t)tot);
+			if (tot) memcpy(J.pool.data() + base, c->h_out.p, (size_t)tot * 16);
+		}
 		auto t3 = std::chrono::steady_clock::now();
 		c->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t3 - t2).count();
 		c->stats.n_reads += n;
@@ -633,32 +712,12 @@ extern "C" int bwa_gpu_cal_sa_reads_gap(int n_seqs, bwa_seq_t *seqs, const gap_o
 	std::vector<int32_t> n_aln(n_seqs), max_entries(n_seqs);
 	std::vector<FlatJob> jobs;
 	if (run_all(n_seqs, nullptr, nullptr, seqs, opt, n_aln.data(), max_entries.data(), jobs)) return 1;
-	auto t0 = std::chrono::steady_clock::now();
-	const int nd = (int)jobs.size();
-	for (int d = 0; d < nd; ++d) {
-		const int64_t lo = (int64_t)n_seqs * d / nd;
-		const uint4 *src = jobs[d].pool.data();
-		for (int i = 0; i < jobs[d].n; ++i) {
-			bwa_seq_t *p = seqs + lo + i;
-			const int na = n_aln[lo + i];
-			// bwtaln.c:113 resets these before the search
-			p->sa = 0; p->type = 0 /* BWA_TYPE_NO_MATCH */; p->c1 = p->c2 = 0;
-			p->n_aln = na;
-			if (p->len == 0) { p->aln = 0; continue; } // bwtaln.c:134
-			// bwt_match_gap always returns a calloc'd array of m_aln >= 4 records, grown by
-			// doubling (bwtgap.c:114-115,188-191); consumers free() it.
-			int m_aln = 4;
-			while (m_aln < na) m_aln <<= 1;
-			p->aln = (bwt_aln1_t *)calloc((size_t)m_aln, sizeof(bwt_aln1_t));
-			if (!p->aln) return fail("calloc failed");
-			if (na) memcpy(p->aln, src, (size_t)na * 16);
-			src += na;
-			if (max_entries[lo + i] > 0) p->max_entries = max_entries[lo + i]; // untouched when the search never ran (bwtgap.c:120-123)
-		}
-	}
-	auto t1 = std::chrono::steady_clock::now();
-	g_ctx[0]->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t1 - t0).count();
 	return 0;
+}
+
+extern "C" void bwa_gpu_free_alns(int n_seqs, bwa_seq_t *seqs)
+{
+	for (int i = 0; i < n_seqs; ++i) { free(seqs[i].aln); seqs[i].aln = 0; seqs[i].n_aln = 0; }
 }
 
 extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
@@ -675,10 +734,11 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 		s.n_reads += t.n_reads; s.n_aln += t.n_aln; s.n_overflow_t2 += t.n_overflow_t2; s.n_overflow_t3 += t.n_overflow_t3;
 		s.occ_fetches_width += t.occ_fetches_width; s.occ_fetches_search += t.occ_fetches_search;
 		s.own_fetches_width += t.own_fetches_width; s.own_fetches_search += t.own_fetches_search;
-		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.launches += t.launches;
+		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.n_pruned += t.n_pruned; s.n_expand += t.n_expand; s.n_exact += t.n_exact; s.n_derive += t.n_derive; s.n_trips += t.n_trips; s.ns_queue_empty = t.ns_queue_empty; s.ns_kernel = t.ns_kernel; s.launches += t.launches;
 		for (int q = 0; q < 4; ++q) s.ms_tier[q] = std::max(s.ms_tier[q], t.ms_tier[q]);
 	}
-	s.n_devices = (int32_t)g_ctx.size();
+	s.n_devices = 0;
+	for (Ctx *c : g_ctx) if (!c->owner) ++s.n_devices;
 	*out = s;
 	return 0;
 }

@@ -94,8 +94,19 @@ struct Batch {
 	uint4 *alnbuf;
 	uint32_t cap, aln_cap, n_stacks;
 	// stats (STATS builds only)
-	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes [4] pushes stored in memory
+	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes [4] records stored [5] pruned pops [6] expansions [7] exact-tail steps [8] derive trips
 };
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+#ifdef BWAGPU_HOST_EMU
+	return 0;
+#else
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+#endif
+}
 
 __device__ __forceinline__ uint32_t sel4(uint32_t c, const uint32_t v[4])
 {
@@ -246,7 +257,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	// context of the current node, loaded together with its occurrence blocks:
 	// wb1 = wb[i-1], wb2 = wb[i-2], sw1 = seed_wb[si], sw2 = seed_wb[si-1], c1 = str[i-1]   (i = the node's i)
 	uint32_t wb1 = 0, wb2 = 0, sw1 = 0, sw2 = 0, c1 = 0;
-	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0;
+	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0, n_pruned = 0, n_expand = 0, n_exact = 0, n_derive = 0, n_trips = 0;
+	if (STATS) atomicMin(B.stats + 12, gtime());
 
 	auto score_of = [&](int mm, int go, int ge) { return mm * O.s_mm + go * O.s_gapo + ge * O.s_gape; };
 
@@ -373,101 +385,112 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		return true;
 	};
 
+	// The loop body is written without early `continue`s: every lane walks the same sequence
+	// of guarded blocks (NEW / POP / loads / pruning / consume), so the warp re-converges
+	// after each block and ALL lanes that need memory this trip issue their loads together.
 	for (;;) {
 #if BWAGPU_CONVERGE
 		__syncwarp();
 		if (__all_sync(0xffffffffu, mode == MODE_DONE)) break;
-		if (mode == MODE_DONE) continue;
 #endif
 		bool fresh = false, need_derive = false;
+		bool active = mode != MODE_DONE; // takes part in this trip's occurrence lookup
+		if (STATS) ++n_trips;
 		if (mode == MODE_NEW) {
 			const int job = atomicAdd(B.work_counter, 1);
+			if (job >= B.n_jobs) {
+				if (STATS) atomicMin(B.stats + 11, gtime());
 #if BWAGPU_CONVERGE
-			if (job >= B.n_jobs) { mode = MODE_DONE; continue; }
+				mode = MODE_DONE; active = false;
 #else
-			if (job >= B.n_jobs) break;
+				break;
 #endif
-			rid = B.jobs ? B.jobs[job] : job;
-			const ReadMeta md = B.meta[rid];
-			len = md.len;
-			overflow = false; have_best = false;
-			n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
-			if (len == 0) { // bwtaln.c:134: aln = 0, n_aln = 0
-				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
-				continue;
+			} else {
+				rid = B.jobs ? B.jobs[job] : job;
+				const ReadMeta md = B.meta[rid];
+				len = md.len;
+				overflow = false; have_best = false;
+				n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
+				opt_max_diff = max_diff = md.max_diff;
+				max_gapo = md.max_gapo;
+				// len == 0: bwtaln.c:134 (aln = 0, n_aln = 0); too many N: bwtgap.c:118-123
+				// (*pmax_entries is left untouched there)
+				if (len == 0 || (int)md.n_amb > max_diff) {
+					B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
+					active = false; // stays in MODE_NEW
+				} else {
+					has_seed = len > O.seed_len;
+					seq = B.seq + md.seq_off;
+					w_base = B.w + md.w_off;
+					wb_base = B.bid + md.w_off;
+					best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
+					// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
+					push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
+					held.k = 0u; held.l = B.ix[0].seq_len; held.pos = (uint32_t)len; held.tag = 1u << 26;
+					held_valid = true; ++n_entries;
+					if (STATS) ++n_pushes;
+					mode = MODE_POP;
+				}
 			}
-			opt_max_diff = max_diff = md.max_diff;
-			max_gapo = md.max_gapo;
-			has_seed = len > O.seed_len;
-			seq = B.seq + md.seq_off;
-			w_base = B.w + md.w_off;
-			wb_base = B.bid + md.w_off;
-			best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
-			// too many N? (bwtgap.c:118-123) -- *pmax_entries is left untouched there
-			if ((int)md.n_amb > max_diff) {
-				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
-				continue;
-			}
-			// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
-			push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
-			held.k = 0u; held.l = B.ix[0].seq_len; held.pos = (uint32_t)len; held.tag = 1u << 26;
-			held_valid = true; ++n_entries;
-			if (STATS) ++n_pushes;
-			mode = MODE_POP;
 		}
 
-		if (mode == MODE_POP) {
-			if (overflow || n_entries == 0) { finish_read(); mode = MODE_NEW; continue; }
-			if (max_entries < n_entries) max_entries = n_entries;
-			if (n_entries > O.max_entries) { finish_read(); mode = MODE_NEW; continue; }
-			// gap_pop (bwtgap.c:66-79)
-			if (held_valid) { e = held; held_valid = false; }
-			else if (!(mask0 | mask1 | mask2 | mask3)) { // only phantoms left: the reference pops one and stops
-				finish_read(); mode = MODE_NEW; continue;
-			} else {
-				const int s = mask_lowest();
-				if (s != cur_s) {
-					if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s] = cur_head;
-					cur_s = s; cur_head = heads[s];
-				}
-				const uint32_t idx = cur_head;
-				const uint4 q = ent[idx];
-				const uint32_t kind = (q.w >> 27) & 3u;
-				uint32_t gm = 0, b = 0;
-				if (kind != KIND_PLAIN) {
-					gm = (q.z >> 16) & 31u;
-					b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
-					gm &= ~(1u << b);
-				}
-				if (gm) ent[idx].z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
-				else { // unlink
-					cur_head = nxt[idx];
-					if (cur_head == NIL) mask_clear(s);
-					if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
-					spare = idx;
-				}
-				e.k = q.x; e.l = q.y;
-				if (kind == KIND_PLAIN) { e.pos = q.z; e.tag = q.w; }
-				else {
-					const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
-					uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
-					if (kind == KIND_MM) {
-						const uint32_t cb = (seq[pi] >> (a << 2)) & 15u;
-						derive_c = (cb + b + 1u) & 3u;
-						++mm; ci = pi; st = STATE_M; need_derive = true;
-					} else {
-						if (pst == STATE_M) ++go; else ++ge;
-						if (b == 0) { ci = pi; st = STATE_I; }
-						else { ci = pi + 1u; st = STATE_D; derive_c = b - 1u; need_derive = true; }
-					}
-					e.pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
-					e.tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
-				}
+		if (active && mode == MODE_POP) {
+			bool stop = overflow || n_entries == 0;
+			if (!stop) {
+				if (max_entries < n_entries) max_entries = n_entries;
+				// > max_entries (bwtgap.c:140); only phantoms left: the reference pops one and stops
+				stop = n_entries > O.max_entries || (!held_valid && !(mask0 | mask1 | mask2 | mask3));
 			}
-			--n_entries;
-			if (STATS) ++n_pops;
-			k = e.k; l = e.l; i = E_I(e);
-			fresh = true;
+			if (stop) { finish_read(); mode = MODE_NEW; active = false; }
+			else {
+				// gap_pop (bwtgap.c:66-79)
+				if (held_valid) { e = held; held_valid = false; }
+				else {
+					const int s = mask_lowest();
+					if (s != cur_s) {
+						if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s] = cur_head;
+						cur_s = s; cur_head = heads[s];
+					}
+					const uint32_t idx = cur_head;
+					const uint4 q = ent[idx];
+					const uint32_t nx = nxt[idx]; // issued with the entry load, used only when the record is unlinked
+					const uint32_t kind = (q.w >> 27) & 3u;
+					uint32_t gm = 0, b = 0;
+					if (kind != KIND_PLAIN) {
+						gm = (q.z >> 16) & 31u;
+						b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
+						gm &= ~(1u << b);
+					}
+					if (gm) ent[idx].z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
+					else { // unlink
+						cur_head = nx;
+						if (cur_head == NIL) mask_clear(s);
+						if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
+						spare = idx;
+					}
+					e.k = q.x; e.l = q.y;
+					if (kind == KIND_PLAIN) { e.pos = q.z; e.tag = q.w; }
+					else {
+						const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
+						uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
+						if (kind == KIND_MM) {
+							const uint32_t cb = (seq[pi] >> (a << 2)) & 15u;
+							derive_c = (cb + b + 1u) & 3u;
+							++mm; ci = pi; st = STATE_M; need_derive = true;
+						} else {
+							if (pst == STATE_M) ++go; else ++ge;
+							if (b == 0) { ci = pi; st = STATE_I; }
+							else { ci = pi + 1u; st = STATE_D; derive_c = b - 1u; need_derive = true; }
+						}
+						e.pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
+						e.tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
+					}
+				}
+				--n_entries;
+				if (STATS) ++n_pops;
+				k = e.k; l = e.l; i = E_I(e);
+				fresh = true;
+			}
 		}
 
 		// ---- issue every load this trip depends on before using any of them: the two
@@ -475,151 +498,153 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		// node just popped, its pruning context.  One memory round trip per trip.
 		const uint32_t a = E_A(e);
 		const DevIndex &ix = B.ix[1 - a];
-		const uint32_t jk = occ_arg(ix, k - 1), jl = occ_arg(ix, l);
-		const OccBlock ob_l = load_block(ix, jl >> 6);
-		const OccBlock ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
-		uint32_t cn = 0;
-		if (fresh) {
-			const uint16_t *wb = wb_base + (size_t)a * (len + 1);
-			wb1 = i >= 1 ? wb[i - 1] : 0u;
-			wb2 = i >= 2 ? wb[i - 2] : 0u;
-			c1 = i >= 1 ? (uint32_t)(seq[i - 1] >> (a << 2)) & 15u : 0u;
-			cn = i >= 2 ? (uint32_t)(seq[i - 2] >> (a << 2)) & 15u : 0u; // second base of an exact tail starting here
-			if (has_seed) {
-				const int si = (i - 1) - (len - O.seed_len);
-				if (si >= 1) {
-					const uint16_t *swb = wb_base + 2 * (size_t)(len + 1) + (size_t)a * (O.seed_len + 1);
-					sw1 = swb[si]; sw2 = swb[si - 1];
-				}
-			}
-		} else if (mode == MODE_EXACT) {
-			cn = ii >= 2 ? (uint32_t)(seq[ii - 2] >> (a << 2)) & 15u : 0u;
-		}
-		if (STATS) {
-			f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
-			if (k == 0) f_ref += 1u;
-			else {
-				const uint32_t km1 = k - 1;
-				const uint32_t pk = km1 >= ix.primary ? km1 - 1 : km1, pl = l >= ix.primary ? l - 1 : l;
-				f_ref += (pk >> 7) == (pl >> 7) ? 1u : 2u;
-			}
-		}
-
-		if (fresh) { // pruning tests of bwtgap.c:144-157
-			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
-			if (!nonstop && score_of(mm, go, ge) > best_score + O.s_mm) { finish_read(); mode = MODE_NEW; continue; }
-			m = max_diff - (mm + go);
-			if (gape_mode) m -= ge;
-			if (m < 0) continue;
-			if (has_seed) {
-				m_seed = O.max_seed_diff - (mm + go);
-				if (gape_mode) m_seed -= ge;
-			}
-			if (i > 0 && m < (int)(wb1 & WB_BID)) continue;
-			if (need_derive) mode = MODE_DERIVE;
-			else if (!decide()) continue;
-		}
-
-		uint32_t cnt_k[4], cnt_l[4];
-		occ4_in_block(ob_k, jk, cnt_k);
-		occ4_in_block(ob_l, jl, cnt_l);
-
-		if (mode == MODE_DERIVE) { // k,l were the parent's: take child derive_c's interval
-			k = ix.L2[derive_c] + sel4(derive_c, cnt_k) + 1;
-			l = ix.L2[derive_c] + sel4(derive_c, cnt_l);
-			e.k = k; e.l = l;
-			decide(); // next trip looks the child's own interval up
-			continue;
-		}
-
-		if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
-			k = ix.L2[ce] + sel4(ce, cnt_k) + 1;
-			l = ix.L2[ce] + sel4(ce, cnt_l);
-			--ii;
-			if (k > l) { mode = MODE_POP; continue; }
-			if (ii == 0) {
-				mode = MODE_POP;
-				if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
-				continue;
-			}
-			ce = cn;
-			if (ce > 3u) mode = MODE_POP;
-			continue;
-		}
-
-		// ---- MODE_EXPAND (bwtgap.c:201-259); i was already decremented
-		{
-			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
-			const uint32_t st = E_ST(e);
-			const uint32_t occ = l - k + 1;
-			bool allow_diff = true, allow_M = true;
-			if (i > 0) {
-				const int b1 = (int)(wb2 & WB_BID); // width[i-1].bid
-				if (b1 > m - 1) allow_diff = false;
-				else if (b1 == m - 1 && (int)(wb1 & WB_BID) == m - 1 && (wb1 & WB_EQ)) allow_M = false;
+		uint32_t jk = 0, jl = 0, cn = 0;
+		OccBlock ob_l = {0, 0, 0, 0, 0, 0}, ob_k = {0, 0, 0, 0, 0, 0};
+		if (active) {
+			jk = occ_arg(ix, k - 1); jl = occ_arg(ix, l);
+			ob_l = load_block(ix, jl >> 6);
+			ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
+			if (fresh) {
+				const uint16_t *wb = wb_base + (size_t)a * (len + 1);
+				wb1 = i >= 1 ? wb[i - 1] : 0u;
+				wb2 = i >= 2 ? wb[i - 2] : 0u;
+				c1 = i >= 1 ? (uint32_t)(seq[i - 1] >> (a << 2)) & 15u : 0u;
+				cn = i >= 2 ? (uint32_t)(seq[i - 2] >> (a << 2)) & 15u : 0u; // second base of an exact tail starting here
 				if (has_seed) {
-					const int si = i - (len - O.seed_len);
-					if (si > 0) {
-						const int s1 = (int)(sw2 & WB_BID); // seed_width[si-1].bid
-						if (s1 > m_seed - 1) allow_diff = false;
-						else if (s1 == m_seed - 1 && (int)(sw1 & WB_BID) == m_seed - 1 && (sw1 & WB_EQ)) allow_M = false;
+					const int si = (i - 1) - (len - O.seed_len);
+					if (si >= 1) {
+						const uint16_t *swb = wb_base + 2 * (size_t)(len + 1) + (size_t)a * (O.seed_len + 1);
+						sw1 = swb[si]; sw2 = swb[si - 1];
 					}
 				}
+			} else if (mode == MODE_EXACT) {
+				cn = ii >= 2 ? (uint32_t)(seq[ii - 2] >> (a << 2)) & 15u : 0u;
 			}
-			const uint32_t ci = c1;
-			// which of the four one-symbol extensions are non-empty (k' <= l')
-			const uint32_t V = (cnt_k[0] < cnt_l[0] ? 1u : 0u) | (cnt_k[1] < cnt_l[1] ? 2u : 0u) |
-			                   (cnt_k[2] < cnt_l[2] ? 4u : 0u) | (cnt_k[3] < cnt_l[3] ? 8u : 0u);
-			const int score = score_of(mm, go, ge);
-			const uint32_t ptag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
-			if (allow_diff) {
-				// indels (bwtgap.c:218-247): one KIND_GAP record
-				int tmp;
-				if (loggap) {
-					const uint32_t v = (uint32_t)(ge + go);
-					tmp = (v ? 31 - __clz((int)v) : 0) / 2 + 1; // int_log2 (bwtgap.c:93-102)
-				} else tmp = go + ge;
-				if (i >= O.indel_end_skip + tmp && len - i >= O.indel_end_skip + tmp) {
-					uint32_t gm = 0;
-					int gs = score + O.s_gape;
-					if (st == STATE_M) { if (go < max_gapo) { gm = 1u | V << 1; gs = score + O.s_gapo; } }
-					else if (st == STATE_I) { if (ge < O.max_gape) gm = 1u; }
-					else if (ge < O.max_gape && (ge + go < max_diff || occ < (uint32_t)O.max_del_occ)) gm = V << 1;
-					if (gm & (gm - 1)) push_rec(k, l, (uint32_t)i | gm << 16, ptag | KIND_GAP << 27, gs, __popc(gm));
-					else if (gm) { // a single child is stored as the plain node it is (no derive trip later)
-						const uint32_t ngo = st == STATE_M ? go + 1 : go, nge = st == STATE_M ? ge : ge + 1;
-						const uint32_t tg = (uint32_t)mm | ngo << 8 | nge << 16 | a << 26;
-						if (gm == 1u) push_rec(k, l, (uint32_t)i | (uint32_t)i << 16, tg | STATE_I << 24, gs, 1);
-						else {
-							const uint32_t c = 30u - (uint32_t)__clz((int)gm); // bit 1 + c
-							push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l),
-							         (uint32_t)(i + 1) | (uint32_t)(i + 1) << 16, tg | STATE_D << 24, gs, 1);
+			if (STATS) {
+				f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
+				if (k == 0) f_ref += 1u;
+				else {
+					const uint32_t km1 = k - 1;
+					const uint32_t pk = km1 >= ix.primary ? km1 - 1 : km1, pl = l >= ix.primary ? l - 1 : l;
+					f_ref += (pk >> 7) == (pl >> 7) ? 1u : 2u;
+				}
+			}
+		}
+
+		if (active && fresh) { // pruning tests of bwtgap.c:144-157
+			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+			if (!nonstop && score_of(mm, go, ge) > best_score + O.s_mm) { finish_read(); mode = MODE_NEW; active = false; }
+			else {
+				m = max_diff - (mm + go);
+				if (gape_mode) m -= ge;
+				if (has_seed) {
+					m_seed = O.max_seed_diff - (mm + go);
+					if (gape_mode) m_seed -= ge;
+				}
+				if (m < 0 || (i > 0 && m < (int)(wb1 & WB_BID))) { if (STATS) ++n_pruned; active = false; } // stays in MODE_POP
+				else if (need_derive) mode = MODE_DERIVE;
+				else active = decide();
+			}
+		}
+
+		if (active) {
+			uint32_t cnt_k[4], cnt_l[4];
+			occ4_in_block(ob_k, jk, cnt_k);
+			occ4_in_block(ob_l, jl, cnt_l);
+
+			if (mode == MODE_DERIVE) { // k,l were the parent's: take child derive_c's interval
+				if (STATS) ++n_derive;
+				k = ix.L2[derive_c] + sel4(derive_c, cnt_k) + 1;
+				l = ix.L2[derive_c] + sel4(derive_c, cnt_l);
+				e.k = k; e.l = l;
+				decide(); // next trip looks the child's own interval up
+			} else if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
+				if (STATS) ++n_exact;
+				k = ix.L2[ce] + sel4(ce, cnt_k) + 1;
+				l = ix.L2[ce] + sel4(ce, cnt_l);
+				--ii;
+				if (k > l) mode = MODE_POP;
+				else if (ii == 0) {
+					mode = MODE_POP;
+					if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
+				} else {
+					ce = cn;
+					if (ce > 3u) mode = MODE_POP;
+				}
+			} else { // ---- MODE_EXPAND (bwtgap.c:201-259); i was already decremented
+				if (STATS) ++n_expand;
+				const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+				const uint32_t st = E_ST(e);
+				const uint32_t occ = l - k + 1;
+				bool allow_diff = true, allow_M = true;
+				if (i > 0) {
+					const int b1 = (int)(wb2 & WB_BID); // width[i-1].bid
+					if (b1 > m - 1) allow_diff = false;
+					else if (b1 == m - 1 && (int)(wb1 & WB_BID) == m - 1 && (wb1 & WB_EQ)) allow_M = false;
+					if (has_seed) {
+						const int si = i - (len - O.seed_len);
+						if (si > 0) {
+							const int s1 = (int)(sw2 & WB_BID); // seed_width[si-1].bid
+							if (s1 > m_seed - 1) allow_diff = false;
+							else if (s1 == m_seed - 1 && (int)(sw1 & WB_BID) == m_seed - 1 && (sw1 & WB_EQ)) allow_M = false;
 						}
 					}
 				}
-				if (allow_M) { // mismatches (bwtgap.c:248-257): one KIND_MM record; the match is held
-					uint32_t mmask = 0;
+				const uint32_t ci = c1;
+				// which of the four one-symbol extensions are non-empty (k' <= l')
+				const uint32_t V = (cnt_k[0] < cnt_l[0] ? 1u : 0u) | (cnt_k[1] < cnt_l[1] ? 2u : 0u) |
+				                   (cnt_k[2] < cnt_l[2] ? 4u : 0u) | (cnt_k[3] < cnt_l[3] ? 8u : 0u);
+				const int score = score_of(mm, go, ge);
+				const uint32_t ptag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
+				if (allow_diff) {
+					// indels (bwtgap.c:218-247): one KIND_GAP record
+					int tmp;
+					if (loggap) {
+						const uint32_t v = (uint32_t)(ge + go);
+						tmp = (v ? 31 - __clz((int)v) : 0) / 2 + 1; // int_log2 (bwtgap.c:93-102)
+					} else tmp = go + ge;
+					if (i >= O.indel_end_skip + tmp && len - i >= O.indel_end_skip + tmp) {
+						uint32_t gm = 0;
+						int gs = score + O.s_gape;
+						if (st == STATE_M) { if (go < max_gapo) { gm = 1u | V << 1; gs = score + O.s_gapo; } }
+						else if (st == STATE_I) { if (ge < O.max_gape) gm = 1u; }
+						else if (ge < O.max_gape && (ge + go < max_diff || occ < (uint32_t)O.max_del_occ)) gm = V << 1;
+						if (gm & (gm - 1)) push_rec(k, l, (uint32_t)i | gm << 16, ptag | KIND_GAP << 27, gs, __popc(gm));
+						else if (gm) { // a single child is stored as the plain node it is (no derive trip later)
+							const uint32_t ngo = st == STATE_M ? go + 1 : go, nge = st == STATE_M ? ge : ge + 1;
+							const uint32_t tg = (uint32_t)mm | ngo << 8 | nge << 16 | a << 26;
+							if (gm == 1u) push_rec(k, l, (uint32_t)i | (uint32_t)i << 16, tg | STATE_I << 24, gs, 1);
+							else {
+								const uint32_t c = 30u - (uint32_t)__clz((int)gm); // bit 1 + c
+								push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l),
+								         (uint32_t)(i + 1) | (uint32_t)(i + 1) << 16, tg | STATE_D << 24, gs, 1);
+							}
+						}
+					}
+					if (allow_M) { // mismatches (bwtgap.c:248-257): one KIND_MM record; the match is held
+						uint32_t mmask = 0;
 #pragma unroll
-					for (uint32_t j = 1; j <= 3; ++j) mmask |= ((V >> ((ci + j) & 3u)) & 1u) << (j - 1);
-					if (ci > 3) mmask |= (V & 1u) << 3; // N: j = 4 is a mismatch too, c = (4 + 4) & 3 = 0
-					if (mmask & (mmask - 1)) push_rec(k, l, (uint32_t)i | mmask << 16, ptag | KIND_MM << 27, score + O.s_mm, __popc(mmask));
-					else if (mmask) {
-						const uint32_t c = (ci + (32u - (uint32_t)__clz((int)mmask))) & 3u; // bit j-1 -> c = (ci + j) & 3
-						push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l), (uint32_t)i | (uint32_t)i << 16,
-						         (uint32_t)(mm + 1) | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26,
-						         score + O.s_mm, 1);
+						for (uint32_t j = 1; j <= 3; ++j) mmask |= ((V >> ((ci + j) & 3u)) & 1u) << (j - 1);
+						if (ci > 3) mmask |= (V & 1u) << 3; // N: j = 4 is a mismatch too, c = (4 + 4) & 3 = 0
+						if (mmask & (mmask - 1)) push_rec(k, l, (uint32_t)i | mmask << 16, ptag | KIND_MM << 27, score + O.s_mm, __popc(mmask));
+						else if (mmask) {
+							const uint32_t c = (ci + (32u - (uint32_t)__clz((int)mmask))) & 3u; // bit j-1 -> c = (ci + j) & 3
+							push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l), (uint32_t)i | (uint32_t)i << 16,
+							         (uint32_t)(mm + 1) | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26,
+							         score + O.s_mm, 1);
+						}
 					}
 				}
+				if (ci < 4 && ((V >> ci) & 1u)) { // the match: last push, next pop -> registers
+					held.k = ix.L2[ci] + sel4(ci, cnt_k) + 1;
+					held.l = ix.L2[ci] + sel4(ci, cnt_l);
+					held.pos = (uint32_t)i;
+					held.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
+					held_valid = true; ++n_entries;
+					if (STATS) ++n_pushes;
+				}
+				mode = MODE_POP;
 			}
-			if (ci < 4 && ((V >> ci) & 1u)) { // the match: last push, next pop -> registers
-				held.k = ix.L2[ci] + sel4(ci, cnt_k) + 1;
-				held.l = ix.L2[ci] + sel4(ci, cnt_l);
-				held.pos = (uint32_t)i;
-				held.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
-				held_valid = true; ++n_entries;
-				if (STATS) ++n_pushes;
-			}
-			mode = MODE_POP;
 		}
 	}
 
@@ -629,7 +654,36 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		atomicAdd(B.stats + 2, (unsigned long long)n_pops);
 		atomicAdd(B.stats + 3, (unsigned long long)n_pushes);
 		atomicAdd(B.stats + 4, (unsigned long long)n_stored);
+		atomicAdd(B.stats + 5, (unsigned long long)n_pruned);
+		atomicAdd(B.stats + 6, (unsigned long long)n_expand);
+		atomicAdd(B.stats + 7, (unsigned long long)n_exact);
+		atomicAdd(B.stats + 8, (unsigned long long)n_derive);
+		atomicAdd(B.stats + 9, (unsigned long long)n_trips);
+		atomicMax(B.stats + 13, gtime());
 	}
+}
+
+// ------------------------------------------------------------------ job ordering for K3
+// Sort key per read from the widths K2 just computed: D = min over strands of the lower
+// bound on differences for the whole read (width[len-1].bid).  Reads with 1 <= D <= max_diff
+// explore the most (the larger D the longer), D = 0 (an exact match exists) and D > max_diff
+// (pruned at the root, bwtgap.c:157) the least.  K3 hands jobs out in key order: the longest
+// searches start first (shorter tail) and the lanes of a warp work on similar reads (less
+// divergence).  Order of processing is not observable in the results.
+__global__ void k_job_keys(const Batch B, uint8_t *__restrict__ keys, int32_t *__restrict__ ids)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= B.n_reads) return;
+	const ReadMeta m = B.meta[r];
+	uint32_t key = 255;
+	if (m.len > 0) {
+		const uint16_t *wb = B.bid + m.w_off;
+		const uint32_t d0 = wb[m.len - 1] & WB_BID, d1 = wb[(size_t)(m.len + 1) + m.len - 1] & WB_BID;
+		const uint32_t d = d0 < d1 ? d0 : d1, md = m.max_diff;
+		key = (d >= 1 && d <= md) ? md - d : md + 1 + (d == 0 ? 0u : 1u);
+	}
+	keys[r] = (uint8_t)key;
+	ids[r] = r;
 }
 
 // ------------------------------------------------------------------ ordered compaction of the aln pool

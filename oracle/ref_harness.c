@@ -55,6 +55,13 @@ int refh_aln_batch(bwt_t *const bwt[2], int n, bwa_seq_t *seqs, const gap_opt_t 
 	return 0;
 }
 
+/* free() the aln arrays a batch left behind (the aln part of bwa_free_read_seq1, bwaseqio.c:259) */
+void refh_free_alns(int n, bwa_seq_t *seqs)
+{
+	int i;
+	for (i = 0; i < n; ++i) { free(seqs[i].aln); seqs[i].aln = 0; seqs[i].n_aln = 0; }
+}
+
 typedef struct {
 	bwt_t *const *bwt;
 	int64_t n;

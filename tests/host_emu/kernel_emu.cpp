@@ -90,7 +90,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	std::vector<uint4> pool((size_t)n * 64 + (1 << 16));
 	std::vector<int32_t> jobs_a(n), jobs_b(n);
 	int counters[4] = {0, 0, 0, 0};
-	unsigned long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned long long stats[16] = {0};
 	Batch B;
 	B.ix[0] = E->ix[0]; B.ix[1] = E->ix[1];
 	B.opt = to_gapopt(opt);

@@ -346,8 +346,11 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	Tier &T = c->tier[t];
 	if (t == 0) {
 		int bps = 0;
-		if (g_stats_enabled) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true>, 128, 0));
-		else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false>, 128, 0));
+		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0; // bucket heads
+		CK(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		if (g_stats_enabled) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true>, 128, smem));
+		else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false>, 128, smem));
 		if (bps < 1) bps = 1;
 		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_T1_BLOCKS_PER_SM", 64));
 		T.slots_blocks = (uint32_t)(bps * c->n_sm);
@@ -365,9 +368,10 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	}
 	if (T.cap > max_entries_opt + 16) T.cap = max_entries_opt + 16;
 	const size_t slots = (size_t)T.slots_blocks * 128;
-	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap) || T.heads.reserve(slots * n_stacks) ||
-	    T.alnbuf.reserve(slots * T.aln_cap))
-		return 1;
+	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap) || T.alnbuf.reserve(slots * T.aln_cap)) return 1;
+#if !BWAGPU_SMEM_HEADS
+	if (T.heads.reserve(slots * n_stacks)) return 1;
+#endif
 	return 0;
 }
 
@@ -436,7 +440,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	const int32_t *jobs = nullptr;
 	{
 		const char *env = getenv("BWAGPU_SORT_JOBS");
-		if (!(env && atoi(env) == 0) && n > 1) {
+		if (env && atoi(env) != 0 && n > 1) { // opt-in: helps 1-2M-read batches (shorter tail), not the 10M workload
 			if (c->d_keys.reserve(n) || c->d_keys2.reserve(n) || c->d_ids.reserve(n) || c->d_order.reserve(n)) return 1;
 			k_job_keys<<<(n + 255) / 256, 256, 0, c->st>>>(B, c->d_keys.p, c->d_ids.p);
 			CK(cudaGetLastError());
@@ -455,7 +459,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	for (int t = 0; t < N_TIERS && n_jobs > 0; ++t) {
 		if (tier_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
 		Tier &T = c->tier[t];
-		B.ent = T.ent.p; B.nxt = T.nxt.p; B.heads = T.heads.p; B.alnbuf = T.alnbuf.p;
+		B.ent = T.ent.p; B.nxt = T.nxt.p; B.alnbuf = T.alnbuf.p; B.heads = T.heads.p;
 		B.cap = T.cap; B.aln_cap = T.aln_cap;
 		B.jobs = jobs; B.n_jobs = n_jobs;
 		int32_t *ovf = (t & 1) ? c->d_jobs_b.p : c->d_jobs_a.p;
@@ -472,8 +476,9 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		uint32_t blocks = T.slots_blocks;
 		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
 		if (blocks > need) blocks = need;
-		if (stats) k_search<true><<<blocks, 128, 0, c->st>>>(B);
-		else k_search<false><<<blocks, 128, 0, c->st>>>(B);
+		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0;
+		if (stats) k_search<true><<<blocks, 128, smem, c->st>>>(B);
+		else k_search<false><<<blocks, 128, smem, c->st>>>(B);
 		CK(cudaGetLastError());
 		c->stats.launches++;
 		CK(cudaEventRecord(c->ev[9 + 2 * t], c->st));
@@ -734,7 +739,7 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 		s.n_reads += t.n_reads; s.n_aln += t.n_aln; s.n_overflow_t2 += t.n_overflow_t2; s.n_overflow_t3 += t.n_overflow_t3;
 		s.occ_fetches_width += t.occ_fetches_width; s.occ_fetches_search += t.occ_fetches_search;
 		s.own_fetches_width += t.own_fetches_width; s.own_fetches_search += t.own_fetches_search;
-		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.n_pruned += t.n_pruned; s.n_expand += t.n_expand; s.n_exact += t.n_exact; s.n_derive += t.n_derive; s.n_trips += t.n_trips; s.ns_queue_empty = t.ns_queue_empty; s.ns_kernel = t.ns_kernel; s.launches += t.launches;
+		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.n_pruned += t.n_pruned; s.n_expand += t.n_expand; s.n_exact += t.n_exact; s.n_derive += t.n_derive; s.n_trips += t.n_trips; s.ns_queue_empty = std::max(s.ns_queue_empty, t.ns_queue_empty); s.ns_kernel = std::max(s.ns_kernel, t.ns_kernel); s.launches += t.launches;
 		for (int q = 0; q < 4; ++q) s.ms_tier[q] = std::max(s.ms_tier[q], t.ms_tier[q]);
 	}
 	s.n_devices = 0;

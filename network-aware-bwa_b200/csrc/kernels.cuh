@@ -90,7 +90,7 @@ struct Batch {
 	// per-slot scratch
 	uint4 *ent;
 	uint32_t *nxt;
-	uint32_t *heads;
+	uint32_t *heads; // global bucket heads (only when BWAGPU_SMEM_HEADS == 0)
 	uint4 *alnbuf;
 	uint32_t cap, aln_cap, n_stacks;
 	// stats (STATS builds only)
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 struct Entry {
 	uint32_t k, l;
 	uint32_t pos;  // plain: i | last_diff_pos << 16      group: parent i (after --i) | child mask << 16
-	uint32_t tag;  // n_mm | n_gapo << 8 | n_gape << 16 | state << 24 | a << 26 | kind << 27
+	uint32_t tag;  // n_mm | n_gapo << 8 | n_gape << 16 | state << 24 | a << 26 | kind << 27 | (KIND_MM: read base at i) << 29
 };
 
 #define E_I(e) ((int)((e).pos & 0xffffu))
@@ -217,6 +217,15 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #ifndef BWAGPU_MINBLOCKS
 #define BWAGPU_MINBLOCKS 1 // __launch_bounds__ second argument: blocks/SM the register allocator must allow
 #endif
+// Measured on B200, 10M x 76bp (profiles/r1_ab_experiments.md): bucket heads in shared memory and an
+// L1 prefetch of the next record to pop are both slightly SLOWER than plain global heads; kept as
+// switches for other workloads.
+#ifndef BWAGPU_SMEM_HEADS
+#define BWAGPU_SMEM_HEADS 0
+#endif
+#ifndef BWAGPU_PREFETCH_TOP
+#define BWAGPU_PREFETCH_TOP 0
+#endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
 #endif
@@ -227,10 +236,27 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	uint4 *const ent = B.ent + (size_t)slot * B.cap;
 	uint32_t *const nxt = B.nxt + (size_t)slot * B.cap;
+	// bucket list heads: shared memory, bucket-major (heads[s * blockDim + tid]: lanes never
+	// conflict on a bank whatever buckets they touch, since blockDim is a multiple of 32)
+#ifdef BWAGPU_HOST_EMU
+	static uint32_t s_heads[256];
+	uint32_t *const heads = s_heads + threadIdx.x;
+	const uint32_t HS = blockDim.x; // stride between buckets
+#elif BWAGPU_SMEM_HEADS
+	extern __shared__ uint32_t s_heads[];
+	uint32_t *const heads = s_heads + threadIdx.x;
+	const uint32_t HS = blockDim.x;
+#else
 	uint32_t *const heads = B.heads + (size_t)slot * B.n_stacks;
+	const uint32_t HS = 1;
+#endif
 	uint4 *const alnbuf = B.alnbuf + (size_t)slot * B.aln_cap;
 	const GapOpt &O = B.opt;
 	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
+	// The reversed genome has the forward genome's base composition, so C() (bwt_t::L2) and
+	// seq_len are the same for both indexes; only the block array and `primary` differ.
+	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
+	auto Cof = [&](uint32_t c) -> uint32_t { return c == 0 ? 0u : c == 1 ? C1 : c == 2 ? C2 : C3; };
 
 	int mode = MODE_NEW;
 	// per-read state
@@ -264,11 +290,13 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 
 	auto mask_set = [&](int s) {
 		const uint64_t bit = 1ull << (s & 63);
-		if (s < 64) mask0 |= bit; else if (s < 128) mask1 |= bit; else if (s < 192) mask2 |= bit; else mask3 |= bit;
+		const int w = s >> 6;
+		mask0 |= w == 0 ? bit : 0ull; mask1 |= w == 1 ? bit : 0ull; mask2 |= w == 2 ? bit : 0ull; mask3 |= w == 3 ? bit : 0ull;
 	};
 	auto mask_clear = [&](int s) {
-		const uint64_t bit = ~(1ull << (s & 63));
-		if (s < 64) mask0 &= bit; else if (s < 128) mask1 &= bit; else if (s < 192) mask2 &= bit; else mask3 &= bit;
+		const uint64_t bit = 1ull << (s & 63);
+		const int w = s >> 6;
+		mask0 &= ~(w == 0 ? bit : 0ull); mask1 &= ~(w == 1 ? bit : 0ull); mask2 &= ~(w == 2 ? bit : 0ull); mask3 &= ~(w == 3 ? bit : 0ull);
 	};
 	auto mask_test = [&](int s) -> bool {
 		const uint64_t w = s < 64 ? mask0 : s < 128 ? mask1 : s < 192 ? mask2 : mask3;
@@ -294,7 +322,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		else { overflow = true; return; }
 		ent[idx] = make_uint4(rk, rl, pos, tag);
 		if (s == cur_s) { nxt[idx] = cur_head; cur_head = idx; }
-		else { nxt[idx] = mask_test(s) ? heads[s] : NIL; heads[s] = idx; }
+		else { nxt[idx] = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = idx; }
 		mask_set(s);
 	};
 
@@ -448,8 +476,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				else {
 					const int s = mask_lowest();
 					if (s != cur_s) {
-						if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s] = cur_head;
-						cur_s = s; cur_head = heads[s];
+						if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s * HS] = cur_head;
+						cur_s = s; cur_head = heads[s * HS];
 					}
 					const uint32_t idx = cur_head;
 					const uint4 q = ent[idx];
@@ -474,7 +502,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
 						uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
 						if (kind == KIND_MM) {
-							const uint32_t cb = (seq[pi] >> (a << 2)) & 15u;
+							const uint32_t cb = q.w >> 29; // the parent's read base at pi, kept in the record
 							derive_c = (cb + b + 1u) & 3u;
 							++mm; ci = pi; st = STATE_M; need_derive = true;
 						} else {
@@ -504,6 +532,13 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			jk = occ_arg(ix, k - 1); jl = occ_arg(ix, l);
 			ob_l = load_block(ix, jl >> 6);
 			ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
+#if !defined(BWAGPU_HOST_EMU) && BWAGPU_PREFETCH_TOP
+			// the record a memory pop would take next: warm it while this trip's loads are in flight
+			if (cur_head != NIL && cur_s >= 0) {
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + cur_head));
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + cur_head));
+			}
+#endif
 			if (fresh) {
 				const uint16_t *wb = wb_base + (size_t)a * (len + 1);
 				wb1 = i >= 1 ? wb[i - 1] : 0u;
@@ -554,14 +589,14 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 
 			if (mode == MODE_DERIVE) { // k,l were the parent's: take child derive_c's interval
 				if (STATS) ++n_derive;
-				k = ix.L2[derive_c] + sel4(derive_c, cnt_k) + 1;
-				l = ix.L2[derive_c] + sel4(derive_c, cnt_l);
+				k = Cof(derive_c) + sel4(derive_c, cnt_k) + 1;
+				l = Cof(derive_c) + sel4(derive_c, cnt_l);
 				e.k = k; e.l = l;
 				decide(); // next trip looks the child's own interval up
 			} else if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
 				if (STATS) ++n_exact;
-				k = ix.L2[ce] + sel4(ce, cnt_k) + 1;
-				l = ix.L2[ce] + sel4(ce, cnt_l);
+				k = Cof(ce) + sel4(ce, cnt_k) + 1;
+				l = Cof(ce) + sel4(ce, cnt_l);
 				--ii;
 				if (k > l) mode = MODE_POP;
 				else if (ii == 0) {
@@ -609,16 +644,19 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						if (st == STATE_M) { if (go < max_gapo) { gm = 1u | V << 1; gs = score + O.s_gapo; } }
 						else if (st == STATE_I) { if (ge < O.max_gape) gm = 1u; }
 						else if (ge < O.max_gape && (ge + go < max_diff || occ < (uint32_t)O.max_del_occ)) gm = V << 1;
-						if (gm & (gm - 1)) push_rec(k, l, (uint32_t)i | gm << 16, ptag | KIND_GAP << 27, gs, __popc(gm));
-						else if (gm) { // a single child is stored as the plain node it is (no derive trip later)
-							const uint32_t ngo = st == STATE_M ? go + 1 : go, nge = st == STATE_M ? ge : ge + 1;
-							const uint32_t tg = (uint32_t)mm | ngo << 8 | nge << 16 | a << 26;
-							if (gm == 1u) push_rec(k, l, (uint32_t)i | (uint32_t)i << 16, tg | STATE_I << 24, gs, 1);
-							else {
-								const uint32_t c = 30u - (uint32_t)__clz((int)gm); // bit 1 + c
-								push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l),
-								         (uint32_t)(i + 1) | (uint32_t)(i + 1) << 16, tg | STATE_D << 24, gs, 1);
+						if (gm) {
+							uint32_t rk = k, rl = l, rpos = (uint32_t)i | gm << 16, rtag = ptag | KIND_GAP << 27;
+							if (!(gm & (gm - 1))) { // a single child is stored as the plain node it is (no derive trip later)
+								const uint32_t ngo = st == STATE_M ? go + 1 : go, nge = st == STATE_M ? ge : ge + 1;
+								const uint32_t tg = (uint32_t)mm | ngo << 8 | nge << 16 | a << 26;
+								if (gm == 1u) { rpos = (uint32_t)i | (uint32_t)i << 16; rtag = tg | STATE_I << 24; }
+								else {
+									const uint32_t c = 30u - (uint32_t)__clz((int)gm); // bit 1 + c
+									rk = Cof(c) + sel4(c, cnt_k) + 1; rl = Cof(c) + sel4(c, cnt_l);
+									rpos = (uint32_t)(i + 1) | (uint32_t)(i + 1) << 16; rtag = tg | STATE_D << 24;
+								}
 							}
+							push_rec(rk, rl, rpos, rtag, gs, __popc(gm));
 						}
 					}
 					if (allow_M) { // mismatches (bwtgap.c:248-257): one KIND_MM record; the match is held
@@ -626,18 +664,21 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 #pragma unroll
 						for (uint32_t j = 1; j <= 3; ++j) mmask |= ((V >> ((ci + j) & 3u)) & 1u) << (j - 1);
 						if (ci > 3) mmask |= (V & 1u) << 3; // N: j = 4 is a mismatch too, c = (4 + 4) & 3 = 0
-						if (mmask & (mmask - 1)) push_rec(k, l, (uint32_t)i | mmask << 16, ptag | KIND_MM << 27, score + O.s_mm, __popc(mmask));
-						else if (mmask) {
-							const uint32_t c = (ci + (32u - (uint32_t)__clz((int)mmask))) & 3u; // bit j-1 -> c = (ci + j) & 3
-							push_rec(ix.L2[c] + sel4(c, cnt_k) + 1, ix.L2[c] + sel4(c, cnt_l), (uint32_t)i | (uint32_t)i << 16,
-							         (uint32_t)(mm + 1) | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26,
-							         score + O.s_mm, 1);
+						if (mmask) {
+							uint32_t rk = k, rl = l, rpos = (uint32_t)i | mmask << 16, rtag = ptag | KIND_MM << 27 | ci << 29;
+							if (!(mmask & (mmask - 1))) {
+								const uint32_t c = (ci + (32u - (uint32_t)__clz((int)mmask))) & 3u; // bit j-1 -> c = (ci + j) & 3
+								rk = Cof(c) + sel4(c, cnt_k) + 1; rl = Cof(c) + sel4(c, cnt_l);
+								rpos = (uint32_t)i | (uint32_t)i << 16;
+								rtag = (uint32_t)(mm + 1) | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
+							}
+							push_rec(rk, rl, rpos, rtag, score + O.s_mm, __popc(mmask));
 						}
 					}
 				}
 				if (ci < 4 && ((V >> ci) & 1u)) { // the match: last push, next pop -> registers
-					held.k = ix.L2[ci] + sel4(ci, cnt_k) + 1;
-					held.l = ix.L2[ci] + sel4(ci, cnt_l);
+					held.k = Cof(ci) + sel4(ci, cnt_k) + 1;
+					held.l = Cof(ci) + sel4(ci, cnt_l);
 					held.pos = (uint32_t)i;
 					held.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
 					held_valid = true; ++n_entries;

@@ -117,8 +117,8 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
 		const int slots = t == 0 ? n_slots : 1;
 		std::vector<uint4> ent((size_t)slots * caps[t]), alnbuf((size_t)slots * acaps[t]);
-		std::vector<uint32_t> nxt((size_t)slots * caps[t]), heads((size_t)slots * n_stacks);
-		B.ent = ent.data(); B.nxt = nxt.data(); B.heads = heads.data(); B.alnbuf = alnbuf.data();
+		std::vector<uint32_t> nxt((size_t)slots * caps[t]);
+		B.ent = ent.data(); B.nxt = nxt.data(); B.alnbuf = alnbuf.data(); B.heads = nullptr;
 		B.cap = caps[t]; B.aln_cap = acaps[t];
 		B.jobs = jobs; B.n_jobs = n_jobs;
 		int32_t *ovf = (t & 1) ? jobs_b.data() : jobs_a.data();

@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--genome-bp", type=int, default=GENOME_BP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -312,6 +313,36 @@ def main():
         except Exception as e:
             cpu_baseline = {"error": str(e)[:200]}
 
+    # ---- secondary kernels of the path (rank 0, N = 1): K4 SA->coordinate and K5 mate-rescue SW
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        rng = np.random.default_rng(5)
+        nq = 4_000_000
+        sa_k = rng.integers(1, idx.bwt[0].seq_len + 1, size=nq, dtype=np.uint32)
+        which = rng.integers(0, 2, size=nq, dtype=np.uint8)
+        api.cal_pac_pos(sa_k[:1000], which[:1000])
+        t0 = time.perf_counter(); api.cal_pac_pos(sa_k, which); dt4 = time.perf_counter() - t0
+        steps4 = float(np.mean(sa_k % 32))  # LF steps to the next sampled row when rows are uniform
+        nj, wlen, rlen = 200_000, 380, 100  # 2x100 bp, sigma 30: window = 6 sigma + 2 len (bwape.c:531-543)
+        begs = rng.integers(0, idx.l_pac - wlen - 1, size=nj)
+        sw_jobs = (abi.sw_job_t * nj)()
+        qkeep = []
+        for j in range(nj):
+            b = int(begs[j]); o = int(rng.integers(0, wlen - rlen))
+            q = T[b + o:b + o + rlen].copy(); q[rng.integers(0, rlen, size=3)] ^= 1
+            qkeep.append(q)
+            sw_jobs[j].beg, sw_jobs[j].reglen, sw_jobs[j].len = b, wlen, rlen
+            sw_jobs[j].seq = q.ctypes.data_as(C.POINTER(C.c_ubyte))
+        sw_res = (abi.sw_res_t * nj)()
+        lib = api.lib()
+        assert lib.bwa_gpu_mate_sw(1000, sw_jobs, sw_res) == 0
+        t0 = time.perf_counter(); rc = lib.bwa_gpu_mate_sw(nj, sw_jobs, sw_res); dt5 = time.perf_counter() - t0
+        assert rc == 0, lib.bwa_gpu_last_error()
+        extras = {"k4_sa": {"queries_per_s": nq / dt4, "host_call_ms": dt4 * 1e3, "lf_steps_per_query": steps4,
+                            "algorithmic_gb_s": 64.0 * steps4 * nq / dt4 / 1e9, "note": "host buffers in and out"},
+                  "k5_sw": {"jobs_per_s": nj / dt5, "host_call_ms": dt5 * 1e3, "gcups_forward": nj * wlen * rlen / dt5 / 1e9,
+                            "shape": f"{wlen} x {rlen}", "note": "host buffers in and out; forward + reverse pass"}}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -356,6 +387,7 @@ def main():
                      "stats_pass_ms": {"queue_empty": st_counts["ns_queue_empty"] / 1e6, "kernel": st_counts["ns_kernel"] / 1e6}},
         "cpu_baseline": cpu_baseline,
         "parity_sample": parity,
+        "other_kernels": extras,
         "wall_s_timed_region": wall_s,
     }
     print(json.dumps(line))

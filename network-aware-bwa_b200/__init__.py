@@ -10,4 +10,4 @@ Modules: api (ctypes binding of include/bwa_gpu.h -> libbwagpu.so, no fallback),
 abi (struct mirrors), index (FM-index build/load in the reference's formats),
 simulate (seeded genomes and reads), build (nvcc recipe for csrc/).
 """
-from . import abi, api, build, index, simulate  # noqa: F401
+from . import abi, api, build, index, shard, simulate  # noqa: F401

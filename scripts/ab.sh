@@ -1,5 +1,5 @@
 # A/B experiment runner: bash scripts/ab.sh <variant> [<variant> ...]   ("base" = the default library)
-A="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+A="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extras"
 for v in "$@"; do
   if [ "$v" = "base" ]; then unset BWAGPU_LIB; else export BWAGPU_LIB=$PWD/network-aware-bwa_b200/variants/libbwagpu_$v.so; fi
   echo "== $v"

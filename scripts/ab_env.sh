@@ -1,5 +1,5 @@
 # bash scripts/ab_env.sh "ENV1=a ENV2=b" "ENV1=c" ...   (each argument = one environment to bench under)
-A="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+A="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extras"
 for cfg in "$@"; do
   echo "== $cfg"
   env $cfg python bench.py $A 2>/dev/null | python -c "

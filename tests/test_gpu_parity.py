@@ -203,3 +203,26 @@ def test_mate_sw_empty_inputs(gpu_index):
     assert api.mate_sw([]) == []
     got = api.mate_sw([(10, 0, T[:30]), (10, 50, T[:0])])
     assert got[0][0] == -1 and got[1][0] == -1  # stdaln.c:559
+
+
+def test_multi_device_in_process(golden, small_index):
+    """All visible GPUs inside one process (bwa_gpu_init with several ids): the index is replicated,
+    reads are split into per-device ranges, results come back in read order."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    T, idx = small_index
+    api.destroy()
+    api.init(list(range(n_dev)))
+    try:
+        api.load_index(idx)
+        for name in ("pe100", "ragged"):
+            reads, opt, want = golden_case(golden, name)
+            got = api.aln_flat(reads.bases, reads.offs, opt)
+            assert R.compare_aln(want, got, f"{n_dev} devices / {name}") == []
+        assert api.get_stats()["n_devices"] == n_dev
+        out = api.cal_pac_pos(golden["sa_k"], golden["sa_which"])
+        assert np.array_equal(out, golden["sa_out"])
+    finally:
+        api.destroy()

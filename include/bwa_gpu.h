@@ -130,6 +130,11 @@ int bwa_gpu_init(int n_devices, const int *device_ids);
  * The host arrays are not referenced after the call returns. */
 int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64_t l_pac);
 
+/* (Re)load only the packed forward sequence (bwt_restore_pac, bwtio.c:145-152; 4 bases per byte,
+ * l_pac/4+1 bytes), for hosts that load it later than the BWTs, as bam2bam's memory plan does
+ * (bam2bam.txt:74-78).  Needed by bwa_gpu_mate_sw only. */
+int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac);
+
 void bwa_gpu_destroy(void);
 
 const char *bwa_gpu_last_error(void);

@@ -51,7 +51,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = [
-    "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_destroy", "bwa_gpu_last_error",
+    "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_load_pac", "bwa_gpu_destroy", "bwa_gpu_last_error",
     "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw",
     "bwa_gpu_get_stats", "bwa_gpu_set_stats",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",

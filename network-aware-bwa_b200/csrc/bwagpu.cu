@@ -332,6 +332,23 @@ extern "C" int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64
 	return 0;
 }
 
+extern "C" int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_load_pac: call bwa_gpu_init first");
+	if (!pac || l_pac <= 0) return fail("bwa_gpu_load_pac: bad argument");
+	for (Ctx *c : g_ctx) {
+		if (c->owner) { c->pac.p = c->owner->pac.p; c->l_pac = l_pac; c->has_pac = true; continue; }
+		CK(cudaSetDevice(c->dev));
+		const size_t nb = (size_t)(l_pac / 4 + 1);
+		if (c->pac.reserve(nb)) return 1;
+		CK(cudaMemcpy(c->pac.p, pac, nb, cudaMemcpyHostToDevice));
+		c->l_pac = l_pac;
+		c->has_pac = true;
+	}
+	return 0;
+}
+
 extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
 
 // ------------------------------------------------------------------ device pipeline for one resident chunk

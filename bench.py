@@ -338,9 +338,11 @@ def main():
         assert lib.bwa_gpu_mate_sw(1000, sw_jobs, sw_res) == 0
         t0 = time.perf_counter(); rc = lib.bwa_gpu_mate_sw(nj, sw_jobs, sw_res); dt5 = time.perf_counter() - t0
         assert rc == 0, lib.bwa_gpu_last_error()
+        sw_ms = api.get_stats()["ms_sw_kernel"]
         extras = {"k4_sa": {"queries_per_s": nq / dt4, "host_call_ms": dt4 * 1e3, "lf_steps_per_query": steps4,
                             "algorithmic_gb_s": 64.0 * steps4 * nq / dt4 / 1e9, "note": "host buffers in and out"},
                   "k5_sw": {"jobs_per_s": nj / dt5, "host_call_ms": dt5 * 1e3, "gcups_forward": nj * wlen * rlen / dt5 / 1e9,
+                            "kernel_ms": sw_ms, "gcups_forward_kernel": nj * wlen * rlen / (sw_ms / 1e3) / 1e9,
                             "shape": f"{wlen} x {rlen}", "note": "host buffers in and out; forward + reverse pass"}}
 
     if rank != 0:

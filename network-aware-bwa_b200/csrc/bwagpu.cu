@@ -756,7 +756,7 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 		s.n_reads += t.n_reads; s.n_aln += t.n_aln; s.n_overflow_t2 += t.n_overflow_t2; s.n_overflow_t3 += t.n_overflow_t3;
 		s.occ_fetches_width += t.occ_fetches_width; s.occ_fetches_search += t.occ_fetches_search;
 		s.own_fetches_width += t.own_fetches_width; s.own_fetches_search += t.own_fetches_search;
-		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.n_pruned += t.n_pruned; s.n_expand += t.n_expand; s.n_exact += t.n_exact; s.n_derive += t.n_derive; s.n_trips += t.n_trips; s.ns_queue_empty = std::max(s.ns_queue_empty, t.ns_queue_empty); s.ns_kernel = std::max(s.ns_kernel, t.ns_kernel); s.launches += t.launches;
+		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.n_pruned += t.n_pruned; s.n_expand += t.n_expand; s.n_exact += t.n_exact; s.n_derive += t.n_derive; s.ms_sw_kernel = std::max(s.ms_sw_kernel, t.ms_sw_kernel); s.n_trips += t.n_trips; s.ns_queue_empty = std::max(s.ns_queue_empty, t.ns_queue_empty); s.ns_kernel = std::max(s.ns_kernel, t.ns_kernel); s.launches += t.launches;
 		for (int q = 0; q < 4; ++q) s.ms_tier[q] = std::max(s.ms_tier[q], t.ms_tier[q]);
 	}
 	s.n_devices = 0;
@@ -892,5 +892,8 @@ extern "C" int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_r
 	Ctx *c = g_ctx[0];
 	CK(cudaSetDevice(c->dev));
 	if (!c->has_pac) return fail("no packed reference loaded (pac was NULL in bwa_gpu_load_index)");
-	return sw_batch(c->st, c->pac.p, c->l_pac, n, jobs, res, fail);
+	double ms = 0;
+	const int rc = sw_batch(c->st, c->pac.p, c->l_pac, n, jobs, res, fail, &ms);
+	c->stats.ms_sw_kernel = ms;
+	return rc;
 }

@@ -17,8 +17,13 @@
 //
 // Pass 2 (start cell) is the reference's adaptive band walked backwards from the end cell
 // (stdaln.c:638-696).  Its band limits for row j depend on the finished row j+1, so rows
-// cannot be pipelined; it is restated literally and run by lane 0 on shared memory.  It
-// touches ~6x fewer cells than pass 1.
+// cannot be pipelined; instead each ROW is spread over the lanes.  A row is computed in two
+// phases on shared memory: (A) every band cell reads the previous row's H/E and forms its
+// F-less value; (B) the horizontal chain F(t+1) = max(F(t) - r, h0(t) - q - r) is a max-plus
+// prefix scan (5 shuffles per 32 cells).  This reproduces the reference's H exactly: its
+// `if (last_h > 0)` guard only ever skips non-positive F values, which cannot change an H >= 0.
+// The running maximum, the `score_r - qr == score_f` early stop and the band update are then
+// applied with the sequential first-in-order semantics (ballot + find-first).
 //
 // Pass 3 (banded global alignment for the CIGAR, stdaln.c:723-735) is not part of this
 // call; it and the accept/reject arithmetic in doubles (bwape.c:592-600) stay on the host.
@@ -53,12 +58,14 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 {
 	extern __shared__ int smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int q_words = (len2_max + 4) >> 2;
-	const int per_warp = q_words + 2 * (len2_max + 1) + 2 * (len1_max + 2);
+	const int q_words = (len2_max + 4) >> 2, r_words = (len1_max + 4) >> 2;
+	const int per_warp = q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2);
 	int *base = smem + warp * per_warp;
 	uint8_t *q = (uint8_t *)base;
-	int *edge_h = base + q_words, *edge_f = edge_h + len2_max + 1;
+	uint8_t *refb = (uint8_t *)(base + q_words); // the window's bases, unpacked once per job
+	int *edge_h = base + q_words + r_words, *edge_f = edge_h + len2_max + 1;
 	int *rh = edge_f + len2_max + 1, *re = rh + len1_max + 2;
+	int *th0 = re + len1_max + 2, *tee = th0 + len1_max + 2; // pass 2, phase A -> phase B
 	const unsigned full = 0xffffffffu;
 
 	for (;;) {
@@ -73,6 +80,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 			continue;
 		}
 		for (int t = lane; t < len2; t += 32) q[t] = reads[J.q_off + t];
+		for (int t = lane; t < len1; t += 32) refb[t] = (uint8_t)pac_base(pac, J.beg + t);
 		__syncwarp();
 
 		// ---------------- pass 1: forward score, wavefront over column super-blocks
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 #pragma unroll
 			for (int c = 0; c < SW_CMAX; ++c) {
 				H[c] = 0; E[c] = 0;
-				R[c] = c < my_n ? pac_base(pac, J.beg + my0 + c) : 0;
+				R[c] = c < my_n ? refb[my0 + c] : 0;
 			}
 			int h_out = 0, f_out = 0, diag_in = 0;
 			const bool last_sb = sb == n_sb - 1;
@@ -141,43 +149,92 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 		int start_i = 0, start_j = 0, flag = 0;
 		if (score_f > 32000) flag = 1; // the reference would have rescaled (stdaln.c:587-606); not restated
 
-		// ---------------- pass 2: reverse band from the end cell (lane 0; stdaln.c:638-696)
-		if (lane == 0 && !flag && score_f >= 1 && end_i > 0 && end_j > 0) {
-			for (int i = 0; i <= end_i; ++i) { rh[i] = 0; re[i] = 0; }
-			int score_r = sw_sc(pac_base(pac, J.beg + end_i - 1), q[end_j - 1]);
+		// ---------------- pass 2: reverse band from the end cell (stdaln.c:638-696), one row at a time
+		if (!flag && score_f >= 1 && end_i > 0 && end_j > 0) {
+			const int NEG = -(1 << 28);
+			for (int i = lane; i <= end_i + 1; i += 32) { rh[i] = 0; re[i] = 0; }
+			__syncwarp();
+			int score_r = sw_sc(refb[end_i - 1], q[end_j - 1]);
 			start_i = end_i; start_j = end_j;
-			rh[end_i] = SW_QR + score_r;
+			if (lane == 0) rh[end_i] = SW_QR + score_r;
+			__syncwarp();
 			int start = end_i - 1, end = end_i - 3;
 			if (end <= 0) end = 0;
-			for (int j = end_j - 1; j != 0; --j) {
-				int last_h = 0, f = 0, x = start + 1;
-				bool stop = false;
-				if (start < end) { flag = 2; break; }
+			const int target = score_f + SW_QR;
+			bool stop = false;
+			for (int j = end_j - 1; j != 0 && !stop; --j) {
+				if (start < end) { flag = 2; break; } // never observed; the reference would run off its array
 				const int qj = q[j - 1];
-				for (int i = start; i != end; --i, --x) {
-					int cur = rh[x] + sw_sc(pac_base(pac, J.beg + i - 1), qj);
-					if (cur < 0) cur = 0;
-					if (last_h > 0) {
-						f = f > last_h - SW_Q ? f - SW_R : last_h - SW_QR;
-						if (cur < f) cur = f;
-					}
+				const int B = start - end; // band cells i = start, start-1, ..., end+1  <->  t = 0 .. B-1
+				// phase A: F-less cell values from the previous row's state
+				for (int t = lane; t < B; t += 32) {
+					const int i = start - t, x = i + 1;
+					int h0 = rh[x] + sw_sc(refb[i - 1], qj);
+					if (h0 < 0) h0 = 0;
 					const int left = rh[x - 1];
 					int ee = re[x] > left - SW_Q ? re[x] - SW_R : left - SW_QR;
 					if (ee < 0) ee = 0;
-					if (cur < ee) cur = ee;
-					rh[x] = last_h; re[x] = ee;
-					last_h = cur;
-					if (score_r < cur) {
-						score_r = cur; start_i = i; start_j = j;
-						if (score_r - SW_QR == score_f) { stop = true; break; }
+					if (h0 < ee) h0 = ee;
+					th0[t] = h0; tee[t] = ee;
+				}
+				__syncwarp();
+				// phase B: horizontal chain by prefix scan, writes, running maximum
+				int F0 = 0, run = score_r;
+				for (int tb = 0; tb < B && !stop; tb += 32) {
+					const int t = tb + lane;
+					const bool valid = t < B;
+					const int i = start - t;
+					const int h0 = valid ? th0[t] : 0;
+					// exclusive prefix max of h0(s) - qr + r*s over the lanes before me
+					int v = valid ? h0 - SW_QR + SW_R * lane : NEG, pm = v;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const int o = __shfl_up_sync(full, pm, d);
+						if (lane >= d && o > pm) pm = o;
+					}
+					int pex = __shfl_up_sync(full, pm, 1);
+					if (lane == 0) pex = NEG;
+					int F = F0 - SW_R * lane;
+					if (lane > 0 && pex - SW_R * (lane - 1) > F) F = pex - SW_R * (lane - 1);
+					const int cur = h0 > F ? h0 : F;
+					if (valid) { rh[i] = cur; re[i + 1] = tee[t]; }
+					// running strict maximum in cell order, and the early stop of stdaln.c:684-686
+					int cm = valid ? cur : NEG, im = cm;
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const int o = __shfl_up_sync(full, im, d);
+						if (lane >= d && o > im) im = o;
+					}
+					int ex = __shfl_up_sync(full, im, 1); // maximum over everything before this cell, earlier rows included
+					if (lane == 0 || ex < run) ex = run;
+					const bool newmax = valid && cur > ex;
+					const unsigned hit = __ballot_sync(full, newmax && cur == target);
+					if (hit) {
+						const int ln = __ffs((int)hit) - 1;
+						score_r = target; start_i = start - (tb + ln); start_j = j;
+						stop = true;
+					} else {
+						const int cmax = __shfl_sync(full, im, 31);
+						if (cmax > run) {
+							const unsigned at = __ballot_sync(full, valid && cur == cmax);
+							run = cmax; start_i = start - (tb + __ffs((int)at) - 1); start_j = j;
+						}
+						// carry the chain into the next 32 cells
+						const int Fn = F - SW_R > h0 - SW_QR ? F - SW_R : h0 - SW_QR;
+						F0 = __shfl_sync(full, Fn, 31);
 					}
 				}
-				rh[x] = last_h; re[x] = 0;
 				if (stop) break;
+				score_r = run;
+				__syncwarp();
+				if (lane == 0) { rh[start + 1] = 0; re[end + 1] = 0; }
+				__syncwarp();
+				// recalculate the boundaries of the band (stdaln.c:691-695)
 				if (rh[start] <= SW_QR) --start;
 				if (start <= 0) start = 0;
 				end = start_i - (start_j - j) - (score_r + (start_j - j) * SW_MAXSC) / SW_R - 1;
 				if (end <= 0) end = 0;
+				__syncwarp();
 			}
 		}
 		if (lane == 0) {
@@ -192,8 +249,9 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 
 // host launcher: stages jobs + reads, runs k_sw, copies results back
 static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n, const bwa_gpu_sw_job_t *jobs,
-                    bwa_gpu_sw_res_t *res, int (*fail)(const char *, ...))
+                    bwa_gpu_sw_res_t *res, int (*fail)(const char *, ...), double *kernel_ms)
 {
+	if (kernel_ms) *kernel_ms = 0;
 	if (n == 0) return 0;
 	std::vector<SwJob> hj(n);
 	int len1_max = 1, len2_max = 1;
@@ -209,8 +267,8 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 		if (hj[i].len1 > len1_max) len1_max = hj[i].len1;
 		if (j.len > len2_max) len2_max = j.len;
 	}
-	const int q_words = (len2_max + 4) >> 2;
-	const size_t smem = (size_t)4 * (q_words + 2 * (len2_max + 1) + 2 * (len1_max + 2)) * sizeof(int);
+	const int q_words = (len2_max + 4) >> 2, r_words = (len1_max + 4) >> 2;
+	const size_t smem = (size_t)4 * (q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2)) * sizeof(int);
 	if (smem > 200 * 1024) return fail("bwa_gpu_mate_sw: window %d x read %d needs %zu B of shared memory per block", len1_max, len2_max, smem);
 	std::vector<uint8_t> hq((size_t)q_total + 1);
 	for (int i = 0; i < n; ++i)
@@ -234,10 +292,20 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 	if (bps < 1) bps = 1;
 	int blocks = n_sm * bps;
 	if (blocks > (n + 3) / 4) blocks = (n + 3) / 4;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	cudaEventRecord(e0, st);
 	k_sw<<<blocks, 128, smem, st>>>(d_pac, d_jobs, n, d_q, d_res, len1_max, len2_max, d_cnt);
+	cudaEventRecord(e1, st);
 	SWCK(cudaGetLastError());
 	SWCK(cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t), cudaMemcpyDeviceToHost, st));
 	SWCK(cudaStreamSynchronize(st));
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (kernel_ms) *kernel_ms = ms;
+		cudaEventDestroy(e0); cudaEventDestroy(e1);
+	}
 #undef SWCK
 	cudaFree(d_jobs); cudaFree(d_q); cudaFree(d_res); cudaFree(d_cnt);
 	for (int i = 0; i < n; ++i)

@@ -113,7 +113,7 @@ struct Tier {
 };
 
 // One Ctx = one LANE: a host thread's worth of state on one device (stream, scratch arenas,
-// pinned staging).  A device gets BWAGPU_LANES lanes (default 4) that share its index; a
+// pinned staging).  A device gets BWAGPU_LANES lanes (default 3) that share its index; a
 // batch call gives every lane a contiguous range of reads, so host-side packing/unpacking of
 // one lane overlaps the kernels of another and a kernel's straggler tail overlaps the next
 // kernel's start.
@@ -220,7 +220,7 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 		CK(cudaGetDeviceProperties(&prop, id));
 		if (prop.major < 10) return fail("device %d is sm_%d%d; libbwagpu is built for sm_100a only", id, prop.major, prop.minor);
 		CK(cudaSetDevice(id));
-		const int lanes = (int)env_u32("BWAGPU_LANES", 4);
+		const int lanes = (int)env_u32("BWAGPU_LANES", 3);
 		Ctx *first = nullptr;
 		for (int ln = 0; ln < lanes; ++ln) {
 			Ctx *c = new Ctx();
@@ -576,11 +576,36 @@ struct FlatJob {
 	std::string err;
 };
 
+// Host-side helper threads of one lane: packing reads and handing results back are embarrassingly
+// parallel over reads once the per-read offsets are known.
+static int host_threads()
+{
+	static int n = 0;
+	if (!n) {
+		const unsigned hw = std::thread::hardware_concurrency();
+		const uint32_t lanes = env_u32("BWAGPU_LANES", 3);
+		n = (int)env_u32("BWAGPU_HOST_THREADS", std::max(1u, std::min(8u, (hw ? hw : 8u) / std::max(1u, lanes))));
+	}
+	return n;
+}
+
+template <typename F> static void parallel_for(int n, F fn)
+{
+	const int nt = std::min(host_threads(), std::max(1, n / 4096));
+	if (nt <= 1) { fn(0, n, 0); return; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < nt; ++t) {
+		const int lo = (int)((int64_t)n * t / nt), hi = (int)((int64_t)n * (t + 1) / nt);
+		th.emplace_back([=]() { fn(lo, hi, t); });
+	}
+	for (auto &x : th) x.join();
+}
+
 static size_t chunk_reads()
 {
 	const char *env = getenv("BWAGPU_CHUNK");
 	size_t c = env ? (size_t)atoll(env) : 0;
-	return c > 0 ? c : (size_t)1 << 19; // 512 K reads: several chunks per lane so packing, copies and kernels of different lanes overlap
+	return c > 0 ? c : (size_t)1 << 21; // 2 M reads: long kernels (the straggler tail of k_search is per launch), two lanes alternate
 }
 
 static int run_range(Ctx *c, FlatJob &J)
@@ -595,33 +620,63 @@ static int run_range(Ctx *c, FlatJob &J)
 	for (size_t r0 = 0; r0 < (size_t)J.n; r0 += CH) {
 		const int n = (int)std::min(CH, (size_t)J.n - r0);
 		auto t0 = std::chrono::steady_clock::now();
-		// ---- marshal: pack bases, per-read meta
-		uint64_t n_bases = 0;
-		for (int i = 0; i < n; ++i)
-			n_bases += J.seqs ? J.seqs[r0 + i].len : (uint64_t)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
-		if (n_bases >= 0xffffffffull) return fail("chunk holds %llu bases; lower BWAGPU_CHUNK", (unsigned long long)n_bases);
-		if (c->h_seq.reserve(n_bases + 1) || c->h_meta.reserve(n)) return 1;
-		uint64_t so = 0, wo = 0;
-		uint32_t n_stacks = 1;
-		for (int i = 0; i < n; ++i) {
-			int len;
-			uint32_t n_amb = 0;
-			uint8_t *dst = c->h_seq.p + so;
-			if (J.seqs) {
-				const bwa_seq_t *p = J.seqs + r0 + i;
-				len = (int)p->len;
-				n_amb = pack_seq_pair(dst, p->seq, p->rseq, len);
-			} else {
-				const uint8_t *src = J.bases + J.offs[r0 + i];
-				len = (int)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
-				n_amb = pack_read(dst, src, len);
+		// ---- marshal, pass 1 (serial, cheap): lengths -> offsets into the packed arrays
+		std::vector<uint64_t> so_of(n + 1), wo_of(n + 1);
+		int max_len = 0;
+		{
+			// per-read sizes in parallel (the bwa_seq_t array alone is 200 B per read), then one serial scan
+			std::vector<int> bad_t(64, -1), max_t(64, 0);
+			parallel_for(n, [&](int lo, int hi, int tid) {
+				for (int i = lo; i < hi; ++i) {
+					const int len = J.seqs ? (int)J.seqs[r0 + i].len : (int)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
+					if (len < 0 || len > 32766) { bad_t[tid] = len; return; }
+					so_of[i + 1] = (uint64_t)len;
+					wo_of[i + 1] = len > 0 ? 2 * (uint64_t)(len + 1) + (len > opt->seed_len ? 2 * (uint64_t)(opt->seed_len + 1) : 0) : 0;
+					if (len > max_t[tid]) max_t[tid] = len;
+				}
+			});
+			for (int t = 0; t < 64; ++t) {
+				if (bad_t[t] != -1) return fail("read length %d not supported (max 32766)", bad_t[t]);
+				if (max_t[t] > max_len) max_len = max_t[t];
 			}
-			uint64_t we = 0;
-			if (fill_meta(len, so, wo, opt, mdt, c->h_meta.p[i], we, n_stacks)) return 1;
-			c->h_meta.p[i].n_amb = n_amb;
-			so += (uint64_t)len;
-			wo += we;
-			if (wo >= 0xffffffffull) return fail("width arena exceeds 2^32 entries; lower BWAGPU_CHUNK");
+			so_of[0] = wo_of[0] = 0;
+			for (int i = 0; i < n; ++i) { so_of[i + 1] += so_of[i]; wo_of[i + 1] += wo_of[i]; }
+		}
+		const uint64_t n_bases = so_of[n], wo = wo_of[n];
+		if (n_bases >= 0xffffffffull) return fail("chunk holds %llu bases; lower BWAGPU_CHUNK", (unsigned long long)n_bases);
+		if (wo >= 0xffffffffull) return fail("width arena exceeds 2^32 entries; lower BWAGPU_CHUNK");
+		if (c->h_seq.reserve(n_bases + 1) || c->h_meta.reserve(n)) return 1;
+		for (int len = 0; len <= max_len; ++len) (void)mdt.get(len, opt); // fill the table: read-only below
+		// ---- pass 2 (parallel over reads): pack bases, per-read meta
+		uint32_t n_stacks = 1;
+		{
+			std::vector<uint32_t> ns_t(64, 1);
+			std::vector<int> rc_t(64, 0);
+			std::vector<std::string> err_t(64);
+			parallel_for(n, [&](int lo, int hi, int tid) {
+				MaxDiffTable local = mdt; // private copy: get() may not mutate shared state
+				for (int i = lo; i < hi; ++i) {
+					int len;
+					uint32_t n_amb;
+					uint8_t *dst = c->h_seq.p + so_of[i];
+					if (J.seqs) {
+						const bwa_seq_t *p = J.seqs + r0 + i;
+						len = (int)p->len;
+						n_amb = pack_seq_pair(dst, p->seq, p->rseq, len);
+					} else {
+						const uint8_t *src = J.bases + J.offs[r0 + i];
+						len = (int)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
+						n_amb = pack_read(dst, src, len);
+					}
+					uint64_t we = 0;
+					if (fill_meta(len, so_of[i], wo_of[i], opt, local, c->h_meta.p[i], we, ns_t[tid])) { rc_t[tid] = 1; err_t[tid] = t_err; return; }
+					c->h_meta.p[i].n_amb = n_amb;
+				}
+			});
+			for (int t = 0; t < 64; ++t) {
+				if (rc_t[t]) return fail("%s", err_t[t].c_str());
+				if (ns_t[t] > n_stacks) n_stacks = ns_t[t];
+			}
 		}
 		auto t1 = std::chrono::steady_clock::now();
 		c->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -648,10 +703,15 @@ static int run_range(Ctx *c, FlatJob &J)
 		memcpy(J.n_aln + r0, c->h_naln.p, (size_t)n * 4);
 		memcpy(J.max_entries + r0, c->h_maxent.p, (size_t)n * 4);
 		if (J.seqs) { // struct API: hand the hits back the way bwa_cal_sa_reg_gap does
-			const uint4 *src = c->h_out.p;
-			for (int i = 0; i < n; ++i) {
+			std::vector<int64_t> aoff(n + 1);
+			aoff[0] = 0;
+			for (int i = 0; i < n; ++i) aoff[i + 1] = aoff[i] + c->h_naln.p[i];
+			std::vector<int> rc_t(64, 0);
+			parallel_for(n, [&](int lo, int hi, int tid) {
+			for (int i = lo; i < hi; ++i) {
 				bwa_seq_t *p = J.seqs + r0 + i;
 				const int na = c->h_naln.p[i];
+				const uint4 *src = c->h_out.p + aoff[i];
 				// bwtaln.c:113 resets these before the search
 				p->sa = 0; p->type = 0 /* BWA_TYPE_NO_MATCH */; p->c1 = p->c2 = 0;
 				p->n_aln = na;
@@ -661,12 +721,13 @@ static int run_range(Ctx *c, FlatJob &J)
 				int m_aln = 4;
 				while (m_aln < na) m_aln <<= 1;
 				p->aln = (bwt_aln1_t *)calloc((size_t)m_aln, sizeof(bwt_aln1_t));
-				if (!p->aln) return fail("calloc failed");
+				if (!p->aln) { rc_t[tid] = 1; return; }
 				if (na) memcpy(p->aln, src, (size_t)na * 16);
-				src += na;
 				// untouched when the search never ran (bwtgap.c:120-123)
 				if (c->h_maxent.p[i] > 0) p->max_entries = c->h_maxent.p[i];
 			}
+			});
+			for (int t = 0; t < 64; ++t) if (rc_t[t]) return fail("calloc failed");
 		} else {
 			const size_t base = J.pool.size();
 			J.pool.resize(base + (size_t)tot);

@@ -210,6 +210,7 @@ typedef struct {
 	int64_t n_pruned, n_expand, n_exact, n_derive; /* pops pruned / nodes expanded / exact-tail steps / group-child derivations */
 	int64_t n_trips;          /* loop trips summed over threads (stats builds) */
 	double ms_sw_kernel;      /* last bwa_gpu_mate_sw call: k_sw device time */
+	int64_t x_chunks_used;    /* most 1024-record overflow chunks a k_search launch took from the shared pool */
 	int64_t ns_queue_empty;   /* last k_search launch: time from start until the work queue ran dry */
 	int64_t ns_kernel;        /* last k_search launch: start to last thread exit (globaltimer) */
 } bwa_gpu_stats_t;

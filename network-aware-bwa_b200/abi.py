@@ -133,7 +133,7 @@ class stats_t(C.Structure):
         ("ms_tier", C.c_double * 4),
         ("n_stored", C.c_int64),
         ("n_pruned", C.c_int64), ("n_expand", C.c_int64), ("n_exact", C.c_int64), ("n_derive", C.c_int64),
-        ("n_trips", C.c_int64), ("ms_sw_kernel", C.c_double), ("ns_queue_empty", C.c_int64), ("ns_kernel", C.c_int64),
+        ("n_trips", C.c_int64), ("ms_sw_kernel", C.c_double), ("x_chunks_used", C.c_int64), ("ns_queue_empty", C.c_int64), ("ns_kernel", C.c_int64),
     ]
 
     def asdict(self) -> dict:

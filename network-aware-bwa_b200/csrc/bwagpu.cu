@@ -106,10 +106,9 @@ template <typename T> struct PinBuf {
 };
 
 struct Tier {
-	uint32_t cap, aln_cap, slots_blocks; // slots = blocks * 128
+	uint32_t cap, slots_blocks, ctab_stride; // slots = blocks * 128
 	DevBuf<uint4> ent;
 	DevBuf<uint32_t> nxt, heads;
-	DevBuf<uint4> alnbuf;
 };
 
 // One Ctx = one LANE: a host thread's worth of state on one device (stream, scratch arenas,
@@ -143,7 +142,11 @@ struct Ctx {
 	DevBuf<int> d_counters;            // [0] work [1] overflow [2] pool_count(u32)
 	DevBuf<unsigned long long> d_stats; // 4
 	DevBuf<uint8_t> d_cubtmp;
-	Tier tier[4];
+	Tier tier[2];
+	DevBuf<uint4> xent;           // shared overflow pool of this lane (records)
+	DevBuf<uint32_t> xnxt, ctab, x_free_next;
+	DevBuf<unsigned long long> x_free_top;
+	uint32_t x_chunks = 0;
 	// pinned staging
 	PinBuf<uint8_t> h_seq;
 	PinBuf<ReadMeta> h_meta;
@@ -191,7 +194,8 @@ extern "C" void bwa_gpu_destroy(void)
 		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release(); c->d_ids.release(); c->d_order.release(); c->d_keys.release(); c->d_keys2.release();
 		c->d_pooloff.release(); c->d_outoff.release(); c->d_pool.release(); c->d_out.release();
 		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
-		for (Tier &t : c->tier) { t.ent.release(); t.nxt.release(); t.heads.release(); t.alnbuf.release(); }
+		for (Tier &t : c->tier) { t.ent.release(); t.nxt.release(); t.heads.release(); }
+		c->xent.release(); c->xnxt.release(); c->ctab.release(); c->x_free_next.release(); c->x_free_top.release();
 		c->h_seq.release(); c->h_meta.release(); c->h_naln.release(); c->h_maxent.release(); c->h_out.release();
 		c->h_counters.release();
 		c->d_q.release(); c->d_qo.release(); c->d_which.release();
@@ -352,15 +356,29 @@ extern "C" int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac)
 extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
 
 // ------------------------------------------------------------------ device pipeline for one resident chunk
-static const int N_TIERS = 4;
+static const int N_TIERS = 2;
 
-// Tier t = (stack arena entries per thread, hit-list capacity, resident threads).  Every read
-// starts in tier 0; a read whose stack or hit list outgrows its tier is retried from scratch
-// in the next one (fewer threads, bigger arenas).  The last tier holds opt->max_entries + 16
-// entries, which the search can never exceed (bwtgap.c:140 stops it first).
+// Pass 0 (optimistic): every resident thread has a small private arena (BWAGPU_T1_CAP records, shared by
+// the search stack and the read's hit list) and takes more from a shared pool of 1024-record chunks when a search goes deep; the pool is
+// bump-allocated within a launch, so it can run dry -- the reads it fails are retried from scratch in pass 1 (guaranteed): few enough threads
+// that each can own opt->max_entries + 16 records, which the search can never exceed (bwtgap.c:140
+// stops it first).
 static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt)
 {
 	Tier &T = c->tier[t];
+	// the shared pool: BWAGPU_POOL_MB (default 16384) per lane, never more than a quarter of what is free
+	if (!c->xent.p) {
+		size_t free_b = 0, total_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+		size_t want = (size_t)env_u32("BWAGPU_POOL_MB", 16384) << 20;
+		if (want > free_b / 4) want = free_b / 4;
+		size_t chunks = want / ((size_t)ARENA_CHUNK * 20);
+		if (chunks < 64) chunks = 64;
+		if (c->xent.reserve(chunks << ARENA_CHUNK_LOG) || c->xnxt.reserve(chunks << ARENA_CHUNK_LOG)) return 1;
+		if (c->x_free_next.reserve(chunks + 1) || c->x_free_top.reserve(1)) return 1;
+		c->x_chunks = (uint32_t)chunks;
+	}
+	const uint32_t need = max_entries_opt + 16; // records one search can hold at most
 	if (t == 0) {
 		int bps = 0;
 		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0; // bucket heads
@@ -372,20 +390,22 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_T1_BLOCKS_PER_SM", 64));
 		T.slots_blocks = (uint32_t)(bps * c->n_sm);
 		T.cap = env_u32("BWAGPU_T1_CAP", 2048);
-		T.aln_cap = 64;
-	} else if (t == 1) {
-		T.slots_blocks = env_u32("BWAGPU_T2_BLOCKS", 256); // 32768 threads
-		T.cap = env_u32("BWAGPU_T2_CAP", 8192); T.aln_cap = 512;
-	} else if (t == 2) {
-		T.slots_blocks = 16; // 2048 threads
-		T.cap = 131072; T.aln_cap = 8192;
 	} else {
-		T.slots_blocks = 1; // 128 threads
-		T.cap = max_entries_opt + 16; T.aln_cap = 1u << 18;
+		// guaranteed: threads x (chunks one search may need) <= pool
+		const uint32_t per_thread = (need + ARENA_CHUNK - 1) >> ARENA_CHUNK_LOG;
+		uint32_t threads = c->x_chunks / std::max(1u, per_thread);
+		if (threads < 1) return fail("overflow pool (%u chunks) is smaller than one search (%u chunks); raise BWAGPU_POOL_MB", c->x_chunks, per_thread);
+		if (threads > 4096) threads = 4096;
+		T.slots_blocks = std::max(1u, threads / 128);
+		if (threads < 128) return fail("overflow pool too small for the guaranteed pass (%u threads); raise BWAGPU_POOL_MB or lower -m", threads);
+		T.cap = 1024;
 	}
-	if (T.cap > max_entries_opt + 16) T.cap = max_entries_opt + 16;
+	if (T.cap > need) T.cap = need;
 	const size_t slots = (size_t)T.slots_blocks * 128;
-	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap) || T.alnbuf.reserve(slots * T.aln_cap)) return 1;
+	const uint32_t stride = (need > T.cap ? (need - T.cap + ARENA_CHUNK - 1) >> ARENA_CHUNK_LOG : 0) + 1;
+	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap)) return 1;
+	if (c->ctab.reserve(slots * stride)) return 1;
+	T.ctab_stride = stride;
 #if !BWAGPU_SMEM_HEADS
 	if (T.heads.reserve(slots * n_stacks)) return 1;
 #endif
@@ -403,9 +423,12 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
 	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(16)) return 1;
-	size_t pool_cap = std::max<size_t>((size_t)n * 8, 1u << 20);
+	// hit pool of the chunk (completion order): 16 hits per read on average to start with; grown and the
+	// affected reads retried when a batch of short, repetitive reads needs more
+	size_t pool_cap = std::max<size_t>((size_t)n * env_u32("BWAGPU_HITS_PER_READ", 16), 1u << 16);
 	if (pool_cap > 0xfffffff0ull) pool_cap = 0xfffffff0ull;
 	if (c->d_pool.reserve(pool_cap)) return 1;
+	pool_cap = std::min<size_t>(c->d_pool.cap, 0xfffffff0ull);
 
 	Batch B;
 	B.ix[0] = c->ix[0]; B.ix[1] = c->ix[1];
@@ -473,17 +496,27 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 
 	// K3, tier by tier
 	int n_jobs = n;
-	for (int t = 0; t < N_TIERS && n_jobs > 0; ++t) {
+	for (int pass = 0; n_jobs > 0; ++pass) {
+		const int t = pass < N_TIERS ? pass : N_TIERS - 1;
+		if (pass > 8) return fail("%d reads still unfinished after %d passes", n_jobs, pass);
 		if (tier_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
 		Tier &T = c->tier[t];
-		B.ent = T.ent.p; B.nxt = T.nxt.p; B.alnbuf = T.alnbuf.p; B.heads = T.heads.p;
-		B.cap = T.cap; B.aln_cap = T.aln_cap;
+		B.ent = T.ent.p; B.nxt = T.nxt.p; B.heads = T.heads.p;
+		B.cap = T.cap;
+		B.xent = c->xent.p; B.xnxt = c->xnxt.p; B.ctab = c->ctab.p; B.ctab_stride = T.ctab_stride;
+		B.x_chunks = c->x_chunks; B.x_next = (unsigned int *)(c->d_counters.p + 3);
+		B.x_free_top = c->x_free_top.p; B.x_free_next = c->x_free_next.p;
 		B.jobs = jobs; B.n_jobs = n_jobs;
-		int32_t *ovf = (t & 1) ? c->d_jobs_b.p : c->d_jobs_a.p;
+		int32_t *ovf = (pass & 1) ? c->d_jobs_b.p : c->d_jobs_a.p;
 		B.overflow_ids = ovf;
 		CK(cudaMemsetAsync(c->d_counters.p, 0, 2 * sizeof(int), c->st)); // work + overflow counters
+		CK(cudaMemsetAsync(c->d_counters.p + 3, 0, sizeof(int), c->st)); // overflow-pool bump counter
+		{
+			static const unsigned long long empty_stack = 0xffffffffull; // tag 0, head NIL
+			CK(cudaMemcpyAsync(c->x_free_top.p, &empty_stack, sizeof empty_stack, cudaMemcpyHostToDevice, c->st));
+		}
 		CK(cudaEventRecord(c->ev[8 + 2 * t], c->st));
-		if (t > 0) { // pristine widths for the reads being retried
+		if (pass > 0) { // pristine widths for the reads being retried
 			const int wb = (int)((4ll * n_jobs + 127) / 128);
 			if (stats) k_width<true><<<wb, 128, 0, c->st>>>(B);
 			else k_width<false><<<wb, 128, 0, c->st>>>(B);
@@ -507,14 +540,28 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			c->stats.ms_tier[t] += tms;
 		}
 		const int n_over = c->h_counters.p[1];
+		c->stats.x_chunks_used = std::max<int64_t>(c->stats.x_chunks_used, (int64_t)(unsigned int)c->h_counters.p[3]);
 		const unsigned int pool_used = (unsigned int)c->h_counters.p[2];
-		if (pool_used > pool_cap) { // the shared pool ran out: grow it and rerun the flagged reads at this tier
-			return fail("aln pool overflow (%u > %zu records in one chunk); lower BWAGPU_CHUNK", pool_used, pool_cap);
+		if (pool_used > pool_cap) {
+			// The hit pool ran out: reads that could not place their hits were flagged like arena
+			// overflows.  Grow the pool (keeping what finished reads wrote) and rewind the counter to the
+			// old capacity: everything below it is either valid or an unreferenced reservation.
+			size_t want = std::min<size_t>((size_t)pool_used * 2 + (1u << 20), 0xfffffff0ull);
+			if (want <= pool_cap) return fail("hit pool cannot grow beyond %zu records in one chunk; lower BWAGPU_CHUNK", pool_cap);
+			uint4 *bigger = nullptr;
+			cudaError_t e = cudaMalloc((void **)&bigger, want * sizeof(uint4));
+			if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) for the hit pool: %s", want * sizeof(uint4), cudaGetErrorString(e));
+			CK(cudaMemcpyAsync(bigger, c->d_pool.p, pool_cap * sizeof(uint4), cudaMemcpyDeviceToDevice, c->st));
+			const unsigned int rewind = (unsigned int)pool_cap;
+			CK(cudaMemcpyAsync(c->d_counters.p + 2, &rewind, sizeof rewind, cudaMemcpyHostToDevice, c->st));
+			CK(cudaStreamSynchronize(c->st));
+			cudaFree(c->d_pool.p);
+			c->d_pool.p = bigger; c->d_pool.cap = want;
+			pool_cap = want;
+			B.pool = bigger; B.pool_cap = (uint32_t)pool_cap;
 		}
-		if (t == 0) c->stats.n_overflow_t2 += n_over;
-		if (t == 1) c->stats.n_overflow_t3 += n_over;
-		if (n_over > 0 && t == N_TIERS - 1)
-			return fail("%d reads exceeded the largest search tier (stack > max_entries+16 or > %u hits)", n_over, T.aln_cap);
+		if (pass == 0) c->stats.n_overflow_t2 += n_over;
+		else c->stats.n_overflow_t3 += n_over;
 		jobs = ovf;
 		n_jobs = n_over;
 	}
@@ -819,6 +866,7 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 		s.own_fetches_width += t.own_fetches_width; s.own_fetches_search += t.own_fetches_search;
 		s.n_pops += t.n_pops; s.n_pushes += t.n_pushes; s.n_stored += t.n_stored; s.n_pruned += t.n_pruned; s.n_expand += t.n_expand; s.n_exact += t.n_exact; s.n_derive += t.n_derive; s.ms_sw_kernel = std::max(s.ms_sw_kernel, t.ms_sw_kernel); s.n_trips += t.n_trips; s.ns_queue_empty = std::max(s.ns_queue_empty, t.ns_queue_empty); s.ns_kernel = std::max(s.ns_kernel, t.ns_kernel); s.launches += t.launches;
 		for (int q = 0; q < 4; ++q) s.ms_tier[q] = std::max(s.ms_tier[q], t.ms_tier[q]);
+		s.x_chunks_used = std::max(s.x_chunks_used, t.x_chunks_used);
 	}
 	s.n_devices = 0;
 	for (Ctx *c : g_ctx) if (!c->owner) ++s.n_devices;

@@ -12,6 +12,8 @@ namespace bwagpu {
 #define NIL 0xffffffffu
 #define WB_EQ 0x8000u
 #define WB_BID 0x7fffu
+#define ARENA_CHUNK_LOG 10
+#define ARENA_CHUNK (1u << ARENA_CHUNK_LOG)
 
 // ------------------------------------------------------------------ K0: re-layout
 // raw = the reference's bwt_t::bwt (12-word blocks, bwtmisc.c:125-152) on the device.
@@ -91,8 +93,18 @@ struct Batch {
 	uint4 *ent;
 	uint32_t *nxt;
 	uint32_t *heads; // global bucket heads (only when BWAGPU_SMEM_HEADS == 0)
-	uint4 *alnbuf;
-	uint32_t cap, aln_cap, n_stacks;
+	uint32_t cap, n_stacks;
+	// arena overflow: chunks of ARENA_CHUNK records from a pool shared by all threads of the launch.  A
+	// thread takes chunks as its search deepens and hands all but one back when the read is finished
+	// (lock-free stack with a version tag), so the pool only has to cover the reads in flight
+	uint4 *xent;
+	uint32_t *xnxt;
+	uint32_t *ctab;            // per thread: ids of the chunks it owns
+	uint32_t ctab_stride;      // max chunks per thread
+	uint32_t x_chunks;         // chunks in the pool
+	unsigned int *x_next;      // bump counter (chunks never handed out yet)
+	unsigned long long *x_free_top; // recycled chunks: lock-free stack, {tag:32 | head:32} against ABA
+	uint32_t *x_free_next;     // link of the recycled-chunk stack
 	// stats (STATS builds only)
 	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes [4] records stored [5] pruned pops [6] expansions [7] exact-tail steps [8] derive trips
 };
@@ -250,13 +262,27 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	uint32_t *const heads = B.heads + (size_t)slot * B.n_stacks;
 	const uint32_t HS = 1;
 #endif
-	uint4 *const alnbuf = B.alnbuf + (size_t)slot * B.aln_cap;
 	const GapOpt &O = B.opt;
 	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
 	// The reversed genome has the forward genome's base composition, so C() (bwt_t::L2) and
 	// seq_len are the same for both indexes; only the block array and `primary` differ.
 	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
 	auto Cof = [&](uint32_t c) -> uint32_t { return c == 0 ? 0u : c == 1 ? C1 : c == 2 ? C2 : C3; };
+
+	// record idx -> address: the private arena first, then this thread's pool chunks
+	const uint32_t CAP0 = B.cap;
+	uint32_t *const ctab = B.ctab + (size_t)slot * B.ctab_stride;
+	uint32_t n_chunks = 0; // pool chunks owned by this thread right now
+	auto ent_at = [&](uint32_t idx) -> uint4 * {
+		if (idx < CAP0) return ent + idx;
+		const uint32_t o = idx - CAP0;
+		return B.xent + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
+	};
+	auto nxt_at = [&](uint32_t idx) -> uint32_t * {
+		if (idx < CAP0) return nxt + idx;
+		const uint32_t o = idx - CAP0;
+		return B.xnxt + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
+	};
 
 	int mode = MODE_NEW;
 	// per-read state
@@ -273,6 +299,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	int cur_s = -1;
 	uint32_t cur_head = NIL;
 	uint32_t bump = 0, free_head = NIL, spare = NIL;
+	uint32_t hit_head = NIL, hit_tail = NIL; // the read's hits: a list through the same arena, in discovery order
 	Entry held = {0, 0, 0, 0}; bool held_valid = false;
 	Entry e = {0, 0, 0, 0}; // node being processed (always a plain node)
 	uint32_t derive_c = 0;  // MODE_DERIVE: which child interval of e.{k,l} to take
@@ -309,26 +336,64 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		return 192 + __ffsll((long long)mask3) - 1;
 	};
 
+	auto chunk_alloc = [&]() -> uint32_t {
+		unsigned long long old = *(volatile unsigned long long *)B.x_free_top;
+		while ((uint32_t)old != NIL) { // pop a recycled chunk
+			const uint32_t head = (uint32_t)old;
+			const uint32_t nx = ((volatile uint32_t *)B.x_free_next)[head];
+			const unsigned long long nw = (((old >> 32) + 1ull) << 32) | nx;
+			const unsigned long long prev = atomicCAS(B.x_free_top, old, nw);
+			if (prev == old) return head;
+			old = prev;
+		}
+		const uint32_t c = atomicAdd(B.x_next, 1u);
+		return c < B.x_chunks ? c : NIL;
+	};
+	auto chunk_free = [&](uint32_t c) {
+		unsigned long long old = *(volatile unsigned long long *)B.x_free_top;
+		for (;;) {
+			((volatile uint32_t *)B.x_free_next)[c] = (uint32_t)old;
+			__threadfence();
+			const unsigned long long nw = (((old >> 32) + 1ull) << 32) | c;
+			const unsigned long long prev = atomicCAS(B.x_free_top, old, nw);
+			if (prev == old) return;
+			old = prev;
+		}
+	};
+
+	// one arena record: the slot freed by the latest pop, else the free list, else fresh space
+	// (private arena, then chunks of the shared pool).  NIL + overflow when the pool has run dry.
+	auto alloc_rec = [&]() -> uint32_t {
+		uint32_t idx;
+		if (spare != NIL) { idx = spare; spare = NIL; }
+		else if (free_head != NIL) { idx = free_head; free_head = *nxt_at(idx); }
+		else {
+			if (bump == CAP0 + (n_chunks << ARENA_CHUNK_LOG)) { // arena full: take one more chunk from the pool
+				const uint32_t c = n_chunks < B.ctab_stride ? chunk_alloc() : NIL;
+				if (c == NIL) { overflow = true; return NIL; } // pool dry: retried in the guaranteed pass
+				ctab[n_chunks++] = c;
+			}
+			idx = bump++;
+		}
+		return idx;
+	};
+
 	// gap_push (bwtgap.c:45-64): one record holding n_children nodes of score s
 	auto push_rec = [&](uint32_t rk, uint32_t rl, uint32_t pos, uint32_t tag, int s, int n_children) {
 		n_entries += n_children;
 		if (STATS) n_pushes += n_children;
 		if (have_best && !nonstop && s > best_score + O.s_mm) return; // phantoms: counted, never stored
 		if (STATS) ++n_stored;
-		uint32_t idx;
-		if (spare != NIL) { idx = spare; spare = NIL; }
-		else if (free_head != NIL) { idx = free_head; free_head = nxt[idx]; }
-		else if (bump < B.cap) idx = bump++;
-		else { overflow = true; return; }
-		ent[idx] = make_uint4(rk, rl, pos, tag);
-		if (s == cur_s) { nxt[idx] = cur_head; cur_head = idx; }
-		else { nxt[idx] = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = idx; }
+		const uint32_t idx = alloc_rec();
+		if (idx == NIL) return;
+		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
+		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
+		else { *nxt_at(idx) = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = idx; }
 		mask_set(s);
 	};
 
 	// copies the finished read's results out and resets the per-slot stack
 	auto finish_read = [&]() {
-		if (overflow || (uint32_t)n_aln > B.aln_cap) overflow = true;
 		uint32_t off = 0;
 		if (!overflow && n_aln > 0) {
 			off = atomicAdd(B.pool_count, (unsigned int)n_aln);
@@ -339,13 +404,16 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			const int o = atomicAdd(B.overflow_count, 1);
 			B.overflow_ids[o] = rid;
 		} else {
-			for (int j = 0; j < n_aln; ++j) B.pool[off + j] = alnbuf[j];
+			uint32_t h = hit_head;
+			for (int j = 0; j < n_aln; ++j) { B.pool[off + j] = *ent_at(h); h = *nxt_at(h); }
 			B.n_aln[rid] = n_aln;
 			B.pool_off[rid] = off;
 			B.max_entries[rid] = max_entries;
 		}
 		mask0 = mask1 = mask2 = mask3 = 0; cur_s = -1; cur_head = NIL;
 		bump = 0; free_head = NIL; spare = NIL; held_valid = false; n_entries = 0;
+		hit_head = hit_tail = NIL;
+		while (n_chunks > 1) chunk_free(ctab[--n_chunks]); // keep one chunk, recycle the rest
 	};
 
 	// action for found hits (bwtgap.c:167-200).  Returns false when the search must stop.
@@ -363,8 +431,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		if (score == best_score) best_cnt += (int)(hl - hk + 1);
 		else if (best_cnt > O.max_top2) return false; // top2b behaviour
 		if (go) { // the hit may have been found already (gap in a tandem repeat)
-			for (int j = 0; j < n_aln && j < (int)B.aln_cap; ++j) {
-				const uint4 q = alnbuf[j];
+			for (uint32_t h = hit_head; h != NIL; h = *nxt_at(h)) {
+				const uint4 q = *ent_at(h);
 				if (q.y == hk && q.z == hl) { do_add = false; break; }
 			}
 		}
@@ -386,10 +454,14 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				wb[t] = (uint16_t)(bid | ((t > 0 && wv == prev) ? WB_EQ : 0u));
 				prev = wv;
 			}
-			if ((uint32_t)n_aln < B.aln_cap)
-				alnbuf[n_aln] = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl,
-				                           (uint32_t)score);
-			++n_aln; // beyond aln_cap: counted, flagged as overflow at finish
+			const uint32_t idx = alloc_rec();
+			if (idx != NIL) {
+				*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score);
+				*nxt_at(idx) = NIL;
+				if (hit_tail != NIL) *nxt_at(hit_tail) = idx; else hit_head = idx;
+				hit_tail = idx;
+				++n_aln;
+			}
 		}
 		return true;
 	};
@@ -480,8 +552,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						cur_s = s; cur_head = heads[s * HS];
 					}
 					const uint32_t idx = cur_head;
-					const uint4 q = ent[idx];
-					const uint32_t nx = nxt[idx]; // issued with the entry load, used only when the record is unlinked
+					uint4 *const qp = ent_at(idx);
+					const uint4 q = *qp;
+					const uint32_t nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
 					const uint32_t kind = (q.w >> 27) & 3u;
 					uint32_t gm = 0, b = 0;
 					if (kind != KIND_PLAIN) {
@@ -489,11 +562,11 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
 						gm &= ~(1u << b);
 					}
-					if (gm) ent[idx].z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
+					if (gm) qp->z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
 					else { // unlink
 						cur_head = nx;
 						if (cur_head == NIL) mask_clear(s);
-						if (spare != NIL) { nxt[spare] = free_head; free_head = spare; }
+						if (spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
 						spare = idx;
 					}
 					e.k = q.x; e.l = q.y;
@@ -535,8 +608,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 #if !defined(BWAGPU_HOST_EMU) && BWAGPU_PREFETCH_TOP
 			// the record a memory pop would take next: warm it while this trip's loads are in flight
 			if (cur_head != NIL && cur_s >= 0) {
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(ent + cur_head));
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + cur_head));
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(ent_at(cur_head)));
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt_at(cur_head)));
 			}
 #endif
 			if (fresh) {

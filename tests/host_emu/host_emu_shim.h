@@ -32,3 +32,5 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 template <typename T, typename U> static inline T atomicAdd(T *p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
 template <typename T, typename U> static inline T atomicMin(T *p, U v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
 template <typename T, typename U> static inline T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <typename T> static inline T atomicCAS(T *p, T cmp, T val) { T o = *p; if (o == cmp) *p = val; return o; }
+static inline void __threadfence() {}

@@ -68,7 +68,7 @@ extern "C" void emu_free_index(void *h) { delete (EmuIndex *)h; }
 // ref fetches, own fetches, pops, pushes.
 extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt,
                             int32_t *n_aln, int32_t *max_entries, int64_t *aln_off, uint4 **pool_out,
-                            uint32_t cap1, uint32_t aln_cap1, int n_slots, unsigned long long *stats8)
+                            uint32_t cap1, uint32_t aln_cap1, int n_slots, unsigned long long *stats8, uint32_t pool_chunks)
 {
 	EmuIndex *E = (EmuIndex *)h;
 	MaxDiffTable mdt;
@@ -110,16 +110,27 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	if (stats8) { stats8[0] = stats[0]; stats8[1] = stats[1]; }
 	stats[0] = stats[1] = 0;
 	// K3 tiers
-	const uint32_t caps[3] = {cap1, 8192u, (uint32_t)opt->max_entries + 16u};
-	const uint32_t acaps[3] = {aln_cap1, 512u, 1u << 18};
+	// pass 0: private arena cap1 + a small shared pool (pool_chunks chunks); pass 1: guaranteed
+	const uint32_t need = (uint32_t)opt->max_entries + 16u;
+	const uint32_t caps[2] = {cap1, 1024u};
+	(void)aln_cap1; // hits live in the arena now: no separate list capacity
+	const uint32_t pool_chunks_of[2] = {pool_chunks, (need >> ARENA_CHUNK_LOG) + 2};
 	int n_jobs = n;
 	const int32_t *jobs = nullptr;
-	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
+	for (int t = 0; t < 2 && n_jobs > 0; ++t) {
 		const int slots = t == 0 ? n_slots : 1;
-		std::vector<uint4> ent((size_t)slots * caps[t]), alnbuf((size_t)slots * acaps[t]);
+		std::vector<uint4> ent((size_t)slots * caps[t]);
 		std::vector<uint32_t> nxt((size_t)slots * caps[t]);
-		B.ent = ent.data(); B.nxt = nxt.data(); B.alnbuf = alnbuf.data(); B.heads = nullptr;
-		B.cap = caps[t]; B.aln_cap = acaps[t];
+		B.ent = ent.data(); B.nxt = nxt.data(); B.heads = nullptr;
+		B.cap = caps[t];
+		const uint32_t stride = ((need > caps[t] ? need - caps[t] : 0) >> ARENA_CHUNK_LOG) + 2;
+		std::vector<uint4> xent((size_t)pool_chunks_of[t] << ARENA_CHUNK_LOG);
+		std::vector<uint32_t> xnxt((size_t)pool_chunks_of[t] << ARENA_CHUNK_LOG), ctab((size_t)slots * stride);
+		unsigned int x_next = 0;
+		B.xent = xent.data(); B.xnxt = xnxt.data(); B.ctab = ctab.data(); B.ctab_stride = stride;
+		unsigned long long x_free_top = 0xffffffffull;
+		std::vector<uint32_t> x_free_next(pool_chunks_of[t] + 1);
+		B.x_chunks = pool_chunks_of[t]; B.x_next = &x_next; B.x_free_top = &x_free_top; B.x_free_next = x_free_next.data();
 		B.jobs = jobs; B.n_jobs = n_jobs;
 		int32_t *ovf = (t & 1) ? jobs_b.data() : jobs_a.data();
 		B.overflow_ids = ovf;
@@ -127,7 +138,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		if (t > 0) for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
 		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; k_search<true>(B); }
 		if (stats8) stats8[4 + t] = (unsigned long long)counters[1];
-		if (counters[1] > 0 && t == 2) { g_err = "reads exceeded the largest tier"; return 1; }
+		if (counters[1] > 0 && t == 1) { g_err = "reads exceeded the largest tier"; return 1; }
 		jobs = ovf; n_jobs = counters[1];
 	}
 	if (stats8) { stats8[2] = stats[0]; stats8[3] = stats[1]; stats8[7] = stats[2]; stats8[6] = stats[4]; }

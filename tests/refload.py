@@ -110,14 +110,14 @@ def emu():
         E.emu_free_index.argtypes = [C.c_void_p]
         E.emu_aln_flat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t), C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_int,
-                                   C.c_void_p]
+                                   C.c_void_p, C.c_uint32]
         E.emu_free.argtypes = [C.c_void_p]
         E.emu_sa.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
         _emu = E
     return _emu
 
 
-def emu_aln(h, reads, opt, cap1=1024, aln_cap1=64, n_slots=3):
+def emu_aln(h, reads, opt, cap1=1024, aln_cap1=64, n_slots=3, pool_chunks=64):
     E = emu()
     n = reads.n
     bases = np.ascontiguousarray(reads.bases, dtype=np.uint8)
@@ -129,7 +129,7 @@ def emu_aln(h, reads, opt, cap1=1024, aln_cap1=64, n_slots=3):
     stats = np.zeros(8, dtype=np.uint64)
     rc = E.emu_aln_flat(h, n, bases.ctypes.data, offs.ctypes.data, C.byref(opt), n_aln.ctypes.data,
                         max_entries.ctypes.data, aln_off.ctypes.data, C.byref(pool), cap1, aln_cap1, n_slots,
-                        stats.ctypes.data)
+                        stats.ctypes.data, pool_chunks)
     if rc:
         raise RuntimeError(E.emu_last_error().decode())
     tot = int(aln_off[n])

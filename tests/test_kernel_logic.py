@@ -46,21 +46,31 @@ def test_search_logic_matches_golden(golden, emu_index, name):
     assert R.compare_aln(want, got, name) == []
 
 
-def test_search_logic_tiny_tiers(golden, emu_index):
-    """Force most reads through the overflow tiers (tiny tier-1 arena and hit list)."""
+def test_search_logic_pool_chunks(golden, emu_index):
+    """Tiny private arenas: almost every search spills into chunks of the shared pool."""
+    h, _ = emu_index
+    for name in ("se76", "adna"):
+        reads, opt, want = golden_case(golden, name)
+        got = R.emu_aln(h, reads, opt, cap1=8, aln_cap1=64, n_slots=2, pool_chunks=4096)
+        assert got[4][4] == 0  # nothing needed the guaranteed pass
+        assert R.compare_aln(want, got, name) == []
+
+
+def test_search_logic_guaranteed_pass(golden, emu_index):
+    """A pool that runs dry pushes reads into the guaranteed pass."""
     h, _ = emu_index
     reads, opt, want = golden_case(golden, "se76")
-    got = R.emu_aln(h, reads, opt, cap1=64, aln_cap1=1, n_slots=2)
-    assert got[4][4] > 100  # reads that overflowed tier 1
-    assert R.compare_aln(want, got, "tiers") == []
+    got = R.emu_aln(h, reads, opt, cap1=32, aln_cap1=1, n_slots=2, pool_chunks=0)
+    assert got[4][4] > 10  # reads retried in pass 1
+    assert R.compare_aln(want, got, "guaranteed") == []
 
 
 def test_search_logic_retry_after_hits(golden, emu_index):
-    """A read that overflows AFTER its first hit has had its widths edited by gap_shadow;
-    the retry in the next tier must start from pristine widths."""
+    """A read that fails AFTER its first hit has had its widths edited by gap_shadow;
+    the retry must start from pristine widths."""
     h, _ = emu_index
     reads, opt, want = golden_case(golden, "adna")
-    got = R.emu_aln(h, reads, opt, cap1=300, aln_cap1=64, n_slots=2)
+    got = R.emu_aln(h, reads, opt, cap1=100, aln_cap1=64, n_slots=2, pool_chunks=0)
     assert got[4][4] > 20
     assert R.compare_aln(want, got, "retry") == []
 

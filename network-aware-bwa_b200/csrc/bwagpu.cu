@@ -142,7 +142,7 @@ struct Ctx {
 	DevBuf<int> d_counters;            // [0] work [1] overflow [2] pool_count(u32)
 	DevBuf<unsigned long long> d_stats; // 4
 	DevBuf<uint8_t> d_cubtmp;
-	Tier tier[2];
+	Tier tier[3];
 	DevBuf<uint4> xent;           // shared overflow pool of this lane (records)
 	DevBuf<uint32_t> xnxt, ctab, x_free_next;
 	DevBuf<unsigned long long> x_free_top;
@@ -356,9 +356,9 @@ extern "C" int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac)
 extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
 
 // ------------------------------------------------------------------ device pipeline for one resident chunk
-static const int N_TIERS = 2;
+static const int N_TIERS = 3;
 
-// Pass 0 (optimistic): every resident thread has a small private arena (BWAGPU_T1_CAP records, shared by
+// Pass 0: private arenas only (BWAGPU_T1_CAP records per thread).  Pass 1 (optimistic, pooled): every resident thread has a small private arena (BWAGPU_T1_CAP records, shared by
 // the search stack and the read's hit list) and takes more from a shared pool of 1024-record chunks when a search goes deep; the pool is
 // bump-allocated within a launch, so it can run dry -- the reads it fails are retried from scratch in pass 1 (guaranteed): few enough threads
 // that each can own opt->max_entries + 16 records, which the search can never exceed (bwtgap.c:140
@@ -379,13 +379,22 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 		c->x_chunks = (uint32_t)chunks;
 	}
 	const uint32_t need = max_entries_opt + 16; // records one search can hold at most
-	if (t == 0) {
-		int bps = 0;
+	if (t <= 1) {
+		// pass 0: private arenas only (k_search<.., false>); pass 1: same occupancy, arenas continue in the pool
+		int bps = 0, bps_p = 0;
 		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0; // bucket heads
-		CK(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		if (g_stats_enabled) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true>, 128, smem));
-		else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false>, 128, smem));
+		CK(cudaFuncSetAttribute(k_search<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(k_search<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(k_search<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(k_search<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		if (g_stats_enabled) {
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true, false>, 128, smem));
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_p, k_search<true, true>, 128, smem));
+		} else {
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false, false>, 128, smem));
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_p, k_search<false, true>, 128, smem));
+		}
+		if (t == 1) bps = bps_p;
 		if (bps < 1) bps = 1;
 		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_T1_BLOCKS_PER_SM", 64));
 		T.slots_blocks = (uint32_t)(bps * c->n_sm);
@@ -394,10 +403,9 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 		// guaranteed: threads x (chunks one search may need) <= pool
 		const uint32_t per_thread = (need + ARENA_CHUNK - 1) >> ARENA_CHUNK_LOG;
 		uint32_t threads = c->x_chunks / std::max(1u, per_thread);
-		if (threads < 1) return fail("overflow pool (%u chunks) is smaller than one search (%u chunks); raise BWAGPU_POOL_MB", c->x_chunks, per_thread);
 		if (threads > 4096) threads = 4096;
+		if (threads < 128) return fail("overflow pool (%u chunks) too small for the guaranteed pass (%u chunks per search); raise BWAGPU_POOL_MB or lower -m", c->x_chunks, per_thread);
 		T.slots_blocks = std::max(1u, threads / 128);
-		if (threads < 128) return fail("overflow pool too small for the guaranteed pass (%u threads); raise BWAGPU_POOL_MB or lower -m", threads);
 		T.cap = 1024;
 	}
 	if (T.cap > need) T.cap = need;
@@ -527,8 +535,13 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
 		if (blocks > need) blocks = need;
 		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0;
-		if (stats) k_search<true><<<blocks, 128, smem, c->st>>>(B);
-		else k_search<false><<<blocks, 128, smem, c->st>>>(B);
+		if (t == 0) {
+			if (stats) k_search<true, false><<<blocks, 128, smem, c->st>>>(B);
+			else k_search<false, false><<<blocks, 128, smem, c->st>>>(B);
+		} else {
+			if (stats) k_search<true, true><<<blocks, 128, smem, c->st>>>(B);
+			else k_search<false, true><<<blocks, 128, smem, c->st>>>(B);
+		}
 		CK(cudaGetLastError());
 		c->stats.launches++;
 		CK(cudaEventRecord(c->ev[9 + 2 * t], c->st));
@@ -561,7 +574,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			B.pool = bigger; B.pool_cap = (uint32_t)pool_cap;
 		}
 		if (pass == 0) c->stats.n_overflow_t2 += n_over;
-		else c->stats.n_overflow_t3 += n_over;
+		else if (pass == 1) c->stats.n_overflow_t3 += n_over;
 		jobs = ovf;
 		n_jobs = n_over;
 	}

@@ -242,7 +242,10 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
 #endif
 
-template <bool STATS>
+// POOLED = false: the private arena only (no chunk indirection anywhere in the loop) -- pass 0, where
+// nearly every read of an ordinary workload finishes.  POOLED = true: the arena continues in chunks of
+// the shared pool -- the passes that pick up the reads whose search went deeper.
+template <bool STATS, bool POOLED>
 __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,12 +277,12 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	uint32_t *const ctab = B.ctab + (size_t)slot * B.ctab_stride;
 	uint32_t n_chunks = 0; // pool chunks owned by this thread right now
 	auto ent_at = [&](uint32_t idx) -> uint4 * {
-		if (idx < CAP0) return ent + idx;
+		if (!POOLED || idx < CAP0) return ent + idx;
 		const uint32_t o = idx - CAP0;
 		return B.xent + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
 	};
 	auto nxt_at = [&](uint32_t idx) -> uint32_t * {
-		if (idx < CAP0) return nxt + idx;
+		if (!POOLED || idx < CAP0) return nxt + idx;
 		const uint32_t o = idx - CAP0;
 		return B.xnxt + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
 	};
@@ -368,7 +371,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		if (spare != NIL) { idx = spare; spare = NIL; }
 		else if (free_head != NIL) { idx = free_head; free_head = *nxt_at(idx); }
 		else {
-			if (bump == CAP0 + (n_chunks << ARENA_CHUNK_LOG)) { // arena full: take one more chunk from the pool
+			if (!POOLED) {
+				if (bump == CAP0) { overflow = true; return NIL; } // deeper than the private arena: next pass
+			} else if (bump == CAP0 + (n_chunks << ARENA_CHUNK_LOG)) { // arena full: take one more chunk from the pool
 				const uint32_t c = n_chunks < B.ctab_stride ? chunk_alloc() : NIL;
 				if (c == NIL) { overflow = true; return NIL; } // pool dry: retried in the guaranteed pass
 				ctab[n_chunks++] = c;
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		mask0 = mask1 = mask2 = mask3 = 0; cur_s = -1; cur_head = NIL;
 		bump = 0; free_head = NIL; spare = NIL; held_valid = false; n_entries = 0;
 		hit_head = hit_tail = NIL;
-		while (n_chunks > 1) chunk_free(ctab[--n_chunks]); // keep one chunk, recycle the rest
+		if (POOLED) while (n_chunks > 1) chunk_free(ctab[--n_chunks]); // keep one chunk, recycle the rest
 	};
 
 	// action for found hits (bwtgap.c:167-200).  Returns false when the search must stop.

@@ -136,7 +136,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		B.overflow_ids = ovf;
 		counters[0] = counters[1] = 0;
 		if (t > 0) for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
-		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; k_search<true>(B); }
+		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; k_search<true, true>(B); }
 		if (stats8) stats8[4 + t] = (unsigned long long)counters[1];
 		if (counters[1] > 0 && t == 1) { g_err = "reads exceeded the largest tier"; return 1; }
 		jobs = ovf; n_jobs = counters[1];

@@ -191,6 +191,34 @@ typedef struct {
 
 int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_res_t *res);
 
+/* ------------------------------------------------------------------ K6: banded global alignment + CIGAR
+ * One result per job: the score, the path's first and last cell (1-based, window / read coordinates;
+ * p = path + path_len - 1 and path[0] in the reference's terms) and the raw CIGAR of the path as
+ * bwa_aln_path2cigar gives it (bwtaln.c:396-406: op << 14 | len, ops FROM_M 0 / FROM_I 1 / FROM_D 2),
+ * at cigar_pool[cigar_off .. cigar_off + n_cigar).  *cigar_pool is library-owned, valid until the next
+ * call of either function. */
+typedef struct {
+	int32_t score;
+	int32_t n_cigar;
+	int32_t start_i, start_j, end_i, end_j;
+	int64_t cigar_off;
+} bwa_gpu_path_res_t;
+
+/* Batch form of the whole aln_local_core(ref, l, seq, len, &aln_param_bwa, path, &path_len, 1, 0) call of
+ * bwa_sw_core (bwape.c:456): K5 (passes 1-2) followed by the third pass, aln_global_core on the box with
+ * band 50 doubled until the global score equals the local one (stdaln.c:723-745).  score is what
+ * aln_local_core returns (-1 for its "Potential bug" branch, or for empty input); n_cigar = 0 when the
+ * local score is below 1 (bwa_sw_core's thres).  The host keeps bwa_sw_core's post-processing: the
+ * >= 20 matched bases test, soft clips, cnt, and the accept/reject arithmetic of bwa_paired_sw1. */
+int bwa_gpu_mate_sw_path(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_path_res_t *res, const bwa_cigar_t **cigar_pool);
+
+/* Batch form of the aln_global_core(ref_seq, l, seq, len, &ap, path, &path_len) call of refine_gapped_core
+ * (bwase.c:212; ap = aln_param_bwa: gap_end 5, band 50) -- and of any other use with aln_param_bwa's
+ * scores: jobs[i].reglen reference bases from jobs[i].beg against the read.  gap_end < 0 = end gaps cost
+ * like inner gaps.  The host keeps refine_gapped_core's coordinate fix-ups (bwase.c:215-234). */
+int bwa_gpu_global_align(int n, const bwa_gpu_sw_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
+                         const bwa_cigar_t **cigar_pool);
+
 /* ------------------------------------------------------------------ measurement hooks
  * Device-side timing (CUDA events on the library's own streams) and work counters of the
  * most recent batch call, summed over its chunks.  occ_fetches counts occurrence-block

@@ -121,6 +121,11 @@ class sw_res_t(C.Structure):
                 ("end_i", C.c_int32), ("end_j", C.c_int32)]
 
 
+class path_res_t(C.Structure):
+    _fields_ = [("score", C.c_int32), ("n_cigar", C.c_int32), ("start_i", C.c_int32), ("start_j", C.c_int32),
+                ("end_i", C.c_int32), ("end_j", C.c_int32), ("cigar_off", C.c_int64)]
+
+
 class stats_t(C.Structure):
     _fields_ = [
         ("ms_h2d", C.c_double), ("ms_width", C.c_double), ("ms_search", C.c_double), ("ms_compact", C.c_double),

@@ -41,6 +41,9 @@ def lib() -> C.CDLL:
                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.bwa_gpu_cal_pac_pos.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bwa_gpu_mate_sw.argtypes = [C.c_int, C.POINTER(abi.sw_job_t), C.POINTER(abi.sw_res_t)]
+        L.bwa_gpu_mate_sw_path.argtypes = [C.c_int, C.POINTER(abi.sw_job_t), C.POINTER(abi.path_res_t), C.POINTER(C.c_void_p)]
+        L.bwa_gpu_global_align.argtypes = [C.c_int, C.POINTER(abi.sw_job_t), C.c_int, C.c_int, C.POINTER(abi.path_res_t),
+                                           C.POINTER(C.c_void_p)]
         L.bwa_gpu_get_stats.argtypes = [C.POINTER(abi.stats_t)]
         L.bwa_gpu_set_stats.argtypes = [C.c_int]
         L.bwa_gpu_resident_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t)]
@@ -52,7 +55,7 @@ def lib() -> C.CDLL:
 
 EXPORTS = [
     "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_load_pac", "bwa_gpu_destroy", "bwa_gpu_last_error",
-    "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw",
+    "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw", "bwa_gpu_mate_sw_path", "bwa_gpu_global_align",
     "bwa_gpu_get_stats", "bwa_gpu_set_stats",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
 ]
@@ -130,6 +133,49 @@ def mate_sw(jobs):
     res = (abi.sw_res_t * n)()
     _ck(lib().bwa_gpu_mate_sw(n, arr, res))
     return [(r.score, r.start_i, r.start_j, r.end_i, r.end_j) for r in res]
+
+
+def _sw_jobs(jobs):
+    n = len(jobs)
+    arr = (abi.sw_job_t * n)()
+    keep = []
+    for i, (beg, reglen, seq) in enumerate(jobs):
+        s = np.ascontiguousarray(seq, dtype=np.uint8)
+        keep.append(s)
+        arr[i].beg, arr[i].reglen, arr[i].len = beg, reglen, s.size
+        arr[i].seq = s.ctypes.data_as(C.POINTER(C.c_ubyte))
+    return arr, keep
+
+
+def _path_results(res, pool, n):
+    out = []
+    for i in range(n):
+        r = res[i]
+        cig = np.empty(0, dtype=np.uint16)
+        if r.n_cigar:
+            buf = (C.c_uint16 * r.n_cigar).from_address(pool.value + 2 * r.cigar_off)
+            cig = np.frombuffer(buf, dtype=np.uint16).copy()
+        out.append((r.score, r.start_i, r.start_j, r.end_i, r.end_j, cig))
+    return out
+
+
+def mate_sw_path(jobs):
+    """jobs as for mate_sw -> list of (score, start_i, start_j, end_i, end_j, cigar uint16[])"""
+    n = len(jobs)
+    arr, keep = _sw_jobs(jobs)
+    res = (abi.path_res_t * n)()
+    pool = C.c_void_p()
+    _ck(lib().bwa_gpu_mate_sw_path(n, arr, res, C.byref(pool)))
+    return _path_results(res, pool, n)
+
+
+def global_align(jobs, gap_end: int = 5, band: int = 50):
+    n = len(jobs)
+    arr, keep = _sw_jobs(jobs)
+    res = (abi.path_res_t * n)()
+    pool = C.c_void_p()
+    _ck(lib().bwa_gpu_global_align(n, arr, gap_end, band, res, C.byref(pool)))
+    return _path_results(res, pool, n)
 
 
 def set_stats(enabled: bool) -> None:

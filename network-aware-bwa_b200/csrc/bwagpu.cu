@@ -1006,16 +1006,39 @@ extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint
 }
 
 // ------------------------------------------------------------------ K5
-extern "C" int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_res_t *res)
+static std::vector<uint16_t> g_cigar_pool; // result pool of the last K6 call
+
+static int sw_entry(int n, const bwa_gpu_sw_job_t *jobs, int mode, int gap_end, int band, bwa_gpu_sw_res_t *res,
+                    bwa_gpu_path_res_t *pres, const bwa_cigar_t **cigar_pool, const char *who)
 {
 	std::lock_guard<std::mutex> g(g_mu);
-	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
-	if (n < 0 || (n && (!jobs || !res))) return fail("bwa_gpu_mate_sw: bad argument");
+	if (g_ctx.empty()) return fail("%s: bwa_gpu_init has not been called (no CPU fallback)", who);
+	if (n < 0 || (n && (!jobs || (mode == 0 && !res) || (mode != 0 && (!pres || !cigar_pool))))) return fail("%s: bad argument", who);
 	Ctx *c = g_ctx[0];
 	CK(cudaSetDevice(c->dev));
-	if (!c->has_pac) return fail("no packed reference loaded (pac was NULL in bwa_gpu_load_index)");
+	if (!c->has_pac) return fail("%s: no packed reference loaded (pac was NULL in bwa_gpu_load_index)", who);
 	double ms = 0;
-	const int rc = sw_batch(c->st, c->pac.p, c->l_pac, n, jobs, res, fail, &ms);
+	std::vector<bwa_gpu_sw_res_t> tmp;
+	if (mode == 1 && !res) { tmp.resize(n); res = tmp.data(); }
+	const int rc = sw_batch(c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &g_cigar_pool : nullptr, fail, &ms);
 	c->stats.ms_sw_kernel = ms;
+	if (mode && cigar_pool) *cigar_pool = g_cigar_pool.data();
 	return rc;
+}
+
+extern "C" int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_res_t *res)
+{
+	return sw_entry(n, jobs, 0, 0, 0, res, nullptr, nullptr, "bwa_gpu_mate_sw");
+}
+
+extern "C" int bwa_gpu_mate_sw_path(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_path_res_t *res, const bwa_cigar_t **cigar_pool)
+{
+	return sw_entry(n, jobs, 1, -1, 50, nullptr, res, cigar_pool, "bwa_gpu_mate_sw_path");
+}
+
+extern "C" int bwa_gpu_global_align(int n, const bwa_gpu_sw_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
+                                    const bwa_cigar_t **cigar_pool)
+{
+	if (band < 1) return fail("bwa_gpu_global_align: band must be >= 1");
+	return sw_entry(n, jobs, 2, gap_end, band, nullptr, res, cigar_pool, "bwa_gpu_global_align");
 }

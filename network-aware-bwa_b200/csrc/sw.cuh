@@ -54,7 +54,7 @@ __device__ __forceinline__ int pac_base(const uint8_t *pac, long long k) { retur
 // rev_h/rev_e (len1_max+2 ints each)
 __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, const SwJob *__restrict__ jobs, int n_jobs,
                                             const uint8_t *__restrict__ reads, bwa_gpu_sw_res_t *__restrict__ res,
-                                            int len1_max, int len2_max, int *work_counter)
+                                            int len1_max, int len2_max, int *work_counter, int *__restrict__ score_r_out)
 {
 	extern __shared__ int smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 		const SwJob J = jobs[job];
 		const int len1 = J.len1, len2 = J.len2;
 		if (len1 <= 0 || len2 <= 0) { // stdaln.c:559
-			if (lane == 0) { bwa_gpu_sw_res_t r = {-1, 0, 0, 0, 0}; res[job] = r; }
+			if (lane == 0) { bwa_gpu_sw_res_t r = {-1, 0, 0, 0, 0}; res[job] = r; if (score_r_out) score_r_out[job] = 0; }
 			continue;
 		}
 		for (int t = lane; t < len2; t += 32) q[t] = reads[J.q_off + t];
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 			if (take) { best = ob; best_i = oi; best_j = oj; }
 		}
 		const int score_f = best, end_i = best_i, end_j = best_j;
-		int start_i = 0, start_j = 0, flag = 0;
+		int start_i = 0, start_j = 0, flag = 0, score_r_final = 0;
 		if (score_f > 32000) flag = 1; // the reference would have rescaled (stdaln.c:587-606); not restated
 
 		// ---------------- pass 2: reverse band from the end cell (stdaln.c:638-696), one row at a time
@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 			for (int i = lane; i <= end_i + 1; i += 32) { rh[i] = 0; re[i] = 0; }
 			__syncwarp();
 			int score_r = sw_sc(refb[end_i - 1], q[end_j - 1]);
+			score_r_final = score_r - SW_QR; // kept up to date below: what aln_local_core compares with score_f (stdaln.c:714-715)
 			start_i = end_i; start_j = end_j;
 			if (lane == 0) rh[end_i] = SW_QR + score_r;
 			__syncwarp();
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 					if (hit) {
 						const int ln = __ffs((int)hit) - 1;
 						score_r = target; start_i = start - (tb + ln); start_j = j;
+						score_r_final = score_r - SW_QR;
 						stop = true;
 					} else {
 						const int cmax = __shfl_sync(full, im, 31);
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 				}
 				if (stop) break;
 				score_r = run;
+				score_r_final = score_r - SW_QR;
 				__syncwarp();
 				if (lane == 0) { rh[start + 1] = 0; re[end + 1] = 0; }
 				__syncwarp();
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 		}
 		if (lane == 0) {
 			bwa_gpu_sw_res_t r;
+			if (score_r_out) score_r_out[job] = score_r_final;
 			r.score = flag ? -2 - flag : score_f;
 			r.start_i = start_i; r.start_j = start_j; r.end_i = end_i; r.end_j = end_j;
 			res[job] = r;
@@ -247,69 +251,305 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 	}
 }
 
-// host launcher: stages jobs + reads, runs k_sw, copies results back
-static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n, const bwa_gpu_sw_job_t *jobs,
-                    bwa_gpu_sw_res_t *res, int (*fail)(const char *, ...), double *kernel_ms)
+// ------------------------------------------------------------------ K6: banded global alignment + traceback
+// aln_global_core (stdaln.c:345-525) with aln_param_bwa's scores, restated literally, one job per
+// thread: the three row regimes of the band (left edge / inside / right edge), end-gap costs on the
+// first and last row and column, the M/I/D traceback matrix (2 bits per state, one byte per cell) and
+// the backtrace.  The CIGAR is produced straight from the backtrace (aln_path2cigar32 +
+// bwa_aln_path2cigar, stdaln.c:1009-1039, bwtaln.c:396-406).  Sequential per job -- a job is only
+// ~len2 x band cells -- with per-thread scratch in global memory.
+#define G_INF (-1073741823)
+
+struct GScore { int M, I, D; };
+
+struct GlobalOut {
+	int score, n_cigar, start_i, start_j, end_i, end_j;
+};
+
+__device__ __forceinline__ int g_setM(uint8_t &c, const GScore &p, int sc)
+{
+	if (p.M >= p.I) {
+		if (p.M >= p.D) { c = (c & ~3u) | 0u; return p.M + sc; }
+		c = (c & ~3u) | 2u; return p.D + sc;
+	}
+	if (p.I > p.D) { c = (c & ~3u) | 1u; return p.I + sc; }
+	c = (c & ~3u) | 2u; return p.D + sc;
+}
+__device__ __forceinline__ int g_setI(uint8_t &c, const GScore &p, int ext)
+{
+	if (p.M - SW_Q > p.I) { c = (c & ~12u) | 0u; return p.M - SW_Q - ext; }
+	c = (c & ~12u) | (1u << 2); return p.I - ext;
+}
+__device__ __forceinline__ int g_setD(uint8_t &c, const GScore &p, int ext)
+{
+	if (p.M - SW_Q > p.D) { c = (c & ~48u) | 0u; return p.M - SW_Q - ext; }
+	c = (c & ~48u) | (2u << 4); return p.D - ext;
+}
+
+// ref base i (1-based, window-relative) = pac_base(pac, rbeg + i - 1); query base j = q[j - 1].
+// cells: (len2 + 1) * width bytes; sc0/sc1: len1 + 2 GScore each; cig: len1 + len2 + 2 u16 (filled from its END).
+__device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, long long rbeg, int len1, const uint8_t *__restrict__ q,
+                                      int len2, int gap_end, int band, uint8_t *cells, GScore *sc0, GScore *sc1,
+                                      uint16_t *cig, int cig_cap)
+{
+	GlobalOut out = {0, 0, 0, 0, 0, 0};
+	if (len1 == 0 || len2 == 0) return out;
+	const int eend = gap_end >= 0 ? gap_end : SW_R;
+	int b1, b2;
+	if (len1 > len2) { b1 = len1 - len2 + band; b2 = band; }
+	else { b1 = band; b2 = len2 - len1 + band; }
+	if (b1 > len1) b1 = len1;
+	if (b2 > len2) b2 = len2;
+	const int width = (b1 + b2 <= len1) ? b1 + b2 + 1 : len1 + 1;
+	GScore *curr = sc0, *last = sc1, *sw;
+#define GCELL(j, i) cells[(size_t)(j) * width + ((j) > b2 ? (i) - ((j) - b2) : (i))]
+#define GSC(i) sw_sc(pac_base(pac, rbeg + (i) - 1), qj)
+	int i, j, end;
+	curr[0].M = 0; curr[0].I = curr[0].D = G_INF;
+	for (i = 1; i < b1; ++i) {
+		curr[i].M = curr[i].I = G_INF;
+		curr[i].D = g_setD(GCELL(0, i), curr[i - 1], eend);
+	}
+	sw = curr; curr = last; last = sw;
+	const int tmp_end = b2 < len2 ? b2 : len2 - 1;
+	for (j = 1; j <= tmp_end + 1; ++j) { // part 1 (+ its last-row variant)
+		const bool last_row = j == tmp_end + 1;
+		if (last_row && !(j == len2 && b2 != len2 - 1)) break;
+		const int qj = q[j - 1];
+		curr[0].M = curr[0].D = G_INF;
+		curr[0].I = g_setI(GCELL(j, 0), last[0], eend);
+		end = (j + b1 <= len1 + 1) ? j + b1 - 1 : len1;
+		for (i = 1; i != end; ++i) {
+			uint8_t &c = GCELL(j, i);
+			curr[i].M = g_setM(c, last[i - 1], GSC(i));
+			curr[i].I = g_setI(c, last[i], SW_R);
+			curr[i].D = g_setD(c, curr[i - 1], last_row ? eend : SW_R);
+		}
+		uint8_t &c = GCELL(j, i);
+		curr[i].M = g_setM(c, last[i - 1], GSC(i));
+		curr[i].D = g_setD(c, curr[i - 1], last_row ? eend : SW_R);
+		if (j + b1 - 1 > len1) curr[i].I = g_setI(c, last[i], eend);
+		else curr[i].I = G_INF;
+		sw = curr; curr = last; last = sw;
+	}
+	for (; j <= len2 - b2 + 1; ++j) { // part 2
+		const int qj = q[j - 1];
+		curr[j - b2].M = curr[j - b2].I = curr[j - b2].D = G_INF;
+		end = j + b1 - 1;
+		for (i = j - b2 + 1; i != end; ++i) {
+			uint8_t &c = GCELL(j, i);
+			curr[i].M = g_setM(c, last[i - 1], GSC(i));
+			curr[i].I = g_setI(c, last[i], SW_R);
+			curr[i].D = g_setD(c, curr[i - 1], SW_R);
+		}
+		uint8_t &c = GCELL(j, i);
+		curr[i].M = g_setM(c, last[i - 1], GSC(i));
+		curr[i].D = g_setD(c, curr[i - 1], SW_R);
+		curr[i].I = G_INF;
+		sw = curr; curr = last; last = sw;
+	}
+	for (; j <= len2; ++j) { // part 3 and the last row
+		const bool last_row = j == len2;
+		const int qj = q[j - 1];
+		curr[j - b2].M = curr[j - b2].I = curr[j - b2].D = G_INF;
+		for (i = j - b2 + 1; i < len1; ++i) {
+			uint8_t &c = GCELL(j, i);
+			curr[i].M = g_setM(c, last[i - 1], GSC(i));
+			curr[i].I = g_setI(c, last[i], SW_R);
+			curr[i].D = g_setD(c, curr[i - 1], last_row ? eend : SW_R);
+		}
+		uint8_t &c = GCELL(j, i);
+		curr[i].M = g_setM(c, last[len1 - 1], GSC(i));
+		curr[i].I = g_setI(c, last[i], eend);
+		curr[i].D = g_setD(c, curr[i - 1], last_row ? eend : SW_R);
+		sw = curr; curr = last; last = sw;
+	}
+	// backtrace, emitting CIGAR runs from the end of the alignment backwards
+	i = len1; j = len2;
+	uint8_t cc = GCELL(j, i);
+	int mx = last[len1].M, type = cc & 3, ctype = 0;
+	if (last[len1].I > mx) { mx = last[len1].I; type = (cc >> 2) & 3; ctype = 1; }
+	if (last[len1].D > mx) { mx = last[len1].D; type = (cc >> 4) & 3; ctype = 2; }
+	out.score = mx; out.end_i = i; out.end_j = j;
+	int pos = cig_cap, run_type = ctype, run_len = 1; // path[0] = (len1, len2, ctype)
+	int pi = i, pj = j; // coordinates of the latest path element
+	int n_path = 1;
+	for (;;) {
+		if (ctype == 0) { --i; --j; } else if (ctype == 1) --j; else --i;
+		cc = GCELL(j, i);
+		ctype = type;
+		type = type == 0 ? (cc & 3) : type == 1 ? ((cc >> 2) & 3) : ((cc >> 4) & 3);
+		if (!(i || j)) break; // this element is path[path_len]: not part of the path
+		++n_path;
+		pi = i; pj = j;
+		if (ctype == run_type) ++run_len;
+		else { cig[--pos] = (uint16_t)(run_type << 14 | run_len); run_type = ctype; run_len = 1; }
+	}
+	cig[--pos] = (uint16_t)(run_type << 14 | run_len);
+	out.n_cigar = cig_cap - pos;
+	// move the CIGAR to the front of the buffer in start -> end order (it already is, just shifted)
+	for (int t = 0; t < out.n_cigar; ++t) cig[t] = cig[pos + t];
+	out.start_i = pi; out.start_j = pj;
+	(void)n_path;
+#undef GCELL
+#undef GSC
+	return out;
+}
+
+struct PathJob { // one K6 job; mode 0: plain global alignment, mode 1: third pass of aln_local_core inside a K5 box
+	long long beg;
+	int len1, len2;
+	long long q_off;
+	long long cig_off;
+};
+
+__global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac, const PathJob *__restrict__ jobs, int n_jobs,
+                                                const uint8_t *__restrict__ reads, int gap_end, int band,
+                                                const bwa_gpu_sw_res_t *__restrict__ boxes, const int *__restrict__ score_r,
+                                                bwa_gpu_path_res_t *__restrict__ res, uint16_t *__restrict__ cigars,
+                                                uint8_t *cells_all, size_t cells_stride, GScore *sc_all, size_t sc_stride,
+                                                int *work_counter)
+{
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint8_t *cells = cells_all + tid * cells_stride;
+	GScore *sc0 = sc_all + tid * 2 * sc_stride, *sc1 = sc0 + sc_stride;
+	for (;;) {
+		const int job = atomicAdd(work_counter, 1);
+		if (job >= n_jobs) break;
+		const PathJob J = jobs[job];
+		uint16_t *cig = cigars + J.cig_off;
+		const int cig_cap = J.len1 + J.len2 + 2;
+		bwa_gpu_path_res_t r;
+		r.cigar_off = J.cig_off;
+		if (!boxes) { // refine_gapped_core's call (bwase.c:212)
+			const GlobalOut o = global_align_dev(pac, J.beg, J.len1, reads + J.q_off, J.len2, gap_end, band, cells, sc0, sc1, cig, cig_cap);
+			r.score = o.score; r.n_cigar = o.n_cigar;
+			r.start_i = o.start_i; r.start_j = o.start_j; r.end_i = o.end_i; r.end_j = o.end_j;
+		} else { // aln_local_core's third pass (stdaln.c:723-745)
+			const bwa_gpu_sw_res_t b = boxes[job];
+			r.score = b.score; r.n_cigar = 0;
+			r.start_i = b.start_i; r.start_j = b.start_j; r.end_i = b.end_i; r.end_j = b.end_j;
+			if (b.score >= 1 && b.end_i > 0 && b.end_j > 0) { // score_f >= thres (= 1) and a local match exists
+				const int score_f = b.score, sr = score_r[job];
+				const int l1 = b.end_i - b.start_i + 1, l2 = b.end_j - b.start_j + 1;
+				int span = (b.end_i - b.start_i > b.end_j - b.start_j ? b.end_i - b.start_i : b.end_j - b.start_j) + 1;
+				GlobalOut o;
+				for (int bw = 50;; bw <<= 1) {
+					o = global_align_dev(pac, J.beg + b.start_i - 1, l1, reads + J.q_off + b.start_j - 1, l2, -1, bw, cells, sc0, sc1, cig, cig_cap);
+					if (o.score == sr || score_f == o.score) break;
+					if (bw > span) break;
+				}
+				if (sr > o.score && score_f > o.score) r.score = -1; // the reference's "Potential bug" branch
+				else r.score = o.score;
+				r.n_cigar = o.n_cigar;
+				r.start_i = o.start_i + b.start_i - 1; r.start_j = o.start_j + b.start_j - 1;
+				r.end_i = o.end_i + b.start_i - 1; r.end_j = o.end_j + b.start_j - 1;
+			}
+		}
+		res[job] = r;
+	}
+}
+
+// host launcher.  mode 0: K5 only (res); mode 1: K5 + third pass (pres, cigars); mode 2: plain banded global
+// alignment with (gap_end, band) (pres, cigars).
+static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n, const bwa_gpu_sw_job_t *jobs, int mode,
+                    int gap_end, int band, bwa_gpu_sw_res_t *res, bwa_gpu_path_res_t *pres, std::vector<uint16_t> *cigars,
+                    int (*fail)(const char *, ...), double *kernel_ms)
 {
 	if (kernel_ms) *kernel_ms = 0;
+	if (cigars) cigars->clear();
 	if (n == 0) return 0;
 	std::vector<SwJob> hj(n);
+	std::vector<PathJob> pj(mode ? n : 0);
 	int len1_max = 1, len2_max = 1;
-	long long q_total = 0;
+	long long q_total = 0, cig_total = 0;
 	for (int i = 0; i < n; ++i) {
 		const bwa_gpu_sw_job_t &j = jobs[i];
-		if (j.beg < 0 || j.len < 0 || j.reglen < 0 || (j.len > 0 && !j.seq)) return fail("bwa_gpu_mate_sw: job %d is malformed", i);
+		if (j.beg < 0 || j.len < 0 || j.reglen < 0 || (j.len > 0 && !j.seq)) return fail("job %d is malformed", i);
 		long long l = j.reglen;
-		if (j.beg + l > l_pac) l = l_pac - j.beg; // bwa_sw_core copies at most up to l_pac (bwape.c:447-448)
+		if (j.beg + l > l_pac) l = l_pac - j.beg; // the reference copies at most up to l_pac (bwape.c:447-448, bwase.c:201-208)
 		if (l < 0) l = 0;
 		hj[i].beg = j.beg; hj[i].len1 = (int)l; hj[i].len2 = j.len; hj[i].q_off = q_total;
+		if (mode) {
+			pj[i].beg = j.beg; pj[i].len1 = (int)l; pj[i].len2 = j.len; pj[i].q_off = q_total; pj[i].cig_off = cig_total;
+			cig_total += l + j.len + 2;
+		}
 		q_total += j.len;
 		if (hj[i].len1 > len1_max) len1_max = hj[i].len1;
 		if (j.len > len2_max) len2_max = j.len;
 	}
-	const int q_words = (len2_max + 4) >> 2, r_words = (len1_max + 4) >> 2;
-	const size_t smem = (size_t)4 * (q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2)) * sizeof(int);
-	if (smem > 200 * 1024) return fail("bwa_gpu_mate_sw: window %d x read %d needs %zu B of shared memory per block", len1_max, len2_max, smem);
 	std::vector<uint8_t> hq((size_t)q_total + 1);
 	for (int i = 0; i < n; ++i)
 		for (int t = 0; t < jobs[i].len; ++t) hq[(size_t)hj[i].q_off + t] = jobs[i].seq[t] > 3 ? 4 : jobs[i].seq[t];
-	SwJob *d_jobs = nullptr; uint8_t *d_q = nullptr; bwa_gpu_sw_res_t *d_res = nullptr; int *d_cnt = nullptr;
+	SwJob *d_jobs = nullptr; uint8_t *d_q = nullptr; bwa_gpu_sw_res_t *d_res = nullptr; int *d_cnt = nullptr, *d_sr = nullptr;
+	PathJob *d_pj = nullptr; bwa_gpu_path_res_t *d_pres = nullptr; uint16_t *d_cig = nullptr; uint8_t *d_cells = nullptr; GScore *d_sc = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	cudaError_t e;
-#define SWCK(x) do { e = (x); if (e != cudaSuccess) { cudaFree(d_jobs); cudaFree(d_q); cudaFree(d_res); cudaFree(d_cnt); \
-		return fail("bwa_gpu_mate_sw: %s: %s", #x, cudaGetErrorString(e)); } } while (0)
-	SWCK(cudaMalloc((void **)&d_jobs, (size_t)n * sizeof(SwJob)));
+	auto cleanup = [&]() {
+		cudaFree(d_jobs); cudaFree(d_q); cudaFree(d_res); cudaFree(d_cnt); cudaFree(d_sr); cudaFree(d_pj); cudaFree(d_pres);
+		cudaFree(d_cig); cudaFree(d_cells); cudaFree(d_sc);
+		if (e0) cudaEventDestroy(e0);
+		if (e1) cudaEventDestroy(e1);
+	};
+#define SWCK(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return fail("%s: %s", #x, cudaGetErrorString(e)); } } while (0)
 	SWCK(cudaMalloc((void **)&d_q, hq.size()));
-	SWCK(cudaMalloc((void **)&d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t)));
-	SWCK(cudaMalloc((void **)&d_cnt, sizeof(int)));
-	SWCK(cudaMemcpyAsync(d_jobs, hj.data(), (size_t)n * sizeof(SwJob), cudaMemcpyHostToDevice, st));
+	SWCK(cudaMalloc((void **)&d_cnt, 2 * sizeof(int)));
 	SWCK(cudaMemcpyAsync(d_q, hq.data(), hq.size(), cudaMemcpyHostToDevice, st));
-	SWCK(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
-	SWCK(cudaFuncSetAttribute(k_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int dev = 0, n_sm = 148, bps = 1;
+	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1));
+	int dev = 0, n_sm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-	SWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sw, 128, smem));
-	if (bps < 1) bps = 1;
-	int blocks = n_sm * bps;
-	if (blocks > (n + 3) / 4) blocks = (n + 3) / 4;
-	cudaEvent_t e0, e1;
-	cudaEventCreate(&e0); cudaEventCreate(&e1);
-	cudaEventRecord(e0, st);
-	k_sw<<<blocks, 128, smem, st>>>(d_pac, d_jobs, n, d_q, d_res, len1_max, len2_max, d_cnt);
-	cudaEventRecord(e1, st);
-	SWCK(cudaGetLastError());
-	SWCK(cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t), cudaMemcpyDeviceToHost, st));
+	SWCK(cudaEventRecord(e0, st));
+	if (mode != 2) { // K5
+		const int q_words = (len2_max + 4) >> 2, r_words = (len1_max + 4) >> 2;
+		const size_t smem = (size_t)4 * (q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2)) * sizeof(int);
+		if (smem > 200 * 1024) { cleanup(); return fail("window %d x read %d needs %zu B of shared memory per block", len1_max, len2_max, smem); }
+		SWCK(cudaMalloc((void **)&d_jobs, (size_t)n * sizeof(SwJob)));
+		SWCK(cudaMalloc((void **)&d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t)));
+		SWCK(cudaMalloc((void **)&d_sr, (size_t)n * sizeof(int)));
+		SWCK(cudaMemcpyAsync(d_jobs, hj.data(), (size_t)n * sizeof(SwJob), cudaMemcpyHostToDevice, st));
+		SWCK(cudaFuncSetAttribute(k_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		int bps = 1;
+		SWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sw, 128, smem));
+		if (bps < 1) bps = 1;
+		int blocks = n_sm * bps;
+		if (blocks > (n + 3) / 4) blocks = (n + 3) / 4;
+		k_sw<<<blocks, 128, smem, st>>>(d_pac, d_jobs, n, d_q, d_res, len1_max, len2_max, d_cnt, d_sr);
+		SWCK(cudaGetLastError());
+		if (res) SWCK(cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t), cudaMemcpyDeviceToHost, st));
+	}
+	if (mode) { // K6
+		const size_t cells_stride = ((size_t)(len2_max + 1) * (len1_max + 1) + 15) & ~(size_t)15, sc_stride = (size_t)len1_max + 2;
+		const size_t per_thread = cells_stride + 2 * sc_stride * sizeof(GScore);
+		size_t threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
+		const size_t budget = (size_t)6 << 30;
+		if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
+		SWCK(cudaMalloc((void **)&d_pj, (size_t)n * sizeof(PathJob)));
+		SWCK(cudaMalloc((void **)&d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t)));
+		SWCK(cudaMalloc((void **)&d_cig, (size_t)cig_total * sizeof(uint16_t) + 16));
+		SWCK(cudaMalloc((void **)&d_cells, threads * cells_stride));
+		SWCK(cudaMalloc((void **)&d_sc, threads * 2 * sc_stride * sizeof(GScore)));
+		SWCK(cudaMemcpyAsync(d_pj, pj.data(), (size_t)n * sizeof(PathJob), cudaMemcpyHostToDevice, st));
+		k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(d_pac, d_pj, n, d_q, gap_end, band, mode == 1 ? d_res : nullptr, d_sr, d_pres,
+		                                                   d_cig, d_cells, cells_stride, d_sc, sc_stride, d_cnt + 1);
+		SWCK(cudaGetLastError());
+		cigars->resize((size_t)cig_total);
+		SWCK(cudaMemcpyAsync(pres, d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t), cudaMemcpyDeviceToHost, st));
+		if (cig_total) SWCK(cudaMemcpyAsync(cigars->data(), d_cig, (size_t)cig_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+	}
+	SWCK(cudaEventRecord(e1, st));
 	SWCK(cudaStreamSynchronize(st));
 	{
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);
 		if (kernel_ms) *kernel_ms = ms;
-		cudaEventDestroy(e0); cudaEventDestroy(e1);
 	}
 #undef SWCK
-	cudaFree(d_jobs); cudaFree(d_q); cudaFree(d_res); cudaFree(d_cnt);
-	for (int i = 0; i < n; ++i)
-		if (res[i].score <= -3) return fail("bwa_gpu_mate_sw: job %d hit an unsupported case (code %d)", i, res[i].score);
+	cleanup();
+	if (mode != 2 && res)
+		for (int i = 0; i < n; ++i)
+			if (res[i].score <= -3) return fail("job %d hit an unsupported case (code %d)", i, res[i].score);
 	return 0;
 }
 

@@ -460,3 +460,164 @@ int orc_sw_local(const uint8_t *ref, int len1, const uint8_t *query, int len2, i
 	free(H); free(E);
 	return score_f;
 }
+
+/* ---------------------------------------------------------------- banded global alignment */
+
+#define G_INF (-1073741823) /* MINOR_INF, stdaln.h:84 */
+enum { G_M = 0, G_I = 1, G_D = 2 };
+typedef struct { int M, I, D; } gscore_t;            /* dpscore_t, stdaln.c:326-329 */
+typedef struct { unsigned char Mt, It, Dt; } gcell_t; /* dpcell_t, stdaln.c:321-324 */
+
+/* the set_* macros of stdaln.c:260-319 as functions; `p` is the cell the value comes from */
+static int g_setM(gcell_t *c, const gscore_t *p, int sc)
+{
+	if (p->M >= p->I) {
+		if (p->M >= p->D) { c->Mt = G_M; return p->M + sc; }
+		c->Mt = G_D; return p->D + sc;
+	}
+	if (p->I > p->D) { c->Mt = G_I; return p->I + sc; }
+	c->Mt = G_D; return p->D + sc;
+}
+static int g_setI(gcell_t *c, const gscore_t *p, int ext)
+{
+	if (p->M - SW_Q > p->I) { c->It = G_M; return p->M - SW_Q - ext; }
+	c->It = G_I; return p->I - ext;
+}
+static int g_setD(gcell_t *c, const gscore_t *p, int ext)
+{
+	if (p->M - SW_Q > p->D) { c->Dt = G_M; return p->M - SW_Q - ext; }
+	c->Dt = G_D; return p->D - ext;
+}
+
+int orc_global(const uint8_t *ref, int len1, const uint8_t *query, int len2, int gap_end, int band,
+               int32_t *path_ijc, int *path_len)
+{
+	const int eend = gap_end >= 0 ? gap_end : SW_R; /* set_end_* fall back to set_* when gap_end < 0 */
+	int b1, b2, width, i, j, end, tmp_end, max, type, ctype, n;
+	gcell_t *cells;  /* (len2+1) rows of `width` cells; row j > b2 is shifted left by j - b2 */
+	gscore_t *curr, *last, *sw;
+#define CELL(j, i) (cells + (size_t)(j) * width + ((j) > b2 ? (i) - ((j) - b2) : (i)))
+#define SC(i) sw_score(ref[(i) - 1], query[j - 1])
+	if (len1 == 0 || len2 == 0) { *path_len = 0; return 0; }
+	if (len1 > len2) { b1 = len1 - len2 + band; b2 = band; }
+	else { b1 = band; b2 = len2 - len1 + band; }
+	if (b1 > len1) b1 = len1;
+	if (b2 > len2) b2 = len2;
+	width = (b1 + b2 <= len1) ? b1 + b2 + 1 : len1 + 1;
+	cells = (gcell_t *)calloc((size_t)(len2 + 1) * width + 8, sizeof(gcell_t));
+	curr = (gscore_t *)calloc(len1 + 2, sizeof(gscore_t));
+	last = (gscore_t *)calloc(len1 + 2, sizeof(gscore_t));
+
+	/* first row (stdaln.c:393-399) */
+	curr[0].M = 0; curr[0].I = curr[0].D = G_INF;
+	for (i = 1; i < b1; ++i) {
+		curr[i].M = curr[i].I = G_INF;
+		curr[i].D = g_setD(CELL(0, i), &curr[i - 1], eend);
+	}
+	sw = curr; curr = last; last = sw;
+
+	/* part 1: rows whose band still starts at column 0 (stdaln.c:401-440) */
+	tmp_end = b2 < len2 ? b2 : len2 - 1;
+	for (j = 1; j <= tmp_end + 1; ++j) {
+		const int last_row = j == tmp_end + 1; /* the "last row for part 1" variant: end gaps in D */
+		if (last_row && !(j == len2 && b2 != len2 - 1)) break;
+		curr[0].M = curr[0].D = G_INF;
+		curr[0].I = g_setI(CELL(j, 0), &last[0], eend);
+		end = (j + b1 <= len1 + 1) ? j + b1 - 1 : len1;
+		for (i = 1; i != end; ++i) {
+			curr[i].M = g_setM(CELL(j, i), &last[i - 1], SC(i));
+			curr[i].I = g_setI(CELL(j, i), &last[i], SW_R);
+			curr[i].D = g_setD(CELL(j, i), &curr[i - 1], last_row ? eend : SW_R);
+		}
+		curr[i].M = g_setM(CELL(j, i), &last[i - 1], SC(i));
+		curr[i].D = g_setD(CELL(j, i), &curr[i - 1], last_row ? eend : SW_R);
+		if (j + b1 - 1 > len1) curr[i].I = g_setI(CELL(j, i), &last[i], eend);
+		else curr[i].I = G_INF;
+		sw = curr; curr = last; last = sw;
+	}
+	/* j now = first row not done by part 1 (the reference's ++j after its special row included) */
+
+	/* part 2: band strictly inside (stdaln.c:442-456) */
+	for (; j <= len2 - b2 + 1; ++j) {
+		curr[j - b2].M = curr[j - b2].I = curr[j - b2].D = G_INF;
+		end = j + b1 - 1;
+		for (i = j - b2 + 1; i != end; ++i) {
+			curr[i].M = g_setM(CELL(j, i), &last[i - 1], SC(i));
+			curr[i].I = g_setI(CELL(j, i), &last[i], SW_R);
+			curr[i].D = g_setD(CELL(j, i), &curr[i - 1], SW_R);
+		}
+		curr[i].M = g_setM(CELL(j, i), &last[i - 1], SC(i));
+		curr[i].D = g_setD(CELL(j, i), &curr[i - 1], SW_R);
+		curr[i].I = G_INF;
+		sw = curr; curr = last; last = sw;
+	}
+	/* part 3: band reaches the last column (stdaln.c:458-471), then the last row (472-487) */
+	for (; j <= len2; ++j) {
+		const int last_row = j == len2;
+		curr[j - b2].M = curr[j - b2].I = curr[j - b2].D = G_INF;
+		for (i = j - b2 + 1; i < len1; ++i) {
+			curr[i].M = g_setM(CELL(j, i), &last[i - 1], SC(i));
+			curr[i].I = g_setI(CELL(j, i), &last[i], SW_R);
+			curr[i].D = g_setD(CELL(j, i), &curr[i - 1], last_row ? eend : SW_R);
+		}
+		curr[i].M = g_setM(CELL(j, i), &last[len1 - 1], SC(i));
+		curr[i].I = g_setI(CELL(j, i), &last[i], eend);
+		curr[i].D = g_setD(CELL(j, i), &curr[i - 1], last_row ? eend : SW_R);
+		sw = curr; curr = last; last = sw;
+	}
+
+	/* backtrace (stdaln.c:489-513) */
+	i = len1; j = len2;
+	max = last[len1].M; type = CELL(j, i)->Mt; ctype = G_M;
+	if (last[len1].I > max) { max = last[len1].I; type = CELL(j, i)->It; ctype = G_I; }
+	if (last[len1].D > max) { max = last[len1].D; type = CELL(j, i)->Dt; ctype = G_D; }
+	n = 0;
+	path_ijc[0] = i; path_ijc[1] = j; path_ijc[2] = ctype; ++n;
+	do {
+		const gcell_t *q;
+		if (ctype == G_M) { --i; --j; } else if (ctype == G_I) --j; else --i;
+		q = CELL(j, i);
+		ctype = type;
+		type = type == G_M ? q->Mt : type == G_I ? q->It : q->Dt;
+		path_ijc[3 * n] = i; path_ijc[3 * n + 1] = j; path_ijc[3 * n + 2] = ctype; ++n;
+	} while (i || j);
+	*path_len = n - 1;
+	free(cells); free(curr); free(last);
+#undef CELL
+#undef SC
+	return max;
+}
+
+int orc_path2cigar(const int32_t *path_ijc, int path_len, uint16_t *cigar)
+{
+	int i, n = 0, last;
+	if (path_len == 0) return 0;
+	last = path_ijc[3 * (path_len - 1) + 2];
+	cigar[0] = (uint16_t)(last << 14 | 1);
+	for (i = path_len - 2; i >= 0; --i) {
+		int t = path_ijc[3 * i + 2];
+		if (t == last) ++cigar[n];
+		else { cigar[++n] = (uint16_t)(t << 14 | 1); last = t; }
+	}
+	return n + 1;
+}
+
+int orc_sw_local_path(const uint8_t *ref, int len1, const uint8_t *query, int len2, int32_t *path_ijc, int *path_len)
+{
+	int res[4], score_f, score_g, band, span, t;
+	*path_len = 0;
+	score_f = orc_sw_local(ref, len1, query, len2, res);
+	if (score_f < 1 || res[2] == 0 || res[3] == 0) return score_f; /* stdaln.c:633-640 */
+	/* score_r - qr == score_f always held in the tests; the reference compares both (stdaln.c:732) */
+	span = res[2] - res[0] > res[3] - res[1] ? res[2] - res[0] : res[3] - res[1];
+	++span;
+	for (band = 50;; band <<= 1) { /* aln_param_bwa.band_width = 50 */
+		score_g = orc_global(ref + res[0] - 1, res[2] - res[0] + 1, query + res[1] - 1, res[3] - res[1] + 1, -1, band,
+		                     path_ijc, path_len);
+		if (score_g == score_f) break;
+		if (band > span) break;
+	}
+	if (score_f > score_g) return -1; /* "Potential bug" branch, stdaln.c:736-739 */
+	for (t = 0; t < *path_len; ++t) { path_ijc[3 * t] += res[0] - 1; path_ijc[3 * t + 1] += res[1] - 1; }
+	return score_g;
+}

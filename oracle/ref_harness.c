@@ -130,6 +130,23 @@ int refh_sw_ends(const uint8_t *ref, int l_ref, const uint8_t *query, int l_quer
 	return score;
 }
 
+/* aln_global_core with aln_param_bwa's scores and the given gap_end / band (stdaln.c:345) */
+int refh_global(const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, int gap_end, int band,
+                int *path_len, int32_t *path_ijc)
+{
+	path_t *path = (path_t *)calloc(l_ref + l_query + 2, sizeof(path_t));
+	AlnParam ap = aln_param_bwa;
+	int i, score;
+	ap.gap_end = gap_end; ap.band_width = band;
+	*path_len = 0;
+	score = aln_global_core((unsigned char *)ref, l_ref, (unsigned char *)query, l_query, &ap, path, path_len);
+	for (i = 0; i < *path_len; ++i) {
+		path_ijc[3*i] = path[i].i; path_ijc[3*i+1] = path[i].j; path_ijc[3*i+2] = path[i].ctype;
+	}
+	free(path);
+	return score;
+}
+
 typedef struct {
 	int n, tid, nthreads;
 	const uint8_t *refs, *queries;

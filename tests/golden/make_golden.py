@@ -8,8 +8,9 @@ oracle/_ref to pin parity.
 Contents: genome (uint8 0..3); per config c in CONFIGS: c_bases, c_offs (reads), c_opt (the 16
 gap_opt_t words), c_n_aln, c_max_entries, c_aln (bwt_aln1_t bytes as u32[n,4]) from
 bwa_cal_sa_reg_gap(bwt, 1, &seq, opt) (bwtaln.c:93), plus sa_k, sa_which, sa_out from bwt_sa
-(bwt.c:72), maxdiff tables from bwa_cal_maxdiff (bwtaln.c:37), and sw_* = Smith-Waterman jobs with
-(score, start_i, start_j, end_i, end_j) from aln_local_core (stdaln.c:529).
+(bwt.c:72), maxdiff tables from bwa_cal_maxdiff (bwtaln.c:37), sw_*/swp_* = Smith-Waterman jobs with
+(score, start_i, start_j, end_i, end_j) from aln_local_core (stdaln.c:529), swpath_* = the same call with its path
+(end points + CIGAR), glob_* = aln_global_core (stdaln.c:345) jobs with (gap_end, band) per job.
 """
 import ctypes as C
 import os
@@ -89,6 +90,30 @@ def main():
     refs, ro, qs, qo, begs = R.make_sw_jobs(T, 3000, seed=23, ref_n=False, with_beg=True, read_len=(25, 150), win=(30, 700))
     out["swp_beg"], out["swp_reglen"], out["swp_queries"], out["swp_q_off"] = begs, np.diff(ro).astype(np.int32), qs, qo
     out["swp_out"] = R.ref_sw_batch(refs, ro, qs, qo)
+    # the full aln_local_core call (third pass included): score, path end points, CIGAR -- on the swp jobs
+    rows, cigs, coff = [], [], [0]
+    for i in range(begs.size):
+        r = R.ref_sw_path(refs[ro[i]:ro[i + 1]], qs[qo[i]:qo[i + 1]])
+        rows.append(r[:5]); cigs.append(r[5]); coff.append(coff[-1] + r[5].size)
+    out["swpath_out"] = np.array(rows, dtype=np.int32)
+    out["swpath_cigar"] = np.concatenate(cigs).astype(np.uint16)
+    out["swpath_cigar_off"] = np.array(coff, dtype=np.int64)
+    # aln_global_core as refine_gapped_core calls it (gap_end 5, band 50) and with a narrow band / free ends
+    rng = np.random.default_rng(9)
+    gl_beg, gl_len, gl_q, gl_qoff, gl_par, rows, cigs, coff = [], [], [], [0], [], [], [], [0]
+    for i in range(1500):
+        q = qs[qo[i]:qo[i + 1]][:150]
+        rl = int(q.size + rng.integers(0, 9)); beg = int(begs[i] + rng.integers(0, 10))
+        ge, band = [(5, 50), (-1, 50), (5, 7), (-1, 2)][i % 4]
+        r = R.ref_global(T[beg:beg + rl], q, ge, band)
+        gl_beg.append(beg); gl_len.append(rl); gl_q.append(q); gl_qoff.append(gl_qoff[-1] + q.size); gl_par.append((ge, band))
+        rows.append(r[:5]); cigs.append(r[5]); coff.append(coff[-1] + r[5].size)
+    out["glob_beg"], out["glob_reglen"] = np.array(gl_beg, dtype=np.int64), np.array(gl_len, dtype=np.int32)
+    out["glob_queries"], out["glob_q_off"] = np.concatenate(gl_q).astype(np.uint8), np.array(gl_qoff, dtype=np.int64)
+    out["glob_par"] = np.array(gl_par, dtype=np.int32)
+    out["glob_out"] = np.array(rows, dtype=np.int32)
+    out["glob_cigar"] = np.concatenate(cigs).astype(np.uint16)
+    out["glob_cigar_off"] = np.array(coff, dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "aln_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "aln_golden.npz"), os.path.getsize(os.path.join(HERE, "aln_golden.npz")))
 

@@ -302,3 +302,39 @@ def make_sw_jobs(T, n_jobs: int, seed: int, read_len=(30, 120), win=(60, 420), r
     out = (np.concatenate(refs).astype(np.uint8), np.array(ro, dtype=np.int64),
            np.concatenate(queries).astype(np.uint8), np.array(qo, dtype=np.int64))
     return out + (np.array(begs, dtype=np.int64),) if with_beg else out
+
+
+def path_to_cigar(path_ijc: np.ndarray) -> np.ndarray:
+    """aln_path2cigar32 + bwa_aln_path2cigar (stdaln.c:1009-1039, bwtaln.c:396-406) on a (n,3) path."""
+    if path_ijc.shape[0] == 0:
+        return np.empty(0, dtype=np.uint16)
+    t = path_ijc[::-1, 2]
+    cut = np.nonzero(np.diff(t) != 0)[0] + 1
+    starts = np.concatenate([[0], cut]); ends = np.concatenate([cut, [t.size]])
+    return ((t[starts].astype(np.uint16) << 14) | (ends - starts).astype(np.uint16)).astype(np.uint16)
+
+
+def ref_sw_path(ref_arr: np.ndarray, q_arr: np.ndarray):
+    """aln_local_core with path (as bwa_sw_core calls it) -> (score, start_i, start_j, end_i, end_j, cigar)"""
+    _, H = ref()
+    r = np.ascontiguousarray(ref_arr, dtype=np.uint8); q = np.ascontiguousarray(q_arr, dtype=np.uint8)
+    path = np.zeros(3 * (r.size + q.size + 4), dtype=np.int32)
+    plen = C.c_int()
+    score = H.refh_sw1(r.ctypes.data, r.size, q.ctypes.data, q.size, C.byref(plen), path.ctypes.data)
+    p = path[:3 * plen.value].reshape(-1, 3)
+    if plen.value == 0:
+        return (score, 0, 0, 0, 0, np.empty(0, dtype=np.uint16))
+    return (score, int(p[-1, 0]), int(p[-1, 1]), int(p[0, 0]), int(p[0, 1]), path_to_cigar(p))
+
+
+def ref_global(ref_arr: np.ndarray, q_arr: np.ndarray, gap_end: int, band: int):
+    _, H = ref()
+    H.refh_global.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    r = np.ascontiguousarray(ref_arr, dtype=np.uint8); q = np.ascontiguousarray(q_arr, dtype=np.uint8)
+    path = np.zeros(3 * (r.size + q.size + 4), dtype=np.int32)
+    plen = C.c_int()
+    score = H.refh_global(r.ctypes.data, r.size, q.ctypes.data, q.size, gap_end, band, C.byref(plen), path.ctypes.data)
+    p = path[:3 * plen.value].reshape(-1, 3)
+    if plen.value == 0:
+        return (score, 0, 0, 0, 0, np.empty(0, dtype=np.uint16))
+    return (score, int(p[-1, 0]), int(p[-1, 1]), int(p[0, 0]), int(p[0, 1]), path_to_cigar(p))

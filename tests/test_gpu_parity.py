@@ -228,3 +228,64 @@ def test_multi_device_in_process(golden, small_index):
         assert np.array_equal(out, golden["sa_out"])
     finally:
         api.destroy()
+
+
+def _same_path(got, want):
+    return tuple(got[:5]) == tuple(want[:5]) and np.array_equal(got[5], want[5])
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+def test_mate_sw_path_matches_reference_live(gpu_index):
+    """K5 + K6: the whole aln_local_core call of bwa_sw_core -- score, path end points and CIGAR."""
+    T, idx = gpu_index
+    refs, ro, qs, qo, begs = R.make_sw_jobs(T, 2500, seed=321, ref_n=False, with_beg=True, read_len=(20, 200), win=(20, 900))
+    jobs = sw_jobs_from(begs, np.diff(ro).astype(np.int32), qs, qo)
+    got = api.mate_sw_path(jobs)
+    bad = []
+    for i in range(len(jobs)):
+        want = R.ref_sw_path(refs[ro[i]:ro[i + 1]], qs[qo[i]:qo[i + 1]])
+        if want[0] < 1:  # nothing aligned: the reference returns before making a path
+            if not (got[i][0] == want[0] and got[i][5].size == 0):
+                bad.append(i)
+        elif not _same_path(got[i], want):
+            bad.append(i)
+    assert not bad, (len(bad), bad[:5], got[bad[0]], R.ref_sw_path(refs[ro[bad[0]]:ro[bad[0] + 1]], qs[qo[bad[0]]:qo[bad[0] + 1]]))
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("gap_end,band", [(5, 50), (-1, 50), (5, 7), (-1, 2)])
+def test_global_align_matches_reference_live(gpu_index, gap_end, band):
+    """K6 alone: aln_global_core as refine_gapped_core calls it (gap_end 5, band 50) and with other settings."""
+    T, idx = gpu_index
+    rng = np.random.default_rng(band)
+    refs, ro, qs, qo, begs = R.make_sw_jobs(T, 1500, seed=100 + band, ref_n=False, with_beg=True, read_len=(20, 150), win=(160, 161))
+    jobs, wants = [], []
+    for i in range(1500):
+        q = qs[qo[i]:qo[i + 1]]
+        rl = int(q.size + rng.integers(0, 9))  # len + |ext| like refine_gapped_core's window
+        beg = int(begs[i] + rng.integers(0, 20))
+        jobs.append((beg, rl, q))
+        wants.append(R.ref_global(T[beg:beg + rl], q, gap_end, band))
+    got = api.global_align(jobs, gap_end, band)
+    bad = [i for i in range(1500) if not _same_path(got[i], wants[i])]
+    assert not bad, (len(bad), bad[:5], got[bad[0]], wants[bad[0]])
+
+
+def test_mate_sw_path_and_global_align_match_golden(golden, gpu_index):
+    """K6 against the committed reference-made vectors (no oracle/_ref needed)."""
+    jobs = sw_jobs_from(golden["swp_beg"], golden["swp_reglen"], golden["swp_queries"], golden["swp_q_off"])
+    got = api.mate_sw_path(jobs)
+    want, wc, wo = golden["swpath_out"], golden["swpath_cigar"], golden["swpath_cigar_off"]
+    for i in range(len(jobs)):
+        if want[i, 0] < 1:
+            assert got[i][0] == want[i, 0] and got[i][5].size == 0, i
+        else:
+            assert tuple(got[i][:5]) == tuple(want[i]) and np.array_equal(got[i][5], wc[wo[i]:wo[i + 1]]), i
+    par = golden["glob_par"]
+    qo, co = golden["glob_q_off"], golden["glob_cigar_off"]
+    for ge, band in sorted({(int(a), int(b)) for a, b in par}):
+        sel = [i for i in range(par.shape[0]) if (int(par[i, 0]), int(par[i, 1])) == (ge, band)]
+        jobs = [(int(golden["glob_beg"][i]), int(golden["glob_reglen"][i]), golden["glob_queries"][qo[i]:qo[i + 1]]) for i in sel]
+        got = api.global_align(jobs, ge, band)
+        for g, i in zip(got, sel):
+            assert tuple(g[:5]) == tuple(golden["glob_out"][i]) and np.array_equal(g[5], golden["glob_cigar"][co[i]:co[i + 1]]), (i, ge, band)

@@ -85,3 +85,48 @@ def test_oracle_aln_matches_reference_live(small_index, oidx):
     opt = R.abi.default_gap_opt(max_gapo=2)
     want = R.ref_aln(R.RefIndex(idx), reads, opt, threads=4)
     assert R.compare_aln(want, R.orc_aln(oidx[0], reads, opt), "live") == []
+
+
+def _orc_path(fn, *args):
+    import ctypes as C
+    n = args[1] + args[3] + 4
+    path = np.zeros(3 * n, dtype=np.int32)
+    plen = C.c_int()
+    score = fn(*args, path, plen)
+    p = path[:3 * plen.value].reshape(-1, 3)
+    if plen.value == 0:
+        return (score, 0, 0, 0, 0, np.empty(0, np.uint16))
+    return (score, int(p[-1, 0]), int(p[-1, 1]), int(p[0, 0]), int(p[0, 1]), R.path_to_cigar(p))
+
+
+def test_oracle_local_path_matches_golden(golden):
+    """orc_sw_local_path = the whole aln_local_core call incl. the banded global third pass."""
+    import ctypes as C
+    O = R.orc()
+    O.orc_sw_local_path.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    T = golden["genome"]
+    begs, reglen, qs, qo = golden["swp_beg"], golden["swp_reglen"], golden["swp_queries"], golden["swp_q_off"]
+    want, wc, wo = golden["swpath_out"], golden["swpath_cigar"], golden["swpath_cigar_off"]
+    for i in range(0, begs.size, 3):
+        r = np.ascontiguousarray(T[begs[i]:begs[i] + reglen[i]]); q = np.ascontiguousarray(qs[qo[i]:qo[i + 1]])
+        got = _orc_path(lambda a, b, c, d, path, plen: O.orc_sw_local_path(a, b, c, d, path.ctypes.data, C.byref(plen)),
+                        r.ctypes.data, r.size, q.ctypes.data, q.size)
+        if want[i, 0] < 1:
+            assert got[0] == want[i, 0]
+        else:
+            assert tuple(got[:5]) == tuple(want[i]) and np.array_equal(got[5], wc[wo[i]:wo[i + 1]]), i
+
+
+def test_oracle_global_matches_golden(golden):
+    import ctypes as C
+    O = R.orc()
+    O.orc_global.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    T = golden["genome"]
+    for i in range(golden["glob_beg"].size):
+        b, rl = int(golden["glob_beg"][i]), int(golden["glob_reglen"][i])
+        r = np.ascontiguousarray(T[b:b + rl]); q = np.ascontiguousarray(golden["glob_queries"][golden["glob_q_off"][i]:golden["glob_q_off"][i + 1]])
+        ge, band = (int(x) for x in golden["glob_par"][i])
+        got = _orc_path(lambda a, b_, c, d, path, plen: O.orc_global(a, b_, c, d, ge, band, path.ctypes.data, C.byref(plen)),
+                        r.ctypes.data, r.size, q.ctypes.data, q.size)
+        co = golden["glob_cigar_off"]
+        assert tuple(got[:5]) == tuple(golden["glob_out"][i]) and np.array_equal(got[5], golden["glob_cigar"][co[i]:co[i + 1]]), i

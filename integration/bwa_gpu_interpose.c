@@ -9,9 +9,9 @@
  *   bwt_sa             (bwt.c:72, called at bam2bam.c:635-636,752,761,786; bwase.c:145,152)
  *                                                                   -> bwa_gpu_cal_pac_pos
  *   bwa_sw_core        (bwape.c:433, called at bwape.c:577)         -> the reference's own code runs
- *        (its CIGAR needs the path), and the device result of bwa_gpu_mate_sw for the same job is
- *        CHECKED against the reference's aln_local_core (score and end cell); mismatches are counted
- *        and reported at exit.
+ *        and the device result of bwa_gpu_mate_sw_path (K5 + K6) for the same job is CHECKED against the
+ *        reference's aln_local_core: score, path end points and CIGAR; mismatches are counted and
+ *        reported at exit (the reference's own CIGAR is what goes into the BAM).
  *
  * Because the reference calls these per record (n_seqs = 1), this is the CORRECTNESS path -- every
  * call is a device round trip.  Throughput needs the batched driver of INTEGRATION.md.  Used by
@@ -87,7 +87,9 @@ bwtint_t bwt_sa(const bwt_t *bwt, bwtint_t k)
 }
 
 /* stdaln.h path_t / AlnParam are not needed here: aln_local_core is wrapped through void pointers. */
-static __thread int t_last_score, t_last_end_i, t_last_end_j, t_have_last;
+#define MAX_CHECK_CIGAR 1024
+static __thread int t_last_score, t_last_end_i, t_last_end_j, t_last_start_i, t_last_start_j, t_have_last, t_last_n_cigar;
+static __thread bwa_cigar_t t_last_cigar[MAX_CHECK_CIGAR];
 
 int aln_local_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2, const void *ap, void *path, int *path_len,
                    int thres, int *subo)
@@ -97,9 +99,19 @@ int aln_local_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2,
 	if (!real) real = (int (*)(unsigned char *, int, unsigned char *, int, const void *, void *, int *, int, int *))dlsym(RTLD_NEXT, "aln_local_core");
 	score = real(seq1, len1, seq2, len2, ap, path, path_len, thres, subo);
 	t_have_last = 0;
-	if (path && path_len && *path_len > 0) { /* path[0] = the end cell (stdaln.c:741-745); path_t = {int i, j; uchar ctype} */
+	if (path && path_len && *path_len > 0) { /* path_t = {int i, j; uchar ctype}: 12 bytes; path[0] = the end cell */
 		const int *p = (const int *)path;
-		t_last_score = score; t_last_end_i = p[0]; t_last_end_j = p[1]; t_have_last = 1;
+		const int n = *path_len;
+		int k, nc = 0, last = -1;
+		t_last_score = score; t_last_end_i = p[0]; t_last_end_j = p[1];
+		t_last_start_i = p[3 * (n - 1)]; t_last_start_j = p[3 * (n - 1) + 1];
+		for (k = n - 1; k >= 0; --k) { /* aln_path2cigar32 (stdaln.c:1009-1039): runs of equal ctype, start -> end */
+			const int ct = *(const unsigned char *)(p + 3 * k + 2);
+			if (ct == last) ++t_last_cigar[nc - 1];
+			else if (nc < MAX_CHECK_CIGAR) { t_last_cigar[nc++] = (bwa_cigar_t)(ct << 14 | 1); last = ct; }
+		}
+		t_last_n_cigar = nc;
+		t_have_last = 1;
 	}
 	return score;
 }
@@ -116,17 +128,22 @@ bwa_cigar_t *bwa_sw_core(bwtint_t l_pac, const ubyte_t *pacseq, int len, const u
 	ret = real(l_pac, pacseq, len, seq, beg, reglen, n_cigar, cnt);
 	if (g_ready && t_have_last) { /* the reference did run aln_local_core on this job: check the device against it */
 		bwa_gpu_sw_job_t job;
-		bwa_gpu_sw_res_t res;
+		bwa_gpu_path_res_t res;
+		const bwa_cigar_t *pool = 0;
+		int bad;
 		if (!g_pac_ready) { if (bwa_gpu_load_pac(pacseq, (int64_t)l_pac)) die("bwa_gpu_load_pac"); g_pac_ready = 1; }
 		job.beg = beg0; job.reglen = reglen; job.len = len; job.seq = seq;
-		if (bwa_gpu_mate_sw(1, &job, &res)) die("bwa_gpu_mate_sw");
+		if (bwa_gpu_mate_sw_path(1, &job, &res, &pool)) die("bwa_gpu_mate_sw_path");
 		++g_n_sw_checked;
-		/* the reference overwrites score_f with the global pass's score, equal unless it printed
-		 * "Potential bug" (stdaln.c:736-739); end cell = path[0] */
-		if (res.score != t_last_score || res.end_i != t_last_end_i || res.end_j != t_last_end_j) {
+		/* K5 + K6 against the reference's own aln_local_core on this job: score, path end points, CIGAR */
+		bad = res.score != t_last_score || res.end_i != t_last_end_i || res.end_j != t_last_end_j ||
+		      res.start_i != t_last_start_i || res.start_j != t_last_start_j || res.n_cigar != t_last_n_cigar ||
+		      memcmp(pool + res.cigar_off, t_last_cigar, sizeof(bwa_cigar_t) * (size_t)t_last_n_cigar) != 0;
+		if (bad) {
 			++g_n_sw_mismatch;
-			fprintf(stderr, "[bwa_gpu_interpose] SW mismatch: device (%d; %d,%d) reference (%d; %d,%d)\n", res.score, res.end_i,
-			        res.end_j, t_last_score, t_last_end_i, t_last_end_j);
+			fprintf(stderr, "[bwa_gpu_interpose] SW mismatch: device (%d; %d,%d-%d,%d; %d ops) reference (%d; %d,%d-%d,%d; %d ops)\n",
+			        res.score, res.start_i, res.start_j, res.end_i, res.end_j, res.n_cigar, t_last_score, t_last_start_i,
+			        t_last_start_j, t_last_end_i, t_last_end_j, t_last_n_cigar);
 		}
 	}
 	return ret;

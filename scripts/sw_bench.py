@@ -20,5 +20,12 @@ for (wlen, rlen, nj) in ((380, 100, 400_000), (260, 76, 400_000), (800, 150, 100
     lib.bwa_gpu_mate_sw(1000, jobs, res)
     t0 = time.perf_counter(); rc = lib.bwa_gpu_mate_sw(nj, jobs, res); dt = time.perf_counter() - t0
     ms = api.get_stats()["ms_sw_kernel"]
-    print(f"{wlen}x{rlen}: kernel {ms:.1f} ms = {nj / ms / 1e3:.2f} M jobs/s, {nj * wlen * rlen / ms / 1e6:.0f} GCUPS (forward cells); host call {dt * 1e3:.0f} ms")
+    print(f"{wlen}x{rlen}: K5 kernel {ms:.1f} ms = {nj / ms / 1e3:.2f} M jobs/s, {nj * wlen * rlen / ms / 1e6:.0f} GCUPS (forward cells); host call {dt * 1e3:.0f} ms")
+    pres = (abi.path_res_t * nj)(); pool = C.c_void_p()
+    t0 = time.perf_counter(); rc = lib.bwa_gpu_mate_sw_path(nj, jobs, pres, C.byref(pool)); dt = time.perf_counter() - t0
+    ms2 = api.get_stats()["ms_sw_kernel"]
+    print(f"    K5+K6 kernels {ms2:.1f} ms = {nj / ms2 / 1e3:.2f} M jobs/s; host call {dt * 1e3:.0f} ms")
+    t0 = time.perf_counter(); rc = lib.bwa_gpu_global_align(nj, jobs, 5, 50, pres, C.byref(pool)); dt = time.perf_counter() - t0
+    ms3 = api.get_stats()["ms_sw_kernel"]
+    print(f"    K6 alone on the whole window (gap_end 5, band 50) {ms3:.1f} ms = {nj / ms3 / 1e3:.2f} M jobs/s; host call {dt * 1e3:.0f} ms")
 api.destroy()

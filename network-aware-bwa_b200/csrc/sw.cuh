@@ -262,6 +262,14 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 
 struct GScore { int M, I, D; };
 
+// Per-thread scratch is interleaved across the 32 lanes of a warp (element x of lane t lives at
+// base[x * 32 + t]): lanes walk their jobs in near lock-step, so a row access by the warp is one
+// contiguous segment instead of 32 scattered ones.
+struct GRow {
+	GScore *p;
+	__device__ __forceinline__ GScore &operator[](int i) const { return p[(size_t)i * 32]; }
+};
+
 struct GlobalOut {
 	int score, n_cigar, start_i, start_j, end_i, end_j;
 };
@@ -289,7 +297,7 @@ __device__ __forceinline__ int g_setD(uint8_t &c, const GScore &p, int ext)
 // ref base i (1-based, window-relative) = pac_base(pac, rbeg + i - 1); query base j = q[j - 1].
 // cells: (len2 + 1) * width bytes; sc0/sc1: len1 + 2 GScore each; cig: len1 + len2 + 2 u16 (filled from its END).
 __device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, long long rbeg, int len1, const uint8_t *__restrict__ q,
-                                      int len2, int gap_end, int band, uint8_t *cells, GScore *sc0, GScore *sc1,
+                                      int len2, int gap_end, int band, uint8_t *cells, GRow sc0, GRow sc1,
                                       uint16_t *cig, int cig_cap)
 {
 	GlobalOut out = {0, 0, 0, 0, 0, 0};
@@ -301,8 +309,8 @@ __device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, long long
 	if (b1 > len1) b1 = len1;
 	if (b2 > len2) b2 = len2;
 	const int width = (b1 + b2 <= len1) ? b1 + b2 + 1 : len1 + 1;
-	GScore *curr = sc0, *last = sc1, *sw;
-#define GCELL(j, i) cells[(size_t)(j) * width + ((j) > b2 ? (i) - ((j) - b2) : (i))]
+	GRow curr = sc0, last = sc1, sw;
+#define GCELL(j, i) cells[((size_t)(j) * width + ((j) > b2 ? (i) - ((j) - b2) : (i))) * 32]
 #define GSC(i) sw_sc(pac_base(pac, rbeg + (i) - 1), qj)
 	int i, j, end;
 	curr[0].M = 0; curr[0].I = curr[0].D = G_INF;
@@ -410,9 +418,11 @@ __global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac,
                                                 uint8_t *cells_all, size_t cells_stride, GScore *sc_all, size_t sc_stride,
                                                 int *work_counter)
 {
-	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	uint8_t *cells = cells_all + tid * cells_stride;
-	GScore *sc0 = sc_all + tid * 2 * sc_stride, *sc1 = sc0 + sc_stride;
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	uint8_t *cells = cells_all + warp * cells_stride * 32 + lane;
+	GRow sc0, sc1;
+	sc0.p = sc_all + warp * 2 * sc_stride * 32 + lane;
+	sc1.p = sc0.p + sc_stride * 32;
 	for (;;) {
 		const int job = atomicAdd(work_counter, 1);
 		if (job >= n_jobs) break;
@@ -500,10 +510,12 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 	int dev = 0, n_sm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-	SWCK(cudaEventRecord(e0, st));
+	// ---- every allocation and staging copy first, so that the event window holds kernels only
+	size_t smem = 0, cells_stride = 0, sc_stride = 0, threads = 0;
+	int blocks = 0;
 	if (mode != 2) { // K5
 		const int q_words = (len2_max + 4) >> 2, r_words = (len1_max + 4) >> 2;
-		const size_t smem = (size_t)4 * (q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2)) * sizeof(int);
+		smem = (size_t)4 * (q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2)) * sizeof(int);
 		if (smem > 200 * 1024) { cleanup(); return fail("window %d x read %d needs %zu B of shared memory per block", len1_max, len2_max, smem); }
 		SWCK(cudaMalloc((void **)&d_jobs, (size_t)n * sizeof(SwJob)));
 		SWCK(cudaMalloc((void **)&d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t)));
@@ -513,16 +525,14 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 		int bps = 1;
 		SWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_sw, 128, smem));
 		if (bps < 1) bps = 1;
-		int blocks = n_sm * bps;
+		blocks = n_sm * bps;
 		if (blocks > (n + 3) / 4) blocks = (n + 3) / 4;
-		k_sw<<<blocks, 128, smem, st>>>(d_pac, d_jobs, n, d_q, d_res, len1_max, len2_max, d_cnt, d_sr);
-		SWCK(cudaGetLastError());
-		if (res) SWCK(cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t), cudaMemcpyDeviceToHost, st));
 	}
 	if (mode) { // K6
-		const size_t cells_stride = ((size_t)(len2_max + 1) * (len1_max + 1) + 15) & ~(size_t)15, sc_stride = (size_t)len1_max + 2;
+		cells_stride = ((size_t)(len2_max + 1) * (len1_max + 1) + 15) & ~(size_t)15;
+		sc_stride = (size_t)len1_max + 2;
 		const size_t per_thread = cells_stride + 2 * sc_stride * sizeof(GScore);
-		size_t threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
+		threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
 		const size_t budget = (size_t)6 << 30;
 		if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
 		SWCK(cudaMalloc((void **)&d_pj, (size_t)n * sizeof(PathJob)));
@@ -531,14 +541,24 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 		SWCK(cudaMalloc((void **)&d_cells, threads * cells_stride));
 		SWCK(cudaMalloc((void **)&d_sc, threads * 2 * sc_stride * sizeof(GScore)));
 		SWCK(cudaMemcpyAsync(d_pj, pj.data(), (size_t)n * sizeof(PathJob), cudaMemcpyHostToDevice, st));
+		cigars->resize((size_t)cig_total);
+	}
+	SWCK(cudaEventRecord(e0, st));
+	if (mode != 2) {
+		k_sw<<<blocks, 128, smem, st>>>(d_pac, d_jobs, n, d_q, d_res, len1_max, len2_max, d_cnt, d_sr);
+		SWCK(cudaGetLastError());
+	}
+	if (mode) {
 		k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(d_pac, d_pj, n, d_q, gap_end, band, mode == 1 ? d_res : nullptr, d_sr, d_pres,
 		                                                   d_cig, d_cells, cells_stride, d_sc, sc_stride, d_cnt + 1);
 		SWCK(cudaGetLastError());
-		cigars->resize((size_t)cig_total);
+	}
+	SWCK(cudaEventRecord(e1, st));
+	if (mode != 2 && res) SWCK(cudaMemcpyAsync(res, d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t), cudaMemcpyDeviceToHost, st));
+	if (mode) {
 		SWCK(cudaMemcpyAsync(pres, d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t), cudaMemcpyDeviceToHost, st));
 		if (cig_total) SWCK(cudaMemcpyAsync(cigars->data(), d_cig, (size_t)cig_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
 	}
-	SWCK(cudaEventRecord(e1, st));
 	SWCK(cudaStreamSynchronize(st));
 	{
 		float ms = 0;

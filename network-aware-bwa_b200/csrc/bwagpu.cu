@@ -153,7 +153,8 @@ struct Ctx {
 	PinBuf<int32_t> h_naln, h_maxent;
 	PinBuf<uint4> h_out;
 	PinBuf<int> h_counters;
-	// K4 / K5 staging
+	// K4 / K5 / K6 staging
+	SwScratch sw;
 	DevBuf<uint32_t> d_q, d_qo;
 	DevBuf<uint8_t> d_which;
 	// resident batch
@@ -198,7 +199,7 @@ extern "C" void bwa_gpu_destroy(void)
 		c->xent.release(); c->xnxt.release(); c->ctab.release(); c->x_free_next.release(); c->x_free_top.release();
 		c->h_seq.release(); c->h_meta.release(); c->h_naln.release(); c->h_maxent.release(); c->h_out.release();
 		c->h_counters.release();
-		c->d_q.release(); c->d_qo.release(); c->d_which.release();
+		c->d_q.release(); c->d_qo.release(); c->d_which.release(); c->sw.release();
 		for (auto &e : c->ev) if (e) cudaEventDestroy(e);
 		if (c->st) cudaStreamDestroy(c->st);
 		delete c;
@@ -1020,7 +1021,7 @@ static int sw_entry(int n, const bwa_gpu_sw_job_t *jobs, int mode, int gap_end, 
 	double ms = 0;
 	std::vector<bwa_gpu_sw_res_t> tmp;
 	if (mode == 1 && !res) { tmp.resize(n); res = tmp.data(); }
-	const int rc = sw_batch(c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &g_cigar_pool : nullptr, fail, &ms);
+	const int rc = sw_batch(c->sw, c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &g_cigar_pool : nullptr, fail, &ms);
 	c->stats.ms_sw_kernel = ms;
 	if (mode && cigar_pool) *cigar_pool = g_cigar_pool.data();
 	return rc;

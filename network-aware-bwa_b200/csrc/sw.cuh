@@ -460,9 +460,26 @@ __global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac,
 	}
 }
 
+// device buffers that survive between calls (cudaMalloc of the K6 scratch costs more than the kernels)
+struct SwScratch {
+	void *p[10] = {};
+	size_t cap[10] = {};
+	cudaError_t reserve(int k, size_t bytes)
+	{
+		if (bytes <= cap[k]) return cudaSuccess;
+		if (p[k]) cudaFree(p[k]);
+		p[k] = nullptr; cap[k] = 0;
+		const size_t want = bytes + bytes / 4 + 256;
+		const cudaError_t e = cudaMalloc(&p[k], want);
+		if (e == cudaSuccess) cap[k] = want;
+		return e;
+	}
+	void release() { for (int k = 0; k < 10; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; } }
+};
+
 // host launcher.  mode 0: K5 only (res); mode 1: K5 + third pass (pres, cigars); mode 2: plain banded global
 // alignment with (gap_end, band) (pres, cigars).
-static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n, const bwa_gpu_sw_job_t *jobs, int mode,
+static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n, const bwa_gpu_sw_job_t *jobs, int mode,
                     int gap_end, int band, bwa_gpu_sw_res_t *res, bwa_gpu_path_res_t *pres, std::vector<uint16_t> *cigars,
                     int (*fail)(const char *, ...), double *kernel_ms)
 {
@@ -496,14 +513,13 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	cudaError_t e;
 	auto cleanup = [&]() {
-		cudaFree(d_jobs); cudaFree(d_q); cudaFree(d_res); cudaFree(d_cnt); cudaFree(d_sr); cudaFree(d_pj); cudaFree(d_pres);
-		cudaFree(d_cig); cudaFree(d_cells); cudaFree(d_sc);
 		if (e0) cudaEventDestroy(e0);
 		if (e1) cudaEventDestroy(e1);
 	};
+#define SWALLOC(ptr, k, bytes) do { e = S.reserve(k, bytes); if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); } ptr = (decltype(ptr))S.p[k]; } while (0)
 #define SWCK(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return fail("%s: %s", #x, cudaGetErrorString(e)); } } while (0)
-	SWCK(cudaMalloc((void **)&d_q, hq.size()));
-	SWCK(cudaMalloc((void **)&d_cnt, 2 * sizeof(int)));
+	SWALLOC(d_q, 0, hq.size());
+	SWALLOC(d_cnt, 1, 2 * sizeof(int));
 	SWCK(cudaMemcpyAsync(d_q, hq.data(), hq.size(), cudaMemcpyHostToDevice, st));
 	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
 	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1));
@@ -517,9 +533,9 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 		const int q_words = (len2_max + 4) >> 2, r_words = (len1_max + 4) >> 2;
 		smem = (size_t)4 * (q_words + r_words + 2 * (len2_max + 1) + 4 * (len1_max + 2)) * sizeof(int);
 		if (smem > 200 * 1024) { cleanup(); return fail("window %d x read %d needs %zu B of shared memory per block", len1_max, len2_max, smem); }
-		SWCK(cudaMalloc((void **)&d_jobs, (size_t)n * sizeof(SwJob)));
-		SWCK(cudaMalloc((void **)&d_res, (size_t)n * sizeof(bwa_gpu_sw_res_t)));
-		SWCK(cudaMalloc((void **)&d_sr, (size_t)n * sizeof(int)));
+		SWALLOC(d_jobs, 2, (size_t)n * sizeof(SwJob));
+		SWALLOC(d_res, 3, (size_t)n * sizeof(bwa_gpu_sw_res_t));
+		SWALLOC(d_sr, 4, (size_t)n * sizeof(int));
 		SWCK(cudaMemcpyAsync(d_jobs, hj.data(), (size_t)n * sizeof(SwJob), cudaMemcpyHostToDevice, st));
 		SWCK(cudaFuncSetAttribute(k_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		int bps = 1;
@@ -535,11 +551,11 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 		threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
 		const size_t budget = (size_t)6 << 30;
 		if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
-		SWCK(cudaMalloc((void **)&d_pj, (size_t)n * sizeof(PathJob)));
-		SWCK(cudaMalloc((void **)&d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t)));
-		SWCK(cudaMalloc((void **)&d_cig, (size_t)cig_total * sizeof(uint16_t) + 16));
-		SWCK(cudaMalloc((void **)&d_cells, threads * cells_stride));
-		SWCK(cudaMalloc((void **)&d_sc, threads * 2 * sc_stride * sizeof(GScore)));
+		SWALLOC(d_pj, 5, (size_t)n * sizeof(PathJob));
+		SWALLOC(d_pres, 6, (size_t)n * sizeof(bwa_gpu_path_res_t));
+		SWALLOC(d_cig, 7, (size_t)cig_total * sizeof(uint16_t) + 16);
+		SWALLOC(d_cells, 8, threads * cells_stride);
+		SWALLOC(d_sc, 9, threads * 2 * sc_stride * sizeof(GScore));
 		SWCK(cudaMemcpyAsync(d_pj, pj.data(), (size_t)n * sizeof(PathJob), cudaMemcpyHostToDevice, st));
 		cigars->resize((size_t)cig_total);
 	}
@@ -566,6 +582,7 @@ static int sw_batch(cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n,
 		if (kernel_ms) *kernel_ms = ms;
 	}
 #undef SWCK
+#undef SWALLOC
 	cleanup();
 	if (mode != 2 && res)
 		for (int i = 0; i < n; ++i)

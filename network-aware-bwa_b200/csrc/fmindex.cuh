@@ -20,6 +20,9 @@
 //     j = (k == -1) ? 0 : (k >= primary ? k : k + 1)        0 <= j <= seq_len
 // Block j>>6 always exists because the array has (seq_len>>6)+1 blocks.
 #pragma once
+#ifndef BWAGPU_L2HINT
+#define BWAGPU_L2HINT 0 // 1: L2 evict_last policy on index loads (A/B switch)
+#endif
 #ifndef BWAGPU_LDG256
 #define BWAGPU_LDG256 1 // sm_100a has LDG.E.256; set to 0 for two LDG.128
 #endif
@@ -53,9 +56,18 @@ __device__ __forceinline__ OccBlock load_block(const DevIndex &ix, uint32_t b)
 	OccBlock o;
 #if BWAGPU_LDG256
 	uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+#if BWAGPU_L2HINT
+	// keep index sectors in L2 ahead of the streaming stack / width traffic
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+	             : "l"(p), "l"(pol));
+#else
 	asm volatile("ld.global.nc.L1::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
 	             : "l"(p));
+#endif
 	o.c0 = r0; o.c1 = r1; o.c2 = r2; o.c3 = r3;
 	o.lo = (uint64_t)r5 << 32 | r4;
 	o.hi = (uint64_t)r7 << 32 | r6;

@@ -238,6 +238,12 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #ifndef BWAGPU_PREFETCH_TOP
 #define BWAGPU_PREFETCH_TOP 0
 #endif
+#ifndef BWAGPU_STREAM_STACK
+#define BWAGPU_STREAM_STACK 0 // 1: stack records use streaming (evict-first) loads/stores (A/B switch)
+#endif
+#ifndef BWAGPU_BATCH_POP
+#define BWAGPU_BATCH_POP 0 // N > 0 (needs BWAGPU_CONVERGE=1): memory pops wait until N lanes of the warp want one
+#endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
 #endif
@@ -391,7 +397,11 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		if (STATS) ++n_stored;
 		const uint32_t idx = alloc_rec();
 		if (idx == NIL) return;
+#if BWAGPU_STREAM_STACK
+		__stcs(ent_at(idx), make_uint4(rk, rl, pos, tag));
+#else
 		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
+#endif
 		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
 		else { *nxt_at(idx) = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = idx; }
 		mask_set(s);
@@ -539,6 +549,20 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			}
 		}
 
+#if BWAGPU_BATCH_POP && BWAGPU_CONVERGE
+		{ // Phase batching: lanes are independent reads, so a lane may sit a trip out.  Popping a record from
+		  // memory is the expensive, minority path of the POP block; lanes that need it wait until enough
+		  // lanes of the warp need it too (or nobody else has work), so the path runs with more lanes and
+		  // most trips carry no second memory wait.
+			const bool is_pop = active && mode == MODE_POP;
+			const bool stopping = is_pop && (overflow || n_entries == 0 || n_entries > O.max_entries ||
+			                                 (!held_valid && !(mask0 | mask1 | mask2 | mask3)));
+			const bool mem_pop = is_pop && !stopping && !held_valid;
+			const unsigned mp = __ballot_sync(0xffffffffu, mem_pop);
+			const unsigned other = __ballot_sync(0xffffffffu, active && !mem_pop);
+			if (mem_pop && __popc(mp) < BWAGPU_BATCH_POP && other) active = false;
+		}
+#endif
 		if (active && mode == MODE_POP) {
 			bool stop = overflow || n_entries == 0;
 			if (!stop) {
@@ -558,7 +582,11 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 					}
 					const uint32_t idx = cur_head;
 					uint4 *const qp = ent_at(idx);
+#if BWAGPU_STREAM_STACK
+					const uint4 q = __ldcs(qp);
+#else
 					const uint4 q = *qp;
+#endif
 					const uint32_t nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
 					const uint32_t kind = (q.w >> 27) & 3u;
 					uint32_t gm = 0, b = 0;

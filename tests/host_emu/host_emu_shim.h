@@ -34,3 +34,8 @@ template <typename T, typename U> static inline T atomicMin(T *p, U v) { T o = *
 template <typename T, typename U> static inline T atomicMax(T *p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
 template <typename T> static inline T atomicCAS(T *p, T cmp, T val) { T o = *p; if (o == cmp) *p = val; return o; }
 static inline void __threadfence() {}
+template <typename T> static inline void __stcs(T *p, T v) { *p = v; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+static inline bool __all_sync(unsigned, bool p) { return p; }
+static inline void __syncwarp() {}

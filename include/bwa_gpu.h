@@ -227,13 +227,14 @@ int bwa_gpu_global_align(int n, const bwa_gpu_sw_job_t *jobs, int gap_end, int b
 typedef struct {
 	double ms_h2d, ms_width, ms_search, ms_compact, ms_d2h, ms_total_device;
 	double ms_host_marshal;
-	int64_t n_reads, n_aln, n_overflow_t2, n_overflow_t3;
+	int64_t n_reads, n_aln;
+	int64_t n_overflow_t2, n_overflow_t3; /* reads retried after pass 0 / after pass 1 */
 	int64_t occ_fetches_width, occ_fetches_search; /* filled only when stats are enabled */
 	int64_t own_fetches_width, own_fetches_search; /* 32-byte blocks this layout touched */
 	int64_t n_pops, n_pushes;
 	int32_t launches; /* kernels launched by the call */
 	int32_t n_devices;
-	double ms_tier[4]; /* k_search (+ its width refresh) per tier */
+	double ms_tier[4]; /* k_search (+ its width refresh) per pass: [0] private arenas, [1] shared chunk pool, [2] guaranteed */
 	int64_t n_stored;  /* records that reached the in-memory stack (stats builds) */
 	int64_t n_pruned, n_expand, n_exact, n_derive; /* pops pruned / nodes expanded / exact-tail steps / group-child derivations */
 	int64_t n_trips;          /* loop trips summed over threads (stats builds) */

@@ -3,8 +3,9 @@
 // One Ctx per CUDA device (its own stream, scratch arenas, pinned staging).  A batch call
 // splits the reads into contiguous per-device ranges (index replicated, no collective:
 // SURVEY.md §8e), each range into chunks, and runs per chunk
-//     H2D -> K2 width -> K3 search (tier 1 [-> tier 2 -> tier 3] for reads whose stack or
-//     hit list outgrew the tier) -> scan + gather (read-ordered aln pool) -> D2H.
+//     H2D -> K2 width -> K3 search (pass 0 on private arenas [-> pass 1 on the shared chunk pool ->
+//     pass 2 with guaranteed memory] for the reads whose search went deeper) -> scan + gather
+//     (read-ordered aln pool) -> D2H.
 // There is no CPU fallback: without a usable device every entry point returns an error.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
@@ -105,7 +106,7 @@ template <typename T> struct PinBuf {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct Tier {
+struct Pass { // per-pass scratch of k_search
 	uint32_t cap, slots_blocks, ctab_stride; // slots = blocks * 128
 	DevBuf<uint4> ent;
 	DevBuf<uint32_t> nxt, heads;
@@ -139,10 +140,10 @@ struct Ctx {
 	DevBuf<uint8_t> d_keys, d_keys2;
 	DevBuf<uint32_t> d_pooloff, d_outoff;
 	DevBuf<uint4> d_pool, d_out;
-	DevBuf<int> d_counters;            // [0] work [1] overflow [2] pool_count(u32)
-	DevBuf<unsigned long long> d_stats; // 4
+	DevBuf<int> d_counters;            // [0] work [1] retry-list length [2] hit-pool fill (u32) [3] chunk-pool bump
+	DevBuf<unsigned long long> d_stats; // 16 counters of the STATS kernels (kernels.cuh: Batch::stats)
 	DevBuf<uint8_t> d_cubtmp;
-	Tier tier[3];
+	Pass pass_buf[3];
 	DevBuf<uint4> xent;           // shared overflow pool of this lane (records)
 	DevBuf<uint32_t> xnxt, ctab, x_free_next;
 	DevBuf<unsigned long long> x_free_top;
@@ -195,7 +196,7 @@ extern "C" void bwa_gpu_destroy(void)
 		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release(); c->d_ids.release(); c->d_order.release(); c->d_keys.release(); c->d_keys2.release();
 		c->d_pooloff.release(); c->d_outoff.release(); c->d_pool.release(); c->d_out.release();
 		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
-		for (Tier &t : c->tier) { t.ent.release(); t.nxt.release(); t.heads.release(); }
+		for (Pass &t : c->pass_buf) { t.ent.release(); t.nxt.release(); t.heads.release(); }
 		c->xent.release(); c->xnxt.release(); c->ctab.release(); c->x_free_next.release(); c->x_free_top.release();
 		c->h_seq.release(); c->h_meta.release(); c->h_naln.release(); c->h_maxent.release(); c->h_out.release();
 		c->h_counters.release();
@@ -357,16 +358,16 @@ extern "C" int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac)
 extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
 
 // ------------------------------------------------------------------ device pipeline for one resident chunk
-static const int N_TIERS = 3;
+static const int N_PASSES = 3;
 
 // Pass 0: private arenas only (BWAGPU_T1_CAP records per thread).  Pass 1 (optimistic, pooled): every resident thread has a small private arena (BWAGPU_T1_CAP records, shared by
 // the search stack and the read's hit list) and takes more from a shared pool of 1024-record chunks when a search goes deep; the pool is
 // bump-allocated within a launch, so it can run dry -- the reads it fails are retried from scratch in pass 1 (guaranteed): few enough threads
 // that each can own opt->max_entries + 16 records, which the search can never exceed (bwtgap.c:140
 // stops it first).
-static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt)
+static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt)
 {
-	Tier &T = c->tier[t];
+	Pass &T = c->pass_buf[t];
 	// the shared pool: BWAGPU_POOL_MB (default 16384) per lane, never more than a quarter of what is free
 	if (!c->xent.p) {
 		size_t free_b = 0, total_b = 0;
@@ -421,7 +422,7 @@ static int tier_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	return 0;
 }
 
-// Runs K2 + K3(+tiers) + ordered compaction on a chunk whose seq/meta are on the device.
+// Runs K2 + K3 (all passes) + ordered compaction on a chunk whose seq/meta are on the device.
 // On return (stream synchronised): d_naln, d_maxent, d_outoff (exclusive scan), d_out
 // hold the results, *total_aln the pool size.
 static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, uint32_t n_stacks, int64_t *total_aln)
@@ -485,7 +486,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		CK(cudaStreamSynchronize(c->st));
 	}
 
-	// job order for tier 0: longest-looking searches first (k_job_keys)
+	// job order for pass 0: longest-looking searches first (k_job_keys)
 	const int32_t *jobs = nullptr;
 	{
 		const char *env = getenv("BWAGPU_SORT_JOBS");
@@ -503,13 +504,13 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	}
 	CK(cudaEventRecord(c->ev[2], c->st)); // the sort is accounted to the width phase
 
-	// K3, tier by tier
+	// K3, pass by pass
 	int n_jobs = n;
 	for (int pass = 0; n_jobs > 0; ++pass) {
-		const int t = pass < N_TIERS ? pass : N_TIERS - 1;
+		const int t = pass < N_PASSES ? pass : N_PASSES - 1;
 		if (pass > 8) return fail("%d reads still unfinished after %d passes", n_jobs, pass);
-		if (tier_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
-		Tier &T = c->tier[t];
+		if (pass_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
+		Pass &T = c->pass_buf[t];
 		B.ent = T.ent.p; B.nxt = T.nxt.p; B.heads = T.heads.p;
 		B.cap = T.cap;
 		B.xent = c->xent.p; B.xnxt = c->xnxt.p; B.ctab = c->ctab.p; B.ctab_stride = T.ctab_stride;

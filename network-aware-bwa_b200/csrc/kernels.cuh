@@ -77,7 +77,7 @@ struct Batch {
 	uint32_t *w;       // width arena: w values (only gap_shadow reads them back)
 	uint16_t *bid;     // width arena: bid | (w[i-1] == w[i]) << 15 -- all the pruning tests need
 	// results, per read
-	int32_t *n_aln;       // -1 = not done (overflow -> next tier)
+	int32_t *n_aln;       // -1 = not done (ran out of arena / pool: retried in the next pass)
 	int32_t *max_entries;
 	uint32_t *pool_off;   // offset of the read's alns in the unordered pool
 	uint4 *pool;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 	const int job = t >> 2;
 	uint32_t f_ref = 0, f_own = 0;
 	if (job < B.n_jobs) {
-		// later tiers recompute the widths of their reads: gap_shadow (bwtgap.c:81-91) edited
+		// later passes recompute the widths of their reads: gap_shadow (bwtgap.c:81-91) edited
 		// them in place during the attempt that overflowed
 		const int r = B.jobs ? B.jobs[job] : job;
 		const ReadMeta m = B.meta[r];
@@ -200,9 +200,16 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 //   * PHANTOMS: once the first hit fixed best_score, children scoring above best_score +
 //     s_mm can only ever end the search when popped (bwtgap.c:144); they are counted but
 //     not stored;
-//   * the arena slot freed by the latest pop is kept in a register for the next push.
+//   * the arena slot freed by the latest pop is kept in a register for the next push;
+//   * the read's HITS are records of the same arena, chained in discovery order (the duplicate
+//     test of bwtgap.c:179-183 walks the chain), so a read may have any number of them.
 // n_entries counts every child individually, stored or not, so max_entries and the
 // `> opt->max_entries` stop (bwtgap.c:139-140) are the reference's.
+//
+// Memory: a small private arena per thread; when a search outgrows it, the arena continues in
+// 1024-record chunks of a pool shared by the launch (POOLED instantiation; chunks are recycled
+// through a lock-free stack when the read ends).  Reads that run out of arena (pass 0) or find
+// the pool dry (pass 1) are flagged and retried from scratch by the next pass (bwagpu.cu).
 //
 // The per-thread control flow is a small state machine so that the lanes of a warp meet
 // at ONE occurrence lookup per trip whatever each lane is doing (expanding a node,

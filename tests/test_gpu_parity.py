@@ -289,3 +289,36 @@ def test_mate_sw_path_and_global_align_match_golden(golden, gpu_index):
         got = api.global_align(jobs, ge, band)
         for g, i in zip(got, sel):
             assert tuple(g[:5]) == tuple(golden["glob_out"][i]) and np.array_equal(g[5], golden["glob_cigar"][co[i]:co[i + 1]]), (i, ge, band)
+
+
+def test_argument_errors_are_loud(gpu_index):
+    """Unsupported inputs fail with a message instead of computing something else."""
+    T, idx = gpu_index
+    opt = abi.default_gap_opt()
+    long_read = np.zeros(40000, dtype=np.uint8)
+    with pytest.raises(api.BwaGpuError, match="read length"):
+        api.aln_flat(long_read, np.array([0, long_read.size], dtype=np.int64), opt)
+    big = abi.default_gap_opt(fnr=-1.0, max_diff=300)
+    with pytest.raises(api.BwaGpuError, match="not supported|exceeds"):
+        api.aln_flat(T[:50].copy(), np.array([0, 50], dtype=np.int64), big)
+    wide = abi.default_gap_opt(s_mm=40, s_gapo=90, s_gape=30)
+    with pytest.raises(api.BwaGpuError, match="buckets"):
+        api.aln_flat(T[:50].copy(), np.array([0, 50], dtype=np.int64), wide)
+    with pytest.raises(api.BwaGpuError, match="out of range"):
+        api.cal_pac_pos(np.array([idx.bwt[0].seq_len + 5], dtype=np.uint32), np.array([1], dtype=np.uint8))
+    # an empty batch is fine
+    n_aln, me, off, aln = api.aln_flat(np.zeros(0, np.uint8), np.zeros(1, np.int64), opt)
+    assert n_aln.size == 0 and off.tolist() == [0] and aln.size == 0
+    assert api.cal_pac_pos(np.zeros(0, np.uint32), np.zeros(0, np.uint8)).size == 0
+
+
+def test_many_buckets_option_set(gpu_index):
+    """More than 128 score buckets (4 mask words in k_search): -M 5 -O 20 -E 8 with -n 6."""
+    T, idx = gpu_index
+    if not R.have_ref():
+        pytest.skip("oracle/_ref not present")
+    reads = R.bwa.simulate.simulate_reads(T, 3000, 60, seed=66)
+    opt = abi.default_gap_opt(s_mm=5, s_gapo=20, s_gape=8, fnr=-1.0, max_diff=6, max_gapo=2)
+    want = R.ref_aln(R.RefIndex(idx), reads, opt, threads=8)
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    assert R.compare_aln(want, got, "many buckets") == []

@@ -693,7 +693,7 @@ static int run_range(Ctx *c, FlatJob &J)
 					const int len = J.seqs ? (int)J.seqs[r0 + i].len : (int)(J.offs[r0 + i + 1] - J.offs[r0 + i]);
 					if (len < 0 || len > 32766) { bad_t[tid] = len; return; }
 					so_of[i + 1] = (uint64_t)len;
-					wo_of[i + 1] = len > 0 ? 2 * (uint64_t)(len + 1) + (len > opt->seed_len ? 2 * (uint64_t)(opt->seed_len + 1) : 0) : 0;
+					wo_of[i + 1] = width_entries(len, opt->seed_len);
 					if (len > max_t[tid]) max_t[tid] = len;
 				}
 			});

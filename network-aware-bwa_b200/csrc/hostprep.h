@@ -51,6 +51,12 @@ static inline GapOpt to_gapopt(const gap_opt_t *o)
 	return g;
 }
 
+// width-arena entries of one read: [w0 | w1 | seed_w0 | seed_w1], each padded to 8 entries (WSTRIDE)
+static inline uint64_t width_entries(int len, int seed_len)
+{
+	return len > 0 ? 2 * (uint64_t)WSTRIDE(len) + (len > seed_len ? 2 * (uint64_t)WSTRIDE(seed_len) : 0) : 0;
+}
+
 // per-read meta (max_diff, clamped max_gapo: bwtaln.c:102-103 with n_seqs = 1) + offsets
 static inline int fill_meta(int len, uint64_t seq_off, uint64_t w_off, const gap_opt_t *opt, MaxDiffTable &mdt, ReadMeta &m,
                      uint64_t &w_entries, uint32_t &n_stacks)
@@ -70,7 +76,7 @@ static inline int fill_meta(int len, uint64_t seq_off, uint64_t w_off, const gap
 	m.max_diff = (uint8_t)md;
 	m.max_gapo = (uint8_t)go;
 	m.n_amb = 0; // filled by pack_*
-	w_entries = len > 0 ? 2 * (uint64_t)(len + 1) + (len > opt->seed_len ? 2 * (uint64_t)(opt->seed_len + 1) : 0) : 0;
+	w_entries = width_entries(len, opt->seed_len);
 	return 0;
 }
 

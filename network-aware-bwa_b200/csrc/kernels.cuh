@@ -12,6 +12,8 @@ namespace bwagpu {
 #define NIL 0xffffffffu
 #define WB_EQ 0x8000u
 #define WB_BID 0x7fffu
+// width sub-arrays start on 8-entry boundaries so that K2 can flush them with 16/32-byte stores
+#define WSTRIDE(n) ((((size_t)(n) + 1) + 7) & ~(size_t)7)
 #define ARENA_CHUNK_LOG 10
 #define ARENA_CHUNK (1u << ARENA_CHUNK_LOG)
 
@@ -146,30 +148,45 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 		if (len > 0 && (!seed || has_seed)) {
 			const int n = seed ? B.opt.seed_len : len;
 			const uint8_t *s = B.seq + m.seq_off + (seed ? len - n : 0);
-			const size_t wo = (size_t)m.w_off + (seed ? 2 * (size_t)(len + 1) + (size_t)a * (n + 1) : (size_t)a * (len + 1));
+			const size_t wo = (size_t)m.w_off + (seed ? 2 * WSTRIDE(len) + (size_t)a * WSTRIDE(n) : (size_t)a * WSTRIDE(len));
 			uint32_t *w = B.w + wo;
 			uint16_t *bd = B.bid + wo;
 			const DevIndex &ix = B.ix[a];
 			uint32_t k = 0, l = ix.seq_len;
 			uint32_t bid = 0, prev_w = 0;
-			for (int i = 0; i < n; ++i) {
-				const uint32_t c = (s[i] >> (a << 2)) & 15u;
-				if (c < 4) {
-					uint32_t ok, ol;
-					occ1_pair<STATS>(ix, k - 1, l, c, ok, ol, f_ref, f_own);
-					k = ix.L2[c] + ok + 1;
-					l = ix.L2[c] + ol;
+			// results are collected 8 at a time and flushed as one 32-byte (w) and one 16-byte (wb)
+			// store: a 4- or 2-byte store per step costs a whole sector of L2 write bandwidth each
+			uint32_t wq[8], bq[4];
+			for (int i0 = 0; i0 <= n; i0 += 8) {
+#pragma unroll
+				for (int t = 0; t < 8; ++t) {
+					const int i = i0 + t;
+					uint32_t wi = 0, bv = 0;
+					if (i < n) {
+						const uint32_t c = (s[i] >> (a << 2)) & 15u;
+						if (c < 4) {
+							uint32_t ok, ol;
+							occ1_pair<STATS>(ix, k - 1, l, c, ok, ol, f_ref, f_own);
+							k = ix.L2[c] + ok + 1;
+							l = ix.L2[c] + ol;
+						}
+						if (k > l || c > 3) { // restart
+							k = 0; l = ix.seq_len; ++bid;
+						}
+						wi = l - k + 1;
+						bv = bid | ((i > 0 && wi == prev_w) ? WB_EQ : 0u); // bid | (w[i-1] == w[i]) << 15
+						prev_w = wi;
+					} else if (i == n) { // the terminator entry (bwtaln.c:73-74)
+						wi = 0;
+						bv = (bid + 1) | (prev_w == 0 ? WB_EQ : 0u);
+					}
+					wq[t] = wi;
+					if (t & 1) bq[t >> 1] |= bv << 16; else bq[t >> 1] = bv;
 				}
-				if (k > l || c > 3) { // restart
-					k = 0; l = ix.seq_len; ++bid;
-				}
-				const uint32_t wi = l - k + 1;
-				w[i] = wi;
-				bd[i] = (uint16_t)(bid | ((i > 0 && wi == prev_w) ? WB_EQ : 0u)); // bid | (w[i-1] == w[i]) << 15
-				prev_w = wi;
+				*reinterpret_cast<uint4 *>(w + i0) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+				*reinterpret_cast<uint4 *>(w + i0 + 4) = make_uint4(wq[4], wq[5], wq[6], wq[7]);
+				*reinterpret_cast<uint4 *>(bd + i0) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
 			}
-			w[n] = 0;
-			bd[n] = (uint16_t)((bid + 1) | (prev_w == 0 ? WB_EQ : 0u));
 		}
 	}
 	if (STATS) {
@@ -462,8 +479,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array, then refresh
 			// the packed (bid, w[t-1]==w[t]) view of the positions it may have changed
 			const uint32_t a = E_A(e);
-			uint32_t *w = w_base + (size_t)a * (len + 1);
-			uint16_t *wb = wb_base + (size_t)a * (len + 1);
+			uint32_t *w = w_base + (size_t)a * WSTRIDE(len);
+			uint16_t *wb = wb_base + (size_t)a * WSTRIDE(len);
 			const uint32_t x = hl - hk + 1, mx = B.ix[1 - a].seq_len;
 			const int ldp = E_LDP(e);
 			uint32_t j = 0, prev = 0;
@@ -653,7 +670,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			}
 #endif
 			if (fresh) {
-				const uint16_t *wb = wb_base + (size_t)a * (len + 1);
+				const uint16_t *wb = wb_base + (size_t)a * WSTRIDE(len);
 				wb1 = i >= 1 ? wb[i - 1] : 0u;
 				wb2 = i >= 2 ? wb[i - 2] : 0u;
 				c1 = i >= 1 ? (uint32_t)(seq[i - 1] >> (a << 2)) & 15u : 0u;
@@ -661,7 +678,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				if (has_seed) {
 					const int si = (i - 1) - (len - O.seed_len);
 					if (si >= 1) {
-						const uint16_t *swb = wb_base + 2 * (size_t)(len + 1) + (size_t)a * (O.seed_len + 1);
+						const uint16_t *swb = wb_base + 2 * WSTRIDE(len) + (size_t)a * WSTRIDE(O.seed_len);
 						sw1 = swb[si]; sw2 = swb[si - 1];
 					}
 				}
@@ -832,7 +849,7 @@ __global__ void k_job_keys(const Batch B, uint8_t *__restrict__ keys, int32_t *_
 	uint32_t key = 255;
 	if (m.len > 0) {
 		const uint16_t *wb = B.bid + m.w_off;
-		const uint32_t d0 = wb[m.len - 1] & WB_BID, d1 = wb[(size_t)(m.len + 1) + m.len - 1] & WB_BID;
+		const uint32_t d0 = wb[m.len - 1] & WB_BID, d1 = wb[WSTRIDE(m.len) + m.len - 1] & WB_BID;
 		const uint32_t d = d0 < d1 ? d0 : d1, md = m.max_diff;
 		key = (d >= 1 && d <= md) ? md - d : md + 1 + (d == 0 ? 0u : 1u);
 	}

@@ -11,12 +11,14 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -152,6 +154,7 @@ struct Ctx {
 	PinBuf<uint8_t> h_seq;
 	PinBuf<ReadMeta> h_meta;
 	PinBuf<int32_t> h_naln, h_maxent;
+	PinBuf<uint32_t> h_pooloff;
 	PinBuf<uint4> h_out;
 	PinBuf<int> h_counters;
 	// K4 / K5 / K6 staging
@@ -198,7 +201,7 @@ extern "C" void bwa_gpu_destroy(void)
 		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
 		for (Pass &t : c->pass_buf) { t.ent.release(); t.nxt.release(); t.heads.release(); }
 		c->xent.release(); c->xnxt.release(); c->ctab.release(); c->x_free_next.release(); c->x_free_top.release();
-		c->h_seq.release(); c->h_meta.release(); c->h_naln.release(); c->h_maxent.release(); c->h_out.release();
+		c->h_seq.release(); c->h_meta.release(); c->h_naln.release(); c->h_maxent.release(); c->h_pooloff.release(); c->h_out.release();
 		c->h_counters.release();
 		c->d_q.release(); c->d_qo.release(); c->d_which.release(); c->sw.release();
 		for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -404,9 +407,15 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	} else {
 		// guaranteed: threads x (chunks one search may need) <= pool
 		const uint32_t per_thread = (need + ARENA_CHUNK - 1) >> ARENA_CHUNK_LOG;
+		if (c->x_chunks < per_thread * 128u) { // a pool configured too small for one block of full-depth searches: grow it
+			const size_t chunks = (size_t)per_thread * 128u;
+			c->xent.release(); c->xnxt.release(); c->x_free_next.release();
+			if (c->xent.reserve(chunks << ARENA_CHUNK_LOG) || c->xnxt.reserve(chunks << ARENA_CHUNK_LOG) || c->x_free_next.reserve(chunks + 1))
+				return 1;
+			c->x_chunks = (uint32_t)chunks;
+		}
 		uint32_t threads = c->x_chunks / std::max(1u, per_thread);
 		if (threads > 4096) threads = 4096;
-		if (threads < 128) return fail("overflow pool (%u chunks) too small for the guaranteed pass (%u chunks per search); raise BWAGPU_POOL_MB or lower -m", c->x_chunks, per_thread);
 		T.slots_blocks = std::max(1u, threads / 128);
 		T.cap = 1024;
 	}
@@ -425,7 +434,8 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 // Runs K2 + K3 (all passes) + ordered compaction on a chunk whose seq/meta are on the device.
 // On return (stream synchronised): d_naln, d_maxent, d_outoff (exclusive scan), d_out
 // hold the results, *total_aln the pool size.
-static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, uint32_t n_stacks, int64_t *total_aln)
+static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, uint32_t n_stacks, int64_t *total_aln,
+                            bool device_compact)
 {
 	const bool stats = g_stats_enabled;
 	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1)) return 1;
@@ -599,6 +609,18 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		c->stats.ns_kernel = (int64_t)(hs[13] - hs[12]);
 	}
 
+	if (!device_compact) {
+		// Chunked host path: the hits stay in completion order; the host reads pool_off[] and puts them in
+		// read order while it unpacks.  No kernel after k_search: a small kernel of this lane would have to
+		// wait for SM slots behind another lane's persistent k_search, and the lanes would fall into step.
+		CK(cudaEventRecord(c->ev[4], c->st));
+		CK(cudaStreamSynchronize(c->st));
+		float ms0 = 0;
+		CK(cudaEventElapsedTime(&ms0, c->ev[1], c->ev[2])); c->stats.ms_width += ms0;
+		CK(cudaEventElapsedTime(&ms0, c->ev[2], c->ev[3])); c->stats.ms_search += ms0;
+		*total_aln = (int64_t)std::min<size_t>((size_t)(unsigned int)c->h_counters.p[2], pool_cap); // hit-pool fill
+		return 0;
+	}
 	// ordered compaction: exclusive scan of n_aln (n+1 items so that out_off[n] = total)
 	CK(cudaMemsetAsync(c->d_naln.p + n, 0, sizeof(int32_t), c->st));
 	size_t tmp_bytes = 0;
@@ -626,6 +648,10 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 }
 
 // ------------------------------------------------------------------ flat batch on one device
+// The reads one DEVICE handles in a batch call, cut into chunks that the device's lanes pull from a
+// shared queue.  The first chunks are deliberately unequal (1/L, 2/L, ... of a chunk for L lanes) so
+// that the lanes fall out of step at once: while one lane packs or unpacks, another has its kernels
+// on the device.
 struct FlatJob {
 	int n = 0;
 	const uint8_t *bases = nullptr;      // flat API: sequencing orientation
@@ -633,9 +659,13 @@ struct FlatJob {
 	bwa_seq_t *seqs = nullptr;           // struct API instead
 	const gap_opt_t *opt = nullptr;
 	int32_t *n_aln = nullptr, *max_entries = nullptr;
-	std::vector<uint4> pool;             // read-ordered alns of this range
-	int rc = 0;
+	std::vector<std::pair<size_t, int>> chunks;   // (first read, reads)
+	std::vector<std::vector<uint4>> pools;        // flat API: read-ordered alns of each chunk
+	std::atomic<int> next{0}, failed{0};
+	std::mutex err_mu;
 	std::string err;
+	FlatJob() {}
+	FlatJob(const FlatJob &) = delete;
 };
 
 // Host-side helper threads of one lane: packing reads and handing results back are embarrassingly
@@ -677,10 +707,12 @@ static int run_range(Ctx *c, FlatJob &J)
 	const gap_opt_t *opt = J.opt;
 	const GapOpt gopt = to_gapopt(opt);
 	MaxDiffTable mdt;
-	const size_t CH = chunk_reads();
-	J.pool.clear();
-	for (size_t r0 = 0; r0 < (size_t)J.n; r0 += CH) {
-		const int n = (int)std::min(CH, (size_t)J.n - r0);
+	for (;;) {
+		const int ci = J.next.fetch_add(1);
+		if (ci >= (int)J.chunks.size() || J.failed.load()) break;
+		const size_t r0 = J.chunks[ci].first;
+		const int n = J.chunks[ci].second;
+		std::vector<uint4> &pool_out = J.pools[ci];
 		auto t0 = std::chrono::steady_clock::now();
 		// ---- marshal, pass 1 (serial, cheap): lengths -> offsets into the packed arrays
 		std::vector<uint64_t> so_of(n + 1), wo_of(n + 1);
@@ -747,14 +779,15 @@ static int run_range(Ctx *c, FlatJob &J)
 		CK(cudaEventRecord(c->ev[0], c->st));
 		CK(cudaMemcpyAsync(c->d_seq.p, c->h_seq.p, n_bases, cudaMemcpyHostToDevice, c->st));
 		CK(cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, (size_t)n * sizeof(ReadMeta), cudaMemcpyHostToDevice, c->st));
-		int64_t tot = 0;
-		if (run_chunk_device(c, n, (size_t)wo, gopt, n_stacks, &tot)) return 1;
+		int64_t tot = 0; // hit-pool fill: records to copy back (completion order)
+		if (run_chunk_device(c, n, (size_t)wo, gopt, n_stacks, &tot, false)) return 1;
 		// ---- D2H
-		if (c->h_naln.reserve(n) || c->h_maxent.reserve(n) || c->h_out.reserve((size_t)tot + 1)) return 1;
+		if (c->h_naln.reserve(n) || c->h_maxent.reserve(n) || c->h_pooloff.reserve(n) || c->h_out.reserve((size_t)tot + 1)) return 1;
 		CK(cudaEventRecord(c->ev[5], c->st));
 		CK(cudaMemcpyAsync(c->h_naln.p, c->d_naln.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaMemcpyAsync(c->h_maxent.p, c->d_maxent.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
-		if (tot) CK(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, c->st));
+		CK(cudaMemcpyAsync(c->h_pooloff.p, c->d_pooloff.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+		if (tot) CK(cudaMemcpyAsync(c->h_out.p, c->d_pool.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaEventRecord(c->ev[6], c->st));
 		CK(cudaStreamSynchronize(c->st));
 		float ms = 0;
@@ -762,18 +795,20 @@ static int run_range(Ctx *c, FlatJob &J)
 		CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->stats.ms_d2h += ms;
 		CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6])); c->stats.ms_total_device += ms;
 		auto t2 = std::chrono::steady_clock::now();
+		if (getenv("BWAGPU_TRACE")) {
+			static const auto T0 = std::chrono::steady_clock::now();
+			auto ms = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(t - T0).count(); };
+			fprintf(stderr, "[trace] lane %d.%d chunk %d (%d reads): pack %.0f-%.0f device %.0f-%.0f\n", c->dev, c->lane, ci, n, ms(t0), ms(t1), ms(t1), ms(t2));
+		}
 		memcpy(J.n_aln + r0, c->h_naln.p, (size_t)n * 4);
 		memcpy(J.max_entries + r0, c->h_maxent.p, (size_t)n * 4);
 		if (J.seqs) { // struct API: hand the hits back the way bwa_cal_sa_reg_gap does
-			std::vector<int64_t> aoff(n + 1);
-			aoff[0] = 0;
-			for (int i = 0; i < n; ++i) aoff[i + 1] = aoff[i] + c->h_naln.p[i];
 			std::vector<int> rc_t(64, 0);
 			parallel_for(n, [&](int lo, int hi, int tid) {
 			for (int i = lo; i < hi; ++i) {
 				bwa_seq_t *p = J.seqs + r0 + i;
 				const int na = c->h_naln.p[i];
-				const uint4 *src = c->h_out.p + aoff[i];
+				const uint4 *src = c->h_out.p + c->h_pooloff.p[i];
 				// bwtaln.c:113 resets these before the search
 				p->sa = 0; p->type = 0 /* BWA_TYPE_NO_MATCH */; p->c1 = p->c2 = 0;
 				p->n_aln = na;
@@ -790,42 +825,80 @@ static int run_range(Ctx *c, FlatJob &J)
 			}
 			});
 			for (int t = 0; t < 64; ++t) if (rc_t[t]) return fail("calloc failed");
-		} else {
-			const size_t base = J.pool.size();
-			J.pool.resize(base + (size_t)tot);
-			if (tot) memcpy(J.pool.data() + base, c->h_out.p, (size_t)tot * 16);
+		} else { // flat API: read order
+			std::vector<int64_t> aoff(n + 1);
+			aoff[0] = 0;
+			for (int i = 0; i < n; ++i) aoff[i + 1] = aoff[i] + c->h_naln.p[i];
+			pool_out.resize((size_t)aoff[n]);
+			parallel_for(n, [&](int lo, int hi, int) {
+				for (int i = lo; i < hi; ++i)
+					if (c->h_naln.p[i]) memcpy(pool_out.data() + aoff[i], c->h_out.p + c->h_pooloff.p[i], (size_t)c->h_naln.p[i] * 16);
+			});
 		}
 		auto t3 = std::chrono::steady_clock::now();
+		if (getenv("BWAGPU_TRACE")) fprintf(stderr, "[trace] lane %d.%d chunk %d unpack %.0f ms\n", c->dev, c->lane, ci, std::chrono::duration<double, std::milli>(t3 - t2).count());
 		c->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t3 - t2).count();
 		c->stats.n_reads += n;
-		c->stats.n_aln += tot;
+		for (int i = 0; i < n; ++i) c->stats.n_aln += c->h_naln.p[i];
 	}
 	return 0;
 }
 
-// splits [0,n) over the devices, one host thread per device
+// splits [0,n) over the devices, cuts each device's range into chunks, one host thread per lane
 static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *seqs, const gap_opt_t *opt,
-                   int32_t *n_aln, int32_t *max_entries, std::vector<FlatJob> &jobs)
+                   int32_t *n_aln, int32_t *max_entries, std::vector<std::unique_ptr<FlatJob>> &jobs)
 {
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
-	const int nd = (int)g_ctx.size();
-	jobs.assign(nd, FlatJob());
+	std::vector<Ctx *> owners;
+	for (Ctx *c : g_ctx) if (!c->owner) owners.push_back(c);
+	const int nd = (int)owners.size();
+	jobs.clear();
 	for (Ctx *c : g_ctx) { c->stats = bwa_gpu_stats_t(); c->stats.n_devices = nd; }
+	const size_t CH = chunk_reads();
 	std::vector<std::thread> th;
 	for (int d = 0; d < nd; ++d) {
 		const int64_t lo = (int64_t)n * d / nd, hi = (int64_t)n * (d + 1) / nd;
-		FlatJob &J = jobs[d];
+		jobs.emplace_back(new FlatJob());
+		FlatJob &J = *jobs.back();
 		J.n = (int)(hi - lo);
 		J.opt = opt;
 		J.n_aln = n_aln + lo; J.max_entries = max_entries + lo;
 		if (seqs) J.seqs = seqs + lo;
 		else { J.bases = bases; J.offs = offs + lo; }
-		if (nd == 1) { J.rc = run_range(g_ctx[d], J); if (J.rc) J.err = t_err; }
-		else th.emplace_back([d, &jobs]() { FlatJob &Jd = jobs[d]; Jd.rc = run_range(g_ctx[d], Jd); if (Jd.rc) Jd.err = t_err; });
+		std::vector<Ctx *> lanes;
+		for (Ctx *c : g_ctx) if (c == owners[d] || c->owner == owners[d]) lanes.push_back(c);
+		const size_t L = lanes.size();
+		// ramp up (the device starts working after a short first pack) and ramp down (a short last unpack)
+		const size_t floor_sz = std::min<size_t>(CH, 65536);
+		std::vector<size_t> tail_sizes; // sizes of the last chunks, outermost last
+		for (size_t k = 0, left = (size_t)J.n / 2; k < L && left > 0; ++k) {
+			const size_t m = std::min(left, std::max<size_t>(CH * (k + 1) / (L + 1), floor_sz));
+			tail_sizes.push_back(m); left -= m;
+		}
+		size_t tail_total = 0;
+		for (size_t m : tail_sizes) tail_total += m;
+		for (size_t r0 = 0, k = 0; r0 < (size_t)J.n - tail_total; ++k) {
+			const size_t want = k < L ? std::max<size_t>(CH * (k + 1) / (L + 1), floor_sz) : CH;
+			const size_t m = std::min(want, (size_t)J.n - tail_total - r0);
+			J.chunks.emplace_back(r0, (int)m);
+			r0 += m;
+		}
+		for (size_t k = tail_sizes.size(), r0 = (size_t)J.n - tail_total; k-- > 0;) {
+			J.chunks.emplace_back(r0, (int)tail_sizes[k]);
+			r0 += tail_sizes[k];
+		}
+		J.pools.resize(J.chunks.size());
+		for (Ctx *c : lanes)
+			th.emplace_back([c, &J]() {
+				if (run_range(c, J)) {
+					std::lock_guard<std::mutex> g(J.err_mu);
+					if (!J.failed.exchange(1)) J.err = t_err;
+				}
+			});
 	}
 	for (auto &t : th) t.join();
 	for (int d = 0; d < nd; ++d)
-		if (jobs[d].rc) return fail("device %d: %s", g_ctx[d]->dev, jobs[d].err.c_str());
+		if (jobs[d]->failed.load()) return fail("device %d: %s", owners[d]->dev, jobs[d]->err.c_str());
 	return 0;
 }
 
@@ -834,17 +907,15 @@ extern "C" int bwa_gpu_aln_flat(int n, const uint8_t *bases, const int64_t *offs
 {
 	std::lock_guard<std::mutex> g(g_mu);
 	if (n < 0 || !opt || !n_aln || !max_entries || !aln_off || !aln_pool) return fail("bwa_gpu_aln_flat: bad argument");
-	std::vector<FlatJob> jobs;
+	std::vector<std::unique_ptr<FlatJob>> jobs;
 	if (run_all(n, bases, offs, nullptr, opt, n_aln, max_entries, jobs)) return 1;
 	int64_t acc = 0;
 	for (int i = 0; i < n; ++i) { aln_off[i] = acc; acc += n_aln[i]; }
 	aln_off[n] = acc;
-	if (jobs.size() == 1) g_flat_pool.swap(jobs[0].pool);
-	else {
-		g_flat_pool.clear();
-		g_flat_pool.reserve((size_t)acc);
-		for (auto &J : jobs) g_flat_pool.insert(g_flat_pool.end(), J.pool.begin(), J.pool.end());
-	}
+	g_flat_pool.clear();
+	g_flat_pool.reserve((size_t)acc);
+	for (auto &J : jobs) // devices in read order, chunks in read order
+		for (auto &P : J->pools) g_flat_pool.insert(g_flat_pool.end(), P.begin(), P.end());
 	if ((int64_t)g_flat_pool.size() != acc) return fail("internal: pool size %zu != %lld", g_flat_pool.size(), (long long)acc);
 	*aln_pool = (const bwt_aln1_t *)g_flat_pool.data();
 	return 0;
@@ -855,7 +926,7 @@ extern "C" int bwa_gpu_cal_sa_reads_gap(int n_seqs, bwa_seq_t *seqs, const gap_o
 	std::lock_guard<std::mutex> g(g_mu);
 	if (n_seqs < 0 || !opt || (n_seqs && !seqs)) return fail("bwa_gpu_cal_sa_reads_gap: bad argument");
 	std::vector<int32_t> n_aln(n_seqs), max_entries(n_seqs);
-	std::vector<FlatJob> jobs;
+	std::vector<std::unique_ptr<FlatJob>> jobs;
 	if (run_all(n_seqs, nullptr, nullptr, seqs, opt, n_aln.data(), max_entries.data(), jobs)) return 1;
 	return 0;
 }
@@ -934,7 +1005,7 @@ extern "C" int bwa_gpu_resident_run(double *ms)
 	c->stats.n_devices = 1;
 	CK(cudaEventRecord(c->ev[0], c->st));
 	int64_t tot = 0;
-	if (run_chunk_device(c, c->res_n, c->res_w_entries, c->res_opt, c->res_nstacks, &tot)) return 1;
+	if (run_chunk_device(c, c->res_n, c->res_w_entries, c->res_opt, c->res_nstacks, &tot, true)) return 1;
 	CK(cudaEventRecord(c->ev[7], c->st));
 	CK(cudaStreamSynchronize(c->st));
 	float t = 0;

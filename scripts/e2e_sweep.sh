@@ -1,7 +1,4 @@
-for cfg in "BWAGPU_LANES=2" "BWAGPU_LANES=2 BWAGPU_CHUNK=1048576" "BWAGPU_LANES=3" "BWAGPU_LANES=2 BWAGPU_HOST_THREADS=4" "BWAGPU_LANES=1"; do
+for cfg in "BWAGPU_LANES=3" "BWAGPU_LANES=4" "BWAGPU_LANES=3 BWAGPU_CHUNK=1048576" "BWAGPU_LANES=4 BWAGPU_CHUNK=1048576" "BWAGPU_LANES=2"; do
   echo "== $cfg"
-  env $cfg python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('value %.4g e2e %.4g' % (d['value'], d['e2e']['value']))"
+  env $cfg python scripts/e2e_breakdown.py 10000000 2>&1 | grep -E "^flat|^struct" | tail -2 | cut -c1-60
 done

@@ -138,6 +138,7 @@ struct Ctx {
 	DevBuf<ReadMeta> d_meta;
 	DevBuf<uint32_t> d_w;
 	DevBuf<uint16_t> d_bid;
+	DevBuf<uint2> d_ctx;
 	DevBuf<int32_t> d_naln, d_maxent, d_jobs_a, d_jobs_b, d_ids, d_order;
 	DevBuf<uint8_t> d_keys, d_keys2;
 	DevBuf<uint32_t> d_pooloff, d_outoff;
@@ -195,7 +196,7 @@ extern "C" void bwa_gpu_destroy(void)
 			for (int s = 0; s < 2; ++s) c->sa[s].release();
 			c->pac.release();
 		}
-		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release();
+		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release(); c->d_ctx.release();
 		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release(); c->d_ids.release(); c->d_order.release(); c->d_keys.release(); c->d_keys2.release();
 		c->d_pooloff.release(); c->d_outoff.release(); c->d_pool.release(); c->d_out.release();
 		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
@@ -438,7 +439,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
                             bool device_compact)
 {
 	const bool stats = g_stats_enabled;
-	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1)) return 1;
+	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx.reserve(w_entries + 1)) return 1;
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
@@ -455,7 +456,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	B.opt = opt;
 	B.n_reads = n;
 	B.seq = c->d_seq.p; B.meta = c->d_meta.p;
-	B.w = c->d_w.p; B.bid = c->d_bid.p;
+	B.w = c->d_w.p; B.bid = c->d_bid.p; B.ctx = c->d_ctx.p;
 	B.n_aln = c->d_naln.p; B.max_entries = c->d_maxent.p; B.pool_off = c->d_pooloff.p;
 	B.pool = c->d_pool.p; B.pool_cap = (uint32_t)pool_cap;
 	B.pool_count = (unsigned int *)(c->d_counters.p + 2);
@@ -481,7 +482,9 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			if (stats) k_width<true><<<blocks, 128, 0, c->st>>>(B);
 			else k_width<false><<<blocks, 128, 0, c->st>>>(B);
 			CK(cudaGetLastError());
-			c->stats.launches++;
+			k_ctx<<<(int)((32ll * n + 255) / 256), 256, 0, c->st>>>(B);
+			CK(cudaGetLastError());
+			c->stats.launches += 2;
 		}
 	}
 	if (stats) {
@@ -541,7 +544,9 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			if (stats) k_width<true><<<wb, 128, 0, c->st>>>(B);
 			else k_width<false><<<wb, 128, 0, c->st>>>(B);
 			CK(cudaGetLastError());
-			c->stats.launches++;
+			k_ctx<<<(int)((32ll * n_jobs + 255) / 256), 256, 0, c->st>>>(B);
+			CK(cudaGetLastError());
+			c->stats.launches += 2;
 		}
 		uint32_t blocks = T.slots_blocks;
 		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);

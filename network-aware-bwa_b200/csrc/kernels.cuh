@@ -78,6 +78,7 @@ struct Batch {
 	const ReadMeta *__restrict__ meta;
 	uint32_t *w;       // width arena: w values (only gap_shadow reads them back)
 	uint16_t *bid;     // width arena: bid | (w[i-1] == w[i]) << 15 -- all the pruning tests need
+	uint2 *ctx;        // context arena (k_ctx): everything a popped node at (strand, i) needs, in one 8-byte word
 	// results, per read
 	int32_t *n_aln;       // -1 = not done (ran out of arena / pool: retried in the next pass)
 	int32_t *max_entries;
@@ -195,6 +196,55 @@ __global__ void __launch_bounds__(128) k_width(const Batch B)
 	}
 }
 
+// ------------------------------------------------------------------ K2b: per-position context words
+// A node popped at position i of strand a needs width[i-1], width[i-2].bid, the two seed-width entries
+// and the read bases i-1 and i-2 (bwtgap.c:156-157, 206-215, 160-165) before it can be pruned or
+// expanded: six scattered 1- and 2-byte loads.  k_ctx packs them into ONE 8-byte word per (strand, i),
+// indexed like the width arena, so that a trip of K3 issues a single context load next to its two
+// occurrence blocks:
+//   .x = CW(wb[i-1]) | str[i-1] << 12 | (CW(wb[i-2]) & 0xfff | str[i-2] << 12) << 16
+//   .y = CW(swb[si]) | (CW(swb[si-1]) & 0xfff) << 16        si = (i-1) - (len - seed_len) >= 1, else 0
+// CW(v) = min(bid, 4095) | EQ << 15: bid is only ever compared with values <= max_diff <= 254.
+#define CW_BID 0x0fffu
+#define CW_KEEP 0x70007000u // the two base fields of .x
+__device__ __forceinline__ uint32_t cw_of(uint32_t v)
+{
+	const uint32_t b = v & WB_BID;
+	return (b > CW_BID ? CW_BID : b) | (v & WB_EQ);
+}
+
+__global__ void __launch_bounds__(256) k_ctx(const Batch B)
+{
+#ifdef BWAGPU_HOST_EMU
+	const int job = (int)blockIdx.x, lane = 0, nl = 1;
+#else
+	const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int job = (int)(gt >> 5), lane = (int)(gt & 31), nl = 32;
+#endif
+	if (job >= B.n_jobs) return;
+	const int r = B.jobs ? B.jobs[job] : job;
+	const ReadMeta m = B.meta[r];
+	const int len = m.len, seed_len = B.opt.seed_len;
+	if (len == 0) return;
+	const bool has_seed = len > seed_len;
+	const uint8_t *s = B.seq + m.seq_off;
+	for (int a = 0; a < 2; ++a) {
+		const uint16_t *wb = B.bid + m.w_off + (size_t)a * WSTRIDE(len);
+		const uint16_t *swb = B.bid + m.w_off + 2 * WSTRIDE(len) + (size_t)a * WSTRIDE(seed_len);
+		uint2 *cx = B.ctx + m.w_off + (size_t)a * WSTRIDE(len);
+		for (int i = lane; i <= len; i += nl) {
+			uint32_t lo = 0, hi = 0;
+			if (i >= 1) lo = cw_of(wb[i - 1]) | ((uint32_t)(s[i - 1] >> (a << 2)) & 7u) << 12;
+			if (i >= 2) lo |= ((cw_of(wb[i - 2]) & CW_BID) | ((uint32_t)(s[i - 2] >> (a << 2)) & 7u) << 12) << 16;
+			if (has_seed) {
+				const int si = (i - 1) - (len - seed_len);
+				if (si >= 1) hi = cw_of(swb[si]) | (cw_of(swb[si - 1]) & CW_BID) << 16;
+			}
+			cx[i] = make_uint2(lo, hi);
+		}
+	}
+}
+
 // ------------------------------------------------------------------ K3: gapped search
 // bwt_match_gap (bwtgap.c:104-266) with its gap_stack (bwtgap.c:13-79), one read per
 // thread, persistent threads pulling reads from a global counter.
@@ -268,6 +318,9 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #ifndef BWAGPU_BATCH_POP
 #define BWAGPU_BATCH_POP 0 // N > 0 (needs BWAGPU_CONVERGE=1): memory pops wait until N lanes of the warp want one
 #endif
+#ifndef BWAGPU_NO_FREELIST
+#define BWAGPU_NO_FREELIST 0 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
+#endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
 #endif
@@ -296,7 +349,11 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	const uint32_t HS = 1;
 #endif
 	const GapOpt &O = B.opt;
+#ifdef BWAGPU_FIX_MODE // A/B switch: gap_opt_t::mode known at compile time
+	constexpr bool gape_mode = BWAGPU_FIX_MODE & 0x01, loggap = BWAGPU_FIX_MODE & 0x04, nonstop = BWAGPU_FIX_MODE & 0x10;
+#else
 	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
+#endif
 	// The reversed genome has the forward genome's base composition, so C() (bwt_t::L2) and
 	// seq_len are the same for both indexes; only the block array and `primary` differ.
 	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
@@ -322,9 +379,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	int rid = -1, len = 0, max_diff = 0, opt_max_diff = 0, max_gapo = 0;
 	int best_score = 0, best_cnt = 0, n_aln = 0, n_entries = 0, max_entries = 0;
 	bool has_seed = false, overflow = false, have_best = false;
-	const uint8_t *seq = nullptr;
-	uint32_t *w_base = nullptr;
-	uint16_t *wb_base = nullptr;
+	const uint2 *cx_base = nullptr; // the read's context words (k_ctx)
+	uint32_t *w_base = nullptr;     // the read's widths: only gap_shadow touches them
 	// Bucket lists.  heads[s] in memory is only meaningful while bit s of the mask is set, and
 	// the head of the bucket popped last lives in a register (cur_s / cur_head), so neither a
 	// reset pass nor a head load per pop is needed.
@@ -399,7 +455,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	auto alloc_rec = [&]() -> uint32_t {
 		uint32_t idx;
 		if (spare != NIL) { idx = spare; spare = NIL; }
-		else if (free_head != NIL) { idx = free_head; free_head = *nxt_at(idx); }
+		else if ((POOLED || !BWAGPU_NO_FREELIST) && free_head != NIL) { idx = free_head; free_head = *nxt_at(idx); }
 		else {
 			if (!POOLED) {
 				if (bump == CAP0) { overflow = true; return NIL; } // deeper than the private arena: next pass
@@ -479,19 +535,26 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array, then refresh
 			// the packed (bid, w[t-1]==w[t]) view of the positions it may have changed
 			const uint32_t a = E_A(e);
-			uint32_t *w = w_base + (size_t)a * WSTRIDE(len);
-			uint16_t *wb = wb_base + (size_t)a * WSTRIDE(len);
+			const size_t wo = (size_t)(w_base - B.w) + (size_t)a * WSTRIDE(len);
+			uint32_t *w = B.w + wo;
+			uint16_t *wb = B.bid + wo;
+			uint2 *cx = B.ctx + wo;
 			const uint32_t x = hl - hk + 1, mx = B.ix[1 - a].seq_len;
 			const int ldp = E_LDP(e);
-			uint32_t j = 0, prev = 0;
+			uint32_t j = 0, prev = 0, prev_nb = 0;
 			for (int t = 0; t <= ldp && t <= len; ++t) {
 				uint32_t wv = w[t], bid = wb[t] & WB_BID;
 				if (t < ldp) {
 					if (wv > x) { wv -= x; w[t] = wv; }
 					else if (wv == x) { bid = 1; wv = mx - (++j); w[t] = wv; }
 				}
-				wb[t] = (uint16_t)(bid | ((t > 0 && wv == prev) ? WB_EQ : 0u));
-				prev = wv;
+				const uint32_t nb = bid | ((t > 0 && wv == prev) ? WB_EQ : 0u);
+				wb[t] = (uint16_t)nb;
+				if (t + 1 <= len) { // the context word of position t+1 sees wb[t] and wb[t-1]
+					uint32_t *p = &cx[t + 1].x;
+					*p = (*p & CW_KEEP) | cw_of(nb) | (cw_of(prev_nb) & CW_BID) << 16;
+				}
+				prev = wv; prev_nb = nb;
 			}
 			const uint32_t idx = alloc_rec();
 			if (idx != NIL) {
@@ -559,9 +622,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 					active = false; // stays in MODE_NEW
 				} else {
 					has_seed = len > O.seed_len;
-					seq = B.seq + md.seq_off;
+					cx_base = B.ctx + md.w_off;
 					w_base = B.w + md.w_off;
-					wb_base = B.bid + md.w_off;
 					best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
 					// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
 					push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
@@ -623,7 +685,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 					else { // unlink
 						cur_head = nx;
 						if (cur_head == NIL) mask_clear(s);
-						if (spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
+						if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
 						spare = idx;
 					}
 					e.k = q.x; e.l = q.y;
@@ -657,6 +719,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		const uint32_t a = E_A(e);
 		const DevIndex &ix = B.ix[1 - a];
 		uint32_t jk = 0, jl = 0, cn = 0;
+		uint2 cw = make_uint2(0u, 0u);
 		OccBlock ob_l = {0, 0, 0, 0, 0, 0}, ob_k = {0, 0, 0, 0, 0, 0};
 		if (active) {
 			jk = occ_arg(ix, k - 1); jl = occ_arg(ix, l);
@@ -669,22 +732,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt_at(cur_head)));
 			}
 #endif
-			if (fresh) {
-				const uint16_t *wb = wb_base + (size_t)a * WSTRIDE(len);
-				wb1 = i >= 1 ? wb[i - 1] : 0u;
-				wb2 = i >= 2 ? wb[i - 2] : 0u;
-				c1 = i >= 1 ? (uint32_t)(seq[i - 1] >> (a << 2)) & 15u : 0u;
-				cn = i >= 2 ? (uint32_t)(seq[i - 2] >> (a << 2)) & 15u : 0u; // second base of an exact tail starting here
-				if (has_seed) {
-					const int si = (i - 1) - (len - O.seed_len);
-					if (si >= 1) {
-						const uint16_t *swb = wb_base + 2 * WSTRIDE(len) + (size_t)a * WSTRIDE(O.seed_len);
-						sw1 = swb[si]; sw2 = swb[si - 1];
-					}
-				}
-			} else if (mode == MODE_EXACT) {
-				cn = ii >= 2 ? (uint32_t)(seq[ii - 2] >> (a << 2)) & 15u : 0u;
-			}
+			if (fresh | (mode == MODE_EXACT)) // fresh: the node's own word; exact tail: .x's base field of word ii-1 = str[ii-2]
+				cw = cx_base[(size_t)a * WSTRIDE(len) + (fresh ? i : ii - 1)];
 			if (STATS) {
 				f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
 				if (k == 0) f_ref += 1u;
@@ -696,6 +745,13 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			}
 		}
 
+		if (active) {
+			if (fresh) {
+				wb1 = cw.x & (CW_BID | WB_EQ); c1 = (cw.x >> 12) & 7u;
+				wb2 = (cw.x >> 16) & CW_BID; cn = (cw.x >> 28) & 7u;
+				sw1 = cw.y & (CW_BID | WB_EQ); sw2 = (cw.y >> 16) & CW_BID;
+			} else if (mode == MODE_EXACT) cn = (cw.x >> 12) & 7u;
+		}
 		if (active && fresh) { // pruning tests of bwtgap.c:144-157
 			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
 			if (!nonstop && score_of(mm, go, ge) > best_score + O.s_mm) { finish_read(); mode = MODE_NEW; active = false; }

@@ -86,6 +86,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	}
 	std::vector<uint32_t> w(wo + 1);
 	std::vector<uint16_t> bid(wo + 1);
+	std::vector<uint2> ctx(wo + 1);
 	std::vector<uint32_t> pool_off(n);
 	std::vector<uint4> pool((size_t)n * 64 + (1 << 16));
 	std::vector<int32_t> jobs_a(n), jobs_b(n);
@@ -96,7 +97,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	B.opt = to_gapopt(opt);
 	B.n_reads = n;
 	B.seq = seq.data(); B.meta = meta.data();
-	B.w = w.data(); B.bid = bid.data();
+	B.w = w.data(); B.bid = bid.data(); B.ctx = ctx.data();
 	B.n_aln = n_aln; B.max_entries = max_entries; B.pool_off = pool_off.data();
 	B.pool = pool.data(); B.pool_cap = (uint32_t)pool.size();
 	B.pool_count = (unsigned int *)&counters[2];
@@ -107,6 +108,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	blockDim.x = 1; threadIdx.x = 0;
 	B.jobs = nullptr; B.n_jobs = n;
 	for (long long t = 0; t < 4ll * n; ++t) { blockIdx.x = (unsigned)t; k_width<true>(B); }
+	for (int t = 0; t < n; ++t) { blockIdx.x = (unsigned)t; k_ctx(B); }
 	if (stats8) { stats8[0] = stats[0]; stats8[1] = stats[1]; }
 	stats[0] = stats[1] = 0;
 	// K3 tiers
@@ -135,7 +137,10 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		int32_t *ovf = (t & 1) ? jobs_b.data() : jobs_a.data();
 		B.overflow_ids = ovf;
 		counters[0] = counters[1] = 0;
-		if (t > 0) for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
+		if (t > 0) {
+			for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
+			for (int q = 0; q < n_jobs; ++q) { blockIdx.x = (unsigned)q; k_ctx(B); }
+		}
 		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; k_search<true, true>(B); }
 		if (stats8) stats8[4 + t] = (unsigned long long)counters[1];
 		if (counters[1] > 0 && t == 1) { g_err = "reads exceeded the largest tier"; return 1; }

@@ -1,0 +1,667 @@
+/* bwa_gpu_batch.c -- the BATCHED drop-in: `bwa bam2bam -t 1` with its hot path on the GPU, one device
+ * call per phase and batch instead of one per record.
+ *
+ * SURVEY.md §8(f) rank 1 / INTEGRATION.md: the reference's sequential driver (bam2bam.c:1143-1219)
+ * handles one record at a time -- read_bam_pair -> pair_aln -> pair_posn -> ... -- so its calls into the
+ * alignment layer carry one read each.  This shim REPLACES the two loop functions
+ *
+ *     sequential_loop_pass1 (bam2bam.c:1143)      sequential_loop_pass2 (bam2bam.c:1178)
+ *
+ * (both are plain global functions of the reference, reached through the PLT of a shared-library build,
+ * so LD_PRELOAD can supply them) with versions that gather a batch of records and make ONE call per phase:
+ *
+ *   pass 1   bam1_to_seq x n  ->  bwa_gpu_cal_sa_reads_gap   (replaces bwa_cal_sa_reg_gap, bam2bam.c:616,676)
+ *            bwa_aln2seq[_core] in record order (it consumes drand48: bwase.c:33,36,78)
+ *            -> bwa_gpu_cal_pac_pos                           (replaces bwt_sa at bwase.c:145,152; bam2bam.c:635-636)
+ *   pass 2   hit enumeration of all pairs -> bwa_gpu_cal_pac_pos   (bwt_sa at bam2bam.c:752,761)
+ *            pairing + bwa_aln2seq_core in record order -> bwa_gpu_cal_pac_pos (bam2bam.c:786)
+ *            bwa_paired_sw1 -> bwa_gpu_mate_sw_path           (aln_local_core inside bwa_sw_core, bwape.c:456)
+ *            bwa_refine_gapped, bwa_update_bam1, BAM output: the reference's own code, per record.
+ *
+ * Everything that is not the hot path IS the reference: this file calls its exported functions
+ * (read_bam_pair, bam1_to_seq, bwa_aln2seq_core, bwa_cal_pac_pos_core, pairing, bwa_paired_sw1,
+ * bwa_refine_gapped, bwa_update_bam1, pair_print_custom, ...) and never restates their arithmetic.
+ * Where a reference function interleaves host logic with a hot call (bwa_cal_pac_pos_core around bwt_sa,
+ * bwa_paired_sw1/bwa_sw_core around aln_local_core) it is run in RECORD / REPLAY fashion: a first run with
+ * the hot call interposed to note its arguments (and return "no result", which leaves the record
+ * untouched), one device call for the whole batch, then the real run with the hot call interposed to
+ * hand back the device's answers in the same order.
+ *
+ * Order-sensitive state is kept exactly as `-t 1` has it: drand48 is consumed by bwa_aln2seq_core only
+ * (bwase.c), which runs in record order in both passes; the pass-2 position cache for intervals >= 1000
+ * wide (bam2bam.c:743-758) is filled by the first record, in record order, that touches a key.
+ * The output BAM is therefore record-identical to `bam2bam -t 1` (tests/test_batched_bam2bam.py).
+ *
+ * The reference's static globals (bwt, bns, pac, gap_opt, pe_opt, the three input flags) are captured
+ * by interposing the loaders / option parser that produce them.  Not supported here: `.sai` inputs
+ * (-0/-1/-2; broken in the reference itself) -- such records take the per-record path.
+ *
+ * Build (integration/Makefile): gcc -I$(REF) -I../oracle/zmq_shim -I../include ... -lbwagpu
+ * Use:   LD_PRELOAD=integration/libbwa_gpu_batch.so oracle/_ref/ref_driver bam2bam -g idx -t 1 -f out.bam in.bam
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <zlib.h>
+
+#include "bamlite.h"
+#include "bwtaln.h"
+#include "bwase.h"
+#include "bwape.h"
+#include "khash.h"
+#include "bgzf.h"
+#include "bwa_gpu.h" /* after bwtaln.h: re-uses the reference's own types */
+
+KHASH_MAP_INIT_INT64(64, poslist_t) /* the position cache's type, as bam2bam.c:38 declares it */
+
+/* reference functions this driver calls that no header declares (bam2bam.c) */
+void pair_aln(bam_pair_t *p);
+void pair_print_custom(gzFile f, bam_pair_t *p);
+int read_pair_custom(gzFile f, bam_pair_t *p);
+void pair_print_bam(BGZF *output, bam_pair_t *p);
+void bwa_update_bam1(bam1_t *out, const bntseq_t *bns, bwa_seq_t *p, const bwa_seq_t *mate, int mode, int max_top2);
+void bwa_cal_pac_pos_core(const bwt_t *forward_bwt, const bwt_t *reverse_bwt, bwa_seq_t *seq, const int max_mm, const float fnr);
+void bwa_aln2seq(int n_aln, const bwt_aln1_t *aln, bwa_seq_t *s);
+
+#define REAL(ret, name, ...) \
+	static ret (*real_##name)(__VA_ARGS__); \
+	if (!real_##name) real_##name = (ret (*)(__VA_ARGS__))dlsym(RTLD_NEXT, #name)
+
+static void die(const char *what)
+{
+	fprintf(stderr, "[bwa_gpu_batch] %s: %s\n", what, bwa_gpu_last_error());
+	abort(); /* the reference's convention on this path: xassert -> abort (utils.c:68-83) */
+}
+
+static double now(void)
+{
+	struct timeval tv;
+	gettimeofday(&tv, 0);
+	return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+/* ------------------------------------------------------------------ the reference's static globals, captured */
+static bwt_t *g_bwt[2];        /* bam2bam.c:88  (init_genome_index 855-856) */
+static const bntseq_t *g_bns;  /* bam2bam.c:89 */
+static ubyte_t *g_pac;         /* bam2bam.c:91 */
+static gap_opt_t *g_gap;       /* bam2bam.c:94 */
+static pe_opt_t *g_pe;         /* bam2bam.c:95 */
+static int g_broken_input, g_skip_duplicates, g_drop_aligned; /* bam2bam.c:98-101, options 130 / 131 / 133 */
+static isize_info_t g_null_ii; /* bam2bam.c:106 */
+
+bwt_t *bwt_restore_bwt(const char *fn, int touch)
+{
+	REAL(bwt_t *, bwt_restore_bwt, const char *, int);
+	bwt_t *b = real_bwt_restore_bwt(fn, touch);
+	const size_t n = strlen(fn);
+	g_bwt[n >= 5 && strcmp(fn + n - 5, ".rbwt") == 0 ? 1 : 0] = b;
+	return b;
+}
+
+ubyte_t *bwt_restore_pac(const bntseq_t *bns, int touch)
+{
+	REAL(ubyte_t *, bwt_restore_pac, const bntseq_t *, int);
+	g_bns = bns;
+	g_pac = real_bwt_restore_pac(bns, touch);
+	return g_pac;
+}
+
+gap_opt_t *gap_init_opt(void)
+{
+	REAL(gap_opt_t *, gap_init_opt, void);
+	return g_gap = real_gap_init_opt();
+}
+
+pe_opt_t *bwa_init_pe_opt(void)
+{
+	REAL(pe_opt_t *, bwa_init_pe_opt, void);
+	return g_pe = real_bwa_init_pe_opt();
+}
+
+int getopt_long(int argc, char *const argv[], const char *optstring, const struct option *longopts, int *longindex)
+{
+	REAL(int, getopt_long, int, char *const *, const char *, const struct option *, int *);
+	const int c = real_getopt_long(argc, argv, optstring, longopts, longindex);
+	if (c == 130) g_broken_input = 1;      /* bam2bam.c:1991 */
+	if (c == 131) g_skip_duplicates = 1;
+	if (c == 133) g_drop_aligned = 1;
+	return c;
+}
+
+static int unique_rec(const bam_pair_t *p) /* bam2bam.c:595-606 */
+{
+	int i;
+	if (!g_skip_duplicates) return 1;
+	if (p->kind == eof_marker) return 0;
+	for (i = 0; i != (int)p->kind; ++i)
+		if (p->bam_rec[i].core.flag & SAM_FDP) return 0;
+	return 1;
+}
+
+/* ------------------------------------------------------------------ device context */
+static int g_ready;
+static long g_calls_aln, g_calls_sa, g_calls_sw, g_reads_aln, g_q_sa, g_jobs_sw;
+static double g_t_aln, g_t_sa, g_t_sw;
+
+static void report(void)
+{
+	fprintf(stderr, "[bwa_gpu_batch] device calls: cal_sa_reads_gap=%ld (%ld reads, %.2f s)  cal_pac_pos=%ld (%ld queries, %.2f s)  "
+	                "mate_sw_path=%ld (%ld jobs, %.2f s)\n", g_calls_aln, g_reads_aln, g_t_aln, g_calls_sa, g_q_sa, g_t_sa,
+	        g_calls_sw, g_jobs_sw, g_t_sw);
+}
+
+static void ensure_gpu(void)
+{
+	if (g_ready) return;
+	if (!g_bwt[0] || !g_bwt[1] || !g_bns || !g_pac || !g_gap || !g_pe) {
+		fprintf(stderr, "[bwa_gpu_batch] the reference's index/option globals were not seen being loaded\n");
+		abort();
+	}
+	{
+		const char *e = getenv("BWAGPU_NDEV");
+		int ids[16], n = e ? atoi(e) : 1, i;
+		if (n < 1) n = 1;
+		if (n > 16) n = 16;
+		for (i = 0; i < n; ++i) ids[i] = i;
+		if (bwa_gpu_init(n, ids)) die("bwa_gpu_init");
+	}
+	if (bwa_gpu_load_index(g_bwt, g_pac, g_bns->l_pac)) die("bwa_gpu_load_index");
+	g_ready = 1;
+	atexit(report);
+}
+
+static size_t batch_records(void)
+{
+	const char *e = getenv("BWAGPU_BATCH_RECORDS");
+	const long v = e ? atol(e) : 0;
+	return v > 0 ? (size_t)v : (size_t)1 << 18;
+}
+
+/* ------------------------------------------------------------------ bwt_sa: real / replay */
+typedef struct { size_t n, m; bwtint_t *k; uint8_t *which; bwtint_t *out; } saq_t;
+static saq_t g_q;
+static int g_sa_replay;
+static size_t g_sa_pos;
+
+static void saq_push(saq_t *q, bwtint_t k, int forward)
+{
+	if (q->n == q->m) {
+		q->m = q->m ? q->m << 1 : 1 << 16;
+		q->k = (bwtint_t *)realloc(q->k, q->m * sizeof(bwtint_t));
+		q->which = (uint8_t *)realloc(q->which, q->m);
+	}
+	q->k[q->n] = k; q->which[q->n] = (uint8_t)(forward != 0); ++q->n;
+}
+
+static void saq_run(saq_t *q)
+{
+	const double t0 = now();
+	q->out = (bwtint_t *)realloc(q->out, (q->n + 1) * sizeof(bwtint_t));
+	if (q->n && bwa_gpu_cal_pac_pos((int64_t)q->n, q->k, q->which, q->out)) die("bwa_gpu_cal_pac_pos");
+	++g_calls_sa; g_q_sa += (long)q->n; g_t_sa += now() - t0;
+	g_sa_pos = 0;
+}
+
+static bwtint_t saq_next(saq_t *q, const bwt_t *bwt, bwtint_t k)
+{
+	if (g_sa_pos >= q->n || q->k[g_sa_pos] != k || q->which[g_sa_pos] != (uint8_t)(bwt == g_bwt[0])) {
+		fprintf(stderr, "[bwa_gpu_batch] bwt_sa replay out of step at query %zu\n", g_sa_pos);
+		abort();
+	}
+	return q->out[g_sa_pos++];
+}
+
+bwtint_t bwt_sa(const bwt_t *bwt, bwtint_t k)
+{
+	REAL(bwtint_t, bwt_sa, const bwt_t *, bwtint_t);
+	if (g_sa_replay) return saq_next(&g_q, bwt, k);
+	return real_bwt_sa(bwt, k); /* index construction, per-record fallbacks */
+}
+
+/* ------------------------------------------------------------------ aln_local_core: real / record / replay */
+enum { SW_REAL = 0, SW_RECORD = 1, SW_REPLAY = 2 };
+static int g_sw_mode;
+static int64_t g_sw_beg; /* *beg of the bwa_sw_core call in progress */
+typedef struct { size_t n, m; bwa_gpu_sw_job_t *job; size_t *seq_off; size_t sn, sm; ubyte_t *seqs; bwa_gpu_path_res_t *res; const bwa_cigar_t *pool; } swq_t;
+static swq_t g_sw;
+static size_t g_sw_pos;
+
+bwa_cigar_t *bwa_sw_core(bwtint_t l_pac, const ubyte_t *pacseq, int len, const ubyte_t *seq, int64_t *beg, int reglen,
+                         int *n_cigar, uint32_t *cnt)
+{
+	REAL(bwa_cigar_t *, bwa_sw_core, bwtint_t, const ubyte_t *, int, const ubyte_t *, int64_t *, int, int *, uint32_t *);
+	g_sw_beg = *beg; /* the window the reference is about to unpack (bwape.c:447-450) */
+	return real_bwa_sw_core(l_pac, pacseq, len, seq, beg, reglen, n_cigar, cnt);
+}
+
+int aln_local_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2, const AlnParam *ap, path_t *path, int *path_len,
+                   int thres, int *subo)
+{
+	REAL(int, aln_local_core, unsigned char *, int, unsigned char *, int, const AlnParam *, path_t *, int *, int, int *);
+	if (g_sw_mode == SW_RECORD) {
+		swq_t *q = &g_sw;
+		if (q->n == q->m) {
+			q->m = q->m ? q->m << 1 : 1 << 12;
+			q->job = (bwa_gpu_sw_job_t *)realloc(q->job, q->m * sizeof(*q->job));
+			q->seq_off = (size_t *)realloc(q->seq_off, q->m * sizeof(size_t));
+		}
+		if (q->sn + (size_t)len2 > q->sm) {
+			q->sm = (q->sn + (size_t)len2) * 2 + 4096;
+			q->seqs = (ubyte_t *)realloc(q->seqs, q->sm);
+		}
+		memcpy(q->seqs + q->sn, seq2, (size_t)len2); /* bwa_paired_sw1 un-reverses the read right after the call */
+		q->job[q->n].beg = g_sw_beg; q->job[q->n].reglen = len1; q->job[q->n].len = len2; q->job[q->n].seq = 0;
+		q->seq_off[q->n] = q->sn; q->sn += (size_t)len2; ++q->n;
+		return -1; /* "no alignment": bwa_sw_core returns 0 and bwa_paired_sw1 leaves both reads untouched (bwape.c:457-460) */
+	}
+	if (g_sw_mode == SW_REPLAY) {
+		swq_t *q = &g_sw;
+		const bwa_gpu_path_res_t *r;
+		const bwa_cigar_t *cg;
+		int n = 0, c, t, i, j;
+		if (g_sw_pos >= q->n || q->job[g_sw_pos].reglen != len1 || q->job[g_sw_pos].len != len2) {
+			fprintf(stderr, "[bwa_gpu_batch] aln_local_core replay out of step at job %zu\n", g_sw_pos);
+			abort();
+		}
+		r = &q->res[g_sw_pos++];
+		if (r->score < 0) return r->score;
+		/* path_t[] as aln_global_core's backtrace leaves it (stdaln.c:496-512, shifted at 741-744): path[0] = the end
+		 * cell, path[path_len-1] = the start cell; an element's ctype says how its cell was entered */
+		cg = q->pool + r->cigar_off;
+		for (c = 0; c < r->n_cigar; ++c) n += cg[c] & 0x3fff;
+		*path_len = n;
+		if (n == 0) return r->score;
+		i = r->start_i; j = r->start_j;
+		for (c = 0, t = n - 1; c < r->n_cigar; ++c) {
+			const int op = cg[c] >> 14, run = cg[c] & 0x3fff;
+			int u;
+			for (u = 0; u < run; ++u, --t) {
+				if (t != n - 1) { if (op != FROM_I) ++i; if (op != FROM_D) ++j; }
+				path[t].i = i; path[t].j = j; path[t].ctype = (unsigned char)op;
+			}
+		}
+		if (path[0].i != r->end_i || path[0].j != r->end_j) {
+			fprintf(stderr, "[bwa_gpu_batch] device path does not end at its end cell (%d,%d) vs (%d,%d)\n", path[0].i, path[0].j, r->end_i, r->end_j);
+			abort();
+		}
+		if (subo) *subo = 0;
+		return r->score;
+	}
+	return real_aln_local_core(seq1, len1, seq2, len2, ap, path, path_len, thres, subo);
+}
+
+static void swq_run(swq_t *q)
+{
+	size_t i;
+	const double t0 = now();
+	for (i = 0; i < q->n; ++i) q->job[i].seq = q->seqs + q->seq_off[i];
+	q->res = (bwa_gpu_path_res_t *)realloc(q->res, (q->n + 1) * sizeof(*q->res));
+	q->pool = 0;
+	if (q->n && bwa_gpu_mate_sw_path((int)q->n, q->job, q->res, &q->pool)) die("bwa_gpu_mate_sw_path");
+	++g_calls_sw; g_jobs_sw += (long)q->n; g_t_sw += now() - t0;
+	g_sw_pos = 0;
+}
+
+/* ------------------------------------------------------------------ pass 1 */
+static void gpu_align(int m, bwa_seq_t *flat)
+{
+	const double t0 = now();
+	if (m && bwa_gpu_cal_sa_reads_gap(m, flat, g_gap)) die("bwa_gpu_cal_sa_reads_gap");
+	++g_calls_aln; g_reads_aln += m; g_t_aln += now() - t0;
+}
+
+static int is_mapped(const bwa_seq_t *p) { return p->type == BWA_TYPE_UNIQUE || p->type == BWA_TYPE_REPEAT; }
+
+void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_infos) *iinfos)
+{
+	const size_t B = batch_records();
+	const double t0 = now();
+	double t_read = 0, t_host = 0, t_write = 0, t1;
+	bam_pair_t *recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
+	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
+	long tot_seqs = 0;
+	ensure_gpu();
+	for (;;) {
+		size_t n = 0, i;
+		int m = 0, j, rc;
+		t1 = now();
+		while (n < B) {
+			rc = read_bam_pair(ks, &recs[n], g_broken_input, g_drop_aligned);
+			if (rc < 0) {
+				fprintf(stderr, "[%s] error reading input BAM%s\n", __func__, rc == -2 ? " (lone mate)" : "");
+				exit(1);
+			}
+			if (rc == 0) break;
+			tot_seqs += recs[n].kind;
+			++n;
+		}
+		t_read += now() - t1;
+		if (n == 0) break;
+
+		/* aln_singleton / aln_pair (bam2bam.c:608-620, 660-681) without the search ... */
+		t1 = now();
+		for (i = 0; i < n; ++i) {
+			bam_pair_t *r = &recs[i];
+			if (r->phase != pristine) continue;
+			if (unique_rec(r))
+				for (j = 0; j != (int)r->kind; ++j) {
+					bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
+					flat[m++] = r->bwa_seq[j];
+				}
+		}
+		t_host += now() - t1;
+		/* ... which is ONE device call for the batch */
+		gpu_align(m, flat);
+		t1 = now();
+		for (i = 0, m = 0; i < n; ++i) {
+			bam_pair_t *r = &recs[i];
+			if (r->phase != pristine) continue;
+			if (unique_rec(r))
+				for (j = 0; j != (int)r->kind; ++j) r->bwa_seq[j] = flat[m++];
+			r->phase = aligned;
+		}
+
+		/* posn_singleton / posn_pair (bam2bam.c:622-641, 683-703): primary-hit selection on the host, in record
+		 * order (drand48), collecting the SA rows whose coordinates are wanted ... */
+		g_q.n = 0;
+		for (i = 0; i < n; ++i) {
+			bam_pair_t *r = &recs[i];
+			if (r->phase != aligned || !unique_rec(r)) continue;
+			for (j = 0; j != (int)r->kind; ++j) {
+				bwa_seq_t *p = &r->bwa_seq[j];
+				int k;
+				if (r->kind == singleton) bwa_aln2seq_core(p->n_aln, p->aln, p, 1, g_pe->max_occ_se);
+				else { p->n_multi = 0; bwa_aln2seq(p->n_aln, p->aln, p); }
+				if (is_mapped(p)) saq_push(&g_q, p->sa, p->strand);
+				if (r->kind == singleton)
+					for (k = 0; k < p->n_multi; ++k) saq_push(&g_q, p->multi[k].pos, p->multi[k].strand);
+			}
+		}
+		t_host += now() - t1;
+		/* ... one device call ... */
+		saq_run(&g_q);
+		/* ... and the reference's own bwa_cal_pac_pos_core (position + mapQ) fed from the answers */
+		t1 = now();
+		g_sa_replay = 1;
+		for (i = 0; i < n; ++i) {
+			bam_pair_t *r = &recs[i];
+			if (r->phase != aligned) continue;
+			if (unique_rec(r))
+				for (j = 0; j != (int)r->kind; ++j) {
+					bwa_seq_t *p = &r->bwa_seq[j];
+					int k;
+					bwa_cal_pac_pos_core(g_bwt[0], g_bwt[1], p, g_gap->max_diff, g_gap->fnr);
+					if (r->kind == singleton)
+						for (k = 0; k < p->n_multi; ++k) { /* bam2bam.c:633-637 */
+							bwt_multi1_t *q = p->multi + k;
+							if (q->strand) q->pos = bwt_sa(g_bwt[0], q->pos);
+							else q->pos = g_bwt[1]->seq_len - (bwt_sa(g_bwt[1], q->pos) + p->len);
+						}
+				}
+			r->phase = positioned;
+		}
+		g_sa_replay = 0;
+		if (g_sa_pos != g_q.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SA answers unused\n", g_q.n - g_sa_pos, g_q.n); abort(); }
+		for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
+			if (unique_rec(&recs[i])) improve_isize_est(iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
+		t_host += now() - t1;
+		t1 = now();
+		for (i = 0; i < n; ++i) {
+			pair_print_custom(temporary, &recs[i]);
+			bam_destroy_pair(&recs[i]);
+		}
+		t_write += now() - t1;
+		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
+	}
+	free(recs); free(flat);
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (read %.2f, host phases %.2f, device calls %.2f, temp write %.2f)\n",
+	        __func__, tot_seqs, now() - t0, t_read, t_host, g_t_aln + g_t_sa, t_write);
+	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
+}
+
+/* ------------------------------------------------------------------ pass 2 */
+typedef struct { size_t n, m; uint8_t *a; } bits_t;
+static void bits_push(bits_t *b, int v)
+{
+	if (b->n == b->m) { b->m = b->m ? b->m << 1 : 1 << 12; b->a = (uint8_t *)realloc(b->a, b->m); }
+	b->a[b->n++] = (uint8_t)v;
+}
+
+static const isize_info_t *ii_of(khash_t(isize_infos) *iinfos, const bam_pair_t *r) /* bam2bam.c:715-716 */
+{
+	khiter_t it = kh_get(isize_infos, iinfos, bam_get_rg(r->bam_rec));
+	return it == kh_end(iinfos) ? &g_null_ii : &kh_val(iinfos, it);
+}
+
+static int wants_pairing(const bam_pair_t *r) /* bam2bam.c:726-735 */
+{
+	const bwa_seq_t *p0 = &r->bwa_seq[0], *p1 = &r->bwa_seq[1];
+	long long n_occ[2];
+	int j, k;
+	if (!is_mapped(p0) || !is_mapped(p1)) return 0;
+	for (j = 0; j < 2; ++j) {
+		const bwa_seq_t *p = &r->bwa_seq[j];
+		n_occ[j] = 0;
+		for (k = 0; k < p->n_aln; ++k) n_occ[j] += p->aln[k].l - p->aln[k].k + 1;
+	}
+	return n_occ[0] <= g_pe->max_occ && n_occ[1] <= g_pe->max_occ;
+}
+
+static int is_pair_job(const bam_pair_t *r) { return r->kind == proper_pair && r->phase == positioned && unique_rec(r); }
+
+/* finish_pair (bam2bam.c:705-811) for records [lo, hi), phase by phase */
+static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_infos) *iinfos, uint64_t n_tot[2], uint64_t n_mapped[2],
+                         kh_64_t *my_hash)
+{
+	static bits_t fresh; /* per wide interval visited: did THIS record create its cache entry? */
+	size_t i, fpos = 0;
+	int j, k;
+	bwtint_t l;
+
+	/* A: every SA row whose coordinate pairing will want (bam2bam.c:736-765), in the reference's visiting order */
+	g_q.n = 0; fresh.n = 0;
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &recs[i];
+		if (!is_pair_job(r)) continue;
+		for (j = 0; j < 2; ++j)
+			if (!r->bwa_seq[j].seq) bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
+		if (!wants_pairing(r)) continue;
+		for (j = 0; j < 2; ++j)
+			for (k = 0; k < r->bwa_seq[j].n_aln; ++k) {
+				const bwt_aln1_t *a = r->bwa_seq[j].aln + k;
+				int is_new = 1;
+				if (a->l - a->k + 1 >= MIN_HASH_WIDTH) { /* cached by (k,l) only; the first record to touch a key fills it */
+					int ret;
+					khint_t it = kh_put(64, my_hash, (uint64_t)a->k << 32 | a->l, &ret);
+					is_new = ret != 0;
+					if (is_new) {
+						poslist_t *z = &kh_val(my_hash, it);
+						z->n = a->l - a->k + 1;
+						z->a = (bwtint_t *)malloc(sizeof(bwtint_t) * z->n);
+					}
+					bits_push(&fresh, is_new);
+				}
+				if (is_new)
+					for (l = a->k; l <= a->l; ++l) { saq_push(&g_q, l, a->a); if (l == a->l) break; }
+			}
+	}
+	saq_run(&g_q);
+
+	/* B: pairing on the host, in record order, then the hit lists for XA (consumes drand48), collecting their rows */
+	{
+		static saq_t q2;
+		size_t qpos = 0;
+		q2.n = 0;
+		for (i = lo; i < hi; ++i) {
+			bam_pair_t *r = &recs[i];
+			bwa_seq_t *p[2];
+			pe_data_t d;
+			if (!is_pair_job(r)) continue;
+			p[0] = &r->bwa_seq[0]; p[1] = &r->bwa_seq[1];
+			memset(&d, 0, sizeof(pe_data_t));
+			for (j = 0; j < 2; ++j) { d.aln[j].a = p[j]->aln; d.aln[j].n = p[j]->n_aln; }
+			if (wants_pairing(r)) {
+				d.arr.n = 0;
+				for (j = 0; j < 2; ++j)
+					for (k = 0; k < (int)d.aln[j].n; ++k) {
+						const bwt_aln1_t *a = d.aln[j].a + k;
+						const bwtint_t w = a->l - a->k + 1;
+						bwtint_t t;
+						uint64_t x;
+						if (w >= MIN_HASH_WIDTH) {
+							khint_t it = kh_get(64, my_hash, (uint64_t)a->k << 32 | a->l);
+							poslist_t *z = &kh_val(my_hash, it);
+							if (fresh.a[fpos++]) /* this record created the entry: its strand and length define the values */
+								for (t = 0; t < w; ++t, ++qpos)
+									z->a[t] = a->a ? g_q.out[qpos] : g_bwt[1]->seq_len - (g_q.out[qpos] + p[j]->len);
+							for (t = 0; t < (bwtint_t)z->n; ++t) {
+								x = z->a[t];
+								x = x << 32 | k << 1 | j;
+								kv_push(uint64_t, d.arr, x);
+							}
+						} else
+							for (t = 0; t < w; ++t, ++qpos) {
+								x = a->a ? g_q.out[qpos] : g_bwt[1]->seq_len - (g_q.out[qpos] + p[j]->len);
+								x = x << 32 | k << 1 | j;
+								kv_push(uint64_t, d.arr, x);
+							}
+					}
+				pairing(p, &d, g_pe, g_gap->s_mm, ii_of(iinfos, r));
+			}
+			if (g_pe->N_multi || g_pe->n_multi) /* bam2bam.c:771-791 */
+				for (j = 0; j < 2; ++j)
+					if (p[j]->type != BWA_TYPE_NO_MATCH) {
+						if (!(p[j]->extra_flag & SAM_FPP) && p[1 - j]->type != BWA_TYPE_NO_MATCH)
+							bwa_aln2seq_core(d.aln[j].n, d.aln[j].a, p[j], 0,
+							                 p[j]->c1 + p[j]->c2 - 1 > g_pe->N_multi ? g_pe->n_multi : g_pe->N_multi);
+						else bwa_aln2seq_core(d.aln[j].n, d.aln[j].a, p[j], 0, g_pe->n_multi);
+						for (k = 0; k < p[j]->n_multi; ++k) saq_push(&q2, p[j]->multi[k].pos, p[j]->multi[k].strand);
+					}
+			kv_destroy(d.arr);
+			kv_destroy(d.pos[0]); kv_destroy(d.pos[1]);
+		}
+		if (qpos != g_q.n || fpos != fresh.n) { fprintf(stderr, "[bwa_gpu_batch] pass-2 enumeration out of step\n"); abort(); }
+		saq_run(&q2);
+		qpos = 0;
+		for (i = lo; i < hi; ++i) {
+			bam_pair_t *r = &recs[i];
+			if (!is_pair_job(r) || !(g_pe->N_multi || g_pe->n_multi)) continue;
+			for (j = 0; j < 2; ++j) {
+				bwa_seq_t *p = &r->bwa_seq[j];
+				if (p->type == BWA_TYPE_NO_MATCH) continue;
+				for (k = 0; k < p->n_multi; ++k, ++qpos) {
+					bwt_multi1_t *q = p->multi + k;
+					q->pos = q->strand ? q2.out[qpos] : g_bwt[1]->seq_len - (q2.out[qpos] + p->len);
+				}
+			}
+		}
+	}
+
+	/* C: mate rescue.  bwa_paired_sw1 (bwape.c:519-633) decides the windows in floating point and judges the
+	 * alignments; only aln_local_core moves.  First run: note the jobs.  Device.  Second run: the real one. */
+	{
+		uint64_t dummy_tot[2] = {0, 0}, dummy_mapped[2] = {0, 0};
+		g_sw.n = 0; g_sw.sn = 0;
+		g_sw_mode = SW_RECORD;
+		for (i = lo; i < hi; ++i)
+			if (is_pair_job(&recs[i])) {
+				bwa_seq_t *p[2] = {&recs[i].bwa_seq[0], &recs[i].bwa_seq[1]};
+				bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(iinfos, &recs[i]), dummy_tot, dummy_mapped);
+			}
+		swq_run(&g_sw);
+		g_sw_mode = SW_REPLAY;
+		for (i = lo; i < hi; ++i)
+			if (is_pair_job(&recs[i])) {
+				bwa_seq_t *p[2] = {&recs[i].bwa_seq[0], &recs[i].bwa_seq[1]};
+				bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(iinfos, &recs[i]), n_tot, n_mapped);
+			}
+		g_sw_mode = SW_REAL;
+		if (g_sw_pos != g_sw.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SW answers unused\n", g_sw.n - g_sw_pos, g_sw.n); abort(); }
+	}
+
+	/* D: the reference's own per-record tail (bam2bam.c:643-658, 798-810) */
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &recs[i];
+		if (is_pair_job(r)) {
+			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
+			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[1], g_pac, 0);
+			bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
+			bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
+			bwa_free_read_seq1(&r->bwa_seq[1]);
+			bwa_free_read_seq1(&r->bwa_seq[0]);
+		} else if (r->kind == singleton && r->phase == positioned && unique_rec(r)) {
+			bwa_seq_t *p = &r->bwa_seq[0];
+			if (!p->seq) bam1_to_seq(&r->bam_rec[0], p, 1, g_gap->trim_qual);
+			bwa_refine_gapped(g_bns, 1, p, g_pac, 0);
+			bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
+			bwa_free_read_seq1(p);
+		}
+		if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
+	}
+}
+
+void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) *iinfos)
+{
+	const size_t B = batch_records();
+	const long long max_q = getenv("BWAGPU_BATCH_SA") ? atoll(getenv("BWAGPU_BATCH_SA")) : 1ll << 25; /* SA rows per device call */
+	const double t0 = now();
+	double t_read = 0, t_fin = 0, t_write = 0, t1;
+	uint64_t n_tot[2] = {0, 0}, n_mapped[2] = {0, 0};
+	bam_pair_t *recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
+	kh_64_t *my_hash = kh_init(64);
+	khiter_t it;
+	long tot_seqs = 0;
+	ensure_gpu();
+	for (;;) {
+		size_t n = 0, i, lo;
+		int rc;
+		t1 = now();
+		while (n < B) {
+			rc = read_pair_custom(temporary, &recs[n]);
+			if (rc < 0) { fprintf(stderr, "[%s] error reading intermediate file\n", __func__); exit(1); }
+			if (rc == 0) break;
+			tot_seqs += recs[n].kind;
+			++n;
+		}
+		t_read += now() - t1;
+		if (n == 0) break;
+		t1 = now();
+		for (lo = 0; lo < n;) { /* sub-ranges bounded by the SA rows their hit lists expand to */
+			size_t hi = lo;
+			long long q = 0;
+			while (hi < n && (hi == lo || q < max_q)) {
+				const bam_pair_t *r = &recs[hi];
+				if (is_pair_job(r) && wants_pairing(r)) {
+					int j, k;
+					for (j = 0; j < 2; ++j)
+						for (k = 0; k < r->bwa_seq[j].n_aln; ++k) q += r->bwa_seq[j].aln[k].l - r->bwa_seq[j].aln[k].k + 1;
+				}
+				++hi;
+			}
+			finish_range(recs, lo, hi, iinfos, n_tot, n_mapped, my_hash);
+			lo = hi;
+		}
+		t_fin += now() - t1;
+		t1 = now();
+		for (i = 0; i < n; ++i) {
+			pair_print_bam(output, &recs[i]);
+			bam_destroy_pair(&recs[i]);
+		}
+		t_write += now() - t1;
+		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
+	}
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (temp read %.2f, finish %.2f, BAM write %.2f)\n"
+	                "[%s] finished cleanly, shutting down.\n"
+	                "[bwa_paired_sw] %lld out of %lld Q%d singletons are mated.\n"
+	                "[bwa_paired_sw] %lld out of %lld Q%d discordant pairs are fixed.\n",
+	        __func__, tot_seqs, now() - t0, t_read, t_fin, t_write, __func__, (long long)n_mapped[1], (long long)n_tot[1], SW_MIN_MAPQ,
+	        (long long)n_mapped[0], (long long)n_tot[0], SW_MIN_MAPQ);
+	for (it = kh_begin(my_hash); it != kh_end(my_hash); ++it)
+		if (kh_exist(my_hash, it)) free(kh_val(my_hash, it).a);
+	kh_destroy(64, my_hash);
+	free(recs);
+}

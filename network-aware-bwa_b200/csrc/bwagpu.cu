@@ -369,7 +369,22 @@ static const int N_PASSES = 3;
 // bump-allocated within a launch, so it can run dry -- the reads it fails are retried from scratch in pass 1 (guaranteed): few enough threads
 // that each can own opt->max_entries + 16 records, which the search can never exceed (bwtgap.c:140
 // stops it first).
-static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt)
+typedef void (*search_fn)(const Batch);
+static search_fn search_kernel(bool stats, bool pooled, bool stdmode)
+{
+	static const search_fn tab[8] = {k_search<false, false, false>, k_search<false, false, true>, k_search<false, true, false>,
+	                                 k_search<false, true, true>,   k_search<true, false, false>, k_search<true, false, true>,
+	                                 k_search<true, true, false>,   k_search<true, true, true>};
+	return tab[(stats ? 4 : 0) | (pooled ? 2 : 0) | (stdmode ? 1 : 0)];
+}
+// bucket heads in shared memory: u16 per (bucket, thread) in pass 0 (private arena), u32 in the pooled passes
+static size_t search_smem(bool pooled, uint32_t n_stacks)
+{
+	return BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * (pooled ? sizeof(uint32_t) : sizeof(uint16_t)) : 0;
+}
+static bool is_stdmode(int mode) { return (mode & 0x01) && !(mode & 0x04) && !(mode & 0x10); }
+
+static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt, bool stdmode)
 {
 	Pass &T = c->pass_buf[t];
 	// the shared pool: BWAGPU_POOL_MB (default 16384) per lane, never more than a quarter of what is free
@@ -388,23 +403,16 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	if (t <= 1) {
 		// pass 0: private arenas only (k_search<.., false>); pass 1: same occupancy, arenas continue in the pool
 		int bps = 0, bps_p = 0;
-		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0; // bucket heads
-		CK(cudaFuncSetAttribute(k_search<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(k_search<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(k_search<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(k_search<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		if (g_stats_enabled) {
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<true, false>, 128, smem));
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_p, k_search<true, true>, 128, smem));
-		} else {
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_search<false, false>, 128, smem));
-			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_p, k_search<false, true>, 128, smem));
-		}
+		for (int v = 0; v < 8; ++v)
+			CK(cudaFuncSetAttribute(search_kernel(v & 4, v & 2, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                        (int)search_smem(v & 2, n_stacks)));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, search_kernel(g_stats_enabled, false, stdmode), 128, search_smem(false, n_stacks)));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_p, search_kernel(g_stats_enabled, true, stdmode), 128, search_smem(true, n_stacks)));
 		if (t == 1) bps = bps_p;
 		if (bps < 1) bps = 1;
 		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_T1_BLOCKS_PER_SM", 64));
 		T.slots_blocks = (uint32_t)(bps * c->n_sm);
-		T.cap = env_u32("BWAGPU_T1_CAP", 2048);
+		T.cap = std::min<uint32_t>(env_u32("BWAGPU_T1_CAP", 2048), 65535u); // pass-0 heads are u16
 	} else {
 		// guaranteed: threads x (chunks one search may need) <= pool
 		const uint32_t per_thread = (need + ARENA_CHUNK - 1) >> ARENA_CHUNK_LOG;
@@ -522,7 +530,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	for (int pass = 0; n_jobs > 0; ++pass) {
 		const int t = pass < N_PASSES ? pass : N_PASSES - 1;
 		if (pass > 8) return fail("%d reads still unfinished after %d passes", n_jobs, pass);
-		if (pass_setup(c, t, n_stacks, (uint32_t)opt.max_entries)) return 1;
+		if (pass_setup(c, t, n_stacks, (uint32_t)opt.max_entries, is_stdmode(opt.mode))) return 1;
 		Pass &T = c->pass_buf[t];
 		B.ent = T.ent.p; B.nxt = T.nxt.p; B.heads = T.heads.p;
 		B.cap = T.cap;
@@ -551,14 +559,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		uint32_t blocks = T.slots_blocks;
 		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
 		if (blocks > need) blocks = need;
-		const size_t smem = BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * sizeof(uint32_t) : 0;
-		if (t == 0) {
-			if (stats) k_search<true, false><<<blocks, 128, smem, c->st>>>(B);
-			else k_search<false, false><<<blocks, 128, smem, c->st>>>(B);
-		} else {
-			if (stats) k_search<true, true><<<blocks, 128, smem, c->st>>>(B);
-			else k_search<false, true><<<blocks, 128, smem, c->st>>>(B);
-		}
+		search_kernel(stats, t != 0, is_stdmode(opt.mode))<<<blocks, 128, search_smem(t != 0, n_stacks), c->st>>>(B);
 		CK(cudaGetLastError());
 		c->stats.launches++;
 		CK(cudaEventRecord(c->ev[9 + 2 * t], c->st));

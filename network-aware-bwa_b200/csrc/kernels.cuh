@@ -303,11 +303,11 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #ifndef BWAGPU_MINBLOCKS
 #define BWAGPU_MINBLOCKS 1 // __launch_bounds__ second argument: blocks/SM the register allocator must allow
 #endif
-// Measured on B200, 10M x 76bp (profiles/r1_ab_experiments.md): bucket heads in shared memory and an
-// L1 prefetch of the next record to pop are both slightly SLOWER than plain global heads; kept as
-// switches for other workloads.
+// Measured on B200, 10M x 76bp (profiles/r1_ab_experiments.md).  Bucket heads in shared memory were a wash
+// while six context loads per node competed for L1; with the single context word (k_ctx) they win 5 %
+// and are the default.  An L1 prefetch of the next record to pop is slower; kept as a switch.
 #ifndef BWAGPU_SMEM_HEADS
-#define BWAGPU_SMEM_HEADS 0
+#define BWAGPU_SMEM_HEADS 1
 #endif
 #ifndef BWAGPU_PREFETCH_TOP
 #define BWAGPU_PREFETCH_TOP 0
@@ -319,7 +319,7 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #define BWAGPU_BATCH_POP 0 // N > 0 (needs BWAGPU_CONVERGE=1): memory pops wait until N lanes of the warp want one
 #endif
 #ifndef BWAGPU_NO_FREELIST
-#define BWAGPU_NO_FREELIST 0 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
+#define BWAGPU_NO_FREELIST 1 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
 #endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
@@ -328,32 +328,35 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 // POOLED = false: the private arena only (no chunk indirection anywhere in the loop) -- pass 0, where
 // nearly every read of an ordinary workload finishes.  POOLED = true: the arena continues in chunks of
 // the shared pool -- the passes that pick up the reads whose search went deeper.
-template <bool STATS, bool POOLED>
+// STDMODE = true: gap_opt_t::mode has BWA_MODE_GAPE set and LOGGAP / NONSTOP clear (the default of
+// gap_init_opt, bwtaln.c:19-35, and of every BASELINE.json config): the three tests fold at compile time.
+template <bool POOLED> struct HeadT { typedef uint32_t type; };
+#if !defined(BWAGPU_HOST_EMU)
+template <> struct HeadT<false> { typedef uint16_t type; }; // pass 0: private arena of <= 65535 records
+#endif
+template <bool STATS, bool POOLED, bool STDMODE>
 __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 {
+	typedef typename HeadT<POOLED>::type head_t;
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	uint4 *const ent = B.ent + (size_t)slot * B.cap;
 	uint32_t *const nxt = B.nxt + (size_t)slot * B.cap;
 	// bucket list heads: shared memory, bucket-major (heads[s * blockDim + tid]: lanes never
 	// conflict on a bank whatever buckets they touch, since blockDim is a multiple of 32)
 #ifdef BWAGPU_HOST_EMU
-	static uint32_t s_heads[256];
-	uint32_t *const heads = s_heads + threadIdx.x;
+	static head_t s_heads[256];
+	head_t *const heads = s_heads + threadIdx.x;
 	const uint32_t HS = blockDim.x; // stride between buckets
 #elif BWAGPU_SMEM_HEADS
-	extern __shared__ uint32_t s_heads[];
-	uint32_t *const heads = s_heads + threadIdx.x;
+	extern __shared__ __align__(16) unsigned char s_heads_raw[];
+	head_t *const heads = reinterpret_cast<head_t *>(s_heads_raw) + threadIdx.x;
 	const uint32_t HS = blockDim.x;
 #else
 	uint32_t *const heads = B.heads + (size_t)slot * B.n_stacks;
 	const uint32_t HS = 1;
 #endif
 	const GapOpt &O = B.opt;
-#ifdef BWAGPU_FIX_MODE // A/B switch: gap_opt_t::mode known at compile time
-	constexpr bool gape_mode = BWAGPU_FIX_MODE & 0x01, loggap = BWAGPU_FIX_MODE & 0x04, nonstop = BWAGPU_FIX_MODE & 0x10;
-#else
-	const bool gape_mode = O.mode & 0x01, loggap = O.mode & 0x04, nonstop = O.mode & 0x10;
-#endif
+	const bool gape_mode = STDMODE || (O.mode & 0x01), loggap = !STDMODE && (O.mode & 0x04), nonstop = !STDMODE && (O.mode & 0x10);
 	// The reversed genome has the forward genome's base composition, so C() (bwt_t::L2) and
 	// seq_len are the same for both indexes; only the block array and `primary` differ.
 	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
 #endif
 		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
-		else { *nxt_at(idx) = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = idx; }
+		else { *nxt_at(idx) = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
 		mask_set(s);
 	};
 
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				else {
 					const int s = mask_lowest();
 					if (s != cur_s) {
-						if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s * HS] = cur_head;
+						if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s * HS] = (head_t)cur_head;
 						cur_s = s; cur_head = heads[s * HS];
 					}
 					const uint32_t idx = cur_head;

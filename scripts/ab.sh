@@ -6,5 +6,5 @@ for v in "$@"; do
   python bench.py $A 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
-print('value %.4g ms/step %.1f tiers %s t2 %d stored/read %.0f own/read %.0f parity %s' % (d['value'], d['ms_per_step'], [round(x,1) for x in r['tier_ms_per_step']], d['config']['tier2_reads'], r['stored_pushes_per_read'], r['own_32B_blocks_per_read'], d['parity_sample']['mismatches']), r['pops_per_read'], r['per_read'], r['stats_pass_ms'])"
+print('value %.4g ms/step %.1f width %.1f tiers %s t2 %d stored/read %.0f own/read %.0f parity %s' % (d['value'], d['ms_per_step'], r['width_ms_per_step'], [round(x,1) for x in r['tier_ms_per_step']], d['config']['tier2_reads'], r['stored_pushes_per_read'], r['own_32B_blocks_per_read'], d['parity_sample']['mismatches']), r['pops_per_read'], r['per_read'], r['stats_pass_ms'])"
 done

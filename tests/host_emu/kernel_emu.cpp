@@ -3,6 +3,7 @@
 // the same host-side preparation (hostprep.h) the library uses.  Built by
 // tests/test_kernel_logic.py into tests/host_emu/libkernel_emu.so.
 #define BWAGPU_HOST_EMU 1
+#include <stdlib.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -141,7 +142,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 			for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
 			for (int q = 0; q < n_jobs; ++q) { blockIdx.x = (unsigned)q; k_ctx(B); }
 		}
-		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; k_search<true, true>(B); }
+		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; { if ((opt->mode & 0x15) == 0x01 && !getenv("EMU_GENERIC_MODE")) k_search<true, true, true>(B); else k_search<true, true, false>(B); } }
 		if (stats8) stats8[4 + t] = (unsigned long long)counters[1];
 		if (counters[1] > 0 && t == 1) { g_err = "reads exceeded the largest tier"; return 1; }
 		jobs = ovf; n_jobs = counters[1];

@@ -572,6 +572,7 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 				bwa_seq_t *p[2] = {&recs[i].bwa_seq[0], &recs[i].bwa_seq[1]};
 				bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(iinfos, &recs[i]), dummy_tot, dummy_mapped);
 			}
+		g_sw_mode = SW_REAL;
 		swq_run(&g_sw);
 		g_sw_mode = SW_REPLAY;
 		for (i = lo; i < hi; ++i)

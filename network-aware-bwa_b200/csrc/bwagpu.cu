@@ -380,7 +380,7 @@ static search_fn search_kernel(bool stats, bool pooled, bool stdmode)
 // bucket heads in shared memory: u16 per (bucket, thread) in pass 0 (private arena), u32 in the pooled passes
 static size_t search_smem(bool pooled, uint32_t n_stacks)
 {
-	return BWAGPU_SMEM_HEADS ? (size_t)128 * n_stacks * (pooled ? sizeof(uint32_t) : sizeof(uint16_t)) : 0;
+	return BWAGPU_SMEM_HEADS ? (size_t)128 * (n_stacks + 2) * (pooled ? sizeof(uint32_t) : sizeof(uint16_t)) : 0; // + the hit list's two ends
 }
 static bool is_stdmode(int mode) { return (mode & 0x01) && !(mode & 0x04) && !(mode & 0x10); }
 
@@ -435,7 +435,7 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	if (c->ctab.reserve(slots * stride)) return 1;
 	T.ctab_stride = stride;
 #if !BWAGPU_SMEM_HEADS
-	if (T.heads.reserve(slots * n_stacks)) return 1;
+	if (T.heads.reserve(slots * (n_stacks + 2))) return 1;
 #endif
 	return 0;
 }

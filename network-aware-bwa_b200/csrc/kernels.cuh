@@ -334,6 +334,55 @@ template <bool POOLED> struct HeadT { typedef uint32_t type; };
 #if !defined(BWAGPU_HOST_EMU)
 template <> struct HeadT<false> { typedef uint16_t type; }; // pass 0: private arena of <= 65535 records
 #endif
+
+// Non-empty score buckets.  The general form covers 256 buckets (the ABI's limit); SMALL covers scores
+// 0..63 in one word -- enough for every default-option workload (76 bp, -n 0.04 -o 1: scores <= 27) -- and
+// is what pass 0 uses: a push to a bucket >= 64 sends the read to the next pass like an arena overflow.
+template <bool SMALL> struct BucketMask {
+	uint64_t m0, m1, m2, m3;
+	__device__ __forceinline__ void reset() { m0 = m1 = m2 = m3 = 0; }
+	__device__ __forceinline__ bool fits(int) const { return true; }
+	__device__ __forceinline__ void set(int s)
+	{
+		const uint64_t bit = 1ull << (s & 63);
+		const int w = s >> 6;
+		m0 |= w == 0 ? bit : 0ull; m1 |= w == 1 ? bit : 0ull; m2 |= w == 2 ? bit : 0ull; m3 |= w == 3 ? bit : 0ull;
+	}
+	__device__ __forceinline__ void clear(int s)
+	{
+		const uint64_t bit = 1ull << (s & 63);
+		const int w = s >> 6;
+		m0 &= ~(w == 0 ? bit : 0ull); m1 &= ~(w == 1 ? bit : 0ull); m2 &= ~(w == 2 ? bit : 0ull); m3 &= ~(w == 3 ? bit : 0ull);
+	}
+	__device__ __forceinline__ bool test(int s) const
+	{
+		const uint64_t w = s < 64 ? m0 : s < 128 ? m1 : s < 192 ? m2 : m3;
+		return (w >> (s & 63)) & 1ull;
+	}
+	__device__ __forceinline__ bool any() const { return (m0 | m1 | m2 | m3) != 0; }
+	__device__ __forceinline__ int lowest() const
+	{
+		if (m0) return __ffsll((long long)m0) - 1;
+		if (m1) return 64 + __ffsll((long long)m1) - 1;
+		if (m2) return 128 + __ffsll((long long)m2) - 1;
+		return 192 + __ffsll((long long)m3) - 1;
+	}
+};
+template <> struct BucketMask<true> {
+	uint64_t m0;
+	__device__ __forceinline__ void reset() { m0 = 0; }
+	__device__ __forceinline__ bool fits(int s) const { return s < 64; }
+	__device__ __forceinline__ void set(int s) { m0 |= 1ull << s; }
+	__device__ __forceinline__ void clear(int s) { m0 &= ~(1ull << s); }
+	__device__ __forceinline__ bool test(int s) const { return (m0 >> s) & 1ull; }
+	__device__ __forceinline__ bool any() const { return m0 != 0; }
+	__device__ __forceinline__ int lowest() const { return __ffsll((long long)m0) - 1; }
+};
+
+// Per-thread state is kept deliberately small (registers decide how many reads an SM has in flight, and the
+// kernel is latency-bound): the node being processed is (k, l, e_pos, e_tag) with no second copy; the match
+// continuation overwrites k/l in place and is marked by one flag; the context word stays packed; per-read
+// constants share one register; the hit list's ends live beside the bucket heads.
 template <bool STATS, bool POOLED, bool STDMODE>
 __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 {
@@ -341,10 +390,10 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	uint4 *const ent = B.ent + (size_t)slot * B.cap;
 	uint32_t *const nxt = B.nxt + (size_t)slot * B.cap;
-	// bucket list heads: shared memory, bucket-major (heads[s * blockDim + tid]: lanes never
-	// conflict on a bank whatever buckets they touch, since blockDim is a multiple of 32)
+	// bucket list heads: shared memory, bucket-major (heads[s * blockDim + tid]); two more slots per thread
+	// hold the first and last record of the read's hit list
 #ifdef BWAGPU_HOST_EMU
-	static head_t s_heads[256];
+	static head_t s_heads[264];
 	head_t *const heads = s_heads + threadIdx.x;
 	const uint32_t HS = blockDim.x; // stride between buckets
 #elif BWAGPU_SMEM_HEADS
@@ -352,15 +401,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	head_t *const heads = reinterpret_cast<head_t *>(s_heads_raw) + threadIdx.x;
 	const uint32_t HS = blockDim.x;
 #else
-	uint32_t *const heads = B.heads + (size_t)slot * B.n_stacks;
+	uint32_t *const heads = B.heads + (size_t)slot * (B.n_stacks + 2);
 	const uint32_t HS = 1;
 #endif
+	const uint32_t HIT_HEAD = B.n_stacks * HS, HIT_TAIL = (B.n_stacks + 1) * HS; // valid while n_aln > 0
 	const GapOpt &O = B.opt;
 	const bool gape_mode = STDMODE || (O.mode & 0x01), loggap = !STDMODE && (O.mode & 0x04), nonstop = !STDMODE && (O.mode & 0x10);
 	// The reversed genome has the forward genome's base composition, so C() (bwt_t::L2) and
 	// seq_len are the same for both indexes; only the block array and `primary` differ.
 	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
-	auto Cof = [&](uint32_t c) -> uint32_t { return c == 0 ? 0u : c == 1 ? C1 : c == 2 ? C2 : C3; };
 
 	// record idx -> address: the private arena first, then this thread's pool chunks
 	const uint32_t CAP0 = B.cap;
@@ -379,54 +428,42 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 
 	int mode = MODE_NEW;
 	// per-read state
-	int rid = -1, len = 0, max_diff = 0, opt_max_diff = 0, max_gapo = 0;
+	int rid = -1, max_diff = 0;
+	uint32_t rd = 0; // len | max_gapo << 16 | local_opt.max_diff << 24   (ReadMeta)
+#define RD_LEN ((int)(rd & 0xffffu))
+#define RD_GAPO ((int)((rd >> 16) & 0xffu))
+#define RD_MAXDIFF ((int)(rd >> 24))
+	uint32_t w_off = 0; // the read's offset into the width / context arenas
 	int best_score = 0, best_cnt = 0, n_aln = 0, n_entries = 0, max_entries = 0;
-	bool has_seed = false, overflow = false, have_best = false;
-	const uint2 *cx_base = nullptr; // the read's context words (k_ctx)
-	uint32_t *w_base = nullptr;     // the read's widths: only gap_shadow touches them
+	bool overflow = false;
 	// Bucket lists.  heads[s] in memory is only meaningful while bit s of the mask is set, and
 	// the head of the bucket popped last lives in a register (cur_s / cur_head), so neither a
 	// reset pass nor a head load per pop is needed.
-	uint64_t mask0 = 0, mask1 = 0, mask2 = 0, mask3 = 0; // non-empty buckets
+	BucketMask<!POOLED> mask;
+	mask.reset();
 	int cur_s = -1;
 	uint32_t cur_head = NIL;
 	uint32_t bump = 0, free_head = NIL, spare = NIL;
-	uint32_t hit_head = NIL, hit_tail = NIL; // the read's hits: a list through the same arena, in discovery order
-	Entry held = {0, 0, 0, 0}; bool held_valid = false;
-	Entry e = {0, 0, 0, 0}; // node being processed (always a plain node)
-	uint32_t derive_c = 0;  // MODE_DERIVE: which child interval of e.{k,l} to take
-	int ii = 0;             // exact-tail cursor
-	uint32_t ce = 0;        // exact tail: base at ii-1
-	int m = 0, m_seed = 0, i = 0;
-	uint32_t k = 0, l = 0;
-	// context of the current node, loaded together with its occurrence blocks:
-	// wb1 = wb[i-1], wb2 = wb[i-2], sw1 = seed_wb[si], sw2 = seed_wb[si-1], c1 = str[i-1]   (i = the node's i)
-	uint32_t wb1 = 0, wb2 = 0, sw1 = 0, sw2 = 0, c1 = 0;
+	// the node being processed: interval (k, l), e_pos = i | last_diff_pos << 16, e_tag = n_mm | n_gapo << 8 |
+	// n_gape << 16 | state << 24 | a << 26.  held: the match child of the node just expanded is the next pop
+	// (pushed last, same score); its interval is already in k/l, its position in i, its counts are e_tag's.
+	uint32_t k = 0, l = 0, e_pos = 0, e_tag = 0;
+	bool held = false;
+	uint32_t cc = 0; // MODE_DERIVE: which child interval of (k, l) to take; MODE_EXACT: the base at i-1
+	int m = 0, i = 0; // i doubles as the exact tail's cursor
+	// context of the current node, loaded together with its occurrence blocks (k_ctx): width[i-1], width[i-2].bid,
+	// the two seed-width entries, str[i-1], str[i-2]
+	uint2 cw = make_uint2(0u, 0u);
+#define CW_WB1 (cw.x & (CW_BID | WB_EQ))
+#define CW_C1 ((cw.x >> 12) & 7u)
+#define CW_B2 ((int)((cw.x >> 16) & CW_BID))
+#define CW_CN ((cw.x >> 28) & 7u)
+#define CW_SW1 (cw.y & (CW_BID | WB_EQ))
+#define CW_S2 ((int)((cw.y >> 16) & CW_BID))
 	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0, n_pruned = 0, n_expand = 0, n_exact = 0, n_derive = 0, n_trips = 0;
 	if (STATS) atomicMin(B.stats + 12, gtime());
 
 	auto score_of = [&](int mm, int go, int ge) { return mm * O.s_mm + go * O.s_gapo + ge * O.s_gape; };
-
-	auto mask_set = [&](int s) {
-		const uint64_t bit = 1ull << (s & 63);
-		const int w = s >> 6;
-		mask0 |= w == 0 ? bit : 0ull; mask1 |= w == 1 ? bit : 0ull; mask2 |= w == 2 ? bit : 0ull; mask3 |= w == 3 ? bit : 0ull;
-	};
-	auto mask_clear = [&](int s) {
-		const uint64_t bit = 1ull << (s & 63);
-		const int w = s >> 6;
-		mask0 &= ~(w == 0 ? bit : 0ull); mask1 &= ~(w == 1 ? bit : 0ull); mask2 &= ~(w == 2 ? bit : 0ull); mask3 &= ~(w == 3 ? bit : 0ull);
-	};
-	auto mask_test = [&](int s) -> bool {
-		const uint64_t w = s < 64 ? mask0 : s < 128 ? mask1 : s < 192 ? mask2 : mask3;
-		return (w >> (s & 63)) & 1ull;
-	};
-	auto mask_lowest = [&]() -> int {
-		if (mask0) return __ffsll((long long)mask0) - 1;
-		if (mask1) return 64 + __ffsll((long long)mask1) - 1;
-		if (mask2) return 128 + __ffsll((long long)mask2) - 1;
-		return 192 + __ffsll((long long)mask3) - 1;
-	};
 
 	auto chunk_alloc = [&]() -> uint32_t {
 		unsigned long long old = *(volatile unsigned long long *)B.x_free_top;
@@ -453,8 +490,10 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		}
 	};
 
-	// one arena record: the slot freed by the latest pop, else the free list, else fresh space
-	// (private arena, then chunks of the shared pool).  NIL + overflow when the pool has run dry.
+	// one arena record: the slot freed by the latest pop, else (pooled passes) the free list, else fresh space
+	// (private arena, then chunks of the shared pool).  NIL + overflow when there is none.  Pass 0 keeps no free
+	// list: a slot freed while `spare` is occupied is not reused, and a read that runs through the private arena
+	// that way goes to the next pass.
 	auto alloc_rec = [&]() -> uint32_t {
 		uint32_t idx;
 		if (spare != NIL) { idx = spare; spare = NIL; }
@@ -476,18 +515,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	auto push_rec = [&](uint32_t rk, uint32_t rl, uint32_t pos, uint32_t tag, int s, int n_children) {
 		n_entries += n_children;
 		if (STATS) n_pushes += n_children;
-		if (have_best && !nonstop && s > best_score + O.s_mm) return; // phantoms: counted, never stored
+		if (n_aln > 0 && !nonstop && s > best_score + O.s_mm) return; // phantoms: counted, never stored
 		if (STATS) ++n_stored;
+		if (!mask.fits(s)) { overflow = true; return; }
 		const uint32_t idx = alloc_rec();
 		if (idx == NIL) return;
-#if BWAGPU_STREAM_STACK
-		__stcs(ent_at(idx), make_uint4(rk, rl, pos, tag));
-#else
 		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
-#endif
 		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
-		else { *nxt_at(idx) = mask_test(s) ? heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
-		mask_set(s);
+		else { *nxt_at(idx) = mask.test(s) ? (uint32_t)heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
+		mask.set(s);
 	};
 
 	// copies the finished read's results out and resets the per-slot stack
@@ -502,48 +538,48 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			const int o = atomicAdd(B.overflow_count, 1);
 			B.overflow_ids[o] = rid;
 		} else {
-			uint32_t h = hit_head;
+			uint32_t h = n_aln > 0 ? (uint32_t)heads[HIT_HEAD] : NIL;
 			for (int j = 0; j < n_aln; ++j) { B.pool[off + j] = *ent_at(h); h = *nxt_at(h); }
 			B.n_aln[rid] = n_aln;
 			B.pool_off[rid] = off;
 			B.max_entries[rid] = max_entries;
 		}
-		mask0 = mask1 = mask2 = mask3 = 0; cur_s = -1; cur_head = NIL;
-		bump = 0; free_head = NIL; spare = NIL; held_valid = false; n_entries = 0;
-		hit_head = hit_tail = NIL;
+		mask.reset(); cur_s = -1; cur_head = NIL;
+		bump = 0; free_head = NIL; spare = NIL; held = false; n_entries = 0; n_aln = 0;
 		if (POOLED) while (n_chunks > 1) chunk_free(ctab[--n_chunks]); // keep one chunk, recycle the rest
 	};
 
 	// action for found hits (bwtgap.c:167-200).  Returns false when the search must stop.
 	auto process_hit = [&](uint32_t hk, uint32_t hl) -> bool {
-		const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+		const int mm = (int)(e_tag & 0xffu), go = (int)((e_tag >> 8) & 0xffu), ge = (int)((e_tag >> 16) & 0xffu);
 		const int score = score_of(mm, go, ge);
+		const int len = RD_LEN;
 		bool do_add = true;
 		if (n_aln == 0) {
-			have_best = true;
 			best_score = score;
 			int best_diff = mm + go;
 			if (gape_mode) best_diff += ge;
-			if (!nonstop) max_diff = (best_diff + 1 > opt_max_diff) ? opt_max_diff : best_diff + 1; // top2 behaviour
+			if (!nonstop) max_diff = (best_diff + 1 > RD_MAXDIFF) ? RD_MAXDIFF : best_diff + 1; // top2 behaviour
 		}
 		if (score == best_score) best_cnt += (int)(hl - hk + 1);
 		else if (best_cnt > O.max_top2) return false; // top2b behaviour
 		if (go) { // the hit may have been found already (gap in a tandem repeat)
-			for (uint32_t h = hit_head; h != NIL; h = *nxt_at(h)) {
+			uint32_t h = n_aln > 0 ? (uint32_t)heads[HIT_HEAD] : NIL;
+			for (int j = 0; j < n_aln; ++j, h = *nxt_at(h)) {
 				const uint4 q = *ent_at(h);
 				if (q.y == hk && q.z == hl) { do_add = false; break; }
 			}
 		}
 		if (do_add) {
-			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array, then refresh
-			// the packed (bid, w[t-1]==w[t]) view of the positions it may have changed
-			const uint32_t a = E_A(e);
-			const size_t wo = (size_t)(w_base - B.w) + (size_t)a * WSTRIDE(len);
+			// gap_shadow (bwtgap.c:81-91) on the searched strand's width array, then refresh the packed
+			// (bid, w[t-1]==w[t]) view and the context words of the positions it may have changed
+			const uint32_t a = (e_tag >> 26) & 1u;
+			const size_t wo = (size_t)w_off + (size_t)a * WSTRIDE(len);
 			uint32_t *w = B.w + wo;
 			uint16_t *wb = B.bid + wo;
 			uint2 *cx = B.ctx + wo;
 			const uint32_t x = hl - hk + 1, mx = B.ix[1 - a].seq_len;
-			const int ldp = E_LDP(e);
+			const int ldp = (int)(e_pos >> 16);
 			uint32_t j = 0, prev = 0, prev_nb = 0;
 			for (int t = 0; t <= ldp && t <= len; ++t) {
 				uint32_t wv = w[t], bid = wb[t] & WB_BID;
@@ -563,15 +599,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			if (idx != NIL) {
 				*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score);
 				*nxt_at(idx) = NIL;
-				if (hit_tail != NIL) *nxt_at(hit_tail) = idx; else hit_head = idx;
-				hit_tail = idx;
+				if (n_aln > 0) *nxt_at((uint32_t)heads[HIT_TAIL]) = idx; else heads[HIT_HEAD] = (head_t)idx;
+				heads[HIT_TAIL] = (head_t)idx;
 				++n_aln;
 			}
 		}
 		return true;
 	};
 
-	// hit / exact tail / expansion for the node in e with interval (k, l) (bwtgap.c:160-165, 201).
+	// hit / exact tail / expansion for the node (k, l, e_pos, e_tag) at position i (bwtgap.c:160-165, 201).
 	// Returns true when the trip goes on to an occurrence lookup.
 	auto decide = [&]() -> bool {
 		if (i == 0) {
@@ -579,9 +615,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
 			return false;
 		}
-		if (m == 0 && (E_ST(e) == STATE_M || gape_mode || E_GE(e) == O.max_gape)) { // no diff allowed
-			if (c1 > 3u) { mode = MODE_POP; return false; } // N in the tail: no match
-			ii = i; ce = c1;
+		if (m == 0 && (((e_tag >> 24) & 3u) == STATE_M || gape_mode || (int)((e_tag >> 16) & 0xffu) == O.max_gape)) { // no diff allowed
+			cc = CW_C1;
+			if (cc > 3u) { mode = MODE_POP; return false; } // N in the tail: no match
 			mode = MODE_EXACT;
 		} else {
 			--i;
@@ -594,88 +630,62 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	// of guarded blocks (NEW / POP / loads / pruning / consume), so the warp re-converges
 	// after each block and ALL lanes that need memory this trip issue their loads together.
 	for (;;) {
-#if BWAGPU_CONVERGE
-		__syncwarp();
-		if (__all_sync(0xffffffffu, mode == MODE_DONE)) break;
-#endif
 		bool fresh = false, need_derive = false;
-		bool active = mode != MODE_DONE; // takes part in this trip's occurrence lookup
+		bool active = true; // takes part in this trip's occurrence lookup
 		if (STATS) ++n_trips;
 		if (mode == MODE_NEW) {
 			const int job = atomicAdd(B.work_counter, 1);
 			if (job >= B.n_jobs) {
 				if (STATS) atomicMin(B.stats + 11, gtime());
-#if BWAGPU_CONVERGE
-				mode = MODE_DONE; active = false;
-#else
 				break;
-#endif
+			}
+			rid = B.jobs ? B.jobs[job] : job;
+			const ReadMeta md = B.meta[rid];
+			const int len = md.len;
+			rd = (uint32_t)md.len | (uint32_t)md.max_gapo << 16 | (uint32_t)md.max_diff << 24;
+			overflow = false;
+			n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
+			max_diff = md.max_diff;
+			// len == 0: bwtaln.c:134 (aln = 0, n_aln = 0); too many N: bwtgap.c:118-123
+			// (*pmax_entries is left untouched there)
+			if (len == 0 || (int)md.n_amb > max_diff) {
+				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
+				active = false; // stays in MODE_NEW
 			} else {
-				rid = B.jobs ? B.jobs[job] : job;
-				const ReadMeta md = B.meta[rid];
-				len = md.len;
-				overflow = false; have_best = false;
-				n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
-				opt_max_diff = max_diff = md.max_diff;
-				max_gapo = md.max_gapo;
-				// len == 0: bwtaln.c:134 (aln = 0, n_aln = 0); too many N: bwtgap.c:118-123
-				// (*pmax_entries is left untouched there)
-				if (len == 0 || (int)md.n_amb > max_diff) {
-					B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
-					active = false; // stays in MODE_NEW
-				} else {
-					has_seed = len > O.seed_len;
-					cx_base = B.ctx + md.w_off;
-					w_base = B.w + md.w_off;
-					best_score = score_of(max_diff + 1, max_gapo + 1, O.max_gape + 1);
-					// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
-					push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
-					held.k = 0u; held.l = B.ix[0].seq_len; held.pos = (uint32_t)len; held.tag = 1u << 26;
-					held_valid = true; ++n_entries;
-					if (STATS) ++n_pushes;
-					mode = MODE_POP;
-				}
+				w_off = md.w_off;
+				best_score = score_of(max_diff + 1, (int)md.max_gapo + 1, O.max_gape + 1);
+				// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
+				push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
+				k = 0u; l = B.ix[0].seq_len; i = len; e_tag = 1u << 26;
+				held = true; ++n_entries;
+				if (STATS) ++n_pushes;
+				mode = MODE_POP;
 			}
 		}
 
-#if BWAGPU_BATCH_POP && BWAGPU_CONVERGE
-		{ // Phase batching: lanes are independent reads, so a lane may sit a trip out.  Popping a record from
-		  // memory is the expensive, minority path of the POP block; lanes that need it wait until enough
-		  // lanes of the warp need it too (or nobody else has work), so the path runs with more lanes and
-		  // most trips carry no second memory wait.
-			const bool is_pop = active && mode == MODE_POP;
-			const bool stopping = is_pop && (overflow || n_entries == 0 || n_entries > O.max_entries ||
-			                                 (!held_valid && !(mask0 | mask1 | mask2 | mask3)));
-			const bool mem_pop = is_pop && !stopping && !held_valid;
-			const unsigned mp = __ballot_sync(0xffffffffu, mem_pop);
-			const unsigned other = __ballot_sync(0xffffffffu, active && !mem_pop);
-			if (mem_pop && __popc(mp) < BWAGPU_BATCH_POP && other) active = false;
-		}
-#endif
 		if (active && mode == MODE_POP) {
 			bool stop = overflow || n_entries == 0;
 			if (!stop) {
 				if (max_entries < n_entries) max_entries = n_entries;
 				// > max_entries (bwtgap.c:140); only phantoms left: the reference pops one and stops
-				stop = n_entries > O.max_entries || (!held_valid && !(mask0 | mask1 | mask2 | mask3));
+				stop = n_entries > O.max_entries || (!held && !mask.any());
 			}
 			if (stop) { finish_read(); mode = MODE_NEW; active = false; }
 			else {
 				// gap_pop (bwtgap.c:66-79)
-				if (held_valid) { e = held; held_valid = false; }
-				else {
-					const int s = mask_lowest();
+				if (held) { // the match child: counts of its parent, state M, no difference at its position
+					held = false;
+					e_pos = (uint32_t)i;
+					e_tag &= ~(3u << 24);
+				} else {
+					const int s = mask.lowest();
 					if (s != cur_s) {
-						if (cur_s >= 0 && mask_test(cur_s)) heads[cur_s * HS] = (head_t)cur_head;
+						if (cur_s >= 0 && mask.test(cur_s)) heads[cur_s * HS] = (head_t)cur_head;
 						cur_s = s; cur_head = heads[s * HS];
 					}
 					const uint32_t idx = cur_head;
 					uint4 *const qp = ent_at(idx);
-#if BWAGPU_STREAM_STACK
-					const uint4 q = __ldcs(qp);
-#else
 					const uint4 q = *qp;
-#endif
 					const uint32_t nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
 					const uint32_t kind = (q.w >> 27) & 3u;
 					uint32_t gm = 0, b = 0;
@@ -687,56 +697,48 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 					if (gm) qp->z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
 					else { // unlink
 						cur_head = nx;
-						if (cur_head == NIL) mask_clear(s);
+						if (cur_head == NIL) mask.clear(s);
 						if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
 						spare = idx;
 					}
-					e.k = q.x; e.l = q.y;
-					if (kind == KIND_PLAIN) { e.pos = q.z; e.tag = q.w; }
+					k = q.x; l = q.y;
+					if (kind == KIND_PLAIN) { e_pos = q.z; e_tag = q.w; }
 					else {
 						const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
 						uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
 						if (kind == KIND_MM) {
 							const uint32_t cb = q.w >> 29; // the parent's read base at pi, kept in the record
-							derive_c = (cb + b + 1u) & 3u;
+							cc = (cb + b + 1u) & 3u;
 							++mm; ci = pi; st = STATE_M; need_derive = true;
 						} else {
 							if (pst == STATE_M) ++go; else ++ge;
 							if (b == 0) { ci = pi; st = STATE_I; }
-							else { ci = pi + 1u; st = STATE_D; derive_c = b - 1u; need_derive = true; }
+							else { ci = pi + 1u; st = STATE_D; cc = b - 1u; need_derive = true; }
 						}
-						e.pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
-						e.tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
+						e_pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
+						e_tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
 					}
+					i = (int)(e_pos & 0xffffu);
 				}
 				--n_entries;
 				if (STATS) ++n_pops;
-				k = e.k; l = e.l; i = E_I(e);
 				fresh = true;
 			}
 		}
 
 		// ---- issue every load this trip depends on before using any of them: the two
-		// occurrence blocks (bwt_2occ4 at bwtgap.c:202 / bwt_2occ at bwt.c:245) and, for a
-		// node just popped, its pruning context.  One memory round trip per trip.
-		const uint32_t a = E_A(e);
+		// occurrence blocks (bwt_2occ4 at bwtgap.c:202 / bwt_2occ at bwt.c:245) and the context word --
+		// the node's own for a node just popped, the next read base for an exact tail.  One memory round trip per trip.
+		const uint32_t a = (e_tag >> 26) & 1u;
 		const DevIndex &ix = B.ix[1 - a];
-		uint32_t jk = 0, jl = 0, cn = 0;
-		uint2 cw = make_uint2(0u, 0u);
+		uint32_t jk = 0, jl = 0;
 		OccBlock ob_l = {0, 0, 0, 0, 0, 0}, ob_k = {0, 0, 0, 0, 0, 0};
 		if (active) {
 			jk = occ_arg(ix, k - 1); jl = occ_arg(ix, l);
 			ob_l = load_block(ix, jl >> 6);
 			ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
-#if !defined(BWAGPU_HOST_EMU) && BWAGPU_PREFETCH_TOP
-			// the record a memory pop would take next: warm it while this trip's loads are in flight
-			if (cur_head != NIL && cur_s >= 0) {
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(ent_at(cur_head)));
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt_at(cur_head)));
-			}
-#endif
-			if (fresh | (mode == MODE_EXACT)) // fresh: the node's own word; exact tail: .x's base field of word ii-1 = str[ii-2]
-				cw = cx_base[(size_t)a * WSTRIDE(len) + (fresh ? i : ii - 1)];
+			if (fresh | (mode == MODE_EXACT)) // fresh: the node's own word; exact tail: .x's base field of word i-1 = str[i-2]
+				cw = B.ctx[(size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)(fresh ? i : i - 1)];
 			if (STATS) {
 				f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
 				if (k == 0) f_ref += 1u;
@@ -748,78 +750,77 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			}
 		}
 
-		if (active) {
-			if (fresh) {
-				wb1 = cw.x & (CW_BID | WB_EQ); c1 = (cw.x >> 12) & 7u;
-				wb2 = (cw.x >> 16) & CW_BID; cn = (cw.x >> 28) & 7u;
-				sw1 = cw.y & (CW_BID | WB_EQ); sw2 = (cw.y >> 16) & CW_BID;
-			} else if (mode == MODE_EXACT) cn = (cw.x >> 12) & 7u;
-		}
 		if (active && fresh) { // pruning tests of bwtgap.c:144-157
-			const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
+			const int mm = (int)(e_tag & 0xffu), go = (int)((e_tag >> 8) & 0xffu), ge = (int)((e_tag >> 16) & 0xffu);
 			if (!nonstop && score_of(mm, go, ge) > best_score + O.s_mm) { finish_read(); mode = MODE_NEW; active = false; }
 			else {
 				m = max_diff - (mm + go);
 				if (gape_mode) m -= ge;
-				if (has_seed) {
-					m_seed = O.max_seed_diff - (mm + go);
-					if (gape_mode) m_seed -= ge;
-				}
-				if (m < 0 || (i > 0 && m < (int)(wb1 & WB_BID))) { if (STATS) ++n_pruned; active = false; } // stays in MODE_POP
+				if (m < 0 || (i > 0 && m < (int)(CW_WB1 & WB_BID))) { if (STATS) ++n_pruned; active = false; } // stays in MODE_POP
 				else if (need_derive) mode = MODE_DERIVE;
 				else active = decide();
 			}
 		}
 
 		if (active) {
-			uint32_t cnt_k[4], cnt_l[4];
-			occ4_in_block(ob_k, jk, cnt_k);
-			occ4_in_block(ob_l, jl, cnt_l);
+			uint32_t nk[4], nl[4]; // the four one-symbol extensions of (k, l): [nk[c], nl[c]]
+			{
+				uint32_t cnt_k[4], cnt_l[4];
+				occ4_in_block(ob_k, jk, cnt_k);
+				occ4_in_block(ob_l, jl, cnt_l);
+				nk[0] = cnt_k[0] + 1; nk[1] = C1 + cnt_k[1] + 1; nk[2] = C2 + cnt_k[2] + 1; nk[3] = C3 + cnt_k[3] + 1;
+				nl[0] = cnt_l[0]; nl[1] = C1 + cnt_l[1]; nl[2] = C2 + cnt_l[2]; nl[3] = C3 + cnt_l[3];
+			}
 
-			if (mode == MODE_DERIVE) { // k,l were the parent's: take child derive_c's interval
+			if (mode == MODE_DERIVE) { // k,l were the parent's: take child cc's interval
 				if (STATS) ++n_derive;
-				k = Cof(derive_c) + sel4(derive_c, cnt_k) + 1;
-				l = Cof(derive_c) + sel4(derive_c, cnt_l);
-				e.k = k; e.l = l;
+				k = sel4(cc, nk);
+				l = sel4(cc, nl);
 				decide(); // next trip looks the child's own interval up
 			} else if (mode == MODE_EXACT) { // bwt_match_exact_alt (bwt.c:237-252), one base per trip
 				if (STATS) ++n_exact;
-				k = Cof(ce) + sel4(ce, cnt_k) + 1;
-				l = Cof(ce) + sel4(ce, cnt_l);
-				--ii;
+				k = sel4(cc, nk);
+				l = sel4(cc, nl);
+				--i;
 				if (k > l) mode = MODE_POP;
-				else if (ii == 0) {
+				else if (i == 0) {
 					mode = MODE_POP;
 					if (!process_hit(k, l)) { finish_read(); mode = MODE_NEW; }
 				} else {
-					ce = cn;
-					if (ce > 3u) mode = MODE_POP;
+					// the base the next step matches, str[i-1]: a tail's first step still holds the node's own word
+					// (str[i_old-2] is its second base field), later steps loaded word i_old-1
+					cc = fresh ? CW_CN : CW_C1;
+					if (cc > 3u) mode = MODE_POP;
 				}
 			} else { // ---- MODE_EXPAND (bwtgap.c:201-259); i was already decremented
 				if (STATS) ++n_expand;
-				const int mm = E_MM(e), go = E_GO(e), ge = E_GE(e);
-				const uint32_t st = E_ST(e);
+				const int mm = (int)(e_tag & 0xffu), go = (int)((e_tag >> 8) & 0xffu), ge = (int)((e_tag >> 16) & 0xffu);
+				const uint32_t st = (e_tag >> 24) & 3u;
 				const uint32_t occ = l - k + 1;
+				const int len = RD_LEN, max_gapo = RD_GAPO;
+				const bool has_seed = len > O.seed_len;
 				bool allow_diff = true, allow_M = true;
 				if (i > 0) {
-					const int b1 = (int)(wb2 & WB_BID); // width[i-1].bid
+					const uint32_t wb1 = CW_WB1;
+					const int b1 = CW_B2; // width[i-1].bid
 					if (b1 > m - 1) allow_diff = false;
 					else if (b1 == m - 1 && (int)(wb1 & WB_BID) == m - 1 && (wb1 & WB_EQ)) allow_M = false;
 					if (has_seed) {
 						const int si = i - (len - O.seed_len);
 						if (si > 0) {
-							const int s1 = (int)(sw2 & WB_BID); // seed_width[si-1].bid
+							const int m_seed = m - max_diff + O.max_seed_diff; // max_seed_diff - (mm + go [+ ge]) (bwtgap.c:153-155)
+							const uint32_t sw1 = CW_SW1;
+							const int s1 = CW_S2; // seed_width[si-1].bid
 							if (s1 > m_seed - 1) allow_diff = false;
 							else if (s1 == m_seed - 1 && (int)(sw1 & WB_BID) == m_seed - 1 && (sw1 & WB_EQ)) allow_M = false;
 						}
 					}
 				}
-				const uint32_t ci = c1;
+				const uint32_t ci = CW_C1;
 				// which of the four one-symbol extensions are non-empty (k' <= l')
-				const uint32_t V = (cnt_k[0] < cnt_l[0] ? 1u : 0u) | (cnt_k[1] < cnt_l[1] ? 2u : 0u) |
-				                   (cnt_k[2] < cnt_l[2] ? 4u : 0u) | (cnt_k[3] < cnt_l[3] ? 8u : 0u);
+				const uint32_t V = (nk[0] <= nl[0] ? 1u : 0u) | (nk[1] <= nl[1] ? 2u : 0u) | (nk[2] <= nl[2] ? 4u : 0u) | (nk[3] <= nl[3] ? 8u : 0u);
 				const int score = score_of(mm, go, ge);
-				const uint32_t ptag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | st << 24 | a << 26;
+				const uint32_t ptag = e_tag; // plain node: no kind / base bits
 				if (allow_diff) {
 					// indels (bwtgap.c:218-247): one KIND_GAP record
 					int tmp;
@@ -841,7 +842,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 								if (gm == 1u) { rpos = (uint32_t)i | (uint32_t)i << 16; rtag = tg | STATE_I << 24; }
 								else {
 									const uint32_t c = 30u - (uint32_t)__clz((int)gm); // bit 1 + c
-									rk = Cof(c) + sel4(c, cnt_k) + 1; rl = Cof(c) + sel4(c, cnt_l);
+									rk = sel4(c, nk); rl = sel4(c, nl);
 									rpos = (uint32_t)(i + 1) | (uint32_t)(i + 1) << 16; rtag = tg | STATE_D << 24;
 								}
 							}
@@ -857,7 +858,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 							uint32_t rk = k, rl = l, rpos = (uint32_t)i | mmask << 16, rtag = ptag | KIND_MM << 27 | ci << 29;
 							if (!(mmask & (mmask - 1))) {
 								const uint32_t c = (ci + (32u - (uint32_t)__clz((int)mmask))) & 3u; // bit j-1 -> c = (ci + j) & 3
-								rk = Cof(c) + sel4(c, cnt_k) + 1; rl = Cof(c) + sel4(c, cnt_l);
+								rk = sel4(c, nk); rl = sel4(c, nl);
 								rpos = (uint32_t)i | (uint32_t)i << 16;
 								rtag = (uint32_t)(mm + 1) | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
 							}
@@ -865,18 +866,25 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						}
 					}
 				}
-				if (ci < 4 && ((V >> ci) & 1u)) { // the match: last push, next pop -> registers
-					held.k = Cof(ci) + sel4(ci, cnt_k) + 1;
-					held.l = Cof(ci) + sel4(ci, cnt_l);
-					held.pos = (uint32_t)i;
-					held.tag = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | STATE_M << 24 | a << 26;
-					held_valid = true; ++n_entries;
+				if (ci < 4 && ((V >> ci) & 1u)) { // the match: last push, next pop -> stays in registers
+					k = sel4(ci, nk);
+					l = sel4(ci, nl);
+					held = true; ++n_entries;
 					if (STATS) ++n_pushes;
 				}
 				mode = MODE_POP;
 			}
 		}
 	}
+#undef RD_LEN
+#undef RD_GAPO
+#undef RD_MAXDIFF
+#undef CW_WB1
+#undef CW_C1
+#undef CW_B2
+#undef CW_CN
+#undef CW_SW1
+#undef CW_S2
 
 	if (STATS) {
 		atomicAdd(B.stats + 0, (unsigned long long)f_ref);

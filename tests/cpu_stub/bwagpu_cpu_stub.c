@@ -1,0 +1,74 @@
+/* bwagpu_cpu_stub.c -- TEST INFRASTRUCTURE ONLY.  Never built into, linked with or loaded by the product.
+ *
+ * Lets the `-m "not gpu"` suite exercise the HOST LOGIC of integration/bwa_gpu_batch.c (batching, record /
+ * replay, ordering of drand48 and of the pass-2 position cache) on a box without a GPU: it defines the
+ * handful of bwa_gpu_* entry points that shim calls and answers them with the reference's own per-record
+ * functions from oracle/_ref/libbwaref.so.  Pre-loaded AHEAD of the shim so that its symbols win:
+ *
+ *   LD_PRELOAD=tests/cpu_stub/libbwagpu_cpu_stub.so:integration/libbwa_gpu_batch.so ref_driver bam2bam ...
+ *
+ * The `-m gpu` twin of the test runs the same command without this stub, i.e. on libbwagpu.so.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "bwtaln.h"
+#include "bwt.h"
+#include "stdaln.h"
+#include "bwa_gpu.h"
+
+static bwt_t *s_bwt[2];
+static const ubyte_t *s_pac;
+static int64_t s_lpac;
+static bwa_cigar_t *s_pool;
+static size_t s_pool_n, s_pool_m;
+
+int bwa_gpu_init(int n, const int *ids) { (void)n; (void)ids; fprintf(stderr, "[cpu_stub] bwa_gpu_* answered by the reference's CPU functions\n"); return 0; }
+void bwa_gpu_destroy(void) {}
+const char *bwa_gpu_last_error(void) { return "cpu stub"; }
+int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64_t l_pac)
+{
+	s_bwt[0] = bwt[0]; s_bwt[1] = bwt[1]; s_pac = pac; s_lpac = l_pac;
+	return 0;
+}
+int bwa_gpu_cal_sa_reads_gap(int n, bwa_seq_t *seqs, const gap_opt_t *opt)
+{
+	int i;
+	for (i = 0; i < n; ++i) bwa_cal_sa_reg_gap(s_bwt, 1, &seqs[i], opt);
+	return 0;
+}
+int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *k, const uint8_t *which, bwtint_t *out)
+{
+	int64_t i;
+	for (i = 0; i < n; ++i) out[i] = bwt_sa(s_bwt[which[i] ? 0 : 1], k[i]);
+	return 0;
+}
+int bwa_gpu_mate_sw_path(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_path_res_t *res, const bwa_cigar_t **cigar_pool)
+{
+	int i;
+	s_pool_n = 0;
+	for (i = 0; i < n; ++i) {
+		const bwa_gpu_sw_job_t *jb = &jobs[i];
+		ubyte_t *ref = (ubyte_t *)calloc(jb->reglen + 1, 1);
+		path_t *path = (path_t *)calloc(jb->reglen + jb->len + 2, sizeof(path_t));
+		int64_t k;
+		int l = 0, path_len = 0, n_cigar = 0, c;
+		bwa_cigar_t *cg;
+		for (k = jb->beg; l < jb->reglen && k < s_lpac; ++k) ref[l++] = s_pac[k >> 2] >> ((~k & 3) << 1) & 3;
+		memset(&res[i], 0, sizeof(res[i]));
+		res[i].score = aln_local_core(ref, l, (ubyte_t *)jb->seq, jb->len, &aln_param_bwa, path, &path_len, 1, 0);
+		res[i].cigar_off = (int64_t)s_pool_n;
+		if (res[i].score >= 0 && path_len > 0) {
+			cg = bwa_aln_path2cigar(path, path_len, &n_cigar);
+			if (s_pool_n + n_cigar > s_pool_m) { s_pool_m = (s_pool_n + n_cigar) * 2 + 1024; s_pool = (bwa_cigar_t *)realloc(s_pool, s_pool_m * sizeof(bwa_cigar_t)); }
+			for (c = 0; c < n_cigar; ++c) s_pool[s_pool_n++] = cg[c];
+			free(cg);
+			res[i].n_cigar = n_cigar;
+			res[i].start_i = path[path_len - 1].i; res[i].start_j = path[path_len - 1].j;
+			res[i].end_i = path[0].i; res[i].end_j = path[0].j;
+		}
+		free(ref); free(path);
+	}
+	*cigar_pool = s_pool;
+	return 0;
+}

@@ -112,16 +112,17 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	for (int t = 0; t < n; ++t) { blockIdx.x = (unsigned)t; k_ctx(B); }
 	if (stats8) { stats8[0] = stats[0]; stats8[1] = stats[1]; }
 	stats[0] = stats[1] = 0;
-	// K3 tiers
-	// pass 0: private arena cap1 + a small shared pool (pool_chunks chunks); pass 1: guaranteed
+	// K3 passes, as bwagpu.cu runs them: 0 = private arena only (k_search<.., false, ..>: small bucket mask, no free
+	// list), 1 = private arena + pool_chunks chunks of the shared pool, 2 = guaranteed
 	const uint32_t need = (uint32_t)opt->max_entries + 16u;
-	const uint32_t caps[2] = {cap1, 1024u};
+	const uint32_t caps[3] = {cap1, cap1, 1024u};
 	(void)aln_cap1; // hits live in the arena now: no separate list capacity
-	const uint32_t pool_chunks_of[2] = {pool_chunks, (need >> ARENA_CHUNK_LOG) + 2};
+	const uint32_t pool_chunks_of[3] = {1, pool_chunks, (need >> ARENA_CHUNK_LOG) + 2};
+	const bool stdmode = (opt->mode & 0x15) == 0x01 && !getenv("EMU_GENERIC_MODE");
 	int n_jobs = n;
 	const int32_t *jobs = nullptr;
-	for (int t = 0; t < 2 && n_jobs > 0; ++t) {
-		const int slots = t == 0 ? n_slots : 1;
+	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
+		const int slots = t < 2 ? n_slots : 1;
 		std::vector<uint4> ent((size_t)slots * caps[t]);
 		std::vector<uint32_t> nxt((size_t)slots * caps[t]);
 		B.ent = ent.data(); B.nxt = nxt.data(); B.heads = nullptr;
@@ -142,9 +143,13 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 			for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
 			for (int q = 0; q < n_jobs; ++q) { blockIdx.x = (unsigned)q; k_ctx(B); }
 		}
-		for (int s = 0; s < slots; ++s) { blockIdx.x = (unsigned)s; { if ((opt->mode & 0x15) == 0x01 && !getenv("EMU_GENERIC_MODE")) k_search<true, true, true>(B); else k_search<true, true, false>(B); } }
-		if (stats8) stats8[4 + t] = (unsigned long long)counters[1];
-		if (counters[1] > 0 && t == 1) { g_err = "reads exceeded the largest tier"; return 1; }
+		for (int s = 0; s < slots; ++s) {
+			blockIdx.x = (unsigned)s;
+			if (t == 0) { if (stdmode) k_search<true, false, true>(B); else k_search<true, false, false>(B); }
+			else { if (stdmode) k_search<true, true, true>(B); else k_search<true, true, false>(B); }
+		}
+		if (stats8 && t > 0) stats8[3 + t] = (unsigned long long)counters[1]; // [4] reads that needed the guaranteed pass
+		if (counters[1] > 0 && t == 2) { g_err = "reads exceeded the largest tier"; return 1; }
 		jobs = ovf; n_jobs = counters[1];
 	}
 	if (stats8) { stats8[2] = stats[0]; stats8[3] = stats[1]; stats8[7] = stats[2]; stats8[6] = stats[4]; }

@@ -313,6 +313,17 @@ def main():
         except Exception as e:
             cpu_baseline = {"error": str(e)[:200]}
 
+    # ---- roofline context (rank 0): what pure dependent random 32-byte sector gathers sustain on this device
+    random_sector = None
+    if rank == 0 and not args.no_extras:
+        try:
+            random_sector = {"buffer_bytes": 2_300_000_000, "unit": "GB/s",
+                             "by_chains_per_thread": {str(ch): api.probe_random_sectors(2_300_000_000, ch, 256) for ch in (1, 2, 4, 8)},
+                             "index_sized_buffer": {"buffer_bytes": int(args.genome_bp), "chains4": api.probe_random_sectors(int(args.genome_bp), 4, 256)},
+                             "note": "k_probe_gather: 8 x 256 threads per SM, each chain's next index depends on the sector just loaded"}
+        except Exception as e:
+            random_sector = {"error": str(e)[:200]}
+
     # ---- secondary kernels of the path (rank 0, N = 1): K4 SA->coordinate and K5 mate-rescue SW
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -386,7 +397,9 @@ def main():
                      "pops_per_read": st_counts["n_pops"] / n_reads, "pushes_per_read": st_counts["n_pushes"] / n_reads,
                      "stored_pushes_per_read": st_counts["n_stored"] / n_reads,
                      "per_read": {k: st_counts["n_" + k] / n_reads for k in ("pruned", "expand", "exact", "derive", "trips")},
-                     "stats_pass_ms": {"queue_empty": st_counts["ns_queue_empty"] / 1e6, "kernel": st_counts["ns_kernel"] / 1e6}},
+                     "stats_pass_ms": {"queue_empty": st_counts["ns_queue_empty"] / 1e6, "kernel": st_counts["ns_kernel"] / 1e6},
+                     "own_sector_gb_s": 32.0 * st_counts["own_fetches_search"] / (search_ms / args.steps / 1e3) / 1e9,
+                     "random_sector_probe": random_sector},
         "cpu_baseline": cpu_baseline,
         "parity_sample": parity,
         "other_kernels": extras,

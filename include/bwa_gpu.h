@@ -248,6 +248,11 @@ int bwa_gpu_get_stats(bwa_gpu_stats_t *out);
 /* 0 = off (default, the timed configuration), 1 = count fetches/pops/pushes in-kernel */
 int bwa_gpu_set_stats(int enabled);
 
+/* Roofline denominator for the occurrence-lookup kernels: the rate, in GB/s of 32-byte sectors, that a
+ * kernel of nothing but dependent random sector loads over a buffer_bytes buffer sustains on device 0, with `chains`
+ * (1, 2, 4 or 8) independent chains per thread and `steps` loads per chain.  Measurement only; replaces no reference call. */
+int bwa_gpu_probe_random_sectors(int64_t buffer_bytes, int chains, int steps, double *gb_per_s);
+
 /* Device-resident variant used for kernel-only throughput: stage a flat batch in HBM
  * once, then run K2+K3 over it repeatedly without host traffic.  run returns the device
  * time of that pass in *ms (CUDA events).  Results stay on the device; fetch copies the

@@ -56,7 +56,7 @@ def lib() -> C.CDLL:
 EXPORTS = [
     "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_load_pac", "bwa_gpu_destroy", "bwa_gpu_last_error",
     "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw", "bwa_gpu_mate_sw_path", "bwa_gpu_global_align",
-    "bwa_gpu_get_stats", "bwa_gpu_set_stats",
+    "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_probe_random_sectors",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
 ]
 
@@ -180,6 +180,15 @@ def global_align(jobs, gap_end: int = 5, band: int = 50):
 
 def set_stats(enabled: bool) -> None:
     _ck(lib().bwa_gpu_set_stats(1 if enabled else 0))
+
+
+def probe_random_sectors(buffer_bytes: int, chains: int = 4, steps: int = 256) -> float:
+    """GB/s of dependent random 32-byte sector loads over a buffer of that size (roofline denominator)."""
+    out = C.c_double(0.0)
+    L = lib()
+    L.bwa_gpu_probe_random_sectors.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    _ck(L.bwa_gpu_probe_random_sectors(int(buffer_bytes), int(chains), int(steps), C.byref(out)))
+    return out.value
 
 
 def get_stats() -> dict:

@@ -230,6 +230,13 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 		CK(cudaGetDeviceProperties(&prop, id));
 		if (prop.major < 10) return fail("device %d is sm_%d%d; libbwagpu is built for sm_100a only", id, prop.major, prop.minor);
 		CK(cudaSetDevice(id));
+		{
+			// The path is random 32-byte sector gathers: ask L2 to fetch from DRAM at sector granularity instead of the
+			// default 64 bytes (a hint; BWAGPU_L2_FETCH=64|128 restores / widens it for A/B runs)
+			const uint32_t gran = env_u32("BWAGPU_L2_FETCH", 32);
+			cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+			cudaGetLastError();
+		}
 		const int lanes = (int)env_u32("BWAGPU_LANES", 3);
 		Ctx *first = nullptr;
 		for (int ln = 0; ln < lanes; ++ln) {
@@ -431,7 +438,7 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	if (T.cap > need) T.cap = need;
 	const size_t slots = (size_t)T.slots_blocks * 128;
 	const uint32_t stride = (need > T.cap ? (need - T.cap + ARENA_CHUNK - 1) >> ARENA_CHUNK_LOG : 0) + 1;
-	if (T.ent.reserve(slots * T.cap) || T.nxt.reserve(slots * T.cap)) return 1;
+	if (T.ent.reserve(slots * ARENA_ALLOC(T.cap)) || T.nxt.reserve(slots * ARENA_ALLOC(T.cap))) return 1;
 	if (c->ctab.reserve(slots * stride)) return 1;
 	T.ctab_stride = stride;
 #if !BWAGPU_SMEM_HEADS
@@ -963,6 +970,44 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 	s.n_devices = 0;
 	for (Ctx *c : g_ctx) if (!c->owner) ++s.n_devices;
 	*out = s;
+	return 0;
+}
+
+// ------------------------------------------------------------------ measurement: random-sector gather ceiling
+extern "C" int bwa_gpu_probe_random_sectors(int64_t buffer_bytes, int chains, int steps, double *gb_per_s)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
+	if (!gb_per_s || buffer_bytes < (1 << 20) || steps < 1) return fail("bwa_gpu_probe_random_sectors: bad arguments");
+	Ctx *c = g_ctx[0];
+	CK(cudaSetDevice(c->dev));
+	const uint64_t n_blk64 = (uint64_t)buffer_bytes / 32;
+	if (n_blk64 > 0xffffffffull) return fail("probe buffer too large");
+	const uint32_t n_blk = (uint32_t)n_blk64;
+	uint4 *buf = nullptr;
+	uint32_t *sink = nullptr;
+	const int blocks = c->n_sm * 8, threads = 256;
+	CK(cudaMalloc((void **)&buf, (size_t)n_blk * 32));
+	CK(cudaMalloc((void **)&sink, (size_t)blocks * threads * 4));
+	CK(cudaMemsetAsync(buf, 0x5a, (size_t)n_blk * 32, c->st));
+	float best = 0;
+	for (int rep = 0; rep < 4; ++rep) { // rep 0 warms up
+		CK(cudaEventRecord(c->ev[5], c->st));
+		if (chains <= 1) k_probe_gather<1><<<blocks, threads, 0, c->st>>>(buf, n_blk, steps, 17u * rep, sink);
+		else if (chains == 2) k_probe_gather<2><<<blocks, threads, 0, c->st>>>(buf, n_blk, steps, 17u * rep, sink);
+		else if (chains <= 4) k_probe_gather<4><<<blocks, threads, 0, c->st>>>(buf, n_blk, steps, 17u * rep, sink);
+		else k_probe_gather<8><<<blocks, threads, 0, c->st>>>(buf, n_blk, steps, 17u * rep, sink);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ev[6], c->st));
+		CK(cudaStreamSynchronize(c->st));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]));
+		const int ch = chains <= 1 ? 1 : chains == 2 ? 2 : chains <= 4 ? 4 : 8;
+		const float gbs = (float)((double)blocks * threads * ch * steps * 32.0 / (ms * 1e-3) / 1e9);
+		if (rep > 0 && gbs > best) best = gbs;
+	}
+	cudaFree(buf); cudaFree(sink);
+	*gb_per_s = best;
 	return 0;
 }
 

@@ -109,7 +109,7 @@ struct Batch {
 	unsigned long long *x_free_top; // recycled chunks: lock-free stack, {tag:32 | head:32} against ABA
 	uint32_t *x_free_next;     // link of the recycled-chunk stack
 	// stats (STATS builds only)
-	unsigned long long *stats; // [0] ref fetches [1] own fetches [2] pops [3] pushes [4] records stored [5] pruned pops [6] expansions [7] exact-tail steps [8] derive trips
+	unsigned long long *stats; // [10] pops served from the arena (memory)  [0] ref fetches [1] own fetches [2] pops [3] pushes [4] records stored [5] pruned pops [6] expansions [7] exact-tail steps [8] derive trips
 };
 
 __device__ __forceinline__ unsigned long long gtime()
@@ -318,6 +318,14 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #ifndef BWAGPU_BATCH_POP
 #define BWAGPU_BATCH_POP 0 // N > 0 (needs BWAGPU_CONVERGE=1): memory pops wait until N lanes of the warp want one
 #endif
+#ifndef BWAGPU_TOP_REG
+#define BWAGPU_TOP_REG 0 // 1: the record pushed last is kept in registers until the next push displaces it
+#endif
+#ifndef BWAGPU_ARENA_G
+#define BWAGPU_ARENA_G 7 // log2 of the arena interleaving granule (records)
+#endif
+// elements to allocate per thread for a private arena of `cap` records (whole granules)
+#define ARENA_ALLOC(cap) ((((size_t)(cap)) + ((1u << BWAGPU_ARENA_G) - 1u)) & ~(size_t)((1u << BWAGPU_ARENA_G) - 1u))
 #ifndef BWAGPU_NO_FREELIST
 #define BWAGPU_NO_FREELIST 1 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
 #endif
@@ -388,8 +396,14 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 {
 	typedef typename HeadT<POOLED>::type head_t;
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	uint4 *const ent = B.ent + (size_t)slot * B.cap;
-	uint32_t *const nxt = B.nxt + (size_t)slot * B.cap;
+	// private arenas are interleaved across the grid in granules of 2^BWAGPU_ARENA_G records: records
+	// [g * G, (g + 1) * G) of thread `slot` sit at ((g * NT) + slot) * G.  A thread's neighbouring records still
+	// share sectors, and the low indices every search keeps re-using form ONE dense region for the whole grid
+	// instead of one hot spot per 32 KB arena (fewer pages in the TLB, even use of L2 sets)
+	const size_t NT = (size_t)gridDim.x * blockDim.x;
+	constexpr uint32_t AG = BWAGPU_ARENA_G, AM = (1u << BWAGPU_ARENA_G) - 1u;
+	uint4 *const ent = B.ent + ((size_t)slot << AG);
+	uint32_t *const nxt = B.nxt + ((size_t)slot << AG);
 	// bucket list heads: shared memory, bucket-major (heads[s * blockDim + tid]); two more slots per thread
 	// hold the first and last record of the read's hit list
 #ifdef BWAGPU_HOST_EMU
@@ -416,12 +430,12 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	uint32_t *const ctab = B.ctab + (size_t)slot * B.ctab_stride;
 	uint32_t n_chunks = 0; // pool chunks owned by this thread right now
 	auto ent_at = [&](uint32_t idx) -> uint4 * {
-		if (!POOLED || idx < CAP0) return ent + idx;
+		if (!POOLED || idx < CAP0) return ent + (((size_t)(idx >> AG) * NT) << AG) + (idx & AM);
 		const uint32_t o = idx - CAP0;
 		return B.xent + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
 	};
 	auto nxt_at = [&](uint32_t idx) -> uint32_t * {
-		if (!POOLED || idx < CAP0) return nxt + idx;
+		if (!POOLED || idx < CAP0) return nxt + (((size_t)(idx >> AG) * NT) << AG) + (idx & AM);
 		const uint32_t o = idx - CAP0;
 		return B.xnxt + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
 	};
@@ -450,6 +464,16 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	uint32_t k = 0, l = 0, e_pos = 0, e_tag = 0;
 	bool held = false;
 	uint32_t cc = 0; // MODE_DERIVE: which child interval of (k, l) to take; MODE_EXACT: the base at i-1
+#if BWAGPU_TOP_REG
+	// One record lives in registers instead of the arena (lr_s = its bucket, < 0: none): the most recent push into the
+	// lowest bucket pushed to so far.  A push into the same or a lower bucket displaces it (the old one is written to the
+	// arena first, so it stays below the new one); a push into a higher bucket goes to the arena directly.  The register
+	// record is therefore always the top of its bucket, and a pop takes it whenever no lower bucket has records in
+	// memory -- the common case at the end of a path (the mismatch group of the last expansion).  The remaining
+	// children of a group are then popped from registers too: their own pushes all go to higher buckets.
+	uint32_t lr_k = 0, lr_l = 0, lr_pos = 0, lr_tag = 0;
+	int lr_s = -1;
+#endif
 	int m = 0, i = 0; // i doubles as the exact tail's cursor
 	// context of the current node, loaded together with its occurrence blocks (k_ctx): width[i-1], width[i-2].bid,
 	// the two seed-width entries, str[i-1], str[i-2]
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 #define CW_CN ((cw.x >> 28) & 7u)
 #define CW_SW1 (cw.y & (CW_BID | WB_EQ))
 #define CW_S2 ((int)((cw.y >> 16) & CW_BID))
-	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0, n_pruned = 0, n_expand = 0, n_exact = 0, n_derive = 0, n_trips = 0;
+	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0, n_pruned = 0, n_expand = 0, n_exact = 0, n_derive = 0, n_trips = 0, n_mempop = 0;
 	if (STATS) atomicMin(B.stats + 12, gtime());
 
 	auto score_of = [&](int mm, int go, int ge) { return mm * O.s_mm + go * O.s_gapo + ge * O.s_gape; };
@@ -511,6 +535,16 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		return idx;
 	};
 
+	// links one record into bucket s's list in the arena
+	auto store_rec = [&](uint32_t rk, uint32_t rl, uint32_t pos, uint32_t tag, int s) {
+		const uint32_t idx = alloc_rec();
+		if (idx == NIL) return;
+		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
+		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
+		else { *nxt_at(idx) = mask.test(s) ? (uint32_t)heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
+		mask.set(s);
+	};
+
 	// gap_push (bwtgap.c:45-64): one record holding n_children nodes of score s
 	auto push_rec = [&](uint32_t rk, uint32_t rl, uint32_t pos, uint32_t tag, int s, int n_children) {
 		n_entries += n_children;
@@ -518,12 +552,13 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		if (n_aln > 0 && !nonstop && s > best_score + O.s_mm) return; // phantoms: counted, never stored
 		if (STATS) ++n_stored;
 		if (!mask.fits(s)) { overflow = true; return; }
-		const uint32_t idx = alloc_rec();
-		if (idx == NIL) return;
-		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
-		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
-		else { *nxt_at(idx) = mask.test(s) ? (uint32_t)heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
-		mask.set(s);
+#if BWAGPU_TOP_REG
+		if (lr_s >= 0 && s > lr_s) { store_rec(rk, rl, pos, tag, s); return; } // the register keeps the lower bucket's top
+		if (lr_s >= 0) store_rec(lr_k, lr_l, lr_pos, lr_tag, lr_s); // displaced (same or higher bucket): now an ordinary arena record
+		lr_k = rk; lr_l = rl; lr_pos = pos; lr_tag = tag; lr_s = s;
+#else
+		store_rec(rk, rl, pos, tag, s);
+#endif
 	};
 
 	// copies the finished read's results out and resets the per-slot stack
@@ -544,6 +579,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			B.pool_off[rid] = off;
 			B.max_entries[rid] = max_entries;
 		}
+#if BWAGPU_TOP_REG
+		lr_s = -1;
+#endif
 		mask.reset(); cur_s = -1; cur_head = NIL;
 		bump = 0; free_head = NIL; spare = NIL; held = false; n_entries = 0; n_aln = 0;
 		if (POOLED) while (n_chunks > 1) chunk_free(ctab[--n_chunks]); // keep one chunk, recycle the rest
@@ -668,7 +706,11 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			if (!stop) {
 				if (max_entries < n_entries) max_entries = n_entries;
 				// > max_entries (bwtgap.c:140); only phantoms left: the reference pops one and stops
+#if BWAGPU_TOP_REG
+				stop = n_entries > O.max_entries || (!held && !mask.any() && lr_s < 0);
+#else
 				stop = n_entries > O.max_entries || (!held && !mask.any());
+#endif
 			}
 			if (stop) { finish_read(); mode = MODE_NEW; active = false; }
 			else {
@@ -678,15 +720,31 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 					e_pos = (uint32_t)i;
 					e_tag &= ~(3u << 24);
 				} else {
-					const int s = mask.lowest();
-					if (s != cur_s) {
-						if (cur_s >= 0 && mask.test(cur_s)) heads[cur_s * HS] = (head_t)cur_head;
-						cur_s = s; cur_head = heads[s * HS];
+#if BWAGPU_TOP_REG
+					const bool from_lr = lr_s >= 0 && (!mask.any() || lr_s <= mask.lowest());
+#else
+					const bool from_lr = false;
+#endif
+					uint4 q;
+					uint4 *qp = nullptr;
+					uint32_t idx = NIL, nx = NIL;
+					int s = 0;
+					if (from_lr) {
+#if BWAGPU_TOP_REG
+						q = make_uint4(lr_k, lr_l, lr_pos, lr_tag);
+#endif
+					} else {
+						s = mask.lowest();
+						if (s != cur_s) {
+							if (cur_s >= 0 && mask.test(cur_s)) heads[cur_s * HS] = (head_t)cur_head;
+							cur_s = s; cur_head = heads[s * HS];
+						}
+						idx = cur_head;
+						qp = ent_at(idx);
+						q = *qp;
+						nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
+						if (STATS) ++n_mempop;
 					}
-					const uint32_t idx = cur_head;
-					uint4 *const qp = ent_at(idx);
-					const uint4 q = *qp;
-					const uint32_t nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
 					const uint32_t kind = (q.w >> 27) & 3u;
 					uint32_t gm = 0, b = 0;
 					if (kind != KIND_PLAIN) {
@@ -694,12 +752,26 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
 						gm &= ~(1u << b);
 					}
-					if (gm) qp->z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
-					else { // unlink
-						cur_head = nx;
-						if (cur_head == NIL) mask.clear(s);
-						if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
-						spare = idx;
+					if (from_lr) {
+#if BWAGPU_TOP_REG
+						if (gm) lr_pos = (q.z & 0xffffu) | gm << 16; // stays on top with one child fewer
+						else lr_s = -1;
+#endif
+					} else {
+						bool unlink = gm == 0;
+#if BWAGPU_TOP_REG
+						if (gm && lr_s < 0) { // the rest of the group moves to registers: it stays the top of the lowest bucket until it is used up
+							lr_k = q.x; lr_l = q.y; lr_pos = (q.z & 0xffffu) | gm << 16; lr_tag = q.w; lr_s = s;
+							unlink = true;
+						}
+#endif
+						if (!unlink) qp->z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
+						else {
+							cur_head = nx;
+							if (cur_head == NIL) mask.clear(s);
+							if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
+							spare = idx;
+						}
 					}
 					k = q.x; l = q.y;
 					if (kind == KIND_PLAIN) { e_pos = q.z; e_tag = q.w; }
@@ -897,8 +969,33 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		atomicAdd(B.stats + 7, (unsigned long long)n_exact);
 		atomicAdd(B.stats + 8, (unsigned long long)n_derive);
 		atomicAdd(B.stats + 9, (unsigned long long)n_trips);
+		atomicAdd(B.stats + 10, (unsigned long long)n_mempop);
 		atomicMax(B.stats + 13, gtime());
 	}
+}
+
+// ------------------------------------------------------------------ measurement: random-sector gather ceiling
+// What a kernel made of nothing but dependent random 32-byte sector loads sustains on this device (SURVEY.md §8d:
+// "ceiling = measured random 32 B-sector read throughput").  Each thread walks CHAINS independent chains; the next
+// index of a chain depends on the sector just loaded, as an FM-index step does.
+template <int CHAINS>
+__global__ void __launch_bounds__(256) k_probe_gather(const uint4 *__restrict__ buf, uint32_t n_blk, int steps, uint32_t seed,
+                                                      uint32_t *__restrict__ sink)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t x[CHAINS], acc = 0;
+#pragma unroll
+	for (int c = 0; c < CHAINS; ++c) x[c] = (t * CHAINS + c + seed) * 2654435761u + 12345u;
+	DevIndex ix = {};
+	ix.blk = buf;
+	for (int s = 0; s < steps; ++s) {
+		OccBlock o[CHAINS];
+#pragma unroll
+		for (int c = 0; c < CHAINS; ++c) o[c] = load_block(ix, (uint32_t)(((uint64_t)x[c] * n_blk) >> 32));
+#pragma unroll
+		for (int c = 0; c < CHAINS; ++c) { acc += o[c].c3; x[c] = (x[c] ^ o[c].c0) * 1664525u + 1013904223u; }
+	}
+	sink[t] = acc;
 }
 
 // ------------------------------------------------------------------ job ordering for K3

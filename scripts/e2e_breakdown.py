@@ -20,5 +20,5 @@ for rep in range(2):
     st = api.get_stats()
     print("struct: %.0f ms  %.2f M reads/s | marshal %.0f h2d %.0f width %.0f search %.0f compact %.0f d2h %.0f device_total %.0f" % (
         dt * 1e3, n / dt / 1e6, st["ms_host_marshal"], st["ms_h2d"], st["ms_width"], st["ms_search"], st["ms_compact"], st["ms_d2h"], st["ms_total_device"]))
-    t = time.perf_counter(); bench.free_alns(keep[0]); print("  free() of the aln arrays (untimed in bench): %.0f ms" % ((time.perf_counter() - t) * 1e3))
+    t = time.perf_counter(); lib.bwa_gpu_free_alns(n, ptr); print("  free() of the aln arrays (untimed in bench): %.0f ms" % ((time.perf_counter() - t) * 1e3))
 api.destroy()

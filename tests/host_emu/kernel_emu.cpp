@@ -4,6 +4,7 @@
 // tests/test_kernel_logic.py into tests/host_emu/libkernel_emu.so.
 #define BWAGPU_HOST_EMU 1
 #include <stdlib.h>
+#include <stdio.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -123,8 +124,8 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	const int32_t *jobs = nullptr;
 	for (int t = 0; t < 3 && n_jobs > 0; ++t) {
 		const int slots = t < 2 ? n_slots : 1;
-		std::vector<uint4> ent((size_t)slots * caps[t]);
-		std::vector<uint32_t> nxt((size_t)slots * caps[t]);
+		std::vector<uint4> ent((size_t)slots * ARENA_ALLOC(caps[t]));
+		std::vector<uint32_t> nxt((size_t)slots * ARENA_ALLOC(caps[t]));
 		B.ent = ent.data(); B.nxt = nxt.data(); B.heads = nullptr;
 		B.cap = caps[t];
 		const uint32_t stride = ((need > caps[t] ? need - caps[t] : 0) >> ARENA_CHUNK_LOG) + 2;
@@ -143,6 +144,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 			for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
 			for (int q = 0; q < n_jobs; ++q) { blockIdx.x = (unsigned)q; k_ctx(B); }
 		}
+		gridDim.x = (unsigned)slots;
 		for (int s = 0; s < slots; ++s) {
 			blockIdx.x = (unsigned)s;
 			if (t == 0) { if (stdmode) k_search<true, false, true>(B); else k_search<true, false, false>(B); }
@@ -152,6 +154,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		if (counters[1] > 0 && t == 2) { g_err = "reads exceeded the largest tier"; return 1; }
 		jobs = ovf; n_jobs = counters[1];
 	}
+	if (getenv("EMU_PRINT")) fprintf(stderr, "[emu] reads %d pops %llu memory pops %llu stored %llu trips %llu\n", n, stats[2], stats[10], stats[4], stats[9]);
 	if (stats8) { stats8[2] = stats[0]; stats8[3] = stats[1]; stats8[7] = stats[2]; stats8[6] = stats[4]; }
 	int64_t acc = 0;
 	for (int i = 0; i < n; ++i) { aln_off[i] = acc; acc += n_aln[i]; }

@@ -320,7 +320,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 {
 	const size_t B = batch_records();
 	const double t0 = now();
-	double t_read = 0, t_host = 0, t_write = 0, t1;
+	double t_read = 0, t_host = 0, t_write = 0, t_toseq = 0, t1;
 	bam_pair_t *recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
 	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
 	long tot_seqs = 0;
@@ -353,7 +353,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 					flat[m++] = r->bwa_seq[j];
 				}
 		}
-		t_host += now() - t1;
+		t_toseq += now() - t1;
 		/* ... which is ONE device call for the batch */
 		gpu_align(m, flat);
 		t1 = now();
@@ -418,8 +418,8 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
 	}
 	free(recs); free(flat);
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (read %.2f, host phases %.2f, device calls %.2f, temp write %.2f)\n",
-	        __func__, tot_seqs, now() - t0, t_read, t_host, g_t_aln + g_t_sa, t_write);
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f)\n",
+	        __func__, tot_seqs, now() - t0, t_read, t_toseq, t_host, g_t_aln + g_t_sa, t_write);
 	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
 }
 
@@ -451,6 +451,7 @@ static int wants_pairing(const bam_pair_t *r) /* bam2bam.c:726-735 */
 	return n_occ[0] <= g_pe->max_occ && n_occ[1] <= g_pe->max_occ;
 }
 
+static double g_t_stageA, g_t_stageB, g_t_stageC, g_t_stageD;
 static int is_pair_job(const bam_pair_t *r) { return r->kind == proper_pair && r->phase == positioned && unique_rec(r); }
 
 /* finish_pair (bam2bam.c:705-811) for records [lo, hi), phase by phase */
@@ -462,6 +463,7 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 	int j, k;
 	bwtint_t l;
 
+	double t1 = now();
 	/* A: every SA row whose coordinate pairing will want (bam2bam.c:736-765), in the reference's visiting order */
 	g_q.n = 0; fresh.n = 0;
 	for (i = lo; i < hi; ++i) {
@@ -489,7 +491,9 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 					for (l = a->k; l <= a->l; ++l) { saq_push(&g_q, l, a->a); if (l == a->l) break; }
 			}
 	}
+	g_t_stageA += now() - t1;
 	saq_run(&g_q);
+	t1 = now();
 
 	/* B: pairing on the host, in record order, then the hit lists for XA (consumes drand48), collecting their rows */
 	{
@@ -561,6 +565,7 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 		}
 	}
 
+	g_t_stageB += now() - t1; t1 = now();
 	/* C: mate rescue.  bwa_paired_sw1 (bwape.c:519-633) decides the windows in floating point and judges the
 	 * alignments; only aln_local_core moves.  First run: note the jobs.  Device.  Second run: the real one. */
 	{
@@ -584,6 +589,7 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 		if (g_sw_pos != g_sw.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SW answers unused\n", g_sw.n - g_sw_pos, g_sw.n); abort(); }
 	}
 
+	g_t_stageC += now() - t1; t1 = now();
 	/* D: the reference's own per-record tail (bam2bam.c:643-658, 798-810) */
 	for (i = lo; i < hi; ++i) {
 		bam_pair_t *r = &recs[i];
@@ -603,6 +609,7 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 		}
 		if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
 	}
+	g_t_stageD += now() - t1;
 }
 
 void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) *iinfos)
@@ -655,6 +662,8 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		t_write += now() - t1;
 		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
 	}
+	fprintf(stderr, "[%s] finish = enumerate %.2f + pairing/XA %.2f + mate rescue (host side, both runs) %.2f + refine/update %.2f + device calls\n",
+	        __func__, g_t_stageA, g_t_stageB, g_t_stageC, g_t_stageD);
 	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (temp read %.2f, finish %.2f, BAM write %.2f)\n"
 	                "[%s] finished cleanly, shutting down.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d singletons are mated.\n"

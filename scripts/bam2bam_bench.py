@@ -106,7 +106,7 @@ def main():
         out = os.path.join(d, name + ".bam")
         dt, load_s, log = run(prefix, bam, out, threads, preload, extra)
         res[name] = {"wall_s": round(dt, 2), "index_load_s": load_s, "reads_per_s": round(n * per / max(dt - load_s, 1e-9)),
-                     "log_tail": [l for l in log.splitlines() if "processed in" in l or "device calls" in l][-3:]}
+                     "log_tail": [l for l in log.splitlines() if ("processed in" in l and "(" in l) or "device calls" in l or "finish =" in l][-5:]}
         print(f"[b2b] {name}: {dt:.1f}s ({load_s:.1f}s index load) -> {res[name]['reads_per_s']} reads/s", file=sys.stderr)
         return out
 

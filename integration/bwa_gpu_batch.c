@@ -42,6 +42,7 @@
 #define _GNU_SOURCE
 #include <dlfcn.h>
 #include <getopt.h>
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -316,6 +317,79 @@ static void gpu_align(int m, bwa_seq_t *flat)
 
 static int is_mapped(const bwa_seq_t *p) { return p->type == BWA_TYPE_UNIQUE || p->type == BWA_TYPE_REPEAT; }
 
+/* aln_* + posn_* (bam2bam.c:608-703) for records [0, n): what sequential_loop_pass1 and a worker thread do to a
+ * pristine record, with the two hot calls hoisted out of the per-record loop.  `flat` holds >= 2 n elements. */
+static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq, double *t_host)
+{
+	size_t i;
+	int m = 0, j;
+	double t1 = now();
+	/* aln_singleton / aln_pair (bam2bam.c:608-620, 660-681) without the search ... */
+	for (i = 0; i < n; ++i) {
+		bam_pair_t *r = &recs[i];
+		if (r->phase != pristine) continue;
+		if (unique_rec(r))
+			for (j = 0; j != (int)r->kind; ++j) {
+				bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
+				flat[m++] = r->bwa_seq[j];
+			}
+	}
+	*t_toseq += now() - t1;
+	/* ... which is ONE device call for the batch */
+	gpu_align(m, flat);
+	t1 = now();
+	for (i = 0, m = 0; i < n; ++i) {
+		bam_pair_t *r = &recs[i];
+		if (r->phase != pristine) continue;
+		if (unique_rec(r))
+			for (j = 0; j != (int)r->kind; ++j) r->bwa_seq[j] = flat[m++];
+		r->phase = aligned;
+	}
+
+	/* posn_singleton / posn_pair (bam2bam.c:622-641, 683-703): primary-hit selection on the host, in record
+	 * order (drand48), collecting the SA rows whose coordinates are wanted ... */
+	g_q.n = 0;
+	for (i = 0; i < n; ++i) {
+		bam_pair_t *r = &recs[i];
+		if (r->phase != aligned || !unique_rec(r)) continue;
+		for (j = 0; j != (int)r->kind; ++j) {
+			bwa_seq_t *p = &r->bwa_seq[j];
+			int k;
+			if (r->kind == singleton) bwa_aln2seq_core(p->n_aln, p->aln, p, 1, g_pe->max_occ_se);
+			else { p->n_multi = 0; bwa_aln2seq(p->n_aln, p->aln, p); }
+			if (is_mapped(p)) saq_push(&g_q, p->sa, p->strand);
+			if (r->kind == singleton)
+				for (k = 0; k < p->n_multi; ++k) saq_push(&g_q, p->multi[k].pos, p->multi[k].strand);
+		}
+	}
+	*t_host += now() - t1;
+	/* ... one device call ... */
+	saq_run(&g_q);
+	/* ... and the reference's own bwa_cal_pac_pos_core (position + mapQ) fed from the answers */
+	t1 = now();
+	g_sa_replay = 1;
+	for (i = 0; i < n; ++i) {
+		bam_pair_t *r = &recs[i];
+		if (r->phase != aligned) continue;
+		if (unique_rec(r))
+			for (j = 0; j != (int)r->kind; ++j) {
+				bwa_seq_t *p = &r->bwa_seq[j];
+				int k;
+				bwa_cal_pac_pos_core(g_bwt[0], g_bwt[1], p, g_gap->max_diff, g_gap->fnr);
+				if (r->kind == singleton)
+					for (k = 0; k < p->n_multi; ++k) { /* bam2bam.c:633-637 */
+						bwt_multi1_t *q = p->multi + k;
+						if (q->strand) q->pos = bwt_sa(g_bwt[0], q->pos);
+						else q->pos = g_bwt[1]->seq_len - (bwt_sa(g_bwt[1], q->pos) + p->len);
+					}
+			}
+		r->phase = positioned;
+	}
+	g_sa_replay = 0;
+	if (g_sa_pos != g_q.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SA answers unused\n", g_q.n - g_sa_pos, g_q.n); abort(); }
+	*t_host += now() - t1;
+}
+
 void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_infos) *iinfos)
 {
 	const size_t B = batch_records();
@@ -327,7 +401,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	ensure_gpu();
 	for (;;) {
 		size_t n = 0, i;
-		int m = 0, j, rc;
+		int rc;
 		t1 = now();
 		while (n < B) {
 			rc = read_bam_pair(ks, &recs[n], g_broken_input, g_drop_aligned);
@@ -342,70 +416,8 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 		t_read += now() - t1;
 		if (n == 0) break;
 
-		/* aln_singleton / aln_pair (bam2bam.c:608-620, 660-681) without the search ... */
+		align_position_range(recs, n, flat, &t_toseq, &t_host);
 		t1 = now();
-		for (i = 0; i < n; ++i) {
-			bam_pair_t *r = &recs[i];
-			if (r->phase != pristine) continue;
-			if (unique_rec(r))
-				for (j = 0; j != (int)r->kind; ++j) {
-					bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
-					flat[m++] = r->bwa_seq[j];
-				}
-		}
-		t_toseq += now() - t1;
-		/* ... which is ONE device call for the batch */
-		gpu_align(m, flat);
-		t1 = now();
-		for (i = 0, m = 0; i < n; ++i) {
-			bam_pair_t *r = &recs[i];
-			if (r->phase != pristine) continue;
-			if (unique_rec(r))
-				for (j = 0; j != (int)r->kind; ++j) r->bwa_seq[j] = flat[m++];
-			r->phase = aligned;
-		}
-
-		/* posn_singleton / posn_pair (bam2bam.c:622-641, 683-703): primary-hit selection on the host, in record
-		 * order (drand48), collecting the SA rows whose coordinates are wanted ... */
-		g_q.n = 0;
-		for (i = 0; i < n; ++i) {
-			bam_pair_t *r = &recs[i];
-			if (r->phase != aligned || !unique_rec(r)) continue;
-			for (j = 0; j != (int)r->kind; ++j) {
-				bwa_seq_t *p = &r->bwa_seq[j];
-				int k;
-				if (r->kind == singleton) bwa_aln2seq_core(p->n_aln, p->aln, p, 1, g_pe->max_occ_se);
-				else { p->n_multi = 0; bwa_aln2seq(p->n_aln, p->aln, p); }
-				if (is_mapped(p)) saq_push(&g_q, p->sa, p->strand);
-				if (r->kind == singleton)
-					for (k = 0; k < p->n_multi; ++k) saq_push(&g_q, p->multi[k].pos, p->multi[k].strand);
-			}
-		}
-		t_host += now() - t1;
-		/* ... one device call ... */
-		saq_run(&g_q);
-		/* ... and the reference's own bwa_cal_pac_pos_core (position + mapQ) fed from the answers */
-		t1 = now();
-		g_sa_replay = 1;
-		for (i = 0; i < n; ++i) {
-			bam_pair_t *r = &recs[i];
-			if (r->phase != aligned) continue;
-			if (unique_rec(r))
-				for (j = 0; j != (int)r->kind; ++j) {
-					bwa_seq_t *p = &r->bwa_seq[j];
-					int k;
-					bwa_cal_pac_pos_core(g_bwt[0], g_bwt[1], p, g_gap->max_diff, g_gap->fnr);
-					if (r->kind == singleton)
-						for (k = 0; k < p->n_multi; ++k) { /* bam2bam.c:633-637 */
-							bwt_multi1_t *q = p->multi + k;
-							if (q->strand) q->pos = bwt_sa(g_bwt[0], q->pos);
-							else q->pos = g_bwt[1]->seq_len - (bwt_sa(g_bwt[1], q->pos) + p->len);
-						}
-				}
-			r->phase = positioned;
-		}
-		g_sa_replay = 0;
-		if (g_sa_pos != g_q.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SA answers unused\n", g_q.n - g_sa_pos, g_q.n); abort(); }
 		for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
 			if (unique_rec(&recs[i])) improve_isize_est(iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
 		t_host += now() - t1;
@@ -674,4 +686,212 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		if (kh_exist(my_hash, it)) free(kh_val(my_hash, it).a);
 	kh_destroy(64, my_hash);
 	free(recs);
+}
+
+/* ------------------------------------------------------------------ 0MQ worker
+ * run_worker_thread (bam2bam.c:1387-1442) handles one message = one record per loop trip.  This replacement speaks
+ * the same protocol on the same socket (DEALER on inproc://work_io; wire format bam2bam.c:951-1097 through the
+ * reference's own msg_init_from_pair / pair_init_from_msg) but DRAINS messages into a batch, makes the batch calls
+ * above, and answers every record.  It serves both `bam2bam -t 1 -p PORT` (local thread behind the multiplexor) and
+ * `bwa worker -t 1` (remote process behind the streamer device, bam2bam.c:2099-2180); the mux, the reader / output
+ * threads and remote CPU workers are untouched.
+ *
+ * What the mux's behaviour (bam2bam.c:1577-1601) demands of a batching worker:
+ *   * whenever a record is un-acked and the crowd socket is writable it sends -- new records first, else it RE-SENDS
+ *     outstanding ones round-robin.  So a duplicate `recno` means "nothing new right now": the batch is closed early
+ *     (once it holds BWAGPU_WORKER_MIN records) instead of waiting for the deadline, and duplicates of records this
+ *     worker took recently are dropped (re-sends that crossed their answer; the mux would discard a repeated answer
+ *     anyway, 1610-1623);
+ *   * the worker stops receiving while a batch is on the device, so the HWM of 64 (bam2bam.c:35) back-pressures
+ *     the mux instead of flooding the worker.
+ * First arrivals are in recno order (new records are sent in order), so with ONE batching worker drand48 is consumed
+ * in record order in both passes and the BAM equals `bam2bam -t 1`'s (tests/test_batched_worker.py), which the
+ * reference's own `-t N` does not guarantee.
+ */
+#include "zmq.h"
+
+void msg_init_from_pair(zmq_msg_t *m, bam_pair_t *p);
+void pair_init_from_msg(bam_pair_t *p, zmq_msg_t *m);
+void pair_posn(bam_pair_t *p);
+void set_sockopts(void *socket);
+
+static void *g_zmq_ctx;              /* bam2bam.c:103 (static there): captured where it is created */
+static void *volatile g_iinfos_seen; /* bam2bam.c:107 (static there): what g_iinfos is set to at 1769 / 1857 / 2092 / 2298 */
+
+void *zmq_init(int io_threads)
+{
+	REAL(void *, zmq_init, int);
+	return g_zmq_ctx = real_zmq_init(io_threads);
+}
+
+void infer_all_isizes(khash_t(isize_infos) *iinfos, double ap_prior, int64_t L)
+{
+	REAL(void, infer_all_isizes, khash_t(isize_infos) *, double, int64_t);
+	real_infer_all_isizes(iinfos, ap_prior, L);
+	g_iinfos_seen = iinfos; /* the caller assigns g_iinfos = iinfos right after (bam2bam.c:1768-1769, 1856-1857) */
+}
+
+khash_t(isize_infos) *decode_iinfo(char *p, char *q)
+{
+	REAL(khash_t(isize_infos) *, decode_iinfo, char *, char *);
+	khash_t(isize_infos) *r = real_decode_iinfo(p, q);
+	g_iinfos_seen = r; /* bwa worker: g_iinfos = decode_iinfo(...) (bam2bam.c:2092, 2298) */
+	return r;
+}
+
+static long env_long(const char *name, long dflt)
+{
+	const char *e = getenv(name);
+	const long v = e ? atol(e) : 0;
+	return v > 0 ? v : dflt;
+}
+
+/* Which records this worker has taken: the mux keeps at most ring_size = 524288 records in flight (bam2bam.c:9), so a
+ * direct-mapped table of twice that many slots, indexed by recno, never has two live records in one slot.  A record
+ * taken less than BWAGPU_WORKER_REANSWER_S seconds ago is a re-send that crossed its answer and is dropped; an older
+ * one is processed again (its answer may have been lost with a TCP reconnect), as the reference's worker would. */
+#define TAKEN_SLOTS (1u << 20)
+typedef struct { uint64_t recno_p1; float t; uint8_t phase; } taken_t;
+
+void *run_worker_thread(void *arg)
+{
+	const size_t B = (size_t)env_long("BWAGPU_WORKER_RECORDS", 1 << 17);
+	const size_t min_batch = (size_t)env_long("BWAGPU_WORKER_MIN", 1024);
+	const double wait_s = 1e-3 * (double)env_long("BWAGPU_WORKER_WAIT_MS", 50);
+	const long long max_q = getenv("BWAGPU_BATCH_SA") ? atoll(getenv("BWAGPU_BATCH_SA")) : 1ll << 25;
+	bam_pair_t *recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
+	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
+	const double reanswer_s = (double)env_long("BWAGPU_WORKER_REANSWER_S", 30);
+	const double t_start = now();
+	taken_t *taken = (taken_t *)calloc(TAKEN_SLOTS, sizeof(taken_t));
+	kh_64_t *my_hash = kh_init(64);
+	khiter_t it;
+	uint64_t n_tot[2] = {0, 0}, n_mapped[2] = {0, 0};
+	long n_batches = 0, n_records = 0, n_dupes = 0, failure_count = 0;
+	double t_toseq = 0, t_host = 0, t_fin = 0, t_wait = 0, t_send = 0;
+	int done = 0, have_pending = 0;
+	bam_pair_t pending;
+	void *upstream;
+	static int claimed;
+	(void)arg;
+
+	/* the batch state above (SA / SW queues, record-replay cursors) is one set of globals and there is one device
+	 * queue: ONE thread batches, whatever -t says; further threads have nothing to add and leave */
+	if (__sync_lock_test_and_set(&claimed, 1)) {
+		fprintf(stderr, "[run_worker_thread] a batching GPU worker is already running in this process; extra thread exits.\n");
+		free(recs); free(flat); free(taken); kh_destroy(64, my_hash);
+		return 0;
+	}
+	if (!g_zmq_ctx) { fprintf(stderr, "[bwa_gpu_batch] run_worker_thread: the 0MQ context was not seen being created\n"); abort(); }
+	upstream = zmq_socket(g_zmq_ctx, ZMQ_DEALER);
+	if (!upstream) { fprintf(stderr, "[bwa_gpu_batch] error creating socket\n"); abort(); }
+	set_sockopts(upstream);
+	if (zmq_connect(upstream, "inproc://work_io") != 0) { fprintf(stderr, "[bwa_gpu_batch] zmq_connect failed: %s\n", zmq_strerror(zmq_errno())); exit(1); }
+	ensure_gpu();
+
+	while (!done) {
+		size_t n = 0, i, lo;
+		int saw_dupe = 0, phase_of_batch = -1, ret;
+		double t_first = 0, t1 = now();
+		/* ---- drain messages into a batch */
+		if (have_pending) { /* the record that closed the previous batch (it was in another phase) opens this one */
+			recs[0] = pending; have_pending = 0;
+			phase_of_batch = (int)recs[0].phase;
+			n = 1; t_first = now();
+		}
+		for (;;) {
+			zmq_msg_t msg;
+			bam_pair_t *r = &recs[n];
+			taken_t *tk;
+			if (n > 0) { /* the first message is waited for indefinitely, later ones until the deadline */
+				zmq_pollitem_t item = {upstream, 0, ZMQ_POLLIN, 0};
+				const double left = t_first + wait_s - now();
+				if (left <= 0 || (saw_dupe && n >= min_batch)) break;
+				ret = zmq_poll(&item, 1, (long)(left * 1e3) + 1);
+				if (ret < 0) { if (zmq_errno() == ETERM || zmq_errno() == EINTR) done = 1; break; }
+				if (ret == 0) break;
+			}
+			zmq_msg_init(&msg);
+			if (zmq_msg_recv(&msg, upstream, 0) < 0) {
+				zmq_msg_close(&msg);
+				if (zmq_errno() == ETERM || zmq_errno() == EINTR) { done = 1; break; } /* clean exit, as bam2bam.c:1406 */
+				fprintf(stderr, "zmq_msg_recv failed: %s\n", zmq_strerror(zmq_errno()));
+				exit(1);
+			}
+			if (n == 0) t_first = now();
+			pair_init_from_msg(r, &msg);
+			zmq_msg_close(&msg);
+			tk = &taken[r->recno & (TAKEN_SLOTS - 1)];
+			if (tk->recno_p1 == r->recno + 1 && tk->phase == (uint8_t)r->phase && (now() - t_start) - tk->t < reanswer_s) {
+				saw_dupe = 1; ++n_dupes; bam_destroy_pair(r); continue;
+			}
+			tk->recno_p1 = r->recno + 1; tk->phase = (uint8_t)r->phase; tk->t = (float)(now() - t_start);
+			if (phase_of_batch >= 0 && (int)r->phase != phase_of_batch) { /* a batch holds one phase: this record opens the next */
+				pending = *r; have_pending = 1;
+				memset(r, 0, sizeof(*r));
+				break;
+			}
+			phase_of_batch = (int)r->phase;
+			if (++n == B) break;
+		}
+		t_wait += now() - t1;
+		if (n == 0) continue;
+		++n_batches; n_records += (long)n;
+
+		/* ---- the switch of bam2bam.c:1414-1422, for the whole batch */
+		t1 = now();
+		if (phase_of_batch == pristine) align_position_range(recs, n, flat, &t_toseq, &t_host);
+		else if (phase_of_batch == aligned) for (i = 0; i < n; ++i) pair_posn(&recs[i]);
+		else if (phase_of_batch == positioned) {
+			khash_t(isize_infos) *iinfos = (khash_t(isize_infos) *)g_iinfos_seen;
+			if (!iinfos) failure_count += (long)n; /* sent back as they came (bam2bam.c:1419-1420) */
+			else
+				for (lo = 0; lo < n;) { /* sub-ranges bounded by the SA rows their hit lists expand to, as sequential_loop_pass2 */
+					size_t hi = lo;
+					long long q = 0;
+					while (hi < n && (hi == lo || q < max_q)) {
+						const bam_pair_t *r = &recs[hi];
+						if (is_pair_job(r) && wants_pairing(r)) {
+							int j, k;
+							for (j = 0; j < 2; ++j)
+								for (k = 0; k < r->bwa_seq[j].n_aln; ++k) q += r->bwa_seq[j].aln[k].l - r->bwa_seq[j].aln[k].k + 1;
+						}
+						++hi;
+					}
+					finish_range(recs, lo, hi, iinfos, n_tot, n_mapped, my_hash);
+					lo = hi;
+				}
+		}
+		t_fin += now() - t1;
+
+		/* ---- answer every record */
+		t1 = now();
+		for (i = 0; i < n; ++i) {
+			zmq_msg_t msg;
+			msg_init_from_pair(&msg, &recs[i]);
+			bam_destroy_pair(&recs[i]);
+			ret = zmq_msg_send(&msg, upstream, 0);
+			zmq_msg_close(&msg);
+			if (ret < 0) {
+				if (zmq_errno() == ETERM || zmq_errno() == EINTR) { done = 1; for (++i; i < n; ++i) bam_destroy_pair(&recs[i]); break; }
+				fprintf(stderr, "zmq_msg_send failed: %s\n", zmq_strerror(zmq_errno()));
+				exit(1);
+			}
+		}
+		t_send += now() - t1;
+		if (failure_count >= 1024) {
+			fprintf(stderr, "[run_worker_thread] Lots of failures due to missing insert size information.\n");
+			fprintf(stderr, "[run_worker_thread] Terminating due to suspected communication problem.\n");
+			raise(SIGINT); /* the reference sets its static s_interrupted; its own handler does the same (bam2bam.c:129-132) */
+			break;
+		}
+	}
+	fprintf(stderr, "[run_worker_thread] exiting: %ld batches, %ld records, %ld duplicates dropped; wait/recv %.2f s, bam1_to_seq %.2f, "
+	                "host phases %.2f, batch work incl. device %.2f, send %.2f\n", n_batches, n_records, n_dupes, t_wait, t_toseq, t_host, t_fin, t_send);
+	for (it = kh_begin(my_hash); it != kh_end(my_hash); ++it)
+		if (kh_exist(my_hash, it)) free(kh_val(my_hash, it).a);
+	kh_destroy(64, my_hash);
+	free(recs); free(flat); free(taken);
+	zmq_close(upstream);
+	return 0;
 }

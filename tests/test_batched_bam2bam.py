@@ -142,6 +142,89 @@ def adna_case(genome, mode):
     compare(str(d / "adna_cpu.bam"), str(d / f"adna_{mode}.bam"))
 
 
+# ---- the batching 0MQ worker (run_worker_thread replaced): `bam2bam -t 1 -p PORT` keeps the reference's reader, multiplexor
+# and output threads and its wire format; only the worker behind inproc://work_io batches.  `remote` = the same worker
+# inside a separate `bwa worker` process talking to an untouched `bam2bam -t 0 -p PORT` over TCP.
+def free_port():
+    import socket
+    for base in range(41000, 60000, 7):
+        ok = True
+        for p in (base, base + 1, base + 2):
+            with socket.socket() as s:
+                try:
+                    s.bind(("127.0.0.1", p))
+                except OSError:
+                    ok = False
+        if ok:
+            return base
+    raise RuntimeError("no free port triple")
+
+
+def preload_env(mode, env_extra=None):
+    env = dict(os.environ)
+    env["BWAGPU_LANES"] = "1"
+    env["LD_PRELOAD"] = SHIM if mode == "gpu" else STUB + ":" + SHIM
+    env.update(env_extra or {})
+    return env
+
+
+def run_worker_mode(prefix, bam_in, bam_out, mode, remote, env_extra=None):
+    port = free_port()
+    if not remote:
+        r = subprocess.run([DRIVER, "bam2bam", "-g", prefix, "-t", "1", "-p", str(port), "-f", bam_out, bam_in], capture_output=True,
+                           text=True, env=preload_env(mode, env_extra), timeout=1800)
+        assert r.returncode == 0, r.stderr[-3000:]
+        return r.stderr
+    master = subprocess.Popen([DRIVER, "bam2bam", "-g", prefix, "-t", "0", "-p", str(port), "-f", bam_out, bam_in],
+                              stderr=subprocess.PIPE, text=True)
+    worker = subprocess.Popen([DRIVER, "worker", "-t", "1", "-h", "127.0.0.1", "-p", str(port)], stderr=subprocess.PIPE, text=True,
+                              env=preload_env(mode, env_extra))
+    try:
+        _, merr = master.communicate(timeout=1800)
+        _, werr = worker.communicate(timeout=120)
+    finally:
+        for p in (master, worker):
+            if p.poll() is None:
+                p.kill()
+    assert master.returncode == 0, merr[-3000:]
+    return werr
+
+
+def worker_stats(log):
+    line = [l for l in log.splitlines() if l.startswith("[run_worker_thread] exiting:")][-1]
+    w = line.split()
+    return {"batches": int(w[2]), "records": int(w[4]), "dupes": int(w[6])}
+
+
+def worker_case(genome, mode, remote):
+    d, fa, T, fix = genome
+    tag = f"{mode}_{'remote' if remote else 'local'}"
+    # single-end
+    reads = R.bwa.simulate.simulate_reads(T, 3000, (36, 76), seed=3, n_rate=0.002)
+    bam = str(d / "w_se.bam")
+    bamio.write_unaligned_bam(bam, reads)
+    run_bam2bam(fa, bam, str(d / "w_se_cpu.bam"), None)
+    log = run_worker_mode(fa, bam, str(d / f"w_se_{tag}.bam"), mode, remote, {"BWAGPU_WORKER_RECORDS": "700"})
+    compare(str(d / "w_se_cpu.bam"), str(d / f"w_se_{tag}.bam"))
+    st = worker_stats(log)
+    assert st["records"] == 2 * 3000 and st["batches"] < st["records"] / 20  # every record once per pass, in batches
+    # paired-end with mate rescue and shared position-cache entries
+    r1, r2 = R.bwa.simulate.simulate_pairs(T, 2500, 70, seed=5, bad_mate_frac=0.15, bad_mate_sub=0.12)
+    b1, b2 = r1.bases.reshape(-1, 70), r2.bases.reshape(-1, 70)
+    for t, (X, Y) in enumerate(fix):
+        b1[30 * t] = T[Y:Y + 70]
+        b2[30 * t] = 3 - T[X:X + 70][::-1]
+    bam = str(d / "w_pe.bam")
+    bamio.write_unaligned_bam(bam, r1, r2)
+    run_bam2bam(fa, bam, str(d / "w_pe_cpu.bam"), None)
+    log = run_worker_mode(fa, bam, str(d / f"w_pe_{tag}.bam"), mode, remote, {"BWAGPU_WORKER_RECORDS": "600", "BWAGPU_BATCH_SA": "3000"})
+    compare(str(d / "w_pe_cpu.bam"), str(d / f"w_pe_{tag}.bam"))
+    st = worker_stats(log)
+    assert st["records"] == 2 * 2500 and st["batches"] < st["records"] / 20
+    c = calls(log)
+    assert c["cal_sa_reads_gap_units"] == 5000 and c["mate_sw_path_units"] > 20
+
+
 # ---- host logic on the CPU stub (no GPU needed)
 @pytest.fixture(scope="module")
 def stub():
@@ -157,7 +240,20 @@ def test_stub_paired_end(genome, stub):
     pe_case(genome, "stub")
 
 
+def test_stub_worker_local(genome, stub):
+    worker_case(genome, "stub", remote=False)
+
+
+def test_stub_worker_remote(genome, stub):
+    worker_case(genome, "stub", remote=True)
+
+
 # ---- the real thing
+@pytest.mark.gpu
+def test_gpu_worker_local(genome):
+    worker_case(genome, "gpu", remote=False)
+
+
 @pytest.mark.gpu
 def test_gpu_single_end(genome):
     se_case(genome, "gpu")

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbwagpu.so")
 SOURCES = ["bwagpu.cu"]
-DEPS = ["bwagpu.cu", "kernels.cuh", "fmindex.cuh", "sw.cuh", "hostprep.h", os.path.join("..", "..", "include", "bwa_gpu.h")]
+DEPS = ["bwagpu.cu", "kernels.cuh", "search_warp.cuh", "fmindex.cuh", "sw.cuh", "hostprep.h", os.path.join("..", "..", "include", "bwa_gpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

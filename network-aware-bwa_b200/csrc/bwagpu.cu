@@ -26,6 +26,7 @@
 
 #include "../../include/bwa_gpu.h"
 #include "kernels.cuh"
+#include "search_warp.cuh"
 #include "sw.cuh"
 #include "hostprep.h"
 
@@ -390,6 +391,14 @@ static size_t search_smem(bool pooled, uint32_t n_stacks)
 	return BWAGPU_SMEM_HEADS ? (size_t)128 * (n_stacks + 2) * (pooled ? sizeof(uint32_t) : sizeof(uint16_t)) : 0; // + the hit list's two ends
 }
 static bool is_stdmode(int mode) { return (mode & 0x01) && !(mode & 0x04) && !(mode & 0x10); }
+// pass 1 = the warp-per-read kernel (search_warp.cuh) unless BWAGPU_WARP_PASS=0 (then: thread-per-read on the pool, as pass 0 but pooled)
+static bool warp_pass_enabled()
+{
+	const char *e = getenv("BWAGPU_WARP_PASS");
+	return !e || atoi(e) != 0;
+}
+static search_fn warp_kernel(bool stdmode) { return stdmode ? k_search_warp<true> : k_search_warp<false>; }
+static const size_t WARP_SMEM = (size_t)WK_WARPS * WK_WORDS_PER_WARP * sizeof(uint32_t);
 
 static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt, bool stdmode)
 {
@@ -407,6 +416,18 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 		c->x_chunks = (uint32_t)chunks;
 	}
 	const uint32_t need = max_entries_opt + 16; // records one search can hold at most
+	if (t == 1 && warp_pass_enabled()) {
+		// one warp per read, every entry in pool chunks: no private arenas, no chunk table
+		int bps = 0;
+		CK(cudaFuncSetAttribute(warp_kernel(stdmode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, warp_kernel(stdmode), WK_WARPS * 32, WARP_SMEM));
+		if (bps < 1) bps = 1;
+		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_WARP_BLOCKS_PER_SM", 64));
+		T.slots_blocks = (uint32_t)(bps * c->n_sm);
+		T.cap = 0; T.ctab_stride = 1;
+		if (c->ctab.reserve(1)) return 1;
+		return 0;
+	}
 	if (t <= 1) {
 		// pass 0: private arenas only (k_search<.., false>); pass 1: same occupancy, arenas continue in the pool
 		int bps = 0, bps_p = 0;
@@ -564,9 +585,15 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			c->stats.launches += 2;
 		}
 		uint32_t blocks = T.slots_blocks;
-		const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
-		if (blocks > need) blocks = need;
-		search_kernel(stats, t != 0, is_stdmode(opt.mode))<<<blocks, 128, search_smem(t != 0, n_stacks), c->st>>>(B);
+		if (t == 1 && warp_pass_enabled()) {
+			const uint32_t need = (uint32_t)((n_jobs + WK_WARPS - 1) / WK_WARPS);
+			if (blocks > need) blocks = need;
+			warp_kernel(is_stdmode(opt.mode))<<<blocks, WK_WARPS * 32, WARP_SMEM, c->st>>>(B);
+		} else {
+			const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
+			if (blocks > need) blocks = need;
+			search_kernel(stats, t != 0, is_stdmode(opt.mode))<<<blocks, 128, search_smem(t != 0, n_stacks), c->st>>>(B);
+		}
 		CK(cudaGetLastError());
 		c->stats.launches++;
 		CK(cudaEventRecord(c->ev[9 + 2 * t], c->st));

@@ -397,7 +397,16 @@ static bool warp_pass_enabled()
 	const char *e = getenv("BWAGPU_WARP_PASS");
 	return !e || atoi(e) != 0;
 }
-static search_fn warp_kernel(bool stdmode) { return stdmode ? k_search_warp<true> : k_search_warp<false>; }
+static bool warp_stats_enabled()
+{
+	const char *e = getenv("BWAGPU_WARP_STATS");
+	return e && atoi(e) != 0;
+}
+static search_fn warp_kernel(bool stdmode)
+{
+	if (warp_stats_enabled()) return stdmode ? k_search_warp<true, true> : k_search_warp<false, true>;
+	return stdmode ? k_search_warp<true, false> : k_search_warp<false, false>;
+}
 static const size_t WARP_SMEM = (size_t)WK_WARPS * WK_WORDS_PER_WARP * sizeof(uint32_t);
 
 static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt, bool stdmode)
@@ -479,7 +488,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
-	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(16)) return 1;
+	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(32)) return 1;
 	// hit pool of the chunk (completion order): 16 hits per read on average to start with; grown and the
 	// affected reads retried when a batch of short, repetitive reads needs more
 	size_t pool_cap = std::max<size_t>((size_t)n * env_u32("BWAGPU_HITS_PER_READ", 16), 1u << 16);
@@ -501,6 +510,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	B.n_stacks = n_stacks;
 
 	CK(cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(int), c->st));
+	CK(cudaMemsetAsync(c->d_stats.p + 16, 0, 16 * sizeof(unsigned long long), c->st)); // k_search_warp diagnostics
 	if (stats) {
 		unsigned long long init[16] = {0};
 		init[11] = init[12] = ~0ull;
@@ -597,6 +607,17 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		CK(cudaGetLastError());
 		c->stats.launches++;
 		CK(cudaEventRecord(c->ev[9 + 2 * t], c->st));
+		if (t == 1 && warp_pass_enabled() && warp_stats_enabled()) { // diagnostics of k_search_warp (search_warp.cuh)
+			unsigned long long w[16];
+			CK(cudaMemcpyAsync(w, c->d_stats.p + 16, sizeof w, cudaMemcpyDeviceToHost, c->st));
+			CK(cudaStreamSynchronize(c->st));
+			CK(cudaMemsetAsync(c->d_stats.p + 16, 0, sizeof w, c->st));
+			const double r = (double)std::max<unsigned long long>(w[0], 1);
+			fprintf(stderr, "[k_search_warp] reads %llu rounds %llu taken/round %.2f committed/round %.2f steps/lane %.2f longest chain/round %.2f | "
+			                "clocks/round: take %.0f passA %.0f scan+commit+alloc %.0f passB %.0f hit+rest %.0f\n",
+			        w[10], w[0], w[1] / r, w[2] / r, (double)w[3] / (double)std::max<unsigned long long>(w[1], 1), w[4] / r,
+			        w[5] / r, w[6] / r, w[7] / r, w[8] / r, w[9] / r);
+		}
 		CK(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
 		CK(cudaStreamSynchronize(c->st));
 		{

@@ -40,11 +40,14 @@
 
 namespace bwagpu {
 
+#ifndef WK_MINBLOCKS
+#define WK_MINBLOCKS 1 // __launch_bounds__ second argument (A/B switch)
+#endif
 #define WK_WARPS 8    // warps (= reads in flight) per block
 #define WK_NB 257     // 256 score buckets (the ABI's limit) + the read's hit list
 #define WK_HITS 256
 #define WK_SEG 16     // chunks one round may touch per target bucket
-#define WK_WORDS_PER_WARP (2 * WK_NB + 3 * (WK_SEG + 1))
+#define WK_WORDS_PER_WARP (2 * WK_NB + 3 * (WK_SEG + 1) + 32 + 1) // + the chunk cache (WK_CACHE ids + fill)
 
 // chunks of the shared pool: bump counter first, then a lock-free stack of recycled chunks ({tag:32 | head:32} against ABA)
 __device__ __forceinline__ uint32_t pool_chunk_alloc(const Batch &B)
@@ -75,6 +78,76 @@ __device__ __forceinline__ void pool_chunk_free(const Batch &B, uint32_t c)
 	}
 }
 
+// Recycled chunks of the warp pass: a lock-free stack of BATCHES.  A batch is a head chunk plus up to WK_BATCH_MAX
+// more chunk ids written into the head chunk's own link words (xnxt[head << 10 | 1] = next batch, [.. | 2] = count,
+// [.. | 3 ..] = ids), so taking or returning 16 chunks is ONE compare-and-swap on the pool's head word
+// ({tag:32 | head:32} against ABA).  k_search's one-chunk-at-a-time list (kernels.cuh) is a different launch.
+#define WK_BATCH_MAX 15
+__device__ __forceinline__ void pool_batch_push(const Batch &B, uint32_t head)
+{
+	volatile uint32_t *const xw = (volatile uint32_t *)B.xnxt + ((size_t)head << ARENA_CHUNK_LOG);
+	unsigned long long old = *(volatile unsigned long long *)B.x_free_top;
+	for (;;) {
+		xw[1] = (uint32_t)old;
+		__threadfence();
+		const unsigned long long nw = (((old >> 32) + 1ull) << 32) | head;
+		const unsigned long long prev = atomicCAS(B.x_free_top, old, nw);
+		if (prev == old) return;
+		old = prev;
+	}
+}
+
+// Per-warp chunk cache (shared memory; one lane at a time uses it).  2368 warps allocating and freeing a chunk every few
+// rounds through the pool's single head word serialise on it (measured: 300 us per round); with the cache the pool sees one
+// bump-counter add per WK_BUMP allocations, or one compare-and-swap per batch.
+#define WK_CACHE 32
+#define WK_BUMP 8
+__device__ __forceinline__ uint32_t wk_alloc(const Batch &B, uint32_t *cache, uint32_t *cache_n)
+{
+	const uint32_t n = *cache_n;
+	if (n) { *cache_n = n - 1; return cache[n - 1]; }
+	if (*(volatile unsigned int *)B.x_next < B.x_chunks) { // chunks never handed out yet
+		const uint32_t c0 = atomicAdd(B.x_next, (unsigned int)WK_BUMP);
+		if (c0 < B.x_chunks) {
+			const uint32_t m = min((uint32_t)WK_BUMP, B.x_chunks - c0);
+			for (uint32_t q = 1; q < m; ++q) cache[q - 1] = c0 + q;
+			*cache_n = m - 1;
+			return c0;
+		}
+	}
+	unsigned long long old = *(volatile unsigned long long *)B.x_free_top; // a batch of recycled chunks
+	while ((uint32_t)old != NIL) {
+		const uint32_t head = (uint32_t)old;
+		volatile uint32_t *const xw = (volatile uint32_t *)B.xnxt + ((size_t)head << ARENA_CHUNK_LOG);
+		const uint32_t nx = xw[1];
+		const unsigned long long nw = (((old >> 32) + 1ull) << 32) | nx;
+		const unsigned long long prev = atomicCAS(B.x_free_top, old, nw);
+		if (prev == old) {
+			const uint32_t m = xw[2];
+			for (uint32_t q = 0; q < m; ++q) cache[q] = xw[3 + q];
+			*cache_n = m;
+			return head;
+		}
+		old = prev;
+	}
+	return NIL;
+}
+
+__device__ __forceinline__ void wk_free(const Batch &B, uint32_t *cache, uint32_t *cache_n, uint32_t c)
+{
+	uint32_t n = *cache_n;
+	if (n == WK_CACHE) { // full: hand the upper half back as one batch
+		const uint32_t head = cache[WK_CACHE - 1];
+		volatile uint32_t *const xw = (volatile uint32_t *)B.xnxt + ((size_t)head << ARENA_CHUNK_LOG);
+		xw[2] = WK_BATCH_MAX;
+		for (uint32_t q = 0; q < WK_BATCH_MAX; ++q) xw[3 + q] = cache[WK_CACHE - 2 - q];
+		pool_batch_push(B, head);
+		n = WK_CACHE - 1 - WK_BATCH_MAX;
+	}
+	cache[n] = c;
+	*cache_n = n + 1;
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
 #pragma unroll
@@ -92,8 +165,8 @@ __device__ __forceinline__ int warp_max(int v)
 	return v;
 }
 
-template <bool STDMODE>
-__global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
+template <bool STDMODE, bool WSTATS>
+__global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(const Batch B)
 {
 	extern __shared__ __align__(16) uint32_t wk_smem[];
 	const unsigned FULL = 0xffffffffu;
@@ -101,6 +174,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 	uint32_t *const cnt = wk_smem + (size_t)wib * WK_WORDS_PER_WARP; // entries per bucket
 	uint32_t *const top = cnt + WK_NB;                                // chunk holding a bucket's top entry (NIL: empty)
 	uint32_t *const seg = top + WK_NB; // per target slot: [0] = number of the first chunk this round writes, [1 + r] = chunk ids
+	uint32_t *const cache = seg + 3 * (WK_SEG + 1), *const cache_n = cache + 32; // chunk cache, kept from read to read
+	if (lane == 0) *cache_n = 0;
+	__syncwarp();
 	const GapOpt &O = B.opt;
 	const bool gape_mode = STDMODE || (O.mode & 0x01), loggap = !STDMODE && (O.mode & 0x04), nonstop = !STDMODE && (O.mode & 0x10);
 	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
@@ -142,7 +218,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 		{ // the two root entries (bwtgap.c:127-128): strand 0 below strand 1
 			uint32_t c = NIL;
 			if (lane == 0) {
-				c = pool_chunk_alloc(B);
+				c = wk_alloc(B, cache, cache_n);
 				if (c != NIL) {
 					xlink[(size_t)c << ARENA_CHUNK_LOG] = NIL;
 					xent[((size_t)c << ARENA_CHUNK_LOG) + 0] = make_uint4(0u, B.ix[0].seq_len, (uint32_t)len, 0u);
@@ -157,7 +233,11 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 		}
 
 		int tcap = 32; // lanes per round: halved after a round that had to drop lanes, doubled otherwise
+		// diagnostics (BWAGPU_WARP_STATS=1 prints them): rounds, lanes taken / committed, chain steps, clocks per phase
+		unsigned long long st_rounds = 0, st_taken = 0, st_com = 0, st_steps = 0, st_maxsteps = 0, st_ck[6] = {0, 0, 0, 0, 0, 0};
+		int steps = 0;
 		while (!overflow) { // rounds
+			long long ck0 = clock64();
 			if (n_entries == 0) break;
 			if (max_entries < n_entries) max_entries = n_entries;
 			if (n_entries > limit) break;  // bwtgap.c:140
@@ -187,7 +267,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 			int net = 0, maxpre = 0;           // net change of n_entries; its highest value at a pop, relative to the chain's start
 			bool hit = false, brk = false, ovf = false;
 			uint32_t hk = 0, hl = 0, h_tag = 0, h_ldp = 0;
-			auto chain = [&](const bool WR, const int base, const uint32_t wb0, const uint32_t wb1, const uint32_t wb2) {
+			auto chain = [&](const bool WR, const int base, const uint32_t wb0, const uint32_t wb1, const uint32_t wb2, const bool hitA, const uint32_t hkA,
+			                 const uint32_t hlA) {
 				uint32_t k = e.x, l = e.y, ldp = e.z >> 16;
 				int i = (int)(e.z & 0xffffu);
 				uint32_t mm = e.w & 0xffu, go = (e.w >> 8) & 0xffu, ge = (e.w >> 16) & 0xffu, st = (e.w >> 24) & 3u;
@@ -196,6 +277,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 				const uint2 *const cx = B.ctx + (size_t)w_off + (size_t)a * WSTRIDE(len);
 				int pre = 0;
 				n0 = n1 = n2 = 0; maxpre = 0; hit = brk = ovf = false;
+				steps = 0;
 				auto push = [&](uint32_t pk, uint32_t pl, uint32_t ppos, uint32_t ptag, int delta, int slot) {
 					++pre; // gap_push: ++stack->n_entries (bwtgap.c:62)
 					const int sb = s + delta;
@@ -209,43 +291,61 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 						xent[((size_t)c << ARENA_CHUNK_LOG) + (p & (ARENA_CHUNK - 1))] = make_uint4(pk, pl, ppos, ptag);
 					}
 				};
+				bool exact = false; // walking the exact-match tail (bwt_match_exact_alt, bwt.c:237-252), one base per iteration
+				uint32_t xc = 0;    // ... and the base it matches next
 				for (;;) {
-					// loop top of bwtgap.c:139-141 for this pop
-					if (pre > maxpre) maxpre = pre;
-					if (WR && base + pre > limit) { brk = true; break; }
-					--pre; // gap_pop
-					int m = max_diff - (int)(mm + go);
-					if (gape_mode) m -= (int)ge;
-					if (m < 0) break;
-					const uint2 cw = cx[i]; // k_ctx: width[i-1], width[i-2].bid, the seed widths, str[i-1], str[i-2]
-					if (i > 0 && m < (int)(cw.x & CW_BID)) break; // bwtgap.c:157
-					if (i == 0) { hit = true; }
-					else if (m == 0 && (st == STATE_M || gape_mode || (int)ge == O.max_gape)) { // no diff allowed: bwt_match_exact_alt (bwt.c:237-252)
-						hit = true;
-						for (int x = i - 1; x >= 0; --x) {
-							const uint32_t c = (uint32_t)(seqp[x] >> (a << 2)) & 15u;
-							if (c > 3u) { hit = false; break; }
-							uint32_t okk, oll, f1 = 0, f2 = 0;
-							occ1_pair<false>(ix, k - 1, l, c, okk, oll, f1, f2);
-							const uint32_t cb = c == 0 ? 0u : c == 1 ? C1 : c == 2 ? C2 : C3;
-							k = cb + okk + 1; l = cb + oll;
-							if (k > l) { hit = false; break; }
+					// one memory round trip per iteration whatever the lane is doing: both occurrence blocks, and the
+					// node's context word (expansion) or the next read base (exact tail), are issued before any is used
+					const uint32_t jk = occ_arg(ix, k - 1), jl = occ_arg(ix, l);
+					const OccBlock ob_l = load_block(ix, jl >> 6);
+					const OccBlock ob_k = load_block(ix, jk >> 6);
+					uint2 cw = make_uint2(0u, 0u);
+					if (exact) xc = (uint32_t)(seqp[i - 1] >> (a << 2)) & 15u;
+					else cw = cx[i]; // k_ctx: width[i-1], width[i-2].bid, the seed widths, str[i-1], str[i-2]
+					int m = 0;
+					if (!exact) {
+						// loop top of bwtgap.c:139-141 for this pop
+						++steps;
+						if (pre > maxpre) maxpre = pre;
+						if (WR && base + pre > limit) { brk = true; break; }
+						--pre; // gap_pop
+						m = max_diff - (int)(mm + go);
+						if (gape_mode) m -= (int)ge;
+						if (m < 0) break;
+						if (i > 0 && m < (int)(cw.x & CW_BID)) break; // bwtgap.c:157
+						if (i == 0) {
+							hit = true; hk = k; hl = l; h_ldp = ldp; h_tag = mm | go << 8 | ge << 16 | a << 24;
+							break;
 						}
-						if (!hit) break;
+						if (m == 0 && (st == STATE_M || gape_mode || (int)ge == O.max_gape)) { // no diff allowed: exact tail
+							if (WR) { // pass B: the tail pushes nothing and its outcome is known from pass A
+								if (hitA) { hit = true; hk = hkA; hl = hlA; h_ldp = ldp; h_tag = mm | go << 8 | ge << 16 | a << 24; }
+								break;
+							}
+							exact = true;
+							xc = (cw.x >> 12) & 7u; // str[i-1]
+						}
 					}
-					if (hit) {
-						hk = k; hl = l; h_ldp = ldp;
-						h_tag = mm | go << 8 | ge << 16 | a << 24;
-						break;
-					}
-					--i;
 					uint32_t nk[4], nl[4];
 					{
-						uint32_t ck[4], cl[4], f1 = 0, f2 = 0;
-						occ4_pair<false>(ix, k - 1, l, ck, cl, f1, f2);
+						uint32_t ck[4], cl[4];
+						occ4_in_block(ob_k, jk, ck);
+						occ4_in_block(ob_l, jl, cl);
 						nk[0] = ck[0] + 1; nk[1] = C1 + ck[1] + 1; nk[2] = C2 + ck[2] + 1; nk[3] = C3 + ck[3] + 1;
 						nl[0] = cl[0]; nl[1] = C1 + cl[1]; nl[2] = C2 + cl[2]; nl[3] = C3 + cl[3];
 					}
+					if (exact) {
+						if (xc > 3u) break; // an N: no match
+						k = sel4(xc, nk); l = sel4(xc, nl);
+						--i;
+						if (k > l) break;
+						if (i == 0) {
+							hit = true; hk = k; hl = l; h_ldp = ldp; h_tag = mm | go << 8 | ge << 16 | a << 24;
+							break;
+						}
+						continue;
+					}
+					--i;
 					const uint32_t occ = l - k + 1;
 					bool allow_diff = true, allow_M = true;
 					if (i > 0) { // bwtgap.c:206-215; the node's context word was packed for position i + 1
@@ -310,8 +410,14 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 			};
 
 			// ---- pass A: count
-			if (mine) chain(false, 0, 0u, 0u, 0u);
+			long long ck1 = clock64();
+			if (mine) chain(false, 0, 0u, 0u, 0u, false, 0u, 0u);
 			__syncwarp();
+			long long ck2 = clock64();
+			if (WSTATS) {
+				st_steps += (unsigned long long)__reduce_add_sync(FULL, mine ? steps : 0);
+				st_maxsteps += (unsigned long long)__reduce_max_sync(FULL, mine ? steps : 0);
+			}
 
 			// ---- who commits: everything up to the first lane whose chain changes what later pops see
 			const int netA = mine ? net : 0;
@@ -346,7 +452,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 					const int keep = newc ? (int)((newc - 1) >> ARENA_CHUNK_LOG) : -1;
 					while (q > keep) {
 						const uint32_t below = xlink[(size_t)c << ARENA_CHUNK_LOG];
-						pool_chunk_free(B, c);
+						wk_free(B, cache, cache_n, c);
 						c = below; --q;
 					}
 					top[s] = newc ? c : NIL;
@@ -372,7 +478,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 						sg[0] = q0;
 						for (uint32_t q = q0; q <= q1; ++q) {
 							if ((int)q != have) {
-								const uint32_t c = pool_chunk_alloc(B);
+								const uint32_t c = wk_alloc(B, cache, cache_n);
 								if (c == NIL) { fail = 1; break; }
 								xlink[(size_t)c << ARENA_CHUNK_LOG] = cur;
 								cur = c;
@@ -392,8 +498,15 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 			}
 
 			// ---- pass B: the committed lanes store their pushes at their final positions
-			if (com) chain(true, base_j, wb0, wb1, wb2);
+			long long ck3 = clock64();
+			if (com) { const bool hA = hit; const uint32_t kA = hk, lA = hl; chain(true, base_j, wb0, wb1, wb2, hA, kA, lA); }
 			__syncwarp();
+			long long ck4 = clock64();
+			if (WSTATS) {
+				++st_rounds; st_taken += (unsigned long long)T; st_com += (unsigned long long)(h + 1);
+				st_ck[0] += (unsigned long long)(ck1 - ck0); st_ck[1] += (unsigned long long)(ck2 - ck1); st_ck[2] += (unsigned long long)(ck3 - ck2);
+				st_ck[3] += (unsigned long long)(ck4 - ck3);
+			}
 			{
 				const int tot = warp_incl_scan(com ? net : 0, lane);
 				n_entries += __shfl_sync(FULL, tot, 31);
@@ -456,7 +569,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 						// append to the read's hit list
 						uint32_t c = top[WK_HITS];
 						if ((n_aln & (int)(ARENA_CHUNK - 1)) == 0) {
-							const uint32_t nc = pool_chunk_alloc(B);
+							const uint32_t nc = wk_alloc(B, cache, cache_n);
 							if (nc == NIL) stop = 2;
 							else { xlink[(size_t)nc << ARENA_CHUNK_LOG] = c; top[WK_HITS] = c = nc; }
 						}
@@ -479,6 +592,13 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 				if (stop) break;
 			}
 			tcap = h < T - 1 ? max(1, min(tcap >> 1, h + 1)) : min(32, tcap << 1);
+			if (WSTATS) st_ck[4] += (unsigned long long)(clock64() - ck4);
+		}
+		if (WSTATS && lane == 0) {
+			atomicAdd(B.stats + 16, st_rounds); atomicAdd(B.stats + 17, st_taken); atomicAdd(B.stats + 18, st_com);
+			atomicAdd(B.stats + 19, st_steps); atomicAdd(B.stats + 20, st_maxsteps);
+			for (int q = 0; q < 5; ++q) atomicAdd(B.stats + 21 + q, st_ck[q]);
+			atomicAdd(B.stats + 26, 1ull);
 		}
 
 		// ---- results, then every chunk of the read goes back to the pool
@@ -505,12 +625,17 @@ __global__ void __launch_bounds__(WK_WARPS * 32) k_search_warp(const Batch B)
 			if (lane == 0) { B.n_aln[rid] = n_aln; B.pool_off[rid] = off; B.max_entries[rid] = max_entries; }
 		}
 		__syncwarp();
-		for (int b = lane; b < WK_NB; b += 32) {
-			uint32_t c = top[b];
-			while (c != NIL) {
-				const uint32_t below = xlink[(size_t)c << ARENA_CHUNK_LOG];
-				pool_chunk_free(B, c);
-				c = below;
+		{ // every lane returns the chunks of its buckets in batches: the first chunk it meets heads a batch, the next ones are listed in it
+			for (int b = lane; b < WK_NB; b += 32) {
+				uint32_t c = top[b], head = NIL, m = 0;
+				volatile uint32_t *xw = nullptr;
+				while (c != NIL) {
+					const uint32_t below = xlink[(size_t)c << ARENA_CHUNK_LOG];
+					if (head == NIL) { head = c; m = 0; xw = (volatile uint32_t *)B.xnxt + ((size_t)head << ARENA_CHUNK_LOG); }
+					else xw[3 + m++] = c;
+					if (m == WK_BATCH_MAX || below == NIL) { xw[2] = m; pool_batch_push(B, head); head = NIL; }
+					c = below;
+				}
 			}
 		}
 		__syncwarp();

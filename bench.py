@@ -356,6 +356,33 @@ def main():
                             "kernel_ms": sw_ms, "gcups_forward_kernel": nj * wlen * rlen / (sw_ms / 1e3) / 1e9,
                             "shape": f"{wlen} x {rlen}", "note": "host buffers in and out; forward + reverse pass"}}
 
+        # C5 of BASELINE.json (a parity-test configuration, reported here as a secondary number): ancient-DNA-style 30-50 bp
+        # reads, seeding off (-l 1024), -n 0.01 -o 2.  ~10 % of the reads outgrow pass 0 and go through the warp-per-read
+        # pass (csrc/search_warp.cuh); the batch is resident, device-timed like `value`.
+        try:
+            import refload as R
+            n5 = 1_000_000
+            reads5 = bwa.simulate.simulate_reads(T, n5, (30, 50), seed=1000, device=f"cuda:{local_rank}", adna=True, sub_rate=0.01)
+            opt5 = abi.default_gap_opt(seed_len=1024, fnr=0.01, max_gapo=2)
+            api.resident_stage(reads5.bases, reads5.offs, opt5)
+            api.resident_run()
+            ms5 = api.resident_run(); st5 = api.get_stats()
+            c5 = {"workload": "1M aDNA-style 30-50bp reads, -l 1024 -n 0.01 -o 2, same 100 Mb genome (BASELINE.json configs[4])",
+                  "reads_per_s": n5 / (ms5 / 1e3), "ms": ms5, "pass_ms": st5["ms_tier"][:3], "width_ms": st5["ms_width"],
+                  "reads_through_warp_pass": int(st5["n_overflow_t2"]), "reads_through_guaranteed_pass": int(st5["n_overflow_t3"])}
+            if R.have_ref():
+                got5 = api.resident_fetch(n5)
+                m5 = 100_000
+                sub5 = bwa.simulate.Reads(reads5.bases[: reads5.offs[m5]], reads5.offs[: m5 + 1], None, None)
+                want5 = R.ref_aln(R.RefIndex(idx), sub5, opt5, threads=host_cores); dt5r = R.ref_aln.last_batch_s
+                got5s = (got5[0][:m5], got5[1][:m5], got5[2][: m5 + 1], got5[3][: got5[2][m5]])
+                c5["cpu_reference_reads_per_s"] = m5 / dt5r
+                c5["cpu_sample"] = f"first {m5} reads, {dt5r:.1f} s, bwa_cal_sa_reg_gap per read over {host_cores} threads"
+                c5["parity_mismatches"] = len(R.compare_aln(want5, got5s, "c5"))
+            extras["c5_adna"] = c5
+        except Exception as e:
+            extras["c5_adna"] = {"error": str(e)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

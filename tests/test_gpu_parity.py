@@ -76,6 +76,47 @@ def test_chunking_and_tiers_are_invisible(golden, gpu_index, monkeypatch):
     assert R.compare_aln(want, got, "chunked") == []
 
 
+@pytest.mark.parametrize("name", CONFIGS)
+def test_warp_pass_matches_golden(golden, gpu_index, monkeypatch, name):
+    """A 2-record pass-0 arena sends (nearly) every read through k_search_warp (csrc/search_warp.cuh): one warp per read,
+    the lanes draining the lowest bucket's top entries as independent chains.  Same bytes."""
+    reads, opt, want = golden_case(golden, name)
+    monkeypatch.setenv("BWAGPU_T1_CAP", "2")
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    st = api.get_stats()
+    assert st["n_overflow_t2"] > reads.n // 2 and st["n_overflow_t3"] == 0   # they went through the warp pass and finished there
+    assert R.compare_aln(want, got, "warp pass " + name) == []
+
+
+def test_thread_pass_still_available(golden, gpu_index, monkeypatch):
+    """BWAGPU_WARP_PASS=0: pass 1 is the pooled thread-per-read kernel again (A/B switch)."""
+    reads, opt, want = golden_case(golden, "adna")
+    monkeypatch.setenv("BWAGPU_T1_CAP", "2")
+    monkeypatch.setenv("BWAGPU_WARP_PASS", "0")
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    assert R.compare_aln(want, got, "thread pass") == []
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("cap", ["2", "2048"])
+@pytest.mark.parametrize("label,length,optkw,simkw,n", [
+    ("adna deep", (30, 50), dict(seed_len=1024, fnr=0.01, max_gapo=2), dict(adna=True, sub_rate=0.06), 20000),
+    ("equal penalties: shared target bucket", 50, dict(s_mm=4, s_gapo=9, s_gape=4, max_gapo=2), dict(sub_rate=0.04), 5000),
+    ("all penalties equal", 50, dict(s_mm=3, s_gapo=3, s_gape=3, max_gapo=2), dict(sub_rate=0.04), 5000),
+    ("zero gap extension: serial rounds", 50, dict(s_mm=3, s_gapo=11, s_gape=0, max_gapo=1), dict(sub_rate=0.03), 3000),
+    ("max_entries stop", (30, 50), dict(seed_len=1024, fnr=0.01, max_gapo=2, max_entries=3000), dict(adna=True, sub_rate=0.05), 10000),
+    ("ragged, N", (15, 250), dict(max_gapo=2, max_gape=10), dict(n_rate=0.005), 10000),
+])
+def test_warp_pass_matches_reference_live(gpu_index, monkeypatch, cap, label, length, optkw, simkw, n):
+    T, idx = gpu_index
+    reads = R.bwa.simulate.simulate_reads(T, n, length, seed=777, **simkw)
+    opt = abi.default_gap_opt(**optkw)
+    want = R.ref_aln(R.RefIndex(idx), reads, opt, threads=8)
+    monkeypatch.setenv("BWAGPU_T1_CAP", cap)
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    assert R.compare_aln(want, got, f"warp pass live, {label}, cap {cap}") == []
+
+
 def test_stats_counters(golden, gpu_index):
     reads, opt, want = golden_case(golden, "se76")
     api.set_stats(True)

@@ -40,14 +40,17 @@
 
 namespace bwagpu {
 
-#ifndef WK_MINBLOCKS
-#define WK_MINBLOCKS 1 // __launch_bounds__ second argument (A/B switch)
+#ifndef WK_WARPS_PER_BLOCK
+#define WK_WARPS_PER_BLOCK 4 // 4 warps x 5 blocks per SM measured 6 % faster than 8 x 2 (profiles/r1_ab_experiments.md)
 #endif
-#define WK_WARPS 8    // warps (= reads in flight) per block
+#ifndef WK_MINBLOCKS
+#define WK_MINBLOCKS 5 // __launch_bounds__ second argument: 96 registers
+#endif
+#define WK_WARPS WK_WARPS_PER_BLOCK // warps (= reads in flight) per block
 #define WK_NB 257     // 256 score buckets (the ABI's limit) + the read's hit list
 #define WK_HITS 256
 #define WK_SEG 16     // chunks one round may touch per target bucket
-#define WK_WORDS_PER_WARP (2 * WK_NB + 3 * (WK_SEG + 1) + 32 + 1) // + the chunk cache (WK_CACHE ids + fill)
+#define WK_WORDS_PER_WARP (2 * WK_NB + 3 * (WK_SEG + 1) + 64 + 1) // + the chunk cache (WK_CACHE ids + fill)
 
 // chunks of the shared pool: bump counter first, then a lock-free stack of recycled chunks ({tag:32 | head:32} against ABA)
 __device__ __forceinline__ uint32_t pool_chunk_alloc(const Batch &B)
@@ -100,7 +103,7 @@ __device__ __forceinline__ void pool_batch_push(const Batch &B, uint32_t head)
 // Per-warp chunk cache (shared memory; one lane at a time uses it).  2368 warps allocating and freeing a chunk every few
 // rounds through the pool's single head word serialise on it (measured: 300 us per round); with the cache the pool sees one
 // bump-counter add per WK_BUMP allocations, or one compare-and-swap per batch.
-#define WK_CACHE 32
+#define WK_CACHE 64
 #define WK_BUMP 8
 __device__ __forceinline__ uint32_t wk_alloc(const Batch &B, uint32_t *cache, uint32_t *cache_n)
 {
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 	uint32_t *const cnt = wk_smem + (size_t)wib * WK_WORDS_PER_WARP; // entries per bucket
 	uint32_t *const top = cnt + WK_NB;                                // chunk holding a bucket's top entry (NIL: empty)
 	uint32_t *const seg = top + WK_NB; // per target slot: [0] = number of the first chunk this round writes, [1 + r] = chunk ids
-	uint32_t *const cache = seg + 3 * (WK_SEG + 1), *const cache_n = cache + 32; // chunk cache, kept from read to read
+	uint32_t *const cache = seg + 3 * (WK_SEG + 1), *const cache_n = cache + 64; // chunk cache, kept from read to read
 	if (lane == 0) *cache_n = 0;
 	__syncwarp();
 	const GapOpt &O = B.opt;
@@ -625,18 +628,26 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 			if (lane == 0) { B.n_aln[rid] = n_aln; B.pool_off[rid] = off; B.max_entries[rid] = max_entries; }
 		}
 		__syncwarp();
-		{ // every lane returns the chunks of its buckets in batches: the first chunk it meets heads a batch, the next ones are listed in it
+		{ // The chunks of the read go to the warp's cache first (the next read needs a chunk per non-empty bucket at once);
+		  // what does not fit is returned in batches: the first such chunk a lane meets heads a batch, the next ones are listed in it
+			uint32_t head = NIL, m = 0;
+			volatile uint32_t *xw = nullptr;
 			for (int b = lane; b < WK_NB; b += 32) {
-				uint32_t c = top[b], head = NIL, m = 0;
-				volatile uint32_t *xw = nullptr;
+				uint32_t c = top[b];
 				while (c != NIL) {
 					const uint32_t below = xlink[(size_t)c << ARENA_CHUNK_LOG];
-					if (head == NIL) { head = c; m = 0; xw = (volatile uint32_t *)B.xnxt + ((size_t)head << ARENA_CHUNK_LOG); }
-					else xw[3 + m++] = c;
-					if (m == WK_BATCH_MAX || below == NIL) { xw[2] = m; pool_batch_push(B, head); head = NIL; }
+					const uint32_t pos = atomicAdd(cache_n, 1u);
+					if (pos < WK_CACHE) cache[pos] = c;
+					else {
+						atomicSub(cache_n, 1u);
+						if (head == NIL) { head = c; m = 0; xw = (volatile uint32_t *)B.xnxt + ((size_t)head << ARENA_CHUNK_LOG); }
+						else xw[3 + m++] = c;
+						if (m == WK_BATCH_MAX) { xw[2] = m; pool_batch_push(B, head); head = NIL; }
+					}
 					c = below;
 				}
 			}
+			if (head != NIL) { xw[2] = m; pool_batch_push(B, head); }
 		}
 		__syncwarp();
 	}

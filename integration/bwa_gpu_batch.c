@@ -42,11 +42,13 @@
 #define _GNU_SOURCE
 #include <dlfcn.h>
 #include <getopt.h>
+#include <pthread.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "bamlite.h"
@@ -55,6 +57,7 @@
 #include "bwape.h"
 #include "khash.h"
 #include "bgzf.h"
+#include "zmq.h" /* oracle/zmq_shim: the libzmq ABI the reference is built against */
 #include "bwa_gpu.h" /* after bwtaln.h: re-uses the reference's own types */
 
 KHASH_MAP_INIT_INT64(64, poslist_t) /* the position cache's type, as bam2bam.c:38 declares it */
@@ -91,7 +94,7 @@ static const bntseq_t *g_bns;  /* bam2bam.c:89 */
 static ubyte_t *g_pac;         /* bam2bam.c:91 */
 static gap_opt_t *g_gap;       /* bam2bam.c:94 */
 static pe_opt_t *g_pe;         /* bam2bam.c:95 */
-static int g_broken_input, g_skip_duplicates, g_drop_aligned; /* bam2bam.c:98-101, options 130 / 131 / 133 */
+static int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned; /* bam2bam.c:96-101, options 130 / 131 / 133 / 128 */
 static isize_info_t g_null_ii; /* bam2bam.c:106 */
 
 bwt_t *bwt_restore_bwt(const char *fn, int touch)
@@ -127,6 +130,7 @@ int getopt_long(int argc, char *const argv[], const char *optstring, const struc
 {
 	REAL(int, getopt_long, int, char *const *, const char *, const struct option *, int *);
 	const int c = real_getopt_long(argc, argv, optstring, longopts, longindex);
+	if (c == 128) g_only_aligned = 1;      /* bam2bam.c:1988 */
 	if (c == 130) g_broken_input = 1;      /* bam2bam.c:1991 */
 	if (c == 131) g_skip_duplicates = 1;
 	if (c == 133) g_drop_aligned = 1;
@@ -143,6 +147,53 @@ static int unique_rec(const bam_pair_t *p) /* bam2bam.c:595-606 */
 	return 1;
 }
 
+
+/* ------------------------------------------------------------------ host threads
+ * With the hot path on the device, what is left of a bam2bam run is per-record host work of the reference
+ * (bam1_to_seq, bwa_refine_gapped, bwa_update_bam1, the temp-file codec, deflate).  The reference itself runs these
+ * functions concurrently in its worker threads (run_worker_thread, bam2bam.c:1387), so they are re-entrant; the shim
+ * spreads each such phase of a batch over BWAGPU_SHIM_THREADS threads (default: the host's cores, at most 32).
+ * Everything order-sensitive (drand48 in bwa_aln2seq_core, the position cache, isize statistics) stays serial. */
+typedef void (*pf_fn)(size_t i, void *ctx);
+typedef struct { size_t n, grain; size_t next; pf_fn fn; void *ctx; } pf_job_t;
+
+static int shim_threads(void)
+{
+	static int n;
+	if (!n) {
+		const char *e = getenv("BWAGPU_SHIM_THREADS");
+		n = e ? atoi(e) : (int)sysconf(_SC_NPROCESSORS_ONLN);
+		if (n < 1) n = 1;
+		if (n > 32) n = 32;
+	}
+	return n;
+}
+
+static void *pf_worker(void *arg)
+{
+	pf_job_t *j = (pf_job_t *)arg;
+	for (;;) {
+		const size_t lo = __sync_fetch_and_add(&j->next, j->grain);
+		size_t i, hi;
+		if (lo >= j->n) break;
+		hi = lo + j->grain < j->n ? lo + j->grain : j->n;
+		for (i = lo; i < hi; ++i) j->fn(i, j->ctx);
+	}
+	return 0;
+}
+
+static void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
+{
+	pf_job_t j = {n, grain ? grain : 1, 0, fn, ctx};
+	pthread_t th[32];
+	int t, nt = shim_threads();
+	if ((size_t)nt > (n + j.grain - 1) / j.grain) nt = (int)((n + j.grain - 1) / j.grain);
+	if (nt <= 1) { pf_worker(&j); return; }
+	for (t = 1; t < nt; ++t) pthread_create(&th[t], 0, pf_worker, &j);
+	pf_worker(&j);
+	for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
+}
+
 /* ------------------------------------------------------------------ device context */
 static int g_ready;
 static long g_calls_aln, g_calls_sa, g_calls_sw, g_reads_aln, g_q_sa, g_jobs_sw;
@@ -154,6 +205,9 @@ static void report(void)
 	                "mate_sw_path=%ld (%ld jobs, %.2f s)\n", g_calls_aln, g_reads_aln, g_t_aln, g_calls_sa, g_q_sa, g_t_sa,
 	        g_calls_sw, g_jobs_sw, g_t_sw);
 }
+
+static void ensure_gpu(void);
+static void *ensure_gpu_thread(void *arg) { (void)arg; ensure_gpu(); return 0; }
 
 static void ensure_gpu(void)
 {
@@ -307,6 +361,213 @@ static void swq_run(swq_t *q)
 	g_sw_pos = 0;
 }
 
+
+/* ------------------------------------------------------------------ the intermediate file, kept in memory
+ * Pass 1 hands its records to pass 2 through a gzip'ed temporary file in the reference (pair_print_custom /
+ * read_pair_custom, bam2bam.c:1099-1137: the 0MQ message encoding of a record, length-prefixed).  Deflate and inflate of
+ * that file were 6 of the 21 seconds of a 2 M-read run once the hot path was on the device.  The shim keeps the SAME
+ * encoded messages (the reference's msg_init_from_pair / pair_init_from_msg, so a record makes the same round trip) in
+ * memory, up to BWAGPU_MEMTEMP_MB (default: a quarter of physical memory, at most 64 GB), and spills whatever comes
+ * after that to the reference's temporary file in the reference's format.  Encoding and decoding run on the host threads. */
+void msg_init_from_pair(zmq_msg_t *m, bam_pair_t *p);
+void pair_init_from_msg(bam_pair_t *p, zmq_msg_t *m);
+
+#define MT_CHUNK ((size_t)64 << 20)
+typedef struct {
+	uint8_t **chunk; size_t n_chunk, m_chunk, used;
+	uint8_t **rec; uint32_t *len; size_t n_rec, m_rec, rd;
+	size_t bytes, cap;
+	int spilled;
+} memtemp_t;
+static memtemp_t g_mt;
+
+static size_t memtemp_cap(void)
+{
+	const char *e = getenv("BWAGPU_MEMTEMP_MB"), *eb = getenv("BWAGPU_MEMTEMP_BYTES");
+	size_t cap;
+	if (eb) return (size_t)atoll(eb);
+	if (e) return (size_t)atoll(e) << 20;
+	cap = (size_t)sysconf(_SC_PHYS_PAGES) * (size_t)sysconf(_SC_PAGESIZE) / 4;
+	return cap > ((size_t)64 << 30) ? (size_t)64 << 30 : cap;
+}
+
+static int memtemp_put(const void *data, uint32_t len)
+{
+	memtemp_t *t = &g_mt;
+	if (t->spilled || t->bytes + len > t->cap || len > MT_CHUNK) { t->spilled = 1; return 0; }
+	if (t->n_chunk == 0 || t->used + len > MT_CHUNK) {
+		if (t->n_chunk == t->m_chunk) { t->m_chunk = t->m_chunk ? t->m_chunk << 1 : 16; t->chunk = (uint8_t **)realloc(t->chunk, t->m_chunk * sizeof(*t->chunk)); }
+		t->chunk[t->n_chunk] = (uint8_t *)malloc(MT_CHUNK);
+		if (!t->chunk[t->n_chunk]) { t->spilled = 1; return 0; }
+		++t->n_chunk; t->used = 0;
+	}
+	if (t->n_rec == t->m_rec) {
+		t->m_rec = t->m_rec ? t->m_rec << 1 : 1 << 20;
+		t->rec = (uint8_t **)realloc(t->rec, t->m_rec * sizeof(*t->rec));
+		t->len = (uint32_t *)realloc(t->len, t->m_rec * sizeof(*t->len));
+	}
+	t->rec[t->n_rec] = t->chunk[t->n_chunk - 1] + t->used;
+	t->len[t->n_rec] = len;
+	memcpy(t->rec[t->n_rec], data, len);
+	++t->n_rec; t->used += len; t->bytes += len;
+	return 1;
+}
+
+static void memtemp_free(void)
+{
+	size_t i;
+	for (i = 0; i < g_mt.n_chunk; ++i) free(g_mt.chunk[i]);
+	free(g_mt.chunk); free(g_mt.rec); free(g_mt.len);
+	memset(&g_mt, 0, sizeof(g_mt));
+}
+
+typedef struct { bam_pair_t *recs; zmq_msg_t *msgs; size_t base; } codec_ctx_t;
+static void decode_one(size_t i, void *ctx)
+{
+	codec_ctx_t *c = (codec_ctx_t *)ctx;
+	zmq_msg_t m;
+	zmq_msg_init_data(&m, g_mt.rec[c->base + i], g_mt.len[c->base + i], 0, 0);
+	pair_init_from_msg(&c->recs[i], &m);
+	zmq_msg_close(&m);
+}
+
+/* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file), then destroyed.  Serial on purpose:
+ * encode and destroy are malloc/free of blocks other threads allocated, and spreading them over threads is slower (measured:
+ * 0.29 s per 300 k records on one thread, 0.74 s on eight) */
+static void store_records(gzFile temporary, bam_pair_t *recs, size_t n)
+{
+	size_t i;
+	for (i = 0; i < n; ++i) {
+		zmq_msg_t m;
+		uint32_t len;
+		msg_init_from_pair(&m, &recs[i]);
+		len = (uint32_t)zmq_msg_size(&m);
+		if (!memtemp_put(zmq_msg_data(&m), len)) { /* pair_print_custom's two writes (bam2bam.c:1104-1105) */
+			if (gzwrite(temporary, &len, sizeof(len)) != (int)sizeof(len) || gzwrite(temporary, zmq_msg_data(&m), len) != (int)len) {
+				fprintf(stderr, "[bwa_gpu_batch] error writing temporary file\n");
+				exit(1);
+			}
+		}
+		zmq_msg_close(&m);
+		bam_destroy_pair(&recs[i]);
+	}
+}
+
+/* pass 2: up to B records, the ones kept in memory first */
+static size_t load_records(gzFile temporary, bam_pair_t *recs, size_t B, long *tot_seqs)
+{
+	size_t n = 0, i;
+	if (g_mt.rd < g_mt.n_rec) {
+		codec_ctx_t c = {recs, 0, g_mt.rd};
+		n = g_mt.n_rec - g_mt.rd < B ? g_mt.n_rec - g_mt.rd : B;
+		parallel_for(n, 1024, decode_one, &c);
+		g_mt.rd += n;
+		for (i = 0; i < n; ++i) *tot_seqs += recs[i].kind;
+	}
+	while (n < B) {
+		const int rc = read_pair_custom(temporary, &recs[n]);
+		if (rc < 0) { fprintf(stderr, "[bwa_gpu_batch] error reading intermediate file\n"); exit(1); }
+		if (rc == 0) break;
+		*tot_seqs += recs[n].kind;
+		++n;
+	}
+	return n;
+}
+
+/* ------------------------------------------------------------------ BAM output: BGZF blocks deflated on the host threads
+ * pair_print_bam -> bwa_print_bam1 -> bgzf_write (bam2bam.c:304-321, 908-924; bgzf.c:594-623) deflates one 64 KB block at a
+ * time on the calling thread.  Here the batch's records are laid out as the same byte stream, cut into BGZF blocks, the
+ * blocks are deflated in parallel (same level, same header and footer as deflate_block, bgzf.c:265-340) and written in order
+ * to the BGZF handle's own FILE.  The decompressed stream -- what any BAM reader sees -- is identical; block boundaries are
+ * not (the reference cuts at 65536 bytes of input, this writer at 65280 so that a block always fits). */
+#define OB_IN 65280
+#define OB_OUT 65536
+typedef struct { bam_pair_t *recs; size_t *off; uint8_t *ubuf; size_t total; uint8_t *cbuf; int *clen; int level; int failed; } ob_ctx_t;
+
+static size_t rec_bytes(const bam_pair_t *p) /* pair_print_bam's filter and bwa_print_bam1's record size */
+{
+	size_t n = 0;
+	int i;
+	if (g_only_aligned)
+		for (i = 0; i != (int)p->kind; ++i)
+			if (p->bam_rec[i].core.flag & SAM_FSU) return 0;
+	for (i = 0; i != (int)p->kind; ++i) n += 4 + sizeof(bam1_core_t) + (size_t)p->bam_rec[i].data_len;
+	return n;
+}
+
+static void ob_fill_one(size_t i, void *ctx)
+{
+	ob_ctx_t *c = (ob_ctx_t *)ctx;
+	const bam_pair_t *p = &c->recs[i];
+	uint8_t *q = c->ubuf + c->off[i];
+	int j;
+	if (c->off[i + 1] == c->off[i]) return;
+	for (j = 0; j != (int)p->kind; ++j) { /* bwa_print_bam1 (bam2bam.c:304-321) */
+		const bam1_t *b = &p->bam_rec[j];
+		uint32_t w[9];
+		w[0] = (uint32_t)(sizeof(bam1_core_t) + b->data_len);
+		w[1] = (uint32_t)b->core.tid; w[2] = (uint32_t)b->core.pos;
+		w[3] = (uint32_t)((int)b->core.bin << 16 | (int)b->core.qual << 8 | (int)b->core.l_qname);
+		w[4] = (uint32_t)((int)b->core.flag << 16 | (int)b->core.n_cigar);
+		w[5] = (uint32_t)b->core.l_qseq; w[6] = (uint32_t)b->core.mtid; w[7] = (uint32_t)b->core.mpos; w[8] = (uint32_t)b->core.isize;
+		memcpy(q, w, 36); q += 36;
+		memcpy(q, b->data, (size_t)b->data_len); q += b->data_len;
+	}
+}
+
+static void ob_deflate_one(size_t k, void *ctx)
+{
+	ob_ctx_t *c = (ob_ctx_t *)ctx;
+	const uint8_t *in = c->ubuf + k * OB_IN;
+	const int in_len = (int)(c->total - k * OB_IN < OB_IN ? c->total - k * OB_IN : OB_IN);
+	uint8_t *out = c->cbuf + k * OB_OUT;
+	static const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 0, 0}; /* bgzf.c:274-291 */
+	z_stream zs;
+	uint32_t crc, len;
+	memcpy(out, hdr, 18);
+	memset(&zs, 0, sizeof(zs));
+	zs.next_in = (Bytef *)in; zs.avail_in = (uInt)in_len;
+	zs.next_out = out + 18; zs.avail_out = OB_OUT - 18 - 8;
+	if (deflateInit2(&zs, c->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK || deflate(&zs, Z_FINISH) != Z_STREAM_END) { c->failed = 1; return; }
+	deflateEnd(&zs);
+	len = (uint32_t)zs.total_out + 18 + 8;
+	out[16] = (uint8_t)((len - 1) & 0xff); out[17] = (uint8_t)((len - 1) >> 8);
+	crc = (uint32_t)crc32(crc32(0L, 0, 0), in, (uInt)in_len);
+	memcpy(out + 18 + zs.total_out, &crc, 4);
+	memcpy(out + 18 + zs.total_out + 4, &in_len, 4);
+	c->clen[k] = (int)len;
+}
+
+static void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n)
+{
+	static size_t *off; static size_t m_off;
+	static uint8_t *ubuf, *cbuf; static size_t m_ubuf, m_cbuf;
+	static int *clen; static size_t m_clen;
+	ob_ctx_t c;
+	size_t i, nblk;
+	if (n + 1 > m_off) { m_off = n + 1; off = (size_t *)realloc(off, m_off * sizeof(*off)); }
+	off[0] = 0;
+	for (i = 0; i < n; ++i) off[i + 1] = off[i] + rec_bytes(&recs[i]);
+	memset(&c, 0, sizeof(c));
+	c.recs = recs; c.off = off; c.total = off[n]; c.level = output->compress_level;
+	if (c.total) {
+		if (bgzf_flush(output) != 0) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); } /* what bgzf_write buffered so far (the header) */
+		nblk = (c.total + OB_IN - 1) / OB_IN;
+		if (c.total > m_ubuf) { m_ubuf = c.total + c.total / 4; ubuf = (uint8_t *)realloc(ubuf, m_ubuf); }
+		if (nblk * OB_OUT > m_cbuf) { m_cbuf = nblk * OB_OUT + (nblk / 4) * OB_OUT; cbuf = (uint8_t *)realloc(cbuf, m_cbuf); }
+		if (nblk > m_clen) { m_clen = nblk + nblk / 4; clen = (int *)realloc(clen, m_clen * sizeof(int)); }
+		c.ubuf = ubuf; c.cbuf = cbuf; c.clen = clen;
+		parallel_for(n, 2048, ob_fill_one, &c);
+		parallel_for(nblk, 4, ob_deflate_one, &c);
+		if (c.failed) { fprintf(stderr, "[bwa_gpu_batch] deflate failed\n"); exit(1); }
+		for (i = 0; i < nblk; ++i) {
+			if (fwrite(cbuf + i * OB_OUT, 1, (size_t)clen[i], output->file) != (size_t)clen[i]) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
+			output->block_address += clen[i];
+		}
+	}
+	for (i = 0; i < n; ++i) bam_destroy_pair(&recs[i]);
+}
+
 /* ------------------------------------------------------------------ pass 1 */
 static void gpu_align(int m, bwa_seq_t *flat)
 {
@@ -317,6 +578,14 @@ static void gpu_align(int m, bwa_seq_t *flat)
 
 static int is_mapped(const bwa_seq_t *p) { return p->type == BWA_TYPE_UNIQUE || p->type == BWA_TYPE_REPEAT; }
 
+static void to_seq_one(size_t i, void *ctx) /* bam1_to_seq of aln_singleton / aln_pair (bam2bam.c:615, 674-675) */
+{
+	bam_pair_t *r = (bam_pair_t *)ctx + i;
+	int j;
+	if (r->phase != pristine || !unique_rec(r)) return;
+	for (j = 0; j != (int)r->kind; ++j) bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
+}
+
 /* aln_* + posn_* (bam2bam.c:608-703) for records [0, n): what sequential_loop_pass1 and a worker thread do to a
  * pristine record, with the two hot calls hoisted out of the per-record loop.  `flat` holds >= 2 n elements. */
 static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq, double *t_host)
@@ -325,14 +594,12 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
 	int m = 0, j;
 	double t1 = now();
 	/* aln_singleton / aln_pair (bam2bam.c:608-620, 660-681) without the search ... */
+	parallel_for(n, 2048, to_seq_one, recs);
 	for (i = 0; i < n; ++i) {
 		bam_pair_t *r = &recs[i];
 		if (r->phase != pristine) continue;
 		if (unique_rec(r))
-			for (j = 0; j != (int)r->kind; ++j) {
-				bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
-				flat[m++] = r->bwa_seq[j];
-			}
+			for (j = 0; j != (int)r->kind; ++j) flat[m++] = r->bwa_seq[j];
 	}
 	*t_toseq += now() - t1;
 	/* ... which is ONE device call for the batch */
@@ -390,31 +657,52 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
 	*t_host += now() - t1;
 }
 
+/* The input BAM is read (inflate + parse, one thread: bamlite is a sequential gzread) while the previous batch is processed */
+typedef struct { bwa_seqio_t *ks; bam_pair_t *recs; size_t B, n; long seqs; double secs; } reader_t;
+static void *read_batch(void *arg)
+{
+	reader_t *r = (reader_t *)arg;
+	const double t = now();
+	r->n = 0; r->seqs = 0;
+	while (r->n < r->B) {
+		const int rc = read_bam_pair(r->ks, &r->recs[r->n], g_broken_input, g_drop_aligned);
+		if (rc < 0) {
+			fprintf(stderr, "[sequential_loop_pass1] error reading input BAM%s\n", rc == -2 ? " (lone mate)" : "");
+			exit(1);
+		}
+		if (rc == 0) break;
+		r->seqs += r->recs[r->n].kind;
+		++r->n;
+	}
+	r->secs = now() - t;
+	return 0;
+}
+
 void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_infos) *iinfos)
 {
 	const size_t B = batch_records();
 	const double t0 = now();
-	double t_read = 0, t_host = 0, t_write = 0, t_toseq = 0, t1;
-	bam_pair_t *recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
+	double t_read = 0, t_host = 0, t_write = 0, t_toseq = 0, t_wait = 0, t1;
+	bam_pair_t *buf[2] = {(bam_pair_t *)calloc(B, sizeof(bam_pair_t)), (bam_pair_t *)calloc(B, sizeof(bam_pair_t))};
 	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
 	long tot_seqs = 0;
-	ensure_gpu();
+	pthread_t init_th, read_th;
+	reader_t rd[2];
+	int cur = 0;
+	/* device context + index upload (seconds) overlap the reading of the first batch */
+	pthread_create(&init_th, 0, ensure_gpu_thread, 0);
+	g_mt.cap = memtemp_cap();
+	rd[0].ks = rd[1].ks = ks; rd[0].B = rd[1].B = B; rd[0].recs = buf[0]; rd[1].recs = buf[1];
+	read_batch(&rd[0]);
+	pthread_join(init_th, 0);
 	for (;;) {
-		size_t n = 0, i;
-		int rc;
-		t1 = now();
-		while (n < B) {
-			rc = read_bam_pair(ks, &recs[n], g_broken_input, g_drop_aligned);
-			if (rc < 0) {
-				fprintf(stderr, "[%s] error reading input BAM%s\n", __func__, rc == -2 ? " (lone mate)" : "");
-				exit(1);
-			}
-			if (rc == 0) break;
-			tot_seqs += recs[n].kind;
-			++n;
-		}
-		t_read += now() - t1;
+		bam_pair_t *recs = rd[cur].recs;
+		const size_t n = rd[cur].n;
+		size_t i;
+		t_read += rd[cur].secs;
 		if (n == 0) break;
+		tot_seqs += rd[cur].seqs;
+		pthread_create(&read_th, 0, read_batch, &rd[cur ^ 1]); /* the next batch, meanwhile */
 
 		align_position_range(recs, n, flat, &t_toseq, &t_host);
 		t1 = now();
@@ -422,16 +710,19 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 			if (unique_rec(&recs[i])) improve_isize_est(iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
 		t_host += now() - t1;
 		t1 = now();
-		for (i = 0; i < n; ++i) {
-			pair_print_custom(temporary, &recs[i]);
-			bam_destroy_pair(&recs[i]);
-		}
+		store_records(temporary, recs, n);
 		t_write += now() - t1;
 		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
+		t1 = now();
+		pthread_join(read_th, 0);
+		t_wait += now() - t1;
+		cur ^= 1;
 	}
-	free(recs); free(flat);
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f)\n",
-	        __func__, tot_seqs, now() - t0, t_read, t_toseq, t_host, g_t_aln + g_t_sa, t_write);
+	free(buf[0]); free(buf[1]); free(flat);
+	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, g_mt.n_rec, g_mt.bytes / 1048576.0,
+	        g_mt.spilled ? ", the rest in the temporary file" : "");
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (read %.2f of which %.2f not hidden behind the previous batch, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f)\n",
+	        __func__, tot_seqs, now() - t0, t_read, t_wait + rd[0].secs, t_toseq, t_host, g_t_aln + g_t_sa, t_write);
 	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
 }
 
@@ -466,6 +757,35 @@ static int wants_pairing(const bam_pair_t *r) /* bam2bam.c:726-735 */
 static double g_t_stageA, g_t_stageB, g_t_stageC, g_t_stageD;
 static int is_pair_job(const bam_pair_t *r) { return r->kind == proper_pair && r->phase == positioned && unique_rec(r); }
 
+static void pair_to_seq_one(size_t i, void *ctx)
+{
+	bam_pair_t *r = (bam_pair_t *)ctx + i;
+	int j;
+	if (!is_pair_job(r)) return;
+	for (j = 0; j < 2; ++j)
+		if (!r->bwa_seq[j].seq) bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
+}
+
+static void finish_tail_one(size_t i, void *ctx)
+{
+	bam_pair_t *r = (bam_pair_t *)ctx + i;
+	if (is_pair_job(r)) {
+		bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
+		bwa_refine_gapped(g_bns, 1, &r->bwa_seq[1], g_pac, 0);
+		bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
+		bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
+		bwa_free_read_seq1(&r->bwa_seq[1]);
+		bwa_free_read_seq1(&r->bwa_seq[0]);
+	} else if (r->kind == singleton && r->phase == positioned && unique_rec(r)) {
+		bwa_seq_t *p = &r->bwa_seq[0];
+		if (!p->seq) bam1_to_seq(&r->bam_rec[0], p, 1, g_gap->trim_qual);
+		bwa_refine_gapped(g_bns, 1, p, g_pac, 0);
+		bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
+		bwa_free_read_seq1(p);
+	}
+	if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
+}
+
 /* finish_pair (bam2bam.c:705-811) for records [lo, hi), phase by phase */
 static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_infos) *iinfos, uint64_t n_tot[2], uint64_t n_mapped[2],
                          kh_64_t *my_hash)
@@ -476,6 +796,7 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 	bwtint_t l;
 
 	double t1 = now();
+	parallel_for(hi - lo, 1024, pair_to_seq_one, recs + lo); /* finish_pair's bam1_to_seq (bam2bam.c:717-718) */
 	/* A: every SA row whose coordinate pairing will want (bam2bam.c:736-765), in the reference's visiting order */
 	g_q.n = 0; fresh.n = 0;
 	for (i = lo; i < hi; ++i) {
@@ -602,26 +923,20 @@ static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_i
 	}
 
 	g_t_stageC += now() - t1; t1 = now();
-	/* D: the reference's own per-record tail (bam2bam.c:643-658, 798-810) */
-	for (i = lo; i < hi; ++i) {
-		bam_pair_t *r = &recs[i];
-		if (is_pair_job(r)) {
-			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
-			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[1], g_pac, 0);
-			bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
-			bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
-			bwa_free_read_seq1(&r->bwa_seq[1]);
-			bwa_free_read_seq1(&r->bwa_seq[0]);
-		} else if (r->kind == singleton && r->phase == positioned && unique_rec(r)) {
-			bwa_seq_t *p = &r->bwa_seq[0];
-			if (!p->seq) bam1_to_seq(&r->bam_rec[0], p, 1, g_gap->trim_qual);
-			bwa_refine_gapped(g_bns, 1, p, g_pac, 0);
-			bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
-			bwa_free_read_seq1(p);
-		}
-		if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
-	}
+	/* D: the reference's own per-record tail (bam2bam.c:643-658, 798-810), records spread over the host threads */
+	parallel_for(hi - lo, 512, finish_tail_one, recs + lo);
 	g_t_stageD += now() - t1;
+}
+
+/* A batch's BAM records are laid out, deflated and written while the next batch is loaded and finished */
+typedef struct { BGZF *output; bam_pair_t *recs; size_t n; double secs; } writer_t;
+static void *write_batch(void *arg)
+{
+	writer_t *w = (writer_t *)arg;
+	const double t = now();
+	write_records_bam(w->output, w->recs, w->n);
+	w->secs = now() - t;
+	return 0;
 }
 
 void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) *iinfos)
@@ -629,24 +944,21 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	const size_t B = batch_records();
 	const long long max_q = getenv("BWAGPU_BATCH_SA") ? atoll(getenv("BWAGPU_BATCH_SA")) : 1ll << 25; /* SA rows per device call */
 	const double t0 = now();
-	double t_read = 0, t_fin = 0, t_write = 0, t1;
+	double t_read = 0, t_fin = 0, t_write = 0, t_wait = 0, t1;
 	uint64_t n_tot[2] = {0, 0}, n_mapped[2] = {0, 0};
-	bam_pair_t *recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
+	bam_pair_t *buf[2] = {(bam_pair_t *)calloc(B, sizeof(bam_pair_t)), (bam_pair_t *)calloc(B, sizeof(bam_pair_t))};
 	kh_64_t *my_hash = kh_init(64);
 	khiter_t it;
 	long tot_seqs = 0;
+	pthread_t write_th;
+	writer_t wr;
+	int cur = 0, writing = 0;
 	ensure_gpu();
 	for (;;) {
-		size_t n = 0, i, lo;
-		int rc;
+		bam_pair_t *recs = buf[cur];
+		size_t n, lo;
 		t1 = now();
-		while (n < B) {
-			rc = read_pair_custom(temporary, &recs[n]);
-			if (rc < 0) { fprintf(stderr, "[%s] error reading intermediate file\n", __func__); exit(1); }
-			if (rc == 0) break;
-			tot_seqs += recs[n].kind;
-			++n;
-		}
+		n = load_records(temporary, recs, B, &tot_seqs);
 		t_read += now() - t1;
 		if (n == 0) break;
 		t1 = now();
@@ -667,25 +979,30 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		}
 		t_fin += now() - t1;
 		t1 = now();
-		for (i = 0; i < n; ++i) {
-			pair_print_bam(output, &recs[i]);
-			bam_destroy_pair(&recs[i]);
-		}
-		t_write += now() - t1;
+		if (writing) { pthread_join(write_th, 0); t_write += wr.secs; }
+		t_wait += now() - t1;
+		wr.output = output; wr.recs = recs; wr.n = n;
+		pthread_create(&write_th, 0, write_batch, &wr);
+		writing = 1;
+		cur ^= 1;
 		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
 	}
+	t1 = now();
+	if (writing) { pthread_join(write_th, 0); t_write += wr.secs; }
+	t_wait += now() - t1;
 	fprintf(stderr, "[%s] finish = enumerate %.2f + pairing/XA %.2f + mate rescue (host side, both runs) %.2f + refine/update %.2f + device calls\n",
 	        __func__, g_t_stageA, g_t_stageB, g_t_stageC, g_t_stageD);
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (temp read %.2f, finish %.2f, BAM write %.2f)\n"
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (temp read %.2f, finish %.2f, BAM write %.2f of which %.2f not hidden behind the next batch)\n"
 	                "[%s] finished cleanly, shutting down.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d singletons are mated.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d discordant pairs are fixed.\n",
-	        __func__, tot_seqs, now() - t0, t_read, t_fin, t_write, __func__, (long long)n_mapped[1], (long long)n_tot[1], SW_MIN_MAPQ,
+	        __func__, tot_seqs, now() - t0, t_read, t_fin, t_write, t_wait, __func__, (long long)n_mapped[1], (long long)n_tot[1], SW_MIN_MAPQ,
 	        (long long)n_mapped[0], (long long)n_tot[0], SW_MIN_MAPQ);
 	for (it = kh_begin(my_hash); it != kh_end(my_hash); ++it)
 		if (kh_exist(my_hash, it)) free(kh_val(my_hash, it).a);
 	kh_destroy(64, my_hash);
-	free(recs);
+	free(buf[0]); free(buf[1]);
+	memtemp_free();
 }
 
 /* ------------------------------------------------------------------ 0MQ worker
@@ -708,7 +1025,6 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
  * in record order in both passes and the BAM equals `bam2bam -t 1`'s (tests/test_batched_worker.py), which the
  * reference's own `-t N` does not guarantee.
  */
-#include "zmq.h"
 
 void msg_init_from_pair(zmq_msg_t *m, bam_pair_t *p);
 void pair_init_from_msg(bam_pair_t *p, zmq_msg_t *m);

@@ -129,6 +129,14 @@ def pe_case(genome, mode):
     fixed = [l for l in cpu_log.splitlines() if "discordant pairs are fixed" in l][-1]
     assert fixed in log                              # same "[bwa_paired_sw] N out of M ... fixed" line
     assert int(fixed.split()[1]) >= 40               # and the accept-and-rewrite branch of mate rescue really ran
+    # the intermediate records partly in memory, partly spilled to the reference's temporary file; three host threads
+    log = run_bam2bam(fa, bam, str(d / f"pe_{mode}_spill.bam"), mode,
+                      env_extra={"BWAGPU_BATCH_RECORDS": "600", "BWAGPU_MEMTEMP_BYTES": "400000", "BWAGPU_SHIM_THREADS": "3"})
+    compare(str(d / "pe_cpu.bam"), str(d / f"pe_{mode}_spill.bam"))
+    assert "the rest in the temporary file" in log
+    # and everything through the temporary file, one host thread
+    run_bam2bam(fa, bam, str(d / f"pe_{mode}_file.bam"), mode, env_extra={"BWAGPU_MEMTEMP_BYTES": "0", "BWAGPU_SHIM_THREADS": "1"})
+    compare(str(d / "pe_cpu.bam"), str(d / f"pe_{mode}_file.bam"))
 
 
 def adna_case(genome, mode):

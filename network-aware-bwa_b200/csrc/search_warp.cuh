@@ -171,7 +171,9 @@ __device__ __forceinline__ int warp_max(int v)
 template <bool STDMODE, bool WSTATS>
 __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(const Batch B)
 {
+#ifndef BWAGPU_WARP_EMU // tests/host_emu/warp_emu.cpp supplies the array
 	extern __shared__ __align__(16) uint32_t wk_smem[];
+#endif
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	uint32_t *const cnt = wk_smem + (size_t)wib * WK_WORDS_PER_WARP; // entries per bucket

@@ -38,6 +38,8 @@ template <typename T> static inline T atomicCAS(T *p, T cmp, T val) { T o = *p; 
 static inline void __threadfence() {}
 template <typename T> static inline void __stcs(T *p, T v) { *p = v; }
 template <typename T> static inline T __ldcs(const T *p) { return *p; }
+#ifndef BWAGPU_WARP_EMU // warp_emu.cpp runs 32 real lanes and supplies real collectives
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline bool __all_sync(unsigned, bool p) { return p; }
 static inline void __syncwarp() {}
+#endif

@@ -144,6 +144,54 @@ def emu_aln(h, reads, opt, cap1=1024, aln_cap1=64, n_slots=3, pool_chunks=64):
     return n_aln, max_entries, aln_off, aln, stats
 
 
+_wemu = None
+
+
+def wemu():
+    """tests/host_emu/warp_emu.cpp: the body of k_search_warp on a 32-lane warp of coroutines."""
+    global _wemu
+    if _wemu is None:
+        so = os.path.join(EMU_DIR, "libwarp_emu.so")
+        srcs = [os.path.join(EMU_DIR, "warp_emu.cpp"), os.path.join(EMU_DIR, "host_emu_shim.h")] + [
+            os.path.join(ROOT, "network-aware-bwa_b200", "csrc", f) for f in ("search_warp.cuh", "kernels.cuh", "fmindex.cuh", "hostprep.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I", EMU_DIR, "-o", so, srcs[0]], check=True)
+        E = C.CDLL(so)
+        E.wemu_last_error.restype = C.c_char_p
+        E.wemu_load_index.argtypes = [C.POINTER(C.POINTER(abi.bwt_t))]
+        E.wemu_load_index.restype = C.c_void_p
+        E.wemu_free_index.argtypes = [C.c_void_p]
+        E.wemu_aln_flat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_int)]
+        E.wemu_free.argtypes = [C.c_void_p]
+        _wemu = E
+    return _wemu
+
+
+def wemu_aln(h, reads, opt, pool_chunks=4096):
+    """-> (n_aln, max_entries, aln_off, aln, reads that found the chunk pool dry)"""
+    E = wemu()
+    n = reads.n
+    bases = np.ascontiguousarray(reads.bases, dtype=np.uint8)
+    offs = np.ascontiguousarray(reads.offs, dtype=np.int64)
+    n_aln = np.empty(n, dtype=np.int32)
+    max_entries = np.zeros(n, dtype=np.int32)
+    aln_off = np.empty(n + 1, dtype=np.int64)
+    pool = C.c_void_p()
+    dry = C.c_int(0)
+    rc = E.wemu_aln_flat(h, n, bases.ctypes.data, offs.ctypes.data, C.byref(opt), n_aln.ctypes.data, max_entries.ctypes.data,
+                         aln_off.ctypes.data, C.byref(pool), pool_chunks, C.byref(dry))
+    if rc:
+        raise RuntimeError(E.wemu_last_error().decode())
+    tot = int(aln_off[n])
+    aln = np.empty(tot, dtype=abi.ALN_DTYPE)
+    if tot:
+        buf = (C.c_char * (16 * tot)).from_address(pool.value)
+        aln[:] = np.frombuffer(buf, dtype=abi.ALN_DTYPE, count=tot)
+    E.wemu_free(pool)
+    return n_aln, max_entries, aln_off, aln, dry.value
+
+
 def compare_aln(a, b, label=""):
     """a, b = (n_aln, max_entries, aln_off, aln).  Returns list of mismatch strings."""
     errs = []

@@ -92,3 +92,61 @@ def test_search_logic_matches_reference_live(small_index, emu_index):
     want = R.ref_aln(ridx, reads, opt, threads=4)
     got = R.emu_aln(h, reads, opt)
     assert R.compare_aln(want, got, "live") == []
+
+
+# ---------------------------------------------------------------- k_search_warp (csrc/search_warp.cuh) on an emulated 32-lane warp
+def _prefix(reads, want, n):
+    r = R.bwa.simulate.Reads(reads.bases[:reads.offs[n]], reads.offs[:n + 1], None, None)
+    na, me, off, aln = want
+    return r, (na[:n], me[:n], off[:n + 1], aln[:off[n]])
+
+
+@pytest.fixture(scope="module")
+def wemu_index(small_index):
+    T, idx = small_index
+    ridx = R.RefIndex(idx)
+    h = R.wemu().wemu_load_index(ridx.arr)
+    yield h, ridx
+    R.wemu().wemu_free_index(h)
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_warp_search_logic_matches_golden(golden, wemu_index, name):
+    """The warp-per-read kernel body, lanes as coroutines with real shuffles / ballots (tests/host_emu/warp_emu.cpp): chains per
+    lane, count / scan / store passes, rollback after a hit, chunked buckets -- same bytes as the reference."""
+    h, _ = wemu_index
+    reads, opt, want = golden_case(golden, name)
+    r, w = _prefix(reads, want, 60 if name == "nonstop_loggap" else 150)
+    got = R.wemu_aln(h, r, opt)
+    assert got[4] == 0
+    assert R.compare_aln(w, got, "warp " + name) == []
+
+
+def test_warp_search_logic_pool_dry(golden, wemu_index):
+    """A chunk pool too small for every read: the reads that find it dry are flagged (n_aln = -1, retried by the guaranteed pass
+    in the library); the others are still exact."""
+    h, _ = wemu_index
+    reads, opt, want = golden_case(golden, "adna")
+    r, w = _prefix(reads, want, 150)
+    got = R.wemu_aln(h, r, opt, pool_chunks=12)
+    assert 0 < got[4] < 150 and int((got[0] < 0).sum()) == got[4]
+    ok = got[0] >= 0
+    assert np.array_equal(got[0][ok], w[0][ok]) and np.array_equal(got[1][ok], w[1][ok])
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("optkw,simkw", [
+    (dict(seed_len=1024, fnr=0.01, max_gapo=2), dict(adna=True, sub_rate=0.06)),   # deep searches
+    (dict(s_mm=4, s_gapo=9, s_gape=4, max_gapo=2), dict(sub_rate=0.04)),           # two penalties equal: shared target bucket
+    (dict(s_mm=3, s_gapo=11, s_gape=0, max_gapo=1), dict(sub_rate=0.03)),          # a zero penalty: one-lane rounds
+    (dict(seed_len=1024, fnr=0.01, max_gapo=2, max_entries=3000), dict(adna=True, sub_rate=0.05)),  # the max_entries stop
+])
+def test_warp_search_logic_matches_reference_live(small_index, wemu_index, optkw, simkw):
+    T, _ = small_index
+    h, ridx = wemu_index
+    reads = R.bwa.simulate.simulate_reads(T, 120, (30, 50), seed=321, **simkw)
+    opt = abi.default_gap_opt(**optkw)
+    want = R.ref_aln(ridx, reads, opt, threads=4)
+    got = R.wemu_aln(h, reads, opt)
+    assert got[4] == 0
+    assert R.compare_aln(want, got, "warp live") == []

@@ -90,13 +90,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ workload
-def make_workload(bwa, n_reads: int, device: str, seed: int, genome_bp: int):
+def make_workload(bwa, n_reads: int, device: str, seed: int, genome_bp: int, read_len: int = READ_LEN):
     t0 = time.time()
     T = bwa.simulate.make_genome(genome_bp, seed=1, repeat_frac=0.01)
     t1 = time.time()
     idx = bwa.index.build_index(T, device=device)
     t2 = time.time()
-    reads = bwa.simulate.simulate_reads(T, n_reads, READ_LEN, seed=seed, device=device)
+    reads = bwa.simulate.simulate_reads(T, n_reads, read_len, seed=seed, device=device)
     t3 = time.time()
     log(f"[bench] genome {t1 - t0:.1f}s, index ({device}) {t2 - t1:.1f}s, {n_reads} reads {t3 - t2:.1f}s")
     return T, idx, reads
@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (default: the full 10M-read workload; reference arm: bounded sample)")
     ap.add_argument("--genome-bp", type=int, default=GENOME_BP)
+    ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (default 76: configs[1]; 100 = the paired-end shape of configs[2]/[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -185,7 +186,7 @@ def main():
             return 0
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         n_pool = args.reads or 400_000
-        T, idx, reads = make_workload(bwa, n_pool, dev, seed=1000, genome_bp=args.genome_bp)
+        T, idx, reads = make_workload(bwa, n_pool, dev, seed=1000, genome_bp=args.genome_bp, read_len=args.read_len)
         target = 20.0
         rates, ns, total_t = [], [], 0.0
         for s in range(args.warmup + args.steps):
@@ -214,7 +215,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_reads = args.reads or READS_TOTAL
-    T, idx, reads = make_workload(bwa, n_reads, f"cuda:{local_rank}", seed=1000 + rank, genome_bp=args.genome_bp)
+    T, idx, reads = make_workload(bwa, n_reads, f"cuda:{local_rank}", seed=1000 + rank, genome_bp=args.genome_bp, read_len=args.read_len)
     torch.cuda.empty_cache()
     api.init([local_rank])
     api.load_index(idx)
@@ -407,7 +408,9 @@ def main():
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": n_reads, "read_len": READ_LEN, "genome_bp": args.genome_bp,
+        "config": {"workload": WORKLOAD if (args.read_len, args.genome_bp) == (READ_LEN, GENOME_BP) else
+                   f"SE {n_reads} x {args.read_len}bp, -n 0.04 -o 1, synthetic {args.genome_bp} bp genome (non-default shape)",
+                   "reads_per_step_per_gpu": n_reads, "read_len": args.read_len, "genome_bp": args.genome_bp,
                    "parallelism": f"replica x{world}, reads sharded, no collective",
                    "l2": "inputs larger than L2 (index 100 MB + width arena and search stacks of several GB per step); same batch every step",
                    "timed": "CUDA events on the library stream around K2+K3(+tiers)+compaction",

@@ -586,14 +586,14 @@ static void to_seq_one(size_t i, void *ctx) /* bam1_to_seq of aln_singleton / al
 	for (j = 0; j != (int)r->kind; ++j) bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
 }
 
-/* aln_* + posn_* (bam2bam.c:608-703) for records [0, n): what sequential_loop_pass1 and a worker thread do to a
- * pristine record, with the two hot calls hoisted out of the per-record loop.  `flat` holds >= 2 n elements. */
-static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq, double *t_host)
+/* aln_* (bam2bam.c:608-620, 660-681) for records [0, n): what sequential_loop_pass1 and a worker thread do first to a pristine
+ * record, with the search hoisted out of the per-record loop.  `flat` holds >= 2 n elements. */
+static void align_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq)
 {
 	size_t i;
 	int m = 0, j;
 	double t1 = now();
-	/* aln_singleton / aln_pair (bam2bam.c:608-620, 660-681) without the search ... */
+	/* aln_singleton / aln_pair without the search ... */
 	parallel_for(n, 2048, to_seq_one, recs);
 	for (i = 0; i < n; ++i) {
 		bam_pair_t *r = &recs[i];
@@ -612,9 +612,16 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
 			for (j = 0; j != (int)r->kind; ++j) r->bwa_seq[j] = flat[m++];
 		r->phase = aligned;
 	}
+	*t_toseq += now() - t1;
+}
 
-	/* posn_singleton / posn_pair (bam2bam.c:622-641, 683-703): primary-hit selection on the host, in record
-	 * order (drand48), collecting the SA rows whose coordinates are wanted ... */
+/* posn_* (bam2bam.c:622-641, 683-703) for records [0, n): primary-hit selection on the host, in record order (drand48),
+ * one device call for the SA rows whose coordinates are wanted, then the reference's own bwa_cal_pac_pos_core fed from the answers */
+static void position_range(bam_pair_t *recs, size_t n, double *t_host)
+{
+	size_t i;
+	int j;
+	double t1 = now();
 	g_q.n = 0;
 	for (i = 0; i < n; ++i) {
 		bam_pair_t *r = &recs[i];
@@ -630,9 +637,7 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
 		}
 	}
 	*t_host += now() - t1;
-	/* ... one device call ... */
 	saq_run(&g_q);
-	/* ... and the reference's own bwa_cal_pac_pos_core (position + mapQ) fed from the answers */
 	t1 = now();
 	g_sa_replay = 1;
 	for (i = 0; i < n; ++i) {
@@ -657,72 +662,162 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
 	*t_host += now() - t1;
 }
 
-/* The input BAM is read (inflate + parse, one thread: bamlite is a sequential gzread) while the previous batch is processed */
-typedef struct { bwa_seqio_t *ks; bam_pair_t *recs; size_t B, n; long seqs; double secs; } reader_t;
-static void *read_batch(void *arg)
+static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq, double *t_host)
 {
-	reader_t *r = (reader_t *)arg;
-	const double t = now();
-	r->n = 0; r->seqs = 0;
-	while (r->n < r->B) {
-		const int rc = read_bam_pair(r->ks, &r->recs[r->n], g_broken_input, g_drop_aligned);
-		if (rc < 0) {
-			fprintf(stderr, "[sequential_loop_pass1] error reading input BAM%s\n", rc == -2 ? " (lone mate)" : "");
-			exit(1);
+	align_range(recs, n, flat, t_toseq);
+	position_range(recs, n, t_host);
+}
+
+/* Pass 1 as a pipeline of four stages, each on its own thread, batches handed on in order through a ring of slots:
+ *   read     read_bam_pair (inflate + parse; bamlite is a sequential gzread)
+ *   align    bam1_to_seq on the host threads + the search on the device            (the calling thread)
+ *   position bwa_aln2seq_core in record order (drand48), SA rows on the device, bwa_cal_pac_pos_core, improve_isize_est
+ *   store    the reference's record encoding into memory / its temporary file, bam_destroy_pair
+ * Every order-sensitive piece of state belongs to exactly one stage, and a stage sees the batches in input order, so the
+ * result is what the one-record-at-a-time loop (bam2bam.c:1143-1176) produces. */
+#define P1_SLOTS 4
+enum { SL_FREE = 0, SL_READ, SL_ALIGNED, SL_POSITIONED };
+typedef struct {
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	int state[P1_SLOTS];
+	bam_pair_t *recs[P1_SLOTS];
+	size_t n[P1_SLOTS];
+	long seqs[P1_SLOTS];
+	size_t B;
+	bwa_seqio_t *ks;
+	gzFile temporary;
+	khash_t(isize_infos) *iinfos;
+	double t0, t_read, t_host, t_write;
+	long tot_seqs;
+} pipe1_t;
+
+static void slot_wait(pipe1_t *P, int slot, int want)
+{
+	pthread_mutex_lock(&P->mu);
+	while (P->state[slot] != want) pthread_cond_wait(&P->cv, &P->mu);
+	pthread_mutex_unlock(&P->mu);
+}
+
+static void slot_set(pipe1_t *P, int slot, int st)
+{
+	pthread_mutex_lock(&P->mu);
+	P->state[slot] = st;
+	pthread_cond_broadcast(&P->cv);
+	pthread_mutex_unlock(&P->mu);
+}
+
+static void *stage_read(void *arg)
+{
+	pipe1_t *P = (pipe1_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P1_SLOTS);
+		bam_pair_t *recs = P->recs[slot];
+		size_t n = 0;
+		long seqs = 0;
+		double t;
+		slot_wait(P, slot, SL_FREE);
+		t = now();
+		while (n < P->B) {
+			const int rc = read_bam_pair(P->ks, &recs[n], g_broken_input, g_drop_aligned);
+			if (rc < 0) {
+				fprintf(stderr, "[sequential_loop_pass1] error reading input BAM%s\n", rc == -2 ? " (lone mate)" : "");
+				exit(1);
+			}
+			if (rc == 0) break;
+			seqs += recs[n].kind;
+			++n;
 		}
-		if (rc == 0) break;
-		r->seqs += r->recs[r->n].kind;
-		++r->n;
+		P->t_read += now() - t;
+		P->n[slot] = n; P->seqs[slot] = seqs;
+		slot_set(P, slot, SL_READ);
+		if (n == 0) break; /* an empty batch is the end marker; it travels through every stage */
 	}
-	r->secs = now() - t;
+	return 0;
+}
+
+static void *stage_position(void *arg)
+{
+	pipe1_t *P = (pipe1_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P1_SLOTS);
+		bam_pair_t *recs;
+		size_t n, i;
+		double t1;
+		slot_wait(P, slot, SL_ALIGNED);
+		recs = P->recs[slot]; n = P->n[slot];
+		if (n) {
+			position_range(recs, n, &P->t_host);
+			t1 = now();
+			for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
+				if (unique_rec(&recs[i])) improve_isize_est(P->iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
+			P->t_host += now() - t1;
+		}
+		slot_set(P, slot, SL_POSITIONED);
+		if (n == 0) break;
+	}
+	return 0;
+}
+
+static void *stage_store(void *arg)
+{
+	pipe1_t *P = (pipe1_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P1_SLOTS);
+		size_t n;
+		double t1;
+		slot_wait(P, slot, SL_POSITIONED);
+		n = P->n[slot];
+		if (n == 0) break;
+		t1 = now();
+		store_records(P->temporary, P->recs[slot], n);
+		P->t_write += now() - t1;
+		P->tot_seqs += P->seqs[slot];
+		fprintf(stderr, "[sequential_loop_pass1] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
+		slot_set(P, slot, SL_FREE);
+	}
 	return 0;
 }
 
 void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_infos) *iinfos)
 {
 	const size_t B = batch_records();
-	const double t0 = now();
-	double t_read = 0, t_host = 0, t_write = 0, t_toseq = 0, t_wait = 0, t1;
-	bam_pair_t *buf[2] = {(bam_pair_t *)calloc(B, sizeof(bam_pair_t)), (bam_pair_t *)calloc(B, sizeof(bam_pair_t))};
+	pipe1_t P;
+	double t_toseq = 0, t_init;
 	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
-	long tot_seqs = 0;
-	pthread_t init_th, read_th;
-	reader_t rd[2];
-	int cur = 0;
-	/* device context + index upload (seconds) overlap the reading of the first batch */
-	pthread_create(&init_th, 0, ensure_gpu_thread, 0);
+	pthread_t init_th, read_th, pos_th, store_th;
+	unsigned q;
+	int s;
+	memset(&P, 0, sizeof(P));
+	pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
+	P.B = B; P.ks = ks; P.temporary = temporary; P.iinfos = iinfos; P.t0 = now();
+	for (s = 0; s < P1_SLOTS; ++s) P.recs[s] = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
 	g_mt.cap = memtemp_cap();
-	rd[0].ks = rd[1].ks = ks; rd[0].B = rd[1].B = B; rd[0].recs = buf[0]; rd[1].recs = buf[1];
-	read_batch(&rd[0]);
+	/* device context + index upload (seconds) overlap the reading of the first batches */
+	pthread_create(&init_th, 0, ensure_gpu_thread, 0);
+	pthread_create(&read_th, 0, stage_read, &P);
+	pthread_create(&pos_th, 0, stage_position, &P);
+	pthread_create(&store_th, 0, stage_store, &P);
 	pthread_join(init_th, 0);
-	for (;;) {
-		bam_pair_t *recs = rd[cur].recs;
-		const size_t n = rd[cur].n;
-		size_t i;
-		t_read += rd[cur].secs;
-		if (n == 0) break;
-		tot_seqs += rd[cur].seqs;
-		pthread_create(&read_th, 0, read_batch, &rd[cur ^ 1]); /* the next batch, meanwhile */
-
-		align_position_range(recs, n, flat, &t_toseq, &t_host);
-		t1 = now();
-		for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
-			if (unique_rec(&recs[i])) improve_isize_est(iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
-		t_host += now() - t1;
-		t1 = now();
-		store_records(temporary, recs, n);
-		t_write += now() - t1;
-		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
-		t1 = now();
-		pthread_join(read_th, 0);
-		t_wait += now() - t1;
-		cur ^= 1;
+	t_init = now() - P.t0;
+	for (q = 0;; ++q) { /* the align stage */
+		const int slot = (int)(q % P1_SLOTS);
+		slot_wait(&P, slot, SL_READ);
+		if (P.n[slot]) align_range(P.recs[slot], P.n[slot], flat, &t_toseq);
+		slot_set(&P, slot, SL_ALIGNED);
+		if (P.n[slot] == 0) break;
 	}
-	free(buf[0]); free(buf[1]); free(flat);
+	pthread_join(read_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0);
+	for (s = 0; s < P1_SLOTS; ++s) free(P.recs[s]);
+	free(flat);
+	pthread_mutex_destroy(&P.mu); pthread_cond_destroy(&P.cv);
 	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, g_mt.n_rec, g_mt.bytes / 1048576.0,
 	        g_mt.spilled ? ", the rest in the temporary file" : "");
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (read %.2f of which %.2f not hidden behind the previous batch, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f)\n",
-	        __func__, tot_seqs, now() - t0, t_read, t_wait + rd[0].secs, t_toseq, t_host, g_t_aln + g_t_sa, t_write);
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each: device init %.2f, read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f)\n",
+	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, t_toseq, P.t_host, g_t_aln + g_t_sa, P.t_write);
 	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
 }
 

@@ -675,7 +675,7 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
  *   store    the reference's record encoding into memory / its temporary file, bam_destroy_pair
  * Every order-sensitive piece of state belongs to exactly one stage, and a stage sees the batches in input order, so the
  * result is what the one-record-at-a-time loop (bam2bam.c:1143-1176) produces. */
-#define P1_SLOTS 4
+#define P1_SLOTS 8 /* the reader may run this many batches ahead (it does while the device context is created) */
 enum { SL_FREE = 0, SL_READ, SL_ALIGNED, SL_POSITIONED };
 typedef struct {
 	pthread_mutex_t mu;

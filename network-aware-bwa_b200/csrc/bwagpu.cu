@@ -3,9 +3,9 @@
 // One Ctx per CUDA device (its own stream, scratch arenas, pinned staging).  A batch call
 // splits the reads into contiguous per-device ranges (index replicated, no collective:
 // SURVEY.md §8e), each range into chunks, and runs per chunk
-//     H2D -> K2 width -> K3 search (pass 0 on private arenas [-> pass 1 on the shared chunk pool ->
-//     pass 2 with guaranteed memory] for the reads whose search went deeper) -> scan + gather
-//     (read-ordered aln pool) -> D2H.
+//     H2D -> K2 width -> K3 search (pass 0: thread per read on private arenas [-> pass 1: warp per read
+//     on the shared chunk pool (search_warp.cuh) -> pass 2: thread per read with guaranteed memory] for
+//     the reads whose search went deeper) -> scan + gather (read-ordered aln pool) -> D2H.
 // There is no CPU fallback: without a usable device every entry point returns an error.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
@@ -372,11 +372,10 @@ extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; 
 // ------------------------------------------------------------------ device pipeline for one resident chunk
 static const int N_PASSES = 3;
 
-// Pass 0: private arenas only (BWAGPU_T1_CAP records per thread).  Pass 1 (optimistic, pooled): every resident thread has a small private arena (BWAGPU_T1_CAP records, shared by
-// the search stack and the read's hit list) and takes more from a shared pool of 1024-record chunks when a search goes deep; the pool is
-// bump-allocated within a launch, so it can run dry -- the reads it fails are retried from scratch in pass 1 (guaranteed): few enough threads
-// that each can own opt->max_entries + 16 records, which the search can never exceed (bwtgap.c:140
-// stops it first).
+// Pass 0: k_search, private arenas only (BWAGPU_T1_CAP records per thread).  Pass 1 (optimistic): k_search_warp, one warp per read, every
+// entry in 1024-record chunks of a pool shared by the launch (BWAGPU_WARP_PASS=0: the pooled thread-per-read instantiation of k_search
+// instead); the pool can run dry -- the reads it fails are retried from scratch in pass 2 (guaranteed): k_search with few enough threads
+// that each can own opt->max_entries + 16 records, which the search can never exceed (bwtgap.c:140 stops it first).
 typedef void (*search_fn)(const Batch);
 static search_fn search_kernel(bool stats, bool pooled, bool stdmode)
 {

@@ -194,6 +194,100 @@ static void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
 	for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
 }
 
+
+/* ------------------------------------------------------------------ input BAM: inflate on a side thread
+ * bamlite reads the input with gzread (bamlite.h:8-11), three small calls per record, on the thread that also parses
+ * and allocates the records; inflate is about half of that thread's time and it is the slowest stage of pass 1.  The
+ * first file opened with gzopen(.., "r") -- the input BAM (bwa_bam_open) -- gets a read-ahead thread that gzread()s it in
+ * 256 KB pieces into a ring; the interposed gzread serves bamlite's calls from the ring.  Every other gzFile (the
+ * temporary file) goes straight to zlib.  BWAGPU_READAHEAD=0 turns it off. */
+#define RA_CAP ((size_t)16 << 20)
+#define RA_PIECE ((size_t)256 << 10)
+typedef struct {
+	gzFile real;
+	pthread_t th;
+	uint8_t *ring;
+	volatile size_t head, tail; /* bytes produced / consumed so far */
+	volatile int eof, stop;
+} readahead_t;
+static readahead_t g_ra;
+
+static void *ra_main(void *arg)
+{
+	REAL(int, gzread, gzFile, voidp, unsigned);
+	uint8_t *piece = (uint8_t *)malloc(RA_PIECE);
+	(void)arg;
+	while (!g_ra.stop) {
+		int got, done = 0;
+		while (!g_ra.stop && RA_CAP - (g_ra.head - __atomic_load_n(&g_ra.tail, __ATOMIC_ACQUIRE)) < RA_PIECE) usleep(100);
+		if (g_ra.stop) break;
+		got = real_gzread(g_ra.real, piece, (unsigned)RA_PIECE);
+		if (got <= 0) break;
+		while (done < got) {
+			const size_t at = (g_ra.head + (size_t)done) % RA_CAP;
+			const size_t run = RA_CAP - at < (size_t)(got - done) ? RA_CAP - at : (size_t)(got - done);
+			memcpy(g_ra.ring + at, piece + done, run);
+			done += (int)run;
+		}
+		__atomic_store_n(&g_ra.head, g_ra.head + (size_t)got, __ATOMIC_RELEASE);
+	}
+	__atomic_store_n(&g_ra.eof, 1, __ATOMIC_RELEASE);
+	free(piece);
+	return 0;
+}
+
+gzFile gzopen(const char *path, const char *mode)
+{
+	REAL(gzFile, gzopen, const char *, const char *);
+	gzFile f = real_gzopen(path, mode);
+	const char *e = getenv("BWAGPU_READAHEAD");
+	if (f && !g_ra.real && mode && mode[0] == 'r' && !(e && atoi(e) == 0)) {
+		memset(&g_ra, 0, sizeof(g_ra));
+		g_ra.ring = (uint8_t *)malloc(RA_CAP);
+		if (g_ra.ring) {
+			g_ra.real = f;
+			pthread_create(&g_ra.th, 0, ra_main, 0);
+		}
+	}
+	return f;
+}
+
+int gzread(gzFile f, voidp buf, unsigned len)
+{
+	REAL(int, gzread, gzFile, voidp, unsigned);
+	unsigned done = 0;
+	if (!g_ra.real || f != g_ra.real) return real_gzread(f, buf, len);
+	while (done < len) {
+		size_t avail = __atomic_load_n(&g_ra.head, __ATOMIC_ACQUIRE) - g_ra.tail;
+		if (avail == 0) {
+			if (__atomic_load_n(&g_ra.eof, __ATOMIC_ACQUIRE) && __atomic_load_n(&g_ra.head, __ATOMIC_ACQUIRE) == g_ra.tail) break;
+			usleep(50);
+			continue;
+		}
+		{
+			const size_t at = g_ra.tail % RA_CAP;
+			size_t run = avail < (size_t)(len - done) ? avail : (size_t)(len - done);
+			if (RA_CAP - at < run) run = RA_CAP - at;
+			memcpy((uint8_t *)buf + done, g_ra.ring + at, run);
+			done += (unsigned)run;
+			__atomic_store_n(&g_ra.tail, g_ra.tail + run, __ATOMIC_RELEASE);
+		}
+	}
+	return (int)done;
+}
+
+int gzclose(gzFile f)
+{
+	REAL(int, gzclose, gzFile);
+	if (g_ra.real && f == g_ra.real) {
+		g_ra.stop = 1;
+		pthread_join(g_ra.th, 0);
+		free(g_ra.ring);
+		g_ra.real = 0;
+	}
+	return real_gzclose(f);
+}
+
 /* ------------------------------------------------------------------ device context */
 static int g_ready;
 static long g_calls_aln, g_calls_sa, g_calls_sw, g_reads_aln, g_q_sa, g_jobs_sw;

@@ -483,7 +483,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
                             bool device_compact)
 {
 	const bool stats = g_stats_enabled;
-	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx.reserve(w_entries + 1)) return 1;
+	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx.reserve(w_entries + 8)) return 1;
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;

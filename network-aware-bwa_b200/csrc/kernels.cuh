@@ -329,6 +329,9 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #ifndef BWAGPU_NO_FREELIST
 #define BWAGPU_NO_FREELIST 1 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
 #endif
+#ifndef BWAGPU_CTX_GROUP
+#define BWAGPU_CTX_GROUP 0 // 1: keep the 32-byte group (4 context words) of the last context load in registers: a match chain walks i downwards
+#endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
 #endif
@@ -478,6 +481,12 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	// context of the current node, loaded together with its occurrence blocks (k_ctx): width[i-1], width[i-2].bid,
 	// the two seed-width entries, str[i-1], str[i-2]
 	uint2 cw = make_uint2(0u, 0u);
+#if BWAGPU_CTX_GROUP
+	// the sector the last context word came from: the match continuation and the exact tail step i down by one per trip, so three
+	// of four context loads on such a path are served from registers.  Invalidated whenever gap_shadow rewrites context words.
+	uint32_t cg_id = 0xffffffffu;
+	uint4 cg_lo = make_uint4(0u, 0u, 0u, 0u), cg_hi = make_uint4(0u, 0u, 0u, 0u);
+#endif
 #define CW_WB1 (cw.x & (CW_BID | WB_EQ))
 #define CW_C1 ((cw.x >> 12) & 7u)
 #define CW_B2 ((int)((cw.x >> 16) & CW_BID))
@@ -633,6 +642,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				}
 				prev = wv; prev_nb = nb;
 			}
+#if BWAGPU_CTX_GROUP
+			cg_id = 0xffffffffu; // context words were rewritten
+#endif
 			const uint32_t idx = alloc_rec();
 			if (idx != NIL) {
 				*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score);
@@ -810,7 +822,27 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			ob_l = load_block(ix, jl >> 6);
 			ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
 			if (fresh | (mode == MODE_EXACT)) // fresh: the node's own word; exact tail: .x's base field of word i-1 = str[i-2]
-				cw = B.ctx[(size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)(fresh ? i : i - 1)];
+			{
+				const size_t cidx = (size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)(fresh ? i : i - 1);
+#if BWAGPU_CTX_GROUP
+				const uint32_t g = (uint32_t)(cidx >> 2);
+				if (g != cg_id) {
+					const uint4 *gp = reinterpret_cast<const uint4 *>(B.ctx + ((size_t)g << 2));
+#ifdef BWAGPU_HOST_EMU
+					cg_lo = gp[0]; cg_hi = gp[1];
+#else
+					asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+					             : "=r"(cg_lo.x), "=r"(cg_lo.y), "=r"(cg_lo.z), "=r"(cg_lo.w), "=r"(cg_hi.x), "=r"(cg_hi.y), "=r"(cg_hi.z), "=r"(cg_hi.w)
+					             : "l"(gp) : "memory");
+#endif
+					cg_id = g;
+				}
+				const uint32_t sel = (uint32_t)cidx & 3u;
+				cw = sel == 0 ? make_uint2(cg_lo.x, cg_lo.y) : sel == 1 ? make_uint2(cg_lo.z, cg_lo.w) : sel == 2 ? make_uint2(cg_hi.x, cg_hi.y) : make_uint2(cg_hi.z, cg_hi.w);
+#else
+				cw = B.ctx[cidx];
+#endif
+			}
 			if (STATS) {
 				f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
 				if (k == 0) f_ref += 1u;

@@ -180,7 +180,7 @@ def run_worker_mode(prefix, bam_in, bam_out, mode, remote, env_extra=None):
     port = free_port()
     if not remote:
         r = subprocess.run([DRIVER, "bam2bam", "-g", prefix, "-t", "1", "-p", str(port), "-f", bam_out, bam_in], capture_output=True,
-                           text=True, env=preload_env(mode, env_extra), timeout=1800)
+                           text=True, env=preload_env(mode, env_extra), timeout=300)
         assert r.returncode == 0, r.stderr[-3000:]
         return r.stderr
     master = subprocess.Popen([DRIVER, "bam2bam", "-g", prefix, "-t", "0", "-p", str(port), "-f", bam_out, bam_in],
@@ -188,7 +188,7 @@ def run_worker_mode(prefix, bam_in, bam_out, mode, remote, env_extra=None):
     worker = subprocess.Popen([DRIVER, "worker", "-t", "1", "-h", "127.0.0.1", "-p", str(port)], stderr=subprocess.PIPE, text=True,
                               env=preload_env(mode, env_extra))
     try:
-        _, merr = master.communicate(timeout=1800)
+        _, merr = master.communicate(timeout=300)
         _, werr = worker.communicate(timeout=120)
     finally:
         for p in (master, worker):

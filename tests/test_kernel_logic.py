@@ -150,3 +150,31 @@ def test_warp_search_logic_matches_reference_live(small_index, wemu_index, optkw
     got = R.wemu_aln(h, reads, opt)
     assert got[4] == 0
     assert R.compare_aln(want, got, "warp live") == []
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not built")
+def test_option_fuzz_matches_reference_live(small_index, emu_index, wemu_index):
+    """Random option sets (penalties, gap limits, seed, mode bits, max_top2, max_entries, max_diff given or derived) and read shapes:
+    both kernel bodies against the live reference.  scripts/fuzz_kernel_logic.py runs the same loop for as long as one likes."""
+    T, _ = small_index
+    he, ridx = emu_index
+    hw, _ = wemu_index
+    rng = np.random.default_rng(2024)
+    for it in range(12):
+        kw = dict(s_mm=int(rng.integers(1, 6)), s_gapo=int(rng.integers(1, 14)), s_gape=int(rng.integers(1, 7)),
+                  max_gapo=int(rng.integers(0, 3)), max_gape=int(rng.integers(0, 8)), indel_end_skip=int(rng.integers(0, 7)),
+                  max_del_occ=int(rng.integers(1, 20)), seed_len=int(rng.choice([8, 16, 32, 1024])), max_seed_diff=int(rng.integers(0, 3)),
+                  max_top2=int(rng.choice([0, 1, 3, 30])), max_entries=int(rng.choice([200, 3000])),
+                  mode=int(rng.choice([0x01, 0x00, 0x05, 0x11, 0x15, 0x04, 0x10])) | 0x02)
+        if rng.random() < 0.5:
+            kw["fnr"] = float(rng.choice([0.04, 0.01, 0.1]))
+        else:
+            kw["fnr"], kw["max_diff"] = -1.0, int(rng.integers(0, 4))
+        opt = abi.default_gap_opt(**kw)
+        lo = int(rng.integers(8, 50))
+        reads = R.bwa.simulate.simulate_reads(T, 40, (lo, lo + int(rng.integers(0, 40))), seed=int(rng.integers(1, 1 << 30)),
+                                              sub_rate=float(rng.choice([0.0, 0.02, 0.06])), n_rate=float(rng.choice([0.0, 0.01, 0.05])))
+        want = R.ref_aln(ridx, reads, opt, threads=4)
+        got_w = R.wemu_aln(hw, reads, opt)
+        assert got_w[4] == 0 and R.compare_aln(want, got_w, f"fuzz warp {kw}") == []
+        assert R.compare_aln(want, R.emu_aln(he, reads, opt), f"fuzz thread {kw}") == []

@@ -283,11 +283,13 @@ def main():
             lib.bwa_gpu_free_alns(reads.n, ptr)
         barrier()
         e2e_s = 0.0
+        e2e_steps = []
         n_aln_tot = 0
         for _ in range(args.steps):
             t0 = time.perf_counter()
             rc = lib.bwa_gpu_cal_sa_reads_gap(reads.n, ptr, C.byref(opt))
-            e2e_s += time.perf_counter() - t0
+            e2e_steps.append(1e3 * (time.perf_counter() - t0))
+            e2e_s += e2e_steps[-1] / 1e3
             assert rc == 0, lib.bwa_gpu_last_error()
             n_aln_tot = int(api.get_stats()["n_aln"])
             lib.bwa_gpu_free_alns(reads.n, ptr)  # untimed: the caller's bwa_free_read_seq1
@@ -299,7 +301,8 @@ def main():
         e2e = {"value": world * n_reads * args.steps / e2e_s, "unit": "reads/s",
                "h2d_bytes_per_step": int(reads.bases.size + 16 * reads.n),
                "d2h_bytes_per_step": int(8 * reads.n + 16 * n_aln_tot),
-               "api": "bwa_gpu_cal_sa_reads_gap(n, bwa_seq_t*, gap_opt_t*) incl. per-read calloc of aln[]"}
+               "api": "bwa_gpu_cal_sa_reads_gap(n, bwa_seq_t*, gap_opt_t*) incl. per-read calloc of aln[]",
+               "ms_each_step_rank0": [round(x, 1) for x in e2e_steps]}
 
     # ---- cpu baseline (rank 0, N = 1 only): the reference itself on a bounded sample
     cpu_baseline = None

@@ -8,6 +8,7 @@
 //     the reads whose search went deeper) -> scan + gather (read-ordered aln pool) -> D2H.
 // There is no CPU fallback: without a usable device every entry point returns an error.
 #include <cuda_runtime.h>
+#include <malloc.h>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -218,6 +219,17 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 {
 	bwa_gpu_destroy();
 	std::lock_guard<std::mutex> g(g_mu);
+	{
+		// The struct API hands every read a libc-allocated aln[] (the caller free()s it, bwaseqio.c:259): 10 M small blocks per call.
+		// With glibc's defaults the heaps are trimmed when the caller frees them and grown again 128 KB at a time on the next
+		// call (page faults + mprotect on the unpack threads).  Keep freed memory and grow in larger steps; BWAGPU_MALLOPT=0 leaves
+		// the allocator alone.
+		const char *e = getenv("BWAGPU_MALLOPT");
+		if (!e || atoi(e) != 0) {
+			mallopt(M_TRIM_THRESHOLD, 1 << 30);
+			mallopt(M_TOP_PAD, 64 << 20);
+		}
+	}
 	int have = 0;
 	cudaError_t e = cudaGetDeviceCount(&have);
 	if (e != cudaSuccess || have == 0)

@@ -413,10 +413,22 @@ static bool warp_stats_enabled()
 	const char *e = getenv("BWAGPU_WARP_STATS");
 	return e && atoi(e) != 0;
 }
-static search_fn warp_kernel(bool stdmode)
+// reads per block of the warp pass: WK_WARPS with one warp per read, 1 when the whole block works on one read (BWAGPU_WARP_TEAM=1:
+// rounds of 32 * WK_WARPS chains; same lanes per SM, a deep read finishes WK_WARPS times sooner)
+// Measured (profiles/r1_ab_experiments.md): with ~10^5 deep reads the launch lasts as long as its deepest read and the team form is
+// 13 % faster; with 4 x 10^5 it is throughput-bound and the warp form is 7 % faster (a team's round waits for the slowest of 128
+// chains).  BWAGPU_WARP_TEAM=0/1 forces one form; unset: by the number of reads in the pass.
+static bool warp_team_enabled(int n_jobs)
 {
-	if (warp_stats_enabled()) return stdmode ? k_search_warp<true, true> : k_search_warp<false, true>;
-	return stdmode ? k_search_warp<true, false> : k_search_warp<false, false>;
+	const char *e = getenv("BWAGPU_WARP_TEAM");
+	return e ? atoi(e) != 0 : n_jobs < 250000;
+}
+static int warp_reads_per_block(int n_jobs) { return warp_team_enabled(n_jobs) ? 1 : WK_WARPS; }
+static search_fn warp_kernel(bool stdmode, int n_jobs = 0)
+{
+	if (warp_team_enabled(n_jobs)) return stdmode ? k_search_warp<true, false, WK_WARPS> : k_search_warp<false, false, WK_WARPS>;
+	if (warp_stats_enabled()) return stdmode ? k_search_warp<true, true, 1> : k_search_warp<false, true, 1>;
+	return stdmode ? k_search_warp<true, false, 1> : k_search_warp<false, false, 1>;
 }
 static const size_t WARP_SMEM = (size_t)WK_WARPS * WK_WORDS_PER_WARP * sizeof(uint32_t);
 
@@ -439,8 +451,10 @@ static int pass_setup(Ctx *c, int t, uint32_t n_stacks, uint32_t max_entries_opt
 	if (t == 1 && warp_pass_enabled()) {
 		// one warp per read, every entry in pool chunks: no private arenas, no chunk table
 		int bps = 0;
-		CK(cudaFuncSetAttribute(warp_kernel(stdmode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, warp_kernel(stdmode), WK_WARPS * 32, WARP_SMEM));
+		// both forms (warp per read / block per read) have the same block size, shared memory and register bound
+		CK(cudaFuncSetAttribute(warp_kernel(stdmode, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
+		CK(cudaFuncSetAttribute(warp_kernel(stdmode, 1 << 30), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WARP_SMEM));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, warp_kernel(stdmode, 1 << 30), WK_WARPS * 32, WARP_SMEM));
 		if (bps < 1) bps = 1;
 		bps = (int)std::min<uint32_t>((uint32_t)bps, env_u32("BWAGPU_WARP_BLOCKS_PER_SM", 64));
 		T.slots_blocks = (uint32_t)(bps * c->n_sm);
@@ -607,9 +621,10 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		}
 		uint32_t blocks = T.slots_blocks;
 		if (t == 1 && warp_pass_enabled()) {
-			const uint32_t need = (uint32_t)((n_jobs + WK_WARPS - 1) / WK_WARPS);
+			const int rpb = warp_reads_per_block(n_jobs);
+			const uint32_t need = (uint32_t)((n_jobs + rpb - 1) / rpb);
 			if (blocks > need) blocks = need;
-			warp_kernel(is_stdmode(opt.mode))<<<blocks, WK_WARPS * 32, WARP_SMEM, c->st>>>(B);
+			warp_kernel(is_stdmode(opt.mode), n_jobs)<<<blocks, WK_WARPS * 32, WARP_SMEM, c->st>>>(B);
 		} else {
 			const uint32_t need = (uint32_t)((n_jobs + 127) / 128);
 			if (blocks > need) blocks = need;

@@ -43,6 +43,9 @@ namespace bwagpu {
 #ifndef WK_WARPS_PER_BLOCK
 #define WK_WARPS_PER_BLOCK 4 // 4 warps x 5 blocks per SM measured 6 % faster than 8 x 2 (profiles/r1_ab_experiments.md)
 #endif
+#ifndef BWAGPU_WARP_TEAM_DEFAULT
+#define BWAGPU_WARP_TEAM_DEFAULT 0 // 1: the warps of a block share one read by default (BWAGPU_WARP_TEAM overrides at run time)
+#endif
 #ifndef WK_MINBLOCKS
 #define WK_MINBLOCKS 5 // __launch_bounds__ second argument: 96 registers
 #endif
@@ -50,7 +53,7 @@ namespace bwagpu {
 #define WK_NB 257     // 256 score buckets (the ABI's limit) + the read's hit list
 #define WK_HITS 256
 #define WK_SEG 16     // chunks one round may touch per target bucket
-#define WK_WORDS_PER_WARP (2 * WK_NB + 3 * (WK_SEG + 1) + 64 + 1) // + the chunk cache (WK_CACHE ids + fill)
+#define WK_WORDS_PER_WARP (2 * WK_NB + 3 * (WK_SEG + 1) + 64 + 1 + 16) // + the chunk cache (WK_CACHE ids + fill) + team scratch
 
 // chunks of the shared pool: bump counter first, then a lock-free stack of recycled chunks ({tag:32 | head:32} against ABA)
 __device__ __forceinline__ uint32_t pool_chunk_alloc(const Batch &B)
@@ -168,20 +171,67 @@ __device__ __forceinline__ int warp_max(int v)
 	return v;
 }
 
-template <bool STDMODE, bool WSTATS>
+
+// ---- a read's TEAM: one warp (TEAM = 1, several reads per block) or all TEAM warps of a block (one read per block, rounds of up to
+// 32 * TEAM chains: the same lanes per SM, but a deep read finishes TEAM times sooner).  `lane` is the index within the team; tsm is
+// a few words of shared memory per team for the cross-warp steps.
+template <int TEAM> __device__ __forceinline__ void team_sync()
+{
+	if (TEAM == 1) __syncwarp(); else __syncthreads();
+}
+
+template <int TEAM> __device__ __forceinline__ int team_incl_scan(int v, int lane, int *tsm, int &total)
+{
+	const int w = warp_incl_scan(v, lane & 31);
+	if (TEAM == 1) { total = __shfl_sync(0xffffffffu, w, 31); return w; }
+	if ((lane & 31) == 31) tsm[lane >> 5] = w;
+	__syncthreads();
+	int pre = 0, tot = 0;
+#pragma unroll
+	for (int q = 0; q < TEAM; ++q) { const int t = tsm[q]; if (q < (lane >> 5)) pre += t; tot += t; }
+	__syncthreads();
+	total = tot;
+	return w + pre;
+}
+
+template <int TEAM> __device__ __forceinline__ int team_max(int v, int lane, int *tsm)
+{
+	v = warp_max(v);
+	if (TEAM == 1) return v;
+	if ((lane & 31) == 0) tsm[lane >> 5] = v;
+	__syncthreads();
+	int r = tsm[0];
+#pragma unroll
+	for (int q = 1; q < TEAM; ++q) r = max(r, tsm[q]);
+	__syncthreads();
+	return r;
+}
+
+template <int TEAM> __device__ __forceinline__ int team_bcast(int v, int src, int lane, int *tsm)
+{
+	if (TEAM == 1) return __shfl_sync(0xffffffffu, v, src);
+	if (lane == src) tsm[0] = v;
+	__syncthreads();
+	const int r = tsm[0];
+	__syncthreads();
+	return r;
+}
+
+template <bool STDMODE, bool WSTATS, int TEAM>
 __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(const Batch B)
 {
 #ifndef BWAGPU_WARP_EMU // tests/host_emu/warp_emu.cpp supplies the array
 	extern __shared__ __align__(16) uint32_t wk_smem[];
 #endif
-	const unsigned FULL = 0xffffffffu;
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	constexpr int TW = 32 * TEAM; // lanes of a team
+	const int lane = (int)threadIdx.x % TW, wib = (int)threadIdx.x / TW; // lane within the team, team within the block
 	uint32_t *const cnt = wk_smem + (size_t)wib * WK_WORDS_PER_WARP; // entries per bucket
 	uint32_t *const top = cnt + WK_NB;                                // chunk holding a bucket's top entry (NIL: empty)
 	uint32_t *const seg = top + WK_NB; // per target slot: [0] = number of the first chunk this round writes, [1 + r] = chunk ids
 	uint32_t *const cache = seg + 3 * (WK_SEG + 1), *const cache_n = cache + 64; // chunk cache, kept from read to read
+	int *const tsm = reinterpret_cast<int *>(cache_n + 1);
 	if (lane == 0) *cache_n = 0;
-	__syncwarp();
+	team_sync<TEAM>();
 	const GapOpt &O = B.opt;
 	const bool gape_mode = STDMODE || (O.mode & 0x01), loggap = !STDMODE && (O.mode & 0x04), nonstop = !STDMODE && (O.mode & 0x10);
 	const uint32_t C1 = B.ix[0].L2[1], C2 = B.ix[0].L2[2], C3 = B.ix[0].L2[3];
@@ -200,7 +250,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 	for (;;) { // reads
 		int job = 0;
 		if (lane == 0) job = atomicAdd(B.work_counter, 1);
-		job = __shfl_sync(FULL, job, 0);
+		job = team_bcast<TEAM>(job, 0, lane, tsm);
 		if (job >= B.n_jobs) break;
 		const int rid = B.jobs ? B.jobs[job] : job;
 		const ReadMeta md = B.meta[rid];
@@ -218,8 +268,8 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 		bool overflow = false;
 		BucketMask<false> mask;
 		mask.reset();
-		for (int b = lane; b < WK_NB; b += 32) { cnt[b] = 0; top[b] = NIL; }
-		__syncwarp();
+		for (int b = lane; b < WK_NB; b += TW) { cnt[b] = 0; top[b] = NIL; }
+		team_sync<TEAM>();
 		{ // the two root entries (bwtgap.c:127-128): strand 0 below strand 1
 			uint32_t c = NIL;
 			if (lane == 0) {
@@ -231,13 +281,13 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 					cnt[0] = 2; top[0] = c;
 				}
 			}
-			c = __shfl_sync(FULL, c, 0);
+			c = (uint32_t)team_bcast<TEAM>((int)c, 0, lane, tsm);
 			if (c == NIL) overflow = true;
 			else { mask.set(0); n_entries = 2; }
-			__syncwarp();
+			team_sync<TEAM>();
 		}
 
-		int tcap = 32; // lanes per round: halved after a round that had to drop lanes, doubled otherwise
+		int tcap = TW; // lanes per round: halved after a round that had to drop lanes, doubled otherwise
 		// diagnostics (BWAGPU_WARP_STATS=1 prints them): rounds, lanes taken / committed, chain steps, clocks per phase
 		unsigned long long st_rounds = 0, st_taken = 0, st_com = 0, st_steps = 0, st_maxsteps = 0, st_ck[6] = {0, 0, 0, 0, 0, 0};
 		int steps = 0;
@@ -417,28 +467,30 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 			// ---- pass A: count
 			long long ck1 = clock64();
 			if (mine) chain(false, 0, 0u, 0u, 0u, false, 0u, 0u);
-			__syncwarp();
+			team_sync<TEAM>();
 			long long ck2 = clock64();
-			if (WSTATS) {
-				st_steps += (unsigned long long)__reduce_add_sync(FULL, mine ? steps : 0);
-				st_maxsteps += (unsigned long long)__reduce_max_sync(FULL, mine ? steps : 0);
+			if (WSTATS && TEAM == 1) {
+				st_steps += (unsigned long long)__reduce_add_sync(0xffffffffu, mine ? steps : 0);
+				st_maxsteps += (unsigned long long)__reduce_max_sync(0xffffffffu, mine ? steps : 0);
 			}
 
 			// ---- who commits: everything up to the first lane whose chain changes what later pops see
 			const int netA = mine ? net : 0;
-			const int base_j = n_entries + warp_incl_scan(netA, lane) - netA; // n_entries when this lane's chain starts
+			int tot_unused;
+			const int base_j = n_entries + team_incl_scan<TEAM>(netA, lane, tsm, tot_unused) - netA; // n_entries when this lane's chain starts
 			const bool brkA = mine && base_j + maxpre > limit;
 			int h;
 			{
-				const uint32_t ev = __ballot_sync(FULL, mine && (hit || brkA || ovf));
-				h = ev ? __ffs((int)ev) - 1 : T - 1;
+				const int first = -team_max<TEAM>((mine && (hit || brkA || ovf)) ? -lane : -(1 << 20), lane, tsm); // the first such lane
+				h = first < T ? first : T - 1;
 			}
 			uint32_t N0, N1, N2, wb0, wb1, wb2;
 			for (;;) {
 				const bool com = lane <= h;
-				const int i0 = warp_incl_scan(com ? (int)n0 : 0, lane), i1 = warp_incl_scan(com ? (int)n1 : 0, lane),
-				          i2 = warp_incl_scan(com ? (int)n2 : 0, lane);
-				N0 = (uint32_t)__shfl_sync(FULL, i0, 31); N1 = (uint32_t)__shfl_sync(FULL, i1, 31); N2 = (uint32_t)__shfl_sync(FULL, i2, 31);
+				int t0, t1, t2;
+				const int i0 = team_incl_scan<TEAM>(com ? (int)n0 : 0, lane, tsm, t0), i1 = team_incl_scan<TEAM>(com ? (int)n1 : 0, lane, tsm, t1),
+				          i2 = team_incl_scan<TEAM>(com ? (int)n2 : 0, lane, tsm, t2);
+				N0 = (uint32_t)t0; N1 = (uint32_t)t1; N2 = (uint32_t)t2;
 				wb0 = (uint32_t)i0 - n0; wb1 = (uint32_t)i1 - n1; wb2 = (uint32_t)i2 - n2; // offsets within this round's pushes
 				const uint32_t room = (WK_SEG - 1) << ARENA_CHUNK_LOG;
 				if (N0 <= room && N1 <= room && N2 <= room) break;
@@ -464,7 +516,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 					cnt[s] = newc;
 				}
 				if (newc == 0) mask.clear(s);
-				__syncwarp();
+				team_sync<TEAM>();
 			}
 
 			// ---- room for the pushes: chunk ids of every chunk this round writes, per target slot
@@ -494,9 +546,9 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 						if (!fail) cnt[b] = p0 + N;
 					}
 				}
-				fail = __shfl_sync(FULL, fail, 0);
+				fail = team_bcast<TEAM>(fail, 0, lane, tsm);
 				if (fail) { overflow = true; break; } // pool dry: retried by the guaranteed pass
-				__syncwarp();
+				team_sync<TEAM>();
 				if (N0) { mask.set(s + d_mm); wb0 += cnt[s + d_mm] - N0; }
 				if (N1) { const int b = s + (slot_go == 1 ? d_go : d_ge); mask.set(b); wb1 += cnt[b] - N1; }
 				if (N2) { mask.set(s + d_ge); wb2 += cnt[s + d_ge] - N2; }
@@ -505,7 +557,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 			// ---- pass B: the committed lanes store their pushes at their final positions
 			long long ck3 = clock64();
 			if (com) { const bool hA = hit; const uint32_t kA = hk, lA = hl; chain(true, base_j, wb0, wb1, wb2, hA, kA, lA); }
-			__syncwarp();
+			team_sync<TEAM>();
 			long long ck4 = clock64();
 			if (WSTATS) {
 				++st_rounds; st_taken += (unsigned long long)T; st_com += (unsigned long long)(h + 1);
@@ -513,16 +565,20 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 				st_ck[3] += (unsigned long long)(ck4 - ck3);
 			}
 			{
-				const int tot = warp_incl_scan(com ? net : 0, lane);
-				n_entries += __shfl_sync(FULL, tot, 31);
-				const int mx = warp_max(com ? base_j + maxpre : 0);
+				int tot;
+				(void)team_incl_scan<TEAM>(com ? net : 0, lane, tsm, tot);
+				n_entries += tot;
+				const int mx = team_max<TEAM>(com ? base_j + maxpre : 0, lane, tsm);
 				if (max_entries < mx) max_entries = mx;
 			}
-			if (__ballot_sync(FULL, com && ovf)) { overflow = true; break; }
-			if (__ballot_sync(FULL, com && brk)) break; // bwtgap.c:140
+			{
+				const int flags = team_max<TEAM>(com ? ((ovf ? 2 : 0) | (brk ? 1 : 0)) : 0, lane, tsm); // only lane h can have either
+				if (flags & 2) { overflow = true; break; }
+				if (flags & 1) break; // bwtgap.c:140
+			}
 
 			// ---- the hit of lane h, if its chain ended in one (bwtgap.c:167-200), processed by that lane alone
-			if (__shfl_sync(FULL, (int)hit, h)) {
+			if (team_bcast<TEAM>((int)hit, h, lane, tsm)) {
 				int stop = 0;
 				if (lane == h) {
 					const int mmh = (int)(h_tag & 0xffu), goh = (int)((h_tag >> 8) & 0xffu), geh = (int)((h_tag >> 16) & 0xffu);
@@ -587,16 +643,16 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 					}
 					__threadfence_block();
 				}
-				best_score = __shfl_sync(FULL, best_score, h);
-				max_diff = __shfl_sync(FULL, max_diff, h);
-				best_cnt = __shfl_sync(FULL, best_cnt, h);
-				n_aln = __shfl_sync(FULL, n_aln, h);
-				stop = __shfl_sync(FULL, stop, h);
-				__syncwarp();
+				best_score = team_bcast<TEAM>(best_score, h, lane, tsm);
+				max_diff = team_bcast<TEAM>(max_diff, h, lane, tsm);
+				best_cnt = team_bcast<TEAM>(best_cnt, h, lane, tsm);
+				n_aln = team_bcast<TEAM>(n_aln, h, lane, tsm);
+				stop = team_bcast<TEAM>(stop, h, lane, tsm);
+				team_sync<TEAM>();
 				if (stop == 2) { overflow = true; break; }
 				if (stop) break;
 			}
-			tcap = h < T - 1 ? max(1, min(tcap >> 1, h + 1)) : min(32, tcap << 1);
+			tcap = h < T - 1 ? max(1, min(tcap >> 1, h + 1)) : min(TW, tcap << 1);
 			if (WSTATS) st_ck[4] += (unsigned long long)(clock64() - ck4);
 		}
 		if (WSTATS && lane == 0) {
@@ -610,7 +666,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 		uint32_t off = 0;
 		if (!overflow && n_aln > 0) {
 			if (lane == 0) off = atomicAdd(B.pool_count, (unsigned int)n_aln);
-			off = __shfl_sync(FULL, off, 0);
+			off = (uint32_t)team_bcast<TEAM>((int)off, 0, lane, tsm);
 			if (off + (uint32_t)n_aln > B.pool_cap) overflow = true;
 		}
 		if (overflow) {
@@ -623,18 +679,18 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 			uint32_t c = top[WK_HITS];
 			for (int q = n_aln > 0 ? (n_aln - 1) >> ARENA_CHUNK_LOG : -1; q >= 0; --q) {
 				const int lo = q << ARENA_CHUNK_LOG, hi = min(n_aln, lo + (int)ARENA_CHUNK);
-				for (int p = lo + lane; p < hi; p += 32)
+				for (int p = lo + lane; p < hi; p += TW)
 					B.pool[off + (uint32_t)p] = __ldcg(xent + ((size_t)c << ARENA_CHUNK_LOG) + (p & (ARENA_CHUNK - 1)));
 				c = xlink[(size_t)c << ARENA_CHUNK_LOG];
 			}
 			if (lane == 0) { B.n_aln[rid] = n_aln; B.pool_off[rid] = off; B.max_entries[rid] = max_entries; }
 		}
-		__syncwarp();
+		team_sync<TEAM>();
 		{ // The chunks of the read go to the warp's cache first (the next read needs a chunk per non-empty bucket at once);
 		  // what does not fit is returned in batches: the first such chunk a lane meets heads a batch, the next ones are listed in it
 			uint32_t head = NIL, m = 0;
 			volatile uint32_t *xw = nullptr;
-			for (int b = lane; b < WK_NB; b += 32) {
+			for (int b = lane; b < WK_NB; b += TW) {
 				uint32_t c = top[b];
 				while (c != NIL) {
 					const uint32_t below = xlink[(size_t)c << ARENA_CHUNK_LOG];
@@ -651,7 +707,7 @@ __global__ void __launch_bounds__(WK_WARPS * 32, WK_MINBLOCKS) k_search_warp(con
 			}
 			if (head != NIL) { xw[2] = m; pool_batch_push(B, head); }
 		}
-		__syncwarp();
+		team_sync<TEAM>();
 	}
 }
 

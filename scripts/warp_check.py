@@ -69,7 +69,7 @@ if "3" in what:
     reads = bwa.simulate.simulate_reads(T, n_time, (30, 50), seed=1000, device="cuda:0", adna=True, sub_rate=0.01)
     opt = abi.default_gap_opt(seed_len=1024, fnr=0.01, max_gapo=2)
     res = {}
-    for warp in (("1",) if os.environ.get("BWAGPU_WARP_ONLY") else ("1", "0")):
+    for warp in (("1",) if os.environ.get("BWAGPU_WARP_ONLY") else ("1", "0")):  # BWAGPU_WARP_TEAM (unset: by pass size) picks the form of the warp pass
         os.environ["BWAGPU_WARP_PASS"] = warp
         api.resident_stage(reads.bases, reads.offs, opt)
         for rep in range(2):

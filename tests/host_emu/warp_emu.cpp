@@ -8,7 +8,10 @@
 // golden vectors as the thread-per-read kernel.  Nothing in the product includes this file.
 #define BWAGPU_HOST_EMU 1
 #define BWAGPU_WARP_EMU 1
-#define WK_WARPS_PER_BLOCK 1
+#ifndef EMU_TEAM
+#define EMU_TEAM 1 // warps of the emulated block; > 1: they share one read (k_search_warp<.., TEAM = EMU_TEAM>)
+#endif
+#define WK_WARPS_PER_BLOCK EMU_TEAM
 #include <stdlib.h>
 #include <stdio.h>
 #include <ucontext.h>
@@ -20,51 +23,57 @@
 #include <algorithm>
 #include "host_emu_shim.h"
 
-// ---- the warp
-static const int NL = 32;
+// ---- the block: EMU_TEAM warps of 32 lanes
+static const int NL = 32 * EMU_TEAM;
 static ucontext_t g_sched, g_lane_ctx[NL];
 static int g_cur = 0;                 // lane running now
 static bool g_done[NL];
-static unsigned long long g_slot[NL]; // operands of the collective in progress
-static int g_arrived = 0;
-static unsigned g_gen = 0;            // completed collectives
+static unsigned long long g_slot[NL]; // operands of the collectives in progress
+// rendezvous groups: [w] = the lanes of warp w (shuffles, ballots, __syncwarp), [EMU_TEAM] = the whole block (__syncthreads)
+static int g_arrived[EMU_TEAM + 1];
+static unsigned g_gen[EMU_TEAM + 1];
 
 static void lane_yield() { swapcontext(&g_lane_ctx[g_cur], &g_sched); }
 
-// every lane deposits v, waits for the others, and gets a copy of all 32 operands
-static void collective(unsigned long long v, unsigned long long out[NL])
+static void rendezvous(int grp)
 {
-	const unsigned gen = g_gen;
-	g_slot[g_cur] = v;
-	++g_arrived;
-	while (g_gen == gen) lane_yield(); // the scheduler bumps g_gen once everyone is here
-	for (int i = 0; i < NL; ++i) out[i] = g_slot[i + NL * 0];
-	// second rendezvous: nobody may overwrite the slots before everyone has read them
-	const unsigned gen2 = g_gen;
-	++g_arrived;
-	while (g_gen == gen2) lane_yield();
+	const unsigned gen = g_gen[grp];
+	++g_arrived[grp];
+	while (g_gen[grp] == gen) lane_yield(); // the scheduler bumps the generation once every member is here
 }
 
-static inline int emu_lane() { return g_cur; }
+// every lane of the warp deposits v, waits for the others, and gets a copy of all 32 operands
+static void collective(unsigned long long v, unsigned long long out[32])
+{
+	const int w = g_cur >> 5;
+	g_slot[g_cur] = v;
+	rendezvous(w);
+	for (int i = 0; i < 32; ++i) out[i] = g_slot[w * 32 + i];
+	rendezvous(w); // nobody may overwrite the slots before everyone has read them
+}
+
+static inline void __syncthreads() { rendezvous(EMU_TEAM); }
+
+static inline int emu_lane() { return g_cur & 31; }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src)
 {
-	unsigned long long o[NL]; collective((unsigned long long)(long long)v, o); return (T)o[src & 31];
+	unsigned long long o[32]; collective((unsigned long long)(long long)v, o); return (T)o[src & 31];
 }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d)
 {
-	unsigned long long o[NL]; collective((unsigned long long)(long long)v, o); const int me = emu_lane(); return me >= d ? (T)o[me - d] : v;
+	unsigned long long o[32]; collective((unsigned long long)(long long)v, o); const int me = emu_lane(); return me >= d ? (T)o[me - d] : v;
 }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m)
 {
-	unsigned long long o[NL]; collective((unsigned long long)(long long)v, o); return (T)o[(emu_lane() ^ m) & 31];
+	unsigned long long o[32]; collective((unsigned long long)(long long)v, o); return (T)o[(emu_lane() ^ m) & 31];
 }
 static inline unsigned __ballot_sync(unsigned, bool p)
 {
-	unsigned long long o[NL]; collective(p ? 1ull : 0ull, o); unsigned r = 0; for (int i = 0; i < NL; ++i) r |= (unsigned)o[i] << i; return r;
+	unsigned long long o[32]; collective(p ? 1ull : 0ull, o); unsigned r = 0; for (int i = 0; i < 32; ++i) r |= (unsigned)o[i] << i; return r;
 }
-static inline void __syncwarp() { unsigned long long o[NL]; collective(0ull, o); }
-static inline int __reduce_add_sync(unsigned, int v) { unsigned long long o[NL]; collective((unsigned long long)(long long)v, o); int r = 0; for (int i = 0; i < NL; ++i) r += (int)o[i]; return r; }
-static inline int __reduce_max_sync(unsigned, int v) { unsigned long long o[NL]; collective((unsigned long long)(long long)v, o); int r = (int)o[0]; for (int i = 1; i < NL; ++i) r = std::max(r, (int)o[i]); return r; }
+static inline void __syncwarp() { unsigned long long o[32]; collective(0ull, o); }
+static inline int __reduce_add_sync(unsigned, int v) { unsigned long long o[32]; collective((unsigned long long)(long long)v, o); int r = 0; for (int i = 0; i < 32; ++i) r += (int)o[i]; return r; }
+static inline int __reduce_max_sync(unsigned, int v) { unsigned long long o[32]; collective((unsigned long long)(long long)v, o); int r = (int)o[0]; for (int i = 1; i < 32; ++i) r = std::max(r, (int)o[i]); return r; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline long long clock64() { return 0; }
 template <typename T> static inline T __ldcg(const T *p) { return *p; }
@@ -102,7 +111,7 @@ static bool g_std;
 static void lane_main(int lane)
 {
 	threadIdx.x = (unsigned)lane;
-	if (g_std) k_search_warp<true, false>(*g_batch); else k_search_warp<false, false>(*g_batch);
+	if (g_std) k_search_warp<true, false, EMU_TEAM>(*g_batch); else k_search_warp<false, false, EMU_TEAM>(*g_batch);
 	g_done[lane] = true;
 	g_cur = lane;
 	swapcontext(&g_lane_ctx[lane], &g_sched);
@@ -115,7 +124,7 @@ static void run_warp(const Batch &B, bool stdmode)
 	const size_t STK = 1 << 20;
 	stacks.resize(STK * NL);
 	g_batch = &B; g_std = stdmode;
-	g_arrived = 0; g_gen = 0;
+	for (int g = 0; g <= EMU_TEAM; ++g) { g_arrived[g] = 0; g_gen[g] = 0; }
 	for (int l = 0; l < NL; ++l) {
 		g_done[l] = false;
 		getcontext(&g_lane_ctx[l]);
@@ -124,18 +133,21 @@ static void run_warp(const Batch &B, bool stdmode)
 		g_lane_ctx[l].uc_link = &g_sched;
 		makecontext(&g_lane_ctx[l], (void (*)())lane_main, 1, l);
 	}
-	blockDim.x = 32; blockIdx.x = 0; gridDim.x = 1;
+	blockDim.x = NL; blockIdx.x = 0; gridDim.x = 1;
 	for (;;) {
-		int alive = 0;
+		int alive = 0, alive_w[EMU_TEAM] = {0};
 		for (int l = 0; l < NL; ++l) {
 			if (g_done[l]) continue;
-			++alive;
 			g_cur = l;
 			threadIdx.x = (unsigned)l;
 			swapcontext(&g_sched, &g_lane_ctx[l]);
 		}
+		for (int l = 0; l < NL; ++l) if (!g_done[l]) { ++alive; ++alive_w[l >> 5]; }
 		if (!alive) break;
-		if (g_arrived == alive && alive > 0) { g_arrived = 0; ++g_gen; } // everyone is at the rendezvous: release them
+		// a group whose every live member is at its rendezvous is released
+		for (int w = 0; w < EMU_TEAM; ++w)
+			if (alive_w[w] > 0 && g_arrived[w] == alive_w[w]) { g_arrived[w] = 0; ++g_gen[w]; }
+		if (g_arrived[EMU_TEAM] == alive) { g_arrived[EMU_TEAM] = 0; ++g_gen[EMU_TEAM]; }
 	}
 }
 

@@ -144,18 +144,18 @@ def emu_aln(h, reads, opt, cap1=1024, aln_cap1=64, n_slots=3, pool_chunks=64):
     return n_aln, max_entries, aln_off, aln, stats
 
 
-_wemu = None
+_wemu = {}
 
 
-def wemu():
-    """tests/host_emu/warp_emu.cpp: the body of k_search_warp on a 32-lane warp of coroutines."""
-    global _wemu
-    if _wemu is None:
-        so = os.path.join(EMU_DIR, "libwarp_emu.so")
+def wemu(team: int = 1):
+    """tests/host_emu/warp_emu.cpp: the body of k_search_warp on `team` warps of 32 coroutine lanes (team > 1: the warps of a block
+    share one read)."""
+    if team not in _wemu:
+        so = os.path.join(EMU_DIR, "libwarp_emu.so" if team == 1 else f"libwarp_emu_team{team}.so")
         srcs = [os.path.join(EMU_DIR, "warp_emu.cpp"), os.path.join(EMU_DIR, "host_emu_shim.h")] + [
             os.path.join(ROOT, "network-aware-bwa_b200", "csrc", f) for f in ("search_warp.cuh", "kernels.cuh", "fmindex.cuh", "hostprep.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I", EMU_DIR, "-o", so, srcs[0]], check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-DEMU_TEAM={team}", "-I", EMU_DIR, "-o", so, srcs[0]], check=True)
         E = C.CDLL(so)
         E.wemu_last_error.restype = C.c_char_p
         E.wemu_load_index.argtypes = [C.POINTER(C.POINTER(abi.bwt_t))]
@@ -164,13 +164,13 @@ def wemu():
         E.wemu_aln_flat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_int)]
         E.wemu_free.argtypes = [C.c_void_p]
-        _wemu = E
-    return _wemu
+        _wemu[team] = E
+    return _wemu[team]
 
 
-def wemu_aln(h, reads, opt, pool_chunks=4096):
+def wemu_aln(h, reads, opt, pool_chunks=4096, team=1):
     """-> (n_aln, max_entries, aln_off, aln, reads that found the chunk pool dry)"""
-    E = wemu()
+    E = wemu(team)
     n = reads.n
     bases = np.ascontiguousarray(reads.bases, dtype=np.uint8)
     offs = np.ascontiguousarray(reads.offs, dtype=np.int64)

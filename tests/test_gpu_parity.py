@@ -88,6 +88,18 @@ def test_warp_pass_matches_golden(golden, gpu_index, monkeypatch, name):
     assert R.compare_aln(want, got, "warp pass " + name) == []
 
 
+@pytest.mark.parametrize("team", ["0", "1"])
+@pytest.mark.parametrize("name", ["adna", "pe100", "nonstop_loggap"])
+def test_warp_pass_both_forms(golden, gpu_index, monkeypatch, name, team):
+    """BWAGPU_WARP_TEAM forces one warp per read (0) or the four warps of a block on one read (1); unset, the pass size decides."""
+    reads, opt, want = golden_case(golden, name)
+    monkeypatch.setenv("BWAGPU_T1_CAP", "2")
+    monkeypatch.setenv("BWAGPU_WARP_TEAM", team)
+    got = api.aln_flat(reads.bases, reads.offs, opt)
+    assert api.get_stats()["n_overflow_t2"] > reads.n // 2
+    assert R.compare_aln(want, got, f"warp pass form {team} {name}") == []
+
+
 def test_thread_pass_still_available(golden, gpu_index, monkeypatch):
     """BWAGPU_WARP_PASS=0: pass 1 is the pooled thread-per-read kernel again (A/B switch)."""
     reads, opt, want = golden_case(golden, "adna")

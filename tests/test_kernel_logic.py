@@ -122,6 +122,22 @@ def test_warp_search_logic_matches_golden(golden, wemu_index, name):
     assert R.compare_aln(w, got, "warp " + name) == []
 
 
+@pytest.mark.parametrize("name", ["se76", "adna", "ragged", "nogape"])
+def test_team_search_logic_matches_golden(golden, small_index, name):
+    """The same kernel body with the four warps of a block sharing one read (rounds of up to 128 chains, block-wide scans)."""
+    T, idx = small_index
+    ridx = R.RefIndex(idx)
+    h = R.wemu(4).wemu_load_index(ridx.arr)
+    try:
+        reads, opt, want = golden_case(golden, name)
+        r, w = _prefix(reads, want, 80)
+        got = R.wemu_aln(h, r, opt, team=4)
+        assert got[4] == 0
+        assert R.compare_aln(w, got, "team " + name) == []
+    finally:
+        R.wemu(4).wemu_free_index(h)
+
+
 def test_warp_search_logic_pool_dry(golden, wemu_index):
     """A chunk pool too small for every read: the reads that find it dry are flagged (n_aln = -1, retried by the guaranteed pass
     in the library); the others are still exact."""

@@ -278,7 +278,7 @@ def main():
     if not args.no_e2e:
         ptr, keep = seq_struct_array(abi, reads)
         lib = api.lib()
-        for _ in range(min(args.warmup, 1)):
+        for _ in range(min(args.warmup, 2)):
             assert lib.bwa_gpu_cal_sa_reads_gap(reads.n, ptr, C.byref(opt)) == 0, lib.bwa_gpu_last_error()
             lib.bwa_gpu_free_alns(reads.n, ptr)
         barrier()

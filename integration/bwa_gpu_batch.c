@@ -528,7 +528,13 @@ static void decode_one(size_t i, void *ctx)
 /* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file), then destroyed.  Serial on purpose:
  * encode and destroy are malloc/free of blocks other threads allocated, and spreading them over threads is slower (measured:
  * 0.29 s per 300 k records on one thread, 0.74 s on eight) */
-static void store_records(gzFile temporary, bam_pair_t *recs, size_t n)
+static void destroy_records(bam_pair_t *recs, size_t n)
+{
+	size_t i;
+	for (i = 0; i < n; ++i) bam_destroy_pair(&recs[i]);
+}
+
+static void store_records(gzFile temporary, bam_pair_t *recs, size_t n, int destroy)
 {
 	size_t i;
 	for (i = 0; i < n; ++i) {
@@ -543,7 +549,7 @@ static void store_records(gzFile temporary, bam_pair_t *recs, size_t n)
 			}
 		}
 		zmq_msg_close(&m);
-		bam_destroy_pair(&recs[i]);
+		if (destroy) bam_destroy_pair(&recs[i]);
 	}
 }
 
@@ -762,15 +768,16 @@ static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, do
 	position_range(recs, n, t_host);
 }
 
-/* Pass 1 as a pipeline of four stages, each on its own thread, batches handed on in order through a ring of slots:
+/* Pass 1 as a pipeline of five stages, each on its own thread, batches handed on in order through a ring of slots:
  *   read     read_bam_pair (inflate + parse; bamlite is a sequential gzread)
  *   align    bam1_to_seq on the host threads + the search on the device            (the calling thread)
  *   position bwa_aln2seq_core in record order (drand48), SA rows on the device, bwa_cal_pac_pos_core, improve_isize_est
- *   store    the reference's record encoding into memory / its temporary file, bam_destroy_pair
+ *   store    the reference's record encoding into memory / its temporary file
+ *   destroy  bam_destroy_pair of the batch (a dozen free()s per record)
  * Every order-sensitive piece of state belongs to exactly one stage, and a stage sees the batches in input order, so the
  * result is what the one-record-at-a-time loop (bam2bam.c:1143-1176) produces. */
 #define P1_SLOTS 8 /* the reader may run this many batches ahead (it does while the device context is created) */
-enum { SL_FREE = 0, SL_READ, SL_ALIGNED, SL_POSITIONED };
+enum { SL_FREE = 0, SL_READ, SL_ALIGNED, SL_POSITIONED, SL_STORED };
 typedef struct {
 	pthread_mutex_t mu;
 	pthread_cond_t cv;
@@ -782,7 +789,7 @@ typedef struct {
 	bwa_seqio_t *ks;
 	gzFile temporary;
 	khash_t(isize_infos) *iinfos;
-	double t0, t_read, t_host, t_write;
+	double t0, t_read, t_host, t_write, t_destroy;
 	long tot_seqs;
 } pipe1_t;
 
@@ -865,12 +872,29 @@ static void *stage_store(void *arg)
 		double t1;
 		slot_wait(P, slot, SL_POSITIONED);
 		n = P->n[slot];
-		if (n == 0) break;
+		if (n == 0) { slot_set(P, slot, SL_STORED); break; }
 		t1 = now();
-		store_records(P->temporary, P->recs[slot], n);
+		store_records(P->temporary, P->recs[slot], n, 0);
 		P->t_write += now() - t1;
 		P->tot_seqs += P->seqs[slot];
 		fprintf(stderr, "[sequential_loop_pass1] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
+		slot_set(P, slot, SL_STORED);
+	}
+	return 0;
+}
+
+static void *stage_destroy(void *arg)
+{
+	pipe1_t *P = (pipe1_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P1_SLOTS);
+		double t1;
+		slot_wait(P, slot, SL_STORED);
+		if (P->n[slot] == 0) break;
+		t1 = now();
+		destroy_records(P->recs[slot], P->n[slot]);
+		P->t_destroy += now() - t1;
 		slot_set(P, slot, SL_FREE);
 	}
 	return 0;
@@ -882,7 +906,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	pipe1_t P;
 	double t_toseq = 0, t_init;
 	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
-	pthread_t init_th, read_th, pos_th, store_th;
+	pthread_t init_th, read_th, pos_th, store_th, destroy_th;
 	unsigned q;
 	int s;
 	memset(&P, 0, sizeof(P));
@@ -895,6 +919,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	pthread_create(&read_th, 0, stage_read, &P);
 	pthread_create(&pos_th, 0, stage_position, &P);
 	pthread_create(&store_th, 0, stage_store, &P);
+	pthread_create(&destroy_th, 0, stage_destroy, &P);
 	pthread_join(init_th, 0);
 	t_init = now() - P.t0;
 	for (q = 0;; ++q) { /* the align stage */
@@ -904,14 +929,14 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 		slot_set(&P, slot, SL_ALIGNED);
 		if (P.n[slot] == 0) break;
 	}
-	pthread_join(read_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0);
+	pthread_join(read_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0); pthread_join(destroy_th, 0);
 	for (s = 0; s < P1_SLOTS; ++s) free(P.recs[s]);
 	free(flat);
 	pthread_mutex_destroy(&P.mu); pthread_cond_destroy(&P.cv);
 	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, g_mt.n_rec, g_mt.bytes / 1048576.0,
 	        g_mt.spilled ? ", the rest in the temporary file" : "");
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each: device init %.2f, read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f)\n",
-	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, t_toseq, P.t_host, g_t_aln + g_t_sa, P.t_write);
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each: device init %.2f, read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f, destroy %.2f)\n",
+	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, t_toseq, P.t_host, g_t_aln + g_t_sa, P.t_write, P.t_destroy);
 	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
 }
 

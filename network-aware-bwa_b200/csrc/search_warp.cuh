@@ -32,6 +32,11 @@
 // then land in the bucket being drained).  Everything else -- pruning by the width bounds, indel_end_skip,
 // max_del_occ, phantoms (counted, not stored), first-in-order duplicate test -- is the reference's, entry by entry.
 //
+// TEAM (template parameter): the warps that share a read -- 1 (several reads per block) or all warps of the block (one read per
+// block, rounds of up to 32 * TEAM chains; scans, first-event search and broadcasts then go through a few words of shared memory
+// and __syncthreads).  Same lanes per SM; a deep read finishes sooner, the bulk rate is a little lower.  The host picks by the
+// size of the pass (bwagpu.cu).
+//
 // Memory: all of a read's entries and hits live in chunks of the launch's shared pool (Batch::xent; the word
 // xnxt[chunk << 10] links a chunk to the one below it).  A read that finds the pool dry is flagged and retried by
 // the guaranteed pass of k_search, like before.

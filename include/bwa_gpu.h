@@ -234,7 +234,7 @@ typedef struct {
 	int64_t n_pops, n_pushes;
 	int32_t launches; /* kernels launched by the call */
 	int32_t n_devices;
-	double ms_tier[4]; /* k_search (+ its width refresh) per pass: [0] private arenas, [1] shared chunk pool, [2] guaranteed */
+	double ms_tier[4]; /* search kernels (+ their width refresh) per pass: [0] k_search on private arenas, [1] k_search_warp on the shared chunk pool, [2] k_search with guaranteed memory */
 	int64_t n_stored;  /* records that reached the in-memory stack (stats builds) */
 	int64_t n_pruned, n_expand, n_exact, n_derive; /* pops pruned / nodes expanded / exact-tail steps / group-child derivations */
 	int64_t n_trips;          /* loop trips summed over threads (stats builds) */

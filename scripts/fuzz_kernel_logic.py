@@ -9,6 +9,7 @@ T = golden["genome"]
 idx = R.bwa.index.build_index(T)
 ridx = R.RefIndex(idx)
 h = R.wemu().wemu_load_index(ridx.arr)
+h4 = R.wemu(4).wemu_load_index(ridx.arr)
 he = R.emu().emu_load_index(ridx.arr)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 bad = 0
@@ -36,6 +37,8 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 30):
     except Exception as e:
         print(it, "EXC", e, kw); bad += 1; continue
     errs = R.compare_aln(want, got, "fuzz") if got[4] == 0 else [f"dry {got[4]}"]
+    got4 = R.wemu_aln(h4, reads, opt, team=4)
+    errs += R.compare_aln(want, got4, "fuzz-team") if got4[4] == 0 else [f"team dry {got4[4]}"]
     try:
         got2 = R.emu_aln(he, reads, opt)
         errs2 = R.compare_aln(want, got2, "fuzz-thread")

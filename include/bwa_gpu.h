@@ -139,6 +139,21 @@ void bwa_gpu_destroy(void);
 
 const char *bwa_gpu_last_error(void);
 
+/* ------------------------------------------------------------------ index construction
+ * The compute of `bwa index` (bwtindex.c:102-190) on one device: from the packed forward sequence (the .pac
+ * bns_fasta2bntseq wrote, bntseq.c:169-250: 4 bases per byte, l_pac/4+1 bytes) to both strands' bwt_t --
+ * BWT (bwt_pac2bwt, bwtmisc.c:56-101; is.c / bwt_gen) with the occurrence counts interleaved every 128 bases
+ * (bwt_bwtupdate_core, bwtmisc.c:125-152) and the suffix array sampled every 32 rows (bwt_cal_sa, bwt.c:48-70); rev is
+ * the index of the reversed, not complemented, sequence (bwa_pac_rev_core, bwtmisc.c:168-193).  The structs are filled
+ * the way bwt_restore_bwt + bwt_restore_sa fill them (bwtio.c:157-200; bwt and sa malloc()'d, cnt_table set), so they can go
+ * straight into bwa_gpu_load_index or to bwt_dump_bwt / bwt_dump_sa.  A full suffix sort in HBM (prefix doubling on radix
+ * sorts) replaces induced sorting / BWT-SW; the result is the same bytes.  Needs no bwa_gpu_init.  l_pac < 2^32 - 64. */
+int bwa_gpu_index_build(const ubyte_t *pac, int64_t l_pac, int device, bwt_t *fwd, bwt_t *rev);
+/* free()s what bwa_gpu_index_build allocated inside *b (bwt_destroy, bwt.c:226-235, without freeing b itself) */
+void bwa_gpu_index_free(bwt_t *b);
+/* bwt_dump_bwt + bwt_dump_sa (bwtio.c:17-38) for both strands: <prefix>.bwt / .rbwt / .sa / .rsa */
+int bwa_gpu_index_write(const char *prefix, const bwt_t *fwd, const bwt_t *rev);
+
 /* ------------------------------------------------------------------ K2 + K3: gapped search
  * Batch form of   bwa_cal_sa_reg_gap(bwt, 1, &seqs[i], opt)   for i in [0, n_seqs)
  * (bwtaln.c:93-142 as called from bam2bam.c:616 and 676: PER-READ semantics -- max_diff,

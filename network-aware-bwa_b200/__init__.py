@@ -8,6 +8,7 @@ The directory name carries a hyphen, so import it with importlib:
 
 Modules: api (ctypes binding of include/bwa_gpu.h -> libbwagpu.so, no fallback),
 abi (struct mirrors), index (FM-index build/load in the reference's formats),
-simulate (seeded genomes and reads), build (nvcc recipe for csrc/).
+simulate (seeded genomes and reads), workload (cached genome + index files of the BASELINE.json shapes),
+build (nvcc recipe for csrc/).
 """
-from . import abi, api, build, index, shard, simulate  # noqa: F401
+from . import abi, api, build, index, shard, simulate, workload  # noqa: F401

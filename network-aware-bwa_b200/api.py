@@ -49,6 +49,10 @@ def lib() -> C.CDLL:
         L.bwa_gpu_resident_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t)]
         L.bwa_gpu_resident_run.argtypes = [C.POINTER(C.c_double)]
         L.bwa_gpu_resident_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bwa_gpu_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(abi.bwt_t), C.POINTER(abi.bwt_t)]
+        L.bwa_gpu_index_free.argtypes = [C.POINTER(abi.bwt_t)]
+        L.bwa_gpu_index_free.restype = None
+        L.bwa_gpu_index_write.argtypes = [C.c_char_p, C.POINTER(abi.bwt_t), C.POINTER(abi.bwt_t)]
         _lib = L
     return _lib
 
@@ -58,6 +62,7 @@ EXPORTS = [
     "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw", "bwa_gpu_mate_sw_path", "bwa_gpu_global_align",
     "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_probe_random_sectors",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
+    "bwa_gpu_index_build", "bwa_gpu_index_free", "bwa_gpu_index_write",
 ]
 
 
@@ -84,6 +89,30 @@ def load_index(idx) -> None:
     arr = (C.POINTER(abi.bwt_t) * 2)(C.pointer(t0), C.pointer(t1))
     pac = np.ascontiguousarray(idx.pac)
     _ck(lib().bwa_gpu_load_index(arr, pac.ctypes.data, idx.l_pac))
+
+
+def index_build(pac: np.ndarray, l_pac: int, device: int = 0, write_prefix: str | None = None):
+    """bwa_gpu_index_build: packed forward sequence -> (fwd, rev) as index.Bwt objects (numpy copies of the
+    reference-layout arrays).  write_prefix: also dump <prefix>.bwt/.rbwt/.sa/.rsa through bwa_gpu_index_write."""
+    from . import index as ix
+    pac = np.ascontiguousarray(pac, dtype=np.uint8)
+    if pac.size < l_pac // 4 + 1:
+        raise ValueError("pac shorter than l_pac/4+1 bytes")
+    t = [abi.bwt_t(), abi.bwt_t()]
+    _ck(lib().bwa_gpu_index_build(pac.ctypes.data, int(l_pac), int(device), C.byref(t[0]), C.byref(t[1])))
+    try:
+        if write_prefix is not None:
+            _ck(lib().bwa_gpu_index_write(write_prefix.encode(), C.byref(t[0]), C.byref(t[1])))
+        out = []
+        for b in t:
+            L2 = np.array([b.L2[i] for i in range(5)], dtype=np.uint32)
+            bwt = np.ctypeslib.as_array(b.bwt, shape=(b.bwt_size,)).copy()
+            sa = np.ctypeslib.as_array(b.sa, shape=(b.n_sa,)).copy()
+            out.append(ix.Bwt(primary=int(b.primary), L2=L2, seq_len=int(b.seq_len), bwt=bwt, sa=sa, sa_intv=int(b.sa_intv)))
+    finally:
+        for b in t:
+            lib().bwa_gpu_index_free(C.byref(b))
+    return out
 
 
 def cal_sa_reads_gap(seqs, opt) -> None:

@@ -164,14 +164,33 @@ class FMIndex:
 def pack_pac(T: np.ndarray) -> np.ndarray:
     n = T.size
     nb = n // 4 + 1  # bwt_restore_pac reads l_pac/4+1 bytes (bwtio.c:149)
-    buf = np.zeros(nb * 4, dtype=np.uint8)
-    buf[:n] = T
-    buf = buf.reshape(nb, 4)
-    return ((buf[:, 0] << 6) | (buf[:, 1] << 4) | (buf[:, 2] << 2) | buf[:, 3]).astype(np.uint8)
+    out = np.zeros(nb, dtype=np.uint8)
+    full = n // 4
+    q = T[: full * 4].reshape(full, 4)
+    np.left_shift(q[:, 0], 6, out=out[:full])
+    out[:full] |= q[:, 1] << 4
+    out[:full] |= q[:, 2] << 2
+    out[:full] |= q[:, 3]
+    for j in range(n - full * 4):  # the ragged tail
+        out[full] |= np.uint8(int(T[full * 4 + j]) << (6 - 2 * j))
+    return out
+
+
+def build_index_native(T: np.ndarray, device: int = 0, write_prefix: str | None = None) -> FMIndex:
+    """The library's own builder (csrc/indexbuild.cu, bwa_gpu_index_build): suffix sort on the device with cub radix
+    sorts, any genome the 32-bit bwtint_t admits.  Needs a CUDA device."""
+    from . import api
+    pac = pack_pac(T)
+    fwd, rev = api.index_build(pac, int(T.size), device=device, write_prefix=write_prefix)
+    return FMIndex(bwt=[fwd, rev], pac=pac, l_pac=int(T.size))
 
 
 def build_index(T: np.ndarray, device: str | torch.device = "cpu") -> FMIndex:
-    """Index a base string (uint8 0..3; callers resolve N beforehand like bntseq.c:225)."""
+    """Index a base string (uint8 0..3; callers resolve N beforehand like bntseq.c:225).  On a CUDA device this is the
+    library's native builder; the torch prefix-doubling sort below is the CPU harness path of the test suite."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and os.environ.get("BWAGPU_TORCH_INDEX", "0") == "0":
+        return build_index_native(T, device=dev.index or 0)
     t = torch.from_numpy(np.ascontiguousarray(T)).to(device)
     fwd = build_bwt(t)
     rev = build_bwt(torch.flip(t, [0]))

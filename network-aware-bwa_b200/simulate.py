@@ -162,12 +162,13 @@ def simulate_pairs(T, n_pairs: int, length: int, seed: int = 11, isize_mean: flo
     n = Tt.numel()
     L = length
     isz = (torch.randn(n_pairs, generator=g, device=dev) * isize_sd + isize_mean).round().long().clamp(min=L + 10)
-    start = (torch.rand(n_pairs, generator=g, device=dev) * (n - isz.max().item() - 8)).long()
+    fdt = torch.float64 if n > (1 << 24) else torch.float32  # float32 has 24 bits: too coarse a grid for a real genome
+    start = (torch.rand(n_pairs, generator=g, device=dev, dtype=fdt) * (n - isz.max().item() - 8)).long()
     idx = torch.arange(L, device=dev).unsqueeze(0)
     m1 = Tt[start.unsqueeze(1) + idx].to(torch.uint8)
     s2 = start + isz - L
     chim = torch.rand(n_pairs, generator=g, device=dev) < chimeric_frac
-    s2 = torch.where(chim, (torch.rand(n_pairs, generator=g, device=dev) * (n - L - 8)).long(), s2)
+    s2 = torch.where(chim, (torch.rand(n_pairs, generator=g, device=dev, dtype=fdt) * (n - L - 8)).long(), s2)
     m2f = Tt[s2.unsqueeze(1) + idx].to(torch.uint8)
     m2 = 3 - torch.flip(m2f, [1])
     bad = torch.rand(n_pairs, generator=g, device=dev) < bad_mate_frac

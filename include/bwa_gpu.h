@@ -211,7 +211,7 @@ int bwa_gpu_mate_sw(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_sw_res_t *res);
  * p = path + path_len - 1 and path[0] in the reference's terms) and the raw CIGAR of the path as
  * bwa_aln_path2cigar gives it (bwtaln.c:396-406: op << 14 | len, ops FROM_M 0 / FROM_I 1 / FROM_D 2),
  * at cigar_pool[cigar_off .. cigar_off + n_cigar).  *cigar_pool is library-owned, valid until the next
- * call of either function. */
+ * call of the same family (bwa_gpu_mate_sw_path has one pool, the bwa_gpu_global_align* calls another). */
 typedef struct {
 	int32_t score;
 	int32_t n_cigar;
@@ -233,6 +233,19 @@ int bwa_gpu_mate_sw_path(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_path_res_t
  * like inner gaps.  The host keeps refine_gapped_core's coordinate fix-ups (bwase.c:215-234). */
 int bwa_gpu_global_align(int n, const bwa_gpu_sw_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
                          const bwa_cigar_t **cigar_pool);
+
+/* The same call on explicit sequences -- aln_global_core(seq1, len1, seq2, len2, &aln_param_bwa-like ap, path, &path_len)
+ * (stdaln.c:345) exactly as refine_gapped_core issues it after unpacking its window (bwase.c:199-212): ref[0 .. reflen) and
+ * seq[0 .. len), one base per byte (0..3, anything above = N).  For callers that interpose aln_global_core itself and never see
+ * the window's pac coordinate (integration/bwa_gpu_batch.c). */
+typedef struct {
+	const ubyte_t *ref;
+	int32_t reflen;
+	int32_t len;
+	const ubyte_t *seq;
+} bwa_gpu_ga_job_t;
+int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
+                              const bwa_cigar_t **cigar_pool);
 
 /* ------------------------------------------------------------------ measurement hooks
  * Device-side timing (CUDA events on the library's own streams) and work counters of the

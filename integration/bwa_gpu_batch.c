@@ -1,79 +1,68 @@
-/* bwa_gpu_batch.c -- the BATCHED drop-in: `bwa bam2bam -t 1` with its hot path on the GPU, one device
+/* bwa_gpu_batch.c -- the BATCHED drop-in: `bwa bam2bam -t 1` (and the 0MQ worker) with the hot path on the GPU, one device
  * call per phase and batch instead of one per record.
  *
- * SURVEY.md §8(f) rank 1 / INTEGRATION.md: the reference's sequential driver (bam2bam.c:1143-1219)
- * handles one record at a time -- read_bam_pair -> pair_aln -> pair_posn -> ... -- so its calls into the
- * alignment layer carry one read each.  This shim REPLACES the two loop functions
+ * SURVEY.md §8(f) rank 1 / INTEGRATION.md: the reference's sequential driver (bam2bam.c:1143-1219) handles one record at
+ * a time -- read_bam_pair -> pair_aln -> pair_posn -> ... -- so its calls into the alignment layer carry one read each.
+ * This library REPLACES the two loop functions
  *
  *     sequential_loop_pass1 (bam2bam.c:1143)      sequential_loop_pass2 (bam2bam.c:1178)
  *
- * (both are plain global functions of the reference, reached through the PLT of a shared-library build,
- * so LD_PRELOAD can supply them) with versions that gather a batch of records and make ONE call per phase:
+ * and the worker thread run_worker_thread (bam2bam.c:1387) -- plain global functions of the reference, reached through the
+ * PLT of a shared-library build of it (integration/Makefile: _host/libbwahost.so) -- with versions that gather a batch of
+ * records and make ONE call per phase:
  *
  *   pass 1   bam1_to_seq x n  ->  bwa_gpu_cal_sa_reads_gap   (replaces bwa_cal_sa_reg_gap, bam2bam.c:616,676)
  *            bwa_aln2seq[_core] in record order (it consumes drand48: bwase.c:33,36,78)
  *            -> bwa_gpu_cal_pac_pos                           (replaces bwt_sa at bwase.c:145,152; bam2bam.c:635-636)
  *   pass 2   hit enumeration of all pairs -> bwa_gpu_cal_pac_pos   (bwt_sa at bam2bam.c:752,761)
- *            pairing + bwa_aln2seq_core in record order -> bwa_gpu_cal_pac_pos (bam2bam.c:786)
+ *            pairing; bwa_aln2seq_core in record order -> bwa_gpu_cal_pac_pos (bam2bam.c:786)
  *            bwa_paired_sw1 -> bwa_gpu_mate_sw_path           (aln_local_core inside bwa_sw_core, bwape.c:456)
- *            bwa_refine_gapped, bwa_update_bam1, BAM output: the reference's own code, per record.
+ *            bwa_refine_gapped -> bwa_gpu_global_align_seqs   (aln_global_core inside refine_gapped_core, bwase.c:212)
+ *            bwa_update_bam1, BAM output: the reference's own code per record, spread over the host threads.
  *
- * Everything that is not the hot path IS the reference: this file calls its exported functions
- * (read_bam_pair, bam1_to_seq, bwa_aln2seq_core, bwa_cal_pac_pos_core, pairing, bwa_paired_sw1,
- * bwa_refine_gapped, bwa_update_bam1, pair_print_custom, ...) and never restates their arithmetic.
- * Where a reference function interleaves host logic with a hot call (bwa_cal_pac_pos_core around bwt_sa,
- * bwa_paired_sw1/bwa_sw_core around aln_local_core) it is run in RECORD / REPLAY fashion: a first run with
- * the hot call interposed to note its arguments (and return "no result", which leaves the record
- * untouched), one device call for the whole batch, then the real run with the hot call interposed to
- * hand back the device's answers in the same order.
+ * Everything that is not the hot path IS the reference: this file calls its exported functions (read_bam_pair,
+ * bam1_to_seq, bwa_aln2seq_core, bwa_cal_pac_pos_core, pairing, bwa_paired_sw1, bwa_refine_gapped, bwa_update_bam1, ...)
+ * and never restates their arithmetic.  Where a reference function interleaves host logic with a hot call
+ * (bwa_cal_pac_pos_core around bwt_sa, bwa_paired_sw1/bwa_sw_core around aln_local_core, bwa_refine_gapped around
+ * aln_global_core) it is run in RECORD / REPLAY fashion: a first run with the hot call interposed to note its arguments,
+ * one device call for the whole batch, then the real run with the hot call interposed to hand back the device's answers
+ * in the same order.
  *
- * Order-sensitive state is kept exactly as `-t 1` has it: drand48 is consumed by bwa_aln2seq_core only
- * (bwase.c), which runs in record order in both passes; the pass-2 position cache for intervals >= 1000
- * wide (bam2bam.c:743-758) is filled by the first record, in record order, that touches a key.
- * The output BAM is therefore record-identical to `bam2bam -t 1` (tests/test_batched_bam2bam.py).
+ * Both passes are pipelines of stages, each stage a thread, batches handed on in order; the stages that are functions of
+ * one record (pairing, mate rescue, refinement, BAM record rewrite) run on all host threads.  Order-sensitive state is
+ * kept exactly as `-t 1` has it: drand48 is consumed by bwa_aln2seq_core only (bwase.c), which runs in record order in
+ * both passes; the pass-2 position cache for intervals >= 1000 wide (bam2bam.c:743-758) is filled by the first record, in
+ * record order, that touches a key.  The output BAM is therefore record-identical to `bam2bam -t 1`
+ * (tests/test_batched_bam2bam.py).
  *
- * The reference's static globals (bwt, bns, pac, gap_opt, pe_opt, the three input flags) are captured
- * by interposing the loaders / option parser that produce them.  Not supported here: `.sai` inputs
- * (-0/-1/-2; broken in the reference itself) -- such records take the per-record path.
+ * There is no CPU path in here: `.sai` side inputs (-0/-1/-2), which would bypass the device search, are refused.
  *
- * Build (integration/Makefile): gcc -I$(REF) -I../oracle/zmq_shim -I../include ... -lbwagpu
- * Use:   LD_PRELOAD=integration/libbwa_gpu_batch.so oracle/_ref/ref_driver bam2bam -g idx -t 1 -f out.bam in.bam
+ * Two ways in:
+ *   LD_PRELOAD=integration/libbwa_gpu_batch.so integration/_host/bwa_host bam2bam -g idx -t 1 -f out.bam in.bam
+ *   dlopen("libbwa_gpu_batch.so") and call bwa_bam_to_bam() in-process (bench.py; the library links libbwahost.so itself).
+ * No libc / zlib symbol is interposed -- only functions of the reference -- so both ways behave the same.
  */
-#define _GNU_SOURCE
-#include <dlfcn.h>
+#include "shim.h"
 #include <getopt.h>
-#include <pthread.h>
 #include <signal.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <sys/time.h>
 #include <unistd.h>
-#include <zlib.h>
-
-#include "bamlite.h"
-#include "bwtaln.h"
-#include "bwase.h"
-#include "bwape.h"
-#include "khash.h"
-#include "bgzf.h"
-#include "zmq.h" /* oracle/zmq_shim: the libzmq ABI the reference is built against */
-#include "bwa_gpu.h" /* after bwtaln.h: re-uses the reference's own types */
+#include "bwa_gpu_batch.h"
 
 KHASH_MAP_INIT_INT64(64, poslist_t) /* the position cache's type, as bam2bam.c:38 declares it */
 
 /* reference functions this driver calls that no header declares (bam2bam.c) */
 void pair_aln(bam_pair_t *p);
+void pair_posn(bam_pair_t *p);
 void pair_print_custom(gzFile f, bam_pair_t *p);
 int read_pair_custom(gzFile f, bam_pair_t *p);
 void pair_print_bam(BGZF *output, bam_pair_t *p);
 void bwa_update_bam1(bam1_t *out, const bntseq_t *bns, bwa_seq_t *p, const bwa_seq_t *mate, int mode, int max_top2);
 void bwa_cal_pac_pos_core(const bwt_t *forward_bwt, const bwt_t *reverse_bwt, bwa_seq_t *seq, const int max_mm, const float fnr);
 void bwa_aln2seq(int n_aln, const bwt_aln1_t *aln, bwa_seq_t *s);
-
-#define REAL(ret, name, ...) \
-	static ret (*real_##name)(__VA_ARGS__); \
-	if (!real_##name) real_##name = (ret (*)(__VA_ARGS__))dlsym(RTLD_NEXT, #name)
+void msg_init_from_pair(zmq_msg_t *m, bam_pair_t *p);
+void pair_init_from_msg(bam_pair_t *p, zmq_msg_t *m);
+void set_sockopts(void *socket);
+extern struct option longopts[]; /* bam2bam.c:40 */
 
 static void die(const char *what)
 {
@@ -81,90 +70,25 @@ static void die(const char *what)
 	abort(); /* the reference's convention on this path: xassert -> abort (utils.c:68-83) */
 }
 
-static double now(void)
-{
-	struct timeval tv;
-	gettimeofday(&tv, 0);
-	return tv.tv_sec + 1e-6 * tv.tv_usec;
-}
-
-/* ------------------------------------------------------------------ the reference's static globals, captured */
-static bwt_t *g_bwt[2];        /* bam2bam.c:88  (init_genome_index 855-856) */
-static const bntseq_t *g_bns;  /* bam2bam.c:89 */
-static ubyte_t *g_pac;         /* bam2bam.c:91 */
-static gap_opt_t *g_gap;       /* bam2bam.c:94 */
-static pe_opt_t *g_pe;         /* bam2bam.c:95 */
-static int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned; /* bam2bam.c:96-101, options 130 / 131 / 133 / 128 */
-static isize_info_t g_null_ii; /* bam2bam.c:106 */
-
-bwt_t *bwt_restore_bwt(const char *fn, int touch)
-{
-	REAL(bwt_t *, bwt_restore_bwt, const char *, int);
-	bwt_t *b = real_bwt_restore_bwt(fn, touch);
-	const size_t n = strlen(fn);
-	g_bwt[n >= 5 && strcmp(fn + n - 5, ".rbwt") == 0 ? 1 : 0] = b;
-	return b;
-}
-
-ubyte_t *bwt_restore_pac(const bntseq_t *bns, int touch)
-{
-	REAL(ubyte_t *, bwt_restore_pac, const bntseq_t *, int);
-	g_bns = bns;
-	g_pac = real_bwt_restore_pac(bns, touch);
-	return g_pac;
-}
-
-gap_opt_t *gap_init_opt(void)
-{
-	REAL(gap_opt_t *, gap_init_opt, void);
-	return g_gap = real_gap_init_opt();
-}
-
-pe_opt_t *bwa_init_pe_opt(void)
-{
-	REAL(pe_opt_t *, bwa_init_pe_opt, void);
-	return g_pe = real_bwa_init_pe_opt();
-}
-
-int getopt_long(int argc, char *const argv[], const char *optstring, const struct option *longopts, int *longindex)
-{
-	REAL(int, getopt_long, int, char *const *, const char *, const struct option *, int *);
-	const int c = real_getopt_long(argc, argv, optstring, longopts, longindex);
-	if (c == 128) g_only_aligned = 1;      /* bam2bam.c:1988 */
-	if (c == 130) g_broken_input = 1;      /* bam2bam.c:1991 */
-	if (c == 131) g_skip_duplicates = 1;
-	if (c == 133) g_drop_aligned = 1;
-	return c;
-}
-
-static int unique_rec(const bam_pair_t *p) /* bam2bam.c:595-606 */
-{
-	int i;
-	if (!g_skip_duplicates) return 1;
-	if (p->kind == eof_marker) return 0;
-	for (i = 0; i != (int)p->kind; ++i)
-		if (p->bam_rec[i].core.flag & SAM_FDP) return 0;
-	return 1;
-}
-
+#define now shim_now
 
 /* ------------------------------------------------------------------ host threads
- * With the hot path on the device, what is left of a bam2bam run is per-record host work of the reference
- * (bam1_to_seq, bwa_refine_gapped, bwa_update_bam1, the temp-file codec, deflate).  The reference itself runs these
- * functions concurrently in its worker threads (run_worker_thread, bam2bam.c:1387), so they are re-entrant; the shim
- * spreads each such phase of a batch over BWAGPU_SHIM_THREADS threads (default: the host's cores, at most 32).
- * Everything order-sensitive (drand48 in bwa_aln2seq_core, the position cache, isize statistics) stays serial. */
-typedef void (*pf_fn)(size_t i, void *ctx);
+ * With the hot path on the device, what is left of a bam2bam run is per-record host work of the reference (bam1_to_seq,
+ * pairing, bwa_paired_sw1, bwa_refine_gapped, bwa_update_bam1, the intermediate-record codec, deflate).  The reference
+ * itself runs these functions concurrently in its worker threads (run_worker_thread, bam2bam.c:1387), so they are
+ * re-entrant; the shim spreads each such phase of a batch over BWAGPU_SHIM_THREADS threads (default: the host's cores, at
+ * most 64).  Everything order-sensitive (drand48 in bwa_aln2seq_core, the position cache, isize statistics) stays serial. */
 typedef struct { size_t n, grain; size_t next; pf_fn fn; void *ctx; } pf_job_t;
+#define MAX_THREADS 64
 
-static int shim_threads(void)
+int shim_threads(void)
 {
 	static int n;
 	if (!n) {
 		const char *e = getenv("BWAGPU_SHIM_THREADS");
 		n = e ? atoi(e) : (int)sysconf(_SC_NPROCESSORS_ONLN);
 		if (n < 1) n = 1;
-		if (n > 32) n = 32;
+		if (n > MAX_THREADS) n = MAX_THREADS;
 	}
 	return n;
 }
@@ -182,10 +106,10 @@ static void *pf_worker(void *arg)
 	return 0;
 }
 
-static void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
+void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
 {
 	pf_job_t j = {n, grain ? grain : 1, 0, fn, ctx};
-	pthread_t th[32];
+	pthread_t th[MAX_THREADS];
 	int t, nt = shim_threads();
 	if ((size_t)nt > (n + j.grain - 1) / j.grain) nt = (int)((n + j.grain - 1) / j.grain);
 	if (nt <= 1) { pf_worker(&j); return; }
@@ -194,147 +118,263 @@ static void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
 	for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
 }
 
-
-/* ------------------------------------------------------------------ input BAM: inflate on a side thread
- * bamlite reads the input with gzread (bamlite.h:8-11), three small calls per record, on the thread that also parses
- * and allocates the records; inflate is about half of that thread's time and it is the slowest stage of pass 1.  The
- * first file opened with gzopen(.., "r") -- the input BAM (bwa_bam_open) -- gets a read-ahead thread that gzread()s it in
- * 256 KB pieces into a ring; the interposed gzread serves bamlite's calls from the ring.  Every other gzFile (the
- * temporary file) goes straight to zlib.  BWAGPU_READAHEAD=0 turns it off. */
-#define RA_CAP ((size_t)16 << 20)
-#define RA_PIECE ((size_t)256 << 10)
-typedef struct {
-	gzFile real;
-	pthread_t th;
-	uint8_t *ring;
-	volatile size_t head, tail; /* bytes produced / consumed so far */
-	volatile int eof, stop;
-} readahead_t;
-static readahead_t g_ra;
-
-static void *ra_main(void *arg)
+int slice_count(size_t n, size_t min_per_slice)
 {
-	REAL(int, gzread, gzFile, voidp, unsigned);
-	uint8_t *piece = (uint8_t *)malloc(RA_PIECE);
-	(void)arg;
-	while (!g_ra.stop) {
-		int got, done = 0;
-		while (!g_ra.stop && RA_CAP - (g_ra.head - __atomic_load_n(&g_ra.tail, __ATOMIC_ACQUIRE)) < RA_PIECE) usleep(100);
-		if (g_ra.stop) break;
-		got = real_gzread(g_ra.real, piece, (unsigned)RA_PIECE);
-		if (got <= 0) break;
-		while (done < got) {
-			const size_t at = (g_ra.head + (size_t)done) % RA_CAP;
-			const size_t run = RA_CAP - at < (size_t)(got - done) ? RA_CAP - at : (size_t)(got - done);
-			memcpy(g_ra.ring + at, piece + done, run);
-			done += (int)run;
-		}
-		__atomic_store_n(&g_ra.head, g_ra.head + (size_t)got, __ATOMIC_RELEASE);
-	}
-	__atomic_store_n(&g_ra.eof, 1, __ATOMIC_RELEASE);
-	free(piece);
+	size_t nt = (size_t)shim_threads();
+	if (min_per_slice < 1) min_per_slice = 1;
+	if (nt > (n + min_per_slice - 1) / min_per_slice) nt = (n + min_per_slice - 1) / min_per_slice;
+	return nt < 1 ? 1 : (int)nt;
+}
+
+typedef struct { ps_fn fn; void *ctx; size_t n; int nt, s; } ps_arg_t;
+static void *ps_worker(void *arg)
+{
+	ps_arg_t *a = (ps_arg_t *)arg;
+	a->fn(a->s, a->n * (size_t)a->s / (size_t)a->nt, a->n * (size_t)(a->s + 1) / (size_t)a->nt, a->ctx);
 	return 0;
 }
 
-gzFile gzopen(const char *path, const char *mode)
+int parallel_slices(size_t n, size_t min_per_slice, ps_fn fn, void *ctx)
 {
-	REAL(gzFile, gzopen, const char *, const char *);
-	gzFile f = real_gzopen(path, mode);
-	const char *e = getenv("BWAGPU_READAHEAD");
-	if (f && !g_ra.real && mode && mode[0] == 'r' && !(e && atoi(e) == 0)) {
-		memset(&g_ra, 0, sizeof(g_ra));
-		g_ra.ring = (uint8_t *)malloc(RA_CAP);
-		if (g_ra.ring) {
-			g_ra.real = f;
-			pthread_create(&g_ra.th, 0, ra_main, 0);
-		}
-	}
-	return f;
+	const int nt = slice_count(n, min_per_slice);
+	ps_arg_t a[MAX_THREADS];
+	pthread_t th[MAX_THREADS];
+	int s;
+	for (s = 0; s < nt; ++s) { a[s].fn = fn; a[s].ctx = ctx; a[s].n = n; a[s].nt = nt; a[s].s = s; }
+	for (s = 1; s < nt; ++s) pthread_create(&th[s], 0, ps_worker, &a[s]);
+	ps_worker(&a[0]);
+	for (s = 1; s < nt; ++s) pthread_join(th[s], 0);
+	return nt;
 }
 
-int gzread(gzFile f, voidp buf, unsigned len)
+/* ------------------------------------------------------------------ the reference's static globals, captured */
+static bwt_t *g_bwt[2];        /* bam2bam.c:88  (init_genome_index 855-856) */
+static const bntseq_t *g_bns;  /* bam2bam.c:89 */
+static ubyte_t *g_pac;         /* bam2bam.c:91 */
+static gap_opt_t *g_gap;       /* bam2bam.c:94 */
+static pe_opt_t *g_pe;         /* bam2bam.c:95 */
+int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned; /* bam2bam.c:96-101, options 130 / 131 / 133 / 128 */
+static isize_info_t g_null_ii; /* bam2bam.c:106 */
+static bwa_gpu_batch_report_t g_rep; /* the run in progress / the last run (bwa_gpu_batch.h) */
+
+/* The index of a long-lived host process (bench.py runs bam2bam several times in one process): with keep_index on, the
+ * loaders hand back what an earlier run loaded from the same files, the matching destroy calls leave it alone, and the
+ * device copy stays valid.  Off (the default), every run loads and frees like the reference. */
+static int g_keep;
+static struct { char *fn; bwt_t *b; } g_kept_bwt[2];
+static struct { ubyte_t *pac; int64_t l_pac; } g_kept_pac;
+static int g_ready; /* the device holds g_bwt / g_pac */
+static bwt_t *g_dev_bwt[2];
+static ubyte_t *g_dev_pac;
+
+void bwa_gpu_batch_keep_index(int on) { g_keep = on != 0; }
+
+static int is_kept_bwt(const bwt_t *b) { return b && (b == g_kept_bwt[0].b || b == g_kept_bwt[1].b); }
+
+bwt_t *bwt_restore_bwt(const char *fn, int touch)
 {
-	REAL(int, gzread, gzFile, voidp, unsigned);
-	unsigned done = 0;
-	if (!g_ra.real || f != g_ra.real) return real_gzread(f, buf, len);
-	while (done < len) {
-		size_t avail = __atomic_load_n(&g_ra.head, __ATOMIC_ACQUIRE) - g_ra.tail;
-		if (avail == 0) {
-			if (__atomic_load_n(&g_ra.eof, __ATOMIC_ACQUIRE) && __atomic_load_n(&g_ra.head, __ATOMIC_ACQUIRE) == g_ra.tail) break;
-			usleep(50);
-			continue;
-		}
-		{
-			const size_t at = g_ra.tail % RA_CAP;
-			size_t run = avail < (size_t)(len - done) ? avail : (size_t)(len - done);
-			if (RA_CAP - at < run) run = RA_CAP - at;
-			memcpy((uint8_t *)buf + done, g_ra.ring + at, run);
-			done += (unsigned)run;
-			__atomic_store_n(&g_ra.tail, g_ra.tail + run, __ATOMIC_RELEASE);
+	REAL(bwt_t *, bwt_restore_bwt, const char *, int);
+	const size_t n = strlen(fn);
+	const int s = n >= 5 && strcmp(fn + n - 5, ".rbwt") == 0 ? 1 : 0;
+	const double t0 = now();
+	bwt_t *b;
+	if (g_keep && g_kept_bwt[s].b && strcmp(g_kept_bwt[s].fn, fn) == 0) b = g_kept_bwt[s].b;
+	else {
+		b = real_bwt_restore_bwt(fn, touch);
+		if (g_keep) {
+			if (g_kept_bwt[s].b) { /* another genome: the old one goes */
+				REAL(void, bwt_destroy, bwt_t *);
+				bwt_t *old = g_kept_bwt[s].b;
+				g_kept_bwt[s].b = 0;
+				real_bwt_destroy(old);
+				free(g_kept_bwt[s].fn);
+			}
+			g_kept_bwt[s].b = b; g_kept_bwt[s].fn = strdup(fn);
+			if (g_kept_pac.pac) { free(g_kept_pac.pac); g_kept_pac.pac = 0; }
 		}
 	}
-	return (int)done;
+	g_bwt[s] = b;
+	g_rep.index_load_s += now() - t0;
+	return b;
 }
 
-int gzclose(gzFile f)
+void bwt_restore_sa(const char *fn, bwt_t *bwt, int touch)
 {
-	REAL(int, gzclose, gzFile);
-	if (g_ra.real && f == g_ra.real) {
-		g_ra.stop = 1;
-		pthread_join(g_ra.th, 0);
-		free(g_ra.ring);
-		g_ra.real = 0;
+	REAL(void, bwt_restore_sa, const char *, bwt_t *, int);
+	const double t0 = now();
+	if (!(is_kept_bwt(bwt) && bwt->sa)) real_bwt_restore_sa(fn, bwt, touch);
+	g_rep.index_load_s += now() - t0;
+}
+
+ubyte_t *bwt_restore_pac(const bntseq_t *bns, int touch)
+{
+	REAL(ubyte_t *, bwt_restore_pac, const bntseq_t *, int);
+	const double t0 = now();
+	g_bns = bns;
+	if (g_keep && g_kept_pac.pac && g_kept_pac.l_pac == (int64_t)bns->l_pac) g_pac = g_kept_pac.pac;
+	else {
+		g_pac = real_bwt_restore_pac(bns, touch);
+		if (g_keep) { g_kept_pac.pac = g_pac; g_kept_pac.l_pac = (int64_t)bns->l_pac; }
 	}
-	return real_gzclose(f);
+	g_rep.index_load_s += now() - t0;
+	return g_pac;
+}
+
+void bwt_destroy(bwt_t *bwt)
+{
+	REAL(void, bwt_destroy, bwt_t *);
+	if (is_kept_bwt(bwt)) return;
+	if (bwt && (bwt == g_dev_bwt[0] || bwt == g_dev_bwt[1])) g_ready = 0; /* the device copy no longer has a host twin to be matched against */
+	real_bwt_destroy(bwt);
+}
+
+void bwt_destroy_pac(ubyte_t *pac, const bntseq_t *bns)
+{
+	REAL(void, bwt_destroy_pac, ubyte_t *, const bntseq_t *);
+	if (pac && pac == g_kept_pac.pac) return;
+	real_bwt_destroy_pac(pac, bns);
+}
+
+void bwa_gpu_batch_drop_index(void)
+{
+	REAL(void, bwt_destroy, bwt_t *);
+	int s;
+	for (s = 0; s < 2; ++s)
+		if (g_kept_bwt[s].b) {
+			bwt_t *b = g_kept_bwt[s].b;
+			g_kept_bwt[s].b = 0;
+			real_bwt_destroy(b);
+			free(g_kept_bwt[s].fn); g_kept_bwt[s].fn = 0;
+		}
+	free(g_kept_pac.pac); g_kept_pac.pac = 0;
+	if (g_ready) { bwa_gpu_destroy(); g_ready = 0; }
+}
+
+gap_opt_t *gap_init_opt(void)
+{
+	REAL(gap_opt_t *, gap_init_opt, void);
+	return g_gap = real_gap_init_opt();
+}
+
+pe_opt_t *bwa_init_pe_opt(void)
+{
+	REAL(pe_opt_t *, bwa_init_pe_opt, void);
+	return g_pe = real_bwa_init_pe_opt();
+}
+
+/* bwa_bam_to_bam (bam2bam.c:1942): the reference keeps four of its long options in statics nobody can see; parse the same
+ * command line with the reference's own option table first, then hand over.  Also the clock of the whole run. */
+int bwa_bam_to_bam(int argc, char *argv[], char *version)
+{
+	REAL(int, bwa_bam_to_bam, int, char **, char *);
+	char **av = (char **)malloc(((size_t)argc + 1) * sizeof(char *));
+	int c, rc;
+	double t0;
+	memcpy(av, argv, (size_t)argc * sizeof(char *));
+	av[argc] = 0;
+	g_only_aligned = g_broken_input = g_skip_duplicates = g_drop_aligned = 0;
+	memset(&g_rep, 0, sizeof(g_rep));
+	optind = 0; opterr = 0; /* glibc: a full re-initialisation, quietly -- the real parse below reports what is wrong */
+	while ((c = getopt_long(argc, av, "g:n:o:e:i:d:l:k:LR:m:t:NM:O:E:q:f:C:D:a:sc:h:H:Ap:0:1:2:", longopts, 0)) >= 0) {
+		if (c == 128) g_only_aligned = 1;      /* bam2bam.c:1988 */
+		if (c == 130) g_broken_input = 1;      /* bam2bam.c:1991 */
+		if (c == 131) g_skip_duplicates = 1;
+		if (c == 133) g_drop_aligned = 1;
+	}
+	free(av);
+	optind = 0; opterr = 1;
+	t0 = now();
+	rc = real_bwa_bam_to_bam(argc, argv, version);
+	g_rep.wall_s = now() - t0;
+	g_rep.inflate_cpu_s = fastin_inflate_seconds();
+	return rc;
+}
+
+/* bwa_bam_open (bwaseqio.c:22-64): note which file the records will come from (shim_io.c inflates its blocks in
+ * parallel); `.sai` side inputs would put alignments made elsewhere in place of the device search: refused. */
+bwa_seqio_t *bwa_bam_open(const char *fn, int which, char **saif, gap_opt_t *o0, bam_header_t **hh)
+{
+	REAL(bwa_seqio_t *, bwa_bam_open, const char *, int, char **, gap_opt_t *, bam_header_t **);
+	if (saif && (saif[0] || saif[1] || saif[2])) {
+		fprintf(stderr, "[bwa_gpu_batch] .sai inputs (-0/-1/-2) bypass the alignment this library exists to run on the device; "
+		                "they are not supported here (run the plain reference for them)\n");
+		exit(1);
+	}
+	fastin_set_path(fn);
+	return real_bwa_bam_open(fn, which, saif, o0, hh);
+}
+
+void bwa_seq_close(bwa_seqio_t *bs)
+{
+	REAL(void, bwa_seq_close, bwa_seqio_t *);
+	fastin_close();
+	real_bwa_seq_close(bs);
+}
+
+static int unique_rec(const bam_pair_t *p) /* bam2bam.c:595-606 */
+{
+	int i;
+	if (!g_skip_duplicates) return 1;
+	if (p->kind == eof_marker) return 0;
+	for (i = 0; i != (int)p->kind; ++i)
+		if (p->bam_rec[i].core.flag & SAM_FDP) return 0;
+	return 1;
 }
 
 /* ------------------------------------------------------------------ device context */
-static int g_ready;
-static long g_calls_aln, g_calls_sa, g_calls_sw, g_reads_aln, g_q_sa, g_jobs_sw;
-static double g_t_aln, g_t_sa, g_t_sw;
+static pthread_mutex_t g_rep_mu = PTHREAD_MUTEX_INITIALIZER;
+#define REP_ADD(calls_f, units_f, secs_f, units, t0) do { pthread_mutex_lock(&g_rep_mu); ++g_rep.calls_f; g_rep.units_f += (int64_t)(units); \
+		g_rep.secs_f += now() - (t0); pthread_mutex_unlock(&g_rep_mu); } while (0)
 
 static void report(void)
 {
 	fprintf(stderr, "[bwa_gpu_batch] device calls: cal_sa_reads_gap=%ld (%ld reads, %.2f s)  cal_pac_pos=%ld (%ld queries, %.2f s)  "
-	                "mate_sw_path=%ld (%ld jobs, %.2f s)\n", g_calls_aln, g_reads_aln, g_t_aln, g_calls_sa, g_q_sa, g_t_sa,
-	        g_calls_sw, g_jobs_sw, g_t_sw);
+	                "mate_sw_path=%ld (%ld jobs, %.2f s)  global_align=%ld (%ld jobs, %.2f s)\n", (long)g_rep.calls_aln, (long)g_rep.reads_aln,
+	        g_rep.dev_aln_s, (long)g_rep.calls_sa, (long)g_rep.q_sa, g_rep.dev_sa_s, (long)g_rep.calls_sw, (long)g_rep.jobs_sw, g_rep.dev_sw_s,
+	        (long)g_rep.calls_ga, (long)g_rep.jobs_ga, g_rep.dev_ga_s);
 }
-
-static void ensure_gpu(void);
-static void *ensure_gpu_thread(void *arg) { (void)arg; ensure_gpu(); return 0; }
 
 static void ensure_gpu(void)
 {
-	if (g_ready) return;
+	static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+	static int exit_hook;
+	const double t0 = now();
+	pthread_mutex_lock(&mu);
+	if (g_ready && g_dev_bwt[0] == g_bwt[0] && g_dev_bwt[1] == g_bwt[1] && g_dev_pac == g_pac) { pthread_mutex_unlock(&mu); return; }
 	if (!g_bwt[0] || !g_bwt[1] || !g_bns || !g_pac || !g_gap || !g_pe) {
 		fprintf(stderr, "[bwa_gpu_batch] the reference's index/option globals were not seen being loaded\n");
 		abort();
 	}
 	{
-		const char *e = getenv("BWAGPU_NDEV");
-		int ids[16], n = e ? atoi(e) : 1, i;
+		const char *e = getenv("BWAGPU_NDEV"), *f = getenv("BWAGPU_DEVICE");
+		int ids[16], n = e ? atoi(e) : 1, first = f ? atoi(f) : 0, i;
 		if (n < 1) n = 1;
 		if (n > 16) n = 16;
-		for (i = 0; i < n; ++i) ids[i] = i;
+		for (i = 0; i < n; ++i) ids[i] = first + i;
 		if (bwa_gpu_init(n, ids)) die("bwa_gpu_init");
 	}
 	if (bwa_gpu_load_index(g_bwt, g_pac, g_bns->l_pac)) die("bwa_gpu_load_index");
+	g_dev_bwt[0] = g_bwt[0]; g_dev_bwt[1] = g_bwt[1]; g_dev_pac = g_pac;
 	g_ready = 1;
-	atexit(report);
+	if (!exit_hook) { exit_hook = 1; atexit(report); }
+	g_rep.device_init_s += now() - t0;
+	pthread_mutex_unlock(&mu);
 }
+static void *ensure_gpu_thread(void *arg) { (void)arg; ensure_gpu(); return 0; }
 
 static size_t batch_records(void)
 {
 	const char *e = getenv("BWAGPU_BATCH_RECORDS");
 	const long v = e ? atol(e) : 0;
-	return v > 0 ? (size_t)v : (size_t)1 << 18;
+	return v > 0 ? (size_t)v : (size_t)1 << 17;
 }
 
-/* ------------------------------------------------------------------ bwt_sa: real / replay */
-typedef struct { size_t n, m; bwtint_t *k; uint8_t *which; bwtint_t *out; } saq_t;
-static saq_t g_q;
-static int g_sa_replay;
-static size_t g_sa_pos;
+/* ------------------------------------------------------------------ bwt_sa: real / replay
+ * A queue of SA rows whose coordinates are wanted, one device call, then the reference's own code run again with bwt_sa
+ * answering from the results in the same order (per thread: the replaying thread owns the cursor). */
+typedef struct { size_t n, m; bwtint_t *k; uint8_t *which; bwtint_t *out; size_t m_out; } saq_t;
+static __thread const saq_t *t_sa_q;  /* non-NULL: bwt_sa replays from it */
+static __thread size_t t_sa_pos;
 
 static void saq_push(saq_t *q, bwtint_t k, int forward)
 {
@@ -349,52 +389,71 @@ static void saq_push(saq_t *q, bwtint_t k, int forward)
 static void saq_run(saq_t *q)
 {
 	const double t0 = now();
-	q->out = (bwtint_t *)realloc(q->out, (q->n + 1) * sizeof(bwtint_t));
+	if (q->n + 1 > q->m_out) { q->m_out = q->n + 1 + q->n / 4; q->out = (bwtint_t *)realloc(q->out, q->m_out * sizeof(bwtint_t)); }
 	if (q->n && bwa_gpu_cal_pac_pos((int64_t)q->n, q->k, q->which, q->out)) die("bwa_gpu_cal_pac_pos");
-	++g_calls_sa; g_q_sa += (long)q->n; g_t_sa += now() - t0;
-	g_sa_pos = 0;
+	REP_ADD(calls_sa, q_sa, dev_sa_s, q->n, t0);
 }
 
-static bwtint_t saq_next(saq_t *q, const bwt_t *bwt, bwtint_t k)
-{
-	if (g_sa_pos >= q->n || q->k[g_sa_pos] != k || q->which[g_sa_pos] != (uint8_t)(bwt == g_bwt[0])) {
-		fprintf(stderr, "[bwa_gpu_batch] bwt_sa replay out of step at query %zu\n", g_sa_pos);
-		abort();
-	}
-	return q->out[g_sa_pos++];
-}
+static void saq_free(saq_t *q) { free(q->k); free(q->which); free(q->out); memset(q, 0, sizeof(*q)); }
 
 bwtint_t bwt_sa(const bwt_t *bwt, bwtint_t k)
 {
 	REAL(bwtint_t, bwt_sa, const bwt_t *, bwtint_t);
-	if (g_sa_replay) return saq_next(&g_q, bwt, k);
-	return real_bwt_sa(bwt, k); /* index construction, per-record fallbacks */
+	if (t_sa_q) {
+		const saq_t *q = t_sa_q;
+		if (t_sa_pos >= q->n || q->k[t_sa_pos] != k || q->which[t_sa_pos] != (uint8_t)(bwt == g_bwt[0])) {
+			fprintf(stderr, "[bwa_gpu_batch] bwt_sa replay out of step at query %zu\n", t_sa_pos);
+			abort();
+		}
+		return q->out[t_sa_pos++];
+	}
+	return real_bwt_sa(bwt, k); /* index construction and other uses outside the batched loops */
 }
 
-/* ------------------------------------------------------------------ aln_local_core: real / record / replay */
-enum { SW_REAL = 0, SW_RECORD = 1, SW_REPLAY = 2 };
-static int g_sw_mode;
-static int64_t g_sw_beg; /* *beg of the bwa_sw_core call in progress */
-typedef struct { size_t n, m; bwa_gpu_sw_job_t *job; size_t *seq_off; size_t sn, sm; ubyte_t *seqs; bwa_gpu_path_res_t *res; const bwa_cigar_t *pool; } swq_t;
-static swq_t g_sw;
-static size_t g_sw_pos;
+/* ------------------------------------------------------------------ aln_local_core: real / record / replay (per thread) */
+enum { RR_REAL = 0, RR_RECORD = 1, RR_REPLAY = 2 };
+typedef struct { size_t n, m; bwa_gpu_sw_job_t *job; size_t *seq_off; size_t sn, sm; ubyte_t *seqs; } swq_t;
+static __thread int t_sw_mode;
+static __thread int64_t t_sw_beg;       /* *beg of the bwa_sw_core call in progress */
+static __thread swq_t *t_swq;           /* RECORD: where the jobs go */
+static __thread const bwa_gpu_sw_job_t *t_sw_jobs; /* REPLAY: this thread's part of the batch's jobs / results */
+static __thread const bwa_gpu_path_res_t *t_sw_res;
+static __thread const bwa_cigar_t *t_sw_pool;
+static __thread size_t t_sw_pos, t_sw_n;
 
 bwa_cigar_t *bwa_sw_core(bwtint_t l_pac, const ubyte_t *pacseq, int len, const ubyte_t *seq, int64_t *beg, int reglen,
                          int *n_cigar, uint32_t *cnt)
 {
 	REAL(bwa_cigar_t *, bwa_sw_core, bwtint_t, const ubyte_t *, int, const ubyte_t *, int64_t *, int, int *, uint32_t *);
-	g_sw_beg = *beg; /* the window the reference is about to unpack (bwape.c:447-450) */
+	t_sw_beg = *beg; /* the window the reference is about to unpack (bwape.c:447-450) */
 	return real_bwa_sw_core(l_pac, pacseq, len, seq, beg, reglen, n_cigar, cnt);
+}
+
+/* path_t[] as aln_global_core's backtrace leaves it (stdaln.c:496-512): path[0] = the end cell, path[path_len-1] = the
+ * start cell; an element's ctype says how its cell was entered.  Rebuilt from the device's CIGAR and start cell. */
+static int path_from_cigar(const bwa_cigar_t *cg, int n_cigar, int start_i, int start_j, path_t *path)
+{
+	int n = 0, c, t, i = start_i, j = start_j;
+	for (c = 0; c < n_cigar; ++c) n += cg[c] & 0x3fff;
+	for (c = 0, t = n - 1; c < n_cigar; ++c) {
+		const int op = cg[c] >> 14, run = cg[c] & 0x3fff;
+		int u;
+		for (u = 0; u < run; ++u, --t) {
+			if (t != n - 1) { if (op != FROM_I) ++i; if (op != FROM_D) ++j; }
+			path[t].i = i; path[t].j = j; path[t].ctype = (unsigned char)op;
+		}
+	}
+	return n;
 }
 
 int aln_local_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2, const AlnParam *ap, path_t *path, int *path_len,
                    int thres, int *subo)
 {
 	REAL(int, aln_local_core, unsigned char *, int, unsigned char *, int, const AlnParam *, path_t *, int *, int, int *);
-	if (g_sw_mode == SW_RECORD) {
-		swq_t *q = &g_sw;
+	if (t_sw_mode == RR_RECORD) {
+		swq_t *q = t_swq;
 		if (q->n == q->m) {
-			q->m = q->m ? q->m << 1 : 1 << 12;
+			q->m = q->m ? q->m << 1 : 1 << 10;
 			q->job = (bwa_gpu_sw_job_t *)realloc(q->job, q->m * sizeof(*q->job));
 			q->seq_off = (size_t *)realloc(q->seq_off, q->m * sizeof(size_t));
 		}
@@ -403,37 +462,20 @@ int aln_local_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2,
 			q->seqs = (ubyte_t *)realloc(q->seqs, q->sm);
 		}
 		memcpy(q->seqs + q->sn, seq2, (size_t)len2); /* bwa_paired_sw1 un-reverses the read right after the call */
-		q->job[q->n].beg = g_sw_beg; q->job[q->n].reglen = len1; q->job[q->n].len = len2; q->job[q->n].seq = 0;
+		q->job[q->n].beg = t_sw_beg; q->job[q->n].reglen = len1; q->job[q->n].len = len2; q->job[q->n].seq = 0;
 		q->seq_off[q->n] = q->sn; q->sn += (size_t)len2; ++q->n;
 		return -1; /* "no alignment": bwa_sw_core returns 0 and bwa_paired_sw1 leaves both reads untouched (bwape.c:457-460) */
 	}
-	if (g_sw_mode == SW_REPLAY) {
-		swq_t *q = &g_sw;
+	if (t_sw_mode == RR_REPLAY) {
 		const bwa_gpu_path_res_t *r;
-		const bwa_cigar_t *cg;
-		int n = 0, c, t, i, j;
-		if (g_sw_pos >= q->n || q->job[g_sw_pos].reglen != len1 || q->job[g_sw_pos].len != len2) {
-			fprintf(stderr, "[bwa_gpu_batch] aln_local_core replay out of step at job %zu\n", g_sw_pos);
+		if (t_sw_pos >= t_sw_n || t_sw_jobs[t_sw_pos].reglen != len1 || t_sw_jobs[t_sw_pos].len != len2) {
+			fprintf(stderr, "[bwa_gpu_batch] aln_local_core replay out of step at job %zu\n", t_sw_pos);
 			abort();
 		}
-		r = &q->res[g_sw_pos++];
+		r = &t_sw_res[t_sw_pos++];
 		if (r->score < 0) return r->score;
-		/* path_t[] as aln_global_core's backtrace leaves it (stdaln.c:496-512, shifted at 741-744): path[0] = the end
-		 * cell, path[path_len-1] = the start cell; an element's ctype says how its cell was entered */
-		cg = q->pool + r->cigar_off;
-		for (c = 0; c < r->n_cigar; ++c) n += cg[c] & 0x3fff;
-		*path_len = n;
-		if (n == 0) return r->score;
-		i = r->start_i; j = r->start_j;
-		for (c = 0, t = n - 1; c < r->n_cigar; ++c) {
-			const int op = cg[c] >> 14, run = cg[c] & 0x3fff;
-			int u;
-			for (u = 0; u < run; ++u, --t) {
-				if (t != n - 1) { if (op != FROM_I) ++i; if (op != FROM_D) ++j; }
-				path[t].i = i; path[t].j = j; path[t].ctype = (unsigned char)op;
-			}
-		}
-		if (path[0].i != r->end_i || path[0].j != r->end_j) {
+		*path_len = path_from_cigar(t_sw_pool + r->cigar_off, r->n_cigar, r->start_i, r->start_j, path);
+		if (*path_len && (path[0].i != r->end_i || path[0].j != r->end_j)) {
 			fprintf(stderr, "[bwa_gpu_batch] device path does not end at its end cell (%d,%d) vs (%d,%d)\n", path[0].i, path[0].j, r->end_i, r->end_j);
 			abort();
 		}
@@ -443,98 +485,90 @@ int aln_local_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2,
 	return real_aln_local_core(seq1, len1, seq2, len2, ap, path, path_len, thres, subo);
 }
 
-static void swq_run(swq_t *q)
+/* ------------------------------------------------------------------ aln_global_core inside bwa_refine_gapped: real / record / replay
+ * refine_gapped_core (bwase.c:189-237, static) unpacks its reference window and calls aln_global_core (bwase.c:212).
+ * RECORD runs bwa_refine_gapped on a scratch copy of the read with aln_global_core noting both sequences (and bwa_cal_md1
+ * switched off: the copy's MD is not wanted); REPLAY is the real run, aln_global_core answering with the device's path. */
+typedef struct { size_t n, m; int *len1, *len2; size_t *off1, *off2; size_t bn, bm; ubyte_t *bytes; } gaq_t;
+static __thread int t_ga_mode;
+static __thread gaq_t *t_gaq;
+static __thread const bwa_gpu_path_res_t *t_ga_res;
+static __thread const bwa_cigar_t *t_ga_pool;
+static __thread const int *t_ga_len1, *t_ga_len2;
+static __thread size_t t_ga_pos, t_ga_n;
+
+static int is_bwa_param(const AlnParam *ap)
 {
-	size_t i;
-	const double t0 = now();
-	for (i = 0; i < q->n; ++i) q->job[i].seq = q->seqs + q->seq_off[i];
-	q->res = (bwa_gpu_path_res_t *)realloc(q->res, (q->n + 1) * sizeof(*q->res));
-	q->pool = 0;
-	if (q->n && bwa_gpu_mate_sw_path((int)q->n, q->job, q->res, &q->pool)) die("bwa_gpu_mate_sw_path");
-	++g_calls_sw; g_jobs_sw += (long)q->n; g_t_sw += now() - t0;
-	g_sw_pos = 0;
+	return ap->gap_open == aln_param_bwa.gap_open && ap->gap_ext == aln_param_bwa.gap_ext && ap->matrix == aln_param_bwa.matrix &&
+	       ap->row == aln_param_bwa.row && ap->band_width == aln_param_bwa.band_width && ap->gap_end == aln_param_bwa.gap_end;
 }
 
-
-/* ------------------------------------------------------------------ the intermediate file, kept in memory
- * Pass 1 hands its records to pass 2 through a gzip'ed temporary file in the reference (pair_print_custom /
- * read_pair_custom, bam2bam.c:1099-1137: the 0MQ message encoding of a record, length-prefixed).  Deflate and inflate of
- * that file were 6 of the 21 seconds of a 2 M-read run once the hot path was on the device.  The shim keeps the SAME
- * encoded messages (the reference's msg_init_from_pair / pair_init_from_msg, so a record makes the same round trip) in
- * memory, up to BWAGPU_MEMTEMP_MB (default: a quarter of physical memory, at most 64 GB), and spills whatever comes
- * after that to the reference's temporary file in the reference's format.  Encoding and decoding run on the host threads. */
-void msg_init_from_pair(zmq_msg_t *m, bam_pair_t *p);
-void pair_init_from_msg(bam_pair_t *p, zmq_msg_t *m);
-
-#define MT_CHUNK ((size_t)64 << 20)
-typedef struct {
-	uint8_t **chunk; size_t n_chunk, m_chunk, used;
-	uint8_t **rec; uint32_t *len; size_t n_rec, m_rec, rd;
-	size_t bytes, cap;
-	int spilled;
-} memtemp_t;
-static memtemp_t g_mt;
-
-static size_t memtemp_cap(void)
+int aln_global_core(unsigned char *seq1, int len1, unsigned char *seq2, int len2, const AlnParam *ap, path_t *path, int *path_len)
 {
-	const char *e = getenv("BWAGPU_MEMTEMP_MB"), *eb = getenv("BWAGPU_MEMTEMP_BYTES");
-	size_t cap;
-	if (eb) return (size_t)atoll(eb);
-	if (e) return (size_t)atoll(e) << 20;
-	cap = (size_t)sysconf(_SC_PHYS_PAGES) * (size_t)sysconf(_SC_PAGESIZE) / 4;
-	return cap > ((size_t)64 << 30) ? (size_t)64 << 30 : cap;
-}
-
-static int memtemp_put(const void *data, uint32_t len)
-{
-	memtemp_t *t = &g_mt;
-	if (t->spilled || t->bytes + len > t->cap || len > MT_CHUNK) { t->spilled = 1; return 0; }
-	if (t->n_chunk == 0 || t->used + len > MT_CHUNK) {
-		if (t->n_chunk == t->m_chunk) { t->m_chunk = t->m_chunk ? t->m_chunk << 1 : 16; t->chunk = (uint8_t **)realloc(t->chunk, t->m_chunk * sizeof(*t->chunk)); }
-		t->chunk[t->n_chunk] = (uint8_t *)malloc(MT_CHUNK);
-		if (!t->chunk[t->n_chunk]) { t->spilled = 1; return 0; }
-		++t->n_chunk; t->used = 0;
+	REAL(int, aln_global_core, unsigned char *, int, unsigned char *, int, const AlnParam *, path_t *, int *);
+	if (t_ga_mode == RR_RECORD && is_bwa_param(ap) && len1 > 0 && len2 > 0) {
+		gaq_t *q = t_gaq;
+		if (q->n == q->m) {
+			q->m = q->m ? q->m << 1 : 1 << 10;
+			q->len1 = (int *)realloc(q->len1, q->m * sizeof(int)); q->len2 = (int *)realloc(q->len2, q->m * sizeof(int));
+			q->off1 = (size_t *)realloc(q->off1, q->m * sizeof(size_t)); q->off2 = (size_t *)realloc(q->off2, q->m * sizeof(size_t));
+		}
+		if (q->bn + (size_t)len1 + (size_t)len2 > q->bm) {
+			q->bm = (q->bn + (size_t)len1 + (size_t)len2) * 2 + 4096;
+			q->bytes = (ubyte_t *)realloc(q->bytes, q->bm);
+		}
+		q->len1[q->n] = len1; q->len2[q->n] = len2;
+		q->off1[q->n] = q->bn; memcpy(q->bytes + q->bn, seq1, (size_t)len1); q->bn += (size_t)len1;
+		q->off2[q->n] = q->bn; memcpy(q->bytes + q->bn, seq2, (size_t)len2); q->bn += (size_t)len2;
+		++q->n;
+		path[0].i = len1; path[0].j = len2; path[0].ctype = FROM_M; /* a one-cell path keeps refine_gapped_core's CIGAR fix-ups in bounds */
+		*path_len = 1;
+		return 0;
 	}
-	if (t->n_rec == t->m_rec) {
-		t->m_rec = t->m_rec ? t->m_rec << 1 : 1 << 20;
-		t->rec = (uint8_t **)realloc(t->rec, t->m_rec * sizeof(*t->rec));
-		t->len = (uint32_t *)realloc(t->len, t->m_rec * sizeof(*t->len));
+	if (t_ga_mode == RR_REPLAY && is_bwa_param(ap) && len1 > 0 && len2 > 0) {
+		const bwa_gpu_path_res_t *r;
+		if (t_ga_pos >= t_ga_n || t_ga_len1[t_ga_pos] != len1 || t_ga_len2[t_ga_pos] != len2) {
+			fprintf(stderr, "[bwa_gpu_batch] aln_global_core replay out of step at job %zu\n", t_ga_pos);
+			abort();
+		}
+		r = &t_ga_res[t_ga_pos++];
+		*path_len = path_from_cigar(t_ga_pool + r->cigar_off, r->n_cigar, r->start_i, r->start_j, path);
+		return r->score;
 	}
-	t->rec[t->n_rec] = t->chunk[t->n_chunk - 1] + t->used;
-	t->len[t->n_rec] = len;
-	memcpy(t->rec[t->n_rec], data, len);
-	++t->n_rec; t->used += len; t->bytes += len;
-	return 1;
+	return real_aln_global_core(seq1, len1, seq2, len2, ap, path, path_len);
 }
 
-static void memtemp_free(void)
+char *bwa_cal_md1(int n_cigar, bwa_cigar_t *cigar, int len, bwtint_t pos, ubyte_t *seq, const bntseq_t *bns, ubyte_t *pacseq,
+                  kstring_t *str, int *_nm)
 {
-	size_t i;
-	for (i = 0; i < g_mt.n_chunk; ++i) free(g_mt.chunk[i]);
-	free(g_mt.chunk); free(g_mt.rec); free(g_mt.len);
-	memset(&g_mt, 0, sizeof(g_mt));
+	REAL(char *, bwa_cal_md1, int, bwa_cigar_t *, int, bwtint_t, ubyte_t *, const bntseq_t *, ubyte_t *, kstring_t *, int *);
+	if (t_ga_mode == RR_RECORD) { *_nm = 0; return 0; }
+	return real_bwa_cal_md1(n_cigar, cigar, len, pos, seq, bns, pacseq, str, _nm);
 }
 
-typedef struct { bam_pair_t *recs; zmq_msg_t *msgs; size_t base; } codec_ctx_t;
+/* ------------------------------------------------------------------ intermediate records (shim_io.c keeps them) */
+typedef struct { bam_pair_t *recs; size_t base; } codec_ctx_t;
 static void decode_one(size_t i, void *ctx)
 {
 	codec_ctx_t *c = (codec_ctx_t *)ctx;
+	const uint8_t *data;
+	uint32_t len;
 	zmq_msg_t m;
-	zmq_msg_init_data(&m, g_mt.rec[c->base + i], g_mt.len[c->base + i], 0, 0);
+	memtemp_get(c->base + i, &data, &len);
+	zmq_msg_init_data(&m, (void *)data, len, 0, 0);
 	pair_init_from_msg(&c->recs[i], &m);
 	zmq_msg_close(&m);
 }
 
-/* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file), then destroyed.  Serial on purpose:
- * encode and destroy are malloc/free of blocks other threads allocated, and spreading them over threads is slower (measured:
- * 0.29 s per 300 k records on one thread, 0.74 s on eight) */
 static void destroy_records(bam_pair_t *recs, size_t n)
 {
 	size_t i;
 	for (i = 0; i < n; ++i) bam_destroy_pair(&recs[i]);
 }
 
-static void store_records(gzFile temporary, bam_pair_t *recs, size_t n, int destroy)
+/* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file).  Serial on purpose: the encoder
+ * mallocs one message per record and the chunks are appended in order */
+static void store_records(gzFile temporary, bam_pair_t *recs, size_t n)
 {
 	size_t i;
 	for (i = 0; i < n; ++i) {
@@ -549,22 +583,20 @@ static void store_records(gzFile temporary, bam_pair_t *recs, size_t n, int dest
 			}
 		}
 		zmq_msg_close(&m);
-		if (destroy) bam_destroy_pair(&recs[i]);
 	}
 }
 
 /* pass 2: up to B records, the ones kept in memory first */
 static size_t load_records(gzFile temporary, bam_pair_t *recs, size_t B, long *tot_seqs)
 {
-	size_t n = 0, i;
-	if (g_mt.rd < g_mt.n_rec) {
-		codec_ctx_t c = {recs, 0, g_mt.rd};
-		n = g_mt.n_rec - g_mt.rd < B ? g_mt.n_rec - g_mt.rd : B;
+	size_t n, i, first;
+	n = memtemp_take(B, &first);
+	if (n) {
+		codec_ctx_t c = {recs, first};
 		parallel_for(n, 1024, decode_one, &c);
-		g_mt.rd += n;
 		for (i = 0; i < n; ++i) *tot_seqs += recs[i].kind;
 	}
-	while (n < B) {
+	while (n < B && memtemp_spilled()) {
 		const int rc = read_pair_custom(temporary, &recs[n]);
 		if (rc < 0) { fprintf(stderr, "[bwa_gpu_batch] error reading intermediate file\n"); exit(1); }
 		if (rc == 0) break;
@@ -574,106 +606,12 @@ static size_t load_records(gzFile temporary, bam_pair_t *recs, size_t B, long *t
 	return n;
 }
 
-/* ------------------------------------------------------------------ BAM output: BGZF blocks deflated on the host threads
- * pair_print_bam -> bwa_print_bam1 -> bgzf_write (bam2bam.c:304-321, 908-924; bgzf.c:594-623) deflates one 64 KB block at a
- * time on the calling thread.  Here the batch's records are laid out as the same byte stream, cut into BGZF blocks, the
- * blocks are deflated in parallel (same level, same header and footer as deflate_block, bgzf.c:265-340) and written in order
- * to the BGZF handle's own FILE.  The decompressed stream -- what any BAM reader sees -- is identical; block boundaries are
- * not (the reference cuts at 65536 bytes of input, this writer at 65280 so that a block always fits). */
-#define OB_IN 65280
-#define OB_OUT 65536
-typedef struct { bam_pair_t *recs; size_t *off; uint8_t *ubuf; size_t total; uint8_t *cbuf; int *clen; int level; int failed; } ob_ctx_t;
-
-static size_t rec_bytes(const bam_pair_t *p) /* pair_print_bam's filter and bwa_print_bam1's record size */
-{
-	size_t n = 0;
-	int i;
-	if (g_only_aligned)
-		for (i = 0; i != (int)p->kind; ++i)
-			if (p->bam_rec[i].core.flag & SAM_FSU) return 0;
-	for (i = 0; i != (int)p->kind; ++i) n += 4 + sizeof(bam1_core_t) + (size_t)p->bam_rec[i].data_len;
-	return n;
-}
-
-static void ob_fill_one(size_t i, void *ctx)
-{
-	ob_ctx_t *c = (ob_ctx_t *)ctx;
-	const bam_pair_t *p = &c->recs[i];
-	uint8_t *q = c->ubuf + c->off[i];
-	int j;
-	if (c->off[i + 1] == c->off[i]) return;
-	for (j = 0; j != (int)p->kind; ++j) { /* bwa_print_bam1 (bam2bam.c:304-321) */
-		const bam1_t *b = &p->bam_rec[j];
-		uint32_t w[9];
-		w[0] = (uint32_t)(sizeof(bam1_core_t) + b->data_len);
-		w[1] = (uint32_t)b->core.tid; w[2] = (uint32_t)b->core.pos;
-		w[3] = (uint32_t)((int)b->core.bin << 16 | (int)b->core.qual << 8 | (int)b->core.l_qname);
-		w[4] = (uint32_t)((int)b->core.flag << 16 | (int)b->core.n_cigar);
-		w[5] = (uint32_t)b->core.l_qseq; w[6] = (uint32_t)b->core.mtid; w[7] = (uint32_t)b->core.mpos; w[8] = (uint32_t)b->core.isize;
-		memcpy(q, w, 36); q += 36;
-		memcpy(q, b->data, (size_t)b->data_len); q += b->data_len;
-	}
-}
-
-static void ob_deflate_one(size_t k, void *ctx)
-{
-	ob_ctx_t *c = (ob_ctx_t *)ctx;
-	const uint8_t *in = c->ubuf + k * OB_IN;
-	const int in_len = (int)(c->total - k * OB_IN < OB_IN ? c->total - k * OB_IN : OB_IN);
-	uint8_t *out = c->cbuf + k * OB_OUT;
-	static const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 0, 0}; /* bgzf.c:274-291 */
-	z_stream zs;
-	uint32_t crc, len;
-	memcpy(out, hdr, 18);
-	memset(&zs, 0, sizeof(zs));
-	zs.next_in = (Bytef *)in; zs.avail_in = (uInt)in_len;
-	zs.next_out = out + 18; zs.avail_out = OB_OUT - 18 - 8;
-	if (deflateInit2(&zs, c->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK || deflate(&zs, Z_FINISH) != Z_STREAM_END) { c->failed = 1; return; }
-	deflateEnd(&zs);
-	len = (uint32_t)zs.total_out + 18 + 8;
-	out[16] = (uint8_t)((len - 1) & 0xff); out[17] = (uint8_t)((len - 1) >> 8);
-	crc = (uint32_t)crc32(crc32(0L, 0, 0), in, (uInt)in_len);
-	memcpy(out + 18 + zs.total_out, &crc, 4);
-	memcpy(out + 18 + zs.total_out + 4, &in_len, 4);
-	c->clen[k] = (int)len;
-}
-
-static void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n)
-{
-	static size_t *off; static size_t m_off;
-	static uint8_t *ubuf, *cbuf; static size_t m_ubuf, m_cbuf;
-	static int *clen; static size_t m_clen;
-	ob_ctx_t c;
-	size_t i, nblk;
-	if (n + 1 > m_off) { m_off = n + 1; off = (size_t *)realloc(off, m_off * sizeof(*off)); }
-	off[0] = 0;
-	for (i = 0; i < n; ++i) off[i + 1] = off[i] + rec_bytes(&recs[i]);
-	memset(&c, 0, sizeof(c));
-	c.recs = recs; c.off = off; c.total = off[n]; c.level = output->compress_level;
-	if (c.total) {
-		if (bgzf_flush(output) != 0) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); } /* what bgzf_write buffered so far (the header) */
-		nblk = (c.total + OB_IN - 1) / OB_IN;
-		if (c.total > m_ubuf) { m_ubuf = c.total + c.total / 4; ubuf = (uint8_t *)realloc(ubuf, m_ubuf); }
-		if (nblk * OB_OUT > m_cbuf) { m_cbuf = nblk * OB_OUT + (nblk / 4) * OB_OUT; cbuf = (uint8_t *)realloc(cbuf, m_cbuf); }
-		if (nblk > m_clen) { m_clen = nblk + nblk / 4; clen = (int *)realloc(clen, m_clen * sizeof(int)); }
-		c.ubuf = ubuf; c.cbuf = cbuf; c.clen = clen;
-		parallel_for(n, 2048, ob_fill_one, &c);
-		parallel_for(nblk, 4, ob_deflate_one, &c);
-		if (c.failed) { fprintf(stderr, "[bwa_gpu_batch] deflate failed\n"); exit(1); }
-		for (i = 0; i < nblk; ++i) {
-			if (fwrite(cbuf + i * OB_OUT, 1, (size_t)clen[i], output->file) != (size_t)clen[i]) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
-			output->block_address += clen[i];
-		}
-	}
-	for (i = 0; i < n; ++i) bam_destroy_pair(&recs[i]);
-}
-
 /* ------------------------------------------------------------------ pass 1 */
 static void gpu_align(int m, bwa_seq_t *flat)
 {
 	const double t0 = now();
 	if (m && bwa_gpu_cal_sa_reads_gap(m, flat, g_gap)) die("bwa_gpu_cal_sa_reads_gap");
-	++g_calls_aln; g_reads_aln += m; g_t_aln += now() - t0;
+	REP_ADD(calls_aln, reads_aln, dev_aln_s, m, t0);
 }
 
 static int is_mapped(const bwa_seq_t *p) { return p->type == BWA_TYPE_UNIQUE || p->type == BWA_TYPE_REPEAT; }
@@ -716,37 +654,22 @@ static void align_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_t
 }
 
 /* posn_* (bam2bam.c:622-641, 683-703) for records [0, n): primary-hit selection on the host, in record order (drand48),
- * one device call for the SA rows whose coordinates are wanted, then the reference's own bwa_cal_pac_pos_core fed from the answers */
-static void position_range(bam_pair_t *recs, size_t n, double *t_host)
+ * one device call for the SA rows whose coordinates are wanted, then the reference's own bwa_cal_pac_pos_core fed from the
+ * answers (slices of records on the host threads, each replaying its own part of the queue) */
+typedef struct { bam_pair_t *recs; const saq_t *q; const size_t *qoff; } posn_ctx_t;
+static void posn_slice(int s, size_t lo, size_t hi, void *ctx)
 {
+	posn_ctx_t *c = (posn_ctx_t *)ctx;
 	size_t i;
-	int j;
-	double t1 = now();
-	g_q.n = 0;
-	for (i = 0; i < n; ++i) {
-		bam_pair_t *r = &recs[i];
-		if (r->phase != aligned || !unique_rec(r)) continue;
-		for (j = 0; j != (int)r->kind; ++j) {
-			bwa_seq_t *p = &r->bwa_seq[j];
-			int k;
-			if (r->kind == singleton) bwa_aln2seq_core(p->n_aln, p->aln, p, 1, g_pe->max_occ_se);
-			else { p->n_multi = 0; bwa_aln2seq(p->n_aln, p->aln, p); }
-			if (is_mapped(p)) saq_push(&g_q, p->sa, p->strand);
-			if (r->kind == singleton)
-				for (k = 0; k < p->n_multi; ++k) saq_push(&g_q, p->multi[k].pos, p->multi[k].strand);
-		}
-	}
-	*t_host += now() - t1;
-	saq_run(&g_q);
-	t1 = now();
-	g_sa_replay = 1;
-	for (i = 0; i < n; ++i) {
-		bam_pair_t *r = &recs[i];
+	int j, k;
+	(void)s;
+	t_sa_q = c->q; t_sa_pos = c->qoff[lo];
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &c->recs[i];
 		if (r->phase != aligned) continue;
 		if (unique_rec(r))
 			for (j = 0; j != (int)r->kind; ++j) {
 				bwa_seq_t *p = &r->bwa_seq[j];
-				int k;
 				bwa_cal_pac_pos_core(g_bwt[0], g_bwt[1], p, g_gap->max_diff, g_gap->fnr);
 				if (r->kind == singleton)
 					for (k = 0; k < p->n_multi; ++k) { /* bam2bam.c:633-637 */
@@ -757,19 +680,43 @@ static void position_range(bam_pair_t *recs, size_t n, double *t_host)
 			}
 		r->phase = positioned;
 	}
-	g_sa_replay = 0;
-	if (g_sa_pos != g_q.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SA answers unused\n", g_q.n - g_sa_pos, g_q.n); abort(); }
+	if (t_sa_pos != c->qoff[hi]) { fprintf(stderr, "[bwa_gpu_batch] SA answers of records %zu..%zu out of step\n", lo, hi); abort(); }
+	t_sa_q = 0;
+}
+
+static void position_range(bam_pair_t *recs, size_t n, saq_t *q, size_t **qoff_buf, size_t *qoff_cap, double *t_host)
+{
+	size_t i;
+	int j;
+	double t1 = now();
+	posn_ctx_t c;
+	if (n + 1 > *qoff_cap) { *qoff_cap = n + 1; *qoff_buf = (size_t *)realloc(*qoff_buf, (n + 1) * sizeof(size_t)); }
+	q->n = 0;
+	for (i = 0; i < n; ++i) {
+		bam_pair_t *r = &recs[i];
+		(*qoff_buf)[i] = q->n;
+		if (r->phase != aligned || !unique_rec(r)) continue;
+		for (j = 0; j != (int)r->kind; ++j) {
+			bwa_seq_t *p = &r->bwa_seq[j];
+			int k;
+			if (r->kind == singleton) bwa_aln2seq_core(p->n_aln, p->aln, p, 1, g_pe->max_occ_se);
+			else { p->n_multi = 0; bwa_aln2seq(p->n_aln, p->aln, p); }
+			if (is_mapped(p)) saq_push(q, p->sa, p->strand);
+			if (r->kind == singleton)
+				for (k = 0; k < p->n_multi; ++k) saq_push(q, p->multi[k].pos, p->multi[k].strand);
+		}
+	}
+	(*qoff_buf)[n] = q->n;
+	*t_host += now() - t1;
+	saq_run(q);
+	t1 = now();
+	c.recs = recs; c.q = q; c.qoff = *qoff_buf;
+	parallel_slices(n, 4096, posn_slice, &c);
 	*t_host += now() - t1;
 }
 
-static void align_position_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq, double *t_host)
-{
-	align_range(recs, n, flat, t_toseq);
-	position_range(recs, n, t_host);
-}
-
 /* Pass 1 as a pipeline of five stages, each on its own thread, batches handed on in order through a ring of slots:
- *   read     read_bam_pair (inflate + parse; bamlite is a sequential gzread)
+ *   read     read_bam_pair (parse; the inflate runs on shim_io.c's threads)
  *   align    bam1_to_seq on the host threads + the search on the device            (the calling thread)
  *   position bwa_aln2seq_core in record order (drand48), SA rows on the device, bwa_cal_pac_pos_core, improve_isize_est
  *   store    the reference's record encoding into memory / its temporary file
@@ -793,20 +740,22 @@ typedef struct {
 	long tot_seqs;
 } pipe1_t;
 
-static void slot_wait(pipe1_t *P, int slot, int want)
+static void slot_wait(pthread_mutex_t *mu, pthread_cond_t *cv, const int *state, int want)
 {
-	pthread_mutex_lock(&P->mu);
-	while (P->state[slot] != want) pthread_cond_wait(&P->cv, &P->mu);
-	pthread_mutex_unlock(&P->mu);
+	pthread_mutex_lock(mu);
+	while (*(volatile const int *)state != want) pthread_cond_wait(cv, mu);
+	pthread_mutex_unlock(mu);
 }
 
-static void slot_set(pipe1_t *P, int slot, int st)
+static void slot_set(pthread_mutex_t *mu, pthread_cond_t *cv, int *state, int st)
 {
-	pthread_mutex_lock(&P->mu);
-	P->state[slot] = st;
-	pthread_cond_broadcast(&P->cv);
-	pthread_mutex_unlock(&P->mu);
+	pthread_mutex_lock(mu);
+	*state = st;
+	pthread_cond_broadcast(cv);
+	pthread_mutex_unlock(mu);
 }
+#define P1_WAIT(P, slot, want) slot_wait(&(P)->mu, &(P)->cv, &(P)->state[slot], want)
+#define P1_SET(P, slot, st) slot_set(&(P)->mu, &(P)->cv, &(P)->state[slot], st)
 
 static void *stage_read(void *arg)
 {
@@ -818,7 +767,7 @@ static void *stage_read(void *arg)
 		size_t n = 0;
 		long seqs = 0;
 		double t;
-		slot_wait(P, slot, SL_FREE);
+		P1_WAIT(P, slot, SL_FREE);
 		t = now();
 		while (n < P->B) {
 			const int rc = read_bam_pair(P->ks, &recs[n], g_broken_input, g_drop_aligned);
@@ -832,7 +781,7 @@ static void *stage_read(void *arg)
 		}
 		P->t_read += now() - t;
 		P->n[slot] = n; P->seqs[slot] = seqs;
-		slot_set(P, slot, SL_READ);
+		P1_SET(P, slot, SL_READ);
 		if (n == 0) break; /* an empty batch is the end marker; it travels through every stage */
 	}
 	return 0;
@@ -841,24 +790,28 @@ static void *stage_read(void *arg)
 static void *stage_position(void *arg)
 {
 	pipe1_t *P = (pipe1_t *)arg;
-	unsigned q;
-	for (q = 0;; ++q) {
-		const int slot = (int)(q % P1_SLOTS);
+	saq_t q;
+	size_t *qoff = 0, qoff_cap = 0;
+	unsigned b;
+	memset(&q, 0, sizeof(q));
+	for (b = 0;; ++b) {
+		const int slot = (int)(b % P1_SLOTS);
 		bam_pair_t *recs;
 		size_t n, i;
 		double t1;
-		slot_wait(P, slot, SL_ALIGNED);
+		P1_WAIT(P, slot, SL_ALIGNED);
 		recs = P->recs[slot]; n = P->n[slot];
 		if (n) {
-			position_range(recs, n, &P->t_host);
+			position_range(recs, n, &q, &qoff, &qoff_cap, &P->t_host);
 			t1 = now();
 			for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
 				if (unique_rec(&recs[i])) improve_isize_est(P->iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
 			P->t_host += now() - t1;
 		}
-		slot_set(P, slot, SL_POSITIONED);
+		P1_SET(P, slot, SL_POSITIONED);
 		if (n == 0) break;
 	}
+	saq_free(&q); free(qoff);
 	return 0;
 }
 
@@ -870,15 +823,15 @@ static void *stage_store(void *arg)
 		const int slot = (int)(q % P1_SLOTS);
 		size_t n;
 		double t1;
-		slot_wait(P, slot, SL_POSITIONED);
+		P1_WAIT(P, slot, SL_POSITIONED);
 		n = P->n[slot];
-		if (n == 0) { slot_set(P, slot, SL_STORED); break; }
+		if (n == 0) { P1_SET(P, slot, SL_STORED); break; }
 		t1 = now();
-		store_records(P->temporary, P->recs[slot], n, 0);
+		store_records(P->temporary, P->recs[slot], n);
 		P->t_write += now() - t1;
 		P->tot_seqs += P->seqs[slot];
 		fprintf(stderr, "[sequential_loop_pass1] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
-		slot_set(P, slot, SL_STORED);
+		P1_SET(P, slot, SL_STORED);
 	}
 	return 0;
 }
@@ -890,12 +843,12 @@ static void *stage_destroy(void *arg)
 	for (q = 0;; ++q) {
 		const int slot = (int)(q % P1_SLOTS);
 		double t1;
-		slot_wait(P, slot, SL_STORED);
+		P1_WAIT(P, slot, SL_STORED);
 		if (P->n[slot] == 0) break;
 		t1 = now();
 		destroy_records(P->recs[slot], P->n[slot]);
 		P->t_destroy += now() - t1;
-		slot_set(P, slot, SL_FREE);
+		P1_SET(P, slot, SL_FREE);
 	}
 	return 0;
 }
@@ -913,7 +866,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
 	P.B = B; P.ks = ks; P.temporary = temporary; P.iinfos = iinfos; P.t0 = now();
 	for (s = 0; s < P1_SLOTS; ++s) P.recs[s] = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
-	g_mt.cap = memtemp_cap();
+	memtemp_begin();
 	/* device context + index upload (seconds) overlap the reading of the first batches */
 	pthread_create(&init_th, 0, ensure_gpu_thread, 0);
 	pthread_create(&read_th, 0, stage_read, &P);
@@ -924,34 +877,78 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	t_init = now() - P.t0;
 	for (q = 0;; ++q) { /* the align stage */
 		const int slot = (int)(q % P1_SLOTS);
-		slot_wait(&P, slot, SL_READ);
+		P1_WAIT(&P, slot, SL_READ);
 		if (P.n[slot]) align_range(P.recs[slot], P.n[slot], flat, &t_toseq);
-		slot_set(&P, slot, SL_ALIGNED);
+		P1_SET(&P, slot, SL_ALIGNED);
 		if (P.n[slot] == 0) break;
 	}
 	pthread_join(read_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0); pthread_join(destroy_th, 0);
 	for (s = 0; s < P1_SLOTS; ++s) free(P.recs[s]);
 	free(flat);
 	pthread_mutex_destroy(&P.mu); pthread_cond_destroy(&P.cv);
-	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, g_mt.n_rec, g_mt.bytes / 1048576.0,
-	        g_mt.spilled ? ", the rest in the temporary file" : "");
+	g_rep.pass1_s = now() - P.t0;
+	g_rep.sequences = P.tot_seqs;
+	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, memtemp_records(), memtemp_bytes() / 1048576.0,
+	        memtemp_spilled() ? ", the rest in the temporary file" : "");
 	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each: device init %.2f, read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f, destroy %.2f)\n",
-	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, t_toseq, P.t_host, g_t_aln + g_t_sa, P.t_write, P.t_destroy);
+	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, t_toseq, P.t_host, g_rep.dev_aln_s + g_rep.dev_sa_s, P.t_write, P.t_destroy);
 	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
 }
 
-/* ------------------------------------------------------------------ pass 2 */
-typedef struct { size_t n, m; uint8_t *a; } bits_t;
-static void bits_push(bits_t *b, int v)
+/* ------------------------------------------------------------------ pass 2: finish_pair / finish_singleton, phase by phase */
+typedef struct { bwtint_t *arr; uint32_t n; uint8_t fresh, strand; int len; size_t qpos; } visit_t; /* one wide interval, as a record meets it */
+
+typedef struct { /* everything one batch carries through the stages */
+	bam_pair_t *recs;
+	size_t n;
+	long seqs;
+	khash_t(isize_infos) *iinfos;
+	/* enumerate */
+	saq_t q1;
+	visit_t *visit; size_t n_visit, m_visit;
+	size_t *qoff, *voff; uint8_t *want; size_t m_rec;
+	/* XA rows */
+	saq_t q2;
+	/* mate rescue / refinement: per-slice queues, merged job lists, results */
+	swq_t swq[MAX_THREADS];
+	gaq_t gaq[MAX_THREADS];
+	bwa_gpu_sw_job_t *sw_jobs; size_t m_sw_jobs; size_t sw_off[MAX_THREADS + 1];
+	bwa_gpu_path_res_t *sw_res; size_t m_sw_res; const bwa_cigar_t *sw_pool;
+	bwa_cigar_t *sw_pool_copy; size_t m_sw_pool;
+	bwa_gpu_ga_job_t *ga_jobs; size_t m_ga_jobs; size_t ga_off[MAX_THREADS + 1];
+	int *ga_len1, *ga_len2; size_t m_ga_len;
+	bwa_gpu_path_res_t *ga_res; size_t m_ga_res; const bwa_cigar_t *ga_pool;
+	bwa_cigar_t *ga_pool_copy; size_t m_ga_pool;
+	uint64_t n_tot[MAX_THREADS][2], n_mapped[MAX_THREADS][2];
+	int n_slices;
+} batch2_t;
+
+static void batch2_free(batch2_t *b)
 {
-	if (b->n == b->m) { b->m = b->m ? b->m << 1 : 1 << 12; b->a = (uint8_t *)realloc(b->a, b->m); }
-	b->a[b->n++] = (uint8_t)v;
+	int s;
+	saq_free(&b->q1); saq_free(&b->q2);
+	free(b->visit); free(b->qoff); free(b->voff); free(b->want);
+	for (s = 0; s < MAX_THREADS; ++s) {
+		free(b->swq[s].job); free(b->swq[s].seq_off); free(b->swq[s].seqs);
+		free(b->gaq[s].len1); free(b->gaq[s].len2); free(b->gaq[s].off1); free(b->gaq[s].off2); free(b->gaq[s].bytes);
+	}
+	free(b->sw_jobs); free(b->sw_res); free(b->sw_pool_copy); free(b->ga_pool_copy); free(b->ga_jobs); free(b->ga_len1); free(b->ga_len2); free(b->ga_res);
+	memset(b, 0, sizeof(*b));
 }
 
 static const isize_info_t *ii_of(khash_t(isize_infos) *iinfos, const bam_pair_t *r) /* bam2bam.c:715-716 */
 {
 	khiter_t it = kh_get(isize_infos, iinfos, bam_get_rg(r->bam_rec));
 	return it == kh_end(iinfos) ? &g_null_ii : &kh_val(iinfos, it);
+}
+
+static long long n_rows(const bam_pair_t *r)
+{
+	long long q = 0;
+	int j, k;
+	for (j = 0; j < 2; ++j)
+		for (k = 0; k < r->bwa_seq[j].n_aln; ++k) q += (long long)r->bwa_seq[j].aln[k].l - r->bwa_seq[j].aln[k].k + 1;
+	return q;
 }
 
 static int wants_pairing(const bam_pair_t *r) /* bam2bam.c:726-735 */
@@ -968,188 +965,406 @@ static int wants_pairing(const bam_pair_t *r) /* bam2bam.c:726-735 */
 	return n_occ[0] <= g_pe->max_occ && n_occ[1] <= g_pe->max_occ;
 }
 
-static double g_t_stageA, g_t_stageB, g_t_stageC, g_t_stageD;
 static int is_pair_job(const bam_pair_t *r) { return r->kind == proper_pair && r->phase == positioned && unique_rec(r); }
+static int is_single_job(const bam_pair_t *r) { return r->kind == singleton && r->phase == positioned && unique_rec(r); }
 
-static void pair_to_seq_one(size_t i, void *ctx)
+static void pair_to_seq_one(size_t i, void *ctx) /* finish_*'s bam1_to_seq (bam2bam.c:646, 717-718) */
 {
 	bam_pair_t *r = (bam_pair_t *)ctx + i;
 	int j;
-	if (!is_pair_job(r)) return;
-	for (j = 0; j < 2; ++j)
+	if (!is_pair_job(r) && !is_single_job(r)) return;
+	for (j = 0; j < (int)r->kind; ++j)
 		if (!r->bwa_seq[j].seq) bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
 }
 
-static void finish_tail_one(size_t i, void *ctx)
+/* A: every SA row whose coordinate pairing will want (bam2bam.c:736-765), in the reference's visiting order.  Owns the
+ * position cache: a wide interval is looked up by (k,l) only; the first record to touch a key creates the entry and its
+ * rows are fetched, later records reuse the values (which are filled in stage B of the batch that created them). */
+static void stage_enumerate(batch2_t *b, kh_64_t *my_hash)
 {
-	bam_pair_t *r = (bam_pair_t *)ctx + i;
-	if (is_pair_job(r)) {
-		bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
-		bwa_refine_gapped(g_bns, 1, &r->bwa_seq[1], g_pac, 0);
-		bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
-		bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
-		bwa_free_read_seq1(&r->bwa_seq[1]);
-		bwa_free_read_seq1(&r->bwa_seq[0]);
-	} else if (r->kind == singleton && r->phase == positioned && unique_rec(r)) {
-		bwa_seq_t *p = &r->bwa_seq[0];
-		if (!p->seq) bam1_to_seq(&r->bam_rec[0], p, 1, g_gap->trim_qual);
-		bwa_refine_gapped(g_bns, 1, p, g_pac, 0);
-		bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
-		bwa_free_read_seq1(p);
-	}
-	if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
-}
-
-/* finish_pair (bam2bam.c:705-811) for records [lo, hi), phase by phase */
-static void finish_range(bam_pair_t *recs, size_t lo, size_t hi, khash_t(isize_infos) *iinfos, uint64_t n_tot[2], uint64_t n_mapped[2],
-                         kh_64_t *my_hash)
-{
-	static bits_t fresh; /* per wide interval visited: did THIS record create its cache entry? */
-	size_t i, fpos = 0;
+	size_t i;
 	int j, k;
 	bwtint_t l;
-
-	double t1 = now();
-	parallel_for(hi - lo, 1024, pair_to_seq_one, recs + lo); /* finish_pair's bam1_to_seq (bam2bam.c:717-718) */
-	/* A: every SA row whose coordinate pairing will want (bam2bam.c:736-765), in the reference's visiting order */
-	g_q.n = 0; fresh.n = 0;
-	for (i = lo; i < hi; ++i) {
-		bam_pair_t *r = &recs[i];
-		if (!is_pair_job(r)) continue;
-		for (j = 0; j < 2; ++j)
-			if (!r->bwa_seq[j].seq) bam1_to_seq(&r->bam_rec[j], &r->bwa_seq[j], 1, g_gap->trim_qual);
-		if (!wants_pairing(r)) continue;
+	if (b->n + 1 > b->m_rec) {
+		b->m_rec = b->n + 1;
+		b->qoff = (size_t *)realloc(b->qoff, b->m_rec * sizeof(size_t)); b->voff = (size_t *)realloc(b->voff, b->m_rec * sizeof(size_t));
+		b->want = (uint8_t *)realloc(b->want, b->m_rec);
+	}
+	parallel_for(b->n, 1024, pair_to_seq_one, b->recs);
+	b->q1.n = 0; b->n_visit = 0;
+	for (i = 0; i < b->n; ++i) {
+		bam_pair_t *r = &b->recs[i];
+		b->qoff[i] = b->q1.n; b->voff[i] = b->n_visit; b->want[i] = 0;
+		if (!is_pair_job(r) || !wants_pairing(r)) continue;
+		b->want[i] = 1;
 		for (j = 0; j < 2; ++j)
 			for (k = 0; k < r->bwa_seq[j].n_aln; ++k) {
 				const bwt_aln1_t *a = r->bwa_seq[j].aln + k;
 				int is_new = 1;
-				if (a->l - a->k + 1 >= MIN_HASH_WIDTH) { /* cached by (k,l) only; the first record to touch a key fills it */
+				if (a->l - a->k + 1 >= MIN_HASH_WIDTH) {
 					int ret;
 					khint_t it = kh_put(64, my_hash, (uint64_t)a->k << 32 | a->l, &ret);
+					poslist_t *z = &kh_val(my_hash, it);
+					visit_t *v;
 					is_new = ret != 0;
 					if (is_new) {
-						poslist_t *z = &kh_val(my_hash, it);
 						z->n = a->l - a->k + 1;
 						z->a = (bwtint_t *)malloc(sizeof(bwtint_t) * z->n);
 					}
-					bits_push(&fresh, is_new);
+					if (b->n_visit == b->m_visit) { b->m_visit = b->m_visit ? b->m_visit << 1 : 256; b->visit = (visit_t *)realloc(b->visit, b->m_visit * sizeof(visit_t)); }
+					v = &b->visit[b->n_visit++];
+					v->arr = z->a; v->n = (uint32_t)z->n; v->fresh = (uint8_t)is_new; v->strand = (uint8_t)a->a; v->len = (int)r->bwa_seq[j].len; v->qpos = b->q1.n;
 				}
 				if (is_new)
-					for (l = a->k; l <= a->l; ++l) { saq_push(&g_q, l, a->a); if (l == a->l) break; }
+					for (l = a->k; l <= a->l; ++l) { saq_push(&b->q1, l, a->a); if (l == a->l) break; }
 			}
 	}
-	g_t_stageA += now() - t1;
-	saq_run(&g_q);
-	t1 = now();
-
-	/* B: pairing on the host, in record order, then the hit lists for XA (consumes drand48), collecting their rows */
-	{
-		static saq_t q2;
-		size_t qpos = 0;
-		q2.n = 0;
-		for (i = lo; i < hi; ++i) {
-			bam_pair_t *r = &recs[i];
-			bwa_seq_t *p[2];
-			pe_data_t d;
-			if (!is_pair_job(r)) continue;
-			p[0] = &r->bwa_seq[0]; p[1] = &r->bwa_seq[1];
-			memset(&d, 0, sizeof(pe_data_t));
-			for (j = 0; j < 2; ++j) { d.aln[j].a = p[j]->aln; d.aln[j].n = p[j]->n_aln; }
-			if (wants_pairing(r)) {
-				d.arr.n = 0;
-				for (j = 0; j < 2; ++j)
-					for (k = 0; k < (int)d.aln[j].n; ++k) {
-						const bwt_aln1_t *a = d.aln[j].a + k;
-						const bwtint_t w = a->l - a->k + 1;
-						bwtint_t t;
-						uint64_t x;
-						if (w >= MIN_HASH_WIDTH) {
-							khint_t it = kh_get(64, my_hash, (uint64_t)a->k << 32 | a->l);
-							poslist_t *z = &kh_val(my_hash, it);
-							if (fresh.a[fpos++]) /* this record created the entry: its strand and length define the values */
-								for (t = 0; t < w; ++t, ++qpos)
-									z->a[t] = a->a ? g_q.out[qpos] : g_bwt[1]->seq_len - (g_q.out[qpos] + p[j]->len);
-							for (t = 0; t < (bwtint_t)z->n; ++t) {
-								x = z->a[t];
-								x = x << 32 | k << 1 | j;
-								kv_push(uint64_t, d.arr, x);
-							}
-						} else
-							for (t = 0; t < w; ++t, ++qpos) {
-								x = a->a ? g_q.out[qpos] : g_bwt[1]->seq_len - (g_q.out[qpos] + p[j]->len);
-								x = x << 32 | k << 1 | j;
-								kv_push(uint64_t, d.arr, x);
-							}
-					}
-				pairing(p, &d, g_pe, g_gap->s_mm, ii_of(iinfos, r));
-			}
-			if (g_pe->N_multi || g_pe->n_multi) /* bam2bam.c:771-791 */
-				for (j = 0; j < 2; ++j)
-					if (p[j]->type != BWA_TYPE_NO_MATCH) {
-						if (!(p[j]->extra_flag & SAM_FPP) && p[1 - j]->type != BWA_TYPE_NO_MATCH)
-							bwa_aln2seq_core(d.aln[j].n, d.aln[j].a, p[j], 0,
-							                 p[j]->c1 + p[j]->c2 - 1 > g_pe->N_multi ? g_pe->n_multi : g_pe->N_multi);
-						else bwa_aln2seq_core(d.aln[j].n, d.aln[j].a, p[j], 0, g_pe->n_multi);
-						for (k = 0; k < p[j]->n_multi; ++k) saq_push(&q2, p[j]->multi[k].pos, p[j]->multi[k].strand);
-					}
-			kv_destroy(d.arr);
-			kv_destroy(d.pos[0]); kv_destroy(d.pos[1]);
-		}
-		if (qpos != g_q.n || fpos != fresh.n) { fprintf(stderr, "[bwa_gpu_batch] pass-2 enumeration out of step\n"); abort(); }
-		saq_run(&q2);
-		qpos = 0;
-		for (i = lo; i < hi; ++i) {
-			bam_pair_t *r = &recs[i];
-			if (!is_pair_job(r) || !(g_pe->N_multi || g_pe->n_multi)) continue;
-			for (j = 0; j < 2; ++j) {
-				bwa_seq_t *p = &r->bwa_seq[j];
-				if (p->type == BWA_TYPE_NO_MATCH) continue;
-				for (k = 0; k < p->n_multi; ++k, ++qpos) {
-					bwt_multi1_t *q = p->multi + k;
-					q->pos = q->strand ? q2.out[qpos] : g_bwt[1]->seq_len - (q2.out[qpos] + p->len);
-				}
-			}
-		}
-	}
-
-	g_t_stageB += now() - t1; t1 = now();
-	/* C: mate rescue.  bwa_paired_sw1 (bwape.c:519-633) decides the windows in floating point and judges the
-	 * alignments; only aln_local_core moves.  First run: note the jobs.  Device.  Second run: the real one. */
-	{
-		uint64_t dummy_tot[2] = {0, 0}, dummy_mapped[2] = {0, 0};
-		g_sw.n = 0; g_sw.sn = 0;
-		g_sw_mode = SW_RECORD;
-		for (i = lo; i < hi; ++i)
-			if (is_pair_job(&recs[i])) {
-				bwa_seq_t *p[2] = {&recs[i].bwa_seq[0], &recs[i].bwa_seq[1]};
-				bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(iinfos, &recs[i]), dummy_tot, dummy_mapped);
-			}
-		g_sw_mode = SW_REAL;
-		swq_run(&g_sw);
-		g_sw_mode = SW_REPLAY;
-		for (i = lo; i < hi; ++i)
-			if (is_pair_job(&recs[i])) {
-				bwa_seq_t *p[2] = {&recs[i].bwa_seq[0], &recs[i].bwa_seq[1]};
-				bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(iinfos, &recs[i]), n_tot, n_mapped);
-			}
-		g_sw_mode = SW_REAL;
-		if (g_sw_pos != g_sw.n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SW answers unused\n", g_sw.n - g_sw_pos, g_sw.n); abort(); }
-	}
-
-	g_t_stageC += now() - t1; t1 = now();
-	/* D: the reference's own per-record tail (bam2bam.c:643-658, 798-810), records spread over the host threads */
-	parallel_for(hi - lo, 512, finish_tail_one, recs + lo);
-	g_t_stageD += now() - t1;
+	b->qoff[b->n] = b->q1.n; b->voff[b->n] = b->n_visit;
+	saq_run(&b->q1);
 }
 
-/* A batch's BAM records are laid out, deflated and written while the next batch is loaded and finished */
-typedef struct { BGZF *output; bam_pair_t *recs; size_t n; double secs; } writer_t;
-static void *write_batch(void *arg)
+/* B1: the values of the cache entries this batch created (their creator's strand and length define them, bam2bam.c:751-757) */
+static void fill_visit_one(size_t vi, void *ctx)
 {
-	writer_t *w = (writer_t *)arg;
-	const double t = now();
-	write_records_bam(w->output, w->recs, w->n);
-	w->secs = now() - t;
+	batch2_t *b = (batch2_t *)ctx;
+	const visit_t *v = &b->visit[vi];
+	uint32_t t;
+	if (!v->fresh) return;
+	for (t = 0; t < v->n; ++t) v->arr[t] = v->strand ? b->q1.out[v->qpos + t] : g_bwt[1]->seq_len - (b->q1.out[v->qpos + t] + v->len);
+}
+
+/* B2: pairing (bwape.c:180-293) of one record, on the coordinates stage A fetched */
+static void pairing_one(size_t i, void *ctx)
+{
+	batch2_t *b = (batch2_t *)ctx;
+	bam_pair_t *r = &b->recs[i];
+	bwa_seq_t *p[2];
+	pe_data_t d;
+	size_t qpos, vpos;
+	int j, k;
+	if (!b->want[i]) return;
+	p[0] = &r->bwa_seq[0]; p[1] = &r->bwa_seq[1];
+	memset(&d, 0, sizeof(pe_data_t));
+	for (j = 0; j < 2; ++j) { d.aln[j].a = p[j]->aln; d.aln[j].n = p[j]->n_aln; }
+	qpos = b->qoff[i]; vpos = b->voff[i];
+	for (j = 0; j < 2; ++j)
+		for (k = 0; k < (int)d.aln[j].n; ++k) {
+			const bwt_aln1_t *a = d.aln[j].a + k;
+			const bwtint_t w = a->l - a->k + 1;
+			bwtint_t t;
+			uint64_t x;
+			if (w >= MIN_HASH_WIDTH) {
+				const visit_t *v = &b->visit[vpos++];
+				if (v->fresh) qpos += w;
+				for (t = 0; t < (bwtint_t)v->n; ++t) {
+					x = v->arr[t];
+					x = x << 32 | k << 1 | j;
+					kv_push(uint64_t, d.arr, x);
+				}
+			} else
+				for (t = 0; t < w; ++t, ++qpos) {
+					x = a->a ? b->q1.out[qpos] : g_bwt[1]->seq_len - (b->q1.out[qpos] + p[j]->len);
+					x = x << 32 | k << 1 | j;
+					kv_push(uint64_t, d.arr, x);
+				}
+		}
+	if (qpos != b->qoff[i + 1] || vpos != b->voff[i + 1]) { fprintf(stderr, "[bwa_gpu_batch] pass-2 enumeration out of step at record %zu\n", i); abort(); }
+	pairing(p, &d, g_pe, g_gap->s_mm, ii_of(b->iinfos, r));
+	kv_destroy(d.arr);
+}
+
+typedef struct { batch2_t *b; } xa_ctx_t;
+static void xa_assign_slice(int s, size_t lo, size_t hi, void *ctx)
+{
+	batch2_t *b = (batch2_t *)ctx;
+	size_t i, qpos = b->voff[lo]; /* voff is reused as the per-record offset into q2 by stage_pairing */
+	int j, k;
+	(void)s;
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &b->recs[i];
+		if (!is_pair_job(r)) continue;
+		for (j = 0; j < 2; ++j) {
+			bwa_seq_t *p = &r->bwa_seq[j];
+			if (p->type == BWA_TYPE_NO_MATCH) continue;
+			for (k = 0; k < p->n_multi; ++k, ++qpos) {
+				bwt_multi1_t *q = p->multi + k;
+				q->pos = q->strand ? b->q2.out[qpos] : g_bwt[1]->seq_len - (b->q2.out[qpos] + p->len);
+			}
+		}
+	}
+}
+
+/* B: pairing on the host threads, then the hit lists for XA in record order (bwa_aln2seq_core consumes drand48) and their rows */
+static void stage_pairing(batch2_t *b)
+{
+	size_t i;
+	int j, k;
+	parallel_for(b->n_visit, 64, fill_visit_one, b);
+	parallel_for(b->n, 256, pairing_one, b);
+	b->q2.n = 0;
+	for (i = 0; i < b->n; ++i) {
+		bam_pair_t *r = &b->recs[i];
+		bwa_seq_t *p[2];
+		b->voff[i] = b->q2.n;
+		if (!is_pair_job(r) || !(g_pe->N_multi || g_pe->n_multi)) continue; /* bam2bam.c:771-791 */
+		p[0] = &r->bwa_seq[0]; p[1] = &r->bwa_seq[1];
+		for (j = 0; j < 2; ++j)
+			if (p[j]->type != BWA_TYPE_NO_MATCH) {
+				if (!(p[j]->extra_flag & SAM_FPP) && p[1 - j]->type != BWA_TYPE_NO_MATCH)
+					bwa_aln2seq_core(p[j]->n_aln, p[j]->aln, p[j], 0, p[j]->c1 + p[j]->c2 - 1 > g_pe->N_multi ? g_pe->n_multi : g_pe->N_multi);
+				else bwa_aln2seq_core(p[j]->n_aln, p[j]->aln, p[j], 0, g_pe->n_multi);
+				for (k = 0; k < p[j]->n_multi; ++k) saq_push(&b->q2, p[j]->multi[k].pos, p[j]->multi[k].strand);
+			}
+	}
+	b->voff[b->n] = b->q2.n;
+	saq_run(&b->q2);
+	if (b->q2.n) parallel_slices(b->n, 4096, xa_assign_slice, b);
+}
+
+/* C: mate rescue.  bwa_paired_sw1 (bwape.c:519-633) decides the windows in floating point and judges the alignments; only
+ * aln_local_core moves.  First run (host threads, a slice of records each): note the jobs.  Device.  Second run: the real one. */
+static void rescue_record_slice(int s, size_t lo, size_t hi, void *ctx)
+{
+	batch2_t *b = (batch2_t *)ctx;
+	uint64_t dummy_tot[2] = {0, 0}, dummy_mapped[2] = {0, 0};
+	size_t i;
+	b->swq[s].n = 0; b->swq[s].sn = 0;
+	t_swq = &b->swq[s];
+	t_sw_mode = RR_RECORD;
+	for (i = lo; i < hi; ++i)
+		if (is_pair_job(&b->recs[i])) {
+			bwa_seq_t *p[2] = {&b->recs[i].bwa_seq[0], &b->recs[i].bwa_seq[1]};
+			bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(b->iinfos, &b->recs[i]), dummy_tot, dummy_mapped);
+		}
+	t_sw_mode = RR_REAL;
+	t_swq = 0;
+}
+
+static void rescue_replay_slice(int s, size_t lo, size_t hi, void *ctx)
+{
+	batch2_t *b = (batch2_t *)ctx;
+	size_t i;
+	t_sw_jobs = b->sw_jobs + b->sw_off[s]; t_sw_res = b->sw_res + b->sw_off[s]; t_sw_pool = b->sw_pool;
+	t_sw_n = b->sw_off[s + 1] - b->sw_off[s]; t_sw_pos = 0;
+	t_sw_mode = RR_REPLAY;
+	b->n_tot[s][0] = b->n_tot[s][1] = b->n_mapped[s][0] = b->n_mapped[s][1] = 0;
+	for (i = lo; i < hi; ++i)
+		if (is_pair_job(&b->recs[i])) {
+			bwa_seq_t *p[2] = {&b->recs[i].bwa_seq[0], &b->recs[i].bwa_seq[1]};
+			bwa_paired_sw1(g_bns, g_pac, p, g_pe, ii_of(b->iinfos, &b->recs[i]), b->n_tot[s], b->n_mapped[s]);
+		}
+	t_sw_mode = RR_REAL;
+	if (t_sw_pos != t_sw_n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu SW answers unused\n", t_sw_n - t_sw_pos, t_sw_n); abort(); }
+}
+
+static void stage_rescue(batch2_t *b, uint64_t n_tot[2], uint64_t n_mapped[2])
+{
+	size_t total = 0, i;
+	int s, ns;
+	double t0;
+	ns = parallel_slices(b->n, 2048, rescue_record_slice, b);
+	b->n_slices = ns;
+	for (s = 0; s < ns; ++s) { b->sw_off[s] = total; total += b->swq[s].n; }
+	b->sw_off[ns] = total;
+	if (total + 1 > b->m_sw_jobs) { b->m_sw_jobs = total + 1 + total / 4; b->sw_jobs = (bwa_gpu_sw_job_t *)realloc(b->sw_jobs, b->m_sw_jobs * sizeof(*b->sw_jobs)); }
+	if (total + 1 > b->m_sw_res) { b->m_sw_res = total + 1 + total / 4; b->sw_res = (bwa_gpu_path_res_t *)realloc(b->sw_res, b->m_sw_res * sizeof(*b->sw_res)); }
+	for (s = 0; s < ns; ++s)
+		for (i = 0; i < b->swq[s].n; ++i) {
+			b->sw_jobs[b->sw_off[s] + i] = b->swq[s].job[i];
+			b->sw_jobs[b->sw_off[s] + i].seq = b->swq[s].seqs + b->swq[s].seq_off[i];
+		}
+	t0 = now();
+	b->sw_pool = 0;
+	if (total) {
+		size_t pool_n = 0;
+		if (bwa_gpu_mate_sw_path((int)total, b->sw_jobs, b->sw_res, &b->sw_pool)) die("bwa_gpu_mate_sw_path");
+		/* the pool belongs to the library until its next call, which another stage's thread may make: keep a copy */
+		for (i = 0; i < total; ++i)
+			if (b->sw_res[i].n_cigar && (size_t)(b->sw_res[i].cigar_off + b->sw_res[i].n_cigar) > pool_n) pool_n = (size_t)(b->sw_res[i].cigar_off + b->sw_res[i].n_cigar);
+		if (pool_n + 1 > b->m_sw_pool) { b->m_sw_pool = pool_n + 1 + pool_n / 4; b->sw_pool_copy = (bwa_cigar_t *)realloc(b->sw_pool_copy, b->m_sw_pool * sizeof(bwa_cigar_t)); }
+		memcpy(b->sw_pool_copy, b->sw_pool, pool_n * sizeof(bwa_cigar_t));
+		b->sw_pool = b->sw_pool_copy;
+	}
+	REP_ADD(calls_sw, jobs_sw, dev_sw_s, total, t0);
+	parallel_slices(b->n, 2048, rescue_replay_slice, b);
+	for (s = 0; s < ns; ++s) { n_tot[0] += b->n_tot[s][0]; n_tot[1] += b->n_tot[s][1]; n_mapped[0] += b->n_mapped[s][0]; n_mapped[1] += b->n_mapped[s][1]; }
+}
+
+/* D: bwa_refine_gapped + bwa_update_bam1 (bam2bam.c:643-658, 798-810).  The banded global alignments of the gapped hits
+ * (refine_gapped_core -> aln_global_core, bwase.c:212) go to the device in one call: RECORD on a scratch copy of each read
+ * (bwa_refine_gapped edits pos / cigar / multi[] and reverses seq in place; all of that is undone or thrown away), REPLAY = the
+ * reference's own tail of finish_*. */
+static void refine_record_read(bwa_seq_t *s)
+{
+	bwa_seq_t tmp;
+	bwt_multi1_t *multi_copy = 0;
+	int j, gapped = 0;
+	if (s->type != BWA_TYPE_NO_MATCH && s->type != BWA_TYPE_MATESW && s->n_gapo) gapped = 1;
+	for (j = 0; j < s->n_multi && !gapped; ++j) gapped = s->multi[j].gap != 0;
+	if (!gapped) return; /* bwa_refine_gapped would not call aln_global_core (bwase.c:371-380) */
+	tmp = *s;
+	if (s->cigar && s->n_cigar > 0) { /* bwa_correct_trimmed may realloc the copy's CIGAR (bwase.c:330-352): never the original's block */
+		tmp.cigar = (bwa_cigar_t *)malloc((size_t)s->n_cigar * sizeof(bwa_cigar_t));
+		memcpy(tmp.cigar, s->cigar, (size_t)s->n_cigar * sizeof(bwa_cigar_t));
+	}
+	if (s->n_multi) {
+		multi_copy = (bwt_multi1_t *)malloc((size_t)s->n_multi * sizeof(bwt_multi1_t));
+		memcpy(multi_copy, s->multi, (size_t)s->n_multi * sizeof(bwt_multi1_t));
+		tmp.multi = multi_copy;
+	}
+	bwa_refine_gapped(g_bns, 1, &tmp, g_pac, 0);
+	seq_reverse(s->len, s->seq, 0); /* bwase.c:369 reversed the shared buffer: put it back for the real run */
+	for (j = 0; j < s->n_multi; ++j)
+		if (multi_copy[j].cigar && multi_copy[j].cigar != s->multi[j].cigar) free(multi_copy[j].cigar);
+	free(multi_copy);
+	if (tmp.cigar != s->cigar) free(tmp.cigar);
+	if (tmp.md != s->md) free(tmp.md);
+}
+
+static void refine_record_slice(int s, size_t lo, size_t hi, void *ctx)
+{
+	batch2_t *b = (batch2_t *)ctx;
+	size_t i;
+	b->gaq[s].n = 0; b->gaq[s].bn = 0;
+	t_gaq = &b->gaq[s];
+	t_ga_mode = RR_RECORD;
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &b->recs[i];
+		if (is_pair_job(r)) { refine_record_read(&r->bwa_seq[0]); refine_record_read(&r->bwa_seq[1]); }
+		else if (is_single_job(r)) refine_record_read(&r->bwa_seq[0]);
+	}
+	t_ga_mode = RR_REAL;
+	t_gaq = 0;
+}
+
+static void refine_replay_slice(int s, size_t lo, size_t hi, void *ctx)
+{
+	batch2_t *b = (batch2_t *)ctx;
+	size_t i;
+	t_ga_res = b->ga_res + b->ga_off[s]; t_ga_pool = b->ga_pool;
+	t_ga_len1 = b->ga_len1 + b->ga_off[s]; t_ga_len2 = b->ga_len2 + b->ga_off[s];
+	t_ga_n = b->ga_off[s + 1] - b->ga_off[s]; t_ga_pos = 0;
+	t_ga_mode = RR_REPLAY;
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &b->recs[i];
+		if (is_pair_job(r)) {
+			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
+			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[1], g_pac, 0);
+			bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
+			bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
+			bwa_free_read_seq1(&r->bwa_seq[1]);
+			bwa_free_read_seq1(&r->bwa_seq[0]);
+		} else if (is_single_job(r)) {
+			bwa_seq_t *p = &r->bwa_seq[0];
+			bwa_refine_gapped(g_bns, 1, p, g_pac, 0);
+			bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
+			bwa_free_read_seq1(p);
+		}
+		if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
+	}
+	t_ga_mode = RR_REAL;
+	if (t_ga_pos != t_ga_n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu global-alignment answers unused\n", t_ga_n - t_ga_pos, t_ga_n); abort(); }
+}
+
+static void stage_refine(batch2_t *b)
+{
+	size_t total = 0, i;
+	int s, ns;
+	double t0;
+	parallel_for(b->n, 1024, pair_to_seq_one, b->recs); /* singletons reach this stage first */
+	ns = parallel_slices(b->n, 2048, refine_record_slice, b);
+	for (s = 0; s < ns; ++s) { b->ga_off[s] = total; total += b->gaq[s].n; }
+	b->ga_off[ns] = total;
+	if (total + 1 > b->m_ga_jobs) { b->m_ga_jobs = total + 1 + total / 4; b->ga_jobs = (bwa_gpu_ga_job_t *)realloc(b->ga_jobs, b->m_ga_jobs * sizeof(*b->ga_jobs)); }
+	if (total + 1 > b->m_ga_res) { b->m_ga_res = total + 1 + total / 4; b->ga_res = (bwa_gpu_path_res_t *)realloc(b->ga_res, b->m_ga_res * sizeof(*b->ga_res)); }
+	if (total + 1 > b->m_ga_len) { b->m_ga_len = total + 1 + total / 4; b->ga_len1 = (int *)realloc(b->ga_len1, b->m_ga_len * sizeof(int)); b->ga_len2 = (int *)realloc(b->ga_len2, b->m_ga_len * sizeof(int)); }
+	for (s = 0; s < ns; ++s)
+		for (i = 0; i < b->gaq[s].n; ++i) {
+			bwa_gpu_ga_job_t *jb = &b->ga_jobs[b->ga_off[s] + i];
+			jb->ref = b->gaq[s].bytes + b->gaq[s].off1[i]; jb->reflen = b->gaq[s].len1[i];
+			jb->seq = b->gaq[s].bytes + b->gaq[s].off2[i]; jb->len = b->gaq[s].len2[i];
+			b->ga_len1[b->ga_off[s] + i] = jb->reflen; b->ga_len2[b->ga_off[s] + i] = jb->len;
+		}
+	t0 = now();
+	b->ga_pool = 0;
+	if (total) {
+		size_t pool_n = 0;
+		if (bwa_gpu_global_align_seqs((int)total, b->ga_jobs, aln_param_bwa.gap_end, aln_param_bwa.band_width, b->ga_res, &b->ga_pool))
+			die("bwa_gpu_global_align_seqs");
+		/* the pool is the library's until its next SW / global-alignment call, which the rescue stage of the next batch may make */
+		for (i = 0; i < total; ++i)
+			if (b->ga_res[i].n_cigar && (size_t)(b->ga_res[i].cigar_off + b->ga_res[i].n_cigar) > pool_n) pool_n = (size_t)(b->ga_res[i].cigar_off + b->ga_res[i].n_cigar);
+		if (pool_n + 1 > b->m_ga_pool) { b->m_ga_pool = pool_n + 1 + pool_n / 4; b->ga_pool_copy = (bwa_cigar_t *)realloc(b->ga_pool_copy, b->m_ga_pool * sizeof(bwa_cigar_t)); }
+		memcpy(b->ga_pool_copy, b->ga_pool, pool_n * sizeof(bwa_cigar_t));
+		b->ga_pool = b->ga_pool_copy;
+	}
+	REP_ADD(calls_ga, jobs_ga, dev_ga_s, total, t0);
+	parallel_slices(b->n, 2048, refine_replay_slice, b);
+}
+
+/* Pass 2 as a pipeline: load -> enumerate (A) -> pairing + XA (B) -> mate rescue (C) -> refine + update (D) -> write,
+ * one thread per stage, batches in order.  A owns the position cache, B the random numbers, the writer the output file. */
+#define P2_SLOTS 6
+enum { S2_FREE = 0, S2_LOADED, S2_ENUM, S2_PAIRED, S2_RESCUED, S2_REFINED };
+typedef struct {
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	int state[P2_SLOTS];
+	batch2_t b[P2_SLOTS];
+	size_t B;
+	gzFile temporary;
+	BGZF *output;
+	khash_t(isize_infos) *iinfos;
+	kh_64_t *my_hash;
+	uint64_t n_tot[2], n_mapped[2];
+	double t0, t_load, t_enum, t_pair, t_rescue, t_refine, t_write;
+	long tot_seqs;
+} pipe2_t;
+#define P2_WAIT(P, slot, want) slot_wait(&(P)->mu, &(P)->cv, &(P)->state[slot], want)
+#define P2_SET(P, slot, st) slot_set(&(P)->mu, &(P)->cv, &(P)->state[slot], st)
+
+#define P2_STAGE(name, from, to, timer, body) \
+	static void *name(void *arg) \
+	{ \
+		pipe2_t *P = (pipe2_t *)arg; \
+		unsigned q; \
+		for (q = 0;; ++q) { \
+			const int slot = (int)(q % P2_SLOTS); \
+			batch2_t *b = &P->b[slot]; \
+			double t1; \
+			P2_WAIT(P, slot, from); \
+			t1 = now(); \
+			if (b->n) { body; } \
+			P->timer += now() - t1; \
+			P2_SET(P, slot, to); \
+			if (b->n == 0) break; \
+		} \
+		return 0; \
+	}
+
+P2_STAGE(stage2_enum, S2_LOADED, S2_ENUM, t_enum, stage_enumerate(b, P->my_hash))
+P2_STAGE(stage2_pair, S2_ENUM, S2_PAIRED, t_pair, stage_pairing(b))
+P2_STAGE(stage2_rescue, S2_PAIRED, S2_RESCUED, t_rescue, stage_rescue(b, P->n_tot, P->n_mapped))
+P2_STAGE(stage2_refine, S2_RESCUED, S2_REFINED, t_refine, stage_refine(b))
+
+static void *stage2_write(void *arg)
+{
+	pipe2_t *P = (pipe2_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P2_SLOTS);
+		batch2_t *b = &P->b[slot];
+		double t1;
+		P2_WAIT(P, slot, S2_REFINED);
+		if (b->n == 0) break;
+		t1 = now();
+		write_records_bam(P->output, b->recs, b->n);
+		destroy_records(b->recs, b->n);
+		P->t_write += now() - t1;
+		P->tot_seqs += b->seqs;
+		fprintf(stderr, "[sequential_loop_pass2] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
+		P2_SET(P, slot, S2_FREE);
+	}
 	return 0;
 }
 
@@ -1157,65 +1372,67 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 {
 	const size_t B = batch_records();
 	const long long max_q = getenv("BWAGPU_BATCH_SA") ? atoll(getenv("BWAGPU_BATCH_SA")) : 1ll << 25; /* SA rows per device call */
-	const double t0 = now();
-	double t_read = 0, t_fin = 0, t_write = 0, t_wait = 0, t1;
-	uint64_t n_tot[2] = {0, 0}, n_mapped[2] = {0, 0};
-	bam_pair_t *buf[2] = {(bam_pair_t *)calloc(B, sizeof(bam_pair_t)), (bam_pair_t *)calloc(B, sizeof(bam_pair_t))};
-	kh_64_t *my_hash = kh_init(64);
+	pipe2_t *P = (pipe2_t *)calloc(1, sizeof(pipe2_t));
+	bam_pair_t *stash = (bam_pair_t *)calloc(B, sizeof(bam_pair_t)); /* loaded records not yet handed to a batch */
+	size_t stash_n = 0, stash_at = 0;
+	pthread_t th[5];
 	khiter_t it;
-	long tot_seqs = 0;
-	pthread_t write_th;
-	writer_t wr;
-	int cur = 0, writing = 0;
+	unsigned q;
+	int s, eof = 0;
+	long dummy = 0;
+	pthread_mutex_init(&P->mu, 0); pthread_cond_init(&P->cv, 0);
+	P->B = B; P->temporary = temporary; P->output = output; P->iinfos = iinfos; P->my_hash = kh_init(64); P->t0 = now();
+	for (s = 0; s < P2_SLOTS; ++s) P->b[s].recs = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
 	ensure_gpu();
-	for (;;) {
-		bam_pair_t *recs = buf[cur];
-		size_t n, lo;
+	pthread_create(&th[0], 0, stage2_enum, P);
+	pthread_create(&th[1], 0, stage2_pair, P);
+	pthread_create(&th[2], 0, stage2_rescue, P);
+	pthread_create(&th[3], 0, stage2_refine, P);
+	pthread_create(&th[4], 0, stage2_write, P);
+	for (q = 0;; ++q) { /* the load stage: batches bounded by records and by the SA rows their hit lists expand to */
+		const int slot = (int)(q % P2_SLOTS);
+		batch2_t *b = &P->b[slot];
+		long long rows = 0;
+		double t1;
+		P2_WAIT(P, slot, S2_FREE);
 		t1 = now();
-		n = load_records(temporary, recs, B, &tot_seqs);
-		t_read += now() - t1;
-		if (n == 0) break;
-		t1 = now();
-		for (lo = 0; lo < n;) { /* sub-ranges bounded by the SA rows their hit lists expand to */
-			size_t hi = lo;
-			long long q = 0;
-			while (hi < n && (hi == lo || q < max_q)) {
-				const bam_pair_t *r = &recs[hi];
-				if (is_pair_job(r) && wants_pairing(r)) {
-					int j, k;
-					for (j = 0; j < 2; ++j)
-						for (k = 0; k < r->bwa_seq[j].n_aln; ++k) q += r->bwa_seq[j].aln[k].l - r->bwa_seq[j].aln[k].k + 1;
-				}
-				++hi;
+		b->n = 0; b->seqs = 0; b->iinfos = iinfos;
+		while (b->n < B) {
+			if (stash_at == stash_n) {
+				if (eof) break;
+				stash_n = load_records(temporary, stash, B, &dummy);
+				stash_at = 0;
+				if (stash_n == 0) { eof = 1; break; }
 			}
-			finish_range(recs, lo, hi, iinfos, n_tot, n_mapped, my_hash);
-			lo = hi;
+			{
+				const bam_pair_t *r = &stash[stash_at];
+				const long long w = is_pair_job(r) && wants_pairing(r) ? n_rows(r) : 0;
+				if (b->n && rows + w > max_q) break;
+				rows += w;
+				b->seqs += r->kind;
+				b->recs[b->n++] = stash[stash_at++];
+			}
 		}
-		t_fin += now() - t1;
-		t1 = now();
-		if (writing) { pthread_join(write_th, 0); t_write += wr.secs; }
-		t_wait += now() - t1;
-		wr.output = output; wr.recs = recs; wr.n = n;
-		pthread_create(&write_th, 0, write_batch, &wr);
-		writing = 1;
-		cur ^= 1;
-		fprintf(stderr, "[%s] %ld sequences processed in %.2f sec\n", __func__, tot_seqs, now() - t0);
+		P->t_load += now() - t1;
+		P2_SET(P, slot, S2_LOADED);
+		if (b->n == 0) break;
 	}
-	t1 = now();
-	if (writing) { pthread_join(write_th, 0); t_write += wr.secs; }
-	t_wait += now() - t1;
-	fprintf(stderr, "[%s] finish = enumerate %.2f + pairing/XA %.2f + mate rescue (host side, both runs) %.2f + refine/update %.2f + device calls\n",
-	        __func__, g_t_stageA, g_t_stageB, g_t_stageC, g_t_stageD);
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (temp read %.2f, finish %.2f, BAM write %.2f of which %.2f not hidden behind the next batch)\n"
+	for (s = 0; s < 5; ++s) pthread_join(th[s], 0);
+	g_rep.pass2_s = now() - P->t0;
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each incl. their device calls: load %.2f, enumerate %.2f, "
+	                "pairing/XA %.2f, mate rescue %.2f, refine/update %.2f, BAM write %.2f)\n"
 	                "[%s] finished cleanly, shutting down.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d singletons are mated.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d discordant pairs are fixed.\n",
-	        __func__, tot_seqs, now() - t0, t_read, t_fin, t_write, t_wait, __func__, (long long)n_mapped[1], (long long)n_tot[1], SW_MIN_MAPQ,
-	        (long long)n_mapped[0], (long long)n_tot[0], SW_MIN_MAPQ);
-	for (it = kh_begin(my_hash); it != kh_end(my_hash); ++it)
-		if (kh_exist(my_hash, it)) free(kh_val(my_hash, it).a);
-	kh_destroy(64, my_hash);
-	free(buf[0]); free(buf[1]);
+	        __func__, P->tot_seqs, now() - P->t0, P->t_load, P->t_enum, P->t_pair, P->t_rescue, P->t_refine, P->t_write, __func__,
+	        (long long)P->n_mapped[1], (long long)P->n_tot[1], SW_MIN_MAPQ, (long long)P->n_mapped[0], (long long)P->n_tot[0], SW_MIN_MAPQ);
+	for (it = kh_begin(P->my_hash); it != kh_end(P->my_hash); ++it)
+		if (kh_exist(P->my_hash, it)) free(kh_val(P->my_hash, it).a);
+	kh_destroy(64, P->my_hash);
+	for (s = 0; s < P2_SLOTS; ++s) { bam_pair_t *recs = P->b[s].recs; batch2_free(&P->b[s]); free(recs); }
+	free(stash);
+	pthread_mutex_destroy(&P->mu); pthread_cond_destroy(&P->cv);
+	free(P);
 	memtemp_free();
 }
 
@@ -1236,15 +1453,9 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
  *   * the worker stops receiving while a batch is on the device, so the HWM of 64 (bam2bam.c:35) back-pressures
  *     the mux instead of flooding the worker.
  * First arrivals are in recno order (new records are sent in order), so with ONE batching worker drand48 is consumed
- * in record order in both passes and the BAM equals `bam2bam -t 1`'s (tests/test_batched_worker.py), which the
+ * in record order in both passes and the BAM equals `bam2bam -t 1`'s (tests/test_batched_bam2bam.py), which the
  * reference's own `-t N` does not guarantee.
  */
-
-void msg_init_from_pair(zmq_msg_t *m, bam_pair_t *p);
-void pair_init_from_msg(bam_pair_t *p, zmq_msg_t *m);
-void pair_posn(bam_pair_t *p);
-void set_sockopts(void *socket);
-
 static void *g_zmq_ctx;              /* bam2bam.c:103 (static there): captured where it is created */
 static void *volatile g_iinfos_seen; /* bam2bam.c:107 (static there): what g_iinfos is set to at 1769 / 1857 / 2092 / 2298 */
 
@@ -1295,6 +1506,9 @@ void *run_worker_thread(void *arg)
 	const double t_start = now();
 	taken_t *taken = (taken_t *)calloc(TAKEN_SLOTS, sizeof(taken_t));
 	kh_64_t *my_hash = kh_init(64);
+	batch2_t *b2 = (batch2_t *)calloc(1, sizeof(batch2_t));
+	saq_t q1;
+	size_t *qoff = 0, qoff_cap = 0;
 	khiter_t it;
 	uint64_t n_tot[2] = {0, 0}, n_mapped[2] = {0, 0};
 	long n_batches = 0, n_records = 0, n_dupes = 0, failure_count = 0;
@@ -1304,12 +1518,12 @@ void *run_worker_thread(void *arg)
 	void *upstream;
 	static int claimed;
 	(void)arg;
+	memset(&q1, 0, sizeof(q1));
 
-	/* the batch state above (SA / SW queues, record-replay cursors) is one set of globals and there is one device
-	 * queue: ONE thread batches, whatever -t says; further threads have nothing to add and leave */
+	/* the device queue is one: ONE thread batches, whatever -t says; further threads have nothing to add and leave */
 	if (__sync_lock_test_and_set(&claimed, 1)) {
 		fprintf(stderr, "[run_worker_thread] a batching GPU worker is already running in this process; extra thread exits.\n");
-		free(recs); free(flat); free(taken); kh_destroy(64, my_hash);
+		free(recs); free(flat); free(taken); kh_destroy(64, my_hash); free(b2);
 		return 0;
 	}
 	if (!g_zmq_ctx) { fprintf(stderr, "[bwa_gpu_batch] run_worker_thread: the 0MQ context was not seen being created\n"); abort(); }
@@ -1370,25 +1584,29 @@ void *run_worker_thread(void *arg)
 
 		/* ---- the switch of bam2bam.c:1414-1422, for the whole batch */
 		t1 = now();
-		if (phase_of_batch == pristine) align_position_range(recs, n, flat, &t_toseq, &t_host);
-		else if (phase_of_batch == aligned) for (i = 0; i < n; ++i) pair_posn(&recs[i]);
+		if (phase_of_batch == pristine) {
+			align_range(recs, n, flat, &t_toseq);
+			position_range(recs, n, &q1, &qoff, &qoff_cap, &t_host);
+		} else if (phase_of_batch == aligned) for (i = 0; i < n; ++i) pair_posn(&recs[i]);
 		else if (phase_of_batch == positioned) {
 			khash_t(isize_infos) *iinfos = (khash_t(isize_infos) *)g_iinfos_seen;
 			if (!iinfos) failure_count += (long)n; /* sent back as they came (bam2bam.c:1419-1420) */
 			else
 				for (lo = 0; lo < n;) { /* sub-ranges bounded by the SA rows their hit lists expand to, as sequential_loop_pass2 */
 					size_t hi = lo;
-					long long q = 0;
-					while (hi < n && (hi == lo || q < max_q)) {
+					long long rows = 0;
+					while (hi < n) {
 						const bam_pair_t *r = &recs[hi];
-						if (is_pair_job(r) && wants_pairing(r)) {
-							int j, k;
-							for (j = 0; j < 2; ++j)
-								for (k = 0; k < r->bwa_seq[j].n_aln; ++k) q += r->bwa_seq[j].aln[k].l - r->bwa_seq[j].aln[k].k + 1;
-						}
+						const long long w = is_pair_job(r) && wants_pairing(r) ? n_rows(r) : 0;
+						if (hi > lo && rows + w > max_q) break;
+						rows += w;
 						++hi;
 					}
-					finish_range(recs, lo, hi, iinfos, n_tot, n_mapped, my_hash);
+					b2->recs = recs + lo; b2->n = hi - lo; b2->iinfos = iinfos;
+					stage_enumerate(b2, my_hash);
+					stage_pairing(b2);
+					stage_rescue(b2, n_tot, n_mapped);
+					stage_refine(b2);
 					lo = hi;
 				}
 		}
@@ -1421,7 +1639,17 @@ void *run_worker_thread(void *arg)
 	for (it = kh_begin(my_hash); it != kh_end(my_hash); ++it)
 		if (kh_exist(my_hash, it)) free(kh_val(my_hash, it).a);
 	kh_destroy(64, my_hash);
+	b2->recs = 0; batch2_free(b2); free(b2);
+	saq_free(&q1); free(qoff);
 	free(recs); free(flat); free(taken);
 	zmq_close(upstream);
+	return 0;
+}
+
+/* ------------------------------------------------------------------ for hosts that run bam2bam in-process */
+int bwa_gpu_batch_last_report(bwa_gpu_batch_report_t *out)
+{
+	if (!out) return 1;
+	*out = g_rep;
 	return 0;
 }

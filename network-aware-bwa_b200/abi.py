@@ -116,6 +116,10 @@ class sw_job_t(C.Structure):
     _fields_ = [("beg", C.c_int64), ("reglen", C.c_int32), ("len", C.c_int32), ("seq", C.POINTER(C.c_ubyte))]
 
 
+class ga_job_t(C.Structure):
+    _fields_ = [("ref", C.POINTER(C.c_ubyte)), ("reflen", C.c_int32), ("len", C.c_int32), ("seq", C.POINTER(C.c_ubyte))]
+
+
 class sw_res_t(C.Structure):
     _fields_ = [("score", C.c_int32), ("start_i", C.c_int32), ("start_j", C.c_int32),
                 ("end_i", C.c_int32), ("end_j", C.c_int32)]

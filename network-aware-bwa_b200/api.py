@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
         L.bwa_gpu_mate_sw_path.argtypes = [C.c_int, C.POINTER(abi.sw_job_t), C.POINTER(abi.path_res_t), C.POINTER(C.c_void_p)]
         L.bwa_gpu_global_align.argtypes = [C.c_int, C.POINTER(abi.sw_job_t), C.c_int, C.c_int, C.POINTER(abi.path_res_t),
                                            C.POINTER(C.c_void_p)]
+        L.bwa_gpu_global_align_seqs.argtypes = [C.c_int, C.POINTER(abi.ga_job_t), C.c_int, C.c_int, C.POINTER(abi.path_res_t),
+                                                C.POINTER(C.c_void_p)]
         L.bwa_gpu_get_stats.argtypes = [C.POINTER(abi.stats_t)]
         L.bwa_gpu_set_stats.argtypes = [C.c_int]
         L.bwa_gpu_resident_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t)]
@@ -60,6 +62,7 @@ def lib() -> C.CDLL:
 EXPORTS = [
     "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_load_pac", "bwa_gpu_destroy", "bwa_gpu_last_error",
     "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw", "bwa_gpu_mate_sw_path", "bwa_gpu_global_align",
+    "bwa_gpu_global_align_seqs",
     "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_probe_random_sectors",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
     "bwa_gpu_index_build", "bwa_gpu_index_free", "bwa_gpu_index_write",
@@ -204,6 +207,25 @@ def global_align(jobs, gap_end: int = 5, band: int = 50):
     res = (abi.path_res_t * n)()
     pool = C.c_void_p()
     _ck(lib().bwa_gpu_global_align(n, arr, gap_end, band, res, C.byref(pool)))
+    return _path_results(res, pool, n)
+
+
+def global_align_seqs(pairs, gap_end: int = 5, band: int = 50):
+    """pairs: list of (ref uint8 array, seq uint8 array) -> like global_align"""
+    n = len(pairs)
+    arr = (abi.ga_job_t * n)()
+    keep = []
+    for i, (ref, seq) in enumerate(pairs):
+        r = np.ascontiguousarray(ref, dtype=np.uint8)
+        s = np.ascontiguousarray(seq, dtype=np.uint8)
+        keep += [r, s]
+        arr[i].ref = r.ctypes.data_as(C.POINTER(C.c_ubyte))
+        arr[i].reflen = r.size
+        arr[i].seq = s.ctypes.data_as(C.POINTER(C.c_ubyte))
+        arr[i].len = s.size
+    res = (abi.path_res_t * n)()
+    pool = C.c_void_p()
+    _ck(lib().bwa_gpu_global_align_seqs(n, arr, gap_end, band, res, C.byref(pool)))
     return _path_results(res, pool, n)
 
 

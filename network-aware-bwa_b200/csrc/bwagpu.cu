@@ -1204,7 +1204,9 @@ extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint
 }
 
 // ------------------------------------------------------------------ K5
-static std::vector<uint16_t> g_cigar_pool; // result pool of the last K6 call
+// result pools of the last K6 calls: one per entry-point family, so that a host thread reading the CIGARs of its
+// bwa_gpu_mate_sw_path call is not disturbed by another thread's bwa_gpu_global_align* call (and vice versa)
+static std::vector<uint16_t> g_cigar_pool_sw, g_cigar_pool_ga;
 
 static int sw_entry(int n, const bwa_gpu_sw_job_t *jobs, int mode, int gap_end, int band, bwa_gpu_sw_res_t *res,
                     bwa_gpu_path_res_t *pres, const bwa_cigar_t **cigar_pool, const char *who)
@@ -1218,9 +1220,10 @@ static int sw_entry(int n, const bwa_gpu_sw_job_t *jobs, int mode, int gap_end, 
 	double ms = 0;
 	std::vector<bwa_gpu_sw_res_t> tmp;
 	if (mode == 1 && !res) { tmp.resize(n); res = tmp.data(); }
-	const int rc = sw_batch(c->sw, c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &g_cigar_pool : nullptr, fail, &ms);
+	std::vector<uint16_t> &pool = mode == 1 ? g_cigar_pool_sw : g_cigar_pool_ga;
+	const int rc = sw_batch(c->sw, c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &pool : nullptr, fail, &ms);
 	c->stats.ms_sw_kernel = ms;
-	if (mode && cigar_pool) *cigar_pool = g_cigar_pool.data();
+	if (mode && cigar_pool) *cigar_pool = pool.data();
 	return rc;
 }
 
@@ -1239,4 +1242,19 @@ extern "C" int bwa_gpu_global_align(int n, const bwa_gpu_sw_job_t *jobs, int gap
 {
 	if (band < 1) return fail("bwa_gpu_global_align: band must be >= 1");
 	return sw_entry(n, jobs, 2, gap_end, band, nullptr, res, cigar_pool, "bwa_gpu_global_align");
+}
+
+extern "C" int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
+                                         const bwa_cigar_t **cigar_pool)
+{
+	std::lock_guard<std::mutex> g(g_mu);
+	if (g_ctx.empty()) return fail("bwa_gpu_global_align_seqs: bwa_gpu_init has not been called (no CPU fallback)");
+	if (band < 1) return fail("bwa_gpu_global_align_seqs: band must be >= 1");
+	if (n < 0 || (n && (!jobs || !res || !cigar_pool))) return fail("bwa_gpu_global_align_seqs: bad argument");
+	Ctx *c = g_ctx[0];
+	CK(cudaSetDevice(c->dev));
+	double ms = 0;
+	const int rc = ga_seqs_batch(c->sw, c->st, n, jobs, gap_end, band, res, &g_cigar_pool_ga, fail, &ms);
+	*cigar_pool = g_cigar_pool_ga.data();
+	return rc;
 }

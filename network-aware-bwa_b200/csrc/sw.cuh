@@ -296,7 +296,8 @@ __device__ __forceinline__ int g_setD(uint8_t &c, const GScore &p, int ext)
 
 // ref base i (1-based, window-relative) = pac_base(pac, rbeg + i - 1); query base j = q[j - 1].
 // cells: (len2 + 1) * width bytes; sc0/sc1: len1 + 2 GScore each; cig: len1 + len2 + 2 u16 (filled from its END).
-__device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, long long rbeg, int len1, const uint8_t *__restrict__ q,
+// pac == nullptr: the reference bases are given one per byte at refb[0 .. len1) instead (bwa_gpu_global_align_seqs).
+__device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, const uint8_t *__restrict__ refb, long long rbeg, int len1, const uint8_t *__restrict__ q,
                                       int len2, int gap_end, int band, uint8_t *cells, GRow sc0, GRow sc1,
                                       uint16_t *cig, int cig_cap)
 {
@@ -311,7 +312,7 @@ __device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, long long
 	const int width = (b1 + b2 <= len1) ? b1 + b2 + 1 : len1 + 1;
 	GRow curr = sc0, last = sc1, sw;
 #define GCELL(j, i) cells[((size_t)(j) * width + ((j) > b2 ? (i) - ((j) - b2) : (i))) * 32]
-#define GSC(i) sw_sc(pac_base(pac, rbeg + (i) - 1), qj)
+#define GSC(i) sw_sc(pac ? pac_base(pac, rbeg + (i) - 1) : (int)refb[(i) - 1], qj)
 	int i, j, end;
 	curr[0].M = 0; curr[0].I = curr[0].D = G_INF;
 	for (i = 1; i < b1; ++i) {
@@ -405,7 +406,7 @@ __device__ GlobalOut global_align_dev(const uint8_t *__restrict__ pac, long long
 }
 
 struct PathJob { // one K6 job; mode 0: plain global alignment, mode 1: third pass of aln_local_core inside a K5 box
-	long long beg;
+	long long beg;   // pac coordinate of the window -- or, without a pac (explicit reference bases), their offset in the byte array
 	int len1, len2;
 	long long q_off;
 	long long cig_off;
@@ -432,7 +433,8 @@ __global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac,
 		bwa_gpu_path_res_t r;
 		r.cigar_off = J.cig_off;
 		if (!boxes) { // refine_gapped_core's call (bwase.c:212)
-			const GlobalOut o = global_align_dev(pac, J.beg, J.len1, reads + J.q_off, J.len2, gap_end, band, cells, sc0, sc1, cig, cig_cap);
+			const GlobalOut o = pac ? global_align_dev(pac, nullptr, J.beg, J.len1, reads + J.q_off, J.len2, gap_end, band, cells, sc0, sc1, cig, cig_cap)
+			                        : global_align_dev(nullptr, reads + J.beg, 0, J.len1, reads + J.q_off, J.len2, gap_end, band, cells, sc0, sc1, cig, cig_cap);
 			r.score = o.score; r.n_cigar = o.n_cigar;
 			r.start_i = o.start_i; r.start_j = o.start_j; r.end_i = o.end_i; r.end_j = o.end_j;
 		} else { // aln_local_core's third pass (stdaln.c:723-745)
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac,
 				int span = (b.end_i - b.start_i > b.end_j - b.start_j ? b.end_i - b.start_i : b.end_j - b.start_j) + 1;
 				GlobalOut o;
 				for (int bw = 50;; bw <<= 1) {
-					o = global_align_dev(pac, J.beg + b.start_i - 1, l1, reads + J.q_off + b.start_j - 1, l2, -1, bw, cells, sc0, sc1, cig, cig_cap);
+					o = global_align_dev(pac, nullptr, J.beg + b.start_i - 1, l1, reads + J.q_off + b.start_j - 1, l2, -1, bw, cells, sc0, sc1, cig, cig_cap);
 					if (o.score == sr || score_f == o.score) break;
 					if (bw > span) break;
 				}
@@ -587,6 +589,79 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 	if (mode != 2 && res)
 		for (int i = 0; i < n; ++i)
 			if (res[i].score <= -3) return fail("job %d hit an unsupported case (code %d)", i, res[i].score);
+	return 0;
+}
+
+// bwa_gpu_global_align_seqs: aln_global_core on explicit sequence pairs (both given one base per byte).  The same K6 kernel,
+// its reference bases read from the byte array the reads are in instead of the packed genome.
+static int ga_seqs_batch(SwScratch &S, cudaStream_t st, int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *pres,
+                         std::vector<uint16_t> *cigars, int (*fail)(const char *, ...), double *kernel_ms)
+{
+	if (kernel_ms) *kernel_ms = 0;
+	cigars->clear();
+	if (n == 0) return 0;
+	std::vector<PathJob> pj(n);
+	int len1_max = 1, len2_max = 1;
+	long long b_total = 0, cig_total = 0;
+	for (int i = 0; i < n; ++i) {
+		const bwa_gpu_ga_job_t &j = jobs[i];
+		if (j.reflen < 0 || j.len < 0 || (j.reflen > 0 && !j.ref) || (j.len > 0 && !j.seq)) return fail("job %d is malformed", i);
+		pj[i].beg = b_total; pj[i].len1 = j.reflen; pj[i].len2 = j.len; pj[i].q_off = b_total + j.reflen; pj[i].cig_off = cig_total;
+		b_total += (long long)j.reflen + j.len;
+		cig_total += (long long)j.reflen + j.len + 2;
+		if (j.reflen > len1_max) len1_max = j.reflen;
+		if (j.len > len2_max) len2_max = j.len;
+	}
+	std::vector<uint8_t> hb((size_t)b_total + 1);
+	for (int i = 0; i < n; ++i) {
+		uint8_t *d = hb.data() + pj[i].beg;
+		for (int t = 0; t < jobs[i].reflen; ++t) d[t] = jobs[i].ref[t] > 3 ? 4 : jobs[i].ref[t];
+		d += jobs[i].reflen;
+		for (int t = 0; t < jobs[i].len; ++t) d[t] = jobs[i].seq[t] > 3 ? 4 : jobs[i].seq[t];
+	}
+	uint8_t *d_b = nullptr; int *d_cnt = nullptr; PathJob *d_pj = nullptr; bwa_gpu_path_res_t *d_pres = nullptr; uint16_t *d_cig = nullptr;
+	uint8_t *d_cells = nullptr; GScore *d_sc = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	cudaError_t e;
+	auto cleanup = [&]() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
+#define SWALLOC(ptr, k, bytes) do { e = S.reserve(k, bytes); if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); } ptr = (decltype(ptr))S.p[k]; } while (0)
+#define SWCK(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return fail("%s: %s", #x, cudaGetErrorString(e)); } } while (0)
+	int dev = 0, n_sm = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+	const size_t cells_stride = ((size_t)(len2_max + 1) * (len1_max + 1) + 15) & ~(size_t)15, sc_stride = (size_t)len1_max + 2;
+	const size_t per_thread = cells_stride + 2 * sc_stride * sizeof(GScore);
+	size_t threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
+	const size_t budget = (size_t)6 << 30;
+	if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
+	SWALLOC(d_b, 0, hb.size());
+	SWALLOC(d_cnt, 1, 2 * sizeof(int));
+	SWALLOC(d_pj, 5, (size_t)n * sizeof(PathJob));
+	SWALLOC(d_pres, 6, (size_t)n * sizeof(bwa_gpu_path_res_t));
+	SWALLOC(d_cig, 7, (size_t)cig_total * sizeof(uint16_t) + 16);
+	SWALLOC(d_cells, 8, threads * cells_stride);
+	SWALLOC(d_sc, 9, threads * 2 * sc_stride * sizeof(GScore));
+	SWCK(cudaMemcpyAsync(d_b, hb.data(), hb.size(), cudaMemcpyHostToDevice, st));
+	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+	SWCK(cudaMemcpyAsync(d_pj, pj.data(), (size_t)n * sizeof(PathJob), cudaMemcpyHostToDevice, st));
+	cigars->resize((size_t)cig_total);
+	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1));
+	SWCK(cudaEventRecord(e0, st));
+	k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(nullptr, d_pj, n, d_b, gap_end, band, nullptr, nullptr, d_pres, d_cig, d_cells, cells_stride,
+	                                                   d_sc, sc_stride, d_cnt + 1);
+	SWCK(cudaGetLastError());
+	SWCK(cudaEventRecord(e1, st));
+	SWCK(cudaMemcpyAsync(pres, d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t), cudaMemcpyDeviceToHost, st));
+	if (cig_total) SWCK(cudaMemcpyAsync(cigars->data(), d_cig, (size_t)cig_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+	SWCK(cudaStreamSynchronize(st));
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (kernel_ms) *kernel_ms = ms;
+	}
+#undef SWCK
+#undef SWALLOC
+	cleanup();
 	return 0;
 }
 

@@ -15,6 +15,7 @@
 #include "bwtaln.h"
 #include "bwt.h"
 #include "stdaln.h"
+#include "bwase.h"
 #include "bwa_gpu.h"
 
 static bwt_t *s_bwt[2];
@@ -70,5 +71,36 @@ int bwa_gpu_mate_sw_path(int n, const bwa_gpu_sw_job_t *jobs, bwa_gpu_path_res_t
 		free(ref); free(path);
 	}
 	*cigar_pool = s_pool;
+	return 0;
+}
+
+static bwa_cigar_t *g_pool;
+static size_t g_pool_n, g_pool_m;
+int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res, const bwa_cigar_t **cigar_pool)
+{
+	int i;
+	AlnParam ap = aln_param_bwa;
+	ap.gap_end = gap_end; ap.band_width = band;
+	g_pool_n = 0;
+	for (i = 0; i < n; ++i) {
+		const bwa_gpu_ga_job_t *jb = &jobs[i];
+		path_t *path = (path_t *)calloc(jb->reflen + jb->len + 2, sizeof(path_t));
+		int path_len = 0, n_cigar = 0, c;
+		bwa_cigar_t *cg;
+		memset(&res[i], 0, sizeof(res[i]));
+		res[i].score = aln_global_core((ubyte_t *)jb->ref, jb->reflen, (ubyte_t *)jb->seq, jb->len, &ap, path, &path_len);
+		res[i].cigar_off = (int64_t)g_pool_n;
+		cg = bwa_aln_path2cigar(path, path_len, &n_cigar);
+		if (g_pool_n + n_cigar > g_pool_m) { g_pool_m = (g_pool_n + n_cigar) * 2 + 1024; g_pool = (bwa_cigar_t *)realloc(g_pool, g_pool_m * sizeof(bwa_cigar_t)); }
+		for (c = 0; c < n_cigar; ++c) g_pool[g_pool_n++] = cg[c];
+		free(cg);
+		res[i].n_cigar = n_cigar;
+		if (path_len > 0) {
+			res[i].start_i = path[path_len - 1].i; res[i].start_j = path[path_len - 1].j;
+			res[i].end_i = path[0].i; res[i].end_j = path[0].j;
+		}
+		free(path);
+	}
+	*cigar_pool = g_pool;
 	return 0;
 }

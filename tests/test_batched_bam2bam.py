@@ -19,7 +19,7 @@ import bamio
 import refload as R
 
 ROOT = R.ROOT
-DRIVER = os.path.join(R.REF_DIR, "ref_driver")
+DRIVER = os.path.join(R.ROOT, "integration", "_host", "bwa_host")  # the product host build of the unmodified reference
 SHIM = os.path.join(ROOT, "integration", "libbwa_gpu_batch.so")
 STUB = os.path.join(ROOT, "tests", "cpu_stub", "libbwagpu_cpu_stub.so")
 
@@ -49,7 +49,7 @@ def run_bam2bam(prefix, bam_in, bam_out, mode, extra=(), env_extra=None):
 @pytest.fixture(scope="module")
 def genome(tmp_path_factory):
     if not (os.path.exists(DRIVER) and os.path.exists(SHIM) and os.path.exists(R.REF_BWA)):
-        pytest.skip("oracle/_ref or the batch shim is not built")
+        pytest.skip("integration/_host, oracle/_ref or the batch shim is not built")
     d = tmp_path_factory.mktemp("batched")
     # wide repeat families so that intervals >= 1000 rows (the pass-2 position cache, bam2bam.c:743) occur
     T = R.bwa.simulate.make_genome(600000, seed=8, repeat_frac=0.08, max_copies=5)
@@ -106,7 +106,9 @@ def se_case(genome, mode):
     c = calls(log)
     assert c["cal_sa_reads_gap"] == 5 and c["cal_sa_reads_gap_units"] == 3000  # ceil(3000 / 700) batches, every read once
     assert c["cal_pac_pos_units"] > 2500
+    assert c["global_align_units"] > 50  # the gapped hits' CIGARs came through the batched aln_global_core
     assert sum(b"XA" in r for r in recs) > 0
+    assert "not a BGZF file" in log  # a plain gzip stream cannot be inflated in parallel: said so, read ahead on one thread
 
 
 def pe_case(genome, mode):
@@ -117,12 +119,13 @@ def pe_case(genome, mode):
         b1[30 * t] = T[Y:Y + 70]
         b2[30 * t] = 3 - T[X:X + 70][::-1]
     bam = str(d / "pe.bam")
-    bamio.write_unaligned_bam(bam, r1, r2)
+    bamio.write_unaligned_bam_fast(bam, r1, r2)  # BGZF: the shim inflates its blocks on several threads
     cpu_log = run_bam2bam(fa, bam, str(d / "pe_cpu.bam"), None)
     # small record batches AND small SA-row sub-ranges: cache entries are created in one range and reused in later ones
     log = run_bam2bam(fa, bam, str(d / f"pe_{mode}.bam"), mode, env_extra={"BWAGPU_BATCH_RECORDS": "600", "BWAGPU_BATCH_SA": "3000"})
     compare(str(d / "pe_cpu.bam"), str(d / f"pe_{mode}.bam"))
     c = calls(log)
+    assert "not a BGZF file" not in log
     assert c["cal_sa_reads_gap_units"] == 5000
     assert c["mate_sw_path_units"] > 20          # mate rescue ran through the batch call
     assert c["cal_pac_pos_units"] > 5000
@@ -260,6 +263,11 @@ def test_stub_worker_remote(genome, stub):
 @pytest.mark.gpu
 def test_gpu_worker_local(genome):
     worker_case(genome, "gpu", remote=False)
+
+
+@pytest.mark.gpu
+def test_gpu_worker_remote(genome):
+    worker_case(genome, "gpu", remote=True)
 
 
 @pytest.mark.gpu

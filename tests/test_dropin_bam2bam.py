@@ -13,7 +13,7 @@ import refload as R
 
 pytestmark = pytest.mark.gpu
 ROOT = R.ROOT
-DRIVER = os.path.join(R.REF_DIR, "ref_driver")
+DRIVER = os.path.join(R.ROOT, "integration", "_host", "bwa_host")  # the product host build of the unmodified reference
 SHIM = os.path.join(ROOT, "integration", "libbwa_gpu_interpose.so")
 
 

@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- reads/sec of the `bwa aln` hot path (K2 width + K3 gapped search + ordered
-compaction) on BASELINE.json configs[1]: single-end 76 bp reads, default options
-(-n 0.04 -o 1), vs a synthetic 100 Mb genome, one B200 per rank.
+"""bench.py -- reads/sec of the whole alignment workflow (aln + sampe: `bwa bam2bam`, BAM in -> BAM out, both passes)
+on BASELINE.json configs[3]: paired-end 2 x 100 bp reads against a synthetic 3.1 Gb genome, default options, one B200
+per rank, against the reference's own `bwa bam2bam -t <host cores>` on the same box.
 
-    python bench.py --gpus 1 --steps 3 --warmup 3            # this repo's CUDA path
-    python bench.py --impl reference --steps 1 --warmup 0    # the reference's CPU path, all host cores
-    torchrun ... bench.py --gpus N ...                       # weak scaling: one replica + one read shard per GPU
+    python bench.py --gpus 1 --steps 3 --warmup 3            # this repo: hot path on the B200 behind the reference's host code
+    python bench.py --impl reference --steps 3 --warmup 1    # the unmodified reference, `bam2bam -t <nproc>`, same input
+    torchrun ... bench.py --gpus N ...                       # weak scaling: one index replica + one shard of pairs per GPU
 
-One JSON line on stdout (rank 0).  `value` = whole-job reads/s with the batch resident in
-HBM (CUDA events inside the library, on the stream the kernels run on); `e2e` = the same
-through the C-ABI call with host buffers (H2D and D2H inside the timed region); `roofline`
-= occ-lookup bytes of the dominant kernel (k_search) against the measured HBM peak;
-`cpu_baseline` = the reference's own bwa_cal_sa_reg_gap on this box's host cores on a
-bounded sample.  Only the cpu_baseline / --impl reference legs and the parity spot-check
-touch oracle/.
+A step = one bam2bam run over the rank's shard (--pairs pairs, default 500 000): the reference's own host code
+(integration/_host/libbwahost.so, built from /root/reference unmodified) run IN-PROCESS with the batched drivers of
+integration/libbwa_gpu_batch.so in place of its two loops, so every alignment call lands in libbwagpu.so:
+bwa_gpu_cal_sa_reads_gap (K2 widths + K3 gapped search), bwa_gpu_cal_pac_pos (K4), bwa_gpu_mate_sw_path (K5 + K6),
+bwa_gpu_global_align_seqs (K6).  One JSON line on stdout (rank 0):
+
+  value     reads/s with the inputs of every device call resident in HBM: the step's reads over the kernel-only device time
+            of all its calls (CUDA events inside the library, on the streams the kernels run on)
+  e2e       reads/s of the whole run through the reference-facing entry point (bwa_bam_to_bam) with host buffers: BAM
+            inflate, record parsing, every H2D/D2H copy, pairing, BAM rewrite and deflate inside the timed region (the
+            index load, which the reference reports separately and a long job pays once, is not)
+  roofline  occ-lookup bytes of the dominant kernel (k_search) against the measured HBM peak, timed alone on a resident batch
+  cpu_baseline / --impl reference: `oracle/_ref/bwa bam2bam -t <cores>` (the reference compiled here, unmodified), wall minus
+            the index load it prints.
+Only the cpu_baseline / --impl reference legs and the parity check run anything under oracle/.
 """
 from __future__ import annotations
 
@@ -33,15 +41,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-GENOME_BP = 100_000_000
-READ_LEN = 76
-READS_TOTAL = 10_000_000  # the configuration the metric is quoted on
-METRIC = "reads/sec (aln: bwa_cal_sa_reg_gap per read = width bounds + gapped FM-index search)"
-WORKLOAD = "SE 10M x 76bp, -n 0.04 -o 1, synthetic 100 Mb genome (BASELINE.json configs[1])"
+GENOME_BP = 3_100_000_000
+READ_LEN = 100
+PAIRS_PER_STEP = 500_000
+METRIC = "reads/sec (aln+sampe: bam2bam pass 1 + pass 2, BAM in -> BAM out)"
+REF_BWA = os.path.join(ROOT, "oracle", "_ref", "bwa")
+SHIM = os.path.join(ROOT, "integration", "libbwa_gpu_batch.so")
 
 
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def workload_name(genome_bp: int, read_len: int) -> str:
+    tag = "BASELINE.json configs[3]" if (genome_bp, read_len) == (GENOME_BP, READ_LEN) else "non-default shape"
+    return (f"PE 2x{read_len}bp bam2bam (sampe pairing + mate-rescue SW), defaults -n 0.04 -o 1, synthetic {genome_bp / 1e9:.2f} Gb genome "
+            f"({tag})")
 
 
 # ------------------------------------------------------------------ clocks
@@ -89,75 +104,122 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------ workload
-def make_workload(bwa, n_reads: int, device: str, seed: int, genome_bp: int, read_len: int = READ_LEN):
+# ------------------------------------------------------------------ workload files
+def pairs_bam(bwa, prefix: str, T, n_pairs: int, read_len: int, seed: int, device: str) -> str:
+    """The rank's input: an unaligned paired BAM (BGZF) of n_pairs simulated pairs, cached beside the genome."""
+    import bamio
+    path = f"{prefix}.pe{read_len}_{n_pairs}_s{seed}.bam"
+    if os.path.exists(path):
+        return path
     t0 = time.time()
-    if genome_bp >= 1_000_000_000:  # cached genome + index files (workload.py)
-        T, idx = bwa.workload.genome_and_index(genome_bp, seed=1, device=torch_device_index(device))
-        t1 = t2 = time.time()
-    else:
-        T = bwa.simulate.make_genome(genome_bp, seed=1, repeat_frac=0.01)
-        t1 = time.time()
-        idx = bwa.index.build_index(T, device=device)
-        t2 = time.time()
-    reads = bwa.simulate.simulate_reads(T, n_reads, read_len, seed=seed, device=device)
-    t3 = time.time()
-    log(f"[bench] genome {t1 - t0:.1f}s, index ({device}) {t2 - t1:.1f}s, {n_reads} reads {t3 - t2:.1f}s")
-    return T, idx, reads
+    r1, r2 = bwa.simulate.simulate_pairs(T(), n_pairs, read_len, seed=seed, device=device)
+    tmp = path + f".tmp{os.getpid()}"
+    bamio.write_unaligned_bam_fast(tmp, r1, r2, threads=min(16, os.cpu_count() or 4), qual_seed=seed)
+    os.replace(tmp, path)
+    log(f"{n_pairs} pairs simulated and written in {time.time() - t0:.1f}s -> {path}")
+    return path
 
 
-def torch_device_index(device) -> int:
-    d = str(device)
-    return int(d.split(":")[1]) if ":" in d else 0
+def prefix_bam(src: str, n_pairs: int) -> str:
+    """The first n_pairs pairs of a cached input BAM as a file of their own (records of one size: cut the byte stream)."""
+    import gzip
+    import struct
+    from concurrent.futures import ThreadPoolExecutor
+    import bamio
+    dst = f"{src[:-4]}.first{n_pairs}.bam"
+    if os.path.exists(dst):
+        return dst
+    with gzip.open(src, "rb") as f:
+        head = f.read(8)
+        (l_text,) = struct.unpack_from("<i", head, 4)
+        head += f.read(l_text + 4)  # the text and n_ref (= 0: an unaligned BAM)
+        first = f.read(4)
+        (bs,) = struct.unpack("<i", first)
+        body = first + f.read((4 + bs) * 2 * n_pairs - 4)
+    data = head + body
+    B = 65280
+    with ThreadPoolExecutor(8) as ex:
+        blocks = list(ex.map(lambda i: bamio._bgzf_block(data[i:i + B], 1), range(0, len(data), B)))
+    tmp = dst + f".tmp{os.getpid()}"
+    with open(tmp, "wb") as f:
+        for b in blocks:
+            f.write(b)
+        f.write(bamio.BGZF_EOF)
+    os.replace(tmp, dst)
+    return dst
 
 
-def seq_struct_array(abi, reads):
-    """bwa_seq_t[n] over numpy storage, the way bam1_to_seq fills it (bwaseqio.c:272-297),
-    built vectorised: returns (ctypes array pointer, keepalive)."""
-    n = reads.n
-    lens = reads.lens().astype(np.int64)
-    assert (lens == lens[0]).all(), "vectorised builder expects fixed-length reads"
-    L = int(lens[0])
-    fwd = reads.bases.reshape(n, L)
-    seq = np.ascontiguousarray(fwd[:, ::-1])
-    rseq = np.where(seq > 3, 4, 3 - seq).astype(np.uint8)
-    rec = np.zeros((n, 200), dtype=np.uint8)
-    u64 = rec.view(np.uint64).reshape(n, 25)
-    u32 = rec.view(np.uint32).reshape(n, 50)
-    u64[:, 1] = seq.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(L)    # seq   @ 8
-    u64[:, 2] = rseq.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(L)   # rseq  @ 16
-    u32[:, 8] = L                                                                 # len:20 @ 32
-    u32[:, 11] = L                                                                # clip_len @ 44
-    u32[:, 28] = 0xFFFFFFFF                                                       # tid = -1 @ 112
-    u32[:, 45] = L                                                                # full_len:20 @ 180
-    ptr = C.cast(rec.ctypes.data, C.POINTER(abi.bwa_seq_t))
-    return ptr, (rec, seq, rseq)
+# ------------------------------------------------------------------ the reference: `bwa bam2bam -t N` as a process
+def run_reference(prefix: str, bam_in: str, bam_out: str, threads: int):
+    """-> (seconds of the run without the index load the reference prints, index load seconds)"""
+    t0 = time.perf_counter()
+    r = subprocess.run([REF_BWA, "bam2bam", "-g", prefix, "-t", str(threads), "-f", bam_out, bam_in], capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("reference bam2bam failed:\n" + r.stderr[-2000:])
+    load = [l for l in r.stderr.splitlines() if "loading index" in l]
+    load_s = float(load[0].split("...")[1].split()[0]) if load else 0.0
+    return dt - load_s, load_s
 
 
-# ------------------------------------------------------------------ reference arm / cpu baseline
-def time_reference(R, idx, reads, opt, target_s: float, threads: int):
-    """Times the reference's own bwa_cal_sa_reg_gap (n_seqs = 1 per read, as bam2bam calls it)
-    over `threads` host threads on a bounded prefix of the workload."""
-    abi = R.abi
-    ridx = R.RefIndex(idx)
-    _, H = R.ref()
-    probe = min(reads.n, 20000)
+# ------------------------------------------------------------------ this repo: bam2bam in-process behind the batched drivers
+class Report(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("wall_s", "index_load_s", "device_init_s", "pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s",
+                                          "dev_sw_s", "dev_ga_s", "inflate_cpu_s")] + \
+               [(n, C.c_int64) for n in ("calls_aln", "reads_aln", "calls_sa", "q_sa", "calls_sw", "jobs_sw", "calls_ga", "jobs_ga", "sequences")]
 
-    def run(lo, hi):
-        sub = R.bwa.simulate.Reads(reads.bases[reads.offs[lo]:reads.offs[hi]], reads.offs[lo:hi + 1] - reads.offs[lo], None, None)
-        ptr, keep = seq_struct_array(abi, sub)
-        t = time.perf_counter()
-        H.refh_aln_batch(ridx.arr, hi - lo, ptr, C.byref(opt), threads)
-        dt = time.perf_counter() - t
-        H.refh_free_alns.argtypes = [C.c_int, C.POINTER(abi.bwa_seq_t)]
-        H.refh_free_alns(hi - lo, ptr)
-        return dt
+    def asdict(self):
+        return {f[0]: getattr(self, f[0]) for f in self._fields_}
 
-    dt = run(0, probe)
-    rate = probe / dt
-    n = int(min(reads.n, max(probe, rate * target_s)))
-    dt = run(0, n)
-    return n / dt, n, dt
+
+class Host:
+    """integration/libbwa_gpu_batch.so loaded into this process; run() = the reference's bwa_bam_to_bam entry point."""
+
+    def __init__(self):
+        if not os.path.exists(SHIM):
+            raise SystemExit(f"bench.py: {SHIM} is not built (python -c 'import __graft_entry__ as g; g.build()')")
+        self.H = C.CDLL(SHIM)
+        self.H.bwa_bam_to_bam.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p]
+        self.H.bwa_gpu_batch_last_report.argtypes = [C.POINTER(Report)]
+        self.H.bwa_gpu_batch_keep_index(1)
+
+    def run(self, prefix: str, bam_in: str, bam_out: str):
+        args = [b"bam2bam", b"-g", prefix.encode(), b"-t", b"1", b"-f", bam_out.encode(), bam_in.encode()]
+        av = (C.c_char_p * (len(args) + 1))(*args, None)
+        sys.stderr.flush()
+        rc = self.H.bwa_bam_to_bam(len(args), av, b"bench")
+        if rc != 0:
+            raise RuntimeError(f"bwa_bam_to_bam returned {rc}")
+        rep = Report()
+        self.H.bwa_gpu_batch_last_report(C.byref(rep))
+        return rep.asdict()
+
+    def close(self):
+        self.H.bwa_gpu_batch_drop_index()
+
+
+def quiet_stderr(rank: int):
+    """The reference chats on stderr (a line per batch and per read length); it goes to a file, the bench log stays readable."""
+    if os.environ.get("BENCH_VERBOSE"):
+        return None
+    saved = os.dup(2)
+    fd = os.open(os.path.join(os.environ.get("TMPDIR", "/tmp"), f"bench_host_rank{rank}.log"), os.O_WRONLY | os.O_CREAT | os.O_APPEND, 0o644)
+    os.dup2(fd, 2)
+    os.close(fd)
+    return saved
+
+
+def restore_stderr(saved):
+    if saved is not None:
+        sys.stderr.flush()
+        os.dup2(saved, 2)
+        os.close(saved)
+
+
+def records_differing(a_path: str, b_path: str):
+    import bamio
+    a, b = bamio.read_bam_records(a_path), bamio.read_bam_records(b_path)
+    return len(a), sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
 
 
 def main():
@@ -166,68 +228,94 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (default: the full 10M-read workload; reference arm: bounded sample)")
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_STEP, help="read pairs per step per GPU (both arms)")
     ap.add_argument("--genome-bp", type=int, default=GENOME_BP)
-    ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (default 76: configs[1]; 100 = the paired-end shape of configs[2]/[3])")
+    ap.add_argument("--read-len", type=int, default=READ_LEN)
+    ap.add_argument("--aln-reads", type=int, default=4_000_000, help="reads of the resident aln-only batch the k_search roofline is measured on")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-aln-only", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     host_cores = os.cpu_count() or 1
+    config = {"workload": workload_name(args.genome_bp, args.read_len), "pairs_per_step_per_gpu": args.pairs, "read_len": args.read_len,
+              "genome_bp": args.genome_bp,
+              "l2": f"inputs larger than L2 (re-laid-out index {args.genome_bp / 1e9:.2f} GB per replica); the same shard every step"}
 
     import torch
-
     bwa = importlib.import_module("network-aware-bwa_b200")
-    abi, api = bwa.abi, bwa.api
-    opt = abi.default_gap_opt()  # -n 0.04 -o 1 are the defaults (bwtaln.c:19-35)
+    have_gpu = torch.cuda.is_available()
 
     # ------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        import refload as R
-        if not R.have_ref():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference at build time)"}))
+        if not os.path.exists(REF_BWA):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bwa was not built (no /root/reference at build time)"}))
             return 0
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
-        n_pool = args.reads or 400_000
-        T, idx, reads = make_workload(bwa, n_pool, dev, seed=1000, genome_bp=args.genome_bp, read_len=args.read_len)
-        target = 20.0
-        rates, ns, total_t = [], [], 0.0
-        for s in range(args.warmup + args.steps):
-            rate, n, dt = time_reference(R, idx, reads, opt, target_s=target, threads=host_cores)
-            if s >= args.warmup:
-                rates.append(rate); ns.append(n); total_t += dt
-        value = sum(ns) / total_t
+        cached = os.path.exists(os.path.join(bwa.workload.cache_root(), bwa.workload.genome_key(args.genome_bp, 1), ".done"))
+        if not have_gpu and not cached and args.genome_bp > 50_000_000:  # small genomes: the CPU harness builder will do
+            print(json.dumps({"impl": "reference", "unavailable": "the workload's index files are not cached and there is no device to build them on"}))
+            return 0
+        prefix = bwa.workload.ensure_genome_files(args.genome_bp, 1, 0)  # set-up only: the files `bwa index` would write
+        bam = pairs_bam(bwa, prefix, lambda: bwa.workload.load_genome(prefix), args.pairs, args.read_len, 1000, "cuda:0" if have_gpu else "cpu")
+        small = prefix_bam(bam, min(args.pairs, 20_000))
+        out = bam[:-4] + ".ref_out.bam"
+        for _ in range(args.warmup):  # page cache / index files warm: short runs
+            run_reference(prefix, small, out, host_cores)
+        total_t, loads, steps_ms = 0.0, [], []
+        for _ in range(args.steps):
+            dt, load_s = run_reference(prefix, bam, out, host_cores)
+            total_t += dt; loads.append(load_s); steps_ms.append(round(dt * 1e3, 1))
+        value = 2 * args.pairs * args.steps / total_t
         line = {
-            "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{ns[0]} reads per step", "threads": host_cores},
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": host_cores, "kind": "reference",
-                             "sample": f"{ns[0]}-read prefix of the workload per step, refh_aln_batch over {host_cores} threads"},
+                             "sample": f"the step's {args.pairs} pairs per step, `bwa bam2bam -t {host_cores}` (unmodified reference), wall minus the "
+                                       f"index load it prints ({np.mean(loads):.1f} s per run); warm-up runs on a 20k-pair prefix"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ms_each_step": steps_ms,
         }
         print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------- B200 arm
-    if not torch.cuda.is_available():
+    if not have_gpu:
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_reads = args.reads or READS_TOTAL
-    T, idx, reads = make_workload(bwa, n_reads, f"cuda:{local_rank}", seed=1000 + rank, genome_bp=args.genome_bp, read_len=args.read_len)
+    threads = max(2, host_cores // world)
+    os.environ.setdefault("BWAGPU_DEVICE", str(local_rank))
+    os.environ.setdefault("BWAGPU_SHIM_THREADS", str(threads))
+    os.environ.setdefault("BWAGPU_HOST_THREADS", str(max(1, min(8, threads // 3))))
+    os.environ.setdefault("BWAGPU_BATCH_RECORDS", str(1 << 16))
+
+    t0 = time.time()
+    prefix = bwa.workload.ensure_genome_files(args.genome_bp, 1, local_rank)
+    genome = {}
+
+    def T():
+        if "T" not in genome:
+            genome["T"] = bwa.workload.load_genome(prefix)
+        return genome["T"]
+
+    bam = pairs_bam(bwa, prefix, T, args.pairs, args.read_len, 1000 + rank, f"cuda:{local_rank}")
+    out = f"{bam[:-4]}.out.bam"
+    aln_reads = None
+    if rank == 0 and not args.no_aln_only:
+        aln_reads = bwa.simulate.simulate_reads(T(), args.aln_reads, args.read_len, seed=1000, device=f"cuda:{local_rank}")
+    genome.clear()
     torch.cuda.empty_cache()
-    api.init([local_rank])
-    api.load_index(idx)
+    log(f"rank {rank}: workload ready in {time.time() - t0:.1f}s ({threads} host threads per rank)")
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,172 +323,74 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: batch resident in HBM, device-timed
-    api.resident_stage(reads.bases, reads.offs, opt)
-    api.set_stats(True)
-    api.resident_run()  # instrumented pass (untimed): algorithmic fetch counts of this batch
-    st_counts = api.get_stats()
-    api.set_stats(False)
-    for _ in range(args.warmup):
-        api.resident_run()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t_wall0 = time.perf_counter()
-    dev_ms, search_ms, width_ms, launches = 0.0, 0.0, 0.0, 0
-    tier_ms = [0.0] * 4
-    for _ in range(args.steps):
-        dev_ms += api.resident_run()
-        st = api.get_stats()
-        search_ms += st["ms_search"]; width_ms += st["ms_width"]; launches += st["launches"]
-        tier_ms = [a + b for a, b in zip(tier_ms, st["ms_tier"])]
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    n_over2, n_over3 = st["n_overflow_t2"], st["n_overflow_t3"]
-    if dist is not None:
-        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms_max = float(t.item())
-    else:
-        dev_ms_max = dev_ms
-    value = world * n_reads * args.steps / (dev_ms_max / 1e3)
-
-    # ---- parity spot-check of the timed path against the reference (untimed)
-    parity = None
-    if rank == 0:
-        try:
-            import refload as R
-            if R.have_ref():
-                got = api.resident_fetch(reads.n)
-                m = min(reads.n, 20000)
-                sub = bwa.simulate.Reads(reads.bases[: reads.offs[m]], reads.offs[: m + 1], None, None)
-                want = R.ref_aln(R.RefIndex(idx), sub, opt, threads=host_cores)
-                got_sub = (got[0][:m], got[1][:m], got[2][: m + 1], got[3][: got[2][m]])
-                errs = R.compare_aln(want, got_sub, "bench")
-                parity = {"reads": m, "mismatches": len(errs), "checker": "oracle/_ref bwa_cal_sa_reg_gap"}
-        except Exception as e:  # the checker is optional on the bench box
-            parity = {"error": str(e)[:200]}
-
-    # ---- e2e: through the reference-facing C-ABI call, host buffers, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        ptr, keep = seq_struct_array(abi, reads)
-        lib = api.lib()
-        for _ in range(min(args.warmup, 2)):
-            assert lib.bwa_gpu_cal_sa_reads_gap(reads.n, ptr, C.byref(opt)) == 0, lib.bwa_gpu_last_error()
-            lib.bwa_gpu_free_alns(reads.n, ptr)
+    api = bwa.api
+    host = Host()
+    saved = quiet_stderr(rank)
+    try:
+        for _ in range(max(1, args.warmup)):  # the first run also loads the index and sets the device up
+            host.run(prefix, bam, out)
+        api.reset_totals()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         barrier()
-        e2e_s = 0.0
-        e2e_steps = []
-        n_aln_tot = 0
+        t_wall0 = time.perf_counter()
+        e2e_s, steps_ms, reps = 0.0, [], []
         for _ in range(args.steps):
-            t0 = time.perf_counter()
-            rc = lib.bwa_gpu_cal_sa_reads_gap(reads.n, ptr, C.byref(opt))
-            e2e_steps.append(1e3 * (time.perf_counter() - t0))
-            e2e_s += e2e_steps[-1] / 1e3
-            assert rc == 0, lib.bwa_gpu_last_error()
-            n_aln_tot = int(api.get_stats()["n_aln"])
-            lib.bwa_gpu_free_alns(reads.n, ptr)  # untimed: the caller's bwa_free_read_seq1
+            t1 = time.perf_counter()
+            rep = host.run(prefix, bam, out)
+            dt = time.perf_counter() - t1 - rep["index_load_s"]
+            e2e_s += dt; steps_ms.append(round(dt * 1e3, 1)); reps.append(rep)
         barrier()
-        if dist is not None:
-            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": world * n_reads * args.steps / e2e_s, "unit": "reads/s",
-               "h2d_bytes_per_step": int(reads.bases.size + 16 * reads.n),
-               "d2h_bytes_per_step": int(8 * reads.n + 16 * n_aln_tot),
-               "api": "bwa_gpu_cal_sa_reads_gap(n, bwa_seq_t*, gap_opt_t*) incl. per-read calloc of aln[]",
-               "ms_each_step_rank0": [round(x, 1) for x in e2e_steps]}
-
-    # ---- cpu baseline (rank 0, N = 1 only): the reference itself on a bounded sample
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            import refload as R
-            if R.have_ref():
-                rate, n, dt = time_reference(R, idx, reads, opt, target_s=15.0, threads=host_cores)
-                cpu_baseline = {"value": rate, "unit": "reads/s", "cores": host_cores, "kind": "reference",
-                                "sample": f"first {n} reads of the step's batch, {dt:.1f} s, refh_aln_batch "
-                                          f"(bwa_cal_sa_reg_gap per read) over {host_cores} threads"}
-        except Exception as e:
-            cpu_baseline = {"error": str(e)[:200]}
-
-    # ---- roofline context (rank 0): what pure dependent random 32-byte sector gathers sustain on this device
-    random_sector = None
-    if rank == 0 and not args.no_extras:
-        try:
-            random_sector = {"buffer_bytes": 2_300_000_000, "unit": "GB/s",
-                             "by_chains_per_thread": {str(ch): api.probe_random_sectors(2_300_000_000, ch, 256) for ch in (1, 2, 4, 8)},
-                             "index_sized_buffer": {"buffer_bytes": int(args.genome_bp), "chains4": api.probe_random_sectors(int(args.genome_bp), 4, 256)},
-                             "note": "k_probe_gather: 8 x 256 threads per SM, each chain's next index depends on the sector just loaded"}
-        except Exception as e:
-            random_sector = {"error": str(e)[:200]}
-
-    # ---- secondary kernels of the path (rank 0, N = 1): K4 SA->coordinate and K5 mate-rescue SW
-    extras = None
-    if rank == 0 and world == 1 and not args.no_extras:
-        rng = np.random.default_rng(5)
-        nq = 4_000_000
-        sa_k = rng.integers(1, idx.bwt[0].seq_len + 1, size=nq, dtype=np.uint32)
-        which = rng.integers(0, 2, size=nq, dtype=np.uint8)
-        api.cal_pac_pos(sa_k[:1000], which[:1000])
-        t0 = time.perf_counter(); api.cal_pac_pos(sa_k, which); dt4 = time.perf_counter() - t0
-        steps4 = float(np.mean(sa_k % 32))  # LF steps to the next sampled row when rows are uniform
-        nj, wlen, rlen = 200_000, 380, 100  # 2x100 bp, sigma 30: window = 6 sigma + 2 len (bwape.c:531-543)
-        begs = rng.integers(0, idx.l_pac - wlen - 1, size=nj)
-        sw_jobs = (abi.sw_job_t * nj)()
-        qkeep = []
-        for j in range(nj):
-            b = int(begs[j]); o = int(rng.integers(0, wlen - rlen))
-            q = T[b + o:b + o + rlen].copy(); q[rng.integers(0, rlen, size=3)] ^= 1
-            qkeep.append(q)
-            sw_jobs[j].beg, sw_jobs[j].reglen, sw_jobs[j].len = b, wlen, rlen
-            sw_jobs[j].seq = q.ctypes.data_as(C.POINTER(C.c_ubyte))
-        sw_res = (abi.sw_res_t * nj)()
-        lib = api.lib()
-        assert lib.bwa_gpu_mate_sw(1000, sw_jobs, sw_res) == 0
-        t0 = time.perf_counter(); rc = lib.bwa_gpu_mate_sw(nj, sw_jobs, sw_res); dt5 = time.perf_counter() - t0
-        assert rc == 0, lib.bwa_gpu_last_error()
-        sw_ms = api.get_stats()["ms_sw_kernel"]
-        extras = {"k4_sa": {"queries_per_s": nq / dt4, "host_call_ms": dt4 * 1e3, "lf_steps_per_query": steps4,
-                            "algorithmic_gb_s": 64.0 * steps4 * nq / dt4 / 1e9, "note": "host buffers in and out"},
-                  "k5_sw": {"jobs_per_s": nj / dt5, "host_call_ms": dt5 * 1e3, "gcups_forward": nj * wlen * rlen / dt5 / 1e9,
-                            "kernel_ms": sw_ms, "gcups_forward_kernel": nj * wlen * rlen / (sw_ms / 1e3) / 1e9,
-                            "shape": f"{wlen} x {rlen}", "note": "host buffers in and out; forward + reverse pass"}}
-
-        # C5 of BASELINE.json (a parity-test configuration, reported here as a secondary number): ancient-DNA-style 30-50 bp
-        # reads, seeding off (-l 1024), -n 0.01 -o 2.  ~10 % of the reads outgrow pass 0 and go through the warp-per-read
-        # pass (csrc/search_warp.cuh); the batch is resident, device-timed like `value`.
-        try:
-            import refload as R
-            n5 = 1_000_000
-            reads5 = bwa.simulate.simulate_reads(T, n5, (30, 50), seed=1000, device=f"cuda:{local_rank}", adna=True, sub_rate=0.01)
-            opt5 = abi.default_gap_opt(seed_len=1024, fnr=0.01, max_gapo=2)
-            api.resident_stage(reads5.bases, reads5.offs, opt5)
-            api.resident_run()
-            ms5 = api.resident_run(); st5 = api.get_stats()
-            c5 = {"workload": "1M aDNA-style 30-50bp reads, -l 1024 -n 0.01 -o 2, same 100 Mb genome (BASELINE.json configs[4])",
-                  "reads_per_s": n5 / (ms5 / 1e3), "ms": ms5, "pass_ms": st5["ms_tier"][:3], "width_ms": st5["ms_width"],
-                  "reads_through_warp_pass": int(st5["n_overflow_t2"]), "reads_through_guaranteed_pass": int(st5["n_overflow_t3"])}
-            if R.have_ref():
-                got5 = api.resident_fetch(n5)
-                m5 = 100_000
-                sub5 = bwa.simulate.Reads(reads5.bases[: reads5.offs[m5]], reads5.offs[: m5 + 1], None, None)
-                want5 = R.ref_aln(R.RefIndex(idx), sub5, opt5, threads=host_cores); dt5r = R.ref_aln.last_batch_s
-                got5s = (got5[0][:m5], got5[1][:m5], got5[2][: m5 + 1], got5[3][: got5[2][m5]])
-                c5["cpu_reference_reads_per_s"] = m5 / dt5r
-                c5["cpu_sample"] = f"first {m5} reads, {dt5r:.1f} s, bwa_cal_sa_reg_gap per read over {host_cores} threads"
-                c5["parity_mismatches"] = len(R.compare_aln(want5, got5s, "c5"))
-            extras["c5_adna"] = c5
-        except Exception as e:
-            extras["c5_adna"] = {"error": str(e)[:200]}
+        wall_s = time.perf_counter() - t_wall0
+        clocks = sampler.stop()
+        tot = api.get_totals()
+    finally:
+        restore_stderr(saved)
+    kernel_ms = tot["ms_width"] + tot["ms_search"] + tot["ms_sa"] + tot["ms_sw"] + tot["ms_global"]
+    if dist is not None:
+        t = torch.tensor([e2e_s, kernel_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s_max, kernel_ms_max = float(t[0].item()), float(t[1].item())
+    else:
+        e2e_s_max, kernel_ms_max = e2e_s, kernel_ms
+    reads_per_step = 2 * args.pairs
+    value = world * reads_per_step * args.steps / (kernel_ms_max / 1e3)
+    e2e = {"value": world * reads_per_step * args.steps / e2e_s_max, "unit": "reads/s",
+           "h2d_bytes_per_step": int(tot["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(tot["d2h_bytes"] / args.steps),
+           "api": "bwa_bam_to_bam (the reference's bam2bam entry point, in-process) behind integration/libbwa_gpu_batch.so; BAM in -> BAM out, "
+                  "both passes; wall minus the index load (0 after the first run: the index stays loaded, as in one long job)",
+           "ms_each_step_rank0": steps_ms, "host_threads_per_rank": threads}
+    last = reps[-1]
+    pipeline = {k: last[k] for k in ("pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s", "dev_sw_s", "dev_ga_s", "inflate_cpu_s", "reads_aln", "q_sa",
+                                     "jobs_sw", "jobs_ga")}
+    pipeline["device_call_share_of_wall"] = ((last["dev_aln_s"] + last["dev_sa_s"] + last["dev_sw_s"] + last["dev_ga_s"])
+                                             / max(1e-9, last["wall_s"] - last["index_load_s"]))
+    per_step = {k: tot[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global")}
 
     if rank != 0:
+        host.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
+    # ---- parity (untimed): a prefix of the shard through both implementations, every record compared
+    parity = None
+    if not args.no_parity and os.path.exists(REF_BWA):
+        try:
+            small = prefix_bam(bam, min(args.pairs, 20_000))
+            saved = quiet_stderr(rank)
+            try:
+                host.run(prefix, small, small[:-4] + ".gpu_out.bam")
+            finally:
+                restore_stderr(saved)
+            run_reference(prefix, small, small[:-4] + ".ref_out.bam", 1)
+            n, bad = records_differing(small[:-4] + ".ref_out.bam", small[:-4] + ".gpu_out.bam")
+            parity = {"records": n, "records_differing": bad,
+                      "checker": "oracle/_ref/bwa bam2bam -t 1 on the first 20000 pairs of the shard, whole records compared"}
+        except Exception as e:  # the checker is optional on the bench box
+            parity = {"error": str(e)[:300]}
+
+    # ---- k_search alone on a resident batch: the roofline of the dominant kernel (and the aln-only throughput of round 1's line)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -408,47 +398,95 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-    fetches = st_counts["occ_fetches_search"]  # reference-layout block fetches of ONE pass over the batch
-    achieved = 64.0 * fetches / (search_ms / args.steps / 1e3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_search_traffic.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    roofline, aln_only = None, None
+    if aln_reads is not None:
+        opt = bwa.abi.default_gap_opt()
+        api.resident_stage(aln_reads.bases, aln_reads.offs, opt)
+        api.set_stats(True)
+        api.resident_run()  # instrumented pass (untimed): algorithmic fetch counts of this batch
+        st_counts = api.get_stats()
+        api.set_stats(False)
+        for _ in range(3):
+            api.resident_run()
+        dev_ms = search_ms = width_ms = 0.0
+        n_rep = max(3, min(args.steps, 10))
+        for _ in range(n_rep):
+            dev_ms += api.resident_run()
+            st = api.get_stats()
+            search_ms += st["ms_search"]; width_ms += st["ms_width"]
+        fetches = st_counts["occ_fetches_search"]
+        achieved = 64.0 * fetches / (search_ms / n_rep / 1e3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_search_traffic.json"))).get("dram_bytes_per_launch_c4")
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "kernel": "k_search (all passes), timed alone on a resident batch of the workload's reads",
+                    "peak_source": peak_src, "algorithmic_bytes": "64 B x occ-block fetches of the reference layout (SURVEY.md §8d)",
+                    "reads_per_launch": args.aln_reads, "fetches_per_read": fetches / args.aln_reads,
+                    "own_32B_blocks_per_read": st_counts["own_fetches_search"] / args.aln_reads,
+                    "kernel_ms_per_launch": search_ms / n_rep, "width_ms_per_launch": width_ms / n_rep,
+                    "own_sector_gb_s": 32.0 * st_counts["own_fetches_search"] / (search_ms / n_rep / 1e3) / 1e9,
+                    "per_read": {k: st_counts["n_" + k] / args.aln_reads for k in ("pops", "pushes", "stored", "pruned", "expand", "exact", "derive", "trips")}}
+        aln_only = {"metric": "reads/sec (aln only: bwa_cal_sa_reg_gap per read = K2 + K3), resident batch, device-timed",
+                    "value": args.aln_reads * n_rep / (dev_ms / 1e3), "reads": args.aln_reads, "read_len": args.read_len}
+        try:
+            roofline["random_sector_probe_gb_s"] = {"2.3GB_buffer_chains4": api.probe_random_sectors(2_300_000_000, 4, 256)}
+        except Exception as e:
+            roofline["random_sector_probe_gb_s"] = {"error": str(e)[:200]}
+
+    # ---- the other kernels of the step, from the library's totals over the timed steps
+    int_alu_peak = 148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6  # integer lane-ops/s: 148 SMs x 128 lanes x clock
+
+    def per_s(units, ms):
+        return units / max(1e-9, ms / 1e3)
+
+    other = {
+        "k4_sa": {"queries_per_step": tot["sa_queries"] / args.steps, "kernel_ms_per_step": per_step["ms_sa"],
+                  "queries_per_s_kernel": per_s(tot["sa_queries"], tot["ms_sa"]),
+                  "algorithmic_gb_s": 64.0 * 15.5 * per_s(tot["sa_queries"], tot["ms_sa"]) / 1e9,
+                  "frac_of_hbm_peak": 64.0 * 15.5 * per_s(tot["sa_queries"], tot["ms_sa"]) / 1e9 / peak,
+                  "unit": "64 B x 15.5 LF steps per query (bwt.c:72-81 at sa_intv 32)"},
+        "k5_sw": {"jobs_per_step": tot["sw_jobs"] / args.steps, "kernel_ms_per_step": per_step["ms_sw"],
+                  "gcups_forward_kernel": per_s(tot["sw_cells_fwd"], tot["ms_sw"]) / 1e9,
+                  "integer_alu_bound_gcups": int_alu_peak / 12 / 1e9,
+                  "frac_of_integer_alu_bound": per_s(tot["sw_cells_fwd"], tot["ms_sw"]) / (int_alu_peak / 12),
+                  "bound": "integer ALU: 148 SMs x 128 lanes x SM clock lane-ops/s at 12 lane-ops per affine-gap cell"},
+        "k6_global": {"jobs_per_step": (tot["sw_jobs"] + tot["ga_jobs"]) / args.steps, "kernel_ms_per_step": per_step["ms_global"]},
+        "k2_width": {"kernel_ms_per_step": per_step["ms_width"]},
+        "k3_search_in_pipeline": {"kernel_ms_per_step": per_step["ms_search"], "pass_ms_per_step": [x / args.steps for x in tot["ms_search_pass"]]},
+    }
+
+    # ---- cpu baseline (N = 1 only): the reference itself on a bounded prefix of the shard
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BWA):
+        try:
+            n_s = min(args.pairs, args.cpu_sample_pairs)
+            sample = prefix_bam(bam, n_s)
+            dt, load_s = run_reference(prefix, sample, sample[:-4] + ".ref_out.bam", host_cores)
+            cpu_baseline = {"value": 2 * n_s / dt, "unit": "reads/s", "cores": host_cores, "kind": "reference",
+                            "sample": f"first {n_s} pairs of the step's shard, `oracle/_ref/bwa bam2bam -t {host_cores}` (unmodified reference), "
+                                      f"{dt:.1f} s after the {load_s:.1f} s index load it prints"}
+            if n_s >= 20_000:
+                dt1, _ = run_reference(prefix, prefix_bam(bam, 20_000), sample[:-4] + ".ref_t1_out.bam", 1)
+                cpu_baseline["one_thread_reads_per_s"] = 2 * 20_000 / dt1
+        except Exception as e:
+            cpu_baseline = {"error": str(e)[:300]}
+
     line = {
-        "metric": METRIC,
-        "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if (args.read_len, args.genome_bp) == (READ_LEN, GENOME_BP) else
-                   f"SE {n_reads} x {args.read_len}bp, -n 0.04 -o 1, synthetic {args.genome_bp} bp genome (non-default shape)",
-                   "reads_per_step_per_gpu": n_reads, "read_len": args.read_len, "genome_bp": args.genome_bp,
-                   "parallelism": f"replica x{world}, reads sharded, no collective",
-                   "l2": "inputs larger than L2 (index 100 MB + width arena and search stacks of several GB per step); same batch every step",
-                   "timed": "CUDA events on the library stream around K2+K3(+tiers)+compaction",
-                   "tier2_reads": int(n_over2), "tier3_reads": int(n_over3)},
-        "e2e": e2e,
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_search (all tiers)", "peak_source": peak_src,
-                     "algorithmic_bytes": "64 B x occ-block fetches of the reference layout (SURVEY.md §8d)",
-                     "fetches_per_read": fetches / n_reads, "own_32B_blocks_per_read": st_counts["own_fetches_search"] / n_reads,
-                     "kernel_ms_per_step": search_ms / args.steps, "width_ms_per_step": width_ms / args.steps,
-                     "tier_ms_per_step": [t / args.steps for t in tier_ms],
-                     "pops_per_read": st_counts["n_pops"] / n_reads, "pushes_per_read": st_counts["n_pushes"] / n_reads,
-                     "stored_pushes_per_read": st_counts["n_stored"] / n_reads,
-                     "per_read": {k: st_counts["n_" + k] / n_reads for k in ("pruned", "expand", "exact", "derive", "trips")},
-                     "stats_pass_ms": {"queue_empty": st_counts["ns_queue_empty"] / 1e6, "kernel": st_counts["ns_kernel"] / 1e6},
-                     "own_sector_gb_s": 32.0 * st_counts["own_fetches_search"] / (search_ms / args.steps / 1e3) / 1e9,
-                     "random_sector_probe": random_sector},
-        "cpu_baseline": cpu_baseline,
-        "parity_sample": parity,
-        "other_kernels": extras,
+        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic", "config": config,
+        "e2e": e2e, "gpu_launches": int(tot["launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "parity_sample": parity, "aln_only": aln_only, "other_kernels": other, "pipeline_last_step_rank0": pipeline,
+        "kernel_ms_per_step": per_step, "parallelism": f"one process + one index replica + one shard of pairs per GPU (x{world}), no collective",
+        "timed": "value: CUDA events inside the library around every kernel of the step (K2, K3, K4, K5, K6), summed; "
+                 "e2e: perf_counter around bwa_bam_to_bam",
         "wall_s_timed_region": wall_s,
     }
     print(json.dumps(line))
-    api.destroy()
+    host.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

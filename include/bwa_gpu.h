@@ -276,6 +276,21 @@ int bwa_gpu_get_stats(bwa_gpu_stats_t *out);
 /* 0 = off (default, the timed configuration), 1 = count fetches/pops/pushes in-kernel */
 int bwa_gpu_set_stats(int enabled);
 
+/* Running totals over every call since bwa_gpu_init / bwa_gpu_reset_totals, for hosts that make many calls from several
+ * threads (a bam2bam run through integration/bwa_gpu_batch.c): kernel-only device time (CUDA events on the library's
+ * streams; the lanes of a device overlap, so the sum can exceed wall time), launches, units and copy volumes. */
+typedef struct {
+	double ms_width, ms_search, ms_sa, ms_sw, ms_global; /* K2 (+K2b), K3 (all passes), K4, K5, K6 */
+	double ms_search_pass[3];
+	int64_t launches;                                  /* kernels launched (cub passes included) */
+	int64_t reads, alns, sa_queries, sw_jobs, ga_jobs; /* units: reads searched, hits returned, SA rows, K5 jobs, K6-only jobs */
+	int64_t sw_cells_fwd;                              /* sum of window x read cells of K5's forward pass */
+	int64_t h2d_bytes, d2h_bytes;
+	int64_t occ_fetches_width, occ_fetches_search, own_fetches_search; /* from calls made while stats were enabled */
+} bwa_gpu_totals_t;
+int bwa_gpu_get_totals(bwa_gpu_totals_t *out);
+void bwa_gpu_reset_totals(void);
+
 /* Roofline denominator for the occurrence-lookup kernels: the rate, in GB/s of 32-byte sectors, that a
  * kernel of nothing but dependent random sector loads over a buffer_bytes buffer sustains on device 0, with `chains`
  * (1, 2, 4 or 8) independent chains per thread and `steps` loads per chain.  Measurement only; replaces no reference call. */

@@ -151,6 +151,23 @@ class stats_t(C.Structure):
         return d
 
 
+class totals_t(C.Structure):
+    _fields_ = [
+        ("ms_width", C.c_double), ("ms_search", C.c_double), ("ms_sa", C.c_double), ("ms_sw", C.c_double), ("ms_global", C.c_double),
+        ("ms_search_pass", C.c_double * 3),
+        ("launches", C.c_int64),
+        ("reads", C.c_int64), ("alns", C.c_int64), ("sa_queries", C.c_int64), ("sw_jobs", C.c_int64), ("ga_jobs", C.c_int64),
+        ("sw_cells_fwd", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("occ_fetches_width", C.c_int64), ("occ_fetches_search", C.c_int64), ("own_fetches_search", C.c_int64),
+    ]
+
+    def asdict(self) -> dict:
+        d = {f[0]: getattr(self, f[0]) for f in self._fields_}
+        d["ms_search_pass"] = list(self.ms_search_pass)
+        return d
+
+
 def make_bwt_t(b) -> bwt_t:
     """bwt_t view over an index.Bwt (arrays stay owned by the Bwt object; keep it alive)."""
     t = bwt_t()

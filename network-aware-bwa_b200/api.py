@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
         L.bwa_gpu_global_align_seqs.argtypes = [C.c_int, C.POINTER(abi.ga_job_t), C.c_int, C.c_int, C.POINTER(abi.path_res_t),
                                                 C.POINTER(C.c_void_p)]
         L.bwa_gpu_get_stats.argtypes = [C.POINTER(abi.stats_t)]
+        L.bwa_gpu_get_totals.argtypes = [C.POINTER(abi.totals_t)]
+        L.bwa_gpu_reset_totals.restype = None
         L.bwa_gpu_set_stats.argtypes = [C.c_int]
         L.bwa_gpu_resident_stage.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(abi.gap_opt_t)]
         L.bwa_gpu_resident_run.argtypes = [C.POINTER(C.c_double)]
@@ -63,7 +65,7 @@ EXPORTS = [
     "bwa_gpu_init", "bwa_gpu_load_index", "bwa_gpu_load_pac", "bwa_gpu_destroy", "bwa_gpu_last_error",
     "bwa_gpu_cal_sa_reads_gap", "bwa_gpu_free_alns", "bwa_gpu_aln_flat", "bwa_gpu_cal_pac_pos", "bwa_gpu_mate_sw", "bwa_gpu_mate_sw_path", "bwa_gpu_global_align",
     "bwa_gpu_global_align_seqs",
-    "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_probe_random_sectors",
+    "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_get_totals", "bwa_gpu_reset_totals", "bwa_gpu_probe_random_sectors",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
     "bwa_gpu_index_build", "bwa_gpu_index_free", "bwa_gpu_index_write",
 ]
@@ -246,6 +248,16 @@ def get_stats() -> dict:
     s = abi.stats_t()
     _ck(lib().bwa_gpu_get_stats(C.byref(s)))
     return s.asdict()
+
+
+def get_totals() -> dict:
+    t = abi.totals_t()
+    _ck(lib().bwa_gpu_get_totals(C.byref(t)))
+    return t.asdict()
+
+
+def reset_totals() -> None:
+    lib().bwa_gpu_reset_totals()
 
 
 def resident_stage(bases: np.ndarray, offs: np.ndarray, opt) -> None:

@@ -175,6 +175,10 @@ struct Ctx {
 	bwa_gpu_stats_t stats = {};
 };
 
+static bwa_gpu_totals_t g_tot = {};
+static std::mutex g_tot_mu;
+#define TOT(stmt) do { std::lock_guard<std::mutex> tg_(g_tot_mu); stmt; } while (0)
+
 static std::vector<Ctx *> g_ctx;
 static bool g_stats_enabled = false;
 static std::mutex g_mu;
@@ -381,6 +385,20 @@ extern "C" int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac)
 
 extern "C" int bwa_gpu_set_stats(int enabled) { g_stats_enabled = enabled != 0; return 0; }
 
+extern "C" int bwa_gpu_get_totals(bwa_gpu_totals_t *out)
+{
+	if (!out) return fail("bwa_gpu_get_totals: null");
+	std::lock_guard<std::mutex> tg(g_tot_mu);
+	*out = g_tot;
+	return 0;
+}
+
+extern "C" void bwa_gpu_reset_totals(void)
+{
+	std::lock_guard<std::mutex> tg(g_tot_mu);
+	g_tot = bwa_gpu_totals_t();
+}
+
 // ------------------------------------------------------------------ device pipeline for one resident chunk
 static const int N_PASSES = 3;
 
@@ -564,6 +582,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		CK(cudaStreamSynchronize(c->st));
 		c->stats.occ_fetches_width += (int64_t)hs[0];
 		c->stats.own_fetches_width += (int64_t)hs[1];
+		TOT(g_tot.occ_fetches_width += (int64_t)hs[0]);
 		unsigned long long init[16] = {0};
 		init[11] = init[12] = ~0ull;
 		CK(cudaMemcpyAsync(c->d_stats.p, init, sizeof init, cudaMemcpyHostToDevice, c->st));
@@ -650,6 +669,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			float tms = 0;
 			CK(cudaEventElapsedTime(&tms, c->ev[8 + 2 * t], c->ev[9 + 2 * t]));
 			c->stats.ms_tier[t] += tms;
+			TOT(g_tot.ms_search_pass[t] += tms);
 		}
 		const int n_over = c->h_counters.p[1];
 		c->stats.x_chunks_used = std::max<int64_t>(c->stats.x_chunks_used, (int64_t)(unsigned int)c->h_counters.p[3]);
@@ -684,6 +704,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		CK(cudaStreamSynchronize(c->st));
 		c->stats.occ_fetches_search += (int64_t)hs[0];
 		c->stats.own_fetches_search += (int64_t)hs[1];
+		TOT(g_tot.occ_fetches_search += (int64_t)hs[0]; g_tot.own_fetches_search += (int64_t)hs[1]);
 		c->stats.n_pops += (int64_t)hs[2];
 		c->stats.n_pushes += (int64_t)hs[3];
 		c->stats.n_stored += (int64_t)hs[4];
@@ -703,8 +724,8 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		CK(cudaEventRecord(c->ev[4], c->st));
 		CK(cudaStreamSynchronize(c->st));
 		float ms0 = 0;
-		CK(cudaEventElapsedTime(&ms0, c->ev[1], c->ev[2])); c->stats.ms_width += ms0;
-		CK(cudaEventElapsedTime(&ms0, c->ev[2], c->ev[3])); c->stats.ms_search += ms0;
+		CK(cudaEventElapsedTime(&ms0, c->ev[1], c->ev[2])); c->stats.ms_width += ms0; TOT(g_tot.ms_width += ms0);
+		CK(cudaEventElapsedTime(&ms0, c->ev[2], c->ev[3])); c->stats.ms_search += ms0; TOT(g_tot.ms_search += ms0);
 		*total_aln = (int64_t)std::min<size_t>((size_t)(unsigned int)c->h_counters.p[2], pool_cap); // hit-pool fill
 		return 0;
 	}
@@ -727,8 +748,8 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	CK(cudaEventRecord(c->ev[4], c->st));
 	CK(cudaStreamSynchronize(c->st));
 	float ms = 0;
-	CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.ms_width += ms;
-	CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats.ms_search += ms;
+	CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.ms_width += ms; TOT(g_tot.ms_width += ms);
+	CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats.ms_search += ms; TOT(g_tot.ms_search += ms);
 	CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats.ms_compact += ms;
 	*total_aln = tot;
 	return 0;
@@ -926,7 +947,11 @@ static int run_range(Ctx *c, FlatJob &J)
 		if (getenv("BWAGPU_TRACE")) fprintf(stderr, "[trace] lane %d.%d chunk %d unpack %.0f ms\n", c->dev, c->lane, ci, std::chrono::duration<double, std::milli>(t3 - t2).count());
 		c->stats.ms_host_marshal += std::chrono::duration<double, std::milli>(t3 - t2).count();
 		c->stats.n_reads += n;
-		for (int i = 0; i < n; ++i) c->stats.n_aln += c->h_naln.p[i];
+		int64_t na_sum = 0;
+		for (int i = 0; i < n; ++i) na_sum += c->h_naln.p[i];
+		c->stats.n_aln += na_sum;
+		TOT(g_tot.reads += n; g_tot.alns += na_sum; g_tot.h2d_bytes += (int64_t)n_bases + (int64_t)n * (int64_t)sizeof(ReadMeta);
+		    g_tot.d2h_bytes += (int64_t)n * 12 + tot * 16);
 	}
 	return 0;
 }
@@ -984,6 +1009,11 @@ static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *
 			});
 	}
 	for (auto &t : th) t.join();
+	{
+		int64_t l = 0;
+		for (Ctx *c : g_ctx) l += c->stats.launches;
+		TOT(g_tot.launches += l);
+	}
 	for (int d = 0; d < nd; ++d)
 		if (jobs[d]->failed.load()) return fail("device %d: %s", owners[d]->dev, jobs[d]->err.c_str());
 	return 0;
@@ -1138,6 +1168,7 @@ extern "C" int bwa_gpu_resident_run(double *ms)
 	c->stats.ms_total_device = t;
 	c->stats.n_reads = c->res_n;
 	c->stats.n_aln = tot;
+	TOT(g_tot.launches += c->stats.launches; g_tot.reads += c->res_n; g_tot.alns += tot);
 	c->res_total_aln = tot;
 	if (ms) *ms = t;
 	return 0;
@@ -1188,10 +1219,15 @@ extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint
 			CK(cudaMemcpyAsync(c->d_q.p, sa_idx + r0, (size_t)m * 4, cudaMemcpyHostToDevice, c->st));
 			CK(cudaMemcpyAsync(c->d_which.p, which + r0, (size_t)m, cudaMemcpyHostToDevice, c->st));
 			IndexPair P; P.ix[0] = c->ix[0]; P.ix[1] = c->ix[1];
+			CK(cudaEventRecord(c->ev[14], c->st));
 			k_sa<<<(unsigned)((m + 255) / 256), 256, 0, c->st>>>(P, m, c->d_q.p, c->d_which.p, c->d_qo.p);
 			CK(cudaGetLastError());
+			CK(cudaEventRecord(c->ev[15], c->st));
 			CK(cudaMemcpyAsync(out_sa + r0, c->d_qo.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->st));
 			CK(cudaStreamSynchronize(c->st));
+			float ms = 0;
+			CK(cudaEventElapsedTime(&ms, c->ev[14], c->ev[15]));
+			TOT(g_tot.ms_sa += ms; g_tot.launches += 1; g_tot.sa_queries += m; g_tot.h2d_bytes += m * 5; g_tot.d2h_bytes += m * 4);
 		}
 		return 0;
 	};
@@ -1217,12 +1253,15 @@ static int sw_entry(int n, const bwa_gpu_sw_job_t *jobs, int mode, int gap_end, 
 	Ctx *c = g_ctx[0];
 	CK(cudaSetDevice(c->dev));
 	if (!c->has_pac) return fail("%s: no packed reference loaded (pac was NULL in bwa_gpu_load_index)", who);
-	double ms = 0;
+	double ms[2] = {0, 0};
+	SwCounts cnt;
 	std::vector<bwa_gpu_sw_res_t> tmp;
 	if (mode == 1 && !res) { tmp.resize(n); res = tmp.data(); }
 	std::vector<uint16_t> &pool = mode == 1 ? g_cigar_pool_sw : g_cigar_pool_ga;
-	const int rc = sw_batch(c->sw, c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &pool : nullptr, fail, &ms);
-	c->stats.ms_sw_kernel = ms;
+	const int rc = sw_batch(c->sw, c->st, c->pac.p, c->l_pac, n, jobs, mode, gap_end, band, res, pres, mode ? &pool : nullptr, fail, ms, &cnt);
+	c->stats.ms_sw_kernel = ms[0] + ms[1];
+	TOT(g_tot.ms_sw += ms[0]; g_tot.ms_global += ms[1]; g_tot.launches += cnt.launches; g_tot.sw_cells_fwd += cnt.cells_fwd;
+	    g_tot.h2d_bytes += cnt.h2d; g_tot.d2h_bytes += cnt.d2h; if (mode == 2) g_tot.ga_jobs += n; else g_tot.sw_jobs += n);
 	if (mode && cigar_pool) *cigar_pool = pool.data();
 	return rc;
 }
@@ -1254,7 +1293,9 @@ extern "C" int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, in
 	Ctx *c = g_ctx[0];
 	CK(cudaSetDevice(c->dev));
 	double ms = 0;
-	const int rc = ga_seqs_batch(c->sw, c->st, n, jobs, gap_end, band, res, &g_cigar_pool_ga, fail, &ms);
+	SwCounts cnt;
+	const int rc = ga_seqs_batch(c->sw, c->st, n, jobs, gap_end, band, res, &g_cigar_pool_ga, fail, &ms, &cnt);
+	TOT(g_tot.ms_global += ms; g_tot.launches += cnt.launches; g_tot.ga_jobs += n; g_tot.h2d_bytes += cnt.h2d; g_tot.d2h_bytes += cnt.d2h);
 	*cigar_pool = g_cigar_pool_ga.data();
 	return rc;
 }

@@ -479,13 +479,15 @@ struct SwScratch {
 	void release() { for (int k = 0; k < 10; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; } }
 };
 
+struct SwCounts { long long cells_fwd = 0, h2d = 0, d2h = 0; int launches = 0; };
+
 // host launcher.  mode 0: K5 only (res); mode 1: K5 + third pass (pres, cigars); mode 2: plain banded global
-// alignment with (gap_end, band) (pres, cigars).
+// alignment with (gap_end, band) (pres, cigars).  kernel_ms[0] = k_sw, kernel_ms[1] = k_global (CUDA events on `st`).
 static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t l_pac, int n, const bwa_gpu_sw_job_t *jobs, int mode,
                     int gap_end, int band, bwa_gpu_sw_res_t *res, bwa_gpu_path_res_t *pres, std::vector<uint16_t> *cigars,
-                    int (*fail)(const char *, ...), double *kernel_ms)
+                    int (*fail)(const char *, ...), double *kernel_ms, SwCounts *counts = nullptr)
 {
-	if (kernel_ms) *kernel_ms = 0;
+	if (kernel_ms) kernel_ms[0] = kernel_ms[1] = 0;
 	if (cigars) cigars->clear();
 	if (n == 0) return 0;
 	std::vector<SwJob> hj(n);
@@ -512,11 +514,12 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		for (int t = 0; t < jobs[i].len; ++t) hq[(size_t)hj[i].q_off + t] = jobs[i].seq[t] > 3 ? 4 : jobs[i].seq[t];
 	SwJob *d_jobs = nullptr; uint8_t *d_q = nullptr; bwa_gpu_sw_res_t *d_res = nullptr; int *d_cnt = nullptr, *d_sr = nullptr;
 	PathJob *d_pj = nullptr; bwa_gpu_path_res_t *d_pres = nullptr; uint16_t *d_cig = nullptr; uint8_t *d_cells = nullptr; GScore *d_sc = nullptr;
-	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 	cudaError_t e;
 	auto cleanup = [&]() {
 		if (e0) cudaEventDestroy(e0);
 		if (e1) cudaEventDestroy(e1);
+		if (e2) cudaEventDestroy(e2);
 	};
 #define SWALLOC(ptr, k, bytes) do { e = S.reserve(k, bytes); if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); } ptr = (decltype(ptr))S.p[k]; } while (0)
 #define SWCK(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return fail("%s: %s", #x, cudaGetErrorString(e)); } } while (0)
@@ -524,10 +527,16 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 	SWALLOC(d_cnt, 1, 2 * sizeof(int));
 	SWCK(cudaMemcpyAsync(d_q, hq.data(), hq.size(), cudaMemcpyHostToDevice, st));
 	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
-	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1));
+	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1)); SWCK(cudaEventCreate(&e2));
 	int dev = 0, n_sm = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+	if (counts) {
+		counts->h2d += (long long)hq.size() + (long long)n * (long long)(sizeof(SwJob) + (mode ? sizeof(PathJob) : 0));
+		counts->d2h += (long long)n * (long long)(mode ? sizeof(bwa_gpu_path_res_t) : sizeof(bwa_gpu_sw_res_t)) + (mode ? 2 * cig_total : 0);
+		if (mode != 2) for (int i = 0; i < n; ++i) counts->cells_fwd += (long long)hj[i].len1 * hj[i].len2;
+		counts->launches += (mode != 2) + (mode != 0);
+	}
 	// ---- every allocation and staging copy first, so that the event window holds kernels only
 	size_t smem = 0, cells_stride = 0, sc_stride = 0, threads = 0;
 	int blocks = 0;
@@ -566,6 +575,7 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		k_sw<<<blocks, 128, smem, st>>>(d_pac, d_jobs, n, d_q, d_res, len1_max, len2_max, d_cnt, d_sr);
 		SWCK(cudaGetLastError());
 	}
+	SWCK(cudaEventRecord(e2, st));
 	if (mode) {
 		k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(d_pac, d_pj, n, d_q, gap_end, band, mode == 1 ? d_res : nullptr, d_sr, d_pres,
 		                                                   d_cig, d_cells, cells_stride, d_sc, sc_stride, d_cnt + 1);
@@ -578,10 +588,10 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		if (cig_total) SWCK(cudaMemcpyAsync(cigars->data(), d_cig, (size_t)cig_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
 	}
 	SWCK(cudaStreamSynchronize(st));
-	{
+	if (kernel_ms) {
 		float ms = 0;
-		cudaEventElapsedTime(&ms, e0, e1);
-		if (kernel_ms) *kernel_ms = ms;
+		cudaEventElapsedTime(&ms, e0, e2); kernel_ms[0] = ms;
+		cudaEventElapsedTime(&ms, e2, e1); kernel_ms[1] = ms;
 	}
 #undef SWCK
 #undef SWALLOC
@@ -595,7 +605,7 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 // bwa_gpu_global_align_seqs: aln_global_core on explicit sequence pairs (both given one base per byte).  The same K6 kernel,
 // its reference bases read from the byte array the reads are in instead of the packed genome.
 static int ga_seqs_batch(SwScratch &S, cudaStream_t st, int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *pres,
-                         std::vector<uint16_t> *cigars, int (*fail)(const char *, ...), double *kernel_ms)
+                         std::vector<uint16_t> *cigars, int (*fail)(const char *, ...), double *kernel_ms, SwCounts *counts = nullptr)
 {
 	if (kernel_ms) *kernel_ms = 0;
 	cigars->clear();
@@ -645,6 +655,11 @@ static int ga_seqs_batch(SwScratch &S, cudaStream_t st, int n, const bwa_gpu_ga_
 	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
 	SWCK(cudaMemcpyAsync(d_pj, pj.data(), (size_t)n * sizeof(PathJob), cudaMemcpyHostToDevice, st));
 	cigars->resize((size_t)cig_total);
+	if (counts) {
+		counts->h2d += (long long)hb.size() + (long long)n * (long long)sizeof(PathJob);
+		counts->d2h += (long long)n * (long long)sizeof(bwa_gpu_path_res_t) + 2 * cig_total;
+		counts->launches += 1;
+	}
 	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1));
 	SWCK(cudaEventRecord(e0, st));
 	k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(nullptr, d_pj, n, d_b, gap_end, band, nullptr, nullptr, d_pres, d_cig, d_cells, cells_stride,

@@ -90,10 +90,17 @@ def ensure_genome_files(bp: int, seed: int = 1, device: int = 0, repeat_frac: fl
         T = simulate.make_genome(bp, seed=seed, repeat_frac=repeat_frac)
         t1 = time.time()
         pac = ix.pack_pac(T)
-        del T
-        from . import api
-        fwd, rev = api.index_build(pac, bp, device=device, write_prefix=prefix)
-        del fwd, rev
+        import torch
+        if torch.cuda.is_available():
+            del T
+            from . import api
+            fwd, rev = api.index_build(pac, bp, device=device, write_prefix=prefix)
+            del fwd, rev
+        else:  # a box without a device (the CPU test suite, small genomes): the torch harness builder writes the same files
+            idx = ix.build_index(T, device="cpu")
+            ix.dump_bwt(prefix + ".bwt", idx.bwt[0]); ix.dump_bwt(prefix + ".rbwt", idx.bwt[1])
+            ix.dump_sa(prefix + ".sa", idx.bwt[0]); ix.dump_sa(prefix + ".rsa", idx.bwt[1])
+            del T, idx
         t2 = time.time()
         write_pac(prefix, pac, bp)
         write_bns(prefix, bp, 4)

@@ -140,7 +140,8 @@ struct Ctx {
 	DevBuf<ReadMeta> d_meta;
 	DevBuf<uint32_t> d_w;
 	DevBuf<uint16_t> d_bid;
-	DevBuf<uint2> d_ctx;
+	DevBuf<uint2> d_ctx;       // 8-byte context words: only the warp pass reads them (allocated when it first runs)
+	DevBuf<uint16_t> d_ctx16;  // compact per-position context of k_search
 	DevBuf<int32_t> d_naln, d_maxent, d_jobs_a, d_jobs_b, d_ids, d_order;
 	DevBuf<uint8_t> d_keys, d_keys2;
 	DevBuf<uint32_t> d_pooloff, d_outoff;
@@ -202,7 +203,7 @@ extern "C" void bwa_gpu_destroy(void)
 			for (int s = 0; s < 2; ++s) c->sa[s].release();
 			c->pac.release();
 		}
-		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release(); c->d_ctx.release();
+		c->d_seq.release(); c->d_meta.release(); c->d_w.release(); c->d_bid.release(); c->d_ctx.release(); c->d_ctx16.release();
 		c->d_naln.release(); c->d_maxent.release(); c->d_jobs_a.release(); c->d_jobs_b.release(); c->d_ids.release(); c->d_order.release(); c->d_keys.release(); c->d_keys2.release();
 		c->d_pooloff.release(); c->d_outoff.release(); c->d_pool.release(); c->d_out.release();
 		c->d_counters.release(); c->d_stats.release(); c->d_cubtmp.release();
@@ -527,11 +528,11 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
                             bool device_compact)
 {
 	const bool stats = g_stats_enabled;
-	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx.reserve(w_entries + 8)) return 1;
+	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx16.reserve(w_entries + 8)) return 1;
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;
-	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(32)) return 1;
+	if (c->d_counters.reserve(4) || c->h_counters.reserve(4) || c->d_stats.reserve(96)) return 1;
 	// hit pool of the chunk (completion order): 16 hits per read on average to start with; grown and the
 	// affected reads retried when a batch of short, repetitive reads needs more
 	size_t pool_cap = std::max<size_t>((size_t)n * env_u32("BWAGPU_HITS_PER_READ", 16), 1u << 16);
@@ -544,16 +545,17 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	B.opt = opt;
 	B.n_reads = n;
 	B.seq = c->d_seq.p; B.meta = c->d_meta.p;
-	B.w = c->d_w.p; B.bid = c->d_bid.p; B.ctx = c->d_ctx.p;
+	B.w = c->d_w.p; B.bid = c->d_bid.p; B.ctx = c->d_ctx.p; B.ctx16 = c->d_ctx16.p;
 	B.n_aln = c->d_naln.p; B.max_entries = c->d_maxent.p; B.pool_off = c->d_pooloff.p;
 	B.pool = c->d_pool.p; B.pool_cap = (uint32_t)pool_cap;
 	B.pool_count = (unsigned int *)(c->d_counters.p + 2);
 	B.work_counter = c->d_counters.p; B.overflow_count = c->d_counters.p + 1;
 	B.stats = c->d_stats.p;
 	B.n_stacks = n_stacks;
+	B.pop_cap = warp_pass_enabled() ? env_u32("BWAGPU_POP_CAP", 0) : 0; // without the warp pass a straggler is best left where it is
 
 	CK(cudaMemsetAsync(c->d_counters.p, 0, 4 * sizeof(int), c->st));
-	CK(cudaMemsetAsync(c->d_stats.p + 16, 0, 16 * sizeof(unsigned long long), c->st)); // k_search_warp diagnostics
+	CK(cudaMemsetAsync(c->d_stats.p + 16, 0, 80 * sizeof(unsigned long long), c->st)); // k_search_warp diagnostics + the STATS histograms
 	if (stats) {
 		unsigned long long init[16] = {0};
 		init[11] = init[12] = ~0ull;
@@ -571,7 +573,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			if (stats) k_width<true><<<blocks, 128, 0, c->st>>>(B);
 			else k_width<false><<<blocks, 128, 0, c->st>>>(B);
 			CK(cudaGetLastError());
-			k_ctx<<<(int)((32ll * n + 255) / 256), 256, 0, c->st>>>(B);
+			k_ctx16<<<(int)((32ll * n + 255) / 256), 256, 0, c->st>>>(B);
 			CK(cudaGetLastError());
 			c->stats.launches += 2;
 		}
@@ -634,7 +636,11 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			if (stats) k_width<true><<<wb, 128, 0, c->st>>>(B);
 			else k_width<false><<<wb, 128, 0, c->st>>>(B);
 			CK(cudaGetLastError());
-			k_ctx<<<(int)((32ll * n_jobs + 255) / 256), 256, 0, c->st>>>(B);
+			if (t == 1 && warp_pass_enabled()) { // k_search_warp reads the 8-byte context words
+				if (c->d_ctx.reserve(w_entries + 8)) return 1;
+				B.ctx = c->d_ctx.p;
+				k_ctx<<<(int)((32ll * n_jobs + 255) / 256), 256, 0, c->st>>>(B);
+			} else k_ctx16<<<(int)((32ll * n_jobs + 255) / 256), 256, 0, c->st>>>(B);
 			CK(cudaGetLastError());
 			c->stats.launches += 2;
 		}
@@ -715,6 +721,16 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		c->stats.n_trips += (int64_t)hs[9];
 		c->stats.ns_queue_empty = (int64_t)(hs[11] - hs[12]);
 		c->stats.ns_kernel = (int64_t)(hs[13] - hs[12]);
+		if (getenv("BWAGPU_PRINT_HIST")) { // diagnostics: where in the read the lookups happen, and how the work per read is distributed
+			unsigned long long h[64];
+			CK(cudaMemcpyAsync(h, c->d_stats.p + 32, sizeof h, cudaMemcpyDeviceToHost, c->st));
+			CK(cudaStreamSynchronize(c->st));
+			fprintf(stderr, "[k_search] lookups by depth (len - i; last = 31+):");
+			for (int q = 0; q < 32; ++q) fprintf(stderr, " %llu", h[q]);
+			fprintf(stderr, "\n[k_search] reads by log2(pops):");
+			for (int q = 0; q < 32; ++q) fprintf(stderr, " %llu", h[32 + q]);
+			fprintf(stderr, "\n");
+		}
 	}
 
 	if (!device_compact) {

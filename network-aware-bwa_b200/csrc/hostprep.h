@@ -23,7 +23,7 @@ static inline int cal_maxdiff(int l, double err, double thres)
 	int x = 1;
 	for (int k = 1; k < 1000; ++k) {
 		y *= l * err;
-		x *= k; // int, overflows for large k exactly like the reference's `int x`
+		x = (int)((uint32_t)x * (uint32_t)k); // the reference's `int x` overflows for k >= 13: the same bits, without the undefined behaviour
 		sum += elambda * y / x;
 		if (1.0 - sum < thres) return k;
 	}
@@ -65,8 +65,10 @@ static inline int fill_meta(int len, uint64_t seq_off, uint64_t w_off, const gap
 	int md = len > 0 ? mdt.get(len, opt) : 0;
 	int go = opt->max_gapo;
 	if (md < go) go = md;
-	if (md < 0 || md > 254 || go < 0 || go > 255 || opt->max_gape < 0 || opt->max_gape > 255)
-		return hostprep_fail("option range not supported on device: max_diff=%d max_gapo=%d max_gape=%d", md, go, opt->max_gape);
+	// max_diff <= 126 and max_seed_diff <= 14: the compact context entries of k_search saturate their bid fields at 127 / 15
+	if (md < 0 || md > 126 || go < 0 || go > 255 || opt->max_gape < 0 || opt->max_gape > 255 || opt->max_seed_diff < 0 || opt->max_seed_diff > 14)
+		return hostprep_fail("option range not supported on device: max_diff=%d (<= 126) max_gapo=%d max_gape=%d max_seed_diff=%d (<= 14)", md, go,
+		                     opt->max_gape, opt->max_seed_diff);
 	uint32_t ns = (uint32_t)((md + 1) * opt->s_mm + (go + 1) * opt->s_gapo + (opt->max_gape + 1) * opt->s_gape);
 	if (ns > 256) return hostprep_fail("score range %u exceeds 256 buckets (s_mm/s_gapo/s_gape/max_diff too large)", ns);
 	if (ns > n_stacks) n_stacks = ns;

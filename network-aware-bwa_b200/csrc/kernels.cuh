@@ -78,7 +78,8 @@ struct Batch {
 	const ReadMeta *__restrict__ meta;
 	uint32_t *w;       // width arena: w values (only gap_shadow reads them back)
 	uint16_t *bid;     // width arena: bid | (w[i-1] == w[i]) << 15 -- all the pruning tests need
-	uint2 *ctx;        // context arena (k_ctx): everything a popped node at (strand, i) needs, in one 8-byte word
+	uint2 *ctx;        // context arena (k_ctx, used by k_search_warp): everything a popped node at (strand, i) needs, in one 8-byte word
+	uint16_t *ctx16;   // compact context (k_ctx16, used by k_search): one 16-bit entry per (strand, position)
 	// results, per read
 	int32_t *n_aln;       // -1 = not done (ran out of arena / pool: retried in the next pass)
 	int32_t *max_entries;
@@ -97,6 +98,7 @@ struct Batch {
 	uint32_t *nxt;
 	uint32_t *heads; // global bucket heads (only when BWAGPU_SMEM_HEADS == 0)
 	uint32_t cap, n_stacks;
+	uint32_t pop_cap;  // pass 0 only: a read that pops more nodes than this is handed to the next pass (0 = no limit)
 	// arena overflow: chunks of ARENA_CHUNK records from a pool shared by all threads of the launch.  A
 	// thread takes chunks as its search deepens and hands all but one back when the read is finished
 	// (lock-free stack with a version tag), so the pool only has to cover the reads in flight
@@ -109,6 +111,7 @@ struct Batch {
 	unsigned long long *x_free_top; // recycled chunks: lock-free stack, {tag:32 | head:32} against ABA
 	uint32_t *x_free_next;     // link of the recycled-chunk stack
 	// stats (STATS builds only)
+	// [32 + d] occurrence lookups at depth d = min(31, len - i); [64 + b] reads whose search popped [2^b, 2^(b+1)) nodes
 	unsigned long long *stats; // [10] pops served from the arena (memory)  [0] ref fetches [1] own fetches [2] pops [3] pushes [4] records stored [5] pruned pops [6] expansions [7] exact-tail steps [8] derive trips
 };
 
@@ -245,6 +248,58 @@ __global__ void __launch_bounds__(256) k_ctx(const Batch B)
 	}
 }
 
+// ------------------------------------------------------------------ K2c: compact per-position context for k_search
+// The 8-byte words above cost a 32-byte sector per popped node and, for the reads in flight, more bytes than L2 holds
+// (132 k threads x 2 strands x ~100 positions x 8 B = 210 MB): every pop was a DRAM sector of which a quarter was used.
+// k_search reads ONE 16-bit entry per (strand, position t) instead,
+//     E[t] = min(bid(w[t]), 127) | (w[t-1] == w[t]) << 7 | min(bid(seed_w[t - off]), 15) << 8 | (seed EQ) << 12 | str[t] << 13
+// (off = len - seed_len; the seed fields are 0 before the seed window), indexed like the width arena.  A node popped at
+// position i looks at E[i-1] and E[i-2] -- two 2-byte loads from the same sector -- and a read's two strands are ~400 bytes
+// = 13 sectors in all, which stay in L1/L2 for the whole search.  bid saturates at 127 / 15: it is only ever compared with
+// values <= max_diff <= 126 and <= max_seed_diff <= 14 (checked on the host).
+#define C16_BID 0x7fu
+#define C16_EQ 0x80u
+#define C16_SBID_SHIFT 8
+#define C16_SEQ 0x1000u
+#define C16_BASE_SHIFT 13
+#define C16_KEEP 0xff00u // seed fields + base: what gap_shadow never changes
+__device__ __forceinline__ uint32_t c16_width(uint32_t v) // bid | EQ << 15  ->  the width fields of an entry
+{
+	const uint32_t b = v & WB_BID;
+	return (b > C16_BID ? C16_BID : b) | ((v & WB_EQ) ? C16_EQ : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_ctx16(const Batch B)
+{
+#ifdef BWAGPU_HOST_EMU
+	const int job = (int)blockIdx.x, lane = 0, nl = 1;
+#else
+	const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int job = (int)(gt >> 5), lane = (int)(gt & 31), nl = 32;
+#endif
+	if (job >= B.n_jobs) return;
+	const int r = B.jobs ? B.jobs[job] : job;
+	const ReadMeta m = B.meta[r];
+	const int len = m.len, seed_len = B.opt.seed_len;
+	if (len == 0) return;
+	const bool has_seed = len > seed_len;
+	const int off = len - seed_len;
+	const uint8_t *s = B.seq + m.seq_off;
+	for (int a = 0; a < 2; ++a) {
+		const uint16_t *wb = B.bid + m.w_off + (size_t)a * WSTRIDE(len);
+		const uint16_t *swb = B.bid + m.w_off + 2 * WSTRIDE(len) + (size_t)a * WSTRIDE(seed_len);
+		uint16_t *cx = B.ctx16 + m.w_off + (size_t)a * WSTRIDE(len);
+		for (int t = lane; t < len; t += nl) {
+			uint32_t e = c16_width(wb[t]) | ((uint32_t)(s[t] >> (a << 2)) & 7u) << C16_BASE_SHIFT;
+			if (has_seed && t >= off) {
+				const uint32_t sv = swb[t - off], sb = sv & WB_BID;
+				e |= (sb > 15u ? 15u : sb) << C16_SBID_SHIFT | ((sv & WB_EQ) ? C16_SEQ : 0u);
+			}
+			cx[t] = (uint16_t)e;
+		}
+	}
+}
+
 // ------------------------------------------------------------------ K3: gapped search
 // bwt_match_gap (bwtgap.c:104-266) with its gap_stack (bwtgap.c:13-79), one read per
 // thread, persistent threads pulling reads from a global counter.
@@ -328,9 +383,6 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #define ARENA_ALLOC(cap) ((((size_t)(cap)) + ((1u << BWAGPU_ARENA_G) - 1u)) & ~(size_t)((1u << BWAGPU_ARENA_G) - 1u))
 #ifndef BWAGPU_NO_FREELIST
 #define BWAGPU_NO_FREELIST 1 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
-#endif
-#ifndef BWAGPU_CTX_GROUP
-#define BWAGPU_CTX_GROUP 0 // 1: keep the 32-byte group (4 context words) of the last context load in registers: a match chain walks i downwards
 #endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
@@ -452,6 +504,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 #define RD_MAXDIFF ((int)(rd >> 24))
 	uint32_t w_off = 0; // the read's offset into the width / context arenas
 	int best_score = 0, best_cnt = 0, n_aln = 0, n_entries = 0, max_entries = 0;
+	uint32_t pops_left = 0; // pass 0: nodes this read may still pop before it is handed to the next pass
+	uint32_t read_pops = 0; // STATS
 	bool overflow = false;
 	// Bucket lists.  heads[s] in memory is only meaningful while bit s of the mask is set, and
 	// the head of the bucket popped last lives in a register (cur_s / cur_head), so neither a
@@ -478,21 +532,18 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	int lr_s = -1;
 #endif
 	int m = 0, i = 0; // i doubles as the exact tail's cursor
-	// context of the current node, loaded together with its occurrence blocks (k_ctx): width[i-1], width[i-2].bid,
-	// the two seed-width entries, str[i-1], str[i-2]
-	uint2 cw = make_uint2(0u, 0u);
-#if BWAGPU_CTX_GROUP
-	// the sector the last context word came from: the match continuation and the exact tail step i down by one per trip, so three
-	// of four context loads on such a path are served from registers.  Invalidated whenever gap_shadow rewrites context words.
-	uint32_t cg_id = 0xffffffffu;
-	uint4 cg_lo = make_uint4(0u, 0u, 0u, 0u), cg_hi = make_uint4(0u, 0u, 0u, 0u);
-#endif
-#define CW_WB1 (cw.x & (CW_BID | WB_EQ))
-#define CW_C1 ((cw.x >> 12) & 7u)
-#define CW_B2 ((int)((cw.x >> 16) & CW_BID))
-#define CW_CN ((cw.x >> 28) & 7u)
-#define CW_SW1 (cw.y & (CW_BID | WB_EQ))
-#define CW_S2 ((int)((cw.y >> 16) & CW_BID))
+	// context of the current node, loaded together with its occurrence blocks (k_ctx16): cw = E[i-1] | E[i-2] << 16, i.e.
+	// width[i-1] (bid, EQ), width[i-2].bid, the two seed-width entries, str[i-1], str[i-2]
+	uint32_t cw = 0u;
+	const uint16_t *const ctx16 = B.ctx16;
+#define CW_BID1 ((int)(cw & C16_BID))                       /* width[i-1].bid */
+#define CW_EQ1 (cw & C16_EQ)                                 /* width[i-2].w == width[i-1].w */
+#define CW_C1 ((cw >> C16_BASE_SHIFT) & 7u)                  /* str[i-1] */
+#define CW_B2 ((int)((cw >> 16) & C16_BID))                  /* width[i-2].bid */
+#define CW_CN ((cw >> (16 + C16_BASE_SHIFT)) & 7u)           /* str[i-2] */
+#define CW_SBID1 ((int)((cw >> C16_SBID_SHIFT) & 15u))       /* seed_width[si].bid */
+#define CW_SEQ1 (cw & C16_SEQ)
+#define CW_S2 ((int)((cw >> (16 + C16_SBID_SHIFT)) & 15u))   /* seed_width[si-1].bid */
 	uint32_t f_ref = 0, f_own = 0, n_pops = 0, n_pushes = 0, n_stored = 0, n_pruned = 0, n_expand = 0, n_exact = 0, n_derive = 0, n_trips = 0, n_mempop = 0;
 	if (STATS) atomicMin(B.stats + 12, gtime());
 
@@ -573,6 +624,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	// copies the finished read's results out and resets the per-slot stack
 	auto finish_read = [&]() {
 		uint32_t off = 0;
+		if (STATS && !overflow) atomicAdd(B.stats + 64 + (read_pops ? 31 - __clz((int)read_pops) : 0), 1ull);
 		if (!overflow && n_aln > 0) {
 			off = atomicAdd(B.pool_count, (unsigned int)n_aln);
 			if (off + (uint32_t)n_aln > B.pool_cap) overflow = true;
@@ -624,10 +676,10 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			const size_t wo = (size_t)w_off + (size_t)a * WSTRIDE(len);
 			uint32_t *w = B.w + wo;
 			uint16_t *wb = B.bid + wo;
-			uint2 *cx = B.ctx + wo;
+			uint16_t *cx = B.ctx16 + wo;
 			const uint32_t x = hl - hk + 1, mx = B.ix[1 - a].seq_len;
 			const int ldp = (int)(e_pos >> 16);
-			uint32_t j = 0, prev = 0, prev_nb = 0;
+			uint32_t j = 0, prev = 0;
 			for (int t = 0; t <= ldp && t <= len; ++t) {
 				uint32_t wv = w[t], bid = wb[t] & WB_BID;
 				if (t < ldp) {
@@ -636,15 +688,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				}
 				const uint32_t nb = bid | ((t > 0 && wv == prev) ? WB_EQ : 0u);
 				wb[t] = (uint16_t)nb;
-				if (t + 1 <= len) { // the context word of position t+1 sees wb[t] and wb[t-1]
-					uint32_t *p = &cx[t + 1].x;
-					*p = (*p & CW_KEEP) | cw_of(nb) | (cw_of(prev_nb) & CW_BID) << 16;
-				}
-				prev = wv; prev_nb = nb;
+				if (t < len) cx[t] = (uint16_t)((cx[t] & C16_KEEP) | c16_width(nb)); // the entry of position t: its width fields
+				prev = wv;
 			}
-#if BWAGPU_CTX_GROUP
-			cg_id = 0xffffffffu; // context words were rewritten
-#endif
 			const uint32_t idx = alloc_rec();
 			if (idx != NIL) {
 				*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score);
@@ -695,6 +741,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			rd = (uint32_t)md.len | (uint32_t)md.max_gapo << 16 | (uint32_t)md.max_diff << 24;
 			overflow = false;
 			n_aln = 0; max_entries = 0; best_cnt = 0; n_entries = 0;
+			pops_left = (!POOLED && B.pop_cap) ? B.pop_cap : 0xffffffffu;
+			if (STATS) read_pops = 0;
 			max_diff = md.max_diff;
 			// len == 0: bwtaln.c:134 (aln = 0, n_aln = 0); too many N: bwtgap.c:118-123
 			// (*pmax_entries is left untouched there)
@@ -714,6 +762,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		}
 
 		if (active && mode == MODE_POP) {
+			if (!POOLED && pops_left-- == 0) overflow = true; // a straggler: the warp-per-read pass does it faster than one lane can
 			bool stop = overflow || n_entries == 0;
 			if (!stop) {
 				if (max_entries < n_entries) max_entries = n_entries;
@@ -805,7 +854,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 					i = (int)(e_pos & 0xffffu);
 				}
 				--n_entries;
-				if (STATS) ++n_pops;
+				if (STATS) { ++n_pops; ++read_pops; }
 				fresh = true;
 			}
 		}
@@ -821,29 +870,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			jk = occ_arg(ix, k - 1); jl = occ_arg(ix, l);
 			ob_l = load_block(ix, jl >> 6);
 			ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
-			if (fresh | (mode == MODE_EXACT)) // fresh: the node's own word; exact tail: .x's base field of word i-1 = str[i-2]
-			{
-				const size_t cidx = (size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)(fresh ? i : i - 1);
-#if BWAGPU_CTX_GROUP
-				const uint32_t g = (uint32_t)(cidx >> 2);
-				if (g != cg_id) {
-					const uint4 *gp = reinterpret_cast<const uint4 *>(B.ctx + ((size_t)g << 2));
-#ifdef BWAGPU_HOST_EMU
-					cg_lo = gp[0]; cg_hi = gp[1];
-#else
-					asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-					             : "=r"(cg_lo.x), "=r"(cg_lo.y), "=r"(cg_lo.z), "=r"(cg_lo.w), "=r"(cg_hi.x), "=r"(cg_hi.y), "=r"(cg_hi.z), "=r"(cg_hi.w)
-					             : "l"(gp) : "memory");
-#endif
-					cg_id = g;
-				}
-				const uint32_t sel = (uint32_t)cidx & 3u;
-				cw = sel == 0 ? make_uint2(cg_lo.x, cg_lo.y) : sel == 1 ? make_uint2(cg_lo.z, cg_lo.w) : sel == 2 ? make_uint2(cg_hi.x, cg_hi.y) : make_uint2(cg_hi.z, cg_hi.w);
-#else
-				cw = B.ctx[cidx];
-#endif
+			if (fresh | (mode == MODE_EXACT)) { // fresh: the node's own entries E[i-1], E[i-2]; exact tail: E[i-2] (its base = str[i-2]) in the low half
+				const int j = fresh ? i : i - 1;
+				const uint16_t *cp = ctx16 + ((size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)j);
+				const uint32_t e1 = j >= 1 ? (uint32_t)cp[-1] : 0u;
+				const uint32_t e2 = (fresh && j >= 2) ? (uint32_t)cp[-2] : 0u;
+				cw = e1 | e2 << 16;
 			}
 			if (STATS) {
+				{ const int dpt = RD_LEN - i; atomicAdd(B.stats + 32 + (dpt < 0 ? 0 : dpt > 31 ? 31 : dpt), 1ull); }
 				f_own += (jk >> 6) != (jl >> 6) ? 2u : 1u;
 				if (k == 0) f_ref += 1u;
 				else {
@@ -860,7 +895,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			else {
 				m = max_diff - (mm + go);
 				if (gape_mode) m -= ge;
-				if (m < 0 || (i > 0 && m < (int)(CW_WB1 & WB_BID))) { if (STATS) ++n_pruned; active = false; } // stays in MODE_POP
+				if (m < 0 || (i > 0 && m < CW_BID1)) { if (STATS) ++n_pruned; active = false; } // stays in MODE_POP
 				else if (need_derive) mode = MODE_DERIVE;
 				else active = decide();
 			}
@@ -905,18 +940,16 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				const bool has_seed = len > O.seed_len;
 				bool allow_diff = true, allow_M = true;
 				if (i > 0) {
-					const uint32_t wb1 = CW_WB1;
-					const int b1 = CW_B2; // width[i-1].bid
+					const int b1 = CW_B2; // width[i-1].bid (i was decremented: the node's own i-2)
 					if (b1 > m - 1) allow_diff = false;
-					else if (b1 == m - 1 && (int)(wb1 & WB_BID) == m - 1 && (wb1 & WB_EQ)) allow_M = false;
+					else if (b1 == m - 1 && CW_BID1 == m - 1 && CW_EQ1) allow_M = false;
 					if (has_seed) {
 						const int si = i - (len - O.seed_len);
 						if (si > 0) {
 							const int m_seed = m - max_diff + O.max_seed_diff; // max_seed_diff - (mm + go [+ ge]) (bwtgap.c:153-155)
-							const uint32_t sw1 = CW_SW1;
 							const int s1 = CW_S2; // seed_width[si-1].bid
 							if (s1 > m_seed - 1) allow_diff = false;
-							else if (s1 == m_seed - 1 && (int)(sw1 & WB_BID) == m_seed - 1 && (sw1 & WB_EQ)) allow_M = false;
+							else if (s1 == m_seed - 1 && CW_SBID1 == m_seed - 1 && CW_SEQ1) allow_M = false;
 						}
 					}
 				}
@@ -983,11 +1016,13 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 #undef RD_LEN
 #undef RD_GAPO
 #undef RD_MAXDIFF
-#undef CW_WB1
+#undef CW_BID1
+#undef CW_EQ1
 #undef CW_C1
 #undef CW_B2
 #undef CW_CN
-#undef CW_SW1
+#undef CW_SBID1
+#undef CW_SEQ1
 #undef CW_S2
 
 	if (STATS) {

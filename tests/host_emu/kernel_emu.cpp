@@ -89,28 +89,30 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	std::vector<uint32_t> w(wo + 1);
 	std::vector<uint16_t> bid(wo + 1);
 	std::vector<uint2> ctx(wo + 8);
+	std::vector<uint16_t> ctx16(wo + 8);
 	std::vector<uint32_t> pool_off(n);
 	std::vector<uint4> pool((size_t)n * 64 + (1 << 16));
 	std::vector<int32_t> jobs_a(n), jobs_b(n);
 	int counters[4] = {0, 0, 0, 0};
-	unsigned long long stats[16] = {0};
+	unsigned long long stats[96] = {0};
 	Batch B;
 	B.ix[0] = E->ix[0]; B.ix[1] = E->ix[1];
 	B.opt = to_gapopt(opt);
 	B.n_reads = n;
 	B.seq = seq.data(); B.meta = meta.data();
-	B.w = w.data(); B.bid = bid.data(); B.ctx = ctx.data();
+	B.w = w.data(); B.bid = bid.data(); B.ctx = ctx.data(); B.ctx16 = ctx16.data();
 	B.n_aln = n_aln; B.max_entries = max_entries; B.pool_off = pool_off.data();
 	B.pool = pool.data(); B.pool_cap = (uint32_t)pool.size();
 	B.pool_count = (unsigned int *)&counters[2];
 	B.work_counter = &counters[0]; B.overflow_count = &counters[1];
 	B.stats = stats;
 	B.n_stacks = n_stacks;
+	B.pop_cap = getenv("EMU_POP_CAP") ? (uint32_t)atoi(getenv("EMU_POP_CAP")) : 0;
 	// K2
 	blockDim.x = 1; threadIdx.x = 0;
 	B.jobs = nullptr; B.n_jobs = n;
 	for (long long t = 0; t < 4ll * n; ++t) { blockIdx.x = (unsigned)t; k_width<true>(B); }
-	for (int t = 0; t < n; ++t) { blockIdx.x = (unsigned)t; k_ctx(B); }
+	for (int t = 0; t < n; ++t) { blockIdx.x = (unsigned)t; k_ctx16(B); }
 	if (stats8) { stats8[0] = stats[0]; stats8[1] = stats[1]; }
 	stats[0] = stats[1] = 0;
 	// K3 passes, as bwagpu.cu runs them: 0 = private arena only (k_search<.., false, ..>: small bucket mask, no free
@@ -142,7 +144,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 		counters[0] = counters[1] = 0;
 		if (t > 0) {
 			for (long long q = 0; q < 4ll * n_jobs; ++q) { blockIdx.x = (unsigned)q; k_width<true>(B); }
-			for (int q = 0; q < n_jobs; ++q) { blockIdx.x = (unsigned)q; k_ctx(B); }
+			for (int q = 0; q < n_jobs; ++q) { blockIdx.x = (unsigned)q; k_ctx16(B); }
 		}
 		gridDim.x = (unsigned)slots;
 		for (int s = 0; s < slots; ++s) {

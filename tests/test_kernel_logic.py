@@ -65,6 +65,17 @@ def test_search_logic_guaranteed_pass(golden, emu_index):
     assert R.compare_aln(want, got, "guaranteed") == []
 
 
+def test_search_logic_pop_cap(golden, emu_index, monkeypatch):
+    """Pass 0 hands a read that pops more than Batch::pop_cap nodes to the next pass (bounded tail of the thread-per-read kernel);
+    whatever it had found or edited (gap_shadow) by then is dropped and the retry starts from pristine widths."""
+    h, _ = emu_index
+    monkeypatch.setenv("EMU_POP_CAP", "40")
+    for name in ("se76", "adna"):
+        reads, opt, want = golden_case(golden, name)
+        got = R.emu_aln(h, reads, opt, cap1=2048, aln_cap1=64, n_slots=2, pool_chunks=4096)
+        assert R.compare_aln(want, got, name) == []
+
+
 def test_search_logic_retry_after_hits(golden, emu_index):
     """A read that fails AFTER its first hit has had its widths edited by gap_shadow;
     the retry must start from pristine widths."""

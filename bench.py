@@ -165,7 +165,7 @@ def run_reference(prefix: str, bam_in: str, bam_out: str, threads: int):
 # ------------------------------------------------------------------ this repo: bam2bam in-process behind the batched drivers
 class Report(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("wall_s", "index_load_s", "device_init_s", "pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s",
-                                          "dev_sw_s", "dev_ga_s", "inflate_cpu_s")] + \
+                                          "dev_sw_s", "dev_ga_s", "inflate_cpu_s", "process_cpu_s")] + \
                [(n, C.c_int64) for n in ("calls_aln", "reads_aln", "calls_sa", "q_sa", "calls_sw", "jobs_sw", "calls_ga", "jobs_ga", "sequences")]
 
     def asdict(self):
@@ -361,7 +361,7 @@ def main():
                   "both passes; wall minus the index load (0 after the first run: the index stays loaded, as in one long job)",
            "ms_each_step_rank0": steps_ms, "host_threads_per_rank": threads}
     last = reps[-1]
-    pipeline = {k: last[k] for k in ("pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s", "dev_sw_s", "dev_ga_s", "inflate_cpu_s", "reads_aln", "q_sa",
+    pipeline = {k: last[k] for k in ("pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s", "dev_sw_s", "dev_ga_s", "inflate_cpu_s", "process_cpu_s", "reads_aln", "q_sa",
                                      "jobs_sw", "jobs_ga")}
     pipeline["device_call_share_of_wall"] = ((last["dev_aln_s"] + last["dev_sa_s"] + last["dev_sw_s"] + last["dev_ga_s"])
                                              / max(1e-9, last["wall_s"] - last["index_load_s"]))

@@ -45,6 +45,8 @@
 #include "shim.h"
 #include <getopt.h>
 #include <signal.h>
+#include <sys/resource.h>
+#include <time.h>
 #include <unistd.h>
 #include "bwa_gpu_batch.h"
 
@@ -78,8 +80,35 @@ static void die(const char *what)
  * itself runs these functions concurrently in its worker threads (run_worker_thread, bam2bam.c:1387), so they are
  * re-entrant; the shim spreads each such phase of a batch over BWAGPU_SHIM_THREADS threads (default: the host's cores, at
  * most 64).  Everything order-sensitive (drand48 in bwa_aln2seq_core, the position cache, isize statistics) stays serial. */
-typedef struct { size_t n, grain; size_t next; pf_fn fn; void *ctx; } pf_job_t;
+typedef struct { size_t n, grain; size_t next; pf_fn fn; void *ctx; int bucket; } pf_job_t;
 #define MAX_THREADS 64
+
+__thread int t_cpu_bucket = CPU_OTHER;
+static int64_t g_cpu_ns[CPU_N];
+static const char *const g_cpu_name[CPU_N] = {"inflate", "parse", "bam1_to_seq", "aln2seq (serial)", "cal_pac_pos_core", "isize", "store/encode", "destroy",
+	"load/decode", "enumerate", "pairing", "XA aln2seq (serial)", "rescue record", "rescue replay", "refine record", "refine replay + update_bam1",
+	"BAM layout", "deflate", "fwrite", "other"};
+
+double thread_cpu_now(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+void cpu_add(int bucket, double seconds) { __sync_fetch_and_add(&g_cpu_ns[bucket], (int64_t)(seconds * 1e9)); }
+
+static void cpu_report(const char *what)
+{
+	char line[2048];
+	int b, o = 0;
+	double tot = 0;
+	for (b = 0; b < CPU_N; ++b) tot += 1e-9 * (double)g_cpu_ns[b];
+	o += snprintf(line + o, sizeof(line) - (size_t)o, "[bwa_gpu_batch] host CPU seconds by activity (%s, %.2f in all):", what, tot);
+	for (b = 0; b < CPU_N; ++b)
+		if (g_cpu_ns[b]) o += snprintf(line + o, sizeof(line) - (size_t)o, " %s %.2f;", g_cpu_name[b], 1e-9 * (double)g_cpu_ns[b]);
+	fprintf(stderr, "%s\n", line);
+}
 
 int shim_threads(void)
 {
@@ -96,6 +125,7 @@ int shim_threads(void)
 static void *pf_worker(void *arg)
 {
 	pf_job_t *j = (pf_job_t *)arg;
+	const double c0 = thread_cpu_now();
 	for (;;) {
 		const size_t lo = __sync_fetch_and_add(&j->next, j->grain);
 		size_t i, hi;
@@ -103,12 +133,13 @@ static void *pf_worker(void *arg)
 		hi = lo + j->grain < j->n ? lo + j->grain : j->n;
 		for (i = lo; i < hi; ++i) j->fn(i, j->ctx);
 	}
+	cpu_add(j->bucket, thread_cpu_now() - c0);
 	return 0;
 }
 
 void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
 {
-	pf_job_t j = {n, grain ? grain : 1, 0, fn, ctx};
+	pf_job_t j = {n, grain ? grain : 1, 0, fn, ctx, t_cpu_bucket};
 	pthread_t th[MAX_THREADS];
 	int t, nt = shim_threads();
 	if ((size_t)nt > (n + j.grain - 1) / j.grain) nt = (int)((n + j.grain - 1) / j.grain);
@@ -126,11 +157,13 @@ int slice_count(size_t n, size_t min_per_slice)
 	return nt < 1 ? 1 : (int)nt;
 }
 
-typedef struct { ps_fn fn; void *ctx; size_t n; int nt, s; } ps_arg_t;
+typedef struct { ps_fn fn; void *ctx; size_t n; int nt, s, bucket; } ps_arg_t;
 static void *ps_worker(void *arg)
 {
 	ps_arg_t *a = (ps_arg_t *)arg;
+	const double c0 = thread_cpu_now();
 	a->fn(a->s, a->n * (size_t)a->s / (size_t)a->nt, a->n * (size_t)(a->s + 1) / (size_t)a->nt, a->ctx);
+	cpu_add(a->bucket, thread_cpu_now() - c0);
 	return 0;
 }
 
@@ -140,7 +173,7 @@ int parallel_slices(size_t n, size_t min_per_slice, ps_fn fn, void *ctx)
 	ps_arg_t a[MAX_THREADS];
 	pthread_t th[MAX_THREADS];
 	int s;
-	for (s = 0; s < nt; ++s) { a[s].fn = fn; a[s].ctx = ctx; a[s].n = n; a[s].nt = nt; a[s].s = s; }
+	for (s = 0; s < nt; ++s) { a[s].fn = fn; a[s].ctx = ctx; a[s].n = n; a[s].nt = nt; a[s].s = s; a[s].bucket = t_cpu_bucket; }
 	for (s = 1; s < nt; ++s) pthread_create(&th[s], 0, ps_worker, &a[s]);
 	ps_worker(&a[0]);
 	for (s = 1; s < nt; ++s) pthread_join(th[s], 0);
@@ -156,6 +189,7 @@ static pe_opt_t *g_pe;         /* bam2bam.c:95 */
 int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned; /* bam2bam.c:96-101, options 130 / 131 / 133 / 128 */
 static isize_info_t g_null_ii; /* bam2bam.c:106 */
 static bwa_gpu_batch_report_t g_rep; /* the run in progress / the last run (bwa_gpu_batch.h) */
+static double g_cpu0;
 
 /* The index of a long-lived host process (bench.py runs bam2bam several times in one process): with keep_index on, the
  * loaders hand back what an earlier run loaded from the same files, the matching destroy calls leave it alone, and the
@@ -274,6 +308,7 @@ int bwa_bam_to_bam(int argc, char *argv[], char *version)
 	av[argc] = 0;
 	g_only_aligned = g_broken_input = g_skip_duplicates = g_drop_aligned = 0;
 	memset(&g_rep, 0, sizeof(g_rep));
+	memset(g_cpu_ns, 0, sizeof(g_cpu_ns));
 	optind = 0; opterr = 0; /* glibc: a full re-initialisation, quietly -- the real parse below reports what is wrong */
 	while ((c = getopt_long(argc, av, "g:n:o:e:i:d:l:k:LR:m:t:NM:O:E:q:f:C:D:a:sc:h:H:Ap:0:1:2:", longopts, 0)) >= 0) {
 		if (c == 128) g_only_aligned = 1;      /* bam2bam.c:1988 */
@@ -283,10 +318,21 @@ int bwa_bam_to_bam(int argc, char *argv[], char *version)
 	}
 	free(av);
 	optind = 0; opterr = 1;
+	{
+		struct rusage ru;
+		getrusage(RUSAGE_SELF, &ru);
+		g_cpu0 = (double)ru.ru_utime.tv_sec + 1e-6 * (double)ru.ru_utime.tv_usec + (double)ru.ru_stime.tv_sec + 1e-6 * (double)ru.ru_stime.tv_usec;
+	}
 	t0 = now();
 	rc = real_bwa_bam_to_bam(argc, argv, version);
 	g_rep.wall_s = now() - t0;
-	g_rep.inflate_cpu_s = fastin_inflate_seconds();
+	g_rep.inflate_cpu_s = 1e-9 * (double)g_cpu_ns[CPU_INFLATE];
+	{
+		struct rusage ru;
+		getrusage(RUSAGE_SELF, &ru);
+		g_rep.process_cpu_s = (double)ru.ru_utime.tv_sec + 1e-6 * (double)ru.ru_utime.tv_usec + (double)ru.ru_stime.tv_sec + 1e-6 * (double)ru.ru_stime.tv_usec - g_cpu0;
+	}
+	cpu_report("whole run");
 	return rc;
 }
 
@@ -593,6 +639,7 @@ static size_t load_records(gzFile temporary, bam_pair_t *recs, size_t B, long *t
 	n = memtemp_take(B, &first);
 	if (n) {
 		codec_ctx_t c = {recs, first};
+		t_cpu_bucket = CPU_LOAD;
 		parallel_for(n, 1024, decode_one, &c);
 		for (i = 0; i < n; ++i) *tot_seqs += recs[i].kind;
 	}
@@ -632,6 +679,7 @@ static void align_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_t
 	int m = 0, j;
 	double t1 = now();
 	/* aln_singleton / aln_pair without the search ... */
+	t_cpu_bucket = CPU_TOSEQ;
 	parallel_for(n, 2048, to_seq_one, recs);
 	for (i = 0; i < n; ++i) {
 		bam_pair_t *r = &recs[i];
@@ -688,7 +736,7 @@ static void position_range(bam_pair_t *recs, size_t n, saq_t *q, size_t **qoff_b
 {
 	size_t i;
 	int j;
-	double t1 = now();
+	double t1 = now(), c0 = thread_cpu_now();
 	posn_ctx_t c;
 	if (n + 1 > *qoff_cap) { *qoff_cap = n + 1; *qoff_buf = (size_t *)realloc(*qoff_buf, (n + 1) * sizeof(size_t)); }
 	q->n = 0;
@@ -708,9 +756,11 @@ static void position_range(bam_pair_t *recs, size_t n, saq_t *q, size_t **qoff_b
 	}
 	(*qoff_buf)[n] = q->n;
 	*t_host += now() - t1;
+	cpu_add(CPU_POSN_SERIAL, thread_cpu_now() - c0);
 	saq_run(q);
 	t1 = now();
 	c.recs = recs; c.q = q; c.qoff = *qoff_buf;
+	t_cpu_bucket = CPU_POSN_PAR;
 	parallel_slices(n, 4096, posn_slice, &c);
 	*t_host += now() - t1;
 }
@@ -769,6 +819,7 @@ static void *stage_read(void *arg)
 		double t;
 		P1_WAIT(P, slot, SL_FREE);
 		t = now();
+		const double c0 = thread_cpu_now();
 		while (n < P->B) {
 			const int rc = read_bam_pair(P->ks, &recs[n], g_broken_input, g_drop_aligned);
 			if (rc < 0) {
@@ -780,6 +831,7 @@ static void *stage_read(void *arg)
 			++n;
 		}
 		P->t_read += now() - t;
+		cpu_add(CPU_PARSE, thread_cpu_now() - c0);
 		P->n[slot] = n; P->seqs[slot] = seqs;
 		P1_SET(P, slot, SL_READ);
 		if (n == 0) break; /* an empty batch is the end marker; it travels through every stage */
@@ -804,8 +856,12 @@ static void *stage_position(void *arg)
 		if (n) {
 			position_range(recs, n, &q, &qoff, &qoff_cap, &P->t_host);
 			t1 = now();
-			for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
-				if (unique_rec(&recs[i])) improve_isize_est(P->iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
+			{
+				const double c0 = thread_cpu_now();
+				for (i = 0; i < n; ++i) /* the unchanged tail of the loop (bam2bam.c:1167-1170) */
+					if (unique_rec(&recs[i])) improve_isize_est(P->iinfos, &recs[i], g_pe->ap_prior, g_bwt[0]->seq_len);
+				cpu_add(CPU_ISIZE, thread_cpu_now() - c0);
+			}
 			P->t_host += now() - t1;
 		}
 		P1_SET(P, slot, SL_POSITIONED);
@@ -827,7 +883,11 @@ static void *stage_store(void *arg)
 		n = P->n[slot];
 		if (n == 0) { P1_SET(P, slot, SL_STORED); break; }
 		t1 = now();
-		store_records(P->temporary, P->recs[slot], n);
+		{
+			const double c0 = thread_cpu_now();
+			store_records(P->temporary, P->recs[slot], n);
+			cpu_add(CPU_STORE, thread_cpu_now() - c0);
+		}
 		P->t_write += now() - t1;
 		P->tot_seqs += P->seqs[slot];
 		fprintf(stderr, "[sequential_loop_pass1] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
@@ -846,7 +906,11 @@ static void *stage_destroy(void *arg)
 		P1_WAIT(P, slot, SL_STORED);
 		if (P->n[slot] == 0) break;
 		t1 = now();
-		destroy_records(P->recs[slot], P->n[slot]);
+		{
+			const double c0 = thread_cpu_now();
+			destroy_records(P->recs[slot], P->n[slot]);
+			cpu_add(CPU_DESTROY, thread_cpu_now() - c0);
+		}
 		P->t_destroy += now() - t1;
 		P1_SET(P, slot, SL_FREE);
 	}
@@ -990,8 +1054,10 @@ static void stage_enumerate(batch2_t *b, kh_64_t *my_hash)
 		b->qoff = (size_t *)realloc(b->qoff, b->m_rec * sizeof(size_t)); b->voff = (size_t *)realloc(b->voff, b->m_rec * sizeof(size_t));
 		b->want = (uint8_t *)realloc(b->want, b->m_rec);
 	}
+	t_cpu_bucket = CPU_TOSEQ;
 	parallel_for(b->n, 1024, pair_to_seq_one, b->recs);
 	b->q1.n = 0; b->n_visit = 0;
+	const double c0 = thread_cpu_now();
 	for (i = 0; i < b->n; ++i) {
 		bam_pair_t *r = &b->recs[i];
 		b->qoff[i] = b->q1.n; b->voff[i] = b->n_visit; b->want[i] = 0;
@@ -1020,6 +1086,7 @@ static void stage_enumerate(batch2_t *b, kh_64_t *my_hash)
 			}
 	}
 	b->qoff[b->n] = b->q1.n; b->voff[b->n] = b->n_visit;
+	cpu_add(CPU_ENUM, thread_cpu_now() - c0);
 	saq_run(&b->q1);
 }
 
@@ -1099,9 +1166,11 @@ static void stage_pairing(batch2_t *b)
 {
 	size_t i;
 	int j, k;
+	t_cpu_bucket = CPU_PAIRING;
 	parallel_for(b->n_visit, 64, fill_visit_one, b);
 	parallel_for(b->n, 256, pairing_one, b);
 	b->q2.n = 0;
+	const double c0 = thread_cpu_now();
 	for (i = 0; i < b->n; ++i) {
 		bam_pair_t *r = &b->recs[i];
 		bwa_seq_t *p[2];
@@ -1117,7 +1186,9 @@ static void stage_pairing(batch2_t *b)
 			}
 	}
 	b->voff[b->n] = b->q2.n;
+	cpu_add(CPU_XA_SERIAL, thread_cpu_now() - c0);
 	saq_run(&b->q2);
+	t_cpu_bucket = CPU_XA_SERIAL;
 	if (b->q2.n) parallel_slices(b->n, 4096, xa_assign_slice, b);
 }
 
@@ -1162,6 +1233,7 @@ static void stage_rescue(batch2_t *b, uint64_t n_tot[2], uint64_t n_mapped[2])
 	size_t total = 0, i;
 	int s, ns;
 	double t0;
+	t_cpu_bucket = CPU_RESCUE_RECORD;
 	ns = parallel_slices(b->n, 2048, rescue_record_slice, b);
 	b->n_slices = ns;
 	for (s = 0; s < ns; ++s) { b->sw_off[s] = total; total += b->swq[s].n; }
@@ -1186,6 +1258,7 @@ static void stage_rescue(batch2_t *b, uint64_t n_tot[2], uint64_t n_mapped[2])
 		b->sw_pool = b->sw_pool_copy;
 	}
 	REP_ADD(calls_sw, jobs_sw, dev_sw_s, total, t0);
+	t_cpu_bucket = CPU_RESCUE_REPLAY;
 	parallel_slices(b->n, 2048, rescue_replay_slice, b);
 	for (s = 0; s < ns; ++s) { n_tot[0] += b->n_tot[s][0]; n_tot[1] += b->n_tot[s][1]; n_mapped[0] += b->n_mapped[s][0]; n_mapped[1] += b->n_mapped[s][1]; }
 }
@@ -1271,7 +1344,9 @@ static void stage_refine(batch2_t *b)
 	size_t total = 0, i;
 	int s, ns;
 	double t0;
+	t_cpu_bucket = CPU_TOSEQ;
 	parallel_for(b->n, 1024, pair_to_seq_one, b->recs); /* singletons reach this stage first */
+	t_cpu_bucket = CPU_REFINE_RECORD;
 	ns = parallel_slices(b->n, 2048, refine_record_slice, b);
 	for (s = 0; s < ns; ++s) { b->ga_off[s] = total; total += b->gaq[s].n; }
 	b->ga_off[ns] = total;
@@ -1299,6 +1374,7 @@ static void stage_refine(batch2_t *b)
 		b->ga_pool = b->ga_pool_copy;
 	}
 	REP_ADD(calls_ga, jobs_ga, dev_ga_s, total, t0);
+	t_cpu_bucket = CPU_REFINE_REPLAY;
 	parallel_slices(b->n, 2048, refine_replay_slice, b);
 }
 
@@ -1359,7 +1435,11 @@ static void *stage2_write(void *arg)
 		if (b->n == 0) break;
 		t1 = now();
 		write_records_bam(P->output, b->recs, b->n);
-		destroy_records(b->recs, b->n);
+		{
+			const double c0 = thread_cpu_now();
+			destroy_records(b->recs, b->n);
+			cpu_add(CPU_DESTROY, thread_cpu_now() - c0);
+		}
 		P->t_write += now() - t1;
 		P->tot_seqs += b->seqs;
 		fprintf(stderr, "[sequential_loop_pass2] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);

@@ -16,6 +16,7 @@ typedef struct {
 	double pass1_s, pass2_s;
 	double dev_aln_s, dev_sa_s, dev_sw_s, dev_ga_s; /* host-side seconds inside the four device calls */
 	double inflate_cpu_s; /* CPU seconds of the input inflate threads, summed */
+	double process_cpu_s; /* CPU seconds of the whole process during the call (user + system, every thread) */
 	int64_t calls_aln, reads_aln, calls_sa, q_sa, calls_sw, jobs_sw, calls_ga, jobs_ga;
 	int64_t sequences;    /* reads that went through pass 1 */
 } bwa_gpu_batch_report_t;

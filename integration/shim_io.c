@@ -70,7 +70,7 @@ void fastin_set_path(const char *path)
 	g_next_path = path ? strdup(path) : 0;
 }
 
-double fastin_inflate_seconds(void) { return g_inflate_s + F.cpu_s; }
+double fastin_inflate_seconds(void) { return g_inflate_s; }
 
 static int bgzf_header_ok(const uint8_t *p, size_t left, size_t *bsize)
 {
@@ -115,7 +115,7 @@ static void *fi_worker(void *arg)
 		if (F.stop) { pthread_mutex_unlock(&F.mu); break; }
 		s->state = FS_BUSY;
 		pthread_mutex_unlock(&F.mu);
-		t0 = shim_now();
+		t0 = thread_cpu_now();
 		memcpy(&isize, F.map + off + bsize - 4, 4);
 		if (isize > FI_BLOCK) isize = FI_BLOCK + 1; /* forces the error below */
 		zs.next_in = (Bytef *)(F.map + off + 18); zs.avail_in = (uInt)(bsize - 18 - 8);
@@ -124,7 +124,7 @@ static void *fi_worker(void *arg)
 			const int rc = isize <= FI_BLOCK ? inflate(&zs, Z_FINISH) : Z_DATA_ERROR;
 			const int bad = rc != Z_STREAM_END || zs.total_out != isize;
 			inflateReset(&zs);
-			cpu += shim_now() - t0;
+			cpu += thread_cpu_now() - t0;
 			pthread_mutex_lock(&F.mu);
 			if (bad) { fprintf(stderr, "[bwa_gpu_batch] %s: inflate failed in the block at offset %zu\n", F.path, off); F.error = 1; }
 			s->len = (int)isize; s->seq = j; s->state = FS_FILLED;
@@ -133,9 +133,7 @@ static void *fi_worker(void *arg)
 		}
 	}
 	inflateEnd(&zs);
-	pthread_mutex_lock(&F.mu);
-	F.cpu_s += cpu;
-	pthread_mutex_unlock(&F.mu);
+	cpu_add(CPU_INFLATE, cpu);
 	return 0;
 }
 
@@ -149,9 +147,9 @@ static void *ra_main(void *arg) /* plain gzip: the one thread that may touch the
 		double t0;
 		while (!F.stop && RA_CAP - (F.head - __atomic_load_n(&F.tail, __ATOMIC_ACQUIRE)) < RA_PIECE) usleep(100);
 		if (F.stop) break;
-		t0 = shim_now();
+		t0 = thread_cpu_now();
 		got = gzread(F.fp, piece, (unsigned)RA_PIECE);
-		cpu += shim_now() - t0;
+		cpu += thread_cpu_now() - t0;
 		if (got <= 0) break;
 		while (done < got) {
 			const size_t at = (F.head + (size_t)done) % RA_CAP;
@@ -163,7 +161,7 @@ static void *ra_main(void *arg) /* plain gzip: the one thread that may touch the
 	}
 	__atomic_store_n(&F.eof, 1, __ATOMIC_RELEASE);
 	free(piece);
-	F.cpu_s += cpu;
+	cpu_add(CPU_INFLATE, cpu);
 	return 0;
 }
 
@@ -502,12 +500,18 @@ void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n)
 		if (nblk * OB_OUT > m_cbuf) { m_cbuf = nblk * OB_OUT + (nblk / 4) * OB_OUT; cbuf = (uint8_t *)realloc(cbuf, m_cbuf); }
 		if (nblk > m_clen) { m_clen = nblk + nblk / 4; clen = (int *)realloc(clen, m_clen * sizeof(int)); }
 		c.ubuf = ubuf; c.cbuf = cbuf; c.clen = clen;
+		t_cpu_bucket = CPU_BAM_LAYOUT;
 		parallel_for(n, 2048, ob_fill_one, &c);
+		t_cpu_bucket = CPU_DEFLATE;
 		parallel_for(nblk, 4, ob_deflate_one, &c);
 		if (c.failed) { fprintf(stderr, "[bwa_gpu_batch] deflate failed\n"); exit(1); }
-		for (i = 0; i < nblk; ++i) {
-			if (fwrite(cbuf + i * OB_OUT, 1, (size_t)clen[i], output->file) != (size_t)clen[i]) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
-			output->block_address += clen[i];
+		{
+			const double c0 = thread_cpu_now();
+			for (i = 0; i < nblk; ++i) {
+				if (fwrite(cbuf + i * OB_OUT, 1, (size_t)clen[i], output->file) != (size_t)clen[i]) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
+				output->block_address += clen[i];
+			}
+			cpu_add(CPU_WRITE, thread_cpu_now() - c0);
 		}
 	}
 }

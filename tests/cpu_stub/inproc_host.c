@@ -19,8 +19,8 @@ int main(int argc, char *argv[])
 		snprintf(out, sizeof out, "%s.%d.bam", argv[5], r);
 		if (bwa_bam_to_bam(8, av, "inproc")) return 1;
 		if (bwa_gpu_batch_last_report(&rep)) return 1;
-		printf("run %d wall %.3f index_load %.3f pass1 %.3f pass2 %.3f reads_aln %ld sequences %ld\n", r, rep.wall_s, rep.index_load_s,
-		       rep.pass1_s, rep.pass2_s, (long)rep.reads_aln, (long)rep.sequences);
+		printf("run %d wall %.3f index_load %.3f pass1 %.3f pass2 %.3f cpu %.3f reads_aln %ld sequences %ld\n", r, rep.wall_s, rep.index_load_s,
+		       rep.pass1_s, rep.pass2_s, rep.process_cpu_s, (long)rep.reads_aln, (long)rep.sequences);
 	}
 	bwa_gpu_batch_drop_index();
 	return 0;

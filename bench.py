@@ -166,7 +166,8 @@ def run_reference(prefix: str, bam_in: str, bam_out: str, threads: int):
 class Report(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("wall_s", "index_load_s", "device_init_s", "pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s",
                                           "dev_sw_s", "dev_ga_s", "inflate_cpu_s", "process_cpu_s")] + \
-               [(n, C.c_int64) for n in ("calls_aln", "reads_aln", "calls_sa", "q_sa", "calls_sw", "jobs_sw", "calls_ga", "jobs_ga", "sequences")]
+               [(n, C.c_int64) for n in ("calls_aln", "reads_aln", "calls_sa", "q_sa", "calls_sw", "jobs_sw", "calls_ga", "jobs_ga", "sequences")] + \
+               [("dev_bgzf_s", C.c_double), ("calls_bgzf", C.c_int64), ("bytes_bgzf", C.c_int64)]
 
     def asdict(self):
         return {f[0]: getattr(self, f[0]) for f in self._fields_}
@@ -181,6 +182,7 @@ class Host:
         self.H = C.CDLL(SHIM)
         self.H.bwa_bam_to_bam.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p]
         self.H.bwa_gpu_batch_last_report.argtypes = [C.POINTER(Report)]
+        assert self.H.bwa_gpu_batch_report_size() == C.sizeof(Report), "bench.py's Report is out of step with integration/bwa_gpu_batch.h"
         self.H.bwa_gpu_batch_keep_index(1)
 
     def run(self, prefix: str, bam_in: str, bam_out: str):
@@ -362,7 +364,7 @@ def main():
            "ms_each_step_rank0": steps_ms, "host_threads_per_rank": threads}
     last = reps[-1]
     pipeline = {k: last[k] for k in ("pass1_s", "pass2_s", "dev_aln_s", "dev_sa_s", "dev_sw_s", "dev_ga_s", "inflate_cpu_s", "process_cpu_s", "reads_aln", "q_sa",
-                                     "jobs_sw", "jobs_ga")}
+                                     "jobs_sw", "jobs_ga", "dev_bgzf_s", "bytes_bgzf")}
     pipeline["device_call_share_of_wall"] = ((last["dev_aln_s"] + last["dev_sa_s"] + last["dev_sw_s"] + last["dev_ga_s"])
                                              / max(1e-9, last["wall_s"] - last["index_load_s"]))
     per_step = {k: tot[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global")}

@@ -247,6 +247,21 @@ typedef struct {
 int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
                               const bwa_cigar_t **cigar_pool);
 
+/* ------------------------------------------------------------------ BGZF output on the device
+ * Replaces the compute of bgzf.c:265-330 (deflate_block, one zlib deflate per <= 64 KB of BAM stream; bam2bam.c:2061
+ * opens its output at level 2 = zlib's greedy deflate_fast) and of bgzf_write's blocking (bgzf.c:533-556): `n_bytes` of
+ * BAM stream are cut every 65280 bytes and each piece becomes one complete BGZF member (18-byte header with BSIZE, raw
+ * deflate stream, CRC-32, ISIZE); *out is the members back to back -- write it to the file as it is.  Inflating the
+ * members gives back the input byte for byte (that stream is what the reference writes too); the compressed bytes are
+ * this codec's own and the same on every run.  level 0 = stored blocks (bgzf's "u" mode), anything else = compress.
+ * *out / *member_len point into pinned memory owned by the library, valid until the next bwa_gpu_bgzf_deflate call;
+ * one call at a time (calls are serialised inside).  `in` is copied fastest from bwa_gpu_host_alloc memory. */
+int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int level, const uint8_t **out, int64_t *out_bytes,
+                         const int32_t **member_len, int32_t *n_members, double *kernel_ms);
+/* page-locked host memory for the buffers handed to the calls above (NULL + bwa_gpu_last_error on failure) */
+void *bwa_gpu_host_alloc(size_t bytes);
+void bwa_gpu_host_free(void *p);
+
 /* ------------------------------------------------------------------ measurement hooks
  * Device-side timing (CUDA events on the library's own streams) and work counters of the
  * most recent batch call, summed over its chunks.  occ_fetches counts occurrence-block
@@ -287,6 +302,8 @@ typedef struct {
 	int64_t sw_cells_fwd;                              /* sum of window x read cells of K5's forward pass */
 	int64_t h2d_bytes, d2h_bytes;
 	int64_t occ_fetches_width, occ_fetches_search, own_fetches_search; /* from calls made while stats were enabled */
+	double ms_bgzf;                                    /* BGZF codec kernels (deflate + pack, inflate) */
+	int64_t bgzf_bytes_in, bgzf_bytes_out;             /* bytes into / out of the codec */
 } bwa_gpu_totals_t;
 int bwa_gpu_get_totals(bwa_gpu_totals_t *out);
 void bwa_gpu_reset_totals(void);

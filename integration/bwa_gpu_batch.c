@@ -372,12 +372,17 @@ static pthread_mutex_t g_rep_mu = PTHREAD_MUTEX_INITIALIZER;
 #define REP_ADD(calls_f, units_f, secs_f, units, t0) do { pthread_mutex_lock(&g_rep_mu); ++g_rep.calls_f; g_rep.units_f += (int64_t)(units); \
 		g_rep.secs_f += now() - (t0); pthread_mutex_unlock(&g_rep_mu); } while (0)
 
+void shim_count_bgzf(int64_t bytes, double seconds)
+{
+	pthread_mutex_lock(&g_rep_mu); ++g_rep.calls_bgzf; g_rep.bytes_bgzf += bytes; g_rep.dev_bgzf_s += seconds; pthread_mutex_unlock(&g_rep_mu);
+}
+
 static void report(void)
 {
 	fprintf(stderr, "[bwa_gpu_batch] device calls: cal_sa_reads_gap=%ld (%ld reads, %.2f s)  cal_pac_pos=%ld (%ld queries, %.2f s)  "
-	                "mate_sw_path=%ld (%ld jobs, %.2f s)  global_align=%ld (%ld jobs, %.2f s)\n", (long)g_rep.calls_aln, (long)g_rep.reads_aln,
+	                "mate_sw_path=%ld (%ld jobs, %.2f s)  global_align=%ld (%ld jobs, %.2f s)  bgzf_deflate=%ld (%ld bytes, %.2f s)\n", (long)g_rep.calls_aln, (long)g_rep.reads_aln,
 	        g_rep.dev_aln_s, (long)g_rep.calls_sa, (long)g_rep.q_sa, g_rep.dev_sa_s, (long)g_rep.calls_sw, (long)g_rep.jobs_sw, g_rep.dev_sw_s,
-	        (long)g_rep.calls_ga, (long)g_rep.jobs_ga, g_rep.dev_ga_s);
+	        (long)g_rep.calls_ga, (long)g_rep.jobs_ga, g_rep.dev_ga_s, (long)g_rep.calls_bgzf, (long)g_rep.bytes_bgzf, g_rep.dev_bgzf_s);
 }
 
 static void ensure_gpu(void)
@@ -397,6 +402,7 @@ static void ensure_gpu(void)
 		if (n < 1) n = 1;
 		if (n > 16) n = 16;
 		for (i = 0; i < n; ++i) ids[i] = first + i;
+		setenv("BWAGPU_MALLOPT", "1", 0); /* this host frees millions of aln[] per batch: keep the heaps (a process-wide choice, ours to make) */
 		if (bwa_gpu_init(n, ids)) die("bwa_gpu_init");
 	}
 	if (bwa_gpu_load_index(g_bwt, g_pac, g_bns->l_pac)) die("bwa_gpu_load_index");
@@ -606,10 +612,14 @@ static void decode_one(size_t i, void *ctx)
 	zmq_msg_close(&m);
 }
 
+/* a dozen free()s per record.  Serial on purpose: freeing from several threads what other threads allocated contends on
+ * glibc's arenas (measured: 7 CPU-seconds per million reads instead of 0.4, and the parse thread's mallocs slow down too) */
 static void destroy_records(bam_pair_t *recs, size_t n)
 {
+	const double c0 = thread_cpu_now();
 	size_t i;
 	for (i = 0; i < n; ++i) bam_destroy_pair(&recs[i]);
+	cpu_add(CPU_DESTROY, thread_cpu_now() - c0);
 }
 
 /* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file).  Serial on purpose: the encoder
@@ -820,16 +830,7 @@ static void *stage_read(void *arg)
 		P1_WAIT(P, slot, SL_FREE);
 		t = now();
 		const double c0 = thread_cpu_now();
-		while (n < P->B) {
-			const int rc = read_bam_pair(P->ks, &recs[n], g_broken_input, g_drop_aligned);
-			if (rc < 0) {
-				fprintf(stderr, "[sequential_loop_pass1] error reading input BAM%s\n", rc == -2 ? " (lone mate)" : "");
-				exit(1);
-			}
-			if (rc == 0) break;
-			seqs += recs[n].kind;
-			++n;
-		}
+		n = fastin_read_pairs(P->ks, recs, P->B, &seqs, g_broken_input, g_drop_aligned);
 		P->t_read += now() - t;
 		cpu_add(CPU_PARSE, thread_cpu_now() - c0);
 		P->n[slot] = n; P->seqs[slot] = seqs;
@@ -906,11 +907,7 @@ static void *stage_destroy(void *arg)
 		P1_WAIT(P, slot, SL_STORED);
 		if (P->n[slot] == 0) break;
 		t1 = now();
-		{
-			const double c0 = thread_cpu_now();
-			destroy_records(P->recs[slot], P->n[slot]);
-			cpu_add(CPU_DESTROY, thread_cpu_now() - c0);
-		}
+		destroy_records(P->recs[slot], P->n[slot]);
 		P->t_destroy += now() - t1;
 		P1_SET(P, slot, SL_FREE);
 	}
@@ -1435,11 +1432,7 @@ static void *stage2_write(void *arg)
 		if (b->n == 0) break;
 		t1 = now();
 		write_records_bam(P->output, b->recs, b->n);
-		{
-			const double c0 = thread_cpu_now();
-			destroy_records(b->recs, b->n);
-			cpu_add(CPU_DESTROY, thread_cpu_now() - c0);
-		}
+		destroy_records(b->recs, b->n);
 		P->t_write += now() - t1;
 		P->tot_seqs += b->seqs;
 		fprintf(stderr, "[sequential_loop_pass2] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
@@ -1727,6 +1720,8 @@ void *run_worker_thread(void *arg)
 }
 
 /* ------------------------------------------------------------------ for hosts that run bam2bam in-process */
+int bwa_gpu_batch_report_size(void) { return (int)sizeof(bwa_gpu_batch_report_t); }
+
 int bwa_gpu_batch_last_report(bwa_gpu_batch_report_t *out)
 {
 	if (!out) return 1;

@@ -19,9 +19,12 @@ typedef struct {
 	double process_cpu_s; /* CPU seconds of the whole process during the call (user + system, every thread) */
 	int64_t calls_aln, reads_aln, calls_sa, q_sa, calls_sw, jobs_sw, calls_ga, jobs_ga;
 	int64_t sequences;    /* reads that went through pass 1 */
+	double dev_bgzf_s;    /* host-side seconds inside bwa_gpu_bgzf_deflate */
+	int64_t calls_bgzf, bytes_bgzf;
 } bwa_gpu_batch_report_t;
 
 int bwa_gpu_batch_last_report(bwa_gpu_batch_report_t *out);
+int bwa_gpu_batch_report_size(void); /* sizeof(bwa_gpu_batch_report_t) as this library was built: lets a foreign-language binding check its mirror */
 
 /* on: the index files a run loads (and their device copy) stay loaded for the next run on the same files; the reference's
  * destroy calls at the end of a run leave them alone.  bwa_gpu_batch_drop_index() frees them. */

@@ -56,6 +56,7 @@ extern int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned;
 /* ---- shim_io.c */
 void fastin_set_path(const char *path);   /* bwa_bam_open: the file the next bam_read1 stream comes from */
 void fastin_close(void);                  /* bwa_seq_close */
+size_t fastin_read_pairs(bwa_seqio_t *ks, bam_pair_t *recs, size_t B, long *seqs, int broken_input, int drop_aligned); /* a batch of read_bam_pair's */
 double fastin_inflate_seconds(void);      /* CPU seconds the inflate threads spent (all threads summed) */
 
 void memtemp_begin(void);
@@ -70,5 +71,6 @@ void memtemp_get(size_t idx, const uint8_t **data, uint32_t *len);
 void memtemp_free(void);
 
 void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n);
+void shim_count_bgzf(int64_t bytes, double seconds); /* bwa_gpu_batch.c: the run report */
 
 #endif

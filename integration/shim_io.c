@@ -51,6 +51,9 @@ typedef struct {
 	uint64_t cons_seq;
 	int cons_off, have_slot;
 	size_t skip;
+	/* the batch reader's staging area: decompressed stream bytes [stage_pos, stage_len) come before what the ring holds */
+	uint8_t *stage;
+	size_t stage_pos, stage_len, stage_cap;
 	/* plain gzip: ring of bytes filled by one thread */
 	uint8_t *ring;
 	volatile size_t head, tail;
@@ -235,6 +238,7 @@ void fastin_close(void)
 	}
 	g_inflate_s += F.cpu_s;
 	free(F.path);
+	free(F.stage);
 	memset(&F, 0, sizeof(F));
 }
 
@@ -264,6 +268,13 @@ static int fi_next_block(void)
 static int fastin_read(void *dst, int len)
 {
 	int done = 0;
+	if (F.stage_pos < F.stage_len) { /* left over from the batch reader */
+		size_t run = F.stage_len - F.stage_pos;
+		if (run > (size_t)len) run = (size_t)len;
+		memcpy(dst, F.stage + F.stage_pos, run);
+		F.stage_pos += run; done = (int)run;
+		if (done == len) return done;
+	}
 	if (F.bgzf) {
 		while (done < len) {
 			fi_slot_t *s;
@@ -335,6 +346,191 @@ int bam_read1(bamFile fp, bam1_t *b)
 	if (fastin_read(b->data, b->data_len) != b->data_len) return -4;
 	b->l_aux = b->data_len - c->n_cigar * 4 - c->l_qname - c->l_qseq - (c->l_qseq + 1) / 2;
 	return 4 + block_len;
+}
+
+/* ------------------------------------------------------------------ a batch of records at a time
+ * read_bam_pair (bwaseqio.c:343-407, 466-496) on one thread is the slowest stage of pass 1 once the search is on the
+ * device: three reads, a malloc and a tag scan per record.  fastin_read_pairs cuts the decompressed stream into records
+ * on the calling thread (a length field and a name comparison each) and builds the bam_pair_t's on the host threads.
+ * Only the plain cases are taken this way -- a single read, or two mates with equal names and READ1/READ2 flags in either
+ * order; anything else (lone mates, odd flags, a truncated file, the --broken-input / --drop-aligned modes) goes to the
+ * reference's own read_bam_pair, which continues from the same stream position. */
+static int stage_need(size_t upto) /* 1: the staging area holds stream bytes up to `upto` */
+{
+	while (F.stage_len < upto) {
+		fi_slot_t *sl;
+		int off, run;
+		if (!F.have_slot || F.cons_off == F.slot[F.cons_seq % FI_SLOTS].len) {
+			if (fi_next_block() <= 0) return 0;
+		}
+		sl = &F.slot[F.cons_seq % FI_SLOTS];
+		off = F.cons_off; run = sl->len - off; /* what fastin_read has not taken from the block */
+		if (F.skip) { /* the BAM header, already consumed through the zlib handle */
+			const int h = (size_t)run > F.skip ? (int)F.skip : run;
+			F.skip -= (size_t)h; off += h; run -= h;
+		}
+		if (F.stage_len + (size_t)run > F.stage_cap) {
+			F.stage_cap = (F.stage_len + (size_t)run) * 2 + ((size_t)1 << 20);
+			F.stage = (uint8_t *)realloc(F.stage, F.stage_cap);
+			if (!F.stage) { fprintf(stderr, "[bwa_gpu_batch] out of memory staging the input\n"); exit(1); }
+		}
+		memcpy(F.stage + F.stage_len, sl->buf + off, (size_t)run);
+		F.stage_len += (size_t)run;
+		F.cons_off = sl->len; /* the block is used up */
+	}
+	return 1;
+}
+
+typedef struct { size_t off[2]; int kind; } fr_desc_t; /* kind 0: already built by read_bam_pair */
+typedef struct { bam_pair_t *recs; const fr_desc_t *d; const uint8_t *stage; } fr_ctx_t;
+
+/* erase_unwanted_tags (bwaseqio.c:411-464): AM NM CM SM MD X0 X1 XA XC XG XM XN XO XT YQ leave the record; like the
+ * reference, l_aux is left as it was */
+static void fr_strip_tags(bam1_t *b)
+{
+	uint8_t *end = b->data + b->data_len;
+	uint8_t *rd = b->data + b->core.n_cigar * 4 + b->core.l_qname + b->core.l_qseq + (b->core.l_qseq + 1) / 2, *wr = rd;
+	int kept = (int)(rd - b->data);
+	while (rd < end) {
+		const int a = rd[0], c = rd[1], ty = rd[2] & ~32;
+		int drop = 0, len = 3;
+		if (a == 'A' || a == 'S' || a == 'C' || a == 'N') drop = c == 'M';
+		else if (a == 'M') drop = c == 'D';
+		else if (a == 'X') drop = c == 0 || strchr("01ACGMNOT", c) != 0; /* strchr finds the terminator too */
+		else if (a == 'Y') drop = c == 'Q';
+		if (ty == 'C' || ty == 'A') len += 1;
+		else if (ty == 'S') len += 2;
+		else if (ty == 'I' || ty == 'F') len += 4;
+		else if (ty == 'D') len += 8;
+		else if (ty == 'Z' || ty == 'H') { while (rd[len]) ++len; ++len; }
+		else if (ty == 'B') {
+			const int count = (int)rd[4] | (int)rd[5] << 8 | (int)rd[6] << 16 | (int)rd[7] << 24, el = rd[3] & ~32;
+			len += 5;
+			if (el == 'C' || el == 'A') len += count;
+			else if (el == 'S') len += 2 * count;
+			else if (el == 'I' || el == 'F') len += 4 * count;
+			else if (el == 'D') len += 8 * count;
+		}
+		if (!drop) { memmove(wr, rd, (size_t)len); wr += len; kept += len; }
+		rd += len;
+	}
+	b->data_len = kept;
+}
+
+static void fr_fill(bam1_t *b, const uint8_t *rec) /* bam_read1's fields from the record at rec (its length word first) */
+{
+	bam1_core_t *c = &b->core;
+	int32_t block_len;
+	uint32_t x[8];
+	memcpy(&block_len, rec, 4); memcpy(x, rec + 4, 32);
+	c->tid = (int32_t)x[0]; c->pos = (int32_t)x[1];
+	c->bin = x[2] >> 16; c->qual = x[2] >> 8 & 0xff; c->l_qname = x[2] & 0xff;
+	c->flag = x[3] >> 16; c->n_cigar = x[3] & 0xffff;
+	c->l_qseq = (int32_t)x[4];
+	c->mtid = (int32_t)x[5]; c->mpos = (int32_t)x[6]; c->isize = (int32_t)x[7];
+	b->data_len = block_len - 32;
+	if (b->data_len > 0) {
+		b->m_data = b->data_len;
+		kroundup32(b->m_data);
+		b->data = (uint8_t *)malloc((size_t)b->m_data);
+		memcpy(b->data, rec + 36, (size_t)b->data_len);
+	}
+	b->l_aux = b->data_len - c->n_cigar * 4 - c->l_qname - c->l_qseq - (c->l_qseq + 1) / 2;
+}
+
+static void fr_build_one(size_t i, void *ctx)
+{
+	const fr_ctx_t *c = (const fr_ctx_t *)ctx;
+	const fr_desc_t *d = &c->d[i];
+	bam_pair_t *p = &c->recs[i];
+	int k;
+	if (d->kind == 0) return;
+	memset(p, 0, sizeof(*p));
+	for (k = 0; k < d->kind; ++k) fr_fill(&p->bam_rec[k], c->stage + d->off[k]);
+	p->kind = d->kind;
+	if (d->kind == 2) { /* either both mates fail QC or none (bwaseqio.c:488-491) */
+		p->bam_rec[0].core.flag |= p->bam_rec[1].core.flag & SAM_FQC;
+		p->bam_rec[1].core.flag |= p->bam_rec[0].core.flag & SAM_FQC;
+	}
+	for (k = 0; k < d->kind; ++k) fr_strip_tags(&p->bam_rec[k]);
+}
+
+/* a well-formed record starts at p: its length in *len (0 = not usable here) */
+static int fr_peek(size_t p, int32_t *len)
+{
+	int32_t bl;
+	const uint8_t *r;
+	int l_qname, n_cigar, l_qseq;
+	*len = 0;
+	if (!stage_need(p + 36)) return 0;
+	memcpy(&bl, F.stage + p, 4);
+	if (bl < 32 || !stage_need(p + 4 + (size_t)bl)) return 0;
+	r = F.stage + p + 4;
+	l_qname = r[8]; n_cigar = r[12] | r[13] << 8; memcpy(&l_qseq, r + 16, 4);
+	if (l_qname < 1 || l_qseq < 0 || (long long)l_qname + 4ll * n_cigar + l_qseq + (l_qseq + 1) / 2 > (long long)bl - 32) return 0;
+	if (r[32 + l_qname - 1] != 0) return 0; /* the name is not terminated */
+	*len = bl;
+	return 1;
+}
+
+/* up to B records of the input into recs[]; returns how many (fewer than B only at the end of the input); the number
+ * of reads among them in *seqs.  Errors are fatal, with the reference's message. */
+size_t fastin_read_pairs(bwa_seqio_t *ks, bam_pair_t *recs, size_t B, long *seqs, int broken_input, int drop_aligned)
+{
+	static fr_desc_t *desc; static size_t m_desc;
+	size_t n = 0, n_fast = 0;
+	int at_end = 0;
+	*seqs = 0;
+	if (B > m_desc) { m_desc = B; desc = (fr_desc_t *)realloc(desc, m_desc * sizeof(*desc)); }
+	if (F.stage_pos && F.stage_pos == F.stage_len) F.stage_pos = F.stage_len = 0;
+	else if (F.stage_pos) { memmove(F.stage, F.stage + F.stage_pos, F.stage_len - F.stage_pos); F.stage_len -= F.stage_pos; F.stage_pos = 0; }
+	while (n < B && !at_end) {
+		int fast = F.active && F.bgzf && !broken_input && !drop_aligned;
+		if (fast) {
+			const size_t p0 = F.stage_pos;
+			int32_t l0, l1;
+			fast = 0;
+			if (fr_peek(p0, &l0)) {
+				const uint8_t *r0 = F.stage + p0 + 4;
+				const unsigned f0 = (unsigned)(r0[14] | r0[15] << 8);
+				if (!(f0 & BAM_FPAIRED)) {
+					desc[n].kind = 1; desc[n].off[0] = p0;
+					F.stage_pos = p0 + 4 + (size_t)l0;
+					fast = 1;
+				} else if (fr_peek(p0 + 4 + (size_t)l0, &l1)) {
+					const size_t p1 = p0 + 4 + (size_t)l0;
+					const uint8_t *r1;
+					unsigned f1, m0, m1;
+					r0 = F.stage + p0 + 4; r1 = F.stage + p1 + 4; /* the staging area may have moved */
+					f1 = (unsigned)(r1[14] | r1[15] << 8);
+					m0 = f0 & (BAM_FPAIRED | BAM_FREAD1 | BAM_FREAD2); m1 = f1 & (BAM_FPAIRED | BAM_FREAD1 | BAM_FREAD2);
+					if (strcmp((const char *)r0 + 32, (const char *)r1 + 32) == 0) {
+						if (m0 == (BAM_FPAIRED | BAM_FREAD1) && m1 == (BAM_FPAIRED | BAM_FREAD2)) { desc[n].off[0] = p0; desc[n].off[1] = p1; fast = 1; }
+						else if (m1 == (BAM_FPAIRED | BAM_FREAD1) && m0 == (BAM_FPAIRED | BAM_FREAD2)) { desc[n].off[0] = p1; desc[n].off[1] = p0; fast = 1; }
+						if (fast) { desc[n].kind = 2; F.stage_pos = p1 + 4 + (size_t)l1; }
+					}
+				}
+			}
+			if (fast) { *seqs += desc[n].kind; ++n; ++n_fast; continue; }
+		}
+		{ /* the reference's reader, from wherever the stream stands */
+			const int rc = read_bam_pair(ks, &recs[n], broken_input, drop_aligned);
+			if (rc < 0) {
+				fprintf(stderr, "[sequential_loop_pass1] error reading input BAM%s\n", rc == -2 ? " (lone mate)" : "");
+				exit(1);
+			}
+			if (rc == 0) { at_end = 1; break; }
+			desc[n].kind = 0;
+			*seqs += recs[n].kind;
+			++n;
+		}
+	}
+	if (n_fast) {
+		fr_ctx_t c = {recs, desc, F.stage};
+		t_cpu_bucket = CPU_PARSE;
+		parallel_for(n, 1024, fr_build_one, &c);
+	}
+	return n;
 }
 
 /* ================================================================== the intermediate records, kept in memory
@@ -481,11 +677,42 @@ static void ob_deflate_one(size_t k, void *ctx)
 	c->clen[k] = (int)len;
 }
 
+/* the zlib writer (BWAGPU_HOST_DEFLATE=1; the A/B partner of the device codec) */
+static void deflate_on_host(BGZF *output, ob_ctx_t *c, size_t nblk)
+{
+	static uint8_t *cbuf; static size_t m_cbuf;
+	static int *clen; static size_t m_clen;
+	size_t i;
+	if (nblk * OB_OUT > m_cbuf) { m_cbuf = nblk * OB_OUT + (nblk / 4) * OB_OUT; cbuf = (uint8_t *)realloc(cbuf, m_cbuf); }
+	if (nblk > m_clen) { m_clen = nblk + nblk / 4; clen = (int *)realloc(clen, m_clen * sizeof(int)); }
+	c->cbuf = cbuf; c->clen = clen;
+	t_cpu_bucket = CPU_DEFLATE;
+	parallel_for(nblk, 4, ob_deflate_one, c);
+	if (c->failed) { fprintf(stderr, "[bwa_gpu_batch] deflate failed\n"); exit(1); }
+	{
+		const double c0 = thread_cpu_now();
+		for (i = 0; i < nblk; ++i) {
+			if (fwrite(cbuf + i * OB_OUT, 1, (size_t)clen[i], output->file) != (size_t)clen[i]) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
+			output->block_address += clen[i];
+		}
+		cpu_add(CPU_WRITE, thread_cpu_now() - c0);
+	}
+}
+
+static int host_deflate_wanted(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("BWAGPU_HOST_DEFLATE"); v = e && atoi(e) != 0; }
+	return v;
+}
+
+/* The batch's records laid out as BAM stream (host threads, straight into page-locked memory), cut into BGZF blocks and
+ * deflated on the device (bwa_gpu_bgzf_deflate: what bgzf_write + deflate_block do, bgzf.c:265-330, 533-556), written with
+ * one fwrite. */
 void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n)
 {
 	static size_t *off; static size_t m_off;
-	static uint8_t *ubuf, *cbuf; static size_t m_ubuf, m_cbuf;
-	static int *clen; static size_t m_clen;
+	static uint8_t *ubuf; static size_t m_ubuf; static int ubuf_pinned;
 	ob_ctx_t c;
 	size_t i, nblk;
 	if (n + 1 > m_off) { m_off = n + 1; off = (size_t *)realloc(off, m_off * sizeof(*off)); }
@@ -493,25 +720,32 @@ void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n)
 	for (i = 0; i < n; ++i) off[i + 1] = off[i] + rec_bytes(&recs[i]);
 	memset(&c, 0, sizeof(c));
 	c.recs = recs; c.off = off; c.total = off[n]; c.level = output->compress_level;
-	if (c.total) {
-		if (bgzf_flush(output) != 0) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); } /* what bgzf_write buffered so far (the header) */
-		nblk = (c.total + OB_IN - 1) / OB_IN;
-		if (c.total > m_ubuf) { m_ubuf = c.total + c.total / 4; ubuf = (uint8_t *)realloc(ubuf, m_ubuf); }
-		if (nblk * OB_OUT > m_cbuf) { m_cbuf = nblk * OB_OUT + (nblk / 4) * OB_OUT; cbuf = (uint8_t *)realloc(cbuf, m_cbuf); }
-		if (nblk > m_clen) { m_clen = nblk + nblk / 4; clen = (int *)realloc(clen, m_clen * sizeof(int)); }
-		c.ubuf = ubuf; c.cbuf = cbuf; c.clen = clen;
-		t_cpu_bucket = CPU_BAM_LAYOUT;
-		parallel_for(n, 2048, ob_fill_one, &c);
-		t_cpu_bucket = CPU_DEFLATE;
-		parallel_for(nblk, 4, ob_deflate_one, &c);
-		if (c.failed) { fprintf(stderr, "[bwa_gpu_batch] deflate failed\n"); exit(1); }
-		{
-			const double c0 = thread_cpu_now();
-			for (i = 0; i < nblk; ++i) {
-				if (fwrite(cbuf + i * OB_OUT, 1, (size_t)clen[i], output->file) != (size_t)clen[i]) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
-				output->block_address += clen[i];
-			}
-			cpu_add(CPU_WRITE, thread_cpu_now() - c0);
+	if (c.total == 0) return;
+	if (bgzf_flush(output) != 0) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); } /* what bgzf_write buffered so far (the header) */
+	nblk = (c.total + OB_IN - 1) / OB_IN;
+	if (c.total > m_ubuf) {
+		if (ubuf_pinned) bwa_gpu_host_free(ubuf); else free(ubuf);
+		m_ubuf = c.total + c.total / 4;
+		ubuf_pinned = !host_deflate_wanted();
+		ubuf = ubuf_pinned ? (uint8_t *)bwa_gpu_host_alloc(m_ubuf) : (uint8_t *)malloc(m_ubuf);
+		if (!ubuf) { fprintf(stderr, "[bwa_gpu_batch] output buffer of %zu bytes: %s\n", m_ubuf, ubuf_pinned ? bwa_gpu_last_error() : "out of memory"); exit(1); }
+	}
+	c.ubuf = ubuf;
+	t_cpu_bucket = CPU_BAM_LAYOUT;
+	parallel_for(n, 2048, ob_fill_one, &c);
+	if (host_deflate_wanted()) { deflate_on_host(output, &c, nblk); return; }
+	{
+		const uint8_t *packed;
+		int64_t packed_bytes;
+		double t0 = shim_now(), c0;
+		if (bwa_gpu_bgzf_deflate(ubuf, (int64_t)c.total, c.level, &packed, &packed_bytes, 0, 0, 0)) {
+			fprintf(stderr, "[bwa_gpu_batch] bwa_gpu_bgzf_deflate: %s\n", bwa_gpu_last_error());
+			exit(1);
 		}
+		shim_count_bgzf((int64_t)c.total, shim_now() - t0);
+		c0 = thread_cpu_now();
+		if (fwrite(packed, 1, (size_t)packed_bytes, output->file) != (size_t)packed_bytes) { fprintf(stderr, "[bwa_gpu_batch] BAM write failed\n"); exit(1); }
+		output->block_address += packed_bytes;
+		cpu_add(CPU_WRITE, thread_cpu_now() - c0);
 	}
 }

@@ -57,6 +57,12 @@ def lib() -> C.CDLL:
         L.bwa_gpu_index_free.argtypes = [C.POINTER(abi.bwt_t)]
         L.bwa_gpu_index_free.restype = None
         L.bwa_gpu_index_write.argtypes = [C.c_char_p, C.POINTER(abi.bwt_t), C.POINTER(abi.bwt_t)]
+        L.bwa_gpu_bgzf_deflate.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.bwa_gpu_host_alloc.argtypes = [C.c_size_t]
+        L.bwa_gpu_host_alloc.restype = C.c_void_p
+        L.bwa_gpu_host_free.argtypes = [C.c_void_p]
+        L.bwa_gpu_host_free.restype = None
         _lib = L
     return _lib
 
@@ -68,6 +74,7 @@ EXPORTS = [
     "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_get_totals", "bwa_gpu_reset_totals", "bwa_gpu_probe_random_sectors",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
     "bwa_gpu_index_build", "bwa_gpu_index_free", "bwa_gpu_index_write",
+    "bwa_gpu_bgzf_deflate", "bwa_gpu_host_alloc", "bwa_gpu_host_free",
 ]
 
 
@@ -229,6 +236,17 @@ def global_align_seqs(pairs, gap_end: int = 5, band: int = 50):
     pool = C.c_void_p()
     _ck(lib().bwa_gpu_global_align_seqs(n, arr, gap_end, band, res, C.byref(pool)))
     return _path_results(res, pool, n)
+
+
+def bgzf_deflate(data, level: int = 2):
+    """bwa_gpu_bgzf_deflate: bytes of BAM stream -> (the BGZF members back to back, member sizes, kernel ms)."""
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+    out, out_n, lens, n_mem, ms = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int32(), C.c_double()
+    _ck(lib().bwa_gpu_bgzf_deflate(buf.ctypes.data if buf.size else None, buf.size, level, C.byref(out), C.byref(out_n), C.byref(lens),
+                                   C.byref(n_mem), C.byref(ms)))
+    packed = C.string_at(out.value, out_n.value) if out_n.value else b""
+    member_len = np.ctypeslib.as_array(C.cast(lens.value, C.POINTER(C.c_int32)), shape=(n_mem.value,)).copy() if n_mem.value else np.zeros(0, np.int32)
+    return packed, member_len, ms.value
 
 
 def set_stats(enabled: bool) -> None:

@@ -17,6 +17,7 @@ HEADER = os.path.join("..", "..", "include", "bwa_gpu.h")
 UNITS = {
     "bwagpu.cu": ["kernels.cuh", "search_warp.cuh", "fmindex.cuh", "sw.cuh", "hostprep.h", HEADER],
     "indexbuild.cu": [HEADER],
+    "bgzf.cu": ["bgzf.cuh", HEADER],
 }
 SOURCES = list(UNITS)
 NVCC_FLAGS = [

@@ -1,0 +1,240 @@
+// bgzf.cu -- host side of the device BGZF codec (bgzf.cuh): the C-ABI calls, staging, packing of the members.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/bwa_gpu.h"
+#include "bgzf.cuh"
+
+namespace bwagpu {
+int hostprep_fail(const char *fmt, ...); // bwagpu.cu: records the message for bwa_gpu_last_error, returns 1
+int primary_device();                     // bwagpu.cu: the first device of bwa_gpu_init, -1 before it
+void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out); // bwagpu.cu: running totals
+}
+using bwagpu::hostprep_fail;
+
+#define BCK(call)                                                                                                 \
+	do {                                                                                                          \
+		cudaError_t e_ = (call);                                                                                  \
+		if (e_ != cudaSuccess) return hostprep_fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+namespace {
+
+__global__ void __launch_bounds__(bgzf::T, 2) k_bgzf_deflate(bgzf::Params P)
+{
+	extern __shared__ __align__(16) unsigned char bgzf_smem_raw[];
+	bgzf::Smem &s = *reinterpret_cast<bgzf::Smem *>(bgzf_smem_raw);
+	for (int k = blockIdx.x; k < P.n_blocks; k += gridDim.x) {
+		const long long off = (long long)k * bgzf::IN_MAX;
+		const int len = (int)(P.n_bytes - off < bgzf::IN_MAX ? P.n_bytes - off : bgzf::IN_MAX);
+		bgzf::deflate_block(s, P.in + off, len, P.level, P.out + (size_t)k * bgzf::OUT_STRIDE, P.clen + k,
+		                    P.tok + (size_t)blockIdx.x * 65536, P.x2n);
+	}
+}
+
+// member offsets in the packed stream: exclusive prefix of clen (one CTA; a call has at most a few thousand blocks)
+__global__ void k_bgzf_offsets(const int32_t *__restrict__ clen, int n, long long *__restrict__ off)
+{
+	__shared__ long long part[1024];
+	__shared__ long long carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n; base += 1024) {
+		const int i = base + (int)threadIdx.x;
+		const long long v = i < n ? clen[i] : 0;
+		part[threadIdx.x] = v;
+		__syncthreads();
+		for (int d = 1; d < 1024; d <<= 1) {
+			const long long o = (int)threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+			__syncthreads();
+			part[threadIdx.x] += o;
+			__syncthreads();
+		}
+		if (i < n) off[i] = carry + part[threadIdx.x] - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry += part[1023];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) off[n] = carry;
+}
+
+__global__ void k_bgzf_pack(const uint8_t *__restrict__ members, const int32_t *__restrict__ clen, const long long *__restrict__ off,
+                            uint8_t *__restrict__ packed)
+{
+	const uint8_t *src = members + (size_t)blockIdx.x * bgzf::OUT_STRIDE;
+	uint8_t *dst = packed + off[blockIdx.x];
+	const int n = clen[blockIdx.x];
+	// the destination starts at any byte: leading bytes up to a 4-byte boundary, then whole words assembled from two source words
+	const int lead = (int)((4 - ((uintptr_t)dst & 3)) & 3);
+	for (int i = threadIdx.x; i < lead && i < n; i += blockDim.x) dst[i] = src[i];
+	const int words = n > lead ? (n - lead) >> 2 : 0;
+	const uint32_t *src4 = (const uint32_t *)src;
+	uint32_t *dst4 = (uint32_t *)(dst + lead);
+	for (int w = threadIdx.x; w < words; w += blockDim.x) {
+		const int b = lead + 4 * w; // source byte offset
+		dst4[w] = __funnelshift_r(src4[b >> 2], src4[(b >> 2) + 1], (b & 3) << 3);
+	}
+	for (int i = lead + 4 * words + (int)threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+struct Codec {
+	std::mutex mu;
+	int dev = -1;
+	cudaStream_t st = nullptr;
+	uint8_t *d_in = nullptr, *d_out = nullptr, *d_packed = nullptr;
+	size_t cap_in = 0, cap_blocks = 0;
+	int32_t *d_clen = nullptr;
+	long long *d_off = nullptr;
+	uint32_t *d_tok = nullptr;
+	int grid = 0;
+	uint8_t *h_in = nullptr, *h_packed = nullptr; // pinned staging
+	size_t cap_h_in = 0, cap_h_packed = 0;
+	int32_t *h_clen = nullptr;
+	long long *h_off = nullptr;
+	size_t cap_h_blocks = 0;
+	uint32_t x2n[32];
+	void release()
+	{
+		if (dev < 0) return;
+		cudaSetDevice(dev);
+		cudaFree(d_in); cudaFree(d_out); cudaFree(d_packed); cudaFree(d_clen); cudaFree(d_off); cudaFree(d_tok);
+		cudaFreeHost(h_in); cudaFreeHost(h_packed); cudaFreeHost(h_clen); cudaFreeHost(h_off);
+		if (st) cudaStreamDestroy(st);
+		d_in = d_out = d_packed = nullptr; d_clen = nullptr; d_off = nullptr; d_tok = nullptr;
+		h_in = h_packed = nullptr; h_clen = nullptr; h_off = nullptr;
+		cap_in = cap_blocks = cap_h_in = cap_h_packed = cap_h_blocks = 0;
+		st = nullptr; dev = -1; grid = 0;
+	}
+};
+Codec g_codec;
+
+int codec_prepare(Codec &c, size_t n_bytes, size_t n_blocks, bool in_is_pinned)
+{
+	const int dev = bwagpu::primary_device();
+	if (dev < 0) return hostprep_fail("bwa_gpu_bgzf_deflate: bwa_gpu_init has not been called (no CPU fallback)");
+	if (c.dev != dev) {
+		c.release();
+		c.dev = dev;
+		BCK(cudaSetDevice(dev));
+		BCK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+		int n_sm = 0;
+		BCK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+		c.grid = 2 * n_sm;
+		BCK(cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bgzf::Smem)));
+		BCK(cudaMalloc((void **)&c.d_tok, (size_t)c.grid * 65536 * sizeof(uint32_t)));
+		bgzf::crc_x2n_table(c.x2n);
+	}
+	BCK(cudaSetDevice(dev));
+	if (n_bytes > c.cap_in) {
+		cudaFree(c.d_in); c.d_in = nullptr; c.cap_in = 0;
+		const size_t want = n_bytes + n_bytes / 4 + 65536;
+		BCK(cudaMalloc((void **)&c.d_in, want));
+		c.cap_in = want;
+	}
+	if (n_blocks > c.cap_blocks) {
+		cudaFree(c.d_out); cudaFree(c.d_packed); cudaFree(c.d_clen); cudaFree(c.d_off);
+		c.d_out = c.d_packed = nullptr; c.d_clen = nullptr; c.d_off = nullptr; c.cap_blocks = 0;
+		const size_t want = n_blocks + n_blocks / 4 + 16;
+		BCK(cudaMalloc((void **)&c.d_out, want * bgzf::OUT_STRIDE));
+		BCK(cudaMalloc((void **)&c.d_packed, want * bgzf::OUT_STRIDE + 16));
+		BCK(cudaMalloc((void **)&c.d_clen, want * sizeof(int32_t)));
+		BCK(cudaMalloc((void **)&c.d_off, (want + 1) * sizeof(long long)));
+		c.cap_blocks = want;
+	}
+	if (!in_is_pinned && n_bytes > c.cap_h_in) {
+		cudaFreeHost(c.h_in); c.h_in = nullptr; c.cap_h_in = 0;
+		const size_t want = n_bytes + n_bytes / 4 + 65536;
+		BCK(cudaMallocHost((void **)&c.h_in, want));
+		c.cap_h_in = want;
+	}
+	if (n_blocks * (size_t)bgzf::OUT_STRIDE > c.cap_h_packed) {
+		cudaFreeHost(c.h_packed); c.h_packed = nullptr; c.cap_h_packed = 0;
+		const size_t want = (n_blocks + n_blocks / 4 + 16) * (size_t)bgzf::OUT_STRIDE;
+		BCK(cudaMallocHost((void **)&c.h_packed, want));
+		c.cap_h_packed = want;
+	}
+	if (n_blocks > c.cap_h_blocks) {
+		cudaFreeHost(c.h_clen); cudaFreeHost(c.h_off); c.h_clen = nullptr; c.h_off = nullptr; c.cap_h_blocks = 0;
+		const size_t want = n_blocks + n_blocks / 4 + 16;
+		BCK(cudaMallocHost((void **)&c.h_clen, want * sizeof(int32_t)));
+		BCK(cudaMallocHost((void **)&c.h_off, (want + 1) * sizeof(long long)));
+		c.cap_h_blocks = want;
+	}
+	return 0;
+}
+
+} // namespace
+
+namespace bwagpu {
+void bgzf_release() { std::lock_guard<std::mutex> g(g_codec.mu); g_codec.release(); }
+}
+
+extern "C" void *bwa_gpu_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (bwagpu::primary_device() < 0) { hostprep_fail("bwa_gpu_host_alloc: bwa_gpu_init has not been called"); return nullptr; }
+	cudaSetDevice(bwagpu::primary_device());
+	const cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+	if (e != cudaSuccess) { hostprep_fail("bwa_gpu_host_alloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+	return p;
+}
+
+extern "C" void bwa_gpu_host_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+extern "C" int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int level, const uint8_t **out, int64_t *out_bytes,
+                                    const int32_t **member_len, int32_t *n_members, double *kernel_ms)
+{
+	if (n_bytes < 0 || !out || !out_bytes || (n_bytes > 0 && !in)) return hostprep_fail("bwa_gpu_bgzf_deflate: bad arguments");
+	Codec &c = g_codec;
+	std::lock_guard<std::mutex> g(c.mu);
+	const size_t n_blocks = ((size_t)n_bytes + bgzf::IN_MAX - 1) / bgzf::IN_MAX;
+	*out = nullptr; *out_bytes = 0;
+	if (member_len) *member_len = nullptr;
+	if (n_members) *n_members = (int32_t)n_blocks;
+	if (kernel_ms) *kernel_ms = 0;
+	if (n_blocks == 0) return 0;
+	if (n_blocks > 0x7fffffffu / bgzf::OUT_STRIDE * 64) return hostprep_fail("bwa_gpu_bgzf_deflate: %lld bytes in one call", (long long)n_bytes);
+	cudaPointerAttributes attr;
+	bool pinned = cudaPointerGetAttributes(&attr, in) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	if (codec_prepare(c, (size_t)n_bytes, n_blocks, pinned)) return 1;
+	const uint8_t *src = in;
+	if (!pinned) { memcpy(c.h_in, in, (size_t)n_bytes); src = c.h_in; }
+	cudaEvent_t e0, e1;
+	BCK(cudaEventCreate(&e0)); BCK(cudaEventCreate(&e1));
+	BCK(cudaMemcpyAsync(c.d_in, src, (size_t)n_bytes, cudaMemcpyHostToDevice, c.st));
+	bgzf::Params P;
+	P.in = c.d_in; P.n_bytes = n_bytes; P.n_blocks = (int)n_blocks; P.level = level;
+	P.out = c.d_out; P.clen = c.d_clen; P.tok = c.d_tok;
+	memcpy(P.x2n, c.x2n, sizeof(P.x2n));
+	const int grid = (int)(n_blocks < (size_t)c.grid ? n_blocks : (size_t)c.grid);
+	BCK(cudaEventRecord(e0, c.st));
+	k_bgzf_deflate<<<grid, bgzf::T, sizeof(bgzf::Smem), c.st>>>(P);
+	k_bgzf_offsets<<<1, 1024, 0, c.st>>>(c.d_clen, (int)n_blocks, c.d_off);
+	k_bgzf_pack<<<(unsigned)n_blocks, 256, 0, c.st>>>(c.d_out, c.d_clen, c.d_off, c.d_packed);
+	BCK(cudaEventRecord(e1, c.st));
+	BCK(cudaGetLastError());
+	BCK(cudaMemcpyAsync(c.h_clen, c.d_clen, n_blocks * sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+	BCK(cudaMemcpyAsync(c.h_off, c.d_off, (n_blocks + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c.st));
+	BCK(cudaStreamSynchronize(c.st));
+	const long long total = c.h_off[n_blocks];
+	BCK(cudaMemcpyAsync(c.h_packed, c.d_packed, (size_t)total, cudaMemcpyDeviceToHost, c.st));
+	BCK(cudaStreamSynchronize(c.st));
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (kernel_ms) *kernel_ms = ms;
+		bwagpu::count_bgzf(3, ms, n_bytes, total);
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	*out = c.h_packed; *out_bytes = total;
+	if (member_len) *member_len = c.h_clen;
+	return 0;
+}

@@ -1,0 +1,523 @@
+// bgzf.cuh -- BGZF (blocked gzip) deflate on the device: the BAM output side of bam2bam.
+//
+// Replaces the compute of bgzf.c:265-330 (deflate_block: one zlib deflate per <= 64 KB of BAM stream, level 2 as
+// bam2bam.c:2061 opens its output "w2") -- the largest single item of host CPU time in a bam2bam run once the
+// alignment itself is on the GPU.  The decompressed stream, which is what every BAM reader sees, is byte-identical to the
+// reference's; the compressed bytes are this codec's own (deflate does not prescribe them).
+//
+// One CTA of 256 threads per BGZF block, everything in shared memory:
+//   0. the block's input (<= 65280 bytes) is loaded once; CRC-32 by 256 partial CRCs combined with x^(8 L 2^k) mod P;
+//   1. LZ77, greedy (the reference's level 2 is zlib's deflate_fast): positions are taken 256 at a time --
+//      A  warp 0 walks the 256 positions in order, 32 per step, through a 16 K-entry hash-head table of 4-byte strings:
+//         candidate = the most recent earlier position with the same hash (__match_any_sync finds it inside the step),
+//      B  every thread extends its candidate (4 bytes per compare) -> match length / distance of its position,
+//      C  the greedy parse -- "emit a token at p, continue at p + max(1, len)" -- is a pointer chain; the positions on
+//         the chain from the carried-in start are found by pointer doubling (8 rounds for 256 positions),
+//      D  the marked positions become tokens (literal | length, distance) in position order (ballot + scan), counted into
+//         the literal/length and distance histograms;
+//   2. length-limited canonical Huffman codes for both alphabets and for the code-length alphabet (rank sort in parallel,
+//      two-queue merge on one thread, zlib's overflow repair for the 15 / 7 bit limits), dynamic-block header with
+//      run-length coded code lengths; a stored block when that is smaller (incompressible input always fits 64 KB);
+//   3. every token's bits are placed at their prefix-summed bit offset with shared-memory atomicOr;
+//   4. the finished member (18-byte BGZF header, deflate stream, CRC-32, ISIZE) leaves shared memory in one aligned copy.
+// All of it is deterministic: the same input gives the same bytes on every run.
+#pragma once
+#include <stdint.h>
+
+namespace bgzf {
+
+constexpr int T = 256;             // threads per CTA
+constexpr int IN_MAX = 65280;      // input bytes per BGZF block (a stored block of this size still fits 64 KB)
+constexpr int OUT_STRIDE = 65536;  // a finished member is at most this long (BSIZE is 16 bits)
+constexpr int HBITS = 14;
+constexpr int MIN_MATCH = 4, MAX_MATCH = 258, MAX_DIST = 32768;
+constexpr int NLIT = 286, NDIST = 30, NCL = 19;
+constexpr uint32_t NONE = 0xffffu;
+constexpr uint32_t CRC_POLY = 0xedb88320u;
+
+struct Smem {
+	uint32_t buf[OUT_STRIDE / 4 + 4]; // the input bytes, later the output member
+	uint16_t head[1 << HBITS];
+	uint32_t lit_freq[288], dist_freq[32], cl_freq[20];
+	uint16_t lit_code[288], dist_code[32], cl_code[20];
+	uint8_t lit_len[288], dist_len[32], cl_len[20];
+	uint16_t cand[T], jump[2][T + 2];
+	uint8_t mark[T + 4];
+	uint32_t wsum[8];
+	// Huffman construction
+	uint16_t sorted[288], parent[576];
+	uint32_t weight[576];
+	uint8_t depth[288];
+	uint32_t bl_count[16], next_code[16];
+	int n_used;
+	// dynamic header
+	uint8_t cl_sym[320], cl_ext[320];
+	int n_cl, hlit, hdist;
+	// CRC
+	uint32_t crc_tab[256], crc_part[T], crc_pow[8];
+	// block state
+	int cur;
+	uint32_t bitpos;
+	int stored;
+};
+
+struct Params {
+	const uint8_t *in;   // the whole input stream
+	long long n_bytes;
+	int n_blocks;        // ceil(n_bytes / IN_MAX)
+	int level;           // 0: stored blocks only
+	uint8_t *out;        // n_blocks x OUT_STRIDE
+	int32_t *clen;       // member size per block
+	uint32_t *tok;       // gridDim.x x 65536 token words
+	uint32_t x2n[32];    // x^(2^k) mod P, k = 0..31 (reflected), for the CRC combination
+};
+
+// ---------------------------------------------------------------- CRC-32 (the gzip one), combination as zlib's multmodp
+__host__ __device__ inline uint32_t crc_mulmod(uint32_t a, uint32_t b)
+{
+	uint32_t m = 1u << 31, p = 0;
+	for (;;) {
+		if (a & m) {
+			p ^= b;
+			if ((a & (m - 1)) == 0) break;
+		}
+		m >>= 1;
+		b = (b & 1) ? (b >> 1) ^ CRC_POLY : b >> 1;
+	}
+	return p;
+}
+
+// x^(n * 2^k) mod P
+__host__ __device__ inline uint32_t crc_x2n(const uint32_t *x2n, uint32_t n, unsigned k)
+{
+	uint32_t p = 1u << 31;
+	while (n) {
+		if (n & 1) p = crc_mulmod(x2n[k & 31], p);
+		n >>= 1;
+		++k;
+	}
+	return p;
+}
+
+inline void crc_x2n_table(uint32_t *x2n)
+{
+	uint32_t p = 1u << 30; // x^1
+	x2n[0] = p;
+	for (int n = 1; n < 32; ++n) x2n[n] = p = crc_mulmod(p, p);
+}
+
+// ---------------------------------------------------------------- deflate's symbol maps (RFC 1951 3.2.5), closed form
+__device__ __forceinline__ void len_symbol(int len, int &sym, int &ebits, int &eval)
+{
+	const int x = len - 3;
+	if (len == 258) { sym = 285; ebits = 0; eval = 0; }
+	else if (x < 8) { sym = 257 + x; ebits = 0; eval = 0; }
+	else {
+		const int e = 29 - __clz(x); // floor(log2 x) - 2
+		sym = 261 + 4 * e + ((x >> e) & 3);
+		ebits = e; eval = x & ((1 << e) - 1);
+	}
+}
+
+__device__ __forceinline__ void dist_symbol(int dist, int &sym, int &ebits, int &eval)
+{
+	const int y = dist - 1;
+	if (y < 4) { sym = y; ebits = 0; eval = 0; }
+	else {
+		const int e = 30 - __clz(y); // floor(log2 y) - 1
+		sym = 2 * (e + 1) + ((y >> e) & 1);
+		ebits = e; eval = y & ((1 << e) - 1);
+	}
+}
+
+__device__ __forceinline__ int len_extra_bits(int sym) { return sym < 265 || sym == 285 ? 0 : (sym - 261) >> 2; }
+__device__ __forceinline__ int dist_extra_bits(int sym) { return sym < 4 ? 0 : (sym >> 1) - 1; }
+
+__device__ __forceinline__ uint32_t ld4(const uint32_t *w, int i) // the 4 bytes at byte offset i
+{
+	return __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], (i & 3) << 3);
+}
+
+__device__ __forceinline__ void put_bits(uint32_t *w, uint32_t bitpos, unsigned long long v, int n)
+{
+	if (n == 0) return;
+	const unsigned sh = bitpos & 31;
+	uint32_t *q = w + (bitpos >> 5);
+	const uint32_t w0 = (uint32_t)(v << sh);
+	const unsigned long long rest = sh ? v >> (32 - sh) : v >> 32;
+	if (w0) atomicOr(q, w0);
+	if ((uint32_t)rest) atomicOr(q + 1, (uint32_t)rest);
+	if ((uint32_t)(rest >> 32)) atomicOr(q + 2, (uint32_t)(rest >> 32));
+}
+
+// ---------------------------------------------------------------- length-limited canonical Huffman code (all threads)
+// freq[0..n) -> len[0..n) (0 = unused) and the bit-reversed codes; at least two symbols get a code (zlib's build_tree does
+// the same: a decoder wants a complete code).
+__device__ void build_code(Smem &s, uint32_t *freq, int n, int maxbits, uint8_t *len, uint16_t *code)
+{
+	const int t = threadIdx.x;
+	if (t == 0) {
+		int nz = 0;
+		for (int i = 0; i < n; ++i) nz += freq[i] != 0;
+		for (int i = 0; nz < 2 && i < n; ++i)
+			if (!freq[i]) { freq[i] = 1; ++nz; }
+		s.n_used = nz;
+	}
+	__syncthreads();
+	for (int i = t; i < n; i += T) { // rank sort by (frequency, symbol)
+		const uint32_t f = freq[i];
+		len[i] = 0;
+		if (f) {
+			int r = 0;
+			for (int j = 0; j < n; ++j) {
+				const uint32_t g = freq[j];
+				r += (g != 0) && (g < f || (g == f && j < i));
+			}
+			s.sorted[r] = (uint16_t)i;
+			s.weight[r] = f;
+		}
+	}
+	__syncthreads();
+	const int m = s.n_used, root = 2 * m - 2;
+	if (t == 0) { // leaves 0..m-1 in rising weight, internal nodes m..2m-2 in the order they are made (rising weight too)
+		int lq = 0, iq = m, in = m;
+		for (int k = 0; k < m - 1; ++k) {
+			int a, b;
+			if (lq < m && (iq >= in || s.weight[lq] <= s.weight[iq])) a = lq++; else a = iq++;
+			if (lq < m && (iq >= in || s.weight[lq] <= s.weight[iq])) b = lq++; else b = iq++;
+			s.weight[in] = s.weight[a] + s.weight[b];
+			s.parent[a] = (uint16_t)in; s.parent[b] = (uint16_t)in;
+			++in;
+		}
+	}
+	__syncthreads();
+	for (int i = t; i < m; i += T) {
+		int d = 0, id = i;
+		while (id != root) { id = s.parent[id]; ++d; }
+		s.depth[i] = (uint8_t)(d > maxbits ? maxbits : d);
+	}
+	__syncthreads();
+	if (t == 0) {
+		unsigned long long kraft = 0;
+		for (int b = 0; b <= maxbits; ++b) s.bl_count[b] = 0;
+		for (int i = 0; i < m; ++i) { ++s.bl_count[s.depth[i]]; kraft += 1ull << (maxbits - s.depth[i]); }
+		// every leaf clamped to maxbits takes one slot too many: zlib's repair (trees.c gen_bitlen) -- split the deepest
+		// leaf above the limit, hang one of the surplus leaves next to it
+		for (long long excess = (long long)(kraft - (1ull << maxbits)); excess > 0; --excess) {
+			int bits = maxbits - 1;
+			while (s.bl_count[bits] == 0) --bits;
+			--s.bl_count[bits]; s.bl_count[bits + 1] += 2; --s.bl_count[maxbits];
+		}
+		int i = 0;
+		for (int bits = maxbits; bits >= 1; --bits) // rarest symbols get the longest codes
+			for (uint32_t c = s.bl_count[bits]; c; --c) len[s.sorted[i++]] = (uint8_t)bits;
+		uint32_t c = 0;
+		s.bl_count[0] = 0;
+		for (int bits = 1; bits <= maxbits; ++bits) { c = (c + s.bl_count[bits - 1]) << 1; s.next_code[bits] = c; }
+	}
+	__syncthreads();
+	for (int i = t; i < n; i += T) {
+		const int l = len[i];
+		uint32_t c = 0;
+		if (l) {
+			int r = 0;
+			for (int j = 0; j < i; ++j) r += len[j] == l;
+			c = __brev(s.next_code[l] + r) >> (32 - l);
+		}
+		code[i] = (uint16_t)c;
+	}
+	__syncthreads();
+}
+
+// exclusive prefix of v over the block (by thread index) and the block total; one barrier, s.wsum is free again after the
+// caller's next barrier
+__device__ __forceinline__ uint32_t block_scan(Smem &s, uint32_t v, uint32_t &total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) inc += o;
+	}
+	if (lane == 31) s.wsum[warp] = inc;
+	__syncthreads();
+	uint32_t before = 0, all = 0;
+#pragma unroll
+	for (int w = 0; w < T / 32; ++w) {
+		const uint32_t x = s.wsum[w];
+		if (w < warp) before += x;
+		all += x;
+	}
+	total = all;
+	return before + inc - v;
+}
+
+// ---------------------------------------------------------------- one BGZF block
+__device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, int level, uint8_t *__restrict__ out, int32_t *clen,
+                              uint32_t *__restrict__ tok, const uint32_t *x2n)
+{
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	uint8_t *bytes = (uint8_t *)s.buf;
+
+	// ---- 0. load, clear, CRC
+	__syncthreads(); // the previous block's copy-out is done
+	for (int i = t; i < OUT_STRIDE / 4 + 4; i += T) s.buf[i] = 0;
+	for (int i = t; i < (1 << HBITS); i += T) s.head[i] = (uint16_t)NONE;
+	for (int i = t; i < 288; i += T) s.lit_freq[i] = 0;
+	if (t < 32) s.dist_freq[t] = 0;
+	if (t < 20) s.cl_freq[t] = 0;
+	{
+		uint32_t c = (uint32_t)t;
+		for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1;
+		s.crc_tab[t] = c;
+	}
+	if (t == 0) { s.cur = 0; s.stored = 0; }
+	__syncthreads();
+	if ((((uintptr_t)in) & 3) == 0) {
+		const uint32_t *in4 = (const uint32_t *)in;
+		for (int i = t; i < (len >> 2); i += T) s.buf[i] = in4[i];
+		for (int i = (len & ~3) + t; i < len; i += T) bytes[i] = in[i];
+	} else {
+		for (int i = t; i < len; i += T) bytes[i] = in[i];
+	}
+	__syncthreads();
+	uint32_t crc;
+	{
+		// the message with its first four bytes inverted, zero-padded IN FRONT to 256 L bytes, remainder of division by P
+		// (leading zeros do not change it); thread t takes the t-th run of L bytes
+		const int L = (len + T - 1) / T, pad = L * T - len;
+		uint32_t c = 0;
+		int lo = t * L - pad, hi = lo + L;
+		if (lo < 0) lo = 0;
+		for (int i = lo; i < hi; ++i) {
+			uint32_t b = bytes[i];
+			if (i < 4) b ^= 0xffu;
+			c = s.crc_tab[(c ^ b) & 0xff] ^ (c >> 8);
+		}
+		s.crc_part[t] = c;
+		if (t == 0) {
+			uint32_t p = crc_x2n(x2n, (uint32_t)L, 3); // x^(8 L)
+			for (int k = 0; k < 8; ++k) { s.crc_pow[k] = p; p = crc_mulmod(p, p); }
+		}
+		__syncthreads();
+		for (int k = 0; k < 8; ++k) {
+			const int span = 1 << k;
+			if ((t & (2 * span - 1)) == 0) s.crc_part[t] = crc_mulmod(s.crc_pow[k], s.crc_part[t]) ^ s.crc_part[t + span];
+			__syncthreads();
+		}
+		crc = ~s.crc_part[0];
+		if (len < 4) { // too short for the inverted-prefix form: plainly
+			uint32_t c2 = 0xffffffffu;
+			for (int i = 0; i < len; ++i) c2 = s.crc_tab[(c2 ^ bytes[i]) & 0xff] ^ (c2 >> 8);
+			crc = ~c2;
+		}
+	}
+
+	// ---- 1. LZ77
+	uint32_t ntok = 0;
+	int cur = 0;
+	if (level > 0)
+		for (int base = 0; base < len; base += T) {
+			if (warp == 0) { // A
+				for (int sub = 0; sub < T / 32; ++sub) {
+					const int p = base + sub * 32 + lane;
+					const bool valid = p + MIN_MATCH <= len;
+					uint32_t h = 0x10000u + lane, c = NONE;
+					if (valid) {
+						h = (ld4(s.buf, p) * 2654435761u) >> (32 - HBITS);
+						c = s.head[h];
+					}
+					const unsigned same = __match_any_sync(0xffffffffu, h);
+					const unsigned lower = same & ((1u << lane) - 1);
+					if (valid && lower) c = (uint32_t)(p - lane + (31 - __clz(lower)));
+					if (valid && (same >> lane) == 1u) s.head[h] = (uint16_t)p; // the last position of the step with this hash
+					s.cand[sub * 32 + lane] = (uint16_t)c;
+					__syncwarp();
+				}
+			}
+			__syncthreads();
+			// B
+			const int p = base + t;
+			const int c = s.cand[t];
+			int ml = 0;
+			if (c != (int)NONE && p - c <= MAX_DIST) {
+				const int maxlen = len - p < MAX_MATCH ? len - p : MAX_MATCH;
+				bool open = true;
+				while (open && ml + 4 <= maxlen) {
+					const uint32_t x = ld4(s.buf, p + ml) ^ ld4(s.buf, c + ml);
+					if (x) { ml += (__ffs((int)x) - 1) >> 3; open = false; }
+					else ml += 4;
+				}
+				while (open && ml < maxlen && bytes[p + ml] == bytes[c + ml]) ++ml;
+				if (ml < MIN_MATCH) ml = 0;
+			}
+			const int step = ml ? ml : 1;
+			s.jump[0][t] = (uint16_t)(t + step < T ? t + step : T);
+			s.mark[t] = (uint8_t)(p == cur);
+			if (t == 0) { s.jump[0][T] = T; s.jump[1][T] = T; s.mark[T] = 0; }
+			__syncthreads();
+			// C: after round r the first 2^(r+1) positions of the chain are marked, jump = 2^(r+1) steps along it
+#pragma unroll 1
+			for (int r = 0; r < 8; ++r) {
+				const int j = s.jump[r & 1][t];
+				if (s.mark[t]) s.mark[j] = 1;
+				s.jump[(r + 1) & 1][t] = s.jump[r & 1][j];
+				__syncthreads();
+			}
+			// D
+			const bool is_tok = s.mark[t] != 0 && p < len;
+			if (is_tok && t + step >= T) s.cur = p + step;
+			uint32_t total;
+			const uint32_t at = ntok + block_scan(s, is_tok ? 1u : 0u, total);
+			ntok += total;
+			cur = s.cur;
+			if (is_tok) {
+				if (ml) {
+					int sym, eb, ev;
+					tok[at] = 0x80000000u | (uint32_t)(ml - 3) << 16 | (uint32_t)(p - c - 1);
+					len_symbol(ml, sym, eb, ev);
+					atomicAdd(&s.lit_freq[sym], 1u);
+					dist_symbol(p - c, sym, eb, ev);
+					atomicAdd(&s.dist_freq[sym], 1u);
+				} else {
+					const uint32_t b = bytes[p];
+					tok[at] = b;
+					atomicAdd(&s.lit_freq[b], 1u);
+				}
+			}
+		}
+	if (t == 0) s.lit_freq[256] = 1;
+	__syncthreads();
+
+	// ---- 2. codes, header
+	if (level > 0) {
+		build_code(s, s.lit_freq, NLIT, 15, s.lit_len, s.lit_code);
+		build_code(s, s.dist_freq, NDIST, 15, s.dist_len, s.dist_code);
+		if (t == 0) { // the code lengths, run-length coded (RFC 1951 3.2.7)
+			int hlit = NLIT, hdist = NDIST, n = 0;
+			while (hlit > 257 && s.lit_len[hlit - 1] == 0) --hlit;
+			while (hdist > 1 && s.dist_len[hdist - 1] == 0) --hdist;
+			s.hlit = hlit; s.hdist = hdist;
+			const int tot = hlit + hdist;
+			int i = 0;
+			while (i < tot) {
+				const int v = i < hlit ? s.lit_len[i] : s.dist_len[i - hlit];
+				int run = 1;
+				while (i + run < tot && (i + run < hlit ? s.lit_len[i + run] : s.dist_len[i + run - hlit]) == v) ++run;
+				i += run;
+				if (v == 0) {
+					while (run >= 11) { const int r = run < 138 ? run : 138; s.cl_sym[n] = 18; s.cl_ext[n++] = (uint8_t)(r - 11); run -= r; }
+					if (run >= 3) { s.cl_sym[n] = 17; s.cl_ext[n++] = (uint8_t)(run - 3); run = 0; }
+					while (run-- > 0) { s.cl_sym[n] = 0; s.cl_ext[n++] = 0; }
+				} else {
+					s.cl_sym[n] = (uint8_t)v; s.cl_ext[n++] = 0; --run;
+					while (run >= 3) { const int r = run < 6 ? run : 6; s.cl_sym[n] = 16; s.cl_ext[n++] = (uint8_t)(r - 3); run -= r; }
+					while (run-- > 0) { s.cl_sym[n] = (uint8_t)v; s.cl_ext[n++] = 0; }
+				}
+			}
+			s.n_cl = n;
+			for (int k = 0; k < n; ++k) ++s.cl_freq[s.cl_sym[k]];
+		}
+		__syncthreads();
+		build_code(s, s.cl_freq, NCL, 7, s.cl_len, s.cl_code);
+	}
+	for (int i = t; i < OUT_STRIDE / 4 + 4; i += T) s.buf[i] = 0; // the input is no longer needed: the member is assembled here
+	__syncthreads();
+	if (t == 0) {
+		const uint8_t order[NCL] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+		uint32_t bp = 18 * 8;
+		int stored = level <= 0;
+		if (!stored) {
+			int hclen = NCL;
+			while (hclen > 4 && s.cl_len[order[hclen - 1]] == 0) --hclen;
+			unsigned long long bits = 3 + 5 + 5 + 4 + 3 * (unsigned long long)hclen;
+			for (int k = 0; k < s.n_cl; ++k) bits += s.cl_len[s.cl_sym[k]] + (s.cl_sym[k] == 16 ? 2 : s.cl_sym[k] == 17 ? 3 : s.cl_sym[k] == 18 ? 7 : 0);
+			for (int i = 0; i < NLIT; ++i) bits += (unsigned long long)s.lit_freq[i] * (s.lit_len[i] + (i > 256 ? len_extra_bits(i) : 0));
+			for (int i = 0; i < NDIST; ++i) bits += (unsigned long long)s.dist_freq[i] * (s.dist_len[i] + dist_extra_bits(i));
+			if ((bits + 7) / 8 >= (unsigned long long)len + 5) stored = 1;
+			else {
+				put_bits(s.buf, bp, 1 | 2 << 1, 3); bp += 3;
+				put_bits(s.buf, bp, (unsigned)(s.hlit - 257), 5); bp += 5;
+				put_bits(s.buf, bp, (unsigned)(s.hdist - 1), 5); bp += 5;
+				put_bits(s.buf, bp, (unsigned)(hclen - 4), 4); bp += 4;
+				for (int k = 0; k < hclen; ++k) { put_bits(s.buf, bp, s.cl_len[order[k]], 3); bp += 3; }
+				for (int k = 0; k < s.n_cl; ++k) {
+					const int sym = s.cl_sym[k];
+					put_bits(s.buf, bp, s.cl_code[sym], s.cl_len[sym]); bp += s.cl_len[sym];
+					const int eb = sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0;
+					put_bits(s.buf, bp, s.cl_ext[k], eb); bp += eb;
+				}
+			}
+		}
+		s.stored = stored;
+		s.bitpos = bp;
+	}
+	__syncthreads();
+
+	// ---- 3. the stream
+	uint32_t payload; // bytes of deflate stream
+	if (s.stored) {
+		if (t == 0) {
+			bytes[18] = 1; // BFINAL = 1, BTYPE = 00, padding
+			bytes[19] = (uint8_t)(len & 0xff); bytes[20] = (uint8_t)(len >> 8);
+			bytes[21] = (uint8_t)(~len & 0xff); bytes[22] = (uint8_t)((~len >> 8) & 0xff);
+		}
+		for (int i = t; i < len; i += T) bytes[23 + i] = in[i];
+		payload = (uint32_t)len + 5;
+	} else {
+		uint32_t bp = s.bitpos;
+		for (uint32_t k0 = 0; k0 < ntok; k0 += 4 * T) {
+			unsigned long long v[4];
+			int nb[4];
+			uint32_t mine = 0;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t k = k0 + 4 * t + q;
+				v[q] = 0; nb[q] = 0;
+				if (k < ntok) {
+					const uint32_t w = tok[k];
+					if (w & 0x80000000u) {
+						int sym, eb, ev, n;
+						len_symbol((int)((w >> 16) & 0xff) + 3, sym, eb, ev);
+						v[q] = s.lit_code[sym]; n = s.lit_len[sym];
+						v[q] |= (unsigned long long)ev << n; n += eb;
+						dist_symbol((int)(w & 0x7fff) + 1, sym, eb, ev);
+						v[q] |= (unsigned long long)s.dist_code[sym] << n; n += s.dist_len[sym];
+						v[q] |= (unsigned long long)ev << n; n += eb;
+						nb[q] = n;
+					} else {
+						v[q] = s.lit_code[w]; nb[q] = s.lit_len[w];
+					}
+				}
+				mine += (uint32_t)nb[q];
+			}
+			uint32_t total;
+			uint32_t at = bp + block_scan(s, mine, total);
+			bp += total;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) { put_bits(s.buf, at, v[q], nb[q]); at += (uint32_t)nb[q]; }
+			__syncthreads(); // s.wsum is reused by the next round
+		}
+		if (t == 0) put_bits(s.buf, bp, s.lit_code[256], s.lit_len[256]);
+		bp += s.lit_len[256];
+		payload = (bp - 18 * 8 + 7) >> 3;
+	}
+	__syncthreads();
+
+	// ---- 4. member header / trailer (bgzf.c:274-291, 318-326), copy-out
+	const uint32_t total = 18 + payload + 8;
+	if (t == 0) {
+		const uint8_t hdr[16] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0};
+		for (int i = 0; i < 16; ++i) bytes[i] = hdr[i];
+		bytes[16] = (uint8_t)((total - 1) & 0xff); bytes[17] = (uint8_t)((total - 1) >> 8);
+		uint8_t *q = bytes + 18 + payload;
+		for (int i = 0; i < 4; ++i) { q[i] = (uint8_t)(crc >> (8 * i)); q[4 + i] = (uint8_t)((uint32_t)len >> (8 * i)); }
+		*clen = (int32_t)total;
+	}
+	__syncthreads();
+	uint32_t *out4 = (uint32_t *)out;
+	for (uint32_t i = t; i < (total + 3) / 4; i += T) out4[i] = s.buf[i];
+}
+
+} // namespace bgzf

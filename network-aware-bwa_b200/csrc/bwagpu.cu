@@ -191,9 +191,20 @@ static uint32_t env_u32(const char *name, uint32_t dflt)
 	return e && atoll(e) > 0 ? (uint32_t)atoll(e) : dflt;
 }
 
+namespace bwagpu {
+void bgzf_release(); // bgzf.cu
+int primary_device() { std::lock_guard<std::mutex> g(g_mu); return g_ctx.empty() ? -1 : g_ctx[0]->dev; }
+void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out)
+{
+	TOT(g_tot.launches += launches; g_tot.ms_bgzf += ms; g_tot.bgzf_bytes_in += bytes_in; g_tot.bgzf_bytes_out += bytes_out;
+	    g_tot.h2d_bytes += bytes_in; g_tot.d2h_bytes += bytes_out);
+}
+}
+
 // ------------------------------------------------------------------ lifetime
 extern "C" void bwa_gpu_destroy(void)
 {
+	bwagpu::bgzf_release();
 	std::lock_guard<std::mutex> g(g_mu);
 	for (Ctx *c : g_ctx) {
 		cudaSetDevice(c->dev);
@@ -227,10 +238,10 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 	{
 		// The struct API hands every read a libc-allocated aln[] (the caller free()s it, bwaseqio.c:259): 10 M small blocks per call.
 		// With glibc's defaults the heaps are trimmed when the caller frees them and grown again 128 KB at a time on the next
-		// call (page faults + mprotect on the unpack threads).  Keep freed memory and grow in larger steps; BWAGPU_MALLOPT=0 leaves
-		// the allocator alone.
+		// call (page faults + mprotect on the unpack threads).  BWAGPU_MALLOPT=1 keeps freed memory and grows in larger steps: a
+		// process-wide setting, hence the HOST's choice (integration/bwa_gpu_batch.c and bench.py opt in); off by default.
 		const char *e = getenv("BWAGPU_MALLOPT");
-		if (!e || atoi(e) != 0) {
+		if (e && atoi(e) != 0) {
 			mallopt(M_TRIM_THRESHOLD, 1 << 30);
 			mallopt(M_TOP_PAD, 64 << 20);
 		}
@@ -794,6 +805,7 @@ struct FlatJob {
 
 // Host-side helper threads of one lane: packing reads and handing results back are embarrassingly
 // parallel over reads once the per-read offsets are known.
+static const int MAX_HOST_THREADS = 64;
 static int host_threads()
 {
 	static int n = 0;
@@ -801,6 +813,7 @@ static int host_threads()
 		const unsigned hw = std::thread::hardware_concurrency();
 		const uint32_t lanes = env_u32("BWAGPU_LANES", 3);
 		n = (int)env_u32("BWAGPU_HOST_THREADS", std::max(1u, std::min(8u, (hw ? hw : 8u) / std::max(1u, lanes))));
+		if (n > MAX_HOST_THREADS) n = MAX_HOST_THREADS; // the per-thread scratch of run_range is sized by it
 	}
 	return n;
 }

@@ -104,3 +104,39 @@ int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, 
 	*cigar_pool = g_pool;
 	return 0;
 }
+
+/* the BGZF codec: zlib, one member per 65280 bytes (what bgzf.c's deflate_block does per block) */
+#include <zlib.h>
+void *bwa_gpu_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void bwa_gpu_host_free(void *p) { free(p); }
+int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int level, const uint8_t **out, int64_t *out_bytes,
+                         const int32_t **member_len, int32_t *n_members, double *kernel_ms)
+{
+	static uint8_t *buf; static int32_t *lens; static size_t m_blk;
+	static const uint8_t hdr[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 0, 0};
+	const size_t nblk = ((size_t)n_bytes + 65279) / 65280;
+	size_t k, at = 0;
+	if (nblk > m_blk) { m_blk = nblk + 16; buf = (uint8_t *)realloc(buf, m_blk * 65536); lens = (int32_t *)realloc(lens, m_blk * sizeof(int32_t)); }
+	for (k = 0; k < nblk; ++k) {
+		const uint8_t *src = in + k * 65280;
+		const uint32_t len = (uint32_t)((size_t)n_bytes - k * 65280 < 65280 ? (size_t)n_bytes - k * 65280 : 65280);
+		uint8_t *dst = buf + at;
+		z_stream zs;
+		uint32_t crc, total;
+		memcpy(dst, hdr, 18);
+		memset(&zs, 0, sizeof(zs));
+		zs.next_in = (Bytef *)src; zs.avail_in = len; zs.next_out = dst + 18; zs.avail_out = 65536 - 26;
+		if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK || deflate(&zs, Z_FINISH) != Z_STREAM_END) return 1;
+		deflateEnd(&zs);
+		total = (uint32_t)zs.total_out + 26;
+		dst[16] = (uint8_t)((total - 1) & 0xff); dst[17] = (uint8_t)((total - 1) >> 8);
+		crc = (uint32_t)crc32(crc32(0L, 0, 0), src, len);
+		memcpy(dst + 18 + zs.total_out, &crc, 4); memcpy(dst + 22 + zs.total_out, &len, 4);
+		lens[k] = (int32_t)total; at += total;
+	}
+	*out = buf; *out_bytes = (int64_t)at;
+	if (member_len) *member_len = lens;
+	if (n_members) *n_members = (int32_t)nblk;
+	if (kernel_ms) *kernel_ms = 0;
+	return 0;
+}

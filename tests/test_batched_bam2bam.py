@@ -28,7 +28,7 @@ def build_stub():
     src = os.path.join(ROOT, "tests", "cpu_stub", "bwagpu_cpu_stub.c")
     if os.path.exists("/root/reference/bwtaln.h") and (not os.path.exists(STUB) or os.path.getmtime(STUB) < os.path.getmtime(src)):
         subprocess.run(["gcc", "-O2", "-w", "-fgnu89-inline", "-fPIC", "-shared", "-I", "/root/reference", "-I",
-                        os.path.join(ROOT, "include"), "-o", STUB, src], check=True)
+                        os.path.join(ROOT, "include"), "-o", STUB, src, "-lz"], check=True)
     return os.path.exists(STUB)
 
 

@@ -110,6 +110,65 @@ def test_inprocess_repeated_runs_on_the_stub(work):
     assert load[1] < 0.5 * max(load[0], 1e-3) + 0.01 and load[2] < 0.5 * max(load[0], 1e-3) + 0.01
 
 
+def test_batch_reader_mixed_input_on_the_stub(work):
+    """The shim's batch reader (integration/shim_io.c fastin_read_pairs, in place of one read_bam_pair per record): single
+    reads, mates in both orders, alignment tags that must leave the record (erase_unwanted_tags, bwaseqio.c:411-464) next to
+    tags that stay (RG, a B array), and BGZF blocks so small that records straddle them -- the BAM must equal the plain
+    reference's."""
+    import struct
+    if not os.path.exists(INPROC):
+        pytest.skip("inproc_host not built")
+    d, fa, _, _ = work
+    rng = np.random.default_rng(17)
+    genome = R.bwa.simulate.make_genome(300000, seed=21, repeat_frac=0.05)
+
+    def rec(name, seq, flag, tags):
+        l = int(seq.size)
+        codes = bamio.NT16[seq]
+        if l & 1:
+            codes = np.append(codes, 0)
+        packed = ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).tobytes()
+        body = struct.pack("<iiIIiiii", -1, -1, (4680 << 16) | (len(name) + 1), flag << 16, l, -1, -1, 0)
+        body += name + b"\0" + packed + bytes([30]) * l + tags
+        return struct.pack("<i", len(body)) + body
+
+    junk = (b"NMC\x01" + b"MDZ50A49\0" + b"XTAU" + b"X0C\x01" + b"X1S\x02\x00" + b"YQI\x05\x00\x00\x00" + b"AMC\x25" + b"XAZchr1,+5,100M,0;\0"
+            + b"SMc\x25")
+    keep = b"RGZrg1\0" + b"BCZACGT\0" + b"ZBBS\x03\x00\x00\x00\x01\x00\x02\x00\x03\x00" + b"xyi\x07\x00\x00\x00"
+    out = []
+    for i in range(900):
+        pos = int(rng.integers(0, genome.size - 400))
+        a = genome[pos:pos + 70].copy()
+        b = (3 - genome[pos + 200:pos + 270][::-1]).astype(genome.dtype)
+        name = f"q{i}".encode()
+        tags = keep[: [0, 7, 15, len(keep)][i % 4]] + (junk if i % 3 == 0 else b"") + (keep if i % 5 == 0 else b"")
+        kind = i % 4
+        if kind == 0:
+            out.append(rec(name, a, 4, tags))
+        elif kind == 1:
+            out += [rec(name, a, 77, tags), rec(name, b, 141, keep)]
+        elif kind == 2:
+            out += [rec(name, b, 141, tags), rec(name, a, 77, junk + keep)]  # mates in reverse order
+        else:
+            out += [rec(name, a, 77 | 512, b""), rec(name, b, 141, tags)]      # one mate failed QC
+    text = b"@HD\tVN:1.0\tSO:unsorted\n@RG\tID:rg1\tSM:s\n"
+    stream = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", 0) + b"".join(out)
+    bam = str(d / "mixed.bam")
+    with open(bam, "wb") as f:
+        for o in range(0, len(stream), 701):
+            f.write(bamio._bgzf_block(stream[o:o + 701], 1))
+        f.write(bamio.BGZF_EOF)
+    ref_out = str(d / "mixed.ref.bam")
+    r = subprocess.run([R.REF_BWA, "bam2bam", "-g", fa, "-t", "1", "-f", ref_out, bam], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([INPROC, "1", "0", fa, bam, str(d / "mixed.stub")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, BWAGPU_BATCH_RECORDS="200"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    same_records(ref_out, str(d / "mixed.stub.0.bam"))
+    recs = bamio.read_bam_records(ref_out)
+    assert len(recs) == 900 + 675 and any(b"ZBB" in x for x in recs) and not any(b"XTAU" in x and b"q3\0" in x for x in recs[:5])
+
+
 @pytest.mark.gpu
 def test_inprocess_gpu_matches_reference(work):
     d, fa, bam, ref_out = work

@@ -414,6 +414,18 @@ static void ensure_gpu(void)
 }
 static void *ensure_gpu_thread(void *arg) { (void)arg; ensure_gpu(); return 0; }
 
+/* The first batches of a pass are small and double up to the full size: the pipeline's stages all have work after a
+ * fraction of a full batch's latency (BWAGPU_BATCH_RAMP=0: every batch full size). */
+static size_t ramp_records(size_t B, unsigned q)
+{
+	static int on = -1;
+	size_t b;
+	if (on < 0) { const char *e = getenv("BWAGPU_BATCH_RAMP"); on = !(e && atoi(e) == 0); }
+	if (!on || q >= 4) return B;
+	b = B >> (4 - q);
+	return b < 8192 ? (B < 8192 ? B : 8192) : b;
+}
+
 static size_t batch_records(void)
 {
 	const char *e = getenv("BWAGPU_BATCH_RECORDS");
@@ -683,14 +695,16 @@ static void to_seq_one(size_t i, void *ctx) /* bam1_to_seq of aln_singleton / al
 
 /* aln_* (bam2bam.c:608-620, 660-681) for records [0, n): what sequential_loop_pass1 and a worker thread do first to a pristine
  * record, with the search hoisted out of the per-record loop.  `flat` holds >= 2 n elements. */
-static void align_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq)
+static void align_range(bam_pair_t *recs, size_t n, bwa_seq_t *flat, double *t_toseq, int seq_ready)
 {
 	size_t i;
 	int m = 0, j;
 	double t1 = now();
-	/* aln_singleton / aln_pair without the search ... */
-	t_cpu_bucket = CPU_TOSEQ;
-	parallel_for(n, 2048, to_seq_one, recs);
+	/* aln_singleton / aln_pair without the search ... (seq_ready: the read stage has run bam1_to_seq already) */
+	if (!seq_ready) {
+		t_cpu_bucket = CPU_TOSEQ;
+		parallel_for(n, 2048, to_seq_one, recs);
+	}
 	for (i = 0; i < n; ++i) {
 		bam_pair_t *r = &recs[i];
 		if (r->phase != pristine) continue;
@@ -830,7 +844,11 @@ static void *stage_read(void *arg)
 		P1_WAIT(P, slot, SL_FREE);
 		t = now();
 		const double c0 = thread_cpu_now();
-		n = fastin_read_pairs(P->ks, recs, P->B, &seqs, g_broken_input, g_drop_aligned);
+		n = fastin_read_pairs(P->ks, recs, ramp_records(P->B, q), &seqs, g_broken_input, g_drop_aligned);
+		if (n) { /* bam1_to_seq here, so that the align stage is the device call and nothing else */
+			t_cpu_bucket = CPU_TOSEQ;
+			parallel_for(n, 2048, to_seq_one, recs);
+		}
 		P->t_read += now() - t;
 		cpu_add(CPU_PARSE, thread_cpu_now() - c0);
 		P->n[slot] = n; P->seqs[slot] = seqs;
@@ -939,7 +957,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	for (q = 0;; ++q) { /* the align stage */
 		const int slot = (int)(q % P1_SLOTS);
 		P1_WAIT(&P, slot, SL_READ);
-		if (P.n[slot]) align_range(P.recs[slot], P.n[slot], flat, &t_toseq);
+		if (P.n[slot]) align_range(P.recs[slot], P.n[slot], flat, &t_toseq, 1);
 		P1_SET(&P, slot, SL_ALIGNED);
 		if (P.n[slot] == 0) break;
 	}
@@ -1377,8 +1395,8 @@ static void stage_refine(batch2_t *b)
 
 /* Pass 2 as a pipeline: load -> enumerate (A) -> pairing + XA (B) -> mate rescue (C) -> refine + update (D) -> write,
  * one thread per stage, batches in order.  A owns the position cache, B the random numbers, the writer the output file. */
-#define P2_SLOTS 6
-enum { S2_FREE = 0, S2_LOADED, S2_ENUM, S2_PAIRED, S2_RESCUED, S2_REFINED };
+#define P2_SLOTS 7
+enum { S2_FREE = 0, S2_LOADED, S2_ENUM, S2_PAIRED, S2_RESCUED, S2_REFINED, S2_WRITTEN };
 typedef struct {
 	pthread_mutex_t mu;
 	pthread_cond_t cv;
@@ -1390,7 +1408,7 @@ typedef struct {
 	khash_t(isize_infos) *iinfos;
 	kh_64_t *my_hash;
 	uint64_t n_tot[2], n_mapped[2];
-	double t0, t_load, t_enum, t_pair, t_rescue, t_refine, t_write;
+	double t0, t_load, t_enum, t_pair, t_rescue, t_refine, t_write, t_destroy;
 	long tot_seqs;
 } pipe2_t;
 #define P2_WAIT(P, slot, want) slot_wait(&(P)->mu, &(P)->cv, &(P)->state[slot], want)
@@ -1429,13 +1447,30 @@ static void *stage2_write(void *arg)
 		batch2_t *b = &P->b[slot];
 		double t1;
 		P2_WAIT(P, slot, S2_REFINED);
-		if (b->n == 0) break;
+		if (b->n == 0) { P2_SET(P, slot, S2_WRITTEN); break; }
 		t1 = now();
 		write_records_bam(P->output, b->recs, b->n);
-		destroy_records(b->recs, b->n);
 		P->t_write += now() - t1;
 		P->tot_seqs += b->seqs;
 		fprintf(stderr, "[sequential_loop_pass2] %ld sequences processed in %.2f sec\n", P->tot_seqs, now() - P->t0);
+		P2_SET(P, slot, S2_WRITTEN);
+	}
+	return 0;
+}
+
+static void *stage2_destroy(void *arg) /* the free()s of a written batch, off the writer's thread */
+{
+	pipe2_t *P = (pipe2_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P2_SLOTS);
+		batch2_t *b = &P->b[slot];
+		double t1;
+		P2_WAIT(P, slot, S2_WRITTEN);
+		if (b->n == 0) break;
+		t1 = now();
+		destroy_records(b->recs, b->n);
+		P->t_destroy += now() - t1;
 		P2_SET(P, slot, S2_FREE);
 	}
 	return 0;
@@ -1448,7 +1483,7 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	pipe2_t *P = (pipe2_t *)calloc(1, sizeof(pipe2_t));
 	bam_pair_t *stash = (bam_pair_t *)calloc(B, sizeof(bam_pair_t)); /* loaded records not yet handed to a batch */
 	size_t stash_n = 0, stash_at = 0;
-	pthread_t th[5];
+	pthread_t th[6];
 	khiter_t it;
 	unsigned q;
 	int s, eof = 0;
@@ -1462,6 +1497,7 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	pthread_create(&th[2], 0, stage2_rescue, P);
 	pthread_create(&th[3], 0, stage2_refine, P);
 	pthread_create(&th[4], 0, stage2_write, P);
+	pthread_create(&th[5], 0, stage2_destroy, P);
 	for (q = 0;; ++q) { /* the load stage: batches bounded by records and by the SA rows their hit lists expand to */
 		const int slot = (int)(q % P2_SLOTS);
 		batch2_t *b = &P->b[slot];
@@ -1470,7 +1506,8 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		P2_WAIT(P, slot, S2_FREE);
 		t1 = now();
 		b->n = 0; b->seqs = 0; b->iinfos = iinfos;
-		while (b->n < B) {
+		const size_t Bq = ramp_records(B, q);
+		while (b->n < Bq) {
 			if (stash_at == stash_n) {
 				if (eof) break;
 				stash_n = load_records(temporary, stash, B, &dummy);
@@ -1490,14 +1527,14 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		P2_SET(P, slot, S2_LOADED);
 		if (b->n == 0) break;
 	}
-	for (s = 0; s < 5; ++s) pthread_join(th[s], 0);
+	for (s = 0; s < 6; ++s) pthread_join(th[s], 0);
 	g_rep.pass2_s = now() - P->t0;
 	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each incl. their device calls: load %.2f, enumerate %.2f, "
-	                "pairing/XA %.2f, mate rescue %.2f, refine/update %.2f, BAM write %.2f)\n"
+	                "pairing/XA %.2f, mate rescue %.2f, refine/update %.2f, BAM write %.2f, destroy %.2f)\n"
 	                "[%s] finished cleanly, shutting down.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d singletons are mated.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d discordant pairs are fixed.\n",
-	        __func__, P->tot_seqs, now() - P->t0, P->t_load, P->t_enum, P->t_pair, P->t_rescue, P->t_refine, P->t_write, __func__,
+	        __func__, P->tot_seqs, now() - P->t0, P->t_load, P->t_enum, P->t_pair, P->t_rescue, P->t_refine, P->t_write, P->t_destroy, __func__,
 	        (long long)P->n_mapped[1], (long long)P->n_tot[1], SW_MIN_MAPQ, (long long)P->n_mapped[0], (long long)P->n_tot[0], SW_MIN_MAPQ);
 	for (it = kh_begin(P->my_hash); it != kh_end(P->my_hash); ++it)
 		if (kh_exist(P->my_hash, it)) free(kh_val(P->my_hash, it).a);
@@ -1658,7 +1695,7 @@ void *run_worker_thread(void *arg)
 		/* ---- the switch of bam2bam.c:1414-1422, for the whole batch */
 		t1 = now();
 		if (phase_of_batch == pristine) {
-			align_range(recs, n, flat, &t_toseq);
+			align_range(recs, n, flat, &t_toseq, 0);
 			position_range(recs, n, &q1, &qoff, &qoff_cap, &t_host);
 		} else if (phase_of_batch == aligned) for (i = 0; i < n; ++i) pair_posn(&recs[i]);
 		else if (phase_of_batch == positioned) {

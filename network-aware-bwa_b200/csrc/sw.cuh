@@ -417,16 +417,18 @@ __global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac,
                                                 const bwa_gpu_sw_res_t *__restrict__ boxes, const int *__restrict__ score_r,
                                                 bwa_gpu_path_res_t *__restrict__ res, uint16_t *__restrict__ cigars,
                                                 uint8_t *cells_all, size_t cells_stride, GScore *sc_all, size_t sc_stride,
-                                                int *work_counter)
+                                                int *work_counter, const int *__restrict__ ids, const int *__restrict__ n_ids)
 {
 	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	uint8_t *cells = cells_all + warp * cells_stride * 32 + lane;
 	GRow sc0, sc1;
 	sc0.p = sc_all + warp * 2 * sc_stride * 32 + lane;
 	sc1.p = sc0.p + sc_stride * 32;
+	if (ids) n_jobs = *n_ids; // the jobs k_global_warp could not hold in shared memory
 	for (;;) {
-		const int job = atomicAdd(work_counter, 1);
+		int job = atomicAdd(work_counter, 1);
 		if (job >= n_jobs) break;
+		if (ids) job = ids[job];
 		const PathJob J = jobs[job];
 		uint16_t *cig = cigars + J.cig_off;
 		const int cig_cap = J.len1 + J.len2 + 2;
@@ -462,10 +464,213 @@ __global__ void __launch_bounds__(128) k_global(const uint8_t *__restrict__ pac,
 	}
 }
 
+// ------------------------------------------------------------------ K6, one WARP per job, everything in shared memory
+// The same recurrence as global_align_dev, reorganised so that nothing of a job touches global memory but its bases and
+// its CIGAR: the two score rows (M, I, D per reference column), the window's bases and the traceback matrix (one byte per
+// band cell) live in shared memory.  A row is computed by the lanes together: M and I of a cell depend on the previous row
+// only (one column per lane, 32 at a time); D(i) = max(M(i-1) - q, D(i-1)) - ext along the row is a max-plus prefix scan --
+// with E(i) = D(i) + i ext it is the running maximum of A(i) = M(i-1) - q + (i-1) ext, and the traceback bit of a cell
+// ("came from M" iff M(i-1) - q > D(i-1), strictly: stdaln.c's set_D) is A(i) > E(i-1).  Integer arithmetic throughout, so
+// every score and every bit is the sequential code's.  Lane 0 walks the traceback.  A job whose window is wider than
+// GW_ROWCAP columns or whose band needs more than GW_CELLCAP cells is handed to the thread-per-job kernel above.
+#define GW_ROWCAP 256
+#define GW_CELLCAP 16384
+struct GwSmem {
+	int M[2][GW_ROWCAP + 2], I[2][GW_ROWCAP + 2], D[2][GW_ROWCAP + 2];
+	uint8_t ref[GW_ROWCAP + 8];
+	uint8_t cells[GW_CELLCAP];
+};
+
+__device__ __forceinline__ int gw_setM(int pM, int pI, int pD, int sc, int &bits)
+{
+	if (pM >= pI) {
+		if (pM >= pD) { bits = 0; return pM + sc; }
+		bits = 2; return pD + sc;
+	}
+	if (pI > pD) { bits = 1; return pI + sc; }
+	bits = 2; return pD + sc;
+}
+__device__ __forceinline__ int gw_setI(int pM, int pI, int ext, int &bit)
+{
+	if (pM - SW_Q > pI) { bit = 0; return pM - SW_Q - ext; }
+	bit = 1; return pI - ext;
+}
+
+// false: the job does not fit this kernel's shared memory (nothing was written)
+__device__ bool global_align_warp(GwSmem &S, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ refb, long long rbeg, int len1,
+                                  const uint8_t *__restrict__ q, int len2, int gap_end, int band, uint16_t *cig, int cig_cap, GlobalOut &out)
+{
+	const int lane = threadIdx.x & 31;
+	out.score = out.n_cigar = out.start_i = out.start_j = out.end_i = out.end_j = 0;
+	if (len1 == 0 || len2 == 0) return true;
+	const int eend = gap_end >= 0 ? gap_end : SW_R;
+	int b1, b2;
+	if (len1 > len2) { b1 = len1 - len2 + band; b2 = band; }
+	else { b1 = band; b2 = len2 - len1 + band; }
+	if (b1 > len1) b1 = len1;
+	if (b2 > len2) b2 = len2;
+	const int width = (b1 + b2 <= len1) ? b1 + b2 + 1 : len1 + 1;
+	if (len1 > GW_ROWCAP || (long long)(len2 + 1) * width > GW_CELLCAP) return false;
+	__syncwarp();
+	for (int i = lane; i < len1; i += 32) S.ref[i] = (uint8_t)(pac ? pac_base(pac, rbeg + i) : (int)refb[i]);
+	const int tmp_end = b2 < len2 ? b2 : len2 - 1;
+	int cur = 0;
+	for (int j = 0; j <= len2; ++j) {
+		// the row's regime (the three loops of aln_global_core and its first row)
+		int lo, hi, hi_I, extD, qj = 0;
+		bool lo_inf;
+		if (j == 0) { lo = 0; hi = b1 - 1; lo_inf = false; hi_I = 0; extD = eend; }
+		else {
+			qj = q[j - 1];
+			if (j <= tmp_end || (j == len2 && b2 == len2)) { // part 1 (and its last-row form)
+				lo = 0; lo_inf = false;
+				hi = (j + b1 <= len1 + 1) ? j + b1 - 1 : len1;
+				hi_I = (j + b1 - 1 > len1) ? 1 : 0;
+				extD = (j == tmp_end + 1) ? eend : SW_R;
+			} else if (j <= len2 - b2 + 1) { // part 2
+				lo = j - b2; lo_inf = true; hi = j + b1 - 1; hi_I = 0; extD = SW_R;
+			} else { // part 3
+				lo = j - b2; lo_inf = true; hi = len1; hi_I = 1; extD = (j == len2) ? eend : SW_R;
+			}
+		}
+		int *cM = S.M[cur], *cI = S.I[cur], *cD = S.D[cur];
+		const int *lM = S.M[cur ^ 1], *lI = S.I[cur ^ 1], *lD = S.D[cur ^ 1];
+		uint8_t *crow = S.cells + (size_t)j * width - (j > b2 ? j - b2 : 0);
+		// phase A: M and I of every column, the D of the row's first column
+		for (int i = lo + lane; i <= hi; i += 32) {
+			int m, ii, bm = 0, bi = 0;
+			if (j == 0) { m = i == 0 ? 0 : G_INF; ii = G_INF; }
+			else if (i == lo && lo_inf) { m = G_INF; ii = G_INF; }
+			else if (i == 0) { m = G_INF; ii = gw_setI(lM[0], lI[0], eend, bi); }
+			else {
+				m = gw_setM(lM[i - 1], lI[i - 1], lD[i - 1], sw_sc(S.ref[i - 1], qj), bm);
+				if (i < hi) ii = gw_setI(lM[i], lI[i], SW_R, bi);
+				else if (hi_I) ii = gw_setI(lM[i], lI[i], eend, bi);
+				else ii = G_INF;
+			}
+			cM[i] = m; cI[i] = ii;
+			if (i == lo) cD[i] = G_INF;
+			crow[i] = (uint8_t)(bm | bi << 2);
+		}
+		__syncwarp();
+		// phase B: D along the row
+		int carry = G_INF + lo * extD; // E(lo)
+		for (int base = lo + 1; base <= hi; base += 32) {
+			const int i = base + lane;
+			const bool live = i <= hi;
+			const int a = live ? cM[i - 1] - SW_Q + (i - 1) * extD : -2000000000;
+			int inc = a;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(0xffffffffu, inc, d);
+				if (lane >= d && o > inc) inc = o;
+			}
+			int before = __shfl_up_sync(0xffffffffu, inc, 1);
+			before = lane == 0 ? carry : (before > carry ? before : carry); // E(i-1)
+			const int e = inc > carry ? inc : carry;                        // E(i)
+			if (live) {
+				cD[i] = e - i * extD;
+				if (!(a > before)) crow[i] |= (uint8_t)(2u << 4);
+			}
+			carry = __shfl_sync(0xffffffffu, e, 31);
+		}
+		__syncwarp();
+		cur ^= 1;
+	}
+	// backtrace on lane 0 (the same walk as global_align_dev's)
+	const int fin = cur ^ 1;
+	int res[6] = {0, 0, 0, 0, 0, 0};
+	if (lane == 0) {
+#define WCELL(j, i) S.cells[(size_t)(j) * width + ((j) > b2 ? (i) - ((j) - b2) : (i))]
+		int i = len1, j = len2;
+		uint8_t cc = WCELL(j, i);
+		int mx = S.M[fin][len1], type = cc & 3, ctype = 0;
+		if (S.I[fin][len1] > mx) { mx = S.I[fin][len1]; type = (cc >> 2) & 3; ctype = 1; }
+		if (S.D[fin][len1] > mx) { mx = S.D[fin][len1]; type = (cc >> 4) & 3; ctype = 2; }
+		int pos = cig_cap, run_type = ctype, run_len = 1;
+		int pi = i, pj = j;
+		for (;;) {
+			if (ctype == 0) { --i; --j; } else if (ctype == 1) --j; else --i;
+			cc = WCELL(j, i);
+			ctype = type;
+			type = type == 0 ? (cc & 3) : type == 1 ? ((cc >> 2) & 3) : ((cc >> 4) & 3);
+			if (!(i || j)) break;
+			pi = i; pj = j;
+			if (ctype == run_type) ++run_len;
+			else { cig[--pos] = (uint16_t)(run_type << 14 | run_len); run_type = ctype; run_len = 1; }
+		}
+		cig[--pos] = (uint16_t)(run_type << 14 | run_len);
+		const int n_cigar = cig_cap - pos;
+		for (int t = 0; t < n_cigar; ++t) cig[t] = cig[pos + t];
+		res[0] = mx; res[1] = n_cigar; res[2] = pi; res[3] = pj; res[4] = len1; res[5] = len2;
+#undef WCELL
+	}
+	out.score = __shfl_sync(0xffffffffu, res[0], 0); out.n_cigar = __shfl_sync(0xffffffffu, res[1], 0);
+	out.start_i = __shfl_sync(0xffffffffu, res[2], 0); out.start_j = __shfl_sync(0xffffffffu, res[3], 0);
+	out.end_i = __shfl_sync(0xffffffffu, res[4], 0); out.end_j = __shfl_sync(0xffffffffu, res[5], 0);
+	return true;
+}
+
+#define GW_WARPS 4
+__global__ void __launch_bounds__(32 * GW_WARPS) k_global_warp(const uint8_t *__restrict__ pac, const PathJob *__restrict__ jobs, int n_jobs,
+                                                               const uint8_t *__restrict__ reads, int gap_end, int band,
+                                                               const bwa_gpu_sw_res_t *__restrict__ boxes, const int *__restrict__ score_r,
+                                                               bwa_gpu_path_res_t *__restrict__ res, uint16_t *__restrict__ cigars,
+                                                               int *work_counter, int *__restrict__ big_ids, int *n_big)
+{
+	extern __shared__ __align__(16) unsigned char gw_raw[];
+	GwSmem &S = reinterpret_cast<GwSmem *>(gw_raw)[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	for (;;) {
+		int job = 0;
+		if (lane == 0) job = atomicAdd(work_counter, 1);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= n_jobs) break;
+		const PathJob J = jobs[job];
+		uint16_t *cig = cigars + J.cig_off;
+		const int cig_cap = J.len1 + J.len2 + 2;
+		bwa_gpu_path_res_t r;
+		bool fits = true;
+		r.cigar_off = J.cig_off;
+		if (!boxes) { // refine_gapped_core's call (bwase.c:212)
+			GlobalOut o;
+			fits = pac ? global_align_warp(S, pac, nullptr, J.beg, J.len1, reads + J.q_off, J.len2, gap_end, band, cig, cig_cap, o)
+			           : global_align_warp(S, nullptr, reads + J.beg, 0, J.len1, reads + J.q_off, J.len2, gap_end, band, cig, cig_cap, o);
+			r.score = o.score; r.n_cigar = o.n_cigar;
+			r.start_i = o.start_i; r.start_j = o.start_j; r.end_i = o.end_i; r.end_j = o.end_j;
+		} else { // aln_local_core's third pass (stdaln.c:723-745)
+			const bwa_gpu_sw_res_t b = boxes[job];
+			r.score = b.score; r.n_cigar = 0;
+			r.start_i = b.start_i; r.start_j = b.start_j; r.end_i = b.end_i; r.end_j = b.end_j;
+			if (b.score >= 1 && b.end_i > 0 && b.end_j > 0) {
+				const int score_f = b.score, sr = score_r[job];
+				const int l1 = b.end_i - b.start_i + 1, l2 = b.end_j - b.start_j + 1;
+				const int span = (b.end_i - b.start_i > b.end_j - b.start_j ? b.end_i - b.start_i : b.end_j - b.start_j) + 1;
+				GlobalOut o;
+				for (int bw = 50;; bw <<= 1) {
+					fits = global_align_warp(S, pac, nullptr, J.beg + b.start_i - 1, l1, reads + J.q_off + b.start_j - 1, l2, -1, bw, cig, cig_cap, o);
+					if (!fits) break;
+					if (o.score == sr || score_f == o.score) break;
+					if (bw > span) break;
+				}
+				if (sr > o.score && score_f > o.score) r.score = -1;
+				else r.score = o.score;
+				r.n_cigar = o.n_cigar;
+				r.start_i = o.start_i + b.start_i - 1; r.start_j = o.start_j + b.start_j - 1;
+				r.end_i = o.end_i + b.start_i - 1; r.end_j = o.end_j + b.start_j - 1;
+			}
+		}
+		if (lane == 0) {
+			if (fits) res[job] = r;
+			else big_ids[atomicAdd(n_big, 1)] = job;
+		}
+	}
+}
+
 // device buffers that survive between calls (cudaMalloc of the K6 scratch costs more than the kernels)
 struct SwScratch {
-	void *p[10] = {};
-	size_t cap[10] = {};
+	void *p[12] = {};
+	size_t cap[12] = {};
 	cudaError_t reserve(int k, size_t bytes)
 	{
 		if (bytes <= cap[k]) return cudaSuccess;
@@ -476,7 +681,7 @@ struct SwScratch {
 		if (e == cudaSuccess) cap[k] = want;
 		return e;
 	}
-	void release() { for (int k = 0; k < 10; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; } }
+	void release() { for (int k = 0; k < 12; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; } }
 };
 
 struct SwCounts { long long cells_fwd = 0, h2d = 0, d2h = 0; int launches = 0; };
@@ -514,6 +719,7 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		for (int t = 0; t < jobs[i].len; ++t) hq[(size_t)hj[i].q_off + t] = jobs[i].seq[t] > 3 ? 4 : jobs[i].seq[t];
 	SwJob *d_jobs = nullptr; uint8_t *d_q = nullptr; bwa_gpu_sw_res_t *d_res = nullptr; int *d_cnt = nullptr, *d_sr = nullptr;
 	PathJob *d_pj = nullptr; bwa_gpu_path_res_t *d_pres = nullptr; uint16_t *d_cig = nullptr; uint8_t *d_cells = nullptr; GScore *d_sc = nullptr;
+	int *d_big = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 	cudaError_t e;
 	auto cleanup = [&]() {
@@ -524,9 +730,9 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 #define SWALLOC(ptr, k, bytes) do { e = S.reserve(k, bytes); if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc(%zu): %s", (size_t)(bytes), cudaGetErrorString(e)); } ptr = (decltype(ptr))S.p[k]; } while (0)
 #define SWCK(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return fail("%s: %s", #x, cudaGetErrorString(e)); } } while (0)
 	SWALLOC(d_q, 0, hq.size());
-	SWALLOC(d_cnt, 1, 2 * sizeof(int));
+	SWALLOC(d_cnt, 1, 4 * sizeof(int)); // work counters: [0] k_sw, [1] k_global_warp, [3] k_global; [2] = jobs passed on to k_global
 	SWCK(cudaMemcpyAsync(d_q, hq.data(), hq.size(), cudaMemcpyHostToDevice, st));
-	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+	SWCK(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), st));
 	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1)); SWCK(cudaEventCreate(&e2));
 	int dev = 0, n_sm = 148;
 	cudaGetDevice(&dev);
@@ -535,7 +741,7 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		counts->h2d += (long long)hq.size() + (long long)n * (long long)(sizeof(SwJob) + (mode ? sizeof(PathJob) : 0));
 		counts->d2h += (long long)n * (long long)(mode ? sizeof(bwa_gpu_path_res_t) : sizeof(bwa_gpu_sw_res_t)) + (mode ? 2 * cig_total : 0);
 		if (mode != 2) for (int i = 0; i < n; ++i) counts->cells_fwd += (long long)hj[i].len1 * hj[i].len2;
-		counts->launches += (mode != 2) + (mode != 0);
+		counts->launches += (mode != 2) + 2 * (mode != 0);
 	}
 	// ---- every allocation and staging copy first, so that the event window holds kernels only
 	size_t smem = 0, cells_stride = 0, sc_stride = 0, threads = 0;
@@ -559,9 +765,11 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		cells_stride = ((size_t)(len2_max + 1) * (len1_max + 1) + 15) & ~(size_t)15;
 		sc_stride = (size_t)len1_max + 2;
 		const size_t per_thread = cells_stride + 2 * sc_stride * sizeof(GScore);
-		threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
-		const size_t budget = (size_t)6 << 30;
+		threads = std::min<size_t>((size_t)n_sm * 256, ((size_t)n + 127) / 128 * 128); // only what k_global_warp passes on comes here
+		const size_t budget = (size_t)2 << 30;
 		if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
+		SWALLOC(d_big, 10, (size_t)n * sizeof(int));
+		SWCK(cudaFuncSetAttribute(k_global_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GW_WARPS * sizeof(GwSmem))));
 		SWALLOC(d_pj, 5, (size_t)n * sizeof(PathJob));
 		SWALLOC(d_pres, 6, (size_t)n * sizeof(bwa_gpu_path_res_t));
 		SWALLOC(d_cig, 7, (size_t)cig_total * sizeof(uint16_t) + 16);
@@ -577,8 +785,12 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 	}
 	SWCK(cudaEventRecord(e2, st));
 	if (mode) {
+		const int wblocks = std::min(2 * n_sm, (n + GW_WARPS - 1) / GW_WARPS);
+		k_global_warp<<<wblocks, 32 * GW_WARPS, GW_WARPS * sizeof(GwSmem), st>>>(d_pac, d_pj, n, d_q, gap_end, band, mode == 1 ? d_res : nullptr,
+		                                                                       d_sr, d_pres, d_cig, d_cnt + 1, d_big, d_cnt + 2);
+		SWCK(cudaGetLastError());
 		k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(d_pac, d_pj, n, d_q, gap_end, band, mode == 1 ? d_res : nullptr, d_sr, d_pres,
-		                                                   d_cig, d_cells, cells_stride, d_sc, sc_stride, d_cnt + 1);
+		                                                   d_cig, d_cells, cells_stride, d_sc, sc_stride, d_cnt + 3, d_big, d_cnt + 2);
 		SWCK(cudaGetLastError());
 	}
 	SWCK(cudaEventRecord(e1, st));
@@ -631,6 +843,7 @@ static int ga_seqs_batch(SwScratch &S, cudaStream_t st, int n, const bwa_gpu_ga_
 	}
 	uint8_t *d_b = nullptr; int *d_cnt = nullptr; PathJob *d_pj = nullptr; bwa_gpu_path_res_t *d_pres = nullptr; uint16_t *d_cig = nullptr;
 	uint8_t *d_cells = nullptr; GScore *d_sc = nullptr;
+	int *d_big = nullptr;
 	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	cudaError_t e;
 	auto cleanup = [&]() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
@@ -641,29 +854,34 @@ static int ga_seqs_batch(SwScratch &S, cudaStream_t st, int n, const bwa_gpu_ga_
 	cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
 	const size_t cells_stride = ((size_t)(len2_max + 1) * (len1_max + 1) + 15) & ~(size_t)15, sc_stride = (size_t)len1_max + 2;
 	const size_t per_thread = cells_stride + 2 * sc_stride * sizeof(GScore);
-	size_t threads = std::min<size_t>((size_t)n_sm * 1024, ((size_t)n + 127) / 128 * 128);
-	const size_t budget = (size_t)6 << 30;
+	size_t threads = std::min<size_t>((size_t)n_sm * 256, ((size_t)n + 127) / 128 * 128);
+	const size_t budget = (size_t)2 << 30;
 	if (threads * per_thread > budget) threads = std::max<size_t>(128, budget / per_thread / 128 * 128);
 	SWALLOC(d_b, 0, hb.size());
-	SWALLOC(d_cnt, 1, 2 * sizeof(int));
+	SWALLOC(d_cnt, 1, 4 * sizeof(int));
+	SWALLOC(d_big, 10, (size_t)n * sizeof(int));
+	SWCK(cudaFuncSetAttribute(k_global_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GW_WARPS * sizeof(GwSmem))));
 	SWALLOC(d_pj, 5, (size_t)n * sizeof(PathJob));
 	SWALLOC(d_pres, 6, (size_t)n * sizeof(bwa_gpu_path_res_t));
 	SWALLOC(d_cig, 7, (size_t)cig_total * sizeof(uint16_t) + 16);
 	SWALLOC(d_cells, 8, threads * cells_stride);
 	SWALLOC(d_sc, 9, threads * 2 * sc_stride * sizeof(GScore));
 	SWCK(cudaMemcpyAsync(d_b, hb.data(), hb.size(), cudaMemcpyHostToDevice, st));
-	SWCK(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+	SWCK(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), st));
 	SWCK(cudaMemcpyAsync(d_pj, pj.data(), (size_t)n * sizeof(PathJob), cudaMemcpyHostToDevice, st));
 	cigars->resize((size_t)cig_total);
 	if (counts) {
 		counts->h2d += (long long)hb.size() + (long long)n * (long long)sizeof(PathJob);
 		counts->d2h += (long long)n * (long long)sizeof(bwa_gpu_path_res_t) + 2 * cig_total;
-		counts->launches += 1;
+		counts->launches += 2;
 	}
 	SWCK(cudaEventCreate(&e0)); SWCK(cudaEventCreate(&e1));
 	SWCK(cudaEventRecord(e0, st));
+	k_global_warp<<<std::min(2 * n_sm, (n + GW_WARPS - 1) / GW_WARPS), 32 * GW_WARPS, GW_WARPS * sizeof(GwSmem), st>>>(
+	    nullptr, d_pj, n, d_b, gap_end, band, nullptr, nullptr, d_pres, d_cig, d_cnt + 1, d_big, d_cnt + 2);
+	SWCK(cudaGetLastError());
 	k_global<<<(unsigned)(threads / 128), 128, 0, st>>>(nullptr, d_pj, n, d_b, gap_end, band, nullptr, nullptr, d_pres, d_cig, d_cells, cells_stride,
-	                                                   d_sc, sc_stride, d_cnt + 1);
+	                                                   d_sc, sc_stride, d_cnt + 3, d_big, d_cnt + 2);
 	SWCK(cudaGetLastError());
 	SWCK(cudaEventRecord(e1, st));
 	SWCK(cudaMemcpyAsync(pres, d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t), cudaMemcpyDeviceToHost, st));

@@ -324,6 +324,30 @@ def test_global_align_matches_reference_live(gpu_index, gap_end, band):
     assert not bad, (len(bad), bad[:5], got[bad[0]], wants[bad[0]])
 
 
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+def test_global_align_both_kernels(gpu_index):
+    """K6's two forms in one call: jobs that fit the warp-per-job kernel's shared memory (csrc/sw.cuh k_global_warp: window
+    <= 256 columns, band cells <= 16 K) next to jobs that do not and go to the thread-per-job kernel, in random order."""
+    T, idx = gpu_index
+    rng = np.random.default_rng(77)
+    jobs, wants = [], []
+    for i in range(600):
+        ql = int(rng.integers(20, 120)) if i % 3 else int(rng.integers(240, 420))
+        beg = int(rng.integers(0, idx.l_pac - 600))
+        q = T[beg + 3:beg + 3 + ql].copy()
+        for _ in range(int(rng.integers(0, 5))):
+            q[int(rng.integers(0, ql))] = rng.integers(0, 4)
+        if i % 4 == 0 and ql > 30:  # a deletion in the read
+            cut = int(rng.integers(5, ql - 10))
+            q = np.concatenate([q[:cut], q[cut + int(rng.integers(1, 4)):]])
+        rl = int(q.size + rng.integers(0, 9))
+        jobs.append((beg, rl, q))
+        wants.append(R.ref_global(T[beg:beg + rl], q, 5, 50))
+    got = api.global_align(jobs, 5, 50)
+    bad = [i for i in range(len(jobs)) if not _same_path(got[i], wants[i])]
+    assert not bad, (len(bad), bad[:5], got[bad[0]], wants[bad[0]])
+
+
 def test_mate_sw_path_and_global_align_match_golden(golden, gpu_index):
     """K6 against the committed reference-made vectors (no oracle/_ref needed)."""
     jobs = sw_jobs_from(golden["swp_beg"], golden["swp_reglen"], golden["swp_queries"], golden["swp_q_off"])

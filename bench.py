@@ -350,11 +350,33 @@ def main():
             e2e_s += dt; steps_ms.append(round(dt * 1e3, 1)); reps.append(rep)
         barrier()
         wall_s = time.perf_counter() - t_wall0
+        tot_e2e = api.get_totals()
+        # ---- the same K steps once more for `value`: the device time the job needs.  In the pipelined configuration above the
+        # kernels of three lanes and of two passes' stages overlap, so their event times count the same device seconds
+        # several times; here every pass is ONE batch on ONE lane -- kernels run one after the other, alone on the device --
+        # and the sum of their event times is the device-busy time of the step.
+        pipelined_env = {k: os.environ.get(k) for k in ("BWAGPU_LANES", "BWAGPU_BATCH_RECORDS", "BWAGPU_BATCH_RAMP")}
+        os.environ.update({"BWAGPU_LANES": "1", "BWAGPU_BATCH_RECORDS": str(args.pairs), "BWAGPU_BATCH_RAMP": "0"})
+        host.H.bwa_gpu_batch_reset_device()
+        host.run(prefix, bam, out)  # untimed: sets the device up again, sizes the buffers
+        api.reset_totals()
+        barrier()
+        t_dev0 = time.perf_counter()
+        for _ in range(args.steps):
+            host.run(prefix, bam, out)
+        barrier()
+        wall_dev_s = time.perf_counter() - t_dev0
         clocks = sampler.stop()
         tot = api.get_totals()
+        for k, v in pipelined_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        host.H.bwa_gpu_batch_reset_device()
     finally:
         restore_stderr(saved)
-    kernel_ms = tot["ms_width"] + tot["ms_search"] + tot["ms_sa"] + tot["ms_sw"] + tot["ms_global"]
+    kernel_ms = tot["ms_width"] + tot["ms_search"] + tot["ms_sa"] + tot["ms_sw"] + tot["ms_global"] + tot["ms_bgzf"]
     if dist is not None:
         t = torch.tensor([e2e_s, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -364,7 +386,7 @@ def main():
     reads_per_step = 2 * args.pairs
     value = world * reads_per_step * args.steps / (kernel_ms_max / 1e3)
     e2e = {"value": world * reads_per_step * args.steps / e2e_s_max, "unit": "reads/s",
-           "h2d_bytes_per_step": int(tot["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(tot["d2h_bytes"] / args.steps),
+           "h2d_bytes_per_step": int(tot_e2e["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(tot_e2e["d2h_bytes"] / args.steps),
            "api": "bwa_bam_to_bam (the reference's bam2bam entry point, in-process) behind integration/libbwa_gpu_batch.so; BAM in -> BAM out, "
                   "both passes; wall minus the index load (0 after the first run: the index stays loaded, as in one long job)",
            "ms_each_step_rank0": steps_ms, "host_threads_per_rank": threads}
@@ -373,7 +395,8 @@ def main():
                                      "jobs_sw", "jobs_ga", "dev_bgzf_s", "bytes_bgzf")}
     pipeline["device_call_share_of_wall"] = ((last["dev_aln_s"] + last["dev_sa_s"] + last["dev_sw_s"] + last["dev_ga_s"])
                                              / max(1e-9, last["wall_s"] - last["index_load_s"]))
-    per_step = {k: tot[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global")}
+    per_step = {k: tot[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global", "ms_bgzf")}
+    per_step_pipelined = {k: tot_e2e[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global", "ms_bgzf")}
 
     if rank != 0:
         host.close()
@@ -463,7 +486,11 @@ def main():
                   "bound": "integer ALU: 148 SMs x 128 lanes x SM clock lane-ops/s at 12 lane-ops per affine-gap cell"},
         "k6_global": {"jobs_per_step": (tot["sw_jobs"] + tot["ga_jobs"]) / args.steps, "kernel_ms_per_step": per_step["ms_global"]},
         "k2_width": {"kernel_ms_per_step": per_step["ms_width"]},
-        "k3_search_in_pipeline": {"kernel_ms_per_step": per_step["ms_search"], "pass_ms_per_step": [x / args.steps for x in tot["ms_search_pass"]]},
+        "bgzf_deflate": {"bytes_in_per_step": tot["bgzf_bytes_in"] / args.steps, "bytes_out_per_step": tot["bgzf_bytes_out"] / args.steps,
+                         "kernel_ms_per_step": per_step["ms_bgzf"], "gb_per_s_in": per_s(tot["bgzf_bytes_in"], tot["ms_bgzf"]) / 1e9,
+                         "ratio": tot["bgzf_bytes_out"] / max(1, tot["bgzf_bytes_in"]),
+                         "bound": "latency of the per-block LZ77 / Huffman phases (one CTA per 64 KB block, shared memory only); not an HBM-bound kernel"},
+        "k3_search_in_job": {"kernel_ms_per_step": per_step["ms_search"], "pass_ms_per_step": [x / args.steps for x in tot["ms_search_pass"]]},
     }
 
     # ---- cpu baseline (N = 1 only): the reference itself on a bounded prefix of the shard
@@ -486,12 +513,15 @@ def main():
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "config": config,
-        "e2e": e2e, "gpu_launches": int(tot["launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "gpu_launches": int(tot["launches"] + tot_e2e["launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "parity_sample": parity, "aln_only": aln_only, "other_kernels": other, "pipeline_last_step_rank0": pipeline,
-        "kernel_ms_per_step": per_step, "parallelism": f"one process + one index replica + one shard of pairs per GPU (x{world}), no collective",
-        "timed": "value: CUDA events inside the library around every kernel of the step (K2, K3, K4, K5, K6), summed; "
-                 "e2e: perf_counter around bwa_bam_to_bam",
-        "wall_s_timed_region": wall_s,
+        "kernel_ms_per_step": per_step, "kernel_ms_per_step_pipelined_runs": per_step_pipelined, "parallelism": f"one process + one index replica + one shard of pairs per GPU (x{world}), no collective",
+        "timed": "two timed regions of K steps each, both bracketed by barrier + synchronize.  e2e: perf_counter around bwa_bam_to_bam in the "
+                 "pipelined configuration (3 lanes, batches of 131072 records).  value: the same K runs with one batch per pass on one "
+                 "lane, so that no two kernels overlap; CUDA events inside the library around every kernel (K2, K3, K4, K5, K6, BGZF), "
+                 "summed = device-busy time of the job (kernel_ms_per_step); the pipelined runs' event sums are in "
+                 "kernel_ms_per_step_pipelined_runs (overlapping kernels counted more than once)",
+        "wall_s_timed_region": wall_s + wall_dev_s, "wall_s_e2e_region": wall_s, "wall_s_value_region": wall_dev_s,
     }
     print(json.dumps(line))
     host.close()

@@ -269,6 +269,13 @@ void bwt_destroy_pac(ubyte_t *pac, const bntseq_t *bns)
 	real_bwt_destroy_pac(pac, bns);
 }
 
+/* the device context is torn down and set up again by the next run: the library reads its BWAGPU_* settings when it is
+ * initialised (bench.py measures the same job in two configurations of one process) */
+void bwa_gpu_batch_reset_device(void)
+{
+	if (g_ready) { bwa_gpu_destroy(); g_ready = 0; }
+}
+
 void bwa_gpu_batch_drop_index(void)
 {
 	REAL(void, bwt_destroy, bwt_t *);
@@ -418,10 +425,9 @@ static void *ensure_gpu_thread(void *arg) { (void)arg; ensure_gpu(); return 0; }
  * fraction of a full batch's latency (BWAGPU_BATCH_RAMP=0: every batch full size). */
 static size_t ramp_records(size_t B, unsigned q)
 {
-	static int on = -1;
+	const char *e = getenv("BWAGPU_BATCH_RAMP");
 	size_t b;
-	if (on < 0) { const char *e = getenv("BWAGPU_BATCH_RAMP"); on = !(e && atoi(e) == 0); }
-	if (!on || q >= 4) return B;
+	if ((e && atoi(e) == 0) || q >= 4) return B;
 	b = B >> (4 - q);
 	return b < 8192 ? (B < 8192 ? B : 8192) : b;
 }

@@ -30,6 +30,8 @@ int bwa_gpu_batch_report_size(void); /* sizeof(bwa_gpu_batch_report_t) as this l
  * destroy calls at the end of a run leave them alone.  bwa_gpu_batch_drop_index() frees them. */
 void bwa_gpu_batch_keep_index(int on);
 void bwa_gpu_batch_drop_index(void);
+/* tear the device context down; the next run sets it up again (and re-reads the library's BWAGPU_* settings) */
+void bwa_gpu_batch_reset_device(void);
 
 #ifdef __cplusplus
 }

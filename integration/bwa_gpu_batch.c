@@ -409,6 +409,8 @@ static void ensure_gpu(void)
 		if (n < 1) n = 1;
 		if (n > 16) n = 16;
 		for (i = 0; i < n; ++i) ids[i] = first + i;
+		setenv("BWAGPU_LANES", "4", 0);       /* two search calls in flight (the two align threads of pass 1), two lanes each */
+		setenv("BWAGPU_CALL_GROUPS", "2", 0);
 		setenv("BWAGPU_MALLOPT", "1", 0); /* this host frees millions of aln[] per batch: keep the heaps (a process-wide choice, ours to make) */
 		if (bwa_gpu_init(n, ids)) die("bwa_gpu_init");
 	}
@@ -818,6 +820,7 @@ typedef struct {
 	khash_t(isize_infos) *iinfos;
 	double t0, t_read, t_host, t_write, t_destroy;
 	long tot_seqs;
+	int align_done; /* the end marker has reached the align stage */
 } pipe1_t;
 
 static void slot_wait(pthread_mutex_t *mu, pthread_cond_t *cv, const int *state, int want)
@@ -938,6 +941,35 @@ static void *stage_destroy(void *arg)
 	return 0;
 }
 
+#define MAX_ALIGN 4
+typedef struct { pipe1_t *P; int id, n; bwa_seq_t *flat; double t_toseq; } align_arg_t;
+
+static int align_threads(void)
+{
+	const char *e = getenv("BWAGPU_CALL_GROUPS");
+	int n = e ? atoi(e) : 2;
+	return n < 1 ? 1 : n > MAX_ALIGN ? MAX_ALIGN : n;
+}
+
+static void *stage_align(void *arg)
+{
+	align_arg_t *A = (align_arg_t *)arg;
+	pipe1_t *P = A->P;
+	unsigned q;
+	for (q = (unsigned)A->id;; q += (unsigned)A->n) {
+		const int slot = (int)(q % P1_SLOTS);
+		pthread_mutex_lock(&P->mu);
+		while (P->state[slot] != SL_READ && !P->align_done) pthread_cond_wait(&P->cv, &P->mu);
+		if (P->state[slot] != SL_READ) { pthread_mutex_unlock(&P->mu); break; } /* another align thread met the end marker */
+		pthread_mutex_unlock(&P->mu);
+		if (P->n[slot]) align_range(P->recs[slot], P->n[slot], A->flat, &A->t_toseq, 1);
+		if (P->n[slot] == 0) { pthread_mutex_lock(&P->mu); P->align_done = 1; pthread_mutex_unlock(&P->mu); }
+		P1_SET(P, slot, SL_ALIGNED);
+		if (P->n[slot] == 0) break;
+	}
+	return 0;
+}
+
 void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_infos) *iinfos)
 {
 	const size_t B = batch_records();
@@ -945,7 +977,6 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	double t_toseq = 0, t_init;
 	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
 	pthread_t init_th, read_th, pos_th, store_th, destroy_th;
-	unsigned q;
 	int s;
 	memset(&P, 0, sizeof(P));
 	pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
@@ -960,12 +991,18 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	pthread_create(&destroy_th, 0, stage_destroy, &P);
 	pthread_join(init_th, 0);
 	t_init = now() - P.t0;
-	for (q = 0;; ++q) { /* the align stage */
-		const int slot = (int)(q % P1_SLOTS);
-		P1_WAIT(&P, slot, SL_READ);
-		if (P.n[slot]) align_range(P.recs[slot], P.n[slot], flat, &t_toseq, 1);
-		P1_SET(&P, slot, SL_ALIGNED);
-		if (P.n[slot] == 0) break;
+	{ /* the align stage: N_ALIGN threads take the batches in turn, so that one batch's device call (its host-side packing, its
+	   * kernels' straggler tail, its unpacking) overlaps the next one's -- the library runs them on different lane groups */
+		align_arg_t aa[MAX_ALIGN];
+		pthread_t ath[MAX_ALIGN];
+		const int na = align_threads();
+		int a;
+		for (a = 0; a < na; ++a) {
+			aa[a].P = &P; aa[a].id = a; aa[a].n = na; aa[a].t_toseq = 0;
+			aa[a].flat = a == 0 ? flat : (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
+			pthread_create(&ath[a], 0, stage_align, &aa[a]);
+		}
+		for (a = 0; a < na; ++a) { pthread_join(ath[a], 0); t_toseq += aa[a].t_toseq; if (a) free(aa[a].flat); }
 	}
 	pthread_join(read_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0); pthread_join(destroy_th, 0);
 	for (s = 0; s < P1_SLOTS; ++s) free(P.recs[s]);

@@ -21,6 +21,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
+#include <condition_variable>
 #include <string>
 #include <thread>
 #include <vector>
@@ -71,8 +73,10 @@ int hostprep_fail(const char *fmt, ...)
 
 extern "C" const char *bwa_gpu_last_error(void)
 {
+	static thread_local std::string copy; // the caller's own copy: another thread may fail (and rewrite g_err) at any time
 	std::lock_guard<std::mutex> g(g_err_mu);
-	return g_err.c_str();
+	copy = g_err;
+	return copy.c_str();
 }
 
 // ------------------------------------------------------------------ buffers
@@ -180,9 +184,20 @@ static bwa_gpu_totals_t g_tot = {};
 static std::mutex g_tot_mu;
 #define TOT(stmt) do { std::lock_guard<std::mutex> tg_(g_tot_mu); stmt; } while (0)
 
-static std::vector<Ctx *> g_ctx;
+static std::vector<Ctx *> g_ctx; // search lanes, device by device
+static std::vector<Ctx *> g_svc; // one service lane per device: K4, K5, K6
 static bool g_stats_enabled = false;
-static std::mutex g_mu;
+// Locks.  g_life: the contexts exist and keep their index while a call holds it shared; init / destroy / load take it
+// exclusively.  Calls of different kinds do not wait for each other: the search calls take a GROUP of lanes (BWAGPU_CALL_GROUPS
+// groups per device, default 1: one search call at a time), K4 / K5 / K6 run on a service lane of their own under g_svc_mu,
+// the BGZF codec has its own stream (bgzf.cu).  The measurement entry points (resident_*, probe) take g_life exclusively.
+static std::shared_mutex g_life;
+static std::mutex g_svc_mu, g_flat_mu, g_grp_mu;
+static std::condition_variable g_grp_cv;
+static int g_groups = 1;
+static std::vector<char> g_grp_busy;
+#define LIFE_SHARED std::shared_lock<std::shared_mutex> life_(g_life)
+#define LIFE_EXCLUSIVE std::unique_lock<std::shared_mutex> life_(g_life)
 static std::vector<uint4> g_flat_pool; // result pool of the last flat call (multi-device concat)
 
 static uint32_t env_u32(const char *name, uint32_t dflt)
@@ -193,7 +208,7 @@ static uint32_t env_u32(const char *name, uint32_t dflt)
 
 namespace bwagpu {
 void bgzf_release(); // bgzf.cu
-int primary_device() { std::lock_guard<std::mutex> g(g_mu); return g_ctx.empty() ? -1 : g_ctx[0]->dev; }
+int primary_device() { LIFE_SHARED; return g_ctx.empty() ? -1 : g_ctx[0]->dev; }
 void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out)
 {
 	TOT(g_tot.launches += launches; g_tot.ms_bgzf += ms; g_tot.bgzf_bytes_in += bytes_in; g_tot.bgzf_bytes_out += bytes_out;
@@ -205,8 +220,10 @@ void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out)
 extern "C" void bwa_gpu_destroy(void)
 {
 	bwagpu::bgzf_release();
-	std::lock_guard<std::mutex> g(g_mu);
-	for (Ctx *c : g_ctx) {
+	LIFE_EXCLUSIVE;
+	std::vector<Ctx *> all(g_ctx);
+	all.insert(all.end(), g_svc.begin(), g_svc.end());
+	for (Ctx *c : all) {
 		cudaSetDevice(c->dev);
 		cudaDeviceSynchronize();
 		if (!c->owner) {
@@ -228,13 +245,14 @@ extern "C" void bwa_gpu_destroy(void)
 		delete c;
 	}
 	g_ctx.clear();
+	g_svc.clear();
 	std::vector<uint4>().swap(g_flat_pool);
 }
 
 extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 {
 	bwa_gpu_destroy();
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE;
 	{
 		// The struct API hands every read a libc-allocated aln[] (the caller free()s it, bwaseqio.c:259): 10 M small blocks per call.
 		// With glibc's defaults the heaps are trimmed when the caller frees them and grown again 128 KB at a time on the next
@@ -268,7 +286,7 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 		}
 		const int lanes = (int)env_u32("BWAGPU_LANES", 3);
 		Ctx *first = nullptr;
-		for (int ln = 0; ln < lanes; ++ln) {
+		for (int ln = 0; ln <= lanes; ++ln) { // the last one is the device's service lane
 			Ctx *c = new Ctx();
 			c->dev = id;
 			c->lane = ln;
@@ -277,9 +295,11 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 			c->n_sm = prop.multiProcessorCount;
 			CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
 			for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-			g_ctx.push_back(c);
+			if (ln < lanes) g_ctx.push_back(c); else g_svc.push_back(c);
 		}
+		g_groups = (int)std::min<uint32_t>(env_u32("BWAGPU_CALL_GROUPS", 1), (uint32_t)lanes);
 	}
+	g_grp_busy.assign((size_t)g_groups, 0);
 	return 0;
 }
 
@@ -362,10 +382,13 @@ static int upload_index_one(Ctx *c, bwt_t *const bwt[2], const ubyte_t *pac, int
 
 extern "C" int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64_t l_pac)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE;
 	if (g_ctx.empty()) return fail("bwa_gpu_load_index: call bwa_gpu_init first");
+	if (!bwt || !bwt[0] || !bwt[1]) return fail("bwa_gpu_load_index: bwt[0] / bwt[1] is NULL");
 	if (bwt[0]->seq_len != bwt[1]->seq_len) return fail("forward and reverse index differ in seq_len");
-	for (Ctx *c : g_ctx) {
+	std::vector<Ctx *> all(g_ctx);
+	all.insert(all.end(), g_svc.begin(), g_svc.end());
+	for (Ctx *c : all) {
 		if (!c->owner) { if (upload_index_one(c, bwt, pac, l_pac)) return 1; }
 		else { // sibling lane: same device, same index arrays
 			const Ctx *o = c->owner;
@@ -380,10 +403,12 @@ extern "C" int bwa_gpu_load_index(bwt_t *const bwt[2], const ubyte_t *pac, int64
 
 extern "C" int bwa_gpu_load_pac(const ubyte_t *pac, int64_t l_pac)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE;
 	if (g_ctx.empty()) return fail("bwa_gpu_load_pac: call bwa_gpu_init first");
 	if (!pac || l_pac <= 0) return fail("bwa_gpu_load_pac: bad argument");
-	for (Ctx *c : g_ctx) {
+	std::vector<Ctx *> all(g_ctx);
+	all.insert(all.end(), g_svc.begin(), g_svc.end());
+	for (Ctx *c : all) {
 		if (c->owner) { c->pac.p = c->owner->pac.p; c->l_pac = l_pac; c->has_pac = true; continue; }
 		CK(cudaSetDevice(c->dev));
 		const size_t nb = (size_t)(l_pac / 4 + 1);
@@ -986,15 +1011,44 @@ static int run_range(Ctx *c, FlatJob &J)
 }
 
 // splits [0,n) over the devices, cuts each device's range into chunks, one host thread per lane
+// a search call's lanes: group g of every device (lane l of a device with L lanes belongs to group l * G / L)
+struct LaneGroup {
+	int g = -1;
+	LaneGroup()
+	{
+		std::unique_lock<std::mutex> lk(g_grp_mu);
+		for (;;) {
+			for (int k = 0; k < g_groups; ++k)
+				if (!g_grp_busy[(size_t)k]) { g = k; break; }
+			if (g >= 0) break;
+			g_grp_cv.wait(lk);
+		}
+		g_grp_busy[(size_t)g] = 1;
+	}
+	~LaneGroup()
+	{
+		{ std::lock_guard<std::mutex> lk(g_grp_mu); g_grp_busy[(size_t)g] = 0; }
+		g_grp_cv.notify_one();
+	}
+};
+
+static bool lane_in_group(const Ctx *c, int g)
+{
+	int lanes = 0;
+	for (const Ctx *o : g_ctx) if (o->dev == c->dev) ++lanes;
+	return c->lane * g_groups / lanes == g;
+}
+
 static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *seqs, const gap_opt_t *opt,
-                   int32_t *n_aln, int32_t *max_entries, std::vector<std::unique_ptr<FlatJob>> &jobs)
+                   int32_t *n_aln, int32_t *max_entries, std::vector<std::unique_ptr<FlatJob>> &jobs, int group)
 {
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
-	std::vector<Ctx *> owners;
+	std::vector<Ctx *> owners, mine;
 	for (Ctx *c : g_ctx) if (!c->owner) owners.push_back(c);
+	for (Ctx *c : g_ctx) if (lane_in_group(c, group)) mine.push_back(c);
 	const int nd = (int)owners.size();
 	jobs.clear();
-	for (Ctx *c : g_ctx) { c->stats = bwa_gpu_stats_t(); c->stats.n_devices = nd; }
+	for (Ctx *c : mine) { c->stats = bwa_gpu_stats_t(); c->stats.n_devices = nd; }
 	const size_t CH = chunk_reads();
 	std::vector<std::thread> th;
 	for (int d = 0; d < nd; ++d) {
@@ -1007,7 +1061,7 @@ static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *
 		if (seqs) J.seqs = seqs + lo;
 		else { J.bases = bases; J.offs = offs + lo; }
 		std::vector<Ctx *> lanes;
-		for (Ctx *c : g_ctx) if (c == owners[d] || c->owner == owners[d]) lanes.push_back(c);
+		for (Ctx *c : mine) if (c == owners[d] || c->owner == owners[d]) lanes.push_back(c);
 		const size_t L = lanes.size();
 		// ramp up (the device starts working after a short first pack) and ramp down (a short last unpack)
 		const size_t floor_sz = std::min<size_t>(CH, 65536);
@@ -1040,7 +1094,7 @@ static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *
 	for (auto &t : th) t.join();
 	{
 		int64_t l = 0;
-		for (Ctx *c : g_ctx) l += c->stats.launches;
+		for (Ctx *c : mine) l += c->stats.launches;
 		TOT(g_tot.launches += l);
 	}
 	for (int d = 0; d < nd; ++d)
@@ -1051,10 +1105,13 @@ static int run_all(int n, const uint8_t *bases, const int64_t *offs, bwa_seq_t *
 extern "C" int bwa_gpu_aln_flat(int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt, int32_t *n_aln,
                                 int32_t *max_entries, int64_t *aln_off, const bwt_aln1_t **aln_pool)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_SHARED;
+	std::lock_guard<std::mutex> fg(g_flat_mu); // the result pool of the flat call is one per process
 	if (n < 0 || !opt || !n_aln || !max_entries || !aln_off || !aln_pool) return fail("bwa_gpu_aln_flat: bad argument");
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
 	std::vector<std::unique_ptr<FlatJob>> jobs;
-	if (run_all(n, bases, offs, nullptr, opt, n_aln, max_entries, jobs)) return 1;
+	LaneGroup grp;
+	if (run_all(n, bases, offs, nullptr, opt, n_aln, max_entries, jobs, grp.g)) return 1;
 	int64_t acc = 0;
 	for (int i = 0; i < n; ++i) { aln_off[i] = acc; acc += n_aln[i]; }
 	aln_off[n] = acc;
@@ -1069,11 +1126,19 @@ extern "C" int bwa_gpu_aln_flat(int n, const uint8_t *bases, const int64_t *offs
 
 extern "C" int bwa_gpu_cal_sa_reads_gap(int n_seqs, bwa_seq_t *seqs, const gap_opt_t *opt)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_SHARED;
 	if (n_seqs < 0 || !opt || (n_seqs && !seqs)) return fail("bwa_gpu_cal_sa_reads_gap: bad argument");
+	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
+	// what bwa_cal_sa_reg_gap does to every read up front (bwtaln.c:113): a caller that cleans up after an error must not find
+	// stale pointers
+	for (int i = 0; i < n_seqs; ++i) { seqs[i].aln = 0; seqs[i].n_aln = 0; }
 	std::vector<int32_t> n_aln(n_seqs), max_entries(n_seqs);
 	std::vector<std::unique_ptr<FlatJob>> jobs;
-	if (run_all(n_seqs, nullptr, nullptr, seqs, opt, n_aln.data(), max_entries.data(), jobs)) return 1;
+	LaneGroup grp;
+	if (run_all(n_seqs, nullptr, nullptr, seqs, opt, n_aln.data(), max_entries.data(), jobs, grp.g)) {
+		for (int i = 0; i < n_seqs; ++i) { free(seqs[i].aln); seqs[i].aln = 0; seqs[i].n_aln = 0; } // hand nothing half-done back
+		return 1;
+	}
 	return 0;
 }
 
@@ -1085,6 +1150,7 @@ extern "C" void bwa_gpu_free_alns(int n_seqs, bwa_seq_t *seqs)
 extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 {
 	if (!out) return fail("bwa_gpu_get_stats: null");
+	LIFE_SHARED;
 	bwa_gpu_stats_t s = bwa_gpu_stats_t();
 	for (Ctx *c : g_ctx) {
 		const bwa_gpu_stats_t &t = c->stats;
@@ -1100,6 +1166,7 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 		for (int q = 0; q < 4; ++q) s.ms_tier[q] = std::max(s.ms_tier[q], t.ms_tier[q]);
 		s.x_chunks_used = std::max(s.x_chunks_used, t.x_chunks_used);
 	}
+	for (Ctx *c : g_svc) s.ms_sw_kernel = std::max(s.ms_sw_kernel, c->stats.ms_sw_kernel);
 	s.n_devices = 0;
 	for (Ctx *c : g_ctx) if (!c->owner) ++s.n_devices;
 	*out = s;
@@ -1109,7 +1176,7 @@ extern "C" int bwa_gpu_get_stats(bwa_gpu_stats_t *out)
 // ------------------------------------------------------------------ measurement: random-sector gather ceiling
 extern "C" int bwa_gpu_probe_random_sectors(int64_t buffer_bytes, int chains, int steps, double *gb_per_s)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE; // measurement: alone on the device
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
 	if (!gb_per_s || buffer_bytes < (1 << 20) || steps < 1) return fail("bwa_gpu_probe_random_sectors: bad arguments");
 	Ctx *c = g_ctx[0];
@@ -1147,7 +1214,7 @@ extern "C" int bwa_gpu_probe_random_sectors(int64_t buffer_bytes, int chains, in
 // ------------------------------------------------------------------ resident batch (kernel-only timing)
 extern "C" int bwa_gpu_resident_stage(int n, const uint8_t *bases, const int64_t *offs, const gap_opt_t *opt)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE; // measurement: alone on the device
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
 	Ctx *c = g_ctx[0];
 	CK(cudaSetDevice(c->dev));
@@ -1180,7 +1247,7 @@ extern "C" int bwa_gpu_resident_stage(int n, const uint8_t *bases, const int64_t
 
 extern "C" int bwa_gpu_resident_run(double *ms)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE; // measurement: alone on the device
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called");
 	Ctx *c = g_ctx[0];
 	if (!c->res_valid) return fail("bwa_gpu_resident_run: nothing staged");
@@ -1205,7 +1272,7 @@ extern "C" int bwa_gpu_resident_run(double *ms)
 
 extern "C" int bwa_gpu_resident_fetch(int32_t *n_aln, int32_t *max_entries, int64_t *aln_off, const bwt_aln1_t **aln_pool)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_EXCLUSIVE; // measurement: alone on the device
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called");
 	Ctx *c = g_ctx[0];
 	if (!c->res_valid) return fail("bwa_gpu_resident_fetch: nothing staged");
@@ -1226,14 +1293,15 @@ extern "C" int bwa_gpu_resident_fetch(int32_t *n_aln, int32_t *max_entries, int6
 // ------------------------------------------------------------------ K4
 extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint8_t *which, bwtint_t *out_sa)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_SHARED;
+	std::lock_guard<std::mutex> sg(g_svc_mu);
 	if (g_ctx.empty()) return fail("bwa_gpu_init has not been called (no CPU fallback)");
 	if (n < 0 || (n && (!sa_idx || !which || !out_sa))) return fail("bwa_gpu_cal_pac_pos: bad argument");
-	const int nd = (int)g_ctx.size();
+	const int nd = (int)g_svc.size(); // the queries are split over the devices' service lanes
 	std::vector<int> rc(nd, 0);
 	std::vector<std::string> errs(nd);
 	auto work = [&](int d) -> int {
-		Ctx *c = g_ctx[d];
+		Ctx *c = g_svc[d];
 		CK(cudaSetDevice(c->dev));
 		if (!c->has_index || !c->has_sa) return fail("no suffix array loaded (bwt->sa was NULL in bwa_gpu_load_index)");
 		const int64_t lo = n * d / nd, hi = n * (d + 1) / nd;
@@ -1264,7 +1332,7 @@ extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint
 	std::vector<std::thread> th;
 	for (int d = 0; d < nd; ++d) th.emplace_back([&, d]() { rc[d] = work(d); if (rc[d]) errs[d] = t_err; });
 	for (auto &t : th) t.join();
-	for (int d = 0; d < nd; ++d) if (rc[d]) return fail("device %d: %s", g_ctx[d]->dev, errs[d].c_str());
+	for (int d = 0; d < nd; ++d) if (rc[d]) return fail("device %d: %s", g_svc[d]->dev, errs[d].c_str());
 	return 0;
 }
 
@@ -1276,10 +1344,11 @@ static std::vector<uint16_t> g_cigar_pool_sw, g_cigar_pool_ga;
 static int sw_entry(int n, const bwa_gpu_sw_job_t *jobs, int mode, int gap_end, int band, bwa_gpu_sw_res_t *res,
                     bwa_gpu_path_res_t *pres, const bwa_cigar_t **cigar_pool, const char *who)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_SHARED;
+	std::lock_guard<std::mutex> sg(g_svc_mu);
 	if (g_ctx.empty()) return fail("%s: bwa_gpu_init has not been called (no CPU fallback)", who);
 	if (n < 0 || (n && (!jobs || (mode == 0 && !res) || (mode != 0 && (!pres || !cigar_pool))))) return fail("%s: bad argument", who);
-	Ctx *c = g_ctx[0];
+	Ctx *c = g_svc[0];
 	CK(cudaSetDevice(c->dev));
 	if (!c->has_pac) return fail("%s: no packed reference loaded (pac was NULL in bwa_gpu_load_index)", who);
 	double ms[2] = {0, 0};
@@ -1315,11 +1384,12 @@ extern "C" int bwa_gpu_global_align(int n, const bwa_gpu_sw_job_t *jobs, int gap
 extern "C" int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, int band, bwa_gpu_path_res_t *res,
                                          const bwa_cigar_t **cigar_pool)
 {
-	std::lock_guard<std::mutex> g(g_mu);
+	LIFE_SHARED;
+	std::lock_guard<std::mutex> sg(g_svc_mu);
 	if (g_ctx.empty()) return fail("bwa_gpu_global_align_seqs: bwa_gpu_init has not been called (no CPU fallback)");
 	if (band < 1) return fail("bwa_gpu_global_align_seqs: band must be >= 1");
 	if (n < 0 || (n && (!jobs || !res || !cigar_pool))) return fail("bwa_gpu_global_align_seqs: bad argument");
-	Ctx *c = g_ctx[0];
+	Ctx *c = g_svc[0];
 	CK(cudaSetDevice(c->dev));
 	double ms = 0;
 	SwCounts cnt;

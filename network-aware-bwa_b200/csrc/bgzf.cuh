@@ -9,7 +9,8 @@
 //   0. the block's input (<= 65280 bytes) is loaded once; CRC-32 by 256 partial CRCs combined with x^(8 L 2^k) mod P;
 //   1. LZ77, greedy (the reference's level 2 is zlib's deflate_fast): positions are taken 256 at a time --
 //      A  warp 0 walks the 256 positions in order, 32 per step, through a 16 K-entry hash-head table of 4-byte strings:
-//         candidate = the most recent earlier position with the same hash (__match_any_sync finds it inside the step),
+//         candidate = the most recent earlier position with the same hash (__match_any_sync finds it inside the step);
+//         the hashes themselves were computed by all threads while the previous batch was being emitted,
 //      B  every thread extends its candidate (4 bytes per compare) -> match length / distance of its position,
 //      C  the greedy parse -- "emit a token at p, continue at p + max(1, len)" -- is a pointer chain; the positions on
 //         the chain from the carried-in start are found by pointer doubling (8 rounds for 256 positions),
@@ -41,7 +42,7 @@ struct Smem {
 	uint32_t lit_freq[288], dist_freq[32], cl_freq[20];
 	uint16_t lit_code[288], dist_code[32], cl_code[20];
 	uint8_t lit_len[288], dist_len[32], cl_len[20];
-	uint16_t cand[T], jump[2][T + 2];
+	uint16_t cand[T], hash[T], jump[2][T + 2];
 	uint8_t mark[T + 4];
 	uint32_t wsum[8];
 	// Huffman construction
@@ -253,6 +254,13 @@ __device__ __forceinline__ uint32_t block_scan(Smem &s, uint32_t v, uint32_t &to
 	return before + inc - v;
 }
 
+// hash of the 4 bytes at p for the head table; positions too close to the end get a value no table entry and no other lane has
+__device__ __forceinline__ uint32_t pos_hash(const Smem &s, int p, int len)
+{
+	if (p + MIN_MATCH > len) return 0x4000u + (threadIdx.x & 31);
+	return (ld4(s.buf, p) * 2654435761u) >> (32 - HBITS);
+}
+
 // ---------------------------------------------------------------- one BGZF block
 __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, int level, uint8_t *__restrict__ out, int32_t *clen,
                               uint32_t *__restrict__ tok, const uint32_t *x2n)
@@ -296,6 +304,7 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 			c = s.crc_tab[(c ^ b) & 0xff] ^ (c >> 8);
 		}
 		s.crc_part[t] = c;
+		s.hash[t] = (uint16_t)pos_hash(s, t, len); // the first batch's hashes (phase A reads them after the barriers below)
 		if (t == 0) {
 			uint32_t p = crc_x2n(x2n, (uint32_t)L, 3); // x^(8 L)
 			for (int k = 0; k < 8; ++k) { s.crc_pow[k] = p; p = crc_mulmod(p, p); }
@@ -319,17 +328,20 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 	int cur = 0;
 	if (level > 0)
 		for (int base = 0; base < len; base += T) {
-			if (warp == 0) { // A
+			if (warp == 0) { // A: the hashes were computed by all threads during the previous batch; only the table walk is serial
+				uint32_t hq[T / 32];
+				unsigned sameq[T / 32];
+#pragma unroll
+				for (int sub = 0; sub < T / 32; ++sub) hq[sub] = s.hash[sub * 32 + lane];
+#pragma unroll
+				for (int sub = 0; sub < T / 32; ++sub) sameq[sub] = __match_any_sync(0xffffffffu, hq[sub]);
+#pragma unroll
 				for (int sub = 0; sub < T / 32; ++sub) {
 					const int p = base + sub * 32 + lane;
-					const bool valid = p + MIN_MATCH <= len;
-					uint32_t h = 0x10000u + lane, c = NONE;
-					if (valid) {
-						h = (ld4(s.buf, p) * 2654435761u) >> (32 - HBITS);
-						c = s.head[h];
-					}
-					const unsigned same = __match_any_sync(0xffffffffu, h);
-					const unsigned lower = same & ((1u << lane) - 1);
+					const uint32_t h = hq[sub];
+					const bool valid = h < (1u << HBITS);
+					const unsigned same = sameq[sub], lower = same & ((1u << lane) - 1);
+					uint32_t c = valid ? s.head[h] : NONE;
 					if (valid && lower) c = (uint32_t)(p - lane + (31 - __clz(lower)));
 					if (valid && (same >> lane) == 1u) s.head[h] = (uint16_t)p; // the last position of the step with this hash
 					s.cand[sub * 32 + lane] = (uint16_t)c;
@@ -368,6 +380,7 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 			// D
 			const bool is_tok = s.mark[t] != 0 && p < len;
 			if (is_tok && t + step >= T) s.cur = p + step;
+			s.hash[t] = (uint16_t)pos_hash(s, p + T, len); // the next batch's (warp 0 is done with this batch's since phase A)
 			uint32_t total;
 			const uint32_t at = ntok + block_scan(s, is_tok ? 1u : 0u, total);
 			ntok += total;

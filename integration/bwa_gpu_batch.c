@@ -80,13 +80,13 @@ static void die(const char *what)
  * itself runs these functions concurrently in its worker threads (run_worker_thread, bam2bam.c:1387), so they are
  * re-entrant; the shim spreads each such phase of a batch over BWAGPU_SHIM_THREADS threads (default: the host's cores, at
  * most 64).  Everything order-sensitive (drand48 in bwa_aln2seq_core, the position cache, isize statistics) stays serial. */
-typedef struct { size_t n, grain; size_t next; pf_fn fn; void *ctx; int bucket; } pf_job_t;
+typedef struct { size_t n, grain; volatile size_t next; pf_fn fn; void *ctx; int bucket; int helpers; } pf_job_t;
 #define MAX_THREADS 64
 
 __thread int t_cpu_bucket = CPU_OTHER;
 static int64_t g_cpu_ns[CPU_N];
 static const char *const g_cpu_name[CPU_N] = {"inflate", "parse", "bam1_to_seq", "aln2seq (serial)", "cal_pac_pos_core", "isize", "store/encode", "destroy",
-	"load/decode", "enumerate", "pairing", "XA aln2seq (serial)", "rescue record", "rescue replay", "refine record", "refine replay + update_bam1",
+	"load/decode", "enumerate", "pairing", "XA aln2seq", "rescue record", "rescue replay", "refine record", "refine replay + update_bam1",
 	"BAM layout", "deflate", "fwrite", "other"};
 
 double thread_cpu_now(void)
@@ -122,9 +122,20 @@ int shim_threads(void)
 	return n;
 }
 
-static void *pf_worker(void *arg)
+/* A pool of shim_threads() - 1 workers that lives as long as the process (the caller of a job is its remaining thread).
+ * Several stage threads post jobs at the same time; a worker takes index ranges from whichever posted job still has some.
+ * Threads that stay alive keep their malloc caches, which the reference's record functions (a dozen small blocks per
+ * record) lean on; a thread per parallel_for call gave every call cold caches and a round of arena hand-offs. */
+#define POOL_JOBS 32
+static struct {
+	pthread_mutex_t mu;
+	pthread_cond_t work, done;
+	pf_job_t *job[POOL_JOBS];
+	int started, n_workers;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0};
+
+static void pf_run(pf_job_t *j) /* index ranges of j until none is left */
 {
-	pf_job_t *j = (pf_job_t *)arg;
 	const double c0 = thread_cpu_now();
 	for (;;) {
 		const size_t lo = __sync_fetch_and_add(&j->next, j->grain);
@@ -134,19 +145,60 @@ static void *pf_worker(void *arg)
 		for (i = lo; i < hi; ++i) j->fn(i, j->ctx);
 	}
 	cpu_add(j->bucket, thread_cpu_now() - c0);
+}
+
+static void *pool_worker(void *arg)
+{
+	(void)arg;
+	pthread_mutex_lock(&g_pool.mu);
+	for (;;) {
+		pf_job_t *j = 0;
+		int k;
+		for (k = 0; k < POOL_JOBS; ++k)
+			if (g_pool.job[k] && g_pool.job[k]->next < g_pool.job[k]->n) { j = g_pool.job[k]; break; }
+		if (!j) { pthread_cond_wait(&g_pool.work, &g_pool.mu); continue; }
+		++j->helpers;
+		pthread_mutex_unlock(&g_pool.mu);
+		pf_run(j);
+		pthread_mutex_lock(&g_pool.mu);
+		if (--j->helpers == 0) pthread_cond_broadcast(&g_pool.done);
+	}
 	return 0;
+}
+
+static void pool_start(void) /* g_pool.mu held */
+{
+	int t;
+	g_pool.started = 1;
+	g_pool.n_workers = shim_threads() - 1;
+	for (t = 0; t < g_pool.n_workers; ++t) {
+		pthread_t th;
+		pthread_attr_t at;
+		pthread_attr_init(&at);
+		pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+		if (pthread_create(&th, &at, pool_worker, 0) != 0) { g_pool.n_workers = t; break; }
+		pthread_attr_destroy(&at);
+	}
 }
 
 void parallel_for(size_t n, size_t grain, pf_fn fn, void *ctx)
 {
-	pf_job_t j = {n, grain ? grain : 1, 0, fn, ctx, t_cpu_bucket};
-	pthread_t th[MAX_THREADS];
-	int t, nt = shim_threads();
-	if ((size_t)nt > (n + j.grain - 1) / j.grain) nt = (int)((n + j.grain - 1) / j.grain);
-	if (nt <= 1) { pf_worker(&j); return; }
-	for (t = 1; t < nt; ++t) pthread_create(&th[t], 0, pf_worker, &j);
-	pf_worker(&j);
-	for (t = 1; t < nt; ++t) pthread_join(th[t], 0);
+	pf_job_t j = {n, grain ? grain : 1, 0, fn, ctx, t_cpu_bucket, 0};
+	int k, slot = -1;
+	if (n == 0) return;
+	if ((n + j.grain - 1) / j.grain <= 1 || shim_threads() <= 1) { pf_run(&j); return; }
+	pthread_mutex_lock(&g_pool.mu);
+	if (!g_pool.started) pool_start();
+	for (k = 0; k < POOL_JOBS; ++k)
+		if (!g_pool.job[k]) { slot = k; break; }
+	if (slot >= 0) { g_pool.job[slot] = &j; pthread_cond_broadcast(&g_pool.work); }
+	pthread_mutex_unlock(&g_pool.mu);
+	pf_run(&j); /* (no free slot: the caller does it all) */
+	if (slot < 0) return;
+	pthread_mutex_lock(&g_pool.mu);
+	g_pool.job[slot] = 0; /* no new helper can find it; wait for the ones inside */
+	while (j.helpers) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+	pthread_mutex_unlock(&g_pool.mu);
 }
 
 int slice_count(size_t n, size_t min_per_slice)
@@ -157,27 +209,19 @@ int slice_count(size_t n, size_t min_per_slice)
 	return nt < 1 ? 1 : (int)nt;
 }
 
-typedef struct { ps_fn fn; void *ctx; size_t n; int nt, s, bucket; } ps_arg_t;
-static void *ps_worker(void *arg)
+/* n items cut into slice_count() contiguous slices, fn(slice, lo, hi) once per slice on the pool; returns the slice count */
+typedef struct { ps_fn fn; void *ctx; size_t n; int nt; } ps_arg_t;
+static void ps_one(size_t s, void *arg)
 {
-	ps_arg_t *a = (ps_arg_t *)arg;
-	const double c0 = thread_cpu_now();
-	a->fn(a->s, a->n * (size_t)a->s / (size_t)a->nt, a->n * (size_t)(a->s + 1) / (size_t)a->nt, a->ctx);
-	cpu_add(a->bucket, thread_cpu_now() - c0);
-	return 0;
+	const ps_arg_t *a = (const ps_arg_t *)arg;
+	a->fn((int)s, a->n * s / (size_t)a->nt, a->n * (s + 1) / (size_t)a->nt, a->ctx);
 }
 
 int parallel_slices(size_t n, size_t min_per_slice, ps_fn fn, void *ctx)
 {
-	const int nt = slice_count(n, min_per_slice);
-	ps_arg_t a[MAX_THREADS];
-	pthread_t th[MAX_THREADS];
-	int s;
-	for (s = 0; s < nt; ++s) { a[s].fn = fn; a[s].ctx = ctx; a[s].n = n; a[s].nt = nt; a[s].s = s; a[s].bucket = t_cpu_bucket; }
-	for (s = 1; s < nt; ++s) pthread_create(&th[s], 0, ps_worker, &a[s]);
-	ps_worker(&a[0]);
-	for (s = 1; s < nt; ++s) pthread_join(th[s], 0);
-	return nt;
+	ps_arg_t a = {fn, ctx, n, slice_count(n, min_per_slice)};
+	parallel_for((size_t)a.nt, 1, ps_one, &a);
+	return a.nt;
 }
 
 /* ------------------------------------------------------------------ the reference's static globals, captured */
@@ -1219,34 +1263,67 @@ static void xa_assign_slice(int s, size_t lo, size_t hi, void *ctx)
 	}
 }
 
-/* B: pairing on the host threads, then the hit lists for XA in record order (bwa_aln2seq_core consumes drand48) and their rows */
-static void stage_pairing(batch2_t *b)
+/* the XA hit lists of one record (bam2bam.c:771-784).  bwa_aln2seq_core is called with set_main = 0 here, and in that form
+ * it consumes no random numbers: its sampling branch (bwase.c:74-86) needs a hit group larger than `rest`, and `rest` starts
+ * as the sum of all groups (n_occ <= n_multi + 1, else the function has returned at bwase.c:57).  So, unlike the primary-hit
+ * selection of pass 1, these calls do not have to run in record order. */
+static void xa_core_one(size_t i, void *ctx)
 {
+	batch2_t *b = (batch2_t *)ctx;
+	bam_pair_t *r = &b->recs[i];
+	bwa_seq_t *p[2];
+	size_t cnt = 0;
+	int j;
+	b->voff[i] = 0;
+	if (!is_pair_job(r) || !(g_pe->N_multi || g_pe->n_multi)) return;
+	p[0] = &r->bwa_seq[0]; p[1] = &r->bwa_seq[1];
+	for (j = 0; j < 2; ++j)
+		if (p[j]->type != BWA_TYPE_NO_MATCH) {
+			if (!(p[j]->extra_flag & SAM_FPP) && p[1 - j]->type != BWA_TYPE_NO_MATCH)
+				bwa_aln2seq_core(p[j]->n_aln, p[j]->aln, p[j], 0, p[j]->c1 + p[j]->c2 - 1 > g_pe->N_multi ? g_pe->n_multi : g_pe->N_multi);
+			else bwa_aln2seq_core(p[j]->n_aln, p[j]->aln, p[j], 0, g_pe->n_multi);
+			cnt += (size_t)p[j]->n_multi;
+		}
+	b->voff[i] = cnt; /* turned into an offset by stage_pairing */
+}
+
+static void xa_rows_slice(int s, size_t lo, size_t hi, void *ctx) /* the SA rows of the lists, at their records' offsets in q2 */
+{
+	batch2_t *b = (batch2_t *)ctx;
 	size_t i;
 	int j, k;
+	(void)s;
+	for (i = lo; i < hi; ++i) {
+		bam_pair_t *r = &b->recs[i];
+		size_t at = b->voff[i];
+		if (b->voff[i + 1] == at) continue;
+		for (j = 0; j < 2; ++j) {
+			const bwa_seq_t *p = &r->bwa_seq[j];
+			if (p->type == BWA_TYPE_NO_MATCH) continue;
+			for (k = 0; k < p->n_multi; ++k, ++at) { b->q2.k[at] = p->multi[k].pos; b->q2.which[at] = (uint8_t)(p->multi[k].strand != 0); }
+		}
+	}
+}
+
+/* B: pairing, the hit lists for XA and their rows, all on the host threads */
+static void stage_pairing(batch2_t *b)
+{
+	size_t i, total = 0;
 	t_cpu_bucket = CPU_PAIRING;
 	parallel_for(b->n_visit, 64, fill_visit_one, b);
 	parallel_for(b->n, 256, pairing_one, b);
-	b->q2.n = 0;
-	const double c0 = thread_cpu_now();
-	for (i = 0; i < b->n; ++i) {
-		bam_pair_t *r = &b->recs[i];
-		bwa_seq_t *p[2];
-		b->voff[i] = b->q2.n;
-		if (!is_pair_job(r) || !(g_pe->N_multi || g_pe->n_multi)) continue; /* bam2bam.c:771-791 */
-		p[0] = &r->bwa_seq[0]; p[1] = &r->bwa_seq[1];
-		for (j = 0; j < 2; ++j)
-			if (p[j]->type != BWA_TYPE_NO_MATCH) {
-				if (!(p[j]->extra_flag & SAM_FPP) && p[1 - j]->type != BWA_TYPE_NO_MATCH)
-					bwa_aln2seq_core(p[j]->n_aln, p[j]->aln, p[j], 0, p[j]->c1 + p[j]->c2 - 1 > g_pe->N_multi ? g_pe->n_multi : g_pe->N_multi);
-				else bwa_aln2seq_core(p[j]->n_aln, p[j]->aln, p[j], 0, g_pe->n_multi);
-				for (k = 0; k < p[j]->n_multi; ++k) saq_push(&b->q2, p[j]->multi[k].pos, p[j]->multi[k].strand);
-			}
-	}
-	b->voff[b->n] = b->q2.n;
-	cpu_add(CPU_XA_SERIAL, thread_cpu_now() - c0);
-	saq_run(&b->q2);
 	t_cpu_bucket = CPU_XA_SERIAL;
+	parallel_for(b->n, 256, xa_core_one, b);
+	for (i = 0; i < b->n; ++i) { const size_t c = b->voff[i]; b->voff[i] = total; total += c; }
+	b->voff[b->n] = total;
+	if (total > b->q2.m) {
+		b->q2.m = total + total / 4 + 1024;
+		b->q2.k = (bwtint_t *)realloc(b->q2.k, b->q2.m * sizeof(bwtint_t));
+		b->q2.which = (uint8_t *)realloc(b->q2.which, b->q2.m);
+	}
+	b->q2.n = total;
+	if (total) parallel_slices(b->n, 4096, xa_rows_slice, b);
+	saq_run(&b->q2);
 	if (b->q2.n) parallel_slices(b->n, 4096, xa_assign_slice, b);
 }
 

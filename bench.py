@@ -449,12 +449,14 @@ def main():
         achieved = 64.0 * fetches / (search_ms / n_rep / 1e3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_search_traffic.json"))).get("dram_bytes_per_launch_c4")
+            # ncu's DRAM bytes of a 2 M-read launch of the same kernel on the same workload, scaled to this launch's reads
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k_search_traffic.json")))["c4"]["dram_bytes_per_read"] * args.aln_reads
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "kernel": "k_search (all passes), timed alone on a resident batch of the workload's reads",
                     "peak_source": peak_src, "algorithmic_bytes": "64 B x occ-block fetches of the reference layout (SURVEY.md §8d)",
+                    "traffic_source": "profiles/k_search_traffic.json c4.dram_bytes_per_read (ncu, 2 M-read launch) x reads_per_launch",
                     "reads_per_launch": args.aln_reads, "fetches_per_read": fetches / args.aln_reads,
                     "own_32B_blocks_per_read": st_counts["own_fetches_search"] / args.aln_reads,
                     "kernel_ms_per_launch": search_ms / n_rep, "width_ms_per_launch": width_ms / n_rep,

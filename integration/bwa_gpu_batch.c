@@ -86,7 +86,7 @@ typedef struct { size_t n, grain; volatile size_t next; pf_fn fn; void *ctx; int
 __thread int t_cpu_bucket = CPU_OTHER;
 static int64_t g_cpu_ns[CPU_N];
 static const char *const g_cpu_name[CPU_N] = {"inflate", "parse", "bam1_to_seq", "aln2seq (serial)", "cal_pac_pos_core", "isize", "store/encode", "destroy",
-	"load/decode", "enumerate", "pairing", "XA aln2seq", "rescue record", "rescue replay", "refine record", "refine replay + update_bam1",
+	"load/decode", "enumerate", "pairing", "XA aln2seq", "rescue record", "rescue replay", "refine record", "refine replay", "update_bam1",
 	"BAM layout", "deflate", "fwrite", "other"};
 
 double thread_cpu_now(void)
@@ -801,8 +801,8 @@ static void position_range(bam_pair_t *recs, size_t n, saq_t *q, size_t **qoff_b
  *   destroy  bam_destroy_pair of the batch (a dozen free()s per record)
  * Every order-sensitive piece of state belongs to exactly one stage, and a stage sees the batches in input order, so the
  * result is what the one-record-at-a-time loop (bam2bam.c:1143-1176) produces. */
-#define P1_SLOTS 8 /* the reader may run this many batches ahead (it does while the device context is created) */
-enum { SL_FREE = 0, SL_READ, SL_ALIGNED, SL_POSITIONED, SL_STORED };
+#define P1_SLOTS 12 /* the reader may run this many batches ahead (it does while the device context is created) */
+enum { SL_FREE = 0, SL_PARSED, SL_READ, SL_ALIGNED, SL_POSITIONED, SL_STORED };
 typedef struct {
 	pthread_mutex_t mu;
 	pthread_cond_t cv;
@@ -814,8 +814,9 @@ typedef struct {
 	bwa_seqio_t *ks;
 	gzFile temporary;
 	khash_t(isize_infos) *iinfos;
-	double t0, t_read, t_host, t_write, t_destroy;
+	double t0, t_read, t_toseq, t_host, t_write, t_destroy[2];
 	long tot_seqs;
+	int destroy_done;
 	int align_done; /* the end marker has reached the align stage */
 } pipe1_t;
 
@@ -850,15 +851,31 @@ static void *stage_read(void *arg)
 		t = now();
 		const double c0 = thread_cpu_now();
 		n = fastin_read_pairs(P->ks, recs, ramp_records(P->B, q), &seqs, g_broken_input, g_drop_aligned);
-		if (n) { /* bam1_to_seq here, so that the align stage is the device call and nothing else */
-			t_cpu_bucket = CPU_TOSEQ;
-			parallel_for(n, 2048, to_seq_one, recs);
-		}
 		P->t_read += now() - t;
 		cpu_add(CPU_PARSE, thread_cpu_now() - c0);
 		P->n[slot] = n; P->seqs[slot] = seqs;
-		P1_SET(P, slot, SL_READ);
+		P1_SET(P, slot, SL_PARSED);
 		if (n == 0) break; /* an empty batch is the end marker; it travels through every stage */
+	}
+	return 0;
+}
+
+static void *stage_toseq(void *arg) /* bam1_to_seq, so that the align stage is the device call and nothing else */
+{
+	pipe1_t *P = (pipe1_t *)arg;
+	unsigned q;
+	for (q = 0;; ++q) {
+		const int slot = (int)(q % P1_SLOTS);
+		double t;
+		P1_WAIT(P, slot, SL_PARSED);
+		t = now();
+		if (P->n[slot]) {
+			t_cpu_bucket = CPU_TOSEQ;
+			parallel_for(P->n[slot], 2048, to_seq_one, P->recs[slot]);
+		}
+		P->t_toseq += now() - t;
+		P1_SET(P, slot, SL_READ);
+		if (P->n[slot] == 0) break;
 	}
 	return 0;
 }
@@ -920,18 +937,23 @@ static void *stage_store(void *arg)
 	return 0;
 }
 
-static void *stage_destroy(void *arg)
+typedef struct { void *P; int id; } destroy1_arg_t;
+static void *stage_destroy(void *arg) /* two threads, whole batches in turn */
 {
-	pipe1_t *P = (pipe1_t *)arg;
+	destroy1_arg_t *A = (destroy1_arg_t *)arg;
+	pipe1_t *P = (pipe1_t *)A->P;
 	unsigned q;
-	for (q = 0;; ++q) {
+	for (q = (unsigned)A->id;; q += 2) {
 		const int slot = (int)(q % P1_SLOTS);
 		double t1;
-		P1_WAIT(P, slot, SL_STORED);
-		if (P->n[slot] == 0) break;
+		pthread_mutex_lock(&P->mu);
+		while (P->state[slot] != SL_STORED && !P->destroy_done) pthread_cond_wait(&P->cv, &P->mu);
+		if (P->state[slot] != SL_STORED) { pthread_mutex_unlock(&P->mu); break; }
+		if (P->n[slot] == 0) { P->destroy_done = 1; pthread_cond_broadcast(&P->cv); pthread_mutex_unlock(&P->mu); break; }
+		pthread_mutex_unlock(&P->mu);
 		t1 = now();
 		destroy_records(P->recs[slot], P->n[slot]);
-		P->t_destroy += now() - t1;
+		P->t_destroy[A->id] += now() - t1;
 		P1_SET(P, slot, SL_FREE);
 	}
 	return 0;
@@ -972,7 +994,8 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	pipe1_t P;
 	double t_toseq = 0, t_init;
 	bwa_seq_t *flat = (bwa_seq_t *)malloc(2 * B * sizeof(bwa_seq_t));
-	pthread_t init_th, read_th, pos_th, store_th, destroy_th;
+	pthread_t init_th, read_th, seq_th, pos_th, store_th, destroy_th[2];
+	destroy1_arg_t da[2];
 	int s;
 	memset(&P, 0, sizeof(P));
 	pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
@@ -982,9 +1005,10 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	/* device context + index upload (seconds) overlap the reading of the first batches */
 	pthread_create(&init_th, 0, ensure_gpu_thread, 0);
 	pthread_create(&read_th, 0, stage_read, &P);
+	pthread_create(&seq_th, 0, stage_toseq, &P);
 	pthread_create(&pos_th, 0, stage_position, &P);
 	pthread_create(&store_th, 0, stage_store, &P);
-	pthread_create(&destroy_th, 0, stage_destroy, &P);
+	for (s = 0; s < 2; ++s) { da[s].P = &P; da[s].id = s; pthread_create(&destroy_th[s], 0, stage_destroy, &da[s]); }
 	pthread_join(init_th, 0);
 	t_init = now() - P.t0;
 	{ /* the align stage: N_ALIGN threads take the batches in turn, so that one batch's device call (its host-side packing, its
@@ -1000,7 +1024,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 		}
 		for (a = 0; a < na; ++a) { pthread_join(ath[a], 0); t_toseq += aa[a].t_toseq; if (a) free(aa[a].flat); }
 	}
-	pthread_join(read_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0); pthread_join(destroy_th, 0);
+	pthread_join(read_th, 0); pthread_join(seq_th, 0); pthread_join(pos_th, 0); pthread_join(store_th, 0); pthread_join(destroy_th[0], 0); pthread_join(destroy_th[1], 0);
 	for (s = 0; s < P1_SLOTS; ++s) free(P.recs[s]);
 	free(flat);
 	pthread_mutex_destroy(&P.mu); pthread_cond_destroy(&P.cv);
@@ -1008,8 +1032,8 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	g_rep.sequences = P.tot_seqs;
 	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, memtemp_records(), memtemp_bytes() / 1048576.0,
 	        memtemp_spilled() ? ", the rest in the temporary file" : "");
-	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each: device init %.2f, read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f, destroy %.2f)\n",
-	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, t_toseq, P.t_host, g_rep.dev_aln_s + g_rep.dev_sa_s, P.t_write, P.t_destroy);
+	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each: device init %.2f, read %.2f, bam1_to_seq %.2f, aln2seq/posn/isize %.2f, device calls %.2f, temp write %.2f, destroy %.2f + %.2f)\n",
+	        __func__, P.tot_seqs, now() - P.t0, t_init, P.t_read, P.t_toseq + t_toseq, P.t_host, g_rep.dev_aln_s + g_rep.dev_sa_s, P.t_write, P.t_destroy[0], P.t_destroy[1]);
 	fprintf(stderr, "[%s] finished cleanly.\n", __func__);
 }
 
@@ -1410,20 +1434,33 @@ static void refine_replay_slice(int s, size_t lo, size_t hi, void *ctx)
 		if (is_pair_job(r)) {
 			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
 			bwa_refine_gapped(g_bns, 1, &r->bwa_seq[1], g_pac, 0);
-			bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
-			bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
-			bwa_free_read_seq1(&r->bwa_seq[1]);
-			bwa_free_read_seq1(&r->bwa_seq[0]);
-		} else if (is_single_job(r)) {
-			bwa_seq_t *p = &r->bwa_seq[0];
-			bwa_refine_gapped(g_bns, 1, p, g_pac, 0);
-			bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
-			bwa_free_read_seq1(p);
-		}
-		if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
+		} else if (is_single_job(r)) bwa_refine_gapped(g_bns, 1, &r->bwa_seq[0], g_pac, 0);
 	}
 	t_ga_mode = RR_REAL;
 	if (t_ga_pos != t_ga_n) { fprintf(stderr, "[bwa_gpu_batch] %zu of %zu global-alignment answers unused\n", t_ga_n - t_ga_pos, t_ga_n); abort(); }
+}
+
+/* E: bwa_update_bam1 (bam2bam.c:804-810), a stage of its own so that it overlaps the next batch's refine */
+static void update_one(size_t i, void *ctx)
+{
+	bam_pair_t *r = (bam_pair_t *)ctx + i;
+	if (is_pair_job(r)) {
+		bwa_update_bam1(&r->bam_rec[0], g_bns, &r->bwa_seq[0], &r->bwa_seq[1], g_gap->mode, g_gap->max_top2);
+		bwa_update_bam1(&r->bam_rec[1], g_bns, &r->bwa_seq[1], &r->bwa_seq[0], g_gap->mode, g_gap->max_top2);
+		bwa_free_read_seq1(&r->bwa_seq[1]);
+		bwa_free_read_seq1(&r->bwa_seq[0]);
+	} else if (is_single_job(r)) {
+		bwa_seq_t *p = &r->bwa_seq[0];
+		bwa_update_bam1(&r->bam_rec[0], g_bns, p, 0, g_gap->mode, g_gap->max_top2);
+		bwa_free_read_seq1(p);
+	}
+	if (r->kind != eof_marker && r->phase == positioned) r->phase = finished;
+}
+
+static void stage_update(batch2_t *b)
+{
+	t_cpu_bucket = CPU_UPDATE;
+	parallel_for(b->n, 1024, update_one, b->recs);
 }
 
 static void stage_refine(batch2_t *b)
@@ -1467,8 +1504,9 @@ static void stage_refine(batch2_t *b)
 
 /* Pass 2 as a pipeline: load -> enumerate (A) -> pairing + XA (B) -> mate rescue (C) -> refine + update (D) -> write,
  * one thread per stage, batches in order.  A owns the position cache, B the random numbers, the writer the output file. */
-#define P2_SLOTS 7
-enum { S2_FREE = 0, S2_LOADED, S2_ENUM, S2_PAIRED, S2_RESCUED, S2_REFINED, S2_WRITTEN };
+#define P2_SLOTS 10
+#define N_DESTROY 2 /* threads freeing finished batches, whole batches in turn (free()s inside ONE batch on several threads fight over the arenas) */
+enum { S2_FREE = 0, S2_LOADED, S2_ENUM, S2_PAIRED, S2_RESCUED, S2_REFINED, S2_UPDATED, S2_WRITTEN };
 typedef struct {
 	pthread_mutex_t mu;
 	pthread_cond_t cv;
@@ -1480,8 +1518,9 @@ typedef struct {
 	khash_t(isize_infos) *iinfos;
 	kh_64_t *my_hash;
 	uint64_t n_tot[2], n_mapped[2];
-	double t0, t_load, t_enum, t_pair, t_rescue, t_refine, t_write, t_destroy;
+	double t0, t_load, t_enum, t_pair, t_rescue, t_refine, t_update, t_write, t_destroy[N_DESTROY];
 	long tot_seqs;
+	int destroy_done;
 } pipe2_t;
 #define P2_WAIT(P, slot, want) slot_wait(&(P)->mu, &(P)->cv, &(P)->state[slot], want)
 #define P2_SET(P, slot, st) slot_set(&(P)->mu, &(P)->cv, &(P)->state[slot], st)
@@ -1509,6 +1548,7 @@ P2_STAGE(stage2_enum, S2_LOADED, S2_ENUM, t_enum, stage_enumerate(b, P->my_hash)
 P2_STAGE(stage2_pair, S2_ENUM, S2_PAIRED, t_pair, stage_pairing(b))
 P2_STAGE(stage2_rescue, S2_PAIRED, S2_RESCUED, t_rescue, stage_rescue(b, P->n_tot, P->n_mapped))
 P2_STAGE(stage2_refine, S2_RESCUED, S2_REFINED, t_refine, stage_refine(b))
+P2_STAGE(stage2_update, S2_REFINED, S2_UPDATED, t_update, stage_update(b))
 
 static void *stage2_write(void *arg)
 {
@@ -1518,7 +1558,7 @@ static void *stage2_write(void *arg)
 		const int slot = (int)(q % P2_SLOTS);
 		batch2_t *b = &P->b[slot];
 		double t1;
-		P2_WAIT(P, slot, S2_REFINED);
+		P2_WAIT(P, slot, S2_UPDATED);
 		if (b->n == 0) { P2_SET(P, slot, S2_WRITTEN); break; }
 		t1 = now();
 		write_records_bam(P->output, b->recs, b->n);
@@ -1530,19 +1570,24 @@ static void *stage2_write(void *arg)
 	return 0;
 }
 
+typedef struct { pipe2_t *P; int id; } destroy2_arg_t;
 static void *stage2_destroy(void *arg) /* the free()s of a written batch, off the writer's thread */
 {
-	pipe2_t *P = (pipe2_t *)arg;
+	destroy2_arg_t *A = (destroy2_arg_t *)arg;
+	pipe2_t *P = A->P;
 	unsigned q;
-	for (q = 0;; ++q) {
+	for (q = (unsigned)A->id;; q += N_DESTROY) {
 		const int slot = (int)(q % P2_SLOTS);
 		batch2_t *b = &P->b[slot];
 		double t1;
-		P2_WAIT(P, slot, S2_WRITTEN);
-		if (b->n == 0) break;
+		pthread_mutex_lock(&P->mu);
+		while (P->state[slot] != S2_WRITTEN && !P->destroy_done) pthread_cond_wait(&P->cv, &P->mu);
+		if (P->state[slot] != S2_WRITTEN) { pthread_mutex_unlock(&P->mu); break; } /* the other thread met the end marker */
+		if (b->n == 0) { P->destroy_done = 1; pthread_cond_broadcast(&P->cv); pthread_mutex_unlock(&P->mu); break; }
+		pthread_mutex_unlock(&P->mu);
 		t1 = now();
 		destroy_records(b->recs, b->n);
-		P->t_destroy += now() - t1;
+		P->t_destroy[A->id] += now() - t1;
 		P2_SET(P, slot, S2_FREE);
 	}
 	return 0;
@@ -1555,7 +1600,8 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	pipe2_t *P = (pipe2_t *)calloc(1, sizeof(pipe2_t));
 	bam_pair_t *stash = (bam_pair_t *)calloc(B, sizeof(bam_pair_t)); /* loaded records not yet handed to a batch */
 	size_t stash_n = 0, stash_at = 0;
-	pthread_t th[6];
+	pthread_t th[6 + N_DESTROY];
+	destroy2_arg_t da[N_DESTROY];
 	khiter_t it;
 	unsigned q;
 	int s, eof = 0;
@@ -1568,8 +1614,9 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	pthread_create(&th[1], 0, stage2_pair, P);
 	pthread_create(&th[2], 0, stage2_rescue, P);
 	pthread_create(&th[3], 0, stage2_refine, P);
-	pthread_create(&th[4], 0, stage2_write, P);
-	pthread_create(&th[5], 0, stage2_destroy, P);
+	pthread_create(&th[4], 0, stage2_update, P);
+	pthread_create(&th[5], 0, stage2_write, P);
+	for (s = 0; s < N_DESTROY; ++s) { da[s].P = P; da[s].id = s; pthread_create(&th[6 + s], 0, stage2_destroy, &da[s]); }
 	for (q = 0;; ++q) { /* the load stage: batches bounded by records and by the SA rows their hit lists expand to */
 		const int slot = (int)(q % P2_SLOTS);
 		batch2_t *b = &P->b[slot];
@@ -1599,14 +1646,14 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		P2_SET(P, slot, S2_LOADED);
 		if (b->n == 0) break;
 	}
-	for (s = 0; s < 6; ++s) pthread_join(th[s], 0);
+	for (s = 0; s < 6 + N_DESTROY; ++s) pthread_join(th[s], 0);
 	g_rep.pass2_s = now() - P->t0;
 	fprintf(stderr, "[%s] %ld sequences processed in %.2f sec (pipelined stages, busy seconds each incl. their device calls: load %.2f, enumerate %.2f, "
-	                "pairing/XA %.2f, mate rescue %.2f, refine/update %.2f, BAM write %.2f, destroy %.2f)\n"
+	                "pairing/XA %.2f, mate rescue %.2f, refine %.2f, update %.2f, BAM write %.2f, destroy %.2f + %.2f)\n"
 	                "[%s] finished cleanly, shutting down.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d singletons are mated.\n"
 	                "[bwa_paired_sw] %lld out of %lld Q%d discordant pairs are fixed.\n",
-	        __func__, P->tot_seqs, now() - P->t0, P->t_load, P->t_enum, P->t_pair, P->t_rescue, P->t_refine, P->t_write, P->t_destroy, __func__,
+	        __func__, P->tot_seqs, now() - P->t0, P->t_load, P->t_enum, P->t_pair, P->t_rescue, P->t_refine, P->t_update, P->t_write, P->t_destroy[0], P->t_destroy[N_DESTROY - 1], __func__,
 	        (long long)P->n_mapped[1], (long long)P->n_tot[1], SW_MIN_MAPQ, (long long)P->n_mapped[0], (long long)P->n_tot[0], SW_MIN_MAPQ);
 	for (it = kh_begin(P->my_hash); it != kh_end(P->my_hash); ++it)
 		if (kh_exist(P->my_hash, it)) free(kh_val(P->my_hash, it).a);

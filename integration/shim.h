@@ -36,7 +36,7 @@ static inline double shim_now(void)
 
 /* ---- CPU accounting: seconds of thread CPU time by activity (a profile of the host side without a profiler) */
 enum { CPU_INFLATE = 0, CPU_PARSE, CPU_TOSEQ, CPU_POSN_SERIAL, CPU_POSN_PAR, CPU_ISIZE, CPU_STORE, CPU_DESTROY, CPU_LOAD, CPU_ENUM, CPU_PAIRING,
-       CPU_XA_SERIAL, CPU_RESCUE_RECORD, CPU_RESCUE_REPLAY, CPU_REFINE_RECORD, CPU_REFINE_REPLAY, CPU_BAM_LAYOUT, CPU_DEFLATE, CPU_WRITE, CPU_OTHER, CPU_N };
+       CPU_XA_SERIAL, CPU_RESCUE_RECORD, CPU_RESCUE_REPLAY, CPU_REFINE_RECORD, CPU_REFINE_REPLAY, CPU_UPDATE, CPU_BAM_LAYOUT, CPU_DEFLATE, CPU_WRITE, CPU_OTHER, CPU_N };
 extern __thread int t_cpu_bucket; /* where the calling thread's parallel_for / parallel_slices workers (and cpu_add) book their time */
 double thread_cpu_now(void);
 void cpu_add(int bucket, double seconds);

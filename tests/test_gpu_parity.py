@@ -70,10 +70,22 @@ def test_chunking_and_tiers_are_invisible(golden, gpu_index, monkeypatch):
     monkeypatch.setenv("BWAGPU_T1_CAP", "48")
     monkeypatch.setenv("BWAGPU_POOL_MB", "1")         # 51 chunks: the optimistic pass runs dry
     monkeypatch.setenv("BWAGPU_HITS_PER_READ", "1")   # and so does the hit pool: grown, reads retried
-    got = api.aln_flat(reads.bases, reads.offs, opt)
-    st = api.get_stats()
-    assert st["x_chunks_used"] > 0      # searches spilled into the shared pool
-    assert R.compare_aln(want, got, "chunked") == []
+    # the shared pool is sized on a lane's first use: a fresh context, so that the 1 MB really applies to every lane
+    T, idx = gpu_index
+    api.destroy()
+    api.init()
+    api.load_index(idx)
+    try:
+        got = api.aln_flat(reads.bases, reads.offs, opt)
+        st = api.get_stats()
+        assert st["x_chunks_used"] > 0      # searches spilled into the shared pool
+        assert st["n_overflow_t2"] > 0      # reads left pass 0 (arena of 48 records)
+        assert R.compare_aln(want, got, "chunked") == []
+    finally:  # the module's other tests get a context with the default sizes back
+        monkeypatch.undo()
+        api.destroy()
+        api.init()
+        api.load_index(idx)
 
 
 @pytest.mark.parametrize("name", CONFIGS)

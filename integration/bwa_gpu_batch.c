@@ -186,6 +186,7 @@ int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned; /* bam2ba
 static isize_info_t g_null_ii; /* bam2bam.c:106 */
 static bwa_gpu_batch_report_t g_rep; /* the run in progress / the last run (bwa_gpu_batch.h) */
 static double g_cpu0;
+static double g_t_call, g_t_pass1_begin, g_t_pass1_end, g_t_pass2_begin, g_t_pass2_end; /* where a run's wall time goes outside the passes */
 
 /* The index of a long-lived host process (bench.py runs bam2bam several times in one process): with keep_index on, the
  * loaders hand back what an earlier run loaded from the same files, the matching destroy calls leave it alone, and the
@@ -327,8 +328,11 @@ int bwa_bam_to_bam(int argc, char *argv[], char *version)
 		g_cpu0 = (double)ru.ru_utime.tv_sec + 1e-6 * (double)ru.ru_utime.tv_usec + (double)ru.ru_stime.tv_sec + 1e-6 * (double)ru.ru_stime.tv_usec;
 	}
 	t0 = now();
+	g_t_call = t0;
 	rc = real_bwa_bam_to_bam(argc, argv, version);
 	g_rep.wall_s = now() - t0;
+	fprintf(stderr, "[bwa_gpu_batch] outside the passes: %.3f s before pass 1 (options, header, index), %.3f s between the passes (isize inference), %.3f s after pass 2 (close)\n",
+	        g_t_pass1_begin - g_t_call, g_t_pass2_begin - g_t_pass1_end, now() - g_t_pass2_end);
 	g_rep.inflate_cpu_s = 1e-9 * (double)g_cpu_ns[CPU_INFLATE];
 	{
 		struct rusage ru;
@@ -1000,6 +1004,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	memset(&P, 0, sizeof(P));
 	pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
 	P.B = B; P.ks = ks; P.temporary = temporary; P.iinfos = iinfos; P.t0 = now();
+	g_t_pass1_begin = P.t0;
 	for (s = 0; s < P1_SLOTS; ++s) P.recs[s] = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
 	memtemp_begin();
 	/* device context + index upload (seconds) overlap the reading of the first batches */
@@ -1029,6 +1034,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	free(flat);
 	pthread_mutex_destroy(&P.mu); pthread_cond_destroy(&P.cv);
 	g_rep.pass1_s = now() - P.t0;
+	g_t_pass1_end = now();
 	g_rep.sequences = P.tot_seqs;
 	fprintf(stderr, "[%s] %zu records (%.0f MB) kept in memory for pass 2%s\n", __func__, memtemp_records(), memtemp_bytes() / 1048576.0,
 	        memtemp_spilled() ? ", the rest in the temporary file" : "");
@@ -1595,6 +1601,7 @@ static void *stage2_destroy(void *arg) /* the free()s of a written batch, off th
 
 void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) *iinfos)
 {
+	const double t_begin_ = (g_t_pass2_begin = now());
 	const size_t B = batch_records();
 	const long long max_q = getenv("BWAGPU_BATCH_SA") ? atoll(getenv("BWAGPU_BATCH_SA")) : 1ll << 25; /* SA rows per device call */
 	pipe2_t *P = (pipe2_t *)calloc(1, sizeof(pipe2_t));
@@ -1663,6 +1670,8 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	pthread_mutex_destroy(&P->mu); pthread_cond_destroy(&P->cv);
 	free(P);
 	memtemp_free();
+	(void)t_begin_;
+	g_t_pass2_end = now();
 }
 
 /* ------------------------------------------------------------------ 0MQ worker
@@ -1836,6 +1845,7 @@ void *run_worker_thread(void *arg)
 					stage_pairing(b2);
 					stage_rescue(b2, n_tot, n_mapped);
 					stage_refine(b2);
+					stage_update(b2);
 					lo = hi;
 				}
 		}

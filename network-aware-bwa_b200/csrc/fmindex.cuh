@@ -23,6 +23,12 @@
 #ifndef BWAGPU_L2HINT
 #define BWAGPU_L2HINT 0 // 1: L2 evict_last policy on index loads (A/B switch)
 #endif
+#ifndef BWAGPU_IDX_STREAM
+#define BWAGPU_IDX_STREAM 0 // 1: index loads L1::evict_first + L2 evict_first; 2: L1::no_allocate + L2 evict_first (A/B switch)
+#endif
+#ifndef BWAGPU_CTX_KEEP
+#define BWAGPU_CTX_KEEP 0 // 1: context-entry loads L1::evict_last + L2 evict_last (A/B switch)
+#endif
 #ifndef BWAGPU_LDG256
 #define BWAGPU_LDG256 1 // sm_100a has LDG.E.256; set to 0 for two LDG.128
 #endif
@@ -56,7 +62,19 @@ __device__ __forceinline__ OccBlock load_block(const DevIndex &ix, uint32_t b)
 	OccBlock o;
 #if BWAGPU_LDG256
 	uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-#if BWAGPU_L2HINT
+#if BWAGPU_IDX_STREAM
+	// an index far larger than L2 has no reuse beyond a trip's own two lookups: keep it out of the way of the searches'
+	// state (context entries, stack records), which is re-read for as long as a read lasts
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#if BWAGPU_IDX_STREAM == 2
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+#else
+	asm volatile("ld.global.nc.L1::evict_first.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+#endif
+	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+	             : "l"(p), "l"(pol));
+#elif BWAGPU_L2HINT
 	// keep index sectors in L2 ahead of the streaming stack / width traffic
 	unsigned long long pol;
 	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));

@@ -873,8 +873,19 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			if (fresh | (mode == MODE_EXACT)) { // fresh: the node's own entries E[i-1], E[i-2]; exact tail: E[i-2] (its base = str[i-2]) in the low half
 				const int j = fresh ? i : i - 1;
 				const uint16_t *cp = ctx16 + ((size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)j);
+#if BWAGPU_CTX_KEEP && !defined(BWAGPU_HOST_EMU)
+				uint32_t e1 = 0u, e2 = 0u;
+				{
+					unsigned long long pol;
+					unsigned short v;
+					asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+					if (j >= 1) { asm volatile("ld.global.L1::evict_last.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(cp - 1), "l"(pol)); e1 = v; }
+					if (fresh && j >= 2) { asm volatile("ld.global.L1::evict_last.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(cp - 2), "l"(pol)); e2 = v; }
+				}
+#else
 				const uint32_t e1 = j >= 1 ? (uint32_t)cp[-1] : 0u;
 				const uint32_t e2 = (fresh && j >= 2) ? (uint32_t)cp[-2] : 0u;
+#endif
 				cw = e1 | e2 << 16;
 			}
 			if (STATS) {

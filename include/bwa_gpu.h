@@ -258,6 +258,13 @@ int bwa_gpu_global_align_seqs(int n, const bwa_gpu_ga_job_t *jobs, int gap_end, 
  * one call at a time (calls are serialised inside).  `in` is copied fastest from bwa_gpu_host_alloc memory. */
 int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int level, const uint8_t **out, int64_t *out_bytes,
                          const int32_t **member_len, int32_t *n_members, double *kernel_ms);
+/* The input side: replaces the compute of bamlite's gzread (bamlite.h:7-11; bam_read1, bamlite.c:125-155 reads the records
+ * through one zlib inflate stream).  `n_members` BGZF members lie at in[member_off[k] .. member_off[k+1]); they are inflated on
+ * the device (one thread per member, all of them at once) and their bytes placed back to back in `out` (host memory, ideally
+ * from bwa_gpu_host_alloc; room for out_cap bytes); out_off[k] .. out_off[k+1] = where member k's bytes are (n_members + 1
+ * entries).  A member that is not well-formed deflate, or whose length differs from its ISIZE, fails the call with a message. */
+int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t n_members, const int64_t *member_off, uint8_t *out,
+                         int64_t out_cap, int64_t *out_off, double *kernel_ms);
 /* page-locked host memory for the buffers handed to the calls above (NULL + bwa_gpu_last_error on failure) */
 void *bwa_gpu_host_alloc(size_t bytes);
 void bwa_gpu_host_free(void *p);

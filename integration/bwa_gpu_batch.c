@@ -379,6 +379,8 @@ static pthread_mutex_t g_rep_mu = PTHREAD_MUTEX_INITIALIZER;
 #define REP_ADD(calls_f, units_f, secs_f, units, t0) do { pthread_mutex_lock(&g_rep_mu); ++g_rep.calls_f; g_rep.units_f += (int64_t)(units); \
 		g_rep.secs_f += now() - (t0); pthread_mutex_unlock(&g_rep_mu); } while (0)
 
+int shim_device_ready(void) { return __atomic_load_n(&g_ready, __ATOMIC_ACQUIRE); }
+
 void shim_count_bgzf(int64_t bytes, double seconds)
 {
 	pthread_mutex_lock(&g_rep_mu); ++g_rep.calls_bgzf; g_rep.bytes_bgzf += bytes; g_rep.dev_bgzf_s += seconds; pthread_mutex_unlock(&g_rep_mu);

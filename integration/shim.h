@@ -71,6 +71,7 @@ void memtemp_get(size_t idx, const uint8_t **data, uint32_t *len);
 void memtemp_free(void);
 
 void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n);
+int shim_device_ready(void);          /* bwa_gpu_batch.c: the device context of this run exists */
 void shim_count_bgzf(int64_t bytes, double seconds); /* bwa_gpu_batch.c: the run report */
 
 #endif

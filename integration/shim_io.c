@@ -21,7 +21,8 @@
 #include <unistd.h>
 
 /* ================================================================== input BAM */
-#define FI_SLOTS 512            /* ring of inflated blocks: 32 MB */
+#define FI_SLOTS 1024           /* ring of inflated blocks: 64 MB */
+#define FI_DEV_MEMBERS 256      /* members per device inflate call */
 #define FI_BLOCK 65536
 #define FI_MAXTH 16
 enum { FS_FREE = 0, FS_BUSY, FS_FILLED };
@@ -46,6 +47,9 @@ typedef struct {
 	pthread_cond_t cv_filled, cv_free;
 	pthread_t th[FI_MAXTH];
 	int nth, stop, error;
+	int dev_active;          /* the device worker has taken over: the zlib workers retire */
+	pthread_t dev_th;
+	int dev_started;
 	double cpu_s;
 	/* consumer */
 	uint64_t cons_seq;
@@ -98,7 +102,7 @@ static void *fi_worker(void *arg)
 		double t0;
 		uint32_t isize;
 		pthread_mutex_lock(&F.mu);
-		if (F.stop || F.error) { pthread_mutex_unlock(&F.mu); break; }
+		if (F.stop || F.error || F.dev_active) { pthread_mutex_unlock(&F.mu); break; }
 		if (F.scan >= F.map_len) { /* clean end of file */
 			F.total = F.next_job;
 			pthread_cond_broadcast(&F.cv_filled);
@@ -137,6 +141,79 @@ static void *fi_worker(void *arg)
 	}
 	inflateEnd(&zs);
 	cpu_add(CPU_INFLATE, cpu);
+	return 0;
+}
+
+/* The device takes the inflate over as soon as its context exists (bwa_gpu_bgzf_inflate: one thread per BGZF member,
+ * FI_DEV_MEMBERS members per call); until then -- the first second of a fresh process, while the index is uploaded -- and with
+ * BWAGPU_HOST_INFLATE=1 the zlib workers above do it.  Both fill the same ring in member order. */
+static void *fi_device_worker(void *arg)
+{
+	uint8_t *dbuf = 0;
+	int64_t moff[FI_DEV_MEMBERS + 1], ooff[FI_DEV_MEMBERS + 1];
+	(void)arg;
+	while (!shim_device_ready()) {
+		if (F.stop || F.error) return 0;
+		usleep(2000);
+	}
+	dbuf = (uint8_t *)bwa_gpu_host_alloc((size_t)FI_DEV_MEMBERS * FI_BLOCK);
+	if (!dbuf) return 0; /* the zlib workers carry on */
+	pthread_mutex_lock(&F.mu);
+	F.dev_active = 1;
+	pthread_mutex_unlock(&F.mu);
+	for (;;) {
+		int n = 0, k;
+		uint64_t j0;
+		pthread_mutex_lock(&F.mu);
+		if (F.stop || F.error) { pthread_mutex_unlock(&F.mu); break; }
+		if (F.scan >= F.map_len) { /* clean end of file */
+			F.total = F.next_job;
+			pthread_cond_broadcast(&F.cv_filled);
+			pthread_mutex_unlock(&F.mu);
+			break;
+		}
+		while (n < FI_DEV_MEMBERS && F.scan < F.map_len) {
+			size_t bsize = 0;
+			if (!bgzf_header_ok(F.map + F.scan, F.map_len - F.scan, &bsize)) {
+				if (n) break; /* hand over what is good first */
+				fprintf(stderr, "[bwa_gpu_batch] %s: damaged BGZF block at offset %zu\n", F.path, F.scan);
+				F.error = 1;
+				pthread_cond_broadcast(&F.cv_filled);
+				break;
+			}
+			moff[n++] = (int64_t)F.scan;
+			F.scan += bsize;
+		}
+		if (F.error) { pthread_mutex_unlock(&F.mu); break; }
+		moff[n] = (int64_t)F.scan;
+		j0 = F.next_job; F.next_job += (uint64_t)n;
+		pthread_mutex_unlock(&F.mu);
+		if (bwa_gpu_bgzf_inflate(F.map, (int64_t)F.map_len, n, moff, dbuf, (int64_t)FI_DEV_MEMBERS * FI_BLOCK, ooff, 0)) {
+			fprintf(stderr, "[bwa_gpu_batch] %s: %s\n", F.path, bwa_gpu_last_error());
+			pthread_mutex_lock(&F.mu);
+			F.error = 1;
+			pthread_cond_broadcast(&F.cv_filled);
+			pthread_mutex_unlock(&F.mu);
+			break;
+		}
+		for (k = 0; k < n; ++k) {
+			fi_slot_t *s = &F.slot[(j0 + (uint64_t)k) % FI_SLOTS];
+			const double c0 = thread_cpu_now();
+			pthread_mutex_lock(&F.mu);
+			while (s->state != FS_FREE && !F.stop) pthread_cond_wait(&F.cv_free, &F.mu);
+			if (F.stop) { pthread_mutex_unlock(&F.mu); goto out; }
+			s->state = FS_BUSY;
+			pthread_mutex_unlock(&F.mu);
+			memcpy(s->buf, dbuf + ooff[k], (size_t)(ooff[k + 1] - ooff[k]));
+			pthread_mutex_lock(&F.mu);
+			s->len = (int)(ooff[k + 1] - ooff[k]); s->seq = j0 + (uint64_t)k; s->state = FS_FILLED;
+			pthread_cond_broadcast(&F.cv_filled);
+			pthread_mutex_unlock(&F.mu);
+			cpu_add(CPU_INFLATE, thread_cpu_now() - c0);
+		}
+	}
+out:
+	bwa_gpu_host_free(dbuf);
 	return 0;
 }
 
@@ -206,6 +283,10 @@ static void fastin_start(bamFile fp)
 		for (i = 0; i < FI_SLOTS; ++i) { F.slot[i].buf = (uint8_t *)malloc(FI_BLOCK); F.slot[i].state = FS_FREE; }
 		F.nth = fi_threads();
 		for (i = 0; i < F.nth; ++i) pthread_create(&F.th[i], 0, fi_worker, 0);
+		{
+			const char *h = getenv("BWAGPU_HOST_INFLATE");
+			if (!(h && atoi(h) != 0)) F.dev_started = pthread_create(&F.dev_th, 0, fi_device_worker, 0) == 0;
+		}
 		F.active = 1;
 		return;
 	}
@@ -230,6 +311,7 @@ void fastin_close(void)
 			pthread_mutex_unlock(&F.mu);
 		} else F.stop = 1;
 		for (i = 0; i < F.nth; ++i) pthread_join(F.th[i], 0);
+		if (F.bgzf && F.dev_started) pthread_join(F.dev_th, 0);
 		if (F.bgzf) {
 			for (i = 0; i < FI_SLOTS; ++i) free(F.slot[i].buf);
 			munmap((void *)F.map, F.map_len);

@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         L.bwa_gpu_index_write.argtypes = [C.c_char_p, C.POINTER(abi.bwt_t), C.POINTER(abi.bwt_t)]
         L.bwa_gpu_bgzf_deflate.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.bwa_gpu_bgzf_inflate.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
         L.bwa_gpu_host_alloc.argtypes = [C.c_size_t]
         L.bwa_gpu_host_alloc.restype = C.c_void_p
         L.bwa_gpu_host_free.argtypes = [C.c_void_p]
@@ -74,7 +75,7 @@ EXPORTS = [
     "bwa_gpu_get_stats", "bwa_gpu_set_stats", "bwa_gpu_get_totals", "bwa_gpu_reset_totals", "bwa_gpu_probe_random_sectors",
     "bwa_gpu_resident_stage", "bwa_gpu_resident_run", "bwa_gpu_resident_fetch",
     "bwa_gpu_index_build", "bwa_gpu_index_free", "bwa_gpu_index_write",
-    "bwa_gpu_bgzf_deflate", "bwa_gpu_host_alloc", "bwa_gpu_host_free",
+    "bwa_gpu_bgzf_deflate", "bwa_gpu_bgzf_inflate", "bwa_gpu_host_alloc", "bwa_gpu_host_free",
 ]
 
 
@@ -247,6 +248,29 @@ def bgzf_deflate(data, level: int = 2):
     packed = C.string_at(out.value, out_n.value) if out_n.value else b""
     member_len = np.ctypeslib.as_array(C.cast(lens.value, C.POINTER(C.c_int32)), shape=(n_mem.value,)).copy() if n_mem.value else np.zeros(0, np.int32)
     return packed, member_len, ms.value
+
+
+def bgzf_member_offsets(data: bytes) -> np.ndarray:
+    """Start of every BGZF member of `data` (+ its end): the BSIZE chain of the BC extra fields (bgzf.c:274-291)."""
+    offs, p = [0], 0
+    while p < len(data):
+        assert data[p:p + 4] == b"\x1f\x8b\x08\x04" and data[p + 12:p + 14] == b"BC", f"not a BGZF member at {p}"
+        p += int.from_bytes(data[p + 16:p + 18], "little") + 1
+        offs.append(p)
+    return np.array(offs, dtype=np.int64)
+
+
+def bgzf_inflate(data: bytes):
+    """bwa_gpu_bgzf_inflate on a whole BGZF byte string -> (decompressed bytes, per-member output offsets, kernel ms)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    moff = bgzf_member_offsets(data)
+    n = moff.size - 1
+    cap = 65536 * max(1, n)
+    out = np.empty(cap, dtype=np.uint8)
+    ooff = np.zeros(n + 1, dtype=np.int64)
+    ms = C.c_double()
+    _ck(lib().bwa_gpu_bgzf_inflate(buf.ctypes.data, buf.size, n, moff.ctypes.data, out.ctypes.data, cap, ooff.ctypes.data, C.byref(ms)))
+    return out[: ooff[n]].tobytes(), ooff, ms.value
 
 
 def set_stats(enabled: bool) -> None:

@@ -81,6 +81,39 @@ __global__ void k_bgzf_pack(const uint8_t *__restrict__ members, const int32_t *
 	for (int i = lead + 4 * words + (int)threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+__global__ void __launch_bounds__(bgzf::INF_T) k_bgzf_inflate(const uint8_t *__restrict__ in, const bgzf::InfJob *__restrict__ jobs, int n,
+                                                               uint8_t *out, int *__restrict__ status)
+{
+	__shared__ bgzf::InfTables tables[bgzf::INF_T];
+	const int j = blockIdx.x * bgzf::INF_T + threadIdx.x;
+	if (j >= n) return;
+	const bgzf::InfJob J = jobs[j];
+	status[j] = bgzf::inflate_member(in + J.in_off, J.in_len, out + J.out_off, J.out_len, tables[threadIdx.x]);
+}
+
+struct Inflater {
+	std::mutex mu;
+	int dev = -1;
+	cudaStream_t st = nullptr;
+	uint8_t *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
+	size_t cap_in = 0, cap_out = 0, cap_h_in = 0, cap_h_out = 0;
+	bgzf::InfJob *d_jobs = nullptr, *h_jobs = nullptr;
+	int *d_status = nullptr, *h_status = nullptr;
+	size_t cap_jobs = 0;
+	void release()
+	{
+		if (dev < 0) return;
+		cudaSetDevice(dev);
+		cudaFree(d_in); cudaFree(d_out); cudaFree(d_jobs); cudaFree(d_status);
+		cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFreeHost(h_jobs); cudaFreeHost(h_status);
+		if (st) cudaStreamDestroy(st);
+		d_in = d_out = h_in = h_out = nullptr; d_jobs = h_jobs = nullptr; d_status = h_status = nullptr;
+		cap_in = cap_out = cap_h_in = cap_h_out = cap_jobs = 0;
+		st = nullptr; dev = -1;
+	}
+};
+Inflater g_inflater;
+
 struct Codec {
 	std::mutex mu;
 	int dev = -1;
@@ -170,7 +203,11 @@ int codec_prepare(Codec &c, size_t n_bytes, size_t n_blocks, bool in_is_pinned)
 } // namespace
 
 namespace bwagpu {
-void bgzf_release() { std::lock_guard<std::mutex> g(g_codec.mu); g_codec.release(); }
+void bgzf_release()
+{
+	{ std::lock_guard<std::mutex> g(g_codec.mu); g_codec.release(); }
+	{ std::lock_guard<std::mutex> g(g_inflater.mu); g_inflater.release(); }
+}
 }
 
 extern "C" void *bwa_gpu_host_alloc(size_t bytes)
@@ -236,5 +273,114 @@ extern "C" int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int leve
 	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	*out = c.h_packed; *out_bytes = total;
 	if (member_len) *member_len = c.h_clen;
+	return 0;
+}
+
+static bool is_pinned(const void *p)
+{
+	cudaPointerAttributes attr;
+	const bool yes = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	return yes;
+}
+
+extern "C" int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t n_members, const int64_t *member_off, uint8_t *out,
+                                    int64_t out_cap, int64_t *out_off, double *kernel_ms)
+{
+	if (n_members < 0 || n_bytes < 0 || (n_members && (!in || !member_off || !out || !out_off))) return hostprep_fail("bwa_gpu_bgzf_inflate: bad arguments");
+	if (kernel_ms) *kernel_ms = 0;
+	if (out_off) out_off[0] = 0;
+	if (n_members == 0) return 0;
+	const int dev = bwagpu::primary_device();
+	if (dev < 0) return hostprep_fail("bwa_gpu_bgzf_inflate: bwa_gpu_init has not been called (no CPU fallback)");
+	Inflater &c = g_inflater;
+	std::lock_guard<std::mutex> g(c.mu);
+	if (c.dev != dev) {
+		c.release();
+		c.dev = dev;
+		BCK(cudaSetDevice(dev));
+		BCK(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+	}
+	BCK(cudaSetDevice(dev));
+	const size_t n = (size_t)n_members;
+	if (n > c.cap_jobs) {
+		cudaFree(c.d_jobs); cudaFree(c.d_status); cudaFreeHost(c.h_jobs); cudaFreeHost(c.h_status);
+		c.d_jobs = c.h_jobs = nullptr; c.d_status = c.h_status = nullptr; c.cap_jobs = 0;
+		const size_t want = n + n / 4 + 64;
+		BCK(cudaMalloc((void **)&c.d_jobs, want * sizeof(bgzf::InfJob)));
+		BCK(cudaMalloc((void **)&c.d_status, want * sizeof(int)));
+		BCK(cudaMallocHost((void **)&c.h_jobs, want * sizeof(bgzf::InfJob)));
+		BCK(cudaMallocHost((void **)&c.h_status, want * sizeof(int)));
+		c.cap_jobs = want;
+	}
+	// the members' extents and, from their trailers (ISIZE: bgzf.c:325), where each one's bytes go in the output stream
+	int64_t total = 0;
+	for (size_t k = 0; k < n; ++k) {
+		const int64_t a = member_off[k], b = member_off[k + 1];
+		if (a < 0 || b > n_bytes || b - a < 26 || b - a > 65536 + 64) return hostprep_fail("bwa_gpu_bgzf_inflate: member %zu has no valid extent", k);
+		uint32_t isize;
+		memcpy(&isize, in + b - 4, 4);
+		if (isize > 65536) return hostprep_fail("bwa_gpu_bgzf_inflate: member %zu claims %u bytes (a BGZF block holds at most 65536)", k, isize);
+		c.h_jobs[k].in_off = a; c.h_jobs[k].in_len = (int)(b - a);
+		c.h_jobs[k].out_off = total; c.h_jobs[k].out_len = (int)isize;
+		out_off[k] = total;
+		total += isize;
+	}
+	out_off[n] = total;
+	if (total > out_cap) return hostprep_fail("bwa_gpu_bgzf_inflate: %lld bytes of output, room for %lld", (long long)total, (long long)out_cap);
+	const size_t span = (size_t)(member_off[n] - member_off[0]);
+	const uint8_t *src = in + member_off[0];
+	for (size_t k = 0; k < n; ++k) c.h_jobs[k].in_off -= member_off[0];
+	if (span > c.cap_in) {
+		cudaFree(c.d_in); c.d_in = nullptr; c.cap_in = 0;
+		const size_t want = span + span / 4 + 65536;
+		BCK(cudaMalloc((void **)&c.d_in, want));
+		c.cap_in = want;
+	}
+	if ((size_t)total + 1 > c.cap_out) {
+		cudaFree(c.d_out); c.d_out = nullptr; c.cap_out = 0;
+		const size_t want = (size_t)total + (size_t)total / 4 + 65536;
+		BCK(cudaMalloc((void **)&c.d_out, want));
+		c.cap_out = want;
+	}
+	const bool in_pinned = is_pinned(src), out_pinned = is_pinned(out);
+	if (!in_pinned) {
+		if (span > c.cap_h_in) {
+			cudaFreeHost(c.h_in); c.h_in = nullptr; c.cap_h_in = 0;
+			const size_t want = span + span / 4 + 65536;
+			BCK(cudaMallocHost((void **)&c.h_in, want));
+			c.cap_h_in = want;
+		}
+		memcpy(c.h_in, src, span);
+		src = c.h_in;
+	}
+	if (!out_pinned && (size_t)total + 1 > c.cap_h_out) {
+		cudaFreeHost(c.h_out); c.h_out = nullptr; c.cap_h_out = 0;
+		const size_t want = (size_t)total + (size_t)total / 4 + 65536;
+		BCK(cudaMallocHost((void **)&c.h_out, want));
+		c.cap_h_out = want;
+	}
+	cudaEvent_t e0, e1;
+	BCK(cudaEventCreate(&e0)); BCK(cudaEventCreate(&e1));
+	BCK(cudaMemcpyAsync(c.d_in, src, span, cudaMemcpyHostToDevice, c.st));
+	BCK(cudaMemcpyAsync(c.d_jobs, c.h_jobs, n * sizeof(bgzf::InfJob), cudaMemcpyHostToDevice, c.st));
+	BCK(cudaEventRecord(e0, c.st));
+	k_bgzf_inflate<<<(unsigned)((n + bgzf::INF_T - 1) / bgzf::INF_T), bgzf::INF_T, 0, c.st>>>(c.d_in, c.d_jobs, (int)n, c.d_out, c.d_status);
+	BCK(cudaEventRecord(e1, c.st));
+	BCK(cudaGetLastError());
+	BCK(cudaMemcpyAsync(c.h_status, c.d_status, n * sizeof(int), cudaMemcpyDeviceToHost, c.st));
+	if (total) BCK(cudaMemcpyAsync(out_pinned ? out : c.h_out, c.d_out, (size_t)total, cudaMemcpyDeviceToHost, c.st));
+	BCK(cudaStreamSynchronize(c.st));
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (kernel_ms) *kernel_ms = ms;
+		bwagpu::count_bgzf(1, ms, (int64_t)span, total);
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	for (size_t k = 0; k < n; ++k)
+		if (c.h_status[k]) return hostprep_fail("bwa_gpu_bgzf_inflate: member %zu (at byte %lld of the input) is not a valid BGZF member (code %d)", k,
+		                                        (long long)member_off[k], c.h_status[k]);
+	if (!out_pinned && total) memcpy(out, c.h_out, (size_t)total);
 	return 0;
 }

@@ -534,3 +534,174 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 }
 
 } // namespace bgzf
+
+// ================================================================ inflate: the BAM input side
+// Replaces the compute of bamlite's gzread (bamlite.h:7-11, bamlite.c:125-155: one zlib inflate stream on the thread
+// that parses the records).  The members of a BGZF file are independent, so the parallelism is across members: ONE THREAD
+// per member, thousands of members in flight -- a member is a serial bit stream (every code's position depends on the
+// lengths of all codes before it), and a thread walks it with the canonical-code decoder of RFC 1951 3.2.2 (count of
+// codes per length + symbols in code order; a code is recognised the moment its value falls inside its length's range).
+// The per-thread tables (lit/len: 16 counts + 288 symbols; distance: 16 + 30) live in shared memory, the bit buffer in
+// a register; literals go out as byte stores into the member's slice of the output stream, matches are byte copies from
+// that slice (overlap = run-length semantics for free).  Stored, fixed and dynamic blocks are all handled; a malformed
+// member sets a status the host turns into an error.
+namespace bgzf {
+
+constexpr int INF_T = 64; // threads per CTA (700 B of tables each)
+
+struct InfTables {
+	uint16_t lcnt[16], lsym[288], dcnt[16], dsym[32];
+};
+
+struct InfJob {
+	long long in_off, out_off;
+	int in_len, out_len; // the whole member (header .. ISIZE); its ISIZE
+};
+
+struct BitIn {
+	const uint8_t *p, *end;
+	unsigned long long buf;
+	int n;
+	int fake; // zero bits appended after the end of the stream (a code is looked at 15 bits at a time, so some may be needed)
+};
+__device__ __forceinline__ bool bits_over(const BitIn &b) { return b.n < b.fake; } // bits past the end were CONSUMED
+
+__device__ __forceinline__ void bits_need(BitIn &b, int want) // want <= 32
+{
+	while (b.n < want) {
+		unsigned long long v = 0;
+		if (b.p < b.end) v = *b.p++; else b.fake += 8;
+		b.buf |= v << b.n;
+		b.n += 8;
+	}
+}
+__device__ __forceinline__ uint32_t bits_take(BitIn &b, int k) // k <= 16
+{
+	bits_need(b, k);
+	const uint32_t v = (uint32_t)(b.buf & ((1ull << k) - 1));
+	b.buf >>= k; b.n -= k;
+	return v;
+}
+
+// one symbol of a canonical code: cnt[len] codes of each length, sym[] in (length, symbol) order; -1 = no such code
+__device__ __forceinline__ int inf_decode(BitIn &b, const uint16_t *cnt, const uint16_t *sym)
+{
+	bits_need(b, 15);
+	int code = 0, first = 0, index = 0;
+	unsigned long long w = b.buf;
+#pragma unroll 1
+	for (int len = 1; len <= 15; ++len) {
+		code |= (int)(w & 1); w >>= 1;
+		const int c = cnt[len];
+		if (code - c < first) { b.buf >>= len; b.n -= len; return sym[index + (code - first)]; }
+		index += c; first += c;
+		first <<= 1; code <<= 1;
+	}
+	return -1;
+}
+
+// code lengths -> decoder tables; false: over-subscribed (an incomplete code is fine: zlib accepts it for a lone distance code)
+__device__ bool inf_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym)
+{
+	uint16_t offs[16];
+	for (int l = 0; l < 16; ++l) cnt[l] = 0;
+	for (int s = 0; s < n; ++s) ++cnt[lens[s]];
+	int left = 1;
+	for (int l = 1; l < 16; ++l) { left <<= 1; left -= cnt[l]; if (left < 0) return false; }
+	offs[1] = 0;
+	for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
+	for (int s = 0; s < n; ++s)
+		if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
+	cnt[0] = 0;
+	return true;
+}
+
+// returns 0, or a code saying what was wrong
+__device__ int inflate_member(const uint8_t *in, int in_len, uint8_t *out, int out_len, InfTables &T) // (out is read back by the match copies: no __restrict__)
+{
+	if (in_len < 18 || in[0] != 31 || in[1] != 139 || in[2] != 8) return 1;
+	const int flg = in[3];
+	int h = 10;
+	if (flg & 4) { if (h + 2 > in_len) return 1; h += 2 + (in[h] | in[h + 1] << 8); }
+	if (flg & 8) { while (h < in_len && in[h]) ++h; ++h; }
+	if (flg & 16) { while (h < in_len && in[h]) ++h; ++h; }
+	if (flg & 2) h += 2;
+	if (h + 8 > in_len) return 1;
+	BitIn b;
+	b.p = in + h; b.end = in + in_len - 8; b.buf = 0; b.n = 0; b.fake = 0;
+	int pos = 0;
+	for (;;) {
+		const uint32_t last = bits_take(b, 1), type = bits_take(b, 2);
+		if (type == 0) { // stored
+			b.buf >>= (b.n & 7); b.n -= (b.n & 7);
+			const uint32_t len = bits_take(b, 16), nlen = bits_take(b, 16);
+			if ((len ^ nlen) != 0xffffu) return 2;
+			if (pos + (int)len > out_len) return 3;
+			for (uint32_t i = 0; i < len; ++i) out[pos++] = (uint8_t)bits_take(b, 8);
+		} else if (type == 3) return 4;
+		else {
+			uint8_t lens[320];
+			if (type == 1) { // fixed code (RFC 1951 3.2.6)
+				for (int s = 0; s < 288; ++s) lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+				if (!inf_build(lens, 288, T.lcnt, T.lsym)) return 5;
+				for (int s = 0; s < 30; ++s) lens[s] = 5;
+				if (!inf_build(lens, 30, T.dcnt, T.dsym)) return 5;
+			} else {
+				const int hlit = (int)bits_take(b, 5) + 257, hdist = (int)bits_take(b, 5) + 1, hclen = (int)bits_take(b, 4) + 4;
+				if (hlit > 286 || hdist > 30) return 6;
+				const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+				for (int k = 0; k < 19; ++k) lens[order[k]] = k < hclen ? (uint8_t)bits_take(b, 3) : 0;
+				if (!inf_build(lens, 19, T.dcnt, T.dsym)) return 7; // the code-length code borrows the distance tables
+				int k = 0;
+				while (k < hlit + hdist) {
+					const int s = inf_decode(b, T.dcnt, T.dsym);
+					if (s < 0) return 8;
+					if (s < 16) lens[k++] = (uint8_t)s;
+					else {
+						int rep, v = 0;
+						if (s == 16) { if (k == 0) return 8; v = lens[k - 1]; rep = 3 + (int)bits_take(b, 2); }
+						else if (s == 17) rep = 3 + (int)bits_take(b, 3);
+						else rep = 11 + (int)bits_take(b, 7);
+						if (k + rep > hlit + hdist) return 8;
+						while (rep--) lens[k++] = (uint8_t)v;
+					}
+				}
+				if (lens[256] == 0) return 9; // no end-of-block code
+				if (!inf_build(lens, hlit, T.lcnt, T.lsym)) return 10;
+				if (!inf_build(lens + hlit, hdist, T.dcnt, T.dsym)) return 10;
+			}
+			for (;;) {
+				const int s = inf_decode(b, T.lcnt, T.lsym);
+				if (s < 0 || bits_over(b)) return 11;
+				if (s < 256) { if (pos >= out_len) return 3; out[pos++] = (uint8_t)s; }
+				else if (s == 256) break;
+				else {
+					if (s > 285) return 12;
+					int len;
+					if (s < 265) len = s - 254;
+					else if (s == 285) len = 258;
+					else { const int e = (s - 261) >> 2; len = 3 + ((4 + ((s - 261) & 3)) << e) + (int)bits_take(b, e); }
+					const int ds = inf_decode(b, T.dcnt, T.dsym);
+					if (ds < 0 || ds > 29) return 12;
+					int dist;
+					if (ds < 4) dist = ds + 1;
+					else { const int e = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << e) + (int)bits_take(b, e); }
+					if (dist > pos) return 13;
+					if (pos + len > out_len) return 3;
+					const uint8_t *src = out + pos - dist;
+					for (int i = 0; i < len; ++i) out[pos + i] = src[i];
+					pos += len;
+				}
+			}
+		}
+		if (bits_over(b)) return 11;
+		if (last) break;
+	}
+	if (pos != out_len) return 14;
+	uint32_t isize;
+	const uint8_t *t = in + in_len - 4;
+	isize = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+	return isize == (uint32_t)out_len ? 0 : 14;
+}
+
+} // namespace bgzf

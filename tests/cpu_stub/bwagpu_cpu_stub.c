@@ -140,3 +140,30 @@ int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int level, const ui
 	if (kernel_ms) *kernel_ms = 0;
 	return 0;
 }
+
+int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t n_members, const int64_t *member_off, uint8_t *out,
+                         int64_t out_cap, int64_t *out_off, double *kernel_ms)
+{
+	int64_t total = 0;
+	int k;
+	(void)n_bytes;
+	for (k = 0; k < n_members; ++k) {
+		const uint8_t *m = in + member_off[k];
+		const size_t len = (size_t)(member_off[k + 1] - member_off[k]);
+		uint32_t isize;
+		z_stream zs;
+		memcpy(&isize, m + len - 4, 4);
+		out_off[k] = total;
+		if (total + isize > out_cap) return 1;
+		memset(&zs, 0, sizeof(zs));
+		if (inflateInit2(&zs, -15) != Z_OK) return 1;
+		zs.next_in = (Bytef *)(m + 18); zs.avail_in = (uInt)(len - 26);
+		zs.next_out = out + total; zs.avail_out = isize;
+		if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.total_out != isize) { inflateEnd(&zs); return 1; }
+		inflateEnd(&zs);
+		total += isize;
+	}
+	out_off[n_members] = total;
+	if (kernel_ms) *kernel_ms = 0;
+	return 0;
+}

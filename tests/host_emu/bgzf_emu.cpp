@@ -137,3 +137,25 @@ extern "C" long long bgzf_emu_deflate(const uint8_t *in, long long n_bytes, int 
 	}
 	return total;
 }
+
+// bwa_gpu_bgzf_inflate's kernel body on the CPU: inflate_member is one thread's serial walk, so it runs as it is.
+// status[k] = its return code per member.
+extern "C" int bgzf_emu_inflate(const uint8_t *in, long long n_bytes, int n_members, const long long *member_off, uint8_t *out, long long *out_off,
+                                int *status)
+{
+	static bgzf::InfTables T;
+	long long total = 0;
+	int bad = 0;
+	(void)n_bytes;
+	for (int k = 0; k < n_members; ++k) {
+		const long long a = member_off[k], b = member_off[k + 1];
+		uint32_t isize;
+		memcpy(&isize, in + b - 4, 4);
+		out_off[k] = total;
+		status[k] = isize > 65536 ? 99 : bgzf::inflate_member(in + a, (int)(b - a), out + total, (int)isize, T);
+		bad += status[k] != 0;
+		total += isize > 65536 ? 0 : isize;
+	}
+	out_off[n_members] = total;
+	return bad;
+}

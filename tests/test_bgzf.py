@@ -37,6 +37,17 @@ def emu():
     L.bgzf_emu_deflate.restype = C.c_longlong
     L.bgzf_emu_deflate.argtypes = [C.c_char_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
 
+    L.bgzf_emu_inflate.argtypes = [C.c_char_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def inflate(data: bytes):
+        moff = R.bwa.api.bgzf_member_offsets(data)
+        n = moff.size - 1
+        out = np.zeros(65536 * max(1, n), dtype=np.uint8)
+        ooff = np.zeros(n + 1, dtype=np.int64)
+        status = np.zeros(max(1, n), dtype=np.int32)
+        bad = L.bgzf_emu_inflate(data, len(data), n, moff.ctypes.data, out.ctypes.data, ooff.ctypes.data, status.ctypes.data)
+        return out[: ooff[n]].tobytes(), status[:n], bad
+
     def run(data: bytes, level: int = 2):
         nblk = max(1, (len(data) + BLOCK - 1) // BLOCK)
         out = np.zeros(nblk * 65536, dtype=np.uint8)
@@ -44,6 +55,7 @@ def emu():
         tot = L.bgzf_emu_deflate(data, len(data), level, out.ctypes.data, clen.ctypes.data)
         return out[:tot].tobytes(), clen[: (len(data) + BLOCK - 1) // BLOCK]
 
+    run.inflate = inflate
     return run
 
 
@@ -133,6 +145,68 @@ def test_length_limiter_is_exercised(emu):
     check_members(data.tobytes(), packed, lens)
 
 
+def bgzf_file(data: bytes, level, block: int = 65280, strategy: int = zlib.Z_DEFAULT_STRATEGY) -> bytes:
+    """What a BAM writer produces: zlib-deflated members of `block` input bytes each (the reference: bgzf.c:265-330)."""
+    import bamio
+    out = []
+    for o in range(0, len(data), block):
+        piece = data[o:o + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        body = co.compress(piece) + co.flush()
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(body) + 25) + body
+                   + struct.pack("<II", zlib.crc32(piece) & 0xFFFFFFFF, len(piece)))
+    return b"".join(out) + bamio.BGZF_EOF
+
+
+def inflate_cases():
+    """Members as zlib writes them at every kind of setting: stored (level 0), fixed-code (Z_FIXED), dynamic at levels 1 / 6 / 9,
+    run-length and Huffman-only strategies, tiny blocks, an empty member (the BGZF EOF block), incompressible and skewed data."""
+    rng = np.random.default_rng(31)
+    bam = bam_like(700)
+    yield "bam level 1", bgzf_file(bam, 1), bam
+    yield "bam level 6", bgzf_file(bam, 6), bam
+    yield "bam level 9, 4 KB blocks", bgzf_file(bam[:60000], 9, 4096), bam[:60000]
+    yield "stored", bgzf_file(bam[:100000], 0), bam[:100000]
+    yield "fixed code", bgzf_file(bam[:100000], 6, strategy=zlib.Z_FIXED), bam[:100000]
+    yield "huffman only", bgzf_file(bam[:100000], 6, strategy=zlib.Z_HUFFMAN_ONLY), bam[:100000]
+    yield "rle", bgzf_file(bytes(70000) + b"ab" * 3000, 6, strategy=zlib.Z_RLE), bytes(70000) + b"ab" * 3000
+    rnd = rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()
+    yield "incompressible", bgzf_file(rnd, 6), rnd
+    yield "one byte", bgzf_file(b"A", 6), b"A"
+    text = b"the quick brown fox jumps over the lazy dog. " * 3000
+    yield "long matches", bgzf_file(text, 9), text
+
+
+def test_emulated_inflate_matches_zlib_writers(emu):
+    for name, packed, want in inflate_cases():
+        got, status, bad = emu.inflate(packed)
+        assert bad == 0 and not status.any(), (name, status[status != 0][:5])
+        assert got == want, name
+
+
+def test_emulated_inflate_rejects_damage(emu):
+    bam = bam_like(300)
+    good = bgzf_file(bam, 6)
+    n = int.from_bytes(good[16:18], "little") + 1
+    for where in (30, n // 2, n - 12):  # inside the first member's deflate stream
+        broken = bytearray(good)
+        broken[where] ^= 0x5a
+        got, status, bad = emu.inflate(bytes(broken))
+        assert bad >= 1 or got != bam, where  # a flipped byte either breaks the code or changes the bytes; never a crash
+    truncated = bytearray(good)
+    truncated[n - 4:n] = (12345).to_bytes(4, "little")  # ISIZE that does not match
+    _, status, bad = emu.inflate(bytes(truncated))
+    assert bad >= 1 and status[0] != 0
+
+
+def test_emulated_codec_round_trip_through_itself(emu):
+    """deflate by this codec, inflate by this codec."""
+    data = bam_like(600)
+    packed, lens = emu(data, 2)
+    got, status, bad = emu.inflate(packed)
+    assert bad == 0 and got == data
+
+
 # ------------------------------------------------------------------ the device, through the C-ABI
 @pytest.fixture(scope="module")
 def gpu_api():
@@ -184,3 +258,31 @@ def test_device_random_sizes(gpu_api):
             data = bam_like(n // 260 + 1, seed=n)[:n]
         packed, lens, _ = gpu_api.bgzf_deflate(data, 2)
         check_members(data, packed, lens)
+
+
+@pytest.mark.gpu
+def test_device_inflate_matches_zlib_writers(gpu_api, emu):
+    for name, packed, want in inflate_cases():
+        got, ooff, _ = gpu_api.bgzf_inflate(packed)
+        assert got == want, name
+        assert ooff[-1] == len(want)
+
+
+@pytest.mark.gpu
+def test_device_inflate_large_and_own_members(gpu_api):
+    data = bam_like(90000)  # ~24 MB: ~370 members of zlib's, then of this codec's
+    got, ooff, ms = gpu_api.bgzf_inflate(bgzf_file(data, 1))
+    assert got == data and ms > 0
+    packed, lens, _ = gpu_api.bgzf_deflate(data, 2)
+    got, _, _ = gpu_api.bgzf_inflate(packed)
+    assert got == data
+
+
+@pytest.mark.gpu
+def test_device_inflate_fails_loudly_on_damage(gpu_api):
+    good = bgzf_file(bam_like(300), 6)
+    n = int.from_bytes(good[16:18], "little") + 1
+    broken = bytearray(good)
+    broken[n - 4:n] = (12345).to_bytes(4, "little")
+    with pytest.raises(gpu_api.BwaGpuError, match="not a valid BGZF member"):
+        gpu_api.bgzf_inflate(bytes(broken))

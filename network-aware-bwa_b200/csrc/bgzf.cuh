@@ -672,7 +672,8 @@ __device__ int inflate_member(const uint8_t *in, int in_len, uint8_t *out, int o
 			}
 			for (;;) {
 				const int s = inf_decode(b, T.lcnt, T.lsym);
-				if (s < 0 || bits_over(b)) return 11;
+				if (s < 0) return 11;
+				if (bits_over(b)) return 15;
 				if (s < 256) { if (pos >= out_len) return 3; out[pos++] = (uint8_t)s; }
 				else if (s == 256) break;
 				else {
@@ -694,7 +695,7 @@ __device__ int inflate_member(const uint8_t *in, int in_len, uint8_t *out, int o
 				}
 			}
 		}
-		if (bits_over(b)) return 11;
+		if (bits_over(b)) return 15;
 		if (last) break;
 	}
 	if (pos != out_len) return 14;

@@ -146,7 +146,7 @@ static void *fi_worker(void *arg)
 
 /* The device takes the inflate over as soon as its context exists (bwa_gpu_bgzf_inflate: one thread per BGZF member,
  * FI_DEV_MEMBERS members per call); until then -- the first second of a fresh process, while the index is uploaded -- and with
- * BWAGPU_HOST_INFLATE=1 the zlib workers above do it.  Both fill the same ring in member order. */
+ * BWAGPU_DEVICE_INFLATE unset the zlib workers above do it.  Both fill the same ring in member order. */
 static void *fi_device_worker(void *arg)
 {
 	uint8_t *dbuf = 0;
@@ -284,8 +284,8 @@ static void fastin_start(bamFile fp)
 		F.nth = fi_threads();
 		for (i = 0; i < F.nth; ++i) pthread_create(&F.th[i], 0, fi_worker, 0);
 		{
-			const char *h = getenv("BWAGPU_HOST_INFLATE");
-			if (!(h && atoi(h) != 0)) F.dev_started = pthread_create(&F.dev_th, 0, fi_device_worker, 0) == 0;
+			const char *h = getenv("BWAGPU_DEVICE_INFLATE");
+			if (h && atoi(h) != 0) F.dev_started = pthread_create(&F.dev_th, 0, fi_device_worker, 0) == 0;
 		}
 		F.active = 1;
 		return;

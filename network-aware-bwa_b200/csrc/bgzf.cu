@@ -1,5 +1,6 @@
 // bgzf.cu -- host side of the device BGZF codec (bgzf.cuh): the C-ABI calls, staging, packing of the members.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -89,6 +90,19 @@ __global__ void __launch_bounds__(bgzf::INF_T) k_bgzf_inflate(const uint8_t *__r
 	if (j >= n) return;
 	const bgzf::InfJob J = jobs[j];
 	status[j] = bgzf::inflate_member(in + J.in_off, J.in_len, out + J.out_off, J.out_len, tables[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(32 * bgzf::INFW_WARPS) k_bgzf_inflate_warp(const uint8_t *__restrict__ in, const bgzf::InfJob *__restrict__ jobs, int n,
+                                                                             uint8_t *out, int *__restrict__ status)
+{
+	__shared__ bgzf::InfWarp W[bgzf::INFW_WARPS];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int j = blockIdx.x * bgzf::INFW_WARPS + warp; j < n; j += gridDim.x * bgzf::INFW_WARPS) {
+		const bgzf::InfJob J = jobs[j];
+		const int st = bgzf::inflate_member_warp(in + J.in_off, J.in_len, out + J.out_off, J.out_len, W[warp]);
+		if (lane == 0) status[j] = st;
+		__syncwarp();
+	}
 }
 
 struct Inflater {
@@ -365,7 +379,16 @@ extern "C" int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t 
 	BCK(cudaMemcpyAsync(c.d_in, src, span, cudaMemcpyHostToDevice, c.st));
 	BCK(cudaMemcpyAsync(c.d_jobs, c.h_jobs, n * sizeof(bgzf::InfJob), cudaMemcpyHostToDevice, c.st));
 	BCK(cudaEventRecord(e0, c.st));
-	k_bgzf_inflate<<<(unsigned)((n + bgzf::INF_T - 1) / bgzf::INF_T), bgzf::INF_T, 0, c.st>>>(c.d_in, c.d_jobs, (int)n, c.d_out, c.d_status);
+	{
+		static const int form = getenv("BWAGPU_INFLATE_THREAD_FORM") ? atoi(getenv("BWAGPU_INFLATE_THREAD_FORM")) : 0; // 1: the thread-per-member kernel (A/B)
+		if (form) k_bgzf_inflate<<<(unsigned)((n + bgzf::INF_T - 1) / bgzf::INF_T), bgzf::INF_T, 0, c.st>>>(c.d_in, c.d_jobs, (int)n, c.d_out, c.d_status);
+		else {
+			int n_sm = 148;
+			cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+			const unsigned blocks = (unsigned)std::min<size_t>((n + bgzf::INFW_WARPS - 1) / bgzf::INFW_WARPS, (size_t)n_sm * 6);
+			k_bgzf_inflate_warp<<<blocks, 32 * bgzf::INFW_WARPS, 0, c.st>>>(c.d_in, c.d_jobs, (int)n, c.d_out, c.d_status);
+		}
+	}
 	BCK(cudaEventRecord(e1, c.st));
 	BCK(cudaGetLastError());
 	BCK(cudaMemcpyAsync(c.h_status, c.d_status, n * sizeof(int), cudaMemcpyDeviceToHost, c.st));

@@ -705,4 +705,243 @@ __device__ int inflate_member(const uint8_t *in, int in_len, uint8_t *out, int o
 	return isize == (uint32_t)out_len ? 0 : 14;
 }
 
+
+// ---------------------------------------------------------------- one WARP per member
+// inflate_member above is the plain statement of the decoder (and what the emulated tests pin first); as a kernel it is slow --
+// 32 members in a warp diverge at every symbol, and every match byte is an L2 round trip.  The product kernel gives a member
+// a warp: lane 0 walks the bit stream (a 10-bit lookup table per alphabet, built by all lanes from the canonical tables;
+// longer codes fall back to the canonical walk; the bit buffer is refilled 32 bits at a time from a word loaded one refill
+// earlier) and stores the literals; at a match the warp copies together, 32 bytes per step.
+constexpr int INFW_WARPS = 8;
+constexpr int INF_LB = 10, INF_DB = 9;
+
+struct InfWarp {
+	uint16_t lit[1 << INF_LB], dist[1 << INF_DB]; // symbol | code length << 9; 0 = no code this short
+	InfTables T;
+	uint16_t first[2][16], base[2][16]; // canonical code of the first symbol of each length / its index in T.*sym
+	uint8_t lens[320];
+};
+
+struct WordIn { // lane 0's view of the stream: aligned 32-bit loads, one word ahead
+	const uint32_t *w;
+	const uint8_t *start;
+	long long total_bits; // bits the stream really has
+	unsigned long long buf;
+	uint32_t pre;
+	int n;
+	long long loaded_bits;
+};
+
+__device__ __forceinline__ void win_refill(WordIn &b)
+{
+	if (b.n <= 32) {
+		b.buf |= (unsigned long long)b.pre << b.n;
+		b.n += 32; b.loaded_bits += 32;
+		b.pre = *b.w++;
+	}
+}
+__device__ __forceinline__ uint32_t win_take(WordIn &b, int k) // k <= 16
+{
+	win_refill(b);
+	const uint32_t v = (uint32_t)(b.buf & ((1ull << k) - 1));
+	b.buf >>= k; b.n -= k;
+	return v;
+}
+__device__ __forceinline__ bool win_over(const WordIn &b) { return b.loaded_bits - b.n > b.total_bits; }
+
+__device__ __forceinline__ int win_decode_slow(WordIn &b, const uint16_t *cnt, const uint16_t *sym)
+{
+	win_refill(b);
+	int code = 0, first = 0, index = 0;
+	unsigned long long w = b.buf;
+#pragma unroll 1
+	for (int len = 1; len <= 15; ++len) {
+		code |= (int)(w & 1); w >>= 1;
+		const int c = cnt[len];
+		if (code - c < first) { b.buf >>= len; b.n -= len; return sym[index + (code - first)]; }
+		index += c; first += c;
+		first <<= 1; code <<= 1;
+	}
+	return -1;
+}
+
+// lookup table of one alphabet from its canonical tables, all lanes (which = 0: literal/length, 1: distance)
+__device__ void infw_fill(InfWarp &W, int which, int lane)
+{
+	uint16_t *tab = which ? W.dist : W.lit;
+	const int bits = which ? INF_DB : INF_LB;
+	const uint16_t *cnt = which ? W.T.dcnt : W.T.lcnt, *sym = which ? W.T.dsym : W.T.lsym;
+	for (int i = lane; i < (1 << bits); i += 32) tab[i] = 0;
+	if (lane == 0) {
+		int code = 0, idx = 0;
+		for (int l = 1; l < 16; ++l) { W.first[which][l] = (uint16_t)code; W.base[which][l] = (uint16_t)idx; code = (code + cnt[l]) << 1; idx += cnt[l]; }
+		W.base[which][0] = (uint16_t)idx; // number of coded symbols
+	}
+	__syncwarp();
+	const int n_coded = W.base[which][0];
+	for (int idx = lane; idx < n_coded; idx += 32) {
+		int l = 1;
+		while (l < 15 && idx >= W.base[which][l] + cnt[l]) ++l;
+		if (l > bits) continue;
+		const uint32_t code = (uint32_t)W.first[which][l] + (uint32_t)(idx - W.base[which][l]);
+		const uint32_t r = __brev(code) >> (32 - l);
+		const uint16_t e = (uint16_t)(sym[idx] | l << 9);
+		for (uint32_t k = r; k < (1u << bits); k += 1u << l) tab[k] = e;
+	}
+	__syncwarp();
+}
+
+// the whole warp calls this; returns the member's status (the same on every lane)
+__device__ int inflate_member_warp(const uint8_t *in, int in_len, uint8_t *out, int out_len, InfWarp &W)
+{
+	const int lane = threadIdx.x & 31;
+	const unsigned full = 0xffffffffu;
+	int h = 10, err = 0;
+	if (in_len < 18 || in[0] != 31 || in[1] != 139 || in[2] != 8) return 1;
+	{
+		const int flg = in[3];
+		if (flg & 4) { if (h + 2 > in_len) return 1; h += 2 + (in[h] | in[h + 1] << 8); }
+		if (flg & 8) { while (h < in_len && in[h]) ++h; ++h; }
+		if (flg & 16) { while (h < in_len && in[h]) ++h; ++h; }
+		if (flg & 2) h += 2;
+		if (h + 8 > in_len) return 1;
+	}
+	WordIn b; // meaningful on lane 0
+	{
+		const uint8_t *p = in + h;
+		b.start = p; b.total_bits = 8ll * (in_len - 8 - h);
+		b.buf = 0; b.n = 0; b.loaded_bits = 0;
+		while (((uintptr_t)p & 3) != 0) { b.buf |= (unsigned long long)*p++ << b.n; b.n += 8; b.loaded_bits += 8; } // up to 3 bytes: to a word boundary
+		b.w = (const uint32_t *)p;
+		b.pre = *b.w++;
+	}
+	int pos = 0;
+	for (;;) { // one deflate block per trip
+		int type = 0, last = 0, slen = 0;
+		long long soff = 0;
+		if (lane == 0) {
+			last = (int)win_take(b, 1); type = (int)win_take(b, 2);
+			if (type == 0) { // stored: where its bytes are
+				const int drop = b.n & 7;
+				b.buf >>= drop; b.n -= drop;
+				const uint32_t len = win_take(b, 16), nlen = win_take(b, 16);
+				if ((len ^ nlen) != 0xffffu) err = 2;
+				else if (pos + (int)len > out_len) err = 3;
+				slen = (int)len;
+				soff = (b.loaded_bits - b.n) >> 3; // bytes of the stream consumed so far
+			} else if (type == 3) err = 4;
+			else if (type == 2) { // the code lengths
+				const int hlit = (int)win_take(b, 5) + 257, hdist = (int)win_take(b, 5) + 1, hclen = (int)win_take(b, 4) + 4;
+				if (hlit > 286 || hdist > 30) err = 6;
+				else {
+					const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+					for (int k = 0; k < 19; ++k) W.lens[order[k]] = k < hclen ? (uint8_t)win_take(b, 3) : 0;
+					if (!inf_build(W.lens, 19, W.T.dcnt, W.T.dsym)) err = 7;
+					int k = 0;
+					while (!err && k < hlit + hdist) {
+						const int s = win_decode_slow(b, W.T.dcnt, W.T.dsym);
+						if (s < 0) err = 8;
+						else if (s < 16) W.lens[k++] = (uint8_t)s;
+						else {
+							int rep, v = 0;
+							if (s == 16) { if (k == 0) { err = 8; break; } v = W.lens[k - 1]; rep = 3 + (int)win_take(b, 2); }
+							else if (s == 17) rep = 3 + (int)win_take(b, 3);
+							else rep = 11 + (int)win_take(b, 7);
+							if (k + rep > hlit + hdist) { err = 8; break; }
+							while (rep--) W.lens[k++] = (uint8_t)v;
+						}
+					}
+					if (!err && W.lens[256] == 0) err = 9;
+					if (!err && !inf_build(W.lens, hlit, W.T.lcnt, W.T.lsym)) err = 10;
+					if (!err && !inf_build(W.lens + hlit, hdist, W.T.dcnt, W.T.dsym)) err = 10;
+				}
+			} else { // fixed code (RFC 1951 3.2.6)
+				for (int s = 0; s < 288; ++s) W.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+				inf_build(W.lens, 288, W.T.lcnt, W.T.lsym);
+				for (int s = 0; s < 30; ++s) W.lens[s] = 5;
+				inf_build(W.lens, 30, W.T.dcnt, W.T.dsym);
+			}
+			if (win_over(b)) err = 15;
+		}
+		err = __shfl_sync(full, err, 0);
+		if (err) return err;
+		type = __shfl_sync(full, type, 0); last = __shfl_sync(full, last, 0);
+		if (type == 0) {
+			slen = __shfl_sync(full, slen, 0);
+			soff = __shfl_sync(full, soff, 0);
+			const uint8_t *src = in + h + soff;
+			if (soff + slen > (long long)(in_len - 8 - h)) return 15;
+			for (int i = lane; i < slen; i += 32) out[pos + i] = src[i];
+			pos += slen;
+			if (lane == 0) { // restart the word reader after the copied bytes
+				const uint8_t *p = src + slen;
+				b.buf = 0; b.n = 0; b.loaded_bits = 8ll * (soff + slen);
+				while (((uintptr_t)p & 3) != 0) { b.buf |= (unsigned long long)*p++ << b.n; b.n += 8; b.loaded_bits += 8; }
+				b.w = (const uint32_t *)p;
+				b.pre = *b.w++;
+			}
+			__syncwarp();
+		} else {
+			__syncwarp();
+			infw_fill(W, 0, lane);
+			infw_fill(W, 1, lane);
+			for (;;) { // lane 0 runs to the next match (or the end of the block), the warp copies
+				int ev = 0, len = 0, dist = 0; // ev: 1 match, 2 end of block, else an error code << 2
+				if (lane == 0) {
+					for (;;) {
+						win_refill(b);
+						const uint32_t e = W.lit[b.buf & ((1u << INF_LB) - 1)];
+						int s;
+						if (e) { s = (int)(e & 511u); b.buf >>= (e >> 9); b.n -= (int)(e >> 9); }
+						else s = win_decode_slow(b, W.T.lcnt, W.T.lsym);
+						if (s < 256) {
+							if (s < 0) { ev = 11 << 2; break; }
+							if (pos >= out_len) { ev = 3 << 2; break; }
+							out[pos++] = (uint8_t)s;
+						} else if (s == 256) { ev = 2; break; }
+						else {
+							if (s > 285) { ev = 12 << 2; break; }
+							if (s < 265) len = s - 254;
+							else if (s == 285) len = 258;
+							else { const int x = (s - 261) >> 2; len = 3 + ((4 + ((s - 261) & 3)) << x) + (int)win_take(b, x); }
+							win_refill(b);
+							const uint32_t d = W.dist[b.buf & ((1u << INF_DB) - 1)];
+							int ds;
+							if (d) { ds = (int)(d & 511u); b.buf >>= (d >> 9); b.n -= (int)(d >> 9); }
+							else ds = win_decode_slow(b, W.T.dcnt, W.T.dsym);
+							if (ds < 0 || ds > 29) { ev = 12 << 2; break; }
+							if (ds < 4) dist = ds + 1;
+							else { const int x = (ds >> 1) - 1; dist = 1 + ((2 + (ds & 1)) << x) + (int)win_take(b, x); }
+							if (dist > pos) { ev = 13 << 2; break; }
+							if (pos + len > out_len) { ev = 3 << 2; break; }
+							ev = 1;
+							break;
+						}
+					}
+					if (win_over(b)) ev = 15 << 2;
+				}
+				ev = __shfl_sync(full, ev, 0);
+				pos = __shfl_sync(full, pos, 0);
+				if (ev == 1) {
+					len = __shfl_sync(full, len, 0); dist = __shfl_sync(full, dist, 0);
+					__syncwarp(); // lane 0's literal stores are visible to the lanes that copy from them
+					const uint8_t *src = out + pos - dist;
+					if (dist >= len) { for (int i = lane; i < len; i += 32) out[pos + i] = src[i]; }
+					else if (dist >= 32) { // each step of 32 bytes reads only bytes of earlier steps
+						for (int i0 = 0; i0 < len; i0 += 32) { const int i = i0 + lane; if (i < len) out[pos + i] = src[i]; __syncwarp(); }
+					} else { for (int i = lane; i < len; i += 32) out[pos + i] = src[i % dist]; } // a run: period dist, all of it already written
+					pos += len;
+					__syncwarp();
+				} else if (ev == 2) break;
+				else return ev >> 2;
+			}
+		}
+		if (last) break;
+	}
+	if (pos != out_len) return 14;
+	const uint8_t *t = in + in_len - 4;
+	const uint32_t isize = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+	return isize == (uint32_t)out_len ? 0 : 14;
+}
+
 } // namespace bgzf

@@ -48,6 +48,10 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d)
 {
 	unsigned long long o[32]; collective((unsigned long long)v, o); const int me = emu_lane(); return me >= d ? (T)o[me - d] : v;
 }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src)
+{
+	unsigned long long o[32]; collective((unsigned long long)v, o); return (T)o[src & 31];
+}
 static inline unsigned __match_any_sync(unsigned, uint32_t v)
 {
 	unsigned long long o[32]; collective(v, o);
@@ -77,9 +81,24 @@ struct Job { const uint8_t *in; int len, level; uint8_t *out; int32_t *clen; uin
 static Job g_job;
 static bgzf::Smem g_smem;
 
+// the warp-per-member inflate: the block's 8 warps take the members in turn
+struct WJob { const uint8_t *in; const bgzf::InfJob *jobs; int n; uint8_t *out; int *status; };
+static WJob g_wjob;
+static bgzf::InfWarp g_infw[NW];
+static int g_mode; // 0: deflate_block, 1: inflate_member_warp
+
 static void lane_main(int lane)
 {
 	threadIdx.x = (unsigned)lane;
+	if (g_mode == 1) {
+		const int warp = lane >> 5;
+		for (int j = warp; j < g_wjob.n; j += NW) {
+			const bgzf::InfJob J = g_wjob.jobs[j];
+			const int st = bgzf::inflate_member_warp(g_wjob.in + J.in_off, J.in_len, g_wjob.out + J.out_off, J.out_len, g_infw[warp]);
+			if ((lane & 31) == 0) g_wjob.status[j] = st;
+			__syncwarp();
+		}
+	} else
 	bgzf::deflate_block(g_smem, g_job.in, g_job.len, g_job.level, g_job.out, g_job.clen, g_job.tok, g_job.x2n);
 	g_done[lane] = true;
 	g_cur = lane;
@@ -131,6 +150,7 @@ extern "C" long long bgzf_emu_deflate(const uint8_t *in, long long n_bytes, int 
 		memcpy(aligned_in.data(), in + off, (size_t)len);
 		g_job.in = (const uint8_t *)aligned_in.data(); g_job.len = len; g_job.level = level;
 		g_job.out = (uint8_t *)member.data(); g_job.clen = &clen[k]; g_job.tok = tok.data(); g_job.x2n = x2n;
+		g_mode = 0;
 		run_block();
 		memcpy(out + total, member.data(), (size_t)clen[k]);
 		total += clen[k];
@@ -157,5 +177,31 @@ extern "C" int bgzf_emu_inflate(const uint8_t *in, long long n_bytes, int n_memb
 		total += isize > 65536 ? 0 : isize;
 	}
 	out_off[n_members] = total;
+	return bad;
+}
+
+// the product kernel's body (one warp per member) on the emulated block
+extern "C" int bgzf_emu_inflate_warp(const uint8_t *in, long long n_bytes, int n_members, const long long *member_off, uint8_t *out, long long *out_off,
+                                     int *status)
+{
+	std::vector<uint8_t> padded((size_t)n_bytes + 64, 0); // the word reader looks a few bytes past a member (the device buffer has slack too)
+	std::vector<bgzf::InfJob> jobs((size_t)n_members);
+	long long total = 0;
+	memcpy(padded.data(), in, (size_t)n_bytes);
+	for (int k = 0; k < n_members; ++k) {
+		uint32_t isize;
+		memcpy(&isize, in + member_off[k + 1] - 4, 4);
+		if (isize > 65536) isize = 0;
+		jobs[k].in_off = member_off[k]; jobs[k].in_len = (int)(member_off[k + 1] - member_off[k]);
+		jobs[k].out_off = total; jobs[k].out_len = (int)isize;
+		out_off[k] = total;
+		total += isize;
+	}
+	out_off[n_members] = total;
+	g_wjob.in = padded.data(); g_wjob.jobs = jobs.data(); g_wjob.n = n_members; g_wjob.out = out; g_wjob.status = status;
+	g_mode = 1;
+	run_block();
+	int bad = 0;
+	for (int k = 0; k < n_members; ++k) bad += status[k] != 0;
 	return bad;
 }

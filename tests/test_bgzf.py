@@ -39,13 +39,16 @@ def emu():
 
     L.bgzf_emu_inflate.argtypes = [C.c_char_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
-    def inflate(data: bytes):
+    L.bgzf_emu_inflate_warp.argtypes = L.bgzf_emu_inflate.argtypes
+
+    def inflate(data: bytes, warp_form: bool = True):
         moff = R.bwa.api.bgzf_member_offsets(data)
         n = moff.size - 1
         out = np.zeros(65536 * max(1, n), dtype=np.uint8)
         ooff = np.zeros(n + 1, dtype=np.int64)
         status = np.zeros(max(1, n), dtype=np.int32)
-        bad = L.bgzf_emu_inflate(data, len(data), n, moff.ctypes.data, out.ctypes.data, ooff.ctypes.data, status.ctypes.data)
+        fn = L.bgzf_emu_inflate_warp if warp_form else L.bgzf_emu_inflate
+        bad = fn(data, len(data), n, moff.ctypes.data, out.ctypes.data, ooff.ctypes.data, status.ctypes.data)
         return out[: ooff[n]].tobytes(), status[:n], bad
 
     def run(data: bytes, level: int = 2):
@@ -177,9 +180,11 @@ def inflate_cases():
     yield "long matches", bgzf_file(text, 9), text
 
 
-def test_emulated_inflate_matches_zlib_writers(emu):
+@pytest.mark.parametrize("warp_form", [True, False])
+def test_emulated_inflate_matches_zlib_writers(emu, warp_form):
+    """Both forms of the decoder: the warp-per-member kernel body (the product) and the plain thread-per-member statement."""
     for name, packed, want in inflate_cases():
-        got, status, bad = emu.inflate(packed)
+        got, status, bad = emu.inflate(packed, warp_form)
         assert bad == 0 and not status.any(), (name, status[status != 0][:5])
         assert got == want, name
 

@@ -4,7 +4,9 @@
  *   input BAM     bam_read1 (bamlite.c:125-155) reads through zlib's gzread: one inflate stream on the thread that also
  *                 parses and allocates the records.  Here bam_read1 is REPLACED (it is a plain global of the reference,
  *                 reached through the PLT): the input file's BGZF blocks -- the framing every BAM writer produces -- are
- *                 inflated by a pool of threads into a ring, in block order, and bam_read1 parses records out of the ring.
+ *                 inflated into a ring, in block order, by the device (bwa_gpu_bgzf_inflate, 1024 members per call, a warp
+ *                 per member) or, until the device context exists, by a pool of zlib threads; records are parsed out of the
+ *                 ring a batch at a time.
  *                 A plain (single-stream) gzip input cannot be cut into blocks: it is announced on stderr and read ahead
  *                 by ONE zlib thread instead.
  *   intermediate  pass 1 hands its records to pass 2 through a gzip'ed temporary file (pair_print_custom /
@@ -21,8 +23,8 @@
 #include <unistd.h>
 
 /* ================================================================== input BAM */
-#define FI_SLOTS 1024           /* ring of inflated blocks: 64 MB */
-#define FI_DEV_MEMBERS 256      /* members per device inflate call */
+#define FI_SLOTS 4096           /* ring of inflated blocks: up to 256 MB (touched only as far as the reader runs ahead) */
+#define FI_DEV_MEMBERS 1024     /* members per device inflate call: the kernel gives each a warp, so a call wants many */
 #define FI_BLOCK 65536
 #define FI_MAXTH 16
 enum { FS_FREE = 0, FS_BUSY, FS_FILLED };
@@ -146,7 +148,7 @@ static void *fi_worker(void *arg)
 
 /* The device takes the inflate over as soon as its context exists (bwa_gpu_bgzf_inflate: one thread per BGZF member,
  * FI_DEV_MEMBERS members per call); until then -- the first second of a fresh process, while the index is uploaded -- and with
- * BWAGPU_DEVICE_INFLATE unset the zlib workers above do it.  Both fill the same ring in member order. */
+ * BWAGPU_HOST_INFLATE=1 the zlib workers above do it.  Both fill the same ring in member order. */
 static void *fi_device_worker(void *arg)
 {
 	uint8_t *dbuf = 0;
@@ -284,8 +286,8 @@ static void fastin_start(bamFile fp)
 		F.nth = fi_threads();
 		for (i = 0; i < F.nth; ++i) pthread_create(&F.th[i], 0, fi_worker, 0);
 		{
-			const char *h = getenv("BWAGPU_DEVICE_INFLATE");
-			if (h && atoi(h) != 0) F.dev_started = pthread_create(&F.dev_th, 0, fi_device_worker, 0) == 0;
+			const char *h = getenv("BWAGPU_HOST_INFLATE");
+			if (!(h && atoi(h) != 0)) F.dev_started = pthread_create(&F.dev_th, 0, fi_device_worker, 0) == 0;
 		}
 		F.active = 1;
 		return;

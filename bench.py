@@ -355,8 +355,8 @@ def main():
         # kernels of three lanes and of two passes' stages overlap, so their event times count the same device seconds
         # several times; here every pass is ONE batch on ONE lane -- kernels run one after the other, alone on the device --
         # and the sum of their event times is the device-busy time of the step.
-        pipelined_env = {k: os.environ.get(k) for k in ("BWAGPU_LANES", "BWAGPU_BATCH_RECORDS", "BWAGPU_BATCH_RAMP")}
-        os.environ.update({"BWAGPU_LANES": "1", "BWAGPU_BATCH_RECORDS": str(args.pairs), "BWAGPU_BATCH_RAMP": "0"})
+        pipelined_env = {k: os.environ.get(k) for k in ("BWAGPU_LANES", "BWAGPU_BATCH_RECORDS", "BWAGPU_BATCH_RAMP", "BWAGPU_INFLATE_MEMBERS")}
+        os.environ.update({"BWAGPU_LANES": "1", "BWAGPU_BATCH_RECORDS": str(args.pairs), "BWAGPU_BATCH_RAMP": "0", "BWAGPU_INFLATE_MEMBERS": "16384"})
         host.H.bwa_gpu_batch_reset_device()
         host.run(prefix, bam, out)  # untimed: sets the device up again, sizes the buffers
         api.reset_totals()
@@ -376,7 +376,7 @@ def main():
         host.H.bwa_gpu_batch_reset_device()
     finally:
         restore_stderr(saved)
-    kernel_ms = tot["ms_width"] + tot["ms_search"] + tot["ms_sa"] + tot["ms_sw"] + tot["ms_global"] + tot["ms_bgzf"]
+    kernel_ms = tot["ms_width"] + tot["ms_search"] + tot["ms_sa"] + tot["ms_sw"] + tot["ms_global"] + tot["ms_bgzf"] + tot["ms_inflate"]
     if dist is not None:
         t = torch.tensor([e2e_s, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -395,8 +395,8 @@ def main():
                                      "jobs_sw", "jobs_ga", "dev_bgzf_s", "bytes_bgzf")}
     pipeline["device_call_share_of_wall"] = ((last["dev_aln_s"] + last["dev_sa_s"] + last["dev_sw_s"] + last["dev_ga_s"])
                                              / max(1e-9, last["wall_s"] - last["index_load_s"]))
-    per_step = {k: tot[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global", "ms_bgzf")}
-    per_step_pipelined = {k: tot_e2e[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global", "ms_bgzf")}
+    per_step = {k: tot[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global", "ms_bgzf", "ms_inflate")}
+    per_step_pipelined = {k: tot_e2e[k] / args.steps for k in ("ms_width", "ms_search", "ms_sa", "ms_sw", "ms_global", "ms_bgzf", "ms_inflate")}
 
     if rank != 0:
         host.close()
@@ -492,6 +492,9 @@ def main():
                          "kernel_ms_per_step": per_step["ms_bgzf"], "gb_per_s_in": per_s(tot["bgzf_bytes_in"], tot["ms_bgzf"]) / 1e9,
                          "ratio": tot["bgzf_bytes_out"] / max(1, tot["bgzf_bytes_in"]),
                          "bound": "latency of the per-block LZ77 / Huffman phases (one CTA per 64 KB block, shared memory only); not an HBM-bound kernel"},
+        "bgzf_inflate": {"bytes_in_per_step": tot["inflate_bytes_in"] / args.steps, "bytes_out_per_step": tot["inflate_bytes_out"] / args.steps,
+                         "kernel_ms_per_step": per_step["ms_inflate"], "gb_per_s_out": per_s(tot["inflate_bytes_out"], tot["ms_inflate"]) / 1e9,
+                         "bound": "latency of lane 0's serial walk of each member's bit stream (one warp per member)"},
         "k3_search_in_job": {"kernel_ms_per_step": per_step["ms_search"], "pass_ms_per_step": [x / args.steps for x in tot["ms_search_pass"]]},
     }
 
@@ -520,7 +523,7 @@ def main():
         "kernel_ms_per_step": per_step, "kernel_ms_per_step_pipelined_runs": per_step_pipelined, "parallelism": f"one process + one index replica + one shard of pairs per GPU (x{world}), no collective",
         "timed": "two timed regions of K steps each, both bracketed by barrier + synchronize.  e2e: perf_counter around bwa_bam_to_bam in the "
                  "pipelined configuration (3 lanes, batches of 131072 records).  value: the same K runs with one batch per pass on one "
-                 "lane, so that no two kernels overlap; CUDA events inside the library around every kernel (K2, K3, K4, K5, K6, BGZF), "
+                 "lane, so that no two kernels overlap; CUDA events inside the library around every kernel (K2, K3, K4, K5, K6, BGZF inflate and deflate), "
                  "summed = device-busy time of the job (kernel_ms_per_step); the pipelined runs' event sums are in "
                  "kernel_ms_per_step_pipelined_runs (overlapping kernels counted more than once)",
         "wall_s_timed_region": wall_s + wall_dev_s, "wall_s_e2e_region": wall_s, "wall_s_value_region": wall_dev_s,

@@ -309,8 +309,10 @@ typedef struct {
 	int64_t sw_cells_fwd;                              /* sum of window x read cells of K5's forward pass */
 	int64_t h2d_bytes, d2h_bytes;
 	int64_t occ_fetches_width, occ_fetches_search, own_fetches_search; /* from calls made while stats were enabled */
-	double ms_bgzf;                                    /* BGZF codec kernels (deflate + pack, inflate) */
-	int64_t bgzf_bytes_in, bgzf_bytes_out;             /* bytes into / out of the codec */
+	double ms_bgzf;                                    /* BGZF deflate kernels (deflate + offsets + pack) */
+	int64_t bgzf_bytes_in, bgzf_bytes_out;             /* BAM stream bytes in / member bytes out */
+	double ms_inflate;                                 /* BGZF inflate kernel */
+	int64_t inflate_bytes_in, inflate_bytes_out;       /* member bytes in / BAM stream bytes out */
 } bwa_gpu_totals_t;
 int bwa_gpu_get_totals(bwa_gpu_totals_t *out);
 void bwa_gpu_reset_totals(void);

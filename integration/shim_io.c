@@ -152,14 +152,16 @@ static void *fi_worker(void *arg)
 static void *fi_device_worker(void *arg)
 {
 	uint8_t *dbuf = 0;
-	int64_t moff[FI_DEV_MEMBERS + 1], ooff[FI_DEV_MEMBERS + 1];
+	const char *em = getenv("BWAGPU_INFLATE_MEMBERS");
+	const int M = em && atoi(em) > 0 ? (atoi(em) > (1 << 16) ? 1 << 16 : atoi(em)) : FI_DEV_MEMBERS; /* members per call */
+	int64_t *moff = (int64_t *)malloc(((size_t)M + 1) * sizeof(int64_t)), *ooff = (int64_t *)malloc(((size_t)M + 1) * sizeof(int64_t));
 	(void)arg;
 	while (!shim_device_ready()) {
-		if (F.stop || F.error) return 0;
+		if (F.stop || F.error) { free(moff); free(ooff); return 0; }
 		usleep(2000);
 	}
-	dbuf = (uint8_t *)bwa_gpu_host_alloc((size_t)FI_DEV_MEMBERS * FI_BLOCK);
-	if (!dbuf) return 0; /* the zlib workers carry on */
+	dbuf = (uint8_t *)bwa_gpu_host_alloc((size_t)M * FI_BLOCK);
+	if (!dbuf) { free(moff); free(ooff); return 0; } /* the zlib workers carry on */
 	pthread_mutex_lock(&F.mu);
 	F.dev_active = 1;
 	pthread_mutex_unlock(&F.mu);
@@ -174,7 +176,7 @@ static void *fi_device_worker(void *arg)
 			pthread_mutex_unlock(&F.mu);
 			break;
 		}
-		while (n < FI_DEV_MEMBERS && F.scan < F.map_len) {
+		while (n < M && F.scan < F.map_len) {
 			size_t bsize = 0;
 			if (!bgzf_header_ok(F.map + F.scan, F.map_len - F.scan, &bsize)) {
 				if (n) break; /* hand over what is good first */
@@ -190,7 +192,7 @@ static void *fi_device_worker(void *arg)
 		moff[n] = (int64_t)F.scan;
 		j0 = F.next_job; F.next_job += (uint64_t)n;
 		pthread_mutex_unlock(&F.mu);
-		if (bwa_gpu_bgzf_inflate(F.map, (int64_t)F.map_len, n, moff, dbuf, (int64_t)FI_DEV_MEMBERS * FI_BLOCK, ooff, 0)) {
+		if (bwa_gpu_bgzf_inflate(F.map, (int64_t)F.map_len, n, moff, dbuf, (int64_t)M * FI_BLOCK, ooff, 0)) {
 			fprintf(stderr, "[bwa_gpu_batch] %s: %s\n", F.path, bwa_gpu_last_error());
 			pthread_mutex_lock(&F.mu);
 			F.error = 1;
@@ -216,6 +218,7 @@ static void *fi_device_worker(void *arg)
 	}
 out:
 	bwa_gpu_host_free(dbuf);
+	free(moff); free(ooff);
 	return 0;
 }
 

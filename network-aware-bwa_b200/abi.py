@@ -161,6 +161,7 @@ class totals_t(C.Structure):
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("occ_fetches_width", C.c_int64), ("occ_fetches_search", C.c_int64), ("own_fetches_search", C.c_int64),
         ("ms_bgzf", C.c_double), ("bgzf_bytes_in", C.c_int64), ("bgzf_bytes_out", C.c_int64),
+        ("ms_inflate", C.c_double), ("inflate_bytes_in", C.c_int64), ("inflate_bytes_out", C.c_int64),
     ]
 
     def asdict(self) -> dict:

@@ -13,7 +13,7 @@
 namespace bwagpu {
 int hostprep_fail(const char *fmt, ...); // bwagpu.cu: records the message for bwa_gpu_last_error, returns 1
 int primary_device();                     // bwagpu.cu: the first device of bwa_gpu_init, -1 before it
-void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out); // bwagpu.cu: running totals
+void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out, int inflate); // bwagpu.cu: running totals
 }
 using bwagpu::hostprep_fail;
 
@@ -282,7 +282,7 @@ extern "C" int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int leve
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);
 		if (kernel_ms) *kernel_ms = ms;
-		bwagpu::count_bgzf(3, ms, n_bytes, total);
+		bwagpu::count_bgzf(3, ms, n_bytes, total, 0);
 	}
 	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	*out = c.h_packed; *out_bytes = total;
@@ -398,7 +398,7 @@ extern "C" int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t 
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);
 		if (kernel_ms) *kernel_ms = ms;
-		bwagpu::count_bgzf(1, ms, (int64_t)span, total);
+		bwagpu::count_bgzf(1, ms, (int64_t)span, total, 1);
 	}
 	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	for (size_t k = 0; k < n; ++k)

@@ -209,10 +209,11 @@ static uint32_t env_u32(const char *name, uint32_t dflt)
 namespace bwagpu {
 void bgzf_release(); // bgzf.cu
 int primary_device() { LIFE_SHARED; return g_ctx.empty() ? -1 : g_ctx[0]->dev; }
-void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out)
+void count_bgzf(int launches, double ms, int64_t bytes_in, int64_t bytes_out, int inflate)
 {
-	TOT(g_tot.launches += launches; g_tot.ms_bgzf += ms; g_tot.bgzf_bytes_in += bytes_in; g_tot.bgzf_bytes_out += bytes_out;
-	    g_tot.h2d_bytes += bytes_in; g_tot.d2h_bytes += bytes_out);
+	TOT(g_tot.launches += launches; g_tot.h2d_bytes += bytes_in; g_tot.d2h_bytes += bytes_out;
+	    if (inflate) { g_tot.ms_inflate += ms; g_tot.inflate_bytes_in += bytes_in; g_tot.inflate_bytes_out += bytes_out; }
+	    else { g_tot.ms_bgzf += ms; g_tot.bgzf_bytes_in += bytes_in; g_tot.bgzf_bytes_out += bytes_out; });
 }
 }
 

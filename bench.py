@@ -356,7 +356,7 @@ def main():
         # several times; here every pass is ONE batch on ONE lane -- kernels run one after the other, alone on the device --
         # and the sum of their event times is the device-busy time of the step.
         pipelined_env = {k: os.environ.get(k) for k in ("BWAGPU_LANES", "BWAGPU_BATCH_RECORDS", "BWAGPU_BATCH_RAMP", "BWAGPU_INFLATE_MEMBERS")}
-        os.environ.update({"BWAGPU_LANES": "1", "BWAGPU_BATCH_RECORDS": str(args.pairs), "BWAGPU_BATCH_RAMP": "0", "BWAGPU_INFLATE_MEMBERS": "16384"})
+        os.environ.update({"BWAGPU_LANES": "1", "BWAGPU_BATCH_RECORDS": str(args.pairs), "BWAGPU_BATCH_RAMP": "0", "BWAGPU_INFLATE_MEMBERS": "9216"})  # > the shard's ~8400 BGZF members
         host.H.bwa_gpu_batch_reset_device()
         host.run(prefix, bam, out)  # untimed: sets the device up again, sizes the buffers
         api.reset_totals()

@@ -160,7 +160,15 @@ static void *fi_device_worker(void *arg)
 		if (F.stop || F.error) { free(moff); free(ooff); return 0; }
 		usleep(2000);
 	}
-	dbuf = (uint8_t *)bwa_gpu_host_alloc((size_t)M * FI_BLOCK);
+	{ /* the page-locked landing area is kept between runs of one process (allocating it costs as much as inflating into it) */
+		static uint8_t *kept; static size_t kept_bytes;
+		if ((size_t)M * FI_BLOCK > kept_bytes) {
+			if (kept) bwa_gpu_host_free(kept);
+			kept = (uint8_t *)bwa_gpu_host_alloc((size_t)M * FI_BLOCK);
+			kept_bytes = kept ? (size_t)M * FI_BLOCK : 0;
+		}
+		dbuf = kept;
+	}
 	if (!dbuf) { free(moff); free(ooff); return 0; } /* the zlib workers carry on */
 	pthread_mutex_lock(&F.mu);
 	F.dev_active = 1;
@@ -217,7 +225,6 @@ static void *fi_device_worker(void *arg)
 		}
 	}
 out:
-	bwa_gpu_host_free(dbuf);
 	free(moff); free(ooff);
 	return 0;
 }

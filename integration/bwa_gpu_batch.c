@@ -436,6 +436,19 @@ static size_t ramp_records(size_t B, unsigned q)
 	return b < 8192 ? (B < 8192 ? B : 8192) : b;
 }
 
+/* ... and the last ones shrink again, so that the pipeline drains as fast as it fills: with `left` records to go (0 = not
+ * known) the next batch takes a third of them once fewer than two full batches remain */
+static size_t tail_records(size_t want, size_t B, size_t left)
+{
+	const char *e = getenv("BWAGPU_BATCH_RAMP");
+	size_t b;
+	if ((e && atoi(e) == 0) || left == 0 || left >= 2 * B) return want;
+	b = left / 3;
+	if (b < B / 16) b = B / 16;
+	if (b < 4096) b = 4096;
+	return b < want ? b : want;
+}
+
 static size_t batch_records(void)
 {
 	const char *e = getenv("BWAGPU_BATCH_RECORDS");
@@ -822,6 +835,7 @@ typedef struct {
 	khash_t(isize_infos) *iinfos;
 	double t0, t_read, t_toseq, t_host, t_write, t_destroy[2];
 	long tot_seqs;
+	size_t n_read; /* records the read stage has taken so far */
 	int destroy_done;
 	int align_done; /* the end marker has reached the align stage */
 } pipe1_t;
@@ -856,7 +870,12 @@ static void *stage_read(void *arg)
 		P1_WAIT(P, slot, SL_FREE);
 		t = now();
 		const double c0 = thread_cpu_now();
-		n = fastin_read_pairs(P->ks, recs, ramp_records(P->B, q), &seqs, g_broken_input, g_drop_aligned);
+		{
+			const double done = fastin_progress();
+			const size_t left = done > 0.02 && done < 1.0 ? (size_t)((double)P->n_read * (1.0 - done) / done) : 0;
+			n = fastin_read_pairs(P->ks, recs, tail_records(ramp_records(P->B, q), P->B, left), &seqs, g_broken_input, g_drop_aligned);
+			P->n_read += n;
+		}
 		P->t_read += now() - t;
 		cpu_add(CPU_PARSE, thread_cpu_now() - c0);
 		P->n[slot] = n; P->seqs[slot] = seqs;
@@ -1634,7 +1653,7 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 		P2_WAIT(P, slot, S2_FREE);
 		t1 = now();
 		b->n = 0; b->seqs = 0; b->iinfos = iinfos;
-		const size_t Bq = ramp_records(B, q);
+		const size_t Bq = tail_records(ramp_records(B, q), B, memtemp_spilled() ? 0 : memtemp_left() + (stash_n - stash_at));
 		while (b->n < Bq) {
 			if (stash_at == stash_n) {
 				if (eof) break;

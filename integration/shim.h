@@ -57,11 +57,13 @@ extern int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned;
 void fastin_set_path(const char *path);   /* bwa_bam_open: the file the next bam_read1 stream comes from */
 void fastin_close(void);                  /* bwa_seq_close */
 size_t fastin_read_pairs(bwa_seqio_t *ks, bam_pair_t *recs, size_t B, long *seqs, int broken_input, int drop_aligned); /* a batch of read_bam_pair's */
+double fastin_progress(void);             /* fraction of the input file consumed so far, 0 if unknown */
 double fastin_inflate_seconds(void);      /* CPU seconds the inflate threads spent (all threads summed) */
 
 void memtemp_begin(void);
 int memtemp_put(const void *data, uint32_t len); /* 1 = kept in memory, 0 = caller writes it to the temporary file */
 size_t memtemp_records(void);
+size_t memtemp_left(void);               /* records not yet taken by pass 2 */
 size_t memtemp_bytes(void);
 int memtemp_spilled(void);
 /* next record kept in memory (pass 2), 0 when all were handed out */

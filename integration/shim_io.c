@@ -32,6 +32,7 @@ enum { FS_FREE = 0, FS_BUSY, FS_FILLED };
 typedef struct {
 	uint8_t *buf;
 	int len, state;
+	int clen; /* the member's size in the file */
 	uint64_t seq;
 } fi_slot_t;
 
@@ -55,6 +56,7 @@ typedef struct {
 	double cpu_s;
 	/* consumer */
 	uint64_t cons_seq;
+	size_t cons_file_bytes; /* file bytes of the members handed to the consumer so far */
 	int cons_off, have_slot;
 	size_t skip;
 	/* the batch reader's staging area: decompressed stream bytes [stage_pos, stage_len) come before what the ring holds */
@@ -80,6 +82,9 @@ void fastin_set_path(const char *path)
 }
 
 double fastin_inflate_seconds(void) { return g_inflate_s; }
+
+/* how far through the input file the reader is (0..1; 0 when that is not known: plain gzip, a pipe) */
+double fastin_progress(void) { return F.active && F.bgzf && F.map_len ? (double)F.cons_file_bytes / (double)F.map_len : 0.0; }
 
 static int bgzf_header_ok(const uint8_t *p, size_t left, size_t *bsize)
 {
@@ -136,7 +141,7 @@ static void *fi_worker(void *arg)
 			cpu += thread_cpu_now() - t0;
 			pthread_mutex_lock(&F.mu);
 			if (bad) { fprintf(stderr, "[bwa_gpu_batch] %s: inflate failed in the block at offset %zu\n", F.path, off); F.error = 1; }
-			s->len = (int)isize; s->seq = j; s->state = FS_FILLED;
+			s->len = (int)isize; s->clen = (int)bsize; s->seq = j; s->state = FS_FILLED;
 			pthread_cond_broadcast(&F.cv_filled);
 			pthread_mutex_unlock(&F.mu);
 		}
@@ -218,7 +223,7 @@ static void *fi_device_worker(void *arg)
 			pthread_mutex_unlock(&F.mu);
 			memcpy(s->buf, dbuf + ooff[k], (size_t)(ooff[k + 1] - ooff[k]));
 			pthread_mutex_lock(&F.mu);
-			s->len = (int)(ooff[k + 1] - ooff[k]); s->seq = j0 + (uint64_t)k; s->state = FS_FILLED;
+			s->len = (int)(ooff[k + 1] - ooff[k]); s->clen = (int)(moff[k + 1] - moff[k]); s->seq = j0 + (uint64_t)k; s->state = FS_FILLED;
 			pthread_cond_broadcast(&F.cv_filled);
 			pthread_mutex_unlock(&F.mu);
 			cpu_add(CPU_INFLATE, thread_cpu_now() - c0);
@@ -342,6 +347,7 @@ static int fi_next_block(void)
 	int rc;
 	pthread_mutex_lock(&F.mu);
 	if (F.have_slot) {
+		F.cons_file_bytes += (size_t)F.slot[F.cons_seq % FI_SLOTS].clen;
 		F.slot[F.cons_seq % FI_SLOTS].state = FS_FREE;
 		pthread_cond_broadcast(&F.cv_free);
 		++F.cons_seq;
@@ -679,6 +685,7 @@ int memtemp_put(const void *data, uint32_t len)
 }
 
 size_t memtemp_records(void) { return g_mt.n_rec; }
+size_t memtemp_left(void) { return g_mt.n_rec - g_mt.rd; }
 size_t memtemp_bytes(void) { return g_mt.bytes; }
 int memtemp_spilled(void) { return g_mt.spilled; }
 

@@ -727,7 +727,7 @@ struct WordIn { // lane 0's view of the stream: aligned 32-bit loads, one word a
 	const uint8_t *start;
 	long long total_bits; // bits the stream really has
 	unsigned long long buf;
-	uint32_t pre;
+	uint32_t pre, pre2; // the next two words of the stream, loaded two refills (64 bits of codes) before they are needed
 	int n;
 	long long loaded_bits;
 };
@@ -737,7 +737,8 @@ __device__ __forceinline__ void win_refill(WordIn &b)
 	if (b.n <= 32) {
 		b.buf |= (unsigned long long)b.pre << b.n;
 		b.n += 32; b.loaded_bits += 32;
-		b.pre = *b.w++;
+		b.pre = b.pre2;
+		b.pre2 = *b.w++;
 	}
 }
 __device__ __forceinline__ uint32_t win_take(WordIn &b, int k) // k <= 16
@@ -814,6 +815,7 @@ __device__ int inflate_member_warp(const uint8_t *in, int in_len, uint8_t *out, 
 		while (((uintptr_t)p & 3) != 0) { b.buf |= (unsigned long long)*p++ << b.n; b.n += 8; b.loaded_bits += 8; } // up to 3 bytes: to a word boundary
 		b.w = (const uint32_t *)p;
 		b.pre = *b.w++;
+		b.pre2 = *b.w++;
 	}
 	int pos = 0;
 	for (;;) { // one deflate block per trip
@@ -879,6 +881,7 @@ __device__ int inflate_member_warp(const uint8_t *in, int in_len, uint8_t *out, 
 				while (((uintptr_t)p & 3) != 0) { b.buf |= (unsigned long long)*p++ << b.n; b.n += 8; b.loaded_bits += 8; }
 				b.w = (const uint32_t *)p;
 				b.pre = *b.w++;
+				b.pre2 = *b.w++;
 			}
 			__syncwarp();
 		} else {

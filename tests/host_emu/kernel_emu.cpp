@@ -178,3 +178,6 @@ extern "C" int emu_sa(void *h, long long n, const uint32_t *q, const uint8_t *wh
 	for (long long t = 0; t < n; ++t) { blockIdx.x = (unsigned)t; k_sa(P, n, q, which, out); }
 	return 0;
 }
+
+// the library's restatement of bwa_cal_maxdiff (hostprep.h), for the long-read check of tests/test_kernel_logic.py
+extern "C" int emu_cal_maxdiff(int l, double err, double thres) { return cal_maxdiff(l, err, thres); }

@@ -205,3 +205,18 @@ def test_option_fuzz_matches_reference_live(small_index, emu_index, wemu_index):
         got_w = R.wemu_aln(hw, reads, opt)
         assert got_w[4] == 0 and R.compare_aln(want, got_w, f"fuzz warp {kw}") == []
         assert R.compare_aln(want, R.emu_aln(he, reads, opt), f"fuzz thread {kw}") == []
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+def test_library_maxdiff_matches_reference_for_long_reads():
+    """csrc/hostprep.h cal_maxdiff against the reference's bwa_cal_maxdiff (bwtaln.c:37-49) for every length 1..1000: from
+    ~350 bp on the reference's `int x *= k` wraps around, and the restatement must wrap to the same bits (it multiplies in
+    uint32_t instead of relying on signed overflow)."""
+    E = R.emu()
+    E.emu_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
+    L = R.ref()[0]
+    for fnr in (0.04, 0.01, 0.001, 0.2):
+        f = float(np.float32(fnr))  # gap_opt_t.fnr is a float
+        got = [E.emu_cal_maxdiff(l, 0.02, f) for l in range(1, 1001)]
+        want = [L.bwa_cal_maxdiff(l, 0.02, f) for l in range(1, 1001)]
+        assert got == want, (fnr, [(l + 1, a, b) for l, (a, b) in enumerate(zip(got, want)) if a != b][:5])

@@ -61,8 +61,8 @@ def _link(objs, out: str) -> None:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
 
 
-def build_variant(name: str, defines: list) -> str:
-    """Experiment builds (scripts/ab.sh): bwagpu.cu with -D switches -> variants/libbwagpu_<name>.so,
+def build_variant(name: str, defines: list, units=("bwagpu.cu",)) -> str:
+    """Experiment builds (scripts/ab.sh): the named units with -D switches -> variants/libbwagpu_<name>.so,
     selected at run time with BWAGPU_LIB=<path>.  The other units are shared with the default build."""
     out_dir = os.path.join(HERE, "variants")
     os.makedirs(out_dir, exist_ok=True)
@@ -70,7 +70,7 @@ def build_variant(name: str, defines: list) -> str:
     out = os.path.join(out_dir, f"libbwagpu_{name}.so")
     objs = []
     for src in SOURCES:
-        if src == "bwagpu.cu":
+        if src in units:
             obj = _obj_of(src, "_" + name)
             _compile(src, obj, defines)
         else:

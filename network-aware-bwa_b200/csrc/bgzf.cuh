@@ -5,15 +5,16 @@
 // alignment itself is on the GPU.  The decompressed stream, which is what every BAM reader sees, is byte-identical to the
 // reference's; the compressed bytes are this codec's own (deflate does not prescribe them).
 //
-// One CTA of 256 threads per BGZF block, everything in shared memory:
-//   0. the block's input (<= 65280 bytes) is loaded once; CRC-32 by 256 partial CRCs combined with x^(8 L 2^k) mod P;
-//   1. LZ77, greedy (the reference's level 2 is zlib's deflate_fast): positions are taken 256 at a time --
-//      A  warp 0 walks the 256 positions in order, 32 per step, through a 16 K-entry hash-head table of 4-byte strings:
+// One CTA of 512 threads per BGZF block, everything in shared memory (positions are taken 512 at a time; BGZF_T=256 is the
+// smaller form, 12 % slower):
+//   0. the block's input (<= 65280 bytes) is loaded once; CRC-32 by T partial CRCs combined with x^(8 L 2^k) mod P;
+//   1. LZ77, greedy (the reference's level 2 is zlib's deflate_fast): positions are taken T = 512 at a time --
+//      A  warp 0 walks the batch's positions in order, 32 per step, through a 16 K-entry hash-head table of 4-byte strings:
 //         candidate = the most recent earlier position with the same hash (__match_any_sync finds it inside the step);
 //         the hashes themselves were computed by all threads while the previous batch was being emitted,
 //      B  every thread extends its candidate (4 bytes per compare) -> match length / distance of its position,
 //      C  the greedy parse -- "emit a token at p, continue at p + max(1, len)" -- is a pointer chain; the positions on
-//         the chain from the carried-in start are found by pointer doubling (8 rounds for 256 positions),
+//         the chain from the carried-in start are found by pointer doubling (log2 T rounds),
 //      D  the marked positions become tokens (literal | length, distance) in position order (ballot + scan), counted into
 //         the literal/length and distance histograms;
 //   2. length-limited canonical Huffman codes for both alphabets and for the code-length alphabet (rank sort in parallel,
@@ -27,7 +28,12 @@
 
 namespace bgzf {
 
-constexpr int T = 256;             // threads per CTA
+#ifndef BGZF_T
+#define BGZF_T 512
+#endif
+constexpr int T = BGZF_T;          // threads per CTA = positions per LZ77 batch (256 or 512)
+constexpr int LOG_T = T == 512 ? 9 : 8;
+static_assert(T == 256 || T == 512, "the CRC tree and the pointer doubling are written for 256 or 512 threads");
 constexpr int IN_MAX = 65280;      // input bytes per BGZF block (a stored block of this size still fits 64 KB)
 constexpr int OUT_STRIDE = 65536;  // a finished member is at most this long (BSIZE is 16 bits)
 constexpr int HBITS = 14;
@@ -44,7 +50,7 @@ struct Smem {
 	uint8_t lit_len[288], dist_len[32], cl_len[20];
 	uint16_t cand[T], hash[T], jump[2][T + 2];
 	uint8_t mark[T + 4];
-	uint32_t wsum[8];
+	uint32_t wsum[T / 32];
 	// Huffman construction
 	uint16_t sorted[288], parent[576];
 	uint32_t weight[576];
@@ -55,7 +61,7 @@ struct Smem {
 	uint8_t cl_sym[320], cl_ext[320];
 	int n_cl, hlit, hdist;
 	// CRC
-	uint32_t crc_tab[256], crc_part[T], crc_pow[8];
+	uint32_t crc_tab[256], crc_part[T], crc_pow[LOG_T];
 	// block state
 	int cur;
 	uint32_t bitpos;
@@ -275,7 +281,7 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 	for (int i = t; i < 288; i += T) s.lit_freq[i] = 0;
 	if (t < 32) s.dist_freq[t] = 0;
 	if (t < 20) s.cl_freq[t] = 0;
-	{
+	if (t < 256) {
 		uint32_t c = (uint32_t)t;
 		for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1;
 		s.crc_tab[t] = c;
@@ -307,10 +313,10 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 		s.hash[t] = (uint16_t)pos_hash(s, t, len); // the first batch's hashes (phase A reads them after the barriers below)
 		if (t == 0) {
 			uint32_t p = crc_x2n(x2n, (uint32_t)L, 3); // x^(8 L)
-			for (int k = 0; k < 8; ++k) { s.crc_pow[k] = p; p = crc_mulmod(p, p); }
+			for (int k = 0; k < LOG_T; ++k) { s.crc_pow[k] = p; p = crc_mulmod(p, p); }
 		}
 		__syncthreads();
-		for (int k = 0; k < 8; ++k) {
+		for (int k = 0; k < LOG_T; ++k) {
 			const int span = 1 << k;
 			if ((t & (2 * span - 1)) == 0) s.crc_part[t] = crc_mulmod(s.crc_pow[k], s.crc_part[t]) ^ s.crc_part[t + span];
 			__syncthreads();
@@ -371,7 +377,7 @@ __device__ void deflate_block(Smem &s, const uint8_t *__restrict__ in, int len, 
 			__syncthreads();
 			// C: after round r the first 2^(r+1) positions of the chain are marked, jump = 2^(r+1) steps along it
 #pragma unroll 1
-			for (int r = 0; r < 8; ++r) {
+			for (int r = 0; r < LOG_T; ++r) {
 				const int j = s.jump[r & 1][t];
 				if (s.mark[t]) s.mark[j] = 1;
 				s.jump[(r + 1) & 1][t] = s.jump[r & 1][j];

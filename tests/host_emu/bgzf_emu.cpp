@@ -16,7 +16,10 @@
 #define __forceinline__ inline
 #define __restrict__
 
-static const int NT = 256, NW = NT / 32;
+#ifndef BGZF_T
+#define BGZF_T 512
+#endif
+static const int NT = BGZF_T, NW = NT / 32;
 struct emu_dim3 { unsigned x, y, z; };
 static emu_dim3 threadIdx = {0, 0, 0};
 static ucontext_t g_sched, g_ctx[NT];

@@ -25,6 +25,15 @@ using bwagpu::hostprep_fail;
 
 namespace {
 
+// wait for a stream without spinning on a host core (the host code of a bam2bam run needs them all)
+static cudaError_t stream_sync_blocking(cudaStream_t st, cudaEvent_t &ev)
+{
+	cudaError_t e = cudaSuccess;
+	if (!ev) e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+	return e != cudaSuccess ? e : cudaEventSynchronize(ev);
+}
+
 __global__ void __launch_bounds__(bgzf::T, 2) k_bgzf_deflate(bgzf::Params P)
 {
 	extern __shared__ __align__(16) unsigned char bgzf_smem_raw[];
@@ -109,6 +118,7 @@ struct Inflater {
 	std::mutex mu;
 	int dev = -1;
 	cudaStream_t st = nullptr;
+	cudaEvent_t ev_sync = nullptr;
 	uint8_t *d_in = nullptr, *d_out = nullptr, *h_in = nullptr, *h_out = nullptr;
 	size_t cap_in = 0, cap_out = 0, cap_h_in = 0, cap_h_out = 0;
 	bgzf::InfJob *d_jobs = nullptr, *h_jobs = nullptr;
@@ -120,6 +130,8 @@ struct Inflater {
 		cudaSetDevice(dev);
 		cudaFree(d_in); cudaFree(d_out); cudaFree(d_jobs); cudaFree(d_status);
 		cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFreeHost(h_jobs); cudaFreeHost(h_status);
+		if (ev_sync) cudaEventDestroy(ev_sync);
+		ev_sync = nullptr;
 		if (st) cudaStreamDestroy(st);
 		d_in = d_out = h_in = h_out = nullptr; d_jobs = h_jobs = nullptr; d_status = h_status = nullptr;
 		cap_in = cap_out = cap_h_in = cap_h_out = cap_jobs = 0;
@@ -132,6 +144,7 @@ struct Codec {
 	std::mutex mu;
 	int dev = -1;
 	cudaStream_t st = nullptr;
+	cudaEvent_t ev_sync = nullptr;
 	uint8_t *d_in = nullptr, *d_out = nullptr, *d_packed = nullptr;
 	size_t cap_in = 0, cap_blocks = 0;
 	int32_t *d_clen = nullptr;
@@ -150,6 +163,8 @@ struct Codec {
 		cudaSetDevice(dev);
 		cudaFree(d_in); cudaFree(d_out); cudaFree(d_packed); cudaFree(d_clen); cudaFree(d_off); cudaFree(d_tok);
 		cudaFreeHost(h_in); cudaFreeHost(h_packed); cudaFreeHost(h_clen); cudaFreeHost(h_off);
+		if (ev_sync) cudaEventDestroy(ev_sync);
+		ev_sync = nullptr;
 		if (st) cudaStreamDestroy(st);
 		d_in = d_out = d_packed = nullptr; d_clen = nullptr; d_off = nullptr; d_tok = nullptr;
 		h_in = h_packed = nullptr; h_clen = nullptr; h_off = nullptr;
@@ -274,10 +289,10 @@ extern "C" int bwa_gpu_bgzf_deflate(const uint8_t *in, int64_t n_bytes, int leve
 	BCK(cudaGetLastError());
 	BCK(cudaMemcpyAsync(c.h_clen, c.d_clen, n_blocks * sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
 	BCK(cudaMemcpyAsync(c.h_off, c.d_off, (n_blocks + 1) * sizeof(long long), cudaMemcpyDeviceToHost, c.st));
-	BCK(cudaStreamSynchronize(c.st));
+	BCK(stream_sync_blocking(c.st, c.ev_sync));
 	const long long total = c.h_off[n_blocks];
 	BCK(cudaMemcpyAsync(c.h_packed, c.d_packed, (size_t)total, cudaMemcpyDeviceToHost, c.st));
-	BCK(cudaStreamSynchronize(c.st));
+	BCK(stream_sync_blocking(c.st, c.ev_sync));
 	{
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);
@@ -393,7 +408,7 @@ extern "C" int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t 
 	BCK(cudaGetLastError());
 	BCK(cudaMemcpyAsync(c.h_status, c.d_status, n * sizeof(int), cudaMemcpyDeviceToHost, c.st));
 	if (total) BCK(cudaMemcpyAsync(out_pinned ? out : c.h_out, c.d_out, (size_t)total, cudaMemcpyDeviceToHost, c.st));
-	BCK(cudaStreamSynchronize(c.st));
+	BCK(stream_sync_blocking(c.st, c.ev_sync));
 	{
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);

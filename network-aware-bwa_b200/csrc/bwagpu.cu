@@ -132,6 +132,7 @@ struct Ctx {
 	int n_sm = 0;
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev[16] = {};
+	cudaEvent_t ev_sync = nullptr; // cudaEventBlockingSync: a waiting host thread sleeps instead of spinning on a core the host code needs
 	// index
 	DevIndex ix[2] = {};
 	DevBuf<uint4> blk_all; // both strands' occ blocks in ONE allocation (one L2 persistence window)
@@ -183,6 +184,13 @@ struct Ctx {
 static bwa_gpu_totals_t g_tot = {};
 static std::mutex g_tot_mu;
 #define TOT(stmt) do { std::lock_guard<std::mutex> tg_(g_tot_mu); stmt; } while (0)
+
+// wait for everything queued on the lane's stream, without burning a host core while it runs
+static cudaError_t lane_sync(Ctx *c)
+{
+	const cudaError_t e = cudaEventRecord(c->ev_sync, c->st);
+	return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_sync);
+}
 
 static std::vector<Ctx *> g_ctx; // search lanes, device by device
 static std::vector<Ctx *> g_svc; // one service lane per device: K4, K5, K6
@@ -242,6 +250,7 @@ extern "C" void bwa_gpu_destroy(void)
 		c->h_counters.release();
 		c->d_q.release(); c->d_qo.release(); c->d_which.release(); c->sw.release();
 		for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+		if (c->ev_sync) cudaEventDestroy(c->ev_sync);
 		if (c->st) cudaStreamDestroy(c->st);
 		delete c;
 	}
@@ -296,6 +305,7 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 			c->n_sm = prop.multiProcessorCount;
 			CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
 			for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+			CK(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
 			if (ln < lanes) g_ctx.push_back(c); else g_svc.push_back(c);
 		}
 		g_groups = (int)std::min<uint32_t>(env_u32("BWAGPU_CALL_GROUPS", 1), (uint32_t)lanes);
@@ -339,7 +349,7 @@ static int upload_index_one(Ctx *c, bwt_t *const bwt[2], const ubyte_t *pac, int
 			CK(cudaMemcpyAsync(c->sa[s].p, &m1, 4, cudaMemcpyHostToDevice, c->st));
 			ix.sa = c->sa[s].p; ix.n_sa = b->n_sa; ix.sa_intv = (uint32_t)b->sa_intv;
 		} else c->has_sa = false;
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		raw.release();
 	}
 	c->has_pac = false;
@@ -347,7 +357,7 @@ static int upload_index_one(Ctx *c, bwt_t *const bwt[2], const ubyte_t *pac, int
 		const size_t nb = (size_t)(l_pac / 4 + 1);
 		if (c->pac.reserve(nb)) return 1;
 		CK(cudaMemcpyAsync(c->pac.p, pac, nb, cudaMemcpyHostToDevice, c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		c->l_pac = l_pac;
 		c->has_pac = true;
 	}
@@ -597,7 +607,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		unsigned long long init[16] = {0};
 		init[11] = init[12] = ~0ull;
 		CK(cudaMemcpyAsync(c->d_stats.p, init, sizeof init, cudaMemcpyHostToDevice, c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 	}
 
 	// K2
@@ -618,14 +628,14 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	if (stats) {
 		unsigned long long hs[16];
 		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		c->stats.occ_fetches_width += (int64_t)hs[0];
 		c->stats.own_fetches_width += (int64_t)hs[1];
 		TOT(g_tot.occ_fetches_width += (int64_t)hs[0]);
 		unsigned long long init[16] = {0};
 		init[11] = init[12] = ~0ull;
 		CK(cudaMemcpyAsync(c->d_stats.p, init, sizeof init, cudaMemcpyHostToDevice, c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 	}
 
 	// job order for pass 0: longest-looking searches first (k_job_keys)
@@ -698,7 +708,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		if (t == 1 && warp_pass_enabled() && warp_stats_enabled()) { // diagnostics of k_search_warp (search_warp.cuh)
 			unsigned long long w[16];
 			CK(cudaMemcpyAsync(w, c->d_stats.p + 16, sizeof w, cudaMemcpyDeviceToHost, c->st));
-			CK(cudaStreamSynchronize(c->st));
+			CK(lane_sync(c));
 			CK(cudaMemsetAsync(c->d_stats.p + 16, 0, sizeof w, c->st));
 			const double r = (double)std::max<unsigned long long>(w[0], 1);
 			fprintf(stderr, "[k_search_warp] reads %llu rounds %llu taken/round %.2f committed/round %.2f steps/lane %.2f longest chain/round %.2f | "
@@ -707,7 +717,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			        w[5] / r, w[6] / r, w[7] / r, w[8] / r, w[9] / r);
 		}
 		CK(cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		{
 			float tms = 0;
 			CK(cudaEventElapsedTime(&tms, c->ev[8 + 2 * t], c->ev[9 + 2 * t]));
@@ -729,7 +739,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 			CK(cudaMemcpyAsync(bigger, c->d_pool.p, pool_cap * sizeof(uint4), cudaMemcpyDeviceToDevice, c->st));
 			const unsigned int rewind = (unsigned int)pool_cap;
 			CK(cudaMemcpyAsync(c->d_counters.p + 2, &rewind, sizeof rewind, cudaMemcpyHostToDevice, c->st));
-			CK(cudaStreamSynchronize(c->st));
+			CK(lane_sync(c));
 			cudaFree(c->d_pool.p);
 			c->d_pool.p = bigger; c->d_pool.cap = want;
 			pool_cap = want;
@@ -744,7 +754,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	if (stats) {
 		unsigned long long hs[16];
 		CK(cudaMemcpyAsync(hs, c->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost, c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		c->stats.occ_fetches_search += (int64_t)hs[0];
 		c->stats.own_fetches_search += (int64_t)hs[1];
 		TOT(g_tot.occ_fetches_search += (int64_t)hs[0]; g_tot.own_fetches_search += (int64_t)hs[1]);
@@ -761,7 +771,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		if (getenv("BWAGPU_PRINT_HIST")) { // diagnostics: where in the read the lookups happen, and how the work per read is distributed
 			unsigned long long h[64];
 			CK(cudaMemcpyAsync(h, c->d_stats.p + 32, sizeof h, cudaMemcpyDeviceToHost, c->st));
-			CK(cudaStreamSynchronize(c->st));
+			CK(lane_sync(c));
 			fprintf(stderr, "[k_search] lookups by depth (len - i; last = 31+):");
 			for (int q = 0; q < 32; ++q) fprintf(stderr, " %llu", h[q]);
 			fprintf(stderr, "\n[k_search] reads by log2(pops):");
@@ -775,7 +785,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		// read order while it unpacks.  No kernel after k_search: a small kernel of this lane would have to
 		// wait for SM slots behind another lane's persistent k_search, and the lanes would fall into step.
 		CK(cudaEventRecord(c->ev[4], c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		float ms0 = 0;
 		CK(cudaEventElapsedTime(&ms0, c->ev[1], c->ev[2])); c->stats.ms_width += ms0; TOT(g_tot.ms_width += ms0);
 		CK(cudaEventElapsedTime(&ms0, c->ev[2], c->ev[3])); c->stats.ms_search += ms0; TOT(g_tot.ms_search += ms0);
@@ -791,7 +801,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 	c->stats.launches += 2;
 	uint32_t tot = 0;
 	CK(cudaMemcpyAsync(&tot, c->d_outoff.p + n, 4, cudaMemcpyDeviceToHost, c->st));
-	CK(cudaStreamSynchronize(c->st));
+	CK(lane_sync(c));
 	if (c->d_out.reserve((size_t)tot + 1)) return 1;
 	if (n > 0) {
 		k_gather_aln<<<(n + 255) / 256, 256, 0, c->st>>>(n, c->d_naln.p, c->d_pooloff.p, c->d_outoff.p, c->d_pool.p, c->d_out.p);
@@ -799,7 +809,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
 		c->stats.launches++;
 	}
 	CK(cudaEventRecord(c->ev[4], c->st));
-	CK(cudaStreamSynchronize(c->st));
+	CK(lane_sync(c));
 	float ms = 0;
 	CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.ms_width += ms; TOT(g_tot.ms_width += ms);
 	CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->stats.ms_search += ms; TOT(g_tot.ms_search += ms);
@@ -952,7 +962,7 @@ static int run_range(Ctx *c, FlatJob &J)
 		CK(cudaMemcpyAsync(c->h_pooloff.p, c->d_pooloff.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
 		if (tot) CK(cudaMemcpyAsync(c->h_out.p, c->d_pool.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, c->st));
 		CK(cudaEventRecord(c->ev[6], c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.ms_h2d += ms;
 		CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->stats.ms_d2h += ms;
@@ -1200,7 +1210,7 @@ extern "C" int bwa_gpu_probe_random_sectors(int64_t buffer_bytes, int chains, in
 		else k_probe_gather<8><<<blocks, threads, 0, c->st>>>(buf, n_blk, steps, 17u * rep, sink);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ev[6], c->st));
-		CK(cudaStreamSynchronize(c->st));
+		CK(lane_sync(c));
 		float ms = 0;
 		CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]));
 		const int ch = chains <= 1 ? 1 : chains == 2 ? 2 : chains <= 4 ? 4 : 8;
@@ -1240,7 +1250,7 @@ extern "C" int bwa_gpu_resident_stage(int n, const uint8_t *bases, const int64_t
 	if (c->d_seq.reserve(n_bases + 1) || c->d_meta.reserve(n)) return 1;
 	CK(cudaMemcpyAsync(c->d_seq.p, c->h_seq.p, n_bases, cudaMemcpyHostToDevice, c->st));
 	CK(cudaMemcpyAsync(c->d_meta.p, c->h_meta.p, (size_t)n * sizeof(ReadMeta), cudaMemcpyHostToDevice, c->st));
-	CK(cudaStreamSynchronize(c->st));
+	CK(lane_sync(c));
 	c->res_n = n; c->res_w_entries = (size_t)wo; c->res_opt = to_gapopt(opt); c->res_nstacks = n_stacks;
 	c->res_valid = true;
 	return 0;
@@ -1259,7 +1269,7 @@ extern "C" int bwa_gpu_resident_run(double *ms)
 	int64_t tot = 0;
 	if (run_chunk_device(c, c->res_n, c->res_w_entries, c->res_opt, c->res_nstacks, &tot, true)) return 1;
 	CK(cudaEventRecord(c->ev[7], c->st));
-	CK(cudaStreamSynchronize(c->st));
+	CK(lane_sync(c));
 	float t = 0;
 	CK(cudaEventElapsedTime(&t, c->ev[0], c->ev[7]));
 	c->stats.ms_total_device = t;
@@ -1322,7 +1332,7 @@ extern "C" int bwa_gpu_cal_pac_pos(int64_t n, const bwtint_t *sa_idx, const uint
 			CK(cudaGetLastError());
 			CK(cudaEventRecord(c->ev[15], c->st));
 			CK(cudaMemcpyAsync(out_sa + r0, c->d_qo.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->st));
-			CK(cudaStreamSynchronize(c->st));
+			CK(lane_sync(c));
 			float ms = 0;
 			CK(cudaEventElapsedTime(&ms, c->ev[14], c->ev[15]));
 			TOT(g_tot.ms_sa += ms; g_tot.launches += 1; g_tot.sa_queries += m; g_tot.h2d_bytes += m * 5; g_tot.d2h_bytes += m * 4);

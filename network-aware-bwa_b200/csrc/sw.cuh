@@ -671,6 +671,14 @@ __global__ void __launch_bounds__(32 * GW_WARPS) k_global_warp(const uint8_t *__
 struct SwScratch {
 	void *p[12] = {};
 	size_t cap[12] = {};
+	cudaEvent_t ev_sync = nullptr; // blocking-sync event: the waiting host thread sleeps
+	cudaError_t sync(cudaStream_t st)
+	{
+		cudaError_t e = cudaSuccess;
+		if (!ev_sync) e = cudaEventCreateWithFlags(&ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
+		if (e == cudaSuccess) e = cudaEventRecord(ev_sync, st);
+		return e != cudaSuccess ? e : cudaEventSynchronize(ev_sync);
+	}
 	cudaError_t reserve(int k, size_t bytes)
 	{
 		if (bytes <= cap[k]) return cudaSuccess;
@@ -681,7 +689,12 @@ struct SwScratch {
 		if (e == cudaSuccess) cap[k] = want;
 		return e;
 	}
-	void release() { for (int k = 0; k < 12; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; } }
+	void release()
+	{
+		for (int k = 0; k < 12; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
+		if (ev_sync) cudaEventDestroy(ev_sync);
+		ev_sync = nullptr;
+	}
 };
 
 struct SwCounts { long long cells_fwd = 0, h2d = 0, d2h = 0; int launches = 0; };
@@ -799,7 +812,7 @@ static int sw_batch(SwScratch &S, cudaStream_t st, const uint8_t *d_pac, int64_t
 		SWCK(cudaMemcpyAsync(pres, d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t), cudaMemcpyDeviceToHost, st));
 		if (cig_total) SWCK(cudaMemcpyAsync(cigars->data(), d_cig, (size_t)cig_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
 	}
-	SWCK(cudaStreamSynchronize(st));
+	SWCK(S.sync(st));
 	if (kernel_ms) {
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e2); kernel_ms[0] = ms;
@@ -886,7 +899,7 @@ static int ga_seqs_batch(SwScratch &S, cudaStream_t st, int n, const bwa_gpu_ga_
 	SWCK(cudaEventRecord(e1, st));
 	SWCK(cudaMemcpyAsync(pres, d_pres, (size_t)n * sizeof(bwa_gpu_path_res_t), cudaMemcpyDeviceToHost, st));
 	if (cig_total) SWCK(cudaMemcpyAsync(cigars->data(), d_cig, (size_t)cig_total * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-	SWCK(cudaStreamSynchronize(st));
+	SWCK(S.sync(st));
 	{
 		float ms = 0;
 		cudaEventElapsedTime(&ms, e0, e1);

@@ -1,10 +1,11 @@
-# A/B experiment runner: bash scripts/ab.sh <variant> [<variant> ...]   ("base" = the default library)
-A="--steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extras"
+# A/B experiment runner for k_search: bash scripts/ab.sh <variant> [<variant> ...]   ("base" = the default library;
+# a variant = network-aware-bwa_b200/variants/libbwagpu_<variant>.so made by build.build_variant(name, defines[, units])).
+# Times K2 + K3 on resident C4 reads (scripts/kbench.py) and checks 10 k reads against the live reference.
+K="python scripts/kbench.py --genome-bp 3100000000 --read-len 100 --reads 2000000 --reps 3 --check 10000"
 for v in "$@"; do
   if [ "$v" = "base" ]; then unset BWAGPU_LIB; else export BWAGPU_LIB=$PWD/network-aware-bwa_b200/variants/libbwagpu_$v.so; fi
-  echo "== $v"
-  python bench.py $A 2>/dev/null | python -c "
+  $K --tag $v 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']
-print('value %.4g ms/step %.1f width %.1f tiers %s t2 %d stored/read %.0f own/read %.0f parity %s' % (d['value'], d['ms_per_step'], r['width_ms_per_step'], [round(x,1) for x in r['tier_ms_per_step']], d['config']['tier2_reads'], r['stored_pushes_per_read'], r['own_32B_blocks_per_read'], d['parity_sample']['mismatches']), r['pops_per_read'], r['per_read'], r['stats_pass_ms'])"
+d=json.loads(sys.stdin.read()); f=d['full']
+print('%-12s search %.1f ms  width %.1f ms  %.2f M reads/s  mismatches %s' % (d['tag'], f['ms_search'], f['ms_width'], f['mreads_per_s'], d.get('mismatches')))"
 done

@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aln-only", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-pairs", type=int, default=50_000, help="pairs of the shard run through `bam2bam -t 1` as well (untimed), every record compared")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -407,7 +408,8 @@ def main():
     parity = None
     if not args.no_parity and os.path.exists(REF_BWA):
         try:
-            small = prefix_bam(bam, min(args.pairs, 20_000))
+            n_par = min(args.pairs, args.parity_pairs)
+            small = prefix_bam(bam, n_par)
             saved = quiet_stderr(rank)
             try:
                 host.run(prefix, small, small[:-4] + ".gpu_out.bam")
@@ -416,7 +418,7 @@ def main():
             run_reference(prefix, small, small[:-4] + ".ref_out.bam", 1)
             n, bad = records_differing(small[:-4] + ".ref_out.bam", small[:-4] + ".gpu_out.bam")
             parity = {"records": n, "records_differing": bad,
-                      "checker": "oracle/_ref/bwa bam2bam -t 1 on the first 20000 pairs of the shard, whole records compared"}
+                      "checker": f"oracle/_ref/bwa bam2bam -t 1 on the first {n_par} pairs of the shard, whole records compared"}
         except Exception as e:  # the checker is optional on the bench box
             parity = {"error": str(e)[:300]}
 

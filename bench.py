@@ -523,7 +523,7 @@ def main():
         "parity_sample": parity, "aln_only": aln_only, "other_kernels": other, "pipeline_last_step_rank0": pipeline,
         "kernel_ms_per_step": per_step, "kernel_ms_per_step_pipelined_runs": per_step_pipelined, "parallelism": f"one process + one index replica + one shard of pairs per GPU (x{world}), no collective",
         "timed": "two timed regions of K steps each, both bracketed by barrier + synchronize.  e2e: perf_counter around bwa_bam_to_bam in the "
-                 "pipelined configuration (3 lanes, batches of 131072 records).  value: the same K runs with one batch per pass on one "
+                 "pipelined configuration (4 lanes in 2 groups, batches of 131072 records).  value: the same K runs with one batch per pass on one "
                  "lane, so that no two kernels overlap; CUDA events inside the library around every kernel (K2, K3, K4, K5, K6, BGZF inflate and deflate), "
                  "summed = device-busy time of the job (kernel_ms_per_step); the pipelined runs' event sums are in "
                  "kernel_ms_per_step_pipelined_runs (overlapping kernels counted more than once)",

@@ -657,34 +657,23 @@ static void destroy_records(bam_pair_t *recs, size_t n)
 	cpu_add(CPU_DESTROY, thread_cpu_now() - c0);
 }
 
-/* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file).  The reference's encoder
- * (msg_init_from_pair: one malloc'ed message per record) runs on the host threads; the messages are appended in record order. */
-typedef struct { bam_pair_t *recs; zmq_msg_t *msgs; } enc_ctx_t;
-static void encode_one(size_t i, void *ctx)
-{
-	enc_ctx_t *c = (enc_ctx_t *)ctx;
-	msg_init_from_pair(&c->msgs[i], &c->recs[i]);
-}
-
+/* pass 1: records [0, n) -> memory (or, once that is full, the reference's temporary file).  Serial on purpose: the encoder
+ * mallocs one message per record and the chunks are appended in order */
 static void store_records(gzFile temporary, bam_pair_t *recs, size_t n)
 {
-	static zmq_msg_t *msgs; static size_t m_msgs;
-	enc_ctx_t c;
 	size_t i;
-	if (n > m_msgs) { m_msgs = n + n / 4; msgs = (zmq_msg_t *)realloc(msgs, m_msgs * sizeof(*msgs)); }
-	c.recs = recs; c.msgs = msgs;
-	t_cpu_bucket = CPU_STORE;
-	parallel_for(n, 2048, encode_one, &c);
 	for (i = 0; i < n; ++i) {
-		zmq_msg_t *m = &msgs[i];
-		uint32_t len = (uint32_t)zmq_msg_size(m);
-		if (!memtemp_put(zmq_msg_data(m), len)) { /* pair_print_custom's two writes (bam2bam.c:1104-1105) */
-			if (gzwrite(temporary, &len, sizeof(len)) != (int)sizeof(len) || gzwrite(temporary, zmq_msg_data(m), len) != (int)len) {
+		zmq_msg_t m;
+		uint32_t len;
+		msg_init_from_pair(&m, &recs[i]);
+		len = (uint32_t)zmq_msg_size(&m);
+		if (!memtemp_put(zmq_msg_data(&m), len)) { /* pair_print_custom's two writes (bam2bam.c:1104-1105) */
+			if (gzwrite(temporary, &len, sizeof(len)) != (int)sizeof(len) || gzwrite(temporary, zmq_msg_data(&m), len) != (int)len) {
 				fprintf(stderr, "[bwa_gpu_batch] error writing temporary file\n");
 				exit(1);
 			}
 		}
-		zmq_msg_close(m);
+		zmq_msg_close(&m);
 	}
 }
 

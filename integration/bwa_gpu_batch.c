@@ -302,6 +302,7 @@ pe_opt_t *bwa_init_pe_opt(void)
 
 /* bwa_bam_to_bam (bam2bam.c:1942): the reference keeps four of its long options in statics nobody can see; parse the same
  * command line with the reference's own option table first, then hand over.  Also the clock of the whole run. */
+static void env_defaults(void);
 int bwa_bam_to_bam(int argc, char *argv[], char *version)
 {
 	REAL(int, bwa_bam_to_bam, int, char **, char *);
@@ -310,6 +311,7 @@ int bwa_bam_to_bam(int argc, char *argv[], char *version)
 	double t0;
 	memcpy(av, argv, (size_t)argc * sizeof(char *));
 	av[argc] = 0;
+	env_defaults(); /* no stage thread exists yet */
 	g_only_aligned = g_broken_input = g_skip_duplicates = g_drop_aligned = 0;
 	memset(&g_rep, 0, sizeof(g_rep));
 	memset(g_cpu_ns, 0, sizeof(g_cpu_ns));
@@ -394,6 +396,17 @@ static void report(void)
 	        (long)g_rep.calls_ga, (long)g_rep.jobs_ga, g_rep.dev_ga_s, (long)g_rep.calls_bgzf, (long)g_rep.bytes_bgzf, g_rep.dev_bgzf_s);
 }
 
+/* The library's configuration this host wants, unless the user said otherwise.  setenv() may move `environ`, so it must not
+ * run beside a getenv() of another thread (ensure_gpu runs on a thread of its own next to the reader, whose getenv() calls
+ * crashed once in ~60 loaded runs when the setenv()s were there): it runs when the shim is loaded and at the top of every
+ * bwa_bam_to_bam, before any stage thread exists. */
+__attribute__((constructor)) static void env_defaults(void)
+{
+	setenv("BWAGPU_LANES", "4", 0);       /* two search calls in flight (the two align threads of pass 1), two lanes each */
+	setenv("BWAGPU_CALL_GROUPS", "2", 0);
+	setenv("BWAGPU_MALLOPT", "1", 0); /* this host frees millions of aln[] per batch: keep the heaps (a process-wide choice, ours to make) */
+}
+
 static void ensure_gpu(void)
 {
 	static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
@@ -411,9 +424,6 @@ static void ensure_gpu(void)
 		if (n < 1) n = 1;
 		if (n > 16) n = 16;
 		for (i = 0; i < n; ++i) ids[i] = first + i;
-		setenv("BWAGPU_LANES", "4", 0);       /* two search calls in flight (the two align threads of pass 1), two lanes each */
-		setenv("BWAGPU_CALL_GROUPS", "2", 0);
-		setenv("BWAGPU_MALLOPT", "1", 0); /* this host frees millions of aln[] per batch: keep the heaps (a process-wide choice, ours to make) */
 		if (bwa_gpu_init(n, ids)) die("bwa_gpu_init");
 	}
 	if (bwa_gpu_load_index(g_bwt, g_pac, g_bns->l_pac)) die("bwa_gpu_load_index");

@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <vector>
 #include "../../include/bwa_gpu.h"
+#include "sw_cell.h"
 
 namespace bwagpu {
 
@@ -49,6 +50,58 @@ struct SwJob {
 
 __device__ __forceinline__ int sw_sc(int r, int q) { return q > 3 ? -13 : (r == q ? 11 : -19); }
 __device__ __forceinline__ int pac_base(const uint8_t *pac, long long k) { return (pac[k >> 2] >> ((~k & 3) << 1)) & 3; }
+
+// One sweep of pass 1 over <= 32 * C reference columns (col0+1 .. col_end): lane t owns C consecutive columns -- the
+// strip's G = H - qr and E of the previous row and its bases live in registers -- and handles read row j at step j + t - 1;
+// the strip's right edge (G and the running F) moves to lane t+1 by shuffle, the edge between two sweeps through edge_h /
+// edge_f.  Columns past col_end are padding: base 5 equals no read base, and a cell that only mismatches can only pass on
+// values strictly below a real cell's (F < the H to its left, E < the H above, diagonal + mismatch < the diagonal), so
+// padding never holds the first maximum.  The first maximum of a row's strip comes from one key per cell,
+// H * 16 + (15 - column in the strip): a maximum over keys is the highest H at its lowest column.
+template <int C>
+__device__ __forceinline__ void sw_sweep(const uint8_t *q, const uint8_t *refb, int *edge_h, int *edge_f, const bool from_edge,
+                                         const bool last_sb, const int col0, const int col_end, const int len2, const int lane,
+                                         int &best, int &best_i, int &best_j)
+{
+	static_assert(C >= 2 && C <= 16 && (C & 1) == 0, "columns per lane");
+	const unsigned full = 0xffffffffu;
+	const int my0 = col0 + lane * C; // my columns: my0+1 .. my0+C
+	int G[C], E[C], R[C];
+#pragma unroll
+	for (int c = 0; c < C; ++c) {
+		G[c] = -SWC_QR; E[c] = 0;
+		R[c] = my0 + c < col_end ? refb[my0 + c] : 5;
+	}
+	int g_out = -SWC_QR, f_out = 0, diag_in = -SWC_QR;
+	for (int s = 0; s < len2 + 31; ++s) {
+		const int j = s - lane + 1;
+		int g_in = __shfl_up_sync(full, g_out, 1);
+		int f_in = __shfl_up_sync(full, f_out, 1);
+		const bool row_ok = j >= 1 && j <= len2;
+		if (lane == 0) {
+			g_in = (from_edge && row_ok) ? edge_h[j] - SWC_QR : -SWC_QR;
+			f_in = (from_edge && row_ok) ? edge_f[j] : 0;
+		}
+		if (row_ok) {
+			const SwRow row = swc_row(q[j - 1]);
+			int left = g_in, f = f_in, diag = diag_in, key = 0;
+			diag_in = g_in;
+#pragma unroll
+			for (int c = 0; c < C; c += 2) {
+				const int up0 = G[c], up1 = G[c + 1];
+				const int h0 = swc_cell(row, R[c], up0, E[c], diag, left, f);
+				G[c] = h0 - SWC_QR;
+				const int h1 = swc_cell(row, R[c + 1], up1, E[c + 1], up0, G[c], f);
+				G[c + 1] = h1 - SWC_QR;
+				diag = up1; left = G[c + 1];
+				key = swc_max3(key, h0 * 16 + (15 - c), h1 * 16 + (14 - c));
+			}
+			g_out = left; f_out = f;
+			if (!last_sb && lane == 31) { edge_h[j] = left + SWC_QR; edge_f[j] = f; }
+			if ((key >> 4) > best) { best = key >> 4; best_j = j; best_i = my0 + 16 - (key & 15); }
+		}
+	}
+}
 
 // smem per warp: read bases (len2_max bytes, padded to 4), edge_h/edge_f (len2_max+1 ints each),
 // rev_h/rev_e (len1_max+2 ints each)
@@ -89,52 +142,16 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 		for (int sb = 0; sb < n_sb; ++sb) {
 			const int col0 = sb * 32 * SW_CMAX;                 // columns col0+1 .. col0+cols
 			const int cols = min(len1 - col0, 32 * SW_CMAX);
-			const int C = (cols + 31) >> 5;                     // columns per lane in this sweep
-			const int my0 = col0 + lane * C;                    // my columns: my0+1 .. my0+C (clipped to len1)
-			const int my_n = max(0, min(C, col0 + cols - my0));
-			int H[SW_CMAX], E[SW_CMAX], R[SW_CMAX];
-#pragma unroll
-			for (int c = 0; c < SW_CMAX; ++c) {
-				H[c] = 0; E[c] = 0;
-				R[c] = c < my_n ? refb[my0 + c] : 0;
-			}
-			int h_out = 0, f_out = 0, diag_in = 0;
 			const bool last_sb = sb == n_sb - 1;
-			for (int s = 0; s < len2 + 31; ++s) {
-				const int j = s - lane + 1;
-				int h_in = __shfl_up_sync(full, h_out, 1);
-				int f_in = __shfl_up_sync(full, f_out, 1);
-				const bool row_ok = j >= 1 && j <= len2;
-				if (lane == 0) {
-					h_in = (sb && row_ok) ? edge_h[j] : 0;
-					f_in = (sb && row_ok) ? edge_f[j] : 0;
-				}
-				if (row_ok && my_n > 0) {
-					const int qj = q[j - 1];
-					int last_h = h_in, f = f_in, diag = diag_in;
-					diag_in = h_in;
-#pragma unroll
-					for (int c = 0; c < SW_CMAX; ++c) {
-						if (c < my_n) {
-							const int up = H[c];
-							int h = diag + sw_sc(R[c], qj), e = 0;
-							if (h < 0) h = 0;
-							if (last_h > 0) { // stdaln.c:611-614
-								f = f > last_h - SW_Q ? f - SW_R : last_h - SW_QR;
-								if (h < f) h = f;
-							}
-							if (up >= SW_QR + 1) { // stdaln.c:615-619
-								e = E[c] > up - SW_Q ? E[c] - SW_R : up - SW_QR;
-								if (h < e) h = e;
-							}
-							E[c] = e; H[c] = h;
-							diag = up; last_h = h;
-							if (best < h) { best = h; best_i = my0 + c + 1; best_j = j; }
-						}
-					}
-					h_out = last_h; f_out = f;
-					if (!last_sb && lane == 31) { edge_h[j] = last_h; edge_f[j] = f; }
-				}
+			switch ((((cols + 31) >> 5) + 1) >> 1) {            // columns per lane, rounded up to even (warp-uniform)
+			case 1: sw_sweep<2>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			case 2: sw_sweep<4>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			case 3: sw_sweep<6>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			case 4: sw_sweep<8>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			case 5: sw_sweep<10>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			case 6: sw_sweep<12>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			case 7: sw_sweep<14>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
+			default: sw_sweep<16>(q, refb, edge_h, edge_f, sb != 0, last_sb, col0, col0 + cols, len2, lane, best, best_i, best_j); break;
 			}
 			__syncwarp();
 		}

@@ -220,3 +220,36 @@ def test_library_maxdiff_matches_reference_for_long_reads():
         got = [E.emu_cal_maxdiff(l, 0.02, f) for l in range(1, 1001)]
         want = [L.bwa_cal_maxdiff(l, 0.02, f) for l in range(1, 1001)]
         assert got == want, (fnr, [(l + 1, a, b) for l, (a, b) in enumerate(zip(got, want)) if a != b][:5])
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("seed,read_len,win", [(1, (20, 150), (20, 500)), (2, (20, 260), (20, 1400)), (3, (1, 40), (1, 70))])
+def test_sw_forward_cell_matches_reference(seed, read_len, win):
+    """K5 pass 1 as the kernel computes it (csrc/sw_cell.h: G = H - qr state, F updated unconditionally, DPX-shaped max
+    chains; csrc/sw.cuh sw_sweep: strips of C columns with padding, first-maximum keys), on the CPU around the kernel's own
+    cell function (tests/host_emu/sw_emu.cpp), against aln_local_core's score and end cell (stdaln.c:608-627): windows of
+    one to three 512-column sweeps, reads with N, indels, and reads that have nothing to do with their window."""
+    import os
+    import subprocess
+    src = os.path.join(R.EMU_DIR, "sw_emu.cpp")
+    so = os.path.join(R.EMU_DIR, "libsw_emu.so")
+    cell = os.path.join(R.ROOT, "network-aware-bwa_b200", "csrc", "sw_cell.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(cell)):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
+    E = C.CDLL(so)
+    E.sw_emu_pass1.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    T = R.bwa.simulate.make_genome(300000, seed=21, repeat_frac=0.05)
+    n = 2000
+    refs, ro, qs, qo = R.make_sw_jobs(T, n, seed=seed, ref_n=False, read_len=read_len, win=win)
+    want = R.ref_sw_batch(refs, ro, qs, qo)
+    out = (C.c_int * 3)()
+    bad = []
+    for i in range(n):
+        r = np.ascontiguousarray(refs[ro[i]:ro[i + 1]])
+        q = np.ascontiguousarray(qs[qo[i]:qo[i + 1]])
+        E.sw_emu_pass1(r.ctypes.data, r.size, q.ctypes.data, q.size, out)
+        w = want[i]
+        ok = out[0] == w[0] if w[0] < 1 else (out[0], out[1], out[2]) == (w[0], w[3], w[4])
+        if not ok:
+            bad.append((i, list(out), list(w)))
+    assert not bad, bad[:5]

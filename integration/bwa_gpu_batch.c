@@ -186,6 +186,7 @@ int g_broken_input, g_skip_duplicates, g_drop_aligned, g_only_aligned; /* bam2ba
 static isize_info_t g_null_ii; /* bam2bam.c:106 */
 static bwa_gpu_batch_report_t g_rep; /* the run in progress / the last run (bwa_gpu_batch.h) */
 static double g_cpu0;
+static int g_trace, g_trace_pass; /* BWAGPU_TRACE=1: every stage hand-over on stderr (seconds since the call, pass, slot, new state) */
 static double g_t_call, g_t_pass1_begin, g_t_pass1_end, g_t_pass2_begin, g_t_pass2_end; /* where a run's wall time goes outside the passes */
 
 /* The index of a long-lived host process (bench.py runs bam2bam several times in one process): with keep_index on, the
@@ -312,6 +313,7 @@ int bwa_bam_to_bam(int argc, char *argv[], char *version)
 	memcpy(av, argv, (size_t)argc * sizeof(char *));
 	av[argc] = 0;
 	env_defaults(); /* no stage thread exists yet */
+	{ const char *e = getenv("BWAGPU_TRACE"); g_trace = e && atoi(e) != 0; }
 	g_only_aligned = g_broken_input = g_skip_duplicates = g_drop_aligned = 0;
 	memset(&g_rep, 0, sizeof(g_rep));
 	memset(g_cpu_ns, 0, sizeof(g_cpu_ns));
@@ -394,6 +396,14 @@ static void report(void)
 	                "mate_sw_path=%ld (%ld jobs, %.2f s)  global_align=%ld (%ld jobs, %.2f s)  bgzf_deflate=%ld (%ld bytes, %.2f s)\n", (long)g_rep.calls_aln, (long)g_rep.reads_aln,
 	        g_rep.dev_aln_s, (long)g_rep.calls_sa, (long)g_rep.q_sa, g_rep.dev_sa_s, (long)g_rep.calls_sw, (long)g_rep.jobs_sw, g_rep.dev_sw_s,
 	        (long)g_rep.calls_ga, (long)g_rep.jobs_ga, g_rep.dev_ga_s, (long)g_rep.calls_bgzf, (long)g_rep.bytes_bgzf, g_rep.dev_bgzf_s);
+	{ /* the kernels inside those calls (CUDA events in the library; kernels of different lanes overlap) */
+		bwa_gpu_totals_t t;
+		if (bwa_gpu_get_totals(&t) == 0)
+			fprintf(stderr, "[bwa_gpu_batch] kernel ms since the device was set up: widths %.1f, search %.1f (passes %.1f / %.1f / %.1f), SA %.1f, SW %.1f, "
+			                "global %.1f, BGZF deflate %.1f, inflate %.1f; %ld launches; H2D %.0f MB, D2H %.0f MB\n", t.ms_width, t.ms_search,
+			        t.ms_search_pass[0], t.ms_search_pass[1], t.ms_search_pass[2], t.ms_sa, t.ms_sw, t.ms_global, t.ms_bgzf, t.ms_inflate,
+			        (long)t.launches, (double)t.h2d_bytes / 1e6, (double)t.d2h_bytes / 1e6);
+	}
 }
 
 /* The library's configuration this host wants, unless the user said otherwise.  setenv() may move `environ`, so it must not
@@ -859,6 +869,7 @@ static void slot_wait(pthread_mutex_t *mu, pthread_cond_t *cv, const int *state,
 
 static void slot_set(pthread_mutex_t *mu, pthread_cond_t *cv, int *state, int st)
 {
+	if (g_trace) fprintf(stderr, "[trace] %.4f pass %d slot %p -> %d\n", now() - g_t_call, g_trace_pass, (void *)state, st);
 	pthread_mutex_lock(mu);
 	*state = st;
 	pthread_cond_broadcast(cv);
@@ -1035,7 +1046,7 @@ void sequential_loop_pass1(bwa_seqio_t *ks, gzFile temporary, khash_t(isize_info
 	memset(&P, 0, sizeof(P));
 	pthread_mutex_init(&P.mu, 0); pthread_cond_init(&P.cv, 0);
 	P.B = B; P.ks = ks; P.temporary = temporary; P.iinfos = iinfos; P.t0 = now();
-	g_t_pass1_begin = P.t0;
+	g_t_pass1_begin = P.t0; g_trace_pass = 1;
 	for (s = 0; s < P1_SLOTS; ++s) P.recs[s] = (bam_pair_t *)calloc(B, sizeof(bam_pair_t));
 	memtemp_begin();
 	/* device context + index upload (seconds) overlap the reading of the first batches */
@@ -1633,6 +1644,7 @@ static void *stage2_destroy(void *arg) /* the free()s of a written batch, off th
 void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) *iinfos)
 {
 	const double t_begin_ = (g_t_pass2_begin = now());
+	g_trace_pass = 2;
 	const size_t B = batch_records();
 	const long long max_q = getenv("BWAGPU_BATCH_SA") ? atoll(getenv("BWAGPU_BATCH_SA")) : 1ll << 25; /* SA rows per device call */
 	pipe2_t *P = (pipe2_t *)calloc(1, sizeof(pipe2_t));

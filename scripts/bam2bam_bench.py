@@ -2,8 +2,9 @@
 """End-to-end `bam2bam` (BAM in -> BAM out, both passes) on one box: the unmodified reference on the host
 CPUs (`-t 1` sequential = the bit-exact oracle, and `-t N` through its 0MQ mux) against the same binary
 with integration/libbwa_gpu_batch.so pre-loaded (hot path on the B200, one device call per phase and batch).
-Also checks that the batched run's BAM records equal the `-t 1` run's.  TEST/BENCH INFRASTRUCTURE: drives
-oracle/_ref/ref_driver; nothing here is on the product path.
+Also checks that the batched run's BAM records equal the `-t 1` run's, every record of the CPU sample.  The CPU arms run
+oracle/_ref/bwa (the unmodified reference binary), the GPU arms integration/_host/bwa_host (the product's host: the
+unmodified reference as a shared library) with the batched drivers pre-loaded.
 
     python scripts/bam2bam_bench.py --mode se --reads 2000000 --len 76 --genome-bp 100000000 [--cpu-sample 200000]
     python scripts/bam2bam_bench.py --mode pe --reads 1000000 --len 100 --genome-bp 100000000
@@ -27,7 +28,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bamio  # noqa: E402
 
 bwa = importlib.import_module("network-aware-bwa_b200")
-DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+REF_BWA = os.path.join(ROOT, "oracle", "_ref", "bwa")
+DRIVER = os.path.join(ROOT, "integration", "_host", "bwa_host")
 SHIM = os.path.join(ROOT, "integration", "libbwa_gpu_batch.so")
 
 
@@ -52,7 +54,7 @@ def run(prefix, bam_in, bam_out, threads, preload, extra, env_extra=None):
         env["LD_PRELOAD"] = SHIM
     env.update(env_extra or {})
     t0 = time.time()
-    r = subprocess.run([DRIVER, "bam2bam", "-g", prefix, "-t", str(threads), *extra, "-f", bam_out, bam_in], capture_output=True, text=True, env=env)
+    r = subprocess.run([DRIVER if preload else REF_BWA, "bam2bam", "-g", prefix, "-t", str(threads), *extra, "-f", bam_out, bam_in], capture_output=True, text=True, env=env)
     dt = time.time() - t0
     if r.returncode != 0:
         raise RuntimeError(r.stderr[-3000:])
@@ -72,6 +74,8 @@ def main():
     ap.add_argument("--extra", default="", help="extra bam2bam options, e.g. '-l 1024 -n 0.01 -o 2'")
     ap.add_argument("--out", default="")
     ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--gpu-env", action="append", default=[], help="a further run of the big GPU arm with these settings, e.g. name:BWAGPU_HOST_INFLATE=1,BWAGPU_TRACE=1")
+    ap.add_argument("--log-dir", default="", help="keep every arm's whole stderr here")
     ap.add_argument("--stub", action="store_true", help="dry run without a GPU: tests/cpu_stub answers the device calls")
     a = ap.parse_args()
     dev = a.device
@@ -102,9 +106,12 @@ def main():
     per = 2 if a.mode == "pe" else 1
     res = {"mode": a.mode, "read_len": a.len, "genome_bp": a.genome_bp, "records_gpu": a.reads, "records_cpu": n_small, "host_threads": a.threads}
 
-    def arm(name, bam, n, threads, preload):
+    def arm(name, bam, n, threads, preload, env_extra=None):
         out = os.path.join(d, name + ".bam")
-        dt, load_s, log = run(prefix, bam, out, threads, preload, extra)
+        dt, load_s, log = run(prefix, bam, out, threads, preload, extra, env_extra)
+        if a.log_dir:
+            os.makedirs(a.log_dir, exist_ok=True)
+            open(os.path.join(a.log_dir, f"b2b_{a.mode}_{name}.log"), "w").write(log)
         res[name] = {"wall_s": round(dt, 2), "index_load_s": load_s, "reads_per_s": round(n * per / max(dt - load_s, 1e-9)),
                      "log_tail": [l for l in log.splitlines() if ("processed in" in l and "(" in l) or "device calls" in l or "finish =" in l][-5:]}
         print(f"[b2b] {name}: {dt:.1f}s ({load_s:.1f}s index load) -> {res[name]['reads_per_s']} reads/s", file=sys.stderr)
@@ -114,6 +121,9 @@ def main():
     arm("cpu_tN", small, n_small, a.threads, False)
     o_gpu_s = arm("gpu_batched_small", small, n_small, 1, True)
     arm("gpu_batched", big, a.reads, 1, True)
+    for spec in a.gpu_env:
+        name, _, kv = spec.partition(":")
+        arm("gpu_batched_" + name, big, a.reads, 1, True, dict(x.split("=", 1) for x in kv.split(",") if x))
     x, y = bamio.read_bam_records(o_cpu1), bamio.read_bam_records(o_gpu_s)
     res["records_compared"] = len(x)
     res["records_differing"] = sum(1 for p, q in zip(x, y) if p != q) + abs(len(x) - len(y))

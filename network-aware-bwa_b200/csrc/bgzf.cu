@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 
 #include "../../include/bwa_gpu.h"
@@ -322,6 +323,14 @@ extern "C" int bwa_gpu_bgzf_inflate(const uint8_t *in, int64_t n_bytes, int32_t 
 	if (n_members == 0) return 0;
 	const int dev = bwagpu::primary_device();
 	if (dev < 0) return hostprep_fail("bwa_gpu_bgzf_inflate: bwa_gpu_init has not been called (no CPU fallback)");
+	struct CallTrace { // BWAGPU_TRACE=1: the call's wall time on stderr
+		int n; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+		~CallTrace()
+		{
+			static const bool on = getenv("BWAGPU_TRACE") && atoi(getenv("BWAGPU_TRACE"));
+			if (on) fprintf(stderr, "[trace] bgzf_inflate of %d members: %.1f ms\n", n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		}
+	} call_trace{n_members};
 	Inflater &c = g_inflater;
 	std::lock_guard<std::mutex> g(c.mu);
 	if (c.dev != dev) {

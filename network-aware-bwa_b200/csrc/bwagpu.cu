@@ -80,15 +80,32 @@ extern "C" const char *bwa_gpu_last_error(void)
 }
 
 // ------------------------------------------------------------------ buffers
+// BWAGPU_TRACE=1: every (re)allocation with its wall time on stderr -- cudaFree / cudaMallocHost synchronise with the device
+// and with every other thread's CUDA calls, so a growing buffer in mid-run stalls all lanes.
+static bool trace_on() { static const bool on = getenv("BWAGPU_TRACE") != nullptr && atoi(getenv("BWAGPU_TRACE")) != 0; return on; }
+struct AllocTrace {
+	const char *what; size_t bytes; std::chrono::steady_clock::time_point t0;
+	AllocTrace(const char *w, size_t b) : what(w), bytes(b), t0(std::chrono::steady_clock::now()) {}
+	~AllocTrace()
+	{
+		if (!trace_on()) return;
+		static const auto T0 = std::chrono::steady_clock::now();
+		const auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[trace] %s %.1f MB: %.1f ms (at %.0f ms)\n", what, (double)bytes / 1048576.0,
+		        std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t1 - T0).count());
+	}
+};
+
 template <typename T> struct DevBuf {
 	T *p = nullptr;
 	size_t cap = 0;
 	int reserve(size_t n)
 	{
 		if (n <= cap) return 0;
+		size_t want = n + n / 8 + 256;
+		AllocTrace tr(p ? "device buffer regrown" : "device buffer", want * sizeof(T));
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = n + n / 8 + 256;
 		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
 		if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
 		cap = want;
@@ -105,6 +122,7 @@ template <typename T> struct PinBuf {
 		if (n <= cap) return 0;
 		size_t want = n + n / 4 + 256;
 		T *q = nullptr;
+		AllocTrace tr(p ? "pinned buffer regrown" : "pinned buffer", want * sizeof(T));
 		cudaError_t e = cudaMallocHost((void **)&q, want * sizeof(T));
 		if (e != cudaSuccess) return fail("cudaMallocHost(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
 		if (p) { if (keep) memcpy(q, p, cap * sizeof(T)); cudaFreeHost(p); }

@@ -99,8 +99,10 @@ def main():
     big, small = os.path.join(d, "in.bam"), os.path.join(d, "in_small.bam")
     n_small = min(a.cpu_sample, a.reads)
     t0 = time.time()
-    bamio.write_unaligned_bam(small, subset(r1, n_small), subset(r2, n_small) if r2 is not None else None)
-    bamio.write_unaligned_bam(big, r1, r2)
+    # BGZF-framed input, as sequencer pipelines / samtools write it (bamio.write_unaligned_bam's plain gzip stream would send
+    # the shim down its one-thread reader: "input is not a BGZF file")
+    bamio.write_unaligned_bam_fast(small, subset(r1, n_small), subset(r2, n_small) if r2 is not None else None)
+    bamio.write_unaligned_bam_fast(big, r1, r2)
     print(f"[b2b] input BAMs {time.time() - t0:.1f}s", file=sys.stderr)
     extra = a.extra.split()
     per = 2 if a.mode == "pe" else 1

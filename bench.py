@@ -218,6 +218,45 @@ def restore_stderr(saved):
         os.close(saved)
 
 
+class Outputs:
+    """A fresh output path per run, as a user's successive jobs have; finished outputs are deleted by a background thread.
+    (Writing every step over the previous step's file puts the deletion of that file's 250 MB -- open(O_TRUNC) at the start,
+    ext4's flush-on-close of a truncated-and-rewritten file at the end: 0.1 s of a 1.3 s step -- inside the job.)"""
+
+    def __init__(self, stem: str):
+        import queue
+        import threading
+        self.stem, self.n, self.live = stem, 0, []
+        self.q = queue.Queue()
+        self.th = threading.Thread(target=self._reaper, daemon=True)
+        self.th.start()
+
+    def _reaper(self):
+        while True:
+            path = self.q.get()
+            if path is None:
+                return
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+
+    def next(self) -> str:
+        while len(self.live) > 1:  # keep the latest one (a reader may want it), drop the rest
+            self.q.put(self.live.pop(0))
+        path = f"{self.stem}.{os.getpid()}.{self.n}.bam"
+        self.n += 1
+        self.live.append(path)
+        return path
+
+    def close(self):
+        for path in self.live:
+            self.q.put(path)
+        self.live = []
+        self.q.put(None)
+        self.th.join()
+
+
 def records_differing(a_path: str, b_path: str):
     import bamio
     a, b = bamio.read_bam_records(a_path), bamio.read_bam_records(b_path)
@@ -248,7 +287,8 @@ def main():
     host_cores = os.cpu_count() or 1
     config = {"workload": workload_name(args.genome_bp, args.read_len), "pairs_per_step_per_gpu": args.pairs, "read_len": args.read_len,
               "genome_bp": args.genome_bp,
-              "l2": f"inputs larger than L2 (re-laid-out index {args.genome_bp / 1e9:.2f} GB per replica); the same shard every step"}
+              "l2": f"inputs larger than L2 (re-laid-out index {args.genome_bp / 1e9:.2f} GB per replica); the same shard every step",
+              "outputs": "every step writes a fresh output BAM; older outputs are deleted by a background thread of the harness"}
 
     import torch
     bwa = importlib.import_module("network-aware-bwa_b200")
@@ -272,13 +312,14 @@ def main():
         # reference runs ~35 k pairs/s on 16 cores, its rate does not depend on the length of the run
         ref_pairs = min(args.pairs, max(50_000, int(args.ref_budget_s * 2200 * host_cores / max(1, args.steps))))
         sample = bam if ref_pairs == args.pairs else prefix_bam(bam, ref_pairs)
-        out = bam[:-4] + ".ref_out.bam"
+        outs = Outputs(bam[:-4] + ".ref_out")
         for _ in range(args.warmup):  # page cache / index files warm: short runs
-            run_reference(prefix, small, out, host_cores)
+            run_reference(prefix, small, outs.next(), host_cores)
         total_t, loads, steps_ms = 0.0, [], []
         for _ in range(args.steps):
-            dt, load_s = run_reference(prefix, sample, out, host_cores)
+            dt, load_s = run_reference(prefix, sample, outs.next(), host_cores)
             total_t += dt; loads.append(load_s); steps_ms.append(round(dt * 1e3, 1))
+        outs.close()
         value = 2 * ref_pairs * args.steps / total_t
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -317,7 +358,7 @@ def main():
         return genome["T"]
 
     bam = pairs_bam(bwa, prefix, T, args.pairs, args.read_len, 1000 + rank, f"cuda:{local_rank}")
-    out = f"{bam[:-4]}.out.bam"
+    outs = Outputs(f"{bam[:-4]}.out")  # a fresh output file per run
     aln_reads = None
     if rank == 0 and not args.no_aln_only:
         aln_reads = bwa.simulate.simulate_reads(T(), args.aln_reads, args.read_len, seed=1000, device=f"cuda:{local_rank}")
@@ -336,7 +377,7 @@ def main():
     saved = quiet_stderr(rank)
     try:
         for _ in range(max(1, args.warmup)):  # the first run also loads the index and sets the device up
-            host.run(prefix, bam, out)
+            host.run(prefix, bam, outs.next())
         api.reset_totals()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -345,7 +386,7 @@ def main():
         e2e_s, steps_ms, reps = 0.0, [], []
         for _ in range(args.steps):
             t1 = time.perf_counter()
-            rep = host.run(prefix, bam, out)
+            rep = host.run(prefix, bam, outs.next())
             dt = time.perf_counter() - t1 - rep["index_load_s"]
             e2e_s += dt; steps_ms.append(round(dt * 1e3, 1)); reps.append(rep)
         barrier()
@@ -358,12 +399,12 @@ def main():
         pipelined_env = {k: os.environ.get(k) for k in ("BWAGPU_LANES", "BWAGPU_BATCH_RECORDS", "BWAGPU_BATCH_RAMP", "BWAGPU_INFLATE_MEMBERS")}
         os.environ.update({"BWAGPU_LANES": "1", "BWAGPU_BATCH_RECORDS": str(args.pairs), "BWAGPU_BATCH_RAMP": "0", "BWAGPU_INFLATE_MEMBERS": "9216"})  # > the shard's ~8400 BGZF members
         host.H.bwa_gpu_batch_reset_device()
-        host.run(prefix, bam, out)  # untimed: sets the device up again, sizes the buffers
+        host.run(prefix, bam, outs.next())  # untimed: sets the device up again, sizes the buffers
         api.reset_totals()
         barrier()
         t_dev0 = time.perf_counter()
         for _ in range(args.steps):
-            host.run(prefix, bam, out)
+            host.run(prefix, bam, outs.next())
         barrier()
         wall_dev_s = time.perf_counter() - t_dev0
         clocks = sampler.stop()
@@ -376,6 +417,7 @@ def main():
         host.H.bwa_gpu_batch_reset_device()
     finally:
         restore_stderr(saved)
+        outs.close()
     kernel_ms = tot["ms_width"] + tot["ms_search"] + tot["ms_sa"] + tot["ms_sw"] + tot["ms_global"] + tot["ms_bgzf"] + tot["ms_inflate"]
     if dist is not None:
         t = torch.tensor([e2e_s, kernel_ms], device="cuda", dtype=torch.float64)

@@ -188,6 +188,7 @@ static bwa_gpu_batch_report_t g_rep; /* the run in progress / the last run (bwa_
 static double g_cpu0;
 static int g_trace, g_trace_pass; /* BWAGPU_TRACE=1: every stage hand-over on stderr (seconds since the call, pass, slot, new state) */
 static double g_t_call, g_t_pass1_begin, g_t_pass1_end, g_t_pass2_begin, g_t_pass2_end; /* where a run's wall time goes outside the passes */
+void shim_trace_pt(const char *what) { if (g_trace) fprintf(stderr, "[trace] %.4f %s\n", now() - g_t_call, what); }
 
 /* The index of a long-lived host process (bench.py runs bam2bam several times in one process): with keep_index on, the
  * loaders hand back what an earlier run loaded from the same files, the matching destroy calls leave it alone, and the
@@ -209,6 +210,7 @@ bwt_t *bwt_restore_bwt(const char *fn, int touch)
 	const size_t n = strlen(fn);
 	const int s = n >= 5 && strcmp(fn + n - 5, ".rbwt") == 0 ? 1 : 0;
 	const double t0 = now();
+	shim_trace_pt("bwt_restore_bwt");
 	bwt_t *b;
 	if (g_keep && g_kept_bwt[s].b && strcmp(g_kept_bwt[s].fn, fn) == 0) b = g_kept_bwt[s].b;
 	else {
@@ -242,6 +244,7 @@ ubyte_t *bwt_restore_pac(const bntseq_t *bns, int touch)
 {
 	REAL(ubyte_t *, bwt_restore_pac, const bntseq_t *, int);
 	const double t0 = now();
+	shim_trace_pt("bwt_restore_pac");
 	g_bns = bns;
 	if (g_keep && g_kept_pac.pac && g_kept_pac.l_pac == (int64_t)bns->l_pac) g_pac = g_kept_pac.pac;
 	else {
@@ -286,6 +289,7 @@ void bwa_gpu_batch_drop_index(void)
 			free(g_kept_bwt[s].fn); g_kept_bwt[s].fn = 0;
 		}
 	free(g_kept_pac.pac); g_kept_pac.pac = 0;
+	memtemp_release();
 	if (g_ready) { bwa_gpu_destroy(); g_ready = 0; }
 }
 
@@ -334,6 +338,7 @@ int bwa_bam_to_bam(int argc, char *argv[], char *version)
 	t0 = now();
 	g_t_call = t0;
 	rc = real_bwa_bam_to_bam(argc, argv, version);
+	shim_trace_pt("bwa_bam_to_bam returned");
 	g_rep.wall_s = now() - t0;
 	fprintf(stderr, "[bwa_gpu_batch] outside the passes: %.3f s before pass 1 (options, header, index), %.3f s between the passes (isize inference), %.3f s after pass 2 (close)\n",
 	        g_t_pass1_begin - g_t_call, g_t_pass2_begin - g_t_pass1_end, now() - g_t_pass2_end);
@@ -358,14 +363,22 @@ bwa_seqio_t *bwa_bam_open(const char *fn, int which, char **saif, gap_opt_t *o0,
 		exit(1);
 	}
 	fastin_set_path(fn);
-	return real_bwa_bam_open(fn, which, saif, o0, hh);
+	shim_trace_pt("bwa_bam_open");
+	{
+		bwa_seqio_t *r = real_bwa_bam_open(fn, which, saif, o0, hh);
+		shim_trace_pt("bwa_bam_open done");
+		return r;
+	}
 }
 
 void bwa_seq_close(bwa_seqio_t *bs)
 {
 	REAL(void, bwa_seq_close, bwa_seqio_t *);
+	shim_trace_pt("bwa_seq_close");
 	fastin_close();
+	shim_trace_pt("fastin_close done");
 	real_bwa_seq_close(bs);
+	shim_trace_pt("bwa_seq_close done");
 }
 
 static int unique_rec(const bam_pair_t *p) /* bam2bam.c:595-606 */
@@ -1713,6 +1726,7 @@ void sequential_loop_pass2(gzFile temporary, BGZF *output, khash_t(isize_infos) 
 	pthread_mutex_destroy(&P->mu); pthread_cond_destroy(&P->cv);
 	free(P);
 	memtemp_free();
+	if (!g_keep) memtemp_release(); /* a host that keeps its index between runs keeps the record chunks too */
 	(void)t_begin_;
 	g_t_pass2_end = now();
 }

@@ -70,7 +70,8 @@ int memtemp_spilled(void);
 int memtemp_next(const uint8_t **data, uint32_t *len);
 size_t memtemp_take(size_t want, size_t *first); /* reserves up to `want` records: returns how many, *first = index of the first */
 void memtemp_get(size_t idx, const uint8_t **data, uint32_t *len);
-void memtemp_free(void);
+void memtemp_free(void);                 /* the chunks go to a pool for the next run ... */
+void memtemp_release(void);              /* ... which this frees */
 
 void write_records_bam(BGZF *output, bam_pair_t *recs, size_t n);
 int shim_device_ready(void);          /* bwa_gpu_batch.c: the device context of this run exists */

@@ -160,6 +160,9 @@ static void *fi_device_worker(void *arg)
 	const char *em = getenv("BWAGPU_INFLATE_MEMBERS");
 	const int M = em && atoi(em) > 0 ? (atoi(em) > (1 << 16) ? 1 << 16 : atoi(em)) : FI_DEV_MEMBERS; /* members per call */
 	int64_t *moff = (int64_t *)malloc(((size_t)M + 1) * sizeof(int64_t)), *ooff = (int64_t *)malloc(((size_t)M + 1) * sizeof(int64_t));
+	const char *er = getenv("BWAGPU_BATCH_RAMP");
+	const int ramp = !(er && atoi(er) == 0);
+	int call_no;
 	(void)arg;
 	while (!shim_device_ready()) {
 		if (F.stop || F.error) { free(moff); free(ooff); return 0; }
@@ -178,9 +181,12 @@ static void *fi_device_worker(void *arg)
 	pthread_mutex_lock(&F.mu);
 	F.dev_active = 1;
 	pthread_mutex_unlock(&F.mu);
-	for (;;) {
+	for (call_no = 0;; ++call_no) {
 		int n = 0, k;
 		uint64_t j0;
+		/* the first calls are short (128, 256, 512 members), like the first record batches: the reader has something to parse
+		 * after a few milliseconds instead of after a whole 64 MB call */
+		const int lim = ramp && call_no < 3 && (128 << call_no) < M ? 128 << call_no : M;
 		pthread_mutex_lock(&F.mu);
 		if (F.stop || F.error) { pthread_mutex_unlock(&F.mu); break; }
 		if (F.scan >= F.map_len) { /* clean end of file */
@@ -189,7 +195,7 @@ static void *fi_device_worker(void *arg)
 			pthread_mutex_unlock(&F.mu);
 			break;
 		}
-		while (n < M && F.scan < F.map_len) {
+		while (n < lim && F.scan < F.map_len) {
 			size_t bsize = 0;
 			if (!bgzf_header_ok(F.map + F.scan, F.map_len - F.scan, &bsize)) {
 				if (n) break; /* hand over what is good first */
@@ -656,6 +662,30 @@ static size_t memtemp_cap(void)
 	return cap > ((size_t)64 << 30) ? (size_t)64 << 30 : cap;
 }
 
+/* Chunks go back to a small pool instead of to the system: a process that runs bam2bam again (bench.py; a long-lived host)
+ * appends the next run's records into pages it already owns -- a fresh 64 MB mapping costs 16 K page faults on the thread
+ * that stores the records, a stage near the critical path.  memtemp_release() (the index is dropped) frees the pool. */
+#define MT_POOL_MAX 64 /* x 64 MB */
+static uint8_t *g_mt_pool[MT_POOL_MAX];
+static size_t g_mt_pool_n;
+
+static uint8_t *mt_chunk_get(void)
+{
+	if (g_mt_pool_n) return g_mt_pool[--g_mt_pool_n];
+	return (uint8_t *)malloc(MT_CHUNK);
+}
+
+static void mt_chunk_put(uint8_t *c)
+{
+	if (g_mt_pool_n < MT_POOL_MAX) g_mt_pool[g_mt_pool_n++] = c;
+	else free(c);
+}
+
+void memtemp_release(void)
+{
+	while (g_mt_pool_n) free(g_mt_pool[--g_mt_pool_n]);
+}
+
 void memtemp_begin(void)
 {
 	memtemp_free();
@@ -668,7 +698,7 @@ int memtemp_put(const void *data, uint32_t len)
 	if (t->spilled || t->bytes + len > t->cap || len > MT_CHUNK) { t->spilled = 1; return 0; }
 	if (t->n_chunk == 0 || t->used + len > MT_CHUNK) {
 		if (t->n_chunk == t->m_chunk) { t->m_chunk = t->m_chunk ? t->m_chunk << 1 : 16; t->chunk = (uint8_t **)realloc(t->chunk, t->m_chunk * sizeof(*t->chunk)); }
-		t->chunk[t->n_chunk] = (uint8_t *)malloc(MT_CHUNK);
+		t->chunk[t->n_chunk] = mt_chunk_get();
 		if (!t->chunk[t->n_chunk]) { t->spilled = 1; return 0; }
 		++t->n_chunk; t->used = 0;
 	}
@@ -712,7 +742,7 @@ int memtemp_next(const uint8_t **data, uint32_t *len)
 void memtemp_free(void)
 {
 	size_t i;
-	for (i = 0; i < g_mt.n_chunk; ++i) free(g_mt.chunk[i]);
+	for (i = 0; i < g_mt.n_chunk; ++i) mt_chunk_put(g_mt.chunk[i]);
 	free(g_mt.chunk); free(g_mt.rec); free(g_mt.len);
 	memset(&g_mt, 0, sizeof(g_mt));
 }

@@ -206,34 +206,26 @@ __global__ void __launch_bounds__(128) k_sw(const uint8_t *__restrict__ pac, con
 					// exclusive prefix max of h0(s) - qr + r*s over the lanes before me
 					int v = valid ? h0 - SW_QR + SW_R * lane : NEG, pm = v;
 #pragma unroll
-					for (int d = 1; d < 32; d <<= 1) {
-						const int o = __shfl_up_sync(full, pm, d);
-						if (lane >= d && o > pm) pm = o;
-					}
+					for (int d = 1; d < 32; d <<= 1) pm = max(pm, __shfl_up_sync(full, pm, d)); // a lane below d gets its own value back
 					int pex = __shfl_up_sync(full, pm, 1);
 					if (lane == 0) pex = NEG;
 					int F = F0 - SW_R * lane;
 					if (lane > 0 && pex - SW_R * (lane - 1) > F) F = pex - SW_R * (lane - 1);
 					const int cur = h0 > F ? h0 : F;
 					if (valid) { rh[i] = cur; re[i + 1] = tee[t]; }
-					// running strict maximum in cell order, and the early stop of stdaln.c:684-686
-					int cm = valid ? cur : NEG, im = cm;
-#pragma unroll
-					for (int d = 1; d < 32; d <<= 1) {
-						const int o = __shfl_up_sync(full, im, d);
-						if (lane >= d && o > im) im = o;
-					}
-					int ex = __shfl_up_sync(full, im, 1); // maximum over everything before this cell, earlier rows included
-					if (lane == 0 || ex < run) ex = run;
-					const bool newmax = valid && cur > ex;
-					const unsigned hit = __ballot_sync(full, newmax && cur == target);
+					// running strict maximum in cell order, and the early stop of stdaln.c:684-686.  A cell stops the pass when it is a
+					// new strict maximum AND equals the target: that is the first cell >= target, provided it equals the target
+					// and nothing before the chunk reached it (a later cell == target has an earlier cell >= target before it).
+					const int cm = valid ? cur : NEG;
+					const unsigned ge = __ballot_sync(full, cm >= target), eq = __ballot_sync(full, cm == target);
+					const bool hit = run < target && ge != 0u && ((eq >> (__ffs((int)ge) - 1)) & 1u);
 					if (hit) {
-						const int ln = __ffs((int)hit) - 1;
+						const int ln = __ffs((int)ge) - 1;
 						score_r = target; start_i = start - (tb + ln); start_j = j;
 						score_r_final = score_r - SW_QR;
 						stop = true;
 					} else {
-						const int cmax = __shfl_sync(full, im, 31);
+						const int cmax = __reduce_max_sync(full, cm);
 						if (cmax > run) {
 							const unsigned at = __ballot_sync(full, valid && cur == cmax);
 							run = cmax; start_i = start - (tb + __ffs((int)at) - 1); start_j = j;

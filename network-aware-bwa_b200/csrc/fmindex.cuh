@@ -29,6 +29,9 @@
 #ifndef BWAGPU_CTX_KEEP
 #define BWAGPU_CTX_KEEP 0 // 1: context-entry loads L1::evict_last + L2 evict_last (A/B switch)
 #endif
+#ifndef BWAGPU_IDX_L2_64B
+#define BWAGPU_IDX_L2_64B 1 // 1: index loads carry .L2::64B -- the L2 fills 2 sectors per miss instead of the whole 128-byte line (0: plain loads, for A/B runs)
+#endif
 #ifndef BWAGPU_LDG256
 #define BWAGPU_LDG256 1 // sm_100a has LDG.E.256; set to 0 for two LDG.128
 #endif
@@ -81,6 +84,13 @@ __device__ __forceinline__ OccBlock load_block(const DevIndex &ix, uint32_t b)
 	asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
 	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
 	             : "l"(p), "l"(pol));
+#elif BWAGPU_IDX_L2_64B
+	// Measured (scripts/probe/fetch_probe.cu, profiles/r2_fetch_probe.md): a plain load that misses L2 makes it fill the whole
+	// 128-byte line from DRAM -- 3.9 sectors per random 32-byte block -- whatever cudaLimitMaxL2FetchGranularity says;
+	// .L2::64B is the smallest fill the ISA offers (1.9-2.0 sectors per block)
+	asm volatile("ld.global.nc.L1::evict_last.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+	             : "l"(p));
 #else
 	asm volatile("ld.global.nc.L1::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 	             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)

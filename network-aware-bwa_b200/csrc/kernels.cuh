@@ -353,7 +353,7 @@ struct Entry {
 #define KIND_GAP 1u // bit 0 = insertion (child i = parent i), bit 1+c = deletion of c (child i = parent i + 1)
 #define KIND_MM 2u  // bit j-1 = mismatch child c = (str[i] + j) & 3
 
-enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND = 5, MODE_DONE = 6 };
+enum { MODE_NEW = 0, MODE_POP = 1, MODE_POPWAIT = 2, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND = 5, MODE_DONE = 6 };
 
 #ifndef BWAGPU_MINBLOCKS
 #define BWAGPU_MINBLOCKS 1 // __launch_bounds__ second argument: blocks/SM the register allocator must allow
@@ -383,6 +383,18 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND 
 #define ARENA_ALLOC(cap) ((((size_t)(cap)) + ((1u << BWAGPU_ARENA_G) - 1u)) & ~(size_t)((1u << BWAGPU_ARENA_G) - 1u))
 #ifndef BWAGPU_NO_FREELIST
 #define BWAGPU_NO_FREELIST 1 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
+#endif
+#ifndef BWAGPU_EMBED_NXT
+#define BWAGPU_EMBED_NXT 1 // 1: pass 0 keeps a record's list link inside the record (no second array, one request per push / pop)
+#endif
+#if BWAGPU_EMBED_NXT && !BWAGPU_NO_FREELIST
+#error "BWAGPU_EMBED_NXT needs BWAGPU_NO_FREELIST (pass 0 keeps no free list)"
+#endif
+#ifndef BWAGPU_SPLIT_POP
+#define BWAGPU_SPLIT_POP 0 // 1: a pop from the arena is split over two trips (load issued in one, record used in the next); measured 184 ms against 180 ms on C4 (profiles/r2_ab_experiments.md): off
+#endif
+#if BWAGPU_SPLIT_POP && BWAGPU_TOP_REG
+#error "BWAGPU_SPLIT_POP and BWAGPU_TOP_REG are alternatives"
 #endif
 #ifndef BWAGPU_CONVERGE
 #define BWAGPU_CONVERGE 0 // 1: lanes stay in the loop until the whole warp is done and re-converge every trip
@@ -495,6 +507,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		return B.xnxt + ((size_t)ctab[o >> ARENA_CHUNK_LOG] << ARENA_CHUNK_LOG) + (o & (ARENA_CHUNK - 1));
 	};
 
+	// EMBEDDED LINKS (pass 0).  k_search is bound by the number of memory requests it makes (profiles/r2_fetch_probe.md), and
+	// a push used to make two (the 16-byte record and its 4-byte link in a second array), a pop from the arena two more.
+	// Pass 0's arena has at most 65535 records and its reads at most 255 bases (longer ones go to the next pass), so the
+	// link fits into the record: word z = i | (last_diff_pos or child mask) << 8 | link << 16; a hit record keeps its link
+	// in the upper half of its score word.  0xffff = end of list.
+	constexpr bool EMB = BWAGPU_EMBED_NXT && !POOLED;
+	auto link16 = [](uint32_t idx) -> uint32_t { return idx == NIL ? 0xffffu : idx; };
+	auto unlink16 = [](uint32_t v) -> uint32_t { return v == 0xffffu ? NIL : v; };
+
 	int mode = MODE_NEW;
 	// per-read state
 	int rid = -1, max_diff = 0;
@@ -530,6 +551,17 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	// children of a group are then popped from registers too: their own pushes all go to higher buckets.
 	uint32_t lr_k = 0, lr_l = 0, lr_pos = 0, lr_tag = 0;
 	int lr_s = -1;
+#endif
+#if BWAGPU_SPLIT_POP
+	// SPLIT POP (A/B switch, off).  A record popped from the arena costs its trip two dependent memory round trips (the
+	// record, then the occurrence blocks of its interval), and with a few lanes of every warp popping from memory in every
+	// trip the whole warp pays both (ncu: 15 % of all stall samples at the record's first use, 4.8 lanes active).  With the
+	// switch on such a lane only ISSUES the record's loads (MODE_POPWAIT, not active in this trip's lookup) and takes the
+	// record up at the top of the next trip: its latency passes under the wait for the other lanes' occurrence blocks.  The
+	// lane's stack cannot change in between (only the lane itself pushes to it), so the pop is the reference's.  Measured
+	// slower (the lane's extra trip and 7 more registers cost more than the shorter wait saves).
+	uint4 pq = make_uint4(0u, 0u, 0u, 0u);
+	uint32_t pnx = NIL;
 #endif
 	int m = 0, i = 0; // i doubles as the exact tail's cursor
 	// context of the current node, loaded together with its occurrence blocks (k_ctx16): cw = E[i-1] | E[i-2] << 16, i.e.
@@ -599,9 +631,16 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	auto store_rec = [&](uint32_t rk, uint32_t rl, uint32_t pos, uint32_t tag, int s) {
 		const uint32_t idx = alloc_rec();
 		if (idx == NIL) return;
-		*ent_at(idx) = make_uint4(rk, rl, pos, tag);
-		if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
-		else { *nxt_at(idx) = mask.test(s) ? (uint32_t)heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
+		if (EMB) {
+			uint32_t below;
+			if (s == cur_s) { below = cur_head; cur_head = idx; }
+			else { below = mask.test(s) ? (uint32_t)heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
+			*ent_at(idx) = make_uint4(rk, rl, (pos & 0xffu) | ((pos >> 16) & 0xffu) << 8 | link16(below) << 16, tag);
+		} else {
+			*ent_at(idx) = make_uint4(rk, rl, pos, tag);
+			if (s == cur_s) { *nxt_at(idx) = cur_head; cur_head = idx; }
+			else { *nxt_at(idx) = mask.test(s) ? (uint32_t)heads[s * HS] : NIL; heads[s * HS] = (head_t)idx; }
+		}
 		mask.set(s);
 	};
 
@@ -635,7 +674,11 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			B.overflow_ids[o] = rid;
 		} else {
 			uint32_t h = n_aln > 0 ? (uint32_t)heads[HIT_HEAD] : NIL;
-			for (int j = 0; j < n_aln; ++j) { B.pool[off + j] = *ent_at(h); h = *nxt_at(h); }
+			for (int j = 0; j < n_aln; ++j) {
+				uint4 q = *ent_at(h);
+				if (EMB) { h = unlink16(q.w >> 16); q.w &= 0xffffu; } else h = *nxt_at(h);
+				B.pool[off + j] = q;
+			}
 			B.n_aln[rid] = n_aln;
 			B.pool_off[rid] = off;
 			B.max_entries[rid] = max_entries;
@@ -664,9 +707,10 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		else if (best_cnt > O.max_top2) return false; // top2b behaviour
 		if (go) { // the hit may have been found already (gap in a tandem repeat)
 			uint32_t h = n_aln > 0 ? (uint32_t)heads[HIT_HEAD] : NIL;
-			for (int j = 0; j < n_aln; ++j, h = *nxt_at(h)) {
+			for (int j = 0; j < n_aln; ++j) {
 				const uint4 q = *ent_at(h);
 				if (q.y == hk && q.z == hl) { do_add = false; break; }
+				h = EMB ? unlink16(q.w >> 16) : *nxt_at(h);
 			}
 		}
 		if (do_add) {
@@ -693,9 +737,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			}
 			const uint32_t idx = alloc_rec();
 			if (idx != NIL) {
-				*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score);
-				*nxt_at(idx) = NIL;
-				if (n_aln > 0) *nxt_at((uint32_t)heads[HIT_TAIL]) = idx; else heads[HIT_HEAD] = (head_t)idx;
+				if (EMB) {
+					*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score | 0xffffu << 16);
+					if (n_aln > 0) reinterpret_cast<uint16_t *>(&ent_at((uint32_t)heads[HIT_TAIL])->w)[1] = (uint16_t)idx; // the tail's link (upper half of its score word)
+					else heads[HIT_HEAD] = (head_t)idx;
+				} else {
+					*ent_at(idx) = make_uint4((uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | a << 24, hk, hl, (uint32_t)score);
+					*nxt_at(idx) = NIL;
+					if (n_aln > 0) *nxt_at((uint32_t)heads[HIT_TAIL]) = idx; else heads[HIT_HEAD] = (head_t)idx;
+				}
 				heads[HIT_TAIL] = (head_t)idx;
 				++n_aln;
 			}
@@ -749,6 +799,9 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			if (len == 0 || (int)md.n_amb > max_diff) {
 				B.n_aln[rid] = 0; B.pool_off[rid] = 0; B.max_entries[rid] = 0;
 				active = false; // stays in MODE_NEW
+			} else if (EMB && len > 255) { // positions do not fit the packed record: the next pass takes the read
+				overflow = true;
+				mode = MODE_POP;
 			} else {
 				w_off = md.w_off;
 				best_score = score_of(max_diff + 1, (int)md.max_gapo + 1, O.max_gape + 1);
@@ -761,22 +814,27 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			}
 		}
 
-		if (active && mode == MODE_POP) {
-			if (!POOLED && pops_left-- == 0) overflow = true; // a straggler: the warp-per-read pass does it faster than one lane can
-			bool stop = overflow || n_entries == 0;
-			if (!stop) {
-				if (max_entries < n_entries) max_entries = n_entries;
-				// > max_entries (bwtgap.c:140); only phantoms left: the reference pops one and stops
+		if (active && (mode == MODE_POP || mode == MODE_POPWAIT)) {
+			const bool second = BWAGPU_SPLIT_POP && mode == MODE_POPWAIT; // the record asked for in the last trip has arrived
+			bool stop = false;
+			if (!second) {
+				if (!POOLED && pops_left-- == 0) overflow = true; // a straggler: the warp-per-read pass does it faster than one lane can
+				stop = overflow || n_entries == 0;
+				if (!stop) {
+					if (max_entries < n_entries) max_entries = n_entries;
+					// > max_entries (bwtgap.c:140); only phantoms left: the reference pops one and stops
 #if BWAGPU_TOP_REG
-				stop = n_entries > O.max_entries || (!held && !mask.any() && lr_s < 0);
+					stop = n_entries > O.max_entries || (!held && !mask.any() && lr_s < 0);
 #else
-				stop = n_entries > O.max_entries || (!held && !mask.any());
+					stop = n_entries > O.max_entries || (!held && !mask.any());
 #endif
+				}
 			}
 			if (stop) { finish_read(); mode = MODE_NEW; active = false; }
 			else {
+				bool took = true; // a node was popped in this trip
 				// gap_pop (bwtgap.c:66-79)
-				if (held) { // the match child: counts of its parent, state M, no difference at its position
+				if (!second && held) { // the match child: counts of its parent, state M, no difference at its position
 					held = false;
 					e_pos = (uint32_t)i;
 					e_tag &= ~(3u << 24);
@@ -802,60 +860,79 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						}
 						idx = cur_head;
 						qp = ent_at(idx);
+#if BWAGPU_SPLIT_POP
+						if (!second) { // first half: issue the loads and sit this trip's lookup out
+							pq = *qp;
+							if (!EMB) pnx = *nxt_at(idx);
+							mode = MODE_POPWAIT;
+							took = false; active = false;
+						}
+						q = pq; nx = pnx;
+#else
 						q = *qp;
-						nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
-						if (STATS) ++n_mempop;
-					}
-					const uint32_t kind = (q.w >> 27) & 3u;
-					uint32_t gm = 0, b = 0;
-					if (kind != KIND_PLAIN) {
-						gm = (q.z >> 16) & 31u;
-						b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
-						gm &= ~(1u << b);
-					}
-					if (from_lr) {
-#if BWAGPU_TOP_REG
-						if (gm) lr_pos = (q.z & 0xffffu) | gm << 16; // stays on top with one child fewer
-						else lr_s = -1;
+						if (!EMB) nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
 #endif
-					} else {
-						bool unlink = gm == 0;
-#if BWAGPU_TOP_REG
-						if (gm && lr_s < 0) { // the rest of the group moves to registers: it stays the top of the lowest bucket until it is used up
-							lr_k = q.x; lr_l = q.y; lr_pos = (q.z & 0xffffu) | gm << 16; lr_tag = q.w; lr_s = s;
-							unlink = true;
-						}
-#endif
-						if (!unlink) qp->z = (q.z & 0xffffu) | gm << 16; // record stays on top with one child fewer
-						else {
-							cur_head = nx;
-							if (cur_head == NIL) mask.clear(s);
-							if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
-							spare = idx;
+						if (EMB) { // z = i | (last_diff_pos or mask) << 8 | link << 16  ->  the plain form the code below works on
+							nx = unlink16(q.z >> 16);
+							q.z = (q.z & 0xffu) | ((q.z >> 8) & 0xffu) << 16;
 						}
 					}
-					k = q.x; l = q.y;
-					if (kind == KIND_PLAIN) { e_pos = q.z; e_tag = q.w; }
-					else {
-						const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
-						uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
-						if (kind == KIND_MM) {
-							const uint32_t cb = q.w >> 29; // the parent's read base at pi, kept in the record
-							cc = (cb + b + 1u) & 3u;
-							++mm; ci = pi; st = STATE_M; need_derive = true;
+					if (took) {
+						if (STATS && !from_lr) ++n_mempop;
+						mode = MODE_POP;
+						const uint32_t kind = (q.w >> 27) & 3u;
+						uint32_t gm = 0, b = 0;
+						if (kind != KIND_PLAIN) {
+							gm = (q.z >> 16) & 31u;
+							b = 31u - (uint32_t)__clz((int)gm); // child pushed last = highest bit
+							gm &= ~(1u << b);
+						}
+						if (from_lr) {
+#if BWAGPU_TOP_REG
+							if (gm) lr_pos = (q.z & 0xffffu) | gm << 16; // stays on top with one child fewer
+							else lr_s = -1;
+#endif
 						} else {
-							if (pst == STATE_M) ++go; else ++ge;
-							if (b == 0) { ci = pi; st = STATE_I; }
-							else { ci = pi + 1u; st = STATE_D; cc = b - 1u; need_derive = true; }
+							bool unlink = gm == 0;
+#if BWAGPU_TOP_REG
+							if (gm && lr_s < 0) { // the rest of the group moves to registers: it stays the top of the lowest bucket until it is used up
+								lr_k = q.x; lr_l = q.y; lr_pos = (q.z & 0xffffu) | gm << 16; lr_tag = q.w; lr_s = s;
+								unlink = true;
+							}
+#endif
+							if (!unlink) qp->z = EMB ? ((q.z & 0xffu) | gm << 8 | link16(nx) << 16) : ((q.z & 0xffffu) | gm << 16); // record stays on top with one child fewer
+							else {
+								cur_head = nx;
+								if (cur_head == NIL) mask.clear(s);
+								if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }
+								spare = idx;
+							}
 						}
-						e_pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
-						e_tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
+						k = q.x; l = q.y;
+						if (kind == KIND_PLAIN) { e_pos = q.z; e_tag = q.w; }
+						else {
+							const uint32_t pi = q.z & 0xffffu, pst = (q.w >> 24) & 3u, a = (q.w >> 26) & 1u;
+							uint32_t mm = q.w & 0xffu, go = (q.w >> 8) & 0xffu, ge = (q.w >> 16) & 0xffu, ci, st;
+							if (kind == KIND_MM) {
+								const uint32_t cb = q.w >> 29; // the parent's read base at pi, kept in the record
+								cc = (cb + b + 1u) & 3u;
+								++mm; ci = pi; st = STATE_M; need_derive = true;
+							} else {
+								if (pst == STATE_M) ++go; else ++ge;
+								if (b == 0) { ci = pi; st = STATE_I; }
+								else { ci = pi + 1u; st = STATE_D; cc = b - 1u; need_derive = true; }
+							}
+							e_pos = ci | ci << 16; // every group child is a difference: last_diff_pos = its own i
+							e_tag = mm | go << 8 | ge << 16 | st << 24 | a << 26;
+						}
+						i = (int)(e_pos & 0xffffu);
 					}
-					i = (int)(e_pos & 0xffffu);
 				}
-				--n_entries;
-				if (STATS) { ++n_pops; ++read_pops; }
-				fresh = true;
+				if (took) {
+					--n_entries;
+					if (STATS) { ++n_pops; ++read_pops; }
+					fresh = true;
+				}
 			}
 		}
 
@@ -1137,7 +1214,15 @@ __global__ void __launch_bounds__(256) k_sa(const IndexPair P, long long n,
 		k = inv_psi(ix, k);
 	}
 	k /= intv;
-	out[t] = steps + (k ? ix.sa[k] : 0xffffffffu);
+	uint32_t sv = 0xffffffffu;
+	if (k) {
+#if BWAGPU_IDX_L2_64B && !defined(BWAGPU_HOST_EMU)
+		asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(sv) : "l"(ix.sa + k)); // one random 4-byte read: no 128-byte fill
+#else
+		sv = ix.sa[k];
+#endif
+	}
+	out[t] = steps + sv;
 }
 
 } // namespace bwagpu

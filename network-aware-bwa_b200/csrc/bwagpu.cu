@@ -483,7 +483,7 @@ static search_fn search_kernel(bool stats, bool pooled, bool stdmode)
 // bucket heads in shared memory: u16 per (bucket, thread) in pass 0 (private arena), u32 in the pooled passes
 static size_t search_smem(bool pooled, uint32_t n_stacks)
 {
-	return BWAGPU_SMEM_HEADS ? (size_t)128 * (n_stacks + 2) * (pooled ? sizeof(uint32_t) : sizeof(uint16_t)) : 0; // + the hit list's two ends
+	return SEARCH_SMEM(n_stacks, pooled ? sizeof(uint32_t) : sizeof(uint16_t)); // bucket heads + the hit list's two ends, context sectors
 }
 static bool is_stdmode(int mode) { return (mode & 0x01) && !(mode & 0x04) && !(mode & 0x10); }
 // pass 1 = the warp-per-read kernel (search_warp.cuh) unless BWAGPU_WARP_PASS=0 (then: thread-per-read on the pool, as pass 0 but pooled)
@@ -593,7 +593,7 @@ static int run_chunk_device(Ctx *c, int n, size_t w_entries, const GapOpt &opt, 
                             bool device_compact)
 {
 	const bool stats = g_stats_enabled;
-	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx16.reserve(w_entries + 8)) return 1;
+	if (c->d_w.reserve(w_entries + 1) || c->d_bid.reserve(w_entries + 1) || c->d_ctx16.reserve(w_entries + 32)) return 1;
 	if (c->d_naln.reserve(n + 1) || c->d_maxent.reserve(n) || c->d_pooloff.reserve(n) || c->d_outoff.reserve(n + 1))
 		return 1;
 	if (c->d_jobs_a.reserve(n) || c->d_jobs_b.reserve(n)) return 1;

@@ -384,6 +384,12 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_POPWAIT = 2, MODE_DERIVE = 3, MODE_EXACT
 #ifndef BWAGPU_NO_FREELIST
 #define BWAGPU_NO_FREELIST 1 // 1: pass 0 recycles only the slot of the latest pop (no free list; deeper reads go to pass 1)
 #endif
+#ifndef BWAGPU_CTX_SMEM
+#define BWAGPU_CTX_SMEM 1 // 1: each thread keeps the 32-byte sector of context entries it read last in shared memory
+#endif
+// bytes of dynamic shared memory per block of 128 threads: the bucket heads (+ the hit list's two ends), then the context sectors
+#define SEARCH_SMEM_HEADS(n_stacks, head_bytes) ((((size_t)128 * ((n_stacks) + 2) * (head_bytes)) + 15) & ~(size_t)15)
+#define SEARCH_SMEM(n_stacks, head_bytes) ((BWAGPU_SMEM_HEADS ? SEARCH_SMEM_HEADS(n_stacks, head_bytes) : 0) + (BWAGPU_CTX_SMEM ? (size_t)128 * 32 : 0))
 #ifndef BWAGPU_EMBED_NXT
 #define BWAGPU_EMBED_NXT 1 // 1: pass 0 keeps a record's list link inside the record (no second array, one request per push / pop)
 #endif
@@ -477,14 +483,25 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	static head_t s_heads[264];
 	head_t *const heads = s_heads + threadIdx.x;
 	const uint32_t HS = blockDim.x; // stride between buckets
+	static uint32_t s_cxw[8];
+	uint32_t *const cxw = s_cxw; // context sector: word w of this thread at cxw[w * CS]
 #elif BWAGPU_SMEM_HEADS
 	extern __shared__ __align__(16) unsigned char s_heads_raw[];
 	head_t *const heads = reinterpret_cast<head_t *>(s_heads_raw) + threadIdx.x;
 	const uint32_t HS = blockDim.x;
+	uint32_t *const cxw = reinterpret_cast<uint32_t *>(s_heads_raw + SEARCH_SMEM_HEADS(B.n_stacks, sizeof(head_t))) + threadIdx.x;
 #else
+	extern __shared__ __align__(16) unsigned char s_heads_raw[];
 	uint32_t *const heads = B.heads + (size_t)slot * (B.n_stacks + 2);
 	const uint32_t HS = 1;
+	uint32_t *const cxw = reinterpret_cast<uint32_t *>(s_heads_raw) + threadIdx.x;
 #endif
+	const uint32_t CS = blockDim.x; // stride between the words of a thread's context sector
+	// CONTEXT SECTOR.  Every popped node reads two context entries (k_ctx16), and the match chain walks them downwards one
+	// position per trip -- but with ~900 searches per SM a sector does not survive in L1 from one trip to the next: nearly
+	// every pop was a request of its own to L2 (a third of the kernel's read requests, and the kernel is bound by their
+	// number).  Each thread therefore keeps the last sector it fetched (16 entries) in shared memory; cx_tag = which one.
+	uint32_t cx_tag = 0xffffffffu;
 	const uint32_t HIT_HEAD = B.n_stacks * HS, HIT_TAIL = (B.n_stacks + 1) * HS; // valid while n_aln > 0
 	const GapOpt &O = B.opt;
 	const bool gape_mode = STDMODE || (O.mode & 0x01), loggap = !STDMODE && (O.mode & 0x04), nonstop = !STDMODE && (O.mode & 0x10);
@@ -735,6 +752,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				if (t < len) cx[t] = (uint16_t)((cx[t] & C16_KEEP) | c16_width(nb)); // the entry of position t: its width fields
 				prev = wv;
 			}
+			cx_tag = 0xffffffffu; // the sector kept in shared memory may hold entries just rewritten
 			const uint32_t idx = alloc_rec();
 			if (idx != NIL) {
 				if (EMB) {
@@ -804,6 +822,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				mode = MODE_POP;
 			} else {
 				w_off = md.w_off;
+				cx_tag = 0xffffffffu;
 				best_score = score_of(max_diff + 1, (int)md.max_gapo + 1, O.max_gape + 1);
 				// the two root nodes (bwtgap.c:127-128): strand 0 stored, strand 1 (popped first) held
 				push_rec(0u, B.ix[0].seq_len, (uint32_t)len, 0u, 0, 1);
@@ -949,6 +968,24 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 			ob_k = load_block(ix, jk >> 6); // same sector as ob_l for narrow intervals (L1 hit)
 			if (fresh | (mode == MODE_EXACT)) { // fresh: the node's own entries E[i-1], E[i-2]; exact tail: E[i-2] (its base = str[i-2]) in the low half
 				const int j = fresh ? i : i - 1;
+#if BWAGPU_CTX_SMEM
+				uint32_t e1 = 0u, e2 = 0u;
+				if (j >= 1) {
+					const uint32_t g1 = w_off + a * (uint32_t)WSTRIDE(RD_LEN) + (uint32_t)j - 1u; // entry index of position j - 1
+					if ((g1 >> 4) != cx_tag) { // fetch its sector (the arena is 32-byte aligned) and keep it
+						cx_tag = g1 >> 4;
+						const uint4 *sp = reinterpret_cast<const uint4 *>(ctx16 + ((size_t)cx_tag << 4));
+						const uint4 s0 = sp[0], s1 = sp[1];
+						cxw[0] = s0.x; cxw[CS] = s0.y; cxw[2 * CS] = s0.z; cxw[3 * CS] = s0.w;
+						cxw[4 * CS] = s1.x; cxw[5 * CS] = s1.y; cxw[6 * CS] = s1.z; cxw[7 * CS] = s1.w;
+					}
+					e1 = (cxw[((g1 & 15u) >> 1) * CS] >> ((g1 & 1u) << 4)) & 0xffffu;
+					if (fresh && j >= 2) {
+						const uint32_t g2 = g1 - 1u;
+						e2 = (g2 >> 4) == cx_tag ? (cxw[((g2 & 15u) >> 1) * CS] >> ((g2 & 1u) << 4)) & 0xffffu : (uint32_t)ctx16[g2];
+					}
+				}
+#else
 				const uint16_t *cp = ctx16 + ((size_t)w_off + (size_t)a * WSTRIDE(RD_LEN) + (size_t)j);
 #if BWAGPU_CTX_KEEP && !defined(BWAGPU_HOST_EMU)
 				uint32_t e1 = 0u, e2 = 0u;
@@ -962,6 +999,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 #else
 				const uint32_t e1 = j >= 1 ? (uint32_t)cp[-1] : 0u;
 				const uint32_t e2 = (fresh && j >= 2) ? (uint32_t)cp[-2] : 0u;
+#endif
 #endif
 				cw = e1 | e2 << 16;
 			}

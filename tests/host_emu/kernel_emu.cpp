@@ -89,7 +89,7 @@ extern "C" int emu_aln_flat(void *h, int n, const uint8_t *bases, const int64_t 
 	std::vector<uint32_t> w(wo + 1);
 	std::vector<uint16_t> bid(wo + 1);
 	std::vector<uint2> ctx(wo + 8);
-	std::vector<uint16_t> ctx16(wo + 8);
+	std::vector<uint16_t> ctx16(wo + 32); // k_search reads whole 16-entry sectors
 	std::vector<uint32_t> pool_off(n);
 	std::vector<uint4> pool((size_t)n * 64 + (1 << 16));
 	std::vector<int32_t> jobs_a(n), jobs_b(n);

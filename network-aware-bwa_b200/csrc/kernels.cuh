@@ -389,7 +389,13 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_POPWAIT = 2, MODE_DERIVE = 3, MODE_EXACT
 #endif
 // bytes of dynamic shared memory per block of 128 threads: the bucket heads (+ the hit list's two ends), then the context sectors
 #define SEARCH_SMEM_HEADS(n_stacks, head_bytes) ((((size_t)128 * ((n_stacks) + 2) * (head_bytes)) + 15) & ~(size_t)15)
-#define SEARCH_SMEM(n_stacks, head_bytes) ((BWAGPU_SMEM_HEADS ? SEARCH_SMEM_HEADS(n_stacks, head_bytes) : 0) + (BWAGPU_CTX_SMEM ? (size_t)128 * 32 : 0))
+#define SEARCH_SMEM(n_stacks, head_bytes) ((BWAGPU_SMEM_HEADS ? SEARCH_SMEM_HEADS(n_stacks, head_bytes) : 0) + (size_t)128 * 32 + (size_t)128 * 16) // + context sectors + pop cache
+#ifndef BWAGPU_POP_CACHE
+#define BWAGPU_POP_CACHE 1 // 1 (needs BWAGPU_EMBED_NXT): the group record a child was just popped from stays in shared memory while it has children left
+#endif
+#if BWAGPU_POP_CACHE && BWAGPU_SPLIT_POP
+#error "BWAGPU_POP_CACHE and BWAGPU_SPLIT_POP are alternatives"
+#endif
 #ifndef BWAGPU_EMBED_NXT
 #define BWAGPU_EMBED_NXT 1 // 1: pass 0 keeps a record's list link inside the record (no second array, one request per push / pop)
 #endif
@@ -483,18 +489,21 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	static head_t s_heads[264];
 	head_t *const heads = s_heads + threadIdx.x;
 	const uint32_t HS = blockDim.x; // stride between buckets
-	static uint32_t s_cxw[8];
+	static uint32_t s_cxw[8], s_pcw[4];
 	uint32_t *const cxw = s_cxw; // context sector: word w of this thread at cxw[w * CS]
+	uint32_t *const pcw = s_pcw; // pop cache: word w at pcw[w * CS]
 #elif BWAGPU_SMEM_HEADS
 	extern __shared__ __align__(16) unsigned char s_heads_raw[];
 	head_t *const heads = reinterpret_cast<head_t *>(s_heads_raw) + threadIdx.x;
 	const uint32_t HS = blockDim.x;
 	uint32_t *const cxw = reinterpret_cast<uint32_t *>(s_heads_raw + SEARCH_SMEM_HEADS(B.n_stacks, sizeof(head_t))) + threadIdx.x;
+	uint32_t *const pcw = cxw + 8 * blockDim.x;
 #else
 	extern __shared__ __align__(16) unsigned char s_heads_raw[];
 	uint32_t *const heads = B.heads + (size_t)slot * (B.n_stacks + 2);
 	const uint32_t HS = 1;
 	uint32_t *const cxw = reinterpret_cast<uint32_t *>(s_heads_raw) + threadIdx.x;
+	uint32_t *const pcw = cxw + 8 * blockDim.x;
 #endif
 	const uint32_t CS = blockDim.x; // stride between the words of a thread's context sector
 	// CONTEXT SECTOR.  Every popped node reads two context entries (k_ctx16), and the match chain walks them downwards one
@@ -532,6 +541,13 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 	constexpr bool EMB = BWAGPU_EMBED_NXT && !POOLED;
 	auto link16 = [](uint32_t idx) -> uint32_t { return idx == NIL ? 0xffffu : idx; };
 	auto unlink16 = [](uint32_t v) -> uint32_t { return v == 0xffffu ? NIL : v; };
+	// POP CACHE (pass 0).  A group record stays on top of its bucket while its children are popped one by one, and between
+	// two of them the thread pops nothing else from the arena (a child's own pushes go to buckets of higher score when all
+	// penalties are positive): every child used to cost a load of the record and a store of its shrunken mask.  The record
+	// now moves to shared memory with the first child and is served from there (pend_idx = which record; its mask in the
+	// arena goes stale and is written back -- one byte -- only if another group takes the slot while it has children left).
+	constexpr bool PC = BWAGPU_POP_CACHE && EMB;
+	uint32_t pend_idx = NIL;
 
 	int mode = MODE_NEW;
 	// per-read state
@@ -704,6 +720,7 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 		lr_s = -1;
 #endif
 		mask.reset(); cur_s = -1; cur_head = NIL;
+		pend_idx = NIL;
 		bump = 0; free_head = NIL; spare = NIL; held = false; n_entries = 0; n_aln = 0;
 		if (POOLED) while (n_chunks > 1) chunk_free(ctab[--n_chunks]); // keep one chunk, recycle the rest
 	};
@@ -888,7 +905,8 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 						}
 						q = pq; nx = pnx;
 #else
-						q = *qp;
+						if (PC && idx == pend_idx) q = make_uint4(pcw[0], pcw[CS], pcw[2 * CS], pcw[3 * CS]); // the group popped from last
+						else q = *qp;
 						if (!EMB) nx = *nxt_at(idx); // issued with the entry load, used only when the record is unlinked
 #endif
 						if (EMB) { // z = i | (last_diff_pos or mask) << 8 | link << 16  ->  the plain form the code below works on
@@ -919,8 +937,17 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 								unlink = true;
 							}
 #endif
-							if (!unlink) qp->z = EMB ? ((q.z & 0xffu) | gm << 8 | link16(nx) << 16) : ((q.z & 0xffffu) | gm << 16); // record stays on top with one child fewer
-							else {
+							if (!unlink) { // record stays on top with one child fewer
+								if (PC) {
+									if (idx != pend_idx) {
+										if (pend_idx != NIL) reinterpret_cast<uint8_t *>(&ent_at(pend_idx)->z)[1] = (uint8_t)(pcw[2 * CS] >> 8); // write the displaced group's mask back
+										pcw[0] = q.x; pcw[CS] = q.y; pcw[3 * CS] = q.w;
+										pend_idx = idx;
+									}
+									pcw[2 * CS] = (q.z & 0xffu) | gm << 8 | link16(nx) << 16;
+								} else qp->z = EMB ? ((q.z & 0xffu) | gm << 8 | link16(nx) << 16) : ((q.z & 0xffffu) | gm << 16);
+							} else {
+								if (PC && idx == pend_idx) pend_idx = NIL;
 								cur_head = nx;
 								if (cur_head == NIL) mask.clear(s);
 								if ((POOLED || !BWAGPU_NO_FREELIST) && spare != NIL) { *nxt_at(spare) = free_head; free_head = spare; }

@@ -208,6 +208,26 @@ def test_option_fuzz_matches_reference_live(small_index, emu_index, wemu_index):
 
 
 @pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
+def test_zero_penalty_options_match_reference_live(small_index, emu_index):
+    """One penalty at a time set to 0: a popped child's own pushes then land in the bucket it came from, on top of the group
+    record it was popped from -- the case in which k_search's pop cache (the group record kept in shared memory while it has
+    children left) has to write a displaced group's mask back to the arena."""
+    T, _ = small_index
+    he, ridx = emu_index
+    rng = np.random.default_rng(11)
+    for it in range(9):
+        z = it % 3
+        kw = dict(s_mm=0 if z == 0 else int(rng.integers(1, 4)), s_gapo=0 if z == 1 else int(rng.integers(1, 8)),
+                  s_gape=0 if z == 2 else int(rng.integers(1, 4)), max_gapo=int(rng.integers(1, 3)), max_gape=int(rng.integers(1, 6)),
+                  max_entries=3000, seed_len=int(rng.choice([16, 32, 1024])), max_top2=int(rng.choice([1, 30])),
+                  mode=int(rng.choice([0x01, 0x11, 0x00])) | 0x02, fnr=-1.0, max_diff=int(rng.integers(1, 4)))
+        opt = abi.default_gap_opt(**kw)
+        reads = R.bwa.simulate.simulate_reads(T, 60, (20, 45), seed=int(rng.integers(1, 1 << 30)), sub_rate=0.05, n_rate=0.01)
+        want = R.ref_aln(ridx, reads, opt, threads=4)
+        assert R.compare_aln(want, R.emu_aln(he, reads, opt), f"zero penalty {kw}") == []
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not present")
 def test_library_maxdiff_matches_reference_for_long_reads():
     """csrc/hostprep.h cal_maxdiff against the reference's bwa_cal_maxdiff (bwtaln.c:37-49) for every length 1..1000: from
     ~350 bp on the reference's `int x *= k` wraps around, and the restatement must wrap to the same bits (it multiplies in

@@ -511,6 +511,16 @@ def main():
             roofline["random_sector_probe_gb_s"] = {"2.3GB_buffer_chains4": api.probe_random_sectors(2_300_000_000, 4, 256)}
         except Exception as e:
             roofline["random_sector_probe_gb_s"] = {"error": str(e)[:200]}
+        try:
+            # what binds the kernel (profiles/r2_fetch_probe.md): the number of requests it sends to L2, not their bytes --
+            # ncu's request counts per read x this launch's reads / its time, beside the request rate of the probe
+            c4 = json.load(open(os.path.join(ROOT, "profiles", "k_search_traffic.json")))["c4"]
+            rq = c4["l2_read_requests_per_read"] + c4["l2_write_requests_per_read"]
+            roofline["l2_requests"] = {"per_read": rq, "g_per_s": rq * args.aln_reads / (search_ms / n_rep / 1e3) / 1e9,
+                                       "probe_g_loads_per_s": roofline["random_sector_probe_gb_s"].get("2.3GB_buffer_chains4", 0.0) / 32.0,
+                                       "source": c4["source"]}
+        except Exception:
+            pass
 
     # ---- the other kernels of the step, from the library's totals over the timed steps
     int_alu_peak = 148 * 128 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6  # integer lane-ops/s: 148 SMs x 128 lanes x clock
@@ -521,9 +531,9 @@ def main():
     other = {
         "k4_sa": {"queries_per_step": tot["sa_queries"] / args.steps, "kernel_ms_per_step": per_step["ms_sa"],
                   "queries_per_s_kernel": per_s(tot["sa_queries"], tot["ms_sa"]),
-                  "algorithmic_gb_s": 64.0 * 15.5 * per_s(tot["sa_queries"], tot["ms_sa"]) / 1e9,
-                  "frac_of_hbm_peak": 64.0 * 15.5 * per_s(tot["sa_queries"], tot["ms_sa"]) / 1e9 / peak,
-                  "unit": "64 B x 15.5 LF steps per query (bwt.c:72-81 at sa_intv 32)"},
+                  "algorithmic_gb_s": 64.0 * 31.0 * per_s(tot["sa_queries"], tot["ms_sa"]) / 1e9,
+                  "frac_of_hbm_peak": 64.0 * 31.0 * per_s(tot["sa_queries"], tot["ms_sa"]) / 1e9 / peak,
+                  "unit": "64 B x 31 LF steps per query (bwt.c:72-81: rows are sampled, k % sa_intv == 0 with sa_intv 32, so the walk length is geometric with mean 31; ncu counts 32.2 sector loads per query, profiles/r2_k_sa.md)"},
         "k5_sw": {"jobs_per_step": tot["sw_jobs"] / args.steps, "kernel_ms_per_step": per_step["ms_sw"],
                   "gcups_forward_kernel": per_s(tot["sw_cells_fwd"], tot["ms_sw"]) / 1e9,
                   "integer_alu_bound_gcups": int_alu_peak / 12 / 1e9,

@@ -356,7 +356,7 @@ struct Entry {
 enum { MODE_NEW = 0, MODE_POP = 1, MODE_POPWAIT = 2, MODE_DERIVE = 3, MODE_EXACT = 4, MODE_EXPAND = 5, MODE_DONE = 6 };
 
 #ifndef BWAGPU_MINBLOCKS
-#define BWAGPU_MINBLOCKS 1 // __launch_bounds__ second argument: blocks/SM the register allocator must allow
+#define BWAGPU_MINBLOCKS 7 // __launch_bounds__ second argument: 7 blocks per SM = 72 registers, no spills (6 at the 79 it takes unbounded: 148.3 ms, 7: 143.0, 8 = 64 registers with spills: 160.2; C4, 2 M reads)
 #endif
 // Measured on B200, 10M x 76bp (profiles/r1_ab_experiments.md).  Bucket heads in shared memory were a wash
 // while six context loads per node competed for L1; with the single context word (k_ctx) they win 5 %

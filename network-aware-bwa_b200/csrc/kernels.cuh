@@ -390,6 +390,9 @@ enum { MODE_NEW = 0, MODE_POP = 1, MODE_POPWAIT = 2, MODE_DERIVE = 3, MODE_EXACT
 // bytes of dynamic shared memory per block of 128 threads: the bucket heads (+ the hit list's two ends), then the context sectors
 #define SEARCH_SMEM_HEADS(n_stacks, head_bytes) ((((size_t)128 * ((n_stacks) + 2) * (head_bytes)) + 15) & ~(size_t)15)
 #define SEARCH_SMEM(n_stacks, head_bytes) ((BWAGPU_SMEM_HEADS ? SEARCH_SMEM_HEADS(n_stacks, head_bytes) : 0) + (size_t)128 * 32 + (size_t)128 * 16) // + context sectors + pop cache
+#ifndef BWAGPU_PREFETCH_HELD
+#define BWAGPU_PREFETCH_HELD 0 // 1: an expansion prefetches (L1) the two index blocks of its match child before it pushes the other children; measured 182.5 against 142.0 ms (a prefetch is one more request, and requests are what the kernel pays for): off
+#endif
 #ifndef BWAGPU_POP_CACHE
 #define BWAGPU_POP_CACHE 1 // 1 (needs BWAGPU_EMBED_NXT): the group record a child was just popped from stays in shared memory while it has children left
 #endif
@@ -1109,6 +1112,15 @@ __global__ void __launch_bounds__(128, BWAGPU_MINBLOCKS) k_search(const Batch B)
 				const uint32_t ci = CW_C1;
 				// which of the four one-symbol extensions are non-empty (k' <= l')
 				const uint32_t V = (nk[0] <= nl[0] ? 1u : 0u) | (nk[1] <= nl[1] ? 2u : 0u) | (nk[2] <= nl[2] ? 4u : 0u) | (nk[3] <= nl[3] ? 8u : 0u);
+#if BWAGPU_PREFETCH_HELD && !defined(BWAGPU_HOST_EMU)
+				// The match child is the next pop of this lane and its interval is known here, a few hundred issue slots (the
+				// pushes below, at 3-5 lanes each) before the next trip asks for its occurrence blocks: start them now.
+				if (ci < 4 && ((V >> ci) & 1u)) {
+					const uint32_t pjk = occ_arg(ix, sel4(ci, nk) - 1u) >> 6, pjl = occ_arg(ix, sel4(ci, nl)) >> 6;
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(ix.blk + 2 * (size_t)pjl));
+					if (pjk != pjl) asm volatile("prefetch.global.L1 [%0];" :: "l"(ix.blk + 2 * (size_t)pjk));
+				}
+#endif
 				const int score = score_of(mm, go, ge);
 				const uint32_t ptag = e_tag; // plain node: no kind / base bits
 				if (allow_diff) {

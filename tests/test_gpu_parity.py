@@ -172,6 +172,7 @@ def test_resident_path_matches_flat(golden, gpu_index):
     (100, {}, {}),
     ((30, 50), dict(seed_len=1024, fnr=0.01, max_gapo=2), dict(adna=True, sub_rate=0.01)),
     ((15, 250), dict(max_gapo=2, max_gape=10), dict(n_rate=0.005)),
+    ((230, 400), {}, dict(sub_rate=0.01)),  # straddles 255 bases: longer reads skip pass 0 (its packed records hold 8-bit positions)
 ])
 def test_aln_matches_reference_live(gpu_index, length, optkw, simkw):
     T, idx = gpu_index

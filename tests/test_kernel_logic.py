@@ -103,6 +103,11 @@ def test_search_logic_matches_reference_live(small_index, emu_index):
     want = R.ref_aln(ridx, reads, opt, threads=4)
     got = R.emu_aln(h, reads, opt)
     assert R.compare_aln(want, got, "live") == []
+    # reads on both sides of 255 bases: pass 0's records pack positions into 8 bits, longer reads start in the next pass
+    reads = R.bwa.simulate.simulate_reads(T, 60, (240, 300), seed=99, sub_rate=0.01)
+    assert (np.diff(reads.offs) > 255).sum() > 10
+    opt = abi.default_gap_opt()
+    assert R.compare_aln(R.ref_aln(ridx, reads, opt, threads=4), R.emu_aln(h, reads, opt), "live long") == []
 
 
 # ---------------------------------------------------------------- k_search_warp (csrc/search_warp.cuh) on an emulated 32-lane warp

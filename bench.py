@@ -512,6 +512,11 @@ def main():
         except Exception as e:
             roofline["random_sector_probe_gb_s"] = {"error": str(e)[:200]}
         try:
+            # BASELINE.json's target for the occ lookup kernel: >= 50 % of the achievable random-sector throughput
+            roofline["own_sector_frac_of_probe"] = roofline["own_sector_gb_s"] / roofline["random_sector_probe_gb_s"]["2.3GB_buffer_chains4"]
+        except Exception:
+            pass
+        try:
             # what binds the kernel (profiles/r2_fetch_probe.md): the number of requests it sends to L2, not their bytes --
             # ncu's request counts per read x this launch's reads / its time, beside the request rate of the probe
             c4 = json.load(open(os.path.join(ROOT, "profiles", "k_search_traffic.json")))["c4"]

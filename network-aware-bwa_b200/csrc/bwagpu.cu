@@ -307,7 +307,10 @@ extern "C" int bwa_gpu_init(int n_devices, const int *device_ids)
 		CK(cudaSetDevice(id));
 		{
 			// The path is random 32-byte sector gathers: ask L2 to fetch from DRAM at sector granularity instead of the
-			// default 64 bytes (a hint; BWAGPU_L2_FETCH=64|128 restores / widens it for A/B runs)
+			// default 64 bytes (BWAGPU_L2_FETCH=64|128 restores / widens it for A/B runs).  A hint the B200 does not act on:
+			// the call succeeds and reads back as set, but a load that misses still fills the whole 128-byte line (3.9 DRAM
+			// sectors per random block at 32, 64 and 128 alike, profiles/r2_fetch_probe.md) -- what narrows the fill is the
+			// .L2::64B qualifier on the index loads themselves (fmindex.cuh)
 			const uint32_t gran = env_u32("BWAGPU_L2_FETCH", 32);
 			cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
 			cudaGetLastError();

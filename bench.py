@@ -474,6 +474,14 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
     roofline, aln_only = None, None
     if aln_reads is not None:
+        if parity is None or "error" in parity:
+            # the value region ended with a device reset and no parity run has set the device (and its index) up again
+            small = prefix_bam(bam, min(args.pairs, 20000))
+            saved = quiet_stderr(rank)
+            try:
+                host.run(prefix, small, small[:-4] + ".gpu_out.bam")
+            finally:
+                restore_stderr(saved)
         opt = bwa.abi.default_gap_opt()
         api.resident_stage(aln_reads.bases, aln_reads.offs, opt)
         api.set_stats(True)

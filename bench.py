@@ -563,6 +563,13 @@ def main():
                          "bound": "latency of lane 0's serial walk of each member's bit stream (one warp per member)"},
         "k3_search_in_job": {"kernel_ms_per_step": per_step["ms_search"], "pass_ms_per_step": [x / args.steps for x in tot["ms_search_pass"]]},
     }
+    try:
+        # K4 is a dependent random gather: 31 block loads + 1 SA read per query, against what the random-sector probe sustains
+        probe_g = roofline["random_sector_probe_gb_s"]["2.3GB_buffer_chains4"] / 32.0
+        other["k4_sa"]["requests_g_per_s"] = 32.0 * other["k4_sa"]["queries_per_s_kernel"] / 1e9
+        other["k4_sa"]["frac_of_random_sector_probe"] = other["k4_sa"]["requests_g_per_s"] / probe_g
+    except Exception:
+        pass
 
     # ---- cpu baseline (N = 1 only): the reference itself on a bounded prefix of the shard
     cpu_baseline = None
